@@ -1,0 +1,439 @@
+"""Host-side mirror of the reference's public API on top of the C ABI.
+
+Names, argument meaning and error behaviour follow rsruckig v2.1.2:
+`Ruckig::{new, reset, validate_input, calculate, update}` (ruckig.rs:110-321),
+`InputParameter` (input_parameter.rs:147-243), `OutputParameter`
+(output_parameter.rs:36-120), `Trajectory::{at_time, get_duration, ...}`
+(trajectory.rs:158-209), `RuckigResult` (result.rs:34-61), the two error
+handlers (error.rs:98-122) — plus the batched entry point `BatchRuckig`.
+
+Everything is computed by the CUDA library; this module only moves buffers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import enum
+
+import numpy as np
+
+from . import _cabi as cabi
+
+
+class ControlInterface(enum.IntEnum):  # input_parameter.rs:35-45
+    Position = 0
+    Velocity = 1
+    Acceleration = 2
+
+
+class Synchronization(enum.IntEnum):  # input_parameter.rs:72-85
+    Time = 0
+    TimeIfNecessary = 1
+    Phase = 2
+    None_ = 3
+
+
+class DurationDiscretization(enum.IntEnum):  # input_parameter.rs:110-117
+    Continuous = 0
+    Discrete = 1
+
+
+class RuckigResult(enum.IntEnum):  # result.rs:34-61
+    Working = 0
+    Finished = 1
+    Error = -1
+    ErrorInvalidInput = -100
+    ErrorTrajectoryDuration = -101
+    ErrorPositionalLimits = -102
+    ErrorZeroLimits = -104
+    ErrorExecutionTimeCalculation = -110
+    ErrorSynchronizationCalculation = -111
+
+
+class ReachedLimits(enum.IntEnum):  # profile.rs:25-34
+    Acc0Acc1Vel = 0
+    Vel = 1
+    Acc0 = 2
+    Acc1 = 3
+    Acc0Acc1 = 4
+    Acc0Vel = 5
+    Acc1Vel = 6
+    None_ = 7
+
+
+class Direction(enum.IntEnum):  # profile.rs:37-41
+    UP = 0
+    DOWN = 1
+
+
+class ControlSigns(enum.IntEnum):  # profile.rs:44-49
+    UDDU = 0
+    UDUD = 1
+
+
+class RuckigError(Exception):  # error.rs:15-34
+    pass
+
+
+class ValidationError(RuckigError):
+    pass
+
+
+class CalculatorError(RuckigError):
+    pass
+
+
+class ThrowErrorHandler:  # error.rs:101-111
+    throws = True
+
+
+class IgnoreErrorHandler:  # error.rs:113-122
+    throws = False
+
+
+_CALC_MESSAGES = {
+    RuckigResult.ErrorZeroLimits: "zero limits conflict",
+    RuckigResult.ErrorExecutionTimeCalculation: "error in step 1 / step 2",
+    RuckigResult.ErrorSynchronizationCalculation: "error in time synchronization",
+}
+
+
+class InputParameter:
+    """input_parameter.rs:147-243 (same defaults: max_acceleration = max_jerk = +inf, all DoFs enabled)."""
+
+    _ARRAYS = ("current_position", "current_velocity", "current_acceleration", "target_position", "target_velocity",
+               "target_acceleration", "max_velocity", "max_acceleration", "max_jerk")
+
+    def __init__(self, dofs: int):
+        self.degrees_of_freedom = int(dofs)
+        self.control_interface = ControlInterface.Position
+        self.synchronization = Synchronization.Time
+        self.duration_discretization = DurationDiscretization.Continuous
+        z = lambda v=0.0: np.full(dofs, v, dtype=np.float64)
+        self.current_position, self.current_velocity, self.current_acceleration = z(), z(), z()
+        self.target_position, self.target_velocity, self.target_acceleration = z(), z(), z()
+        self.max_velocity, self.max_acceleration, self.max_jerk = z(), z(np.inf), z(np.inf)
+        self.min_velocity = None
+        self.min_acceleration = None
+        self.enabled = np.ones(dofs, dtype=bool)
+        self.per_dof_control_interface = None
+        self.per_dof_synchronization = None
+        self.minimum_duration = None
+        self.interrupt_calculation_duration = None
+
+    def _key(self):
+        opt = lambda a: None if a is None else tuple(np.asarray(a, dtype=np.float64).tolist())
+        opti = lambda a: None if a is None else tuple(int(x) for x in a)
+        return (tuple(tuple(np.asarray(getattr(self, f), dtype=np.float64).tolist()) for f in self._ARRAYS),
+                tuple(bool(x) for x in self.enabled), self.minimum_duration, opt(self.min_velocity), opt(self.min_acceleration),
+                int(self.control_interface), int(self.synchronization), int(self.duration_discretization),
+                opti(self.per_dof_control_interface), opti(self.per_dof_synchronization))
+
+    def __eq__(self, other):  # input_parameter.rs:190-211
+        return isinstance(other, InputParameter) and self._key() == other._key()
+
+    def copy(self) -> "InputParameter":
+        o = InputParameter(self.degrees_of_freedom)
+        for f in self._ARRAYS:
+            setattr(o, f, np.array(getattr(self, f), dtype=np.float64))
+        o.enabled = np.array(self.enabled, dtype=bool)
+        for f in ("min_velocity", "min_acceleration"):
+            v = getattr(self, f)
+            setattr(o, f, None if v is None else np.array(v, dtype=np.float64))
+        for f in ("per_dof_control_interface", "per_dof_synchronization"):
+            v = getattr(self, f)
+            setattr(o, f, None if v is None else list(v))
+        o.control_interface, o.synchronization = self.control_interface, self.synchronization
+        o.duration_discretization, o.minimum_duration = self.duration_discretization, self.minimum_duration
+        return o
+
+    # -- n = 1 view for the C ABI ------------------------------------------------------------
+    def as_batch(self, delta_time: float, error_mode: int):
+        """(desc, rk_batch_in, keepalive) describing this single problem as a batch of one."""
+        D = self.degrees_of_freedom
+        keep = []
+        fields = {}
+        for f in self._ARRAYS:
+            a = np.ascontiguousarray(np.asarray(getattr(self, f), dtype=np.float64).reshape(D))
+            keep.append(a)
+            fields[f] = a
+        for f in ("min_velocity", "min_acceleration"):
+            v = getattr(self, f)
+            if v is not None:
+                a = np.ascontiguousarray(np.asarray(v, dtype=np.float64).reshape(D))
+                keep.append(a)
+                fields[f] = a
+        en = np.ascontiguousarray(np.asarray(self.enabled, dtype=np.uint8).reshape(D))
+        keep.append(en)
+        fields["enabled"] = en
+        if self.minimum_duration is not None:
+            md = np.array([float(self.minimum_duration)], dtype=np.float64)
+            keep.append(md)
+            fields["minimum_duration"] = md
+        desc, k2 = cabi.make_desc(1, D, control_interface=self.control_interface, synchronization=self.synchronization,
+                                  duration_discretization=self.duration_discretization, error_mode=error_mode,
+                                  memory_space=cabi.RK_MEM_HOST, delta_time=delta_time,
+                                  per_dof_control_interface=self.per_dof_control_interface,
+                                  per_dof_synchronization=self.per_dof_synchronization)
+        keep += k2
+        return desc, cabi.make_in(fields), keep
+
+
+class Profile:
+    """Host copy of one DoF's Profile (profile.rs:76-118)."""
+
+    def __init__(self):
+        self.t = np.zeros(7); self.t_sum = np.zeros(7); self.j = np.zeros(7)
+        self.a = np.zeros(8); self.v = np.zeros(8); self.p = np.zeros(8)
+        self.brake_duration = 0.0
+        self.brake_t = np.zeros(2)
+        self.limits = ReachedLimits.None_
+        self.direction = Direction.UP
+        self.control_signs = ControlSigns.UDDU
+
+
+class Trajectory:
+    """trajectory.rs:14-21. The profiles live on the GPU (an rk_trajectories of one); fields are read on demand."""
+
+    def __init__(self, dofs: int):
+        self.degrees_of_freedom = int(dofs)
+        self.duration = 0.0
+        self.independent_min_durations = np.zeros(dofs)
+        self._engine = None  # set by Ruckig.calculate
+        self._dev = None
+
+    def get_duration(self) -> float:  # trajectory.rs:197-199
+        return self.duration
+
+    def get_independent_min_durations(self):  # trajectory.rs:207-209
+        return self.independent_min_durations
+
+    def get_profiles(self):  # trajectory.rs:192-194: one section of `dof` profiles
+        assert self._dev is not None, "calculate() has not filled this trajectory"
+        eng, D = self._engine, self.degrees_of_freedom
+        rd = lambda f: eng.read(self._dev, f, 1, D)
+        t, ts, j, a, v, p = (rd(f) for f in (cabi.RK_FIELD_T, cabi.RK_FIELD_T_SUM, cabi.RK_FIELD_J, cabi.RK_FIELD_A,
+                                             cabi.RK_FIELD_V, cabi.RK_FIELD_P))
+        bd, bt, codes = rd(cabi.RK_FIELD_BRAKE_DURATION), rd(cabi.RK_FIELD_BRAKE_T), rd(cabi.RK_FIELD_CODES)
+        out = []
+        for d in range(D):
+            q = Profile()
+            q.t, q.t_sum, q.j = t[:, d, 0].copy(), ts[:, d, 0].copy(), j[:, d, 0].copy()
+            q.a, q.v, q.p = a[:, d, 0].copy(), v[:, d, 0].copy(), p[:, d, 0].copy()
+            q.brake_duration, q.brake_t = float(bd[0, d, 0]), bt[:, d, 0].copy()
+            c = int(codes[d, 0])
+            q.limits, q.control_signs, q.direction = ReachedLimits(c & 0xFF), ControlSigns((c >> 8) & 0xFF), Direction((c >> 16) & 0xFF)
+            out.append(q)
+        return [out]
+
+    def at_time(self, time: float):
+        """Trajectory::at_time (trajectory.rs:158-189): returns (position, velocity, acceleration, jerk, section)."""
+        assert self._dev is not None, "calculate() has not filled this trajectory"
+        return self._engine.at_time(self._dev, self.degrees_of_freedom, time)
+
+
+class OutputParameter:
+    """output_parameter.rs:36-61."""
+
+    def __init__(self, dofs: int):
+        self.degrees_of_freedom = int(dofs)
+        self.trajectory = Trajectory(dofs)
+        self.new_position = np.zeros(dofs)
+        self.new_velocity = np.zeros(dofs)
+        self.new_acceleration = np.zeros(dofs)
+        self.new_jerk = np.zeros(dofs)
+        self.time = 0.0
+        self.new_section = 0
+        self.did_section_change = False
+        self.new_calculation = False
+        self.was_calculation_interrupted = False
+        self.calculation_duration = 0.0
+
+    def pass_to_input(self, input: InputParameter):  # output_parameter.rs:110-120
+        input.current_position = self.new_position.copy()
+        input.current_velocity = self.new_velocity.copy()
+        input.current_acceleration = self.new_acceleration.copy()
+
+
+class _Engine:
+    """One rk_handle per process/device, shared by the n = 1 façade objects."""
+
+    _instances: dict = {}
+
+    @classmethod
+    def get(cls, device: int = 0) -> "_Engine":
+        if device not in cls._instances:
+            cls._instances[device] = _Engine(device)
+        return cls._instances[device]
+
+    def __init__(self, device: int):
+        self.lib = cabi.load()
+        self.h = C.c_void_p()
+        cabi.check(self.lib.rk_create(device, C.byref(self.h)))
+        self.device = device
+
+    def new_trajectories(self, n: int, dof: int) -> C.c_void_p:
+        t = C.c_void_p()
+        cabi.check(self.lib.rk_trajectories_create(self.h, n, dof, C.byref(t)))
+        return t
+
+    def free_trajectories(self, t):
+        if t is not None and self.lib is not None:
+            self.lib.rk_trajectories_destroy(t)
+
+    def read(self, traj, field: int, n: int, dof: int) -> np.ndarray:
+        if field in (cabi.RK_FIELD_STATUS, cabi.RK_FIELD_LIMITING_DOF):
+            out = np.empty(n, dtype=np.int32)
+        elif field == cabi.RK_FIELD_DURATION:
+            out = np.empty(n, dtype=np.float64)
+        elif field == cabi.RK_FIELD_INDEPENDENT_MIN_DURATIONS:
+            out = np.empty((dof, n), dtype=np.float64)
+        elif field == cabi.RK_FIELD_CODES:
+            out = np.empty((dof, n), dtype=np.uint32)
+        else:
+            out = np.empty((cabi.FIELD_SLOTS[field], dof, n), dtype=np.float64)
+        cabi.check(self.lib.rk_trajectories_read(self.h, traj, field, out.ctypes.data, cabi.RK_MEM_HOST))
+        return out
+
+    def at_time(self, traj, dof: int, time: float):
+        # time_start + delta_time with delta_time = 0 would give K identical samples; one sample at `time`
+        # is "time_start = time, then add 0.0": the kernel adds delta_time once before the first sample.
+        sd = cabi.RkSampleDesc(float(time), 0.0, 1, cabi.RK_MEM_HOST)
+        pos, vel, acc, jerk = (np.empty((1, dof, 1)) for _ in range(4))
+        sec = np.empty((1, 1), dtype=np.int32)
+        so = cabi.RkSampleOut(pos.ctypes.data, vel.ctypes.data, acc.ctypes.data, jerk.ctypes.data, sec.ctypes.data)
+        cabi.check(self.lib.rk_at_time_batch(self.h, traj, C.byref(sd), C.byref(so)))
+        return pos[0, :, 0].copy(), vel[0, :, 0].copy(), acc[0, :, 0].copy(), jerk[0, :, 0].copy(), int(sec[0, 0])
+
+
+class Ruckig:
+    """ruckig.rs:76-321 for a single problem; every calculation runs on the GPU as a batch of one."""
+
+    def __init__(self, dofs: int, delta_time: float, error_handler=ThrowErrorHandler, device: int = 0):
+        self.degrees_of_freedom = int(dofs)
+        self.delta_time = float(delta_time)
+        self.error_handler = error_handler
+        self.current_input = InputParameter(dofs)
+        self.current_input_initialized = False
+        self._engine = _Engine.get(device)
+
+    def reset(self):  # ruckig.rs:125-127
+        self.current_input_initialized = False
+
+    def validate_input(self, input: InputParameter, check_current_state_within_limits: bool,
+                       check_target_state_within_limits: bool) -> bool:
+        """ruckig.rs:150-171. Raises ValidationError under ThrowErrorHandler; returns validity otherwise."""
+        desc, bin_, keep = input.as_batch(self.delta_time, cabi.RK_ERRORS_THROW)
+        valid = np.zeros(1, dtype=np.uint8)
+        cabi.check(self._engine.lib.rk_validate_batch(self._engine.h, C.byref(desc), C.byref(bin_),
+                                                      int(check_current_state_within_limits),
+                                                      int(check_target_state_within_limits), valid.ctypes.data))
+        if not valid[0] and self.error_handler.throws:
+            raise ValidationError("input does not pass InputParameter::validate")
+        return bool(valid[0])
+
+    def calculate(self, input: InputParameter, traj: Trajectory) -> RuckigResult:
+        """ruckig.rs:210-218."""
+        eng = self._engine
+        throws = self.error_handler.throws
+        desc, bin_, keep = input.as_batch(self.delta_time, cabi.RK_ERRORS_THROW if throws else cabi.RK_ERRORS_IGNORE)
+        if traj._dev is None or traj._engine is not eng:
+            traj._engine = eng
+            traj._dev = eng.new_trajectories(1, self.degrees_of_freedom)
+        status = np.zeros(1, dtype=np.int32)
+        duration = np.zeros(1)
+        imd = np.zeros((self.degrees_of_freedom, 1))
+        out = cabi.RkBatchOut(status.ctypes.data, duration.ctypes.data, imd.ctypes.data)
+        cabi.check(eng.lib.rk_calculate_batch(eng.h, C.byref(desc), C.byref(bin_), traj._dev, C.byref(out)))
+        code = RuckigResult(int(status[0]))
+        if throws and code == RuckigResult.ErrorInvalidInput:
+            raise ValidationError("input does not pass InputParameter::validate")
+        traj.duration = float(duration[0])
+        traj.independent_min_durations = imd[:, 0].copy()
+        if throws and code in _CALC_MESSAGES:
+            raise CalculatorError(_CALC_MESSAGES[code])
+        return code
+
+    def update(self, input: InputParameter, output: OutputParameter) -> RuckigResult:
+        """ruckig.rs:266-321 (output.time is not reset on a new calculation, as in the reference)."""
+        output.new_calculation = False
+        if not self.current_input_initialized or input != self.current_input:
+            self.calculate(input, output.trajectory)  # Ok(Error*) codes are dropped, ruckig.rs:285
+            output.new_calculation = True
+            self.current_input = input.copy()
+            self.current_input_initialized = True
+
+        output.time += self.delta_time
+        p, v, a, j, _section = output.trajectory.at_time(output.time)
+        output.new_position, output.new_velocity, output.new_acceleration, output.new_jerk = p, v, a, j
+        output.did_section_change = False  # ruckig.rs:300-302: new_section is passed by value
+        output.pass_to_input(self.current_input)
+        if output.time > output.trajectory.get_duration():
+            return RuckigResult.Finished
+        return RuckigResult.Working
+
+
+class BatchRuckig:
+    """The batched entry point: Ruckig::calculate / Trajectory::at_time for n independent problems.
+
+    Arrays are SoA `[dof][n]` float64 (numpy = host buffers, torch CUDA tensors = device buffers).
+    """
+
+    def __init__(self, dofs: int, delta_time: float, error_handler=ThrowErrorHandler, device: int = 0):
+        self.degrees_of_freedom = int(dofs)
+        self.delta_time = float(delta_time)
+        self.error_handler = error_handler
+        self._engine = _Engine.get(device)
+        self._traj = None
+        self._n = 0
+
+    @property
+    def handle(self):
+        return self._engine.h
+
+    def _ensure(self, n: int):
+        if self._traj is None or self._n != n:
+            if self._traj is not None:
+                self._engine.free_trajectories(self._traj)
+            self._traj = self._engine.new_trajectories(n, self.degrees_of_freedom)
+            self._n = n
+
+    def calculate(self, fields: dict, *, n: int, memory_space: int, control_interface=ControlInterface.Position,
+                  synchronization=Synchronization.Time, duration_discretization=DurationDiscretization.Continuous,
+                  per_dof_control_interface=None, per_dof_synchronization=None, status=None, duration=None,
+                  independent_min_durations=None):
+        """fields: name -> buffer for the rk_batch_in members. Outputs (optional) are caller-owned buffers."""
+        self._ensure(n)
+        desc, keep = cabi.make_desc(n, self.degrees_of_freedom, control_interface=control_interface,
+                                    synchronization=synchronization, duration_discretization=duration_discretization,
+                                    error_mode=cabi.RK_ERRORS_THROW if self.error_handler.throws else cabi.RK_ERRORS_IGNORE,
+                                    memory_space=memory_space, delta_time=self.delta_time,
+                                    per_dof_control_interface=per_dof_control_interface,
+                                    per_dof_synchronization=per_dof_synchronization)
+        bin_ = cabi.make_in(fields)
+        out = cabi.RkBatchOut(cabi.ptr(status), cabi.ptr(duration), cabi.ptr(independent_min_durations))
+        eng = self._engine
+        cabi.check(eng.lib.rk_calculate_batch(eng.h, C.byref(desc), C.byref(bin_), self._traj, C.byref(out)))
+
+    def validate(self, fields: dict, *, n: int, check_current: bool, check_target: bool, **kw) -> np.ndarray:
+        desc, keep = cabi.make_desc(n, self.degrees_of_freedom, memory_space=cabi.RK_MEM_HOST, delta_time=self.delta_time, **kw)
+        bin_ = cabi.make_in(fields)
+        valid = np.zeros(n, dtype=np.uint8)
+        eng = self._engine
+        cabi.check(eng.lib.rk_validate_batch(eng.h, C.byref(desc), C.byref(bin_), int(check_current), int(check_target), valid.ctypes.data))
+        return valid
+
+    def read(self, field: int) -> np.ndarray:
+        return self._engine.read(self._traj, field, self._n, self.degrees_of_freedom)
+
+    def at_time(self, *, time_start: float, delta_time: float, steps: int, memory_space: int, position=None,
+                velocity=None, acceleration=None, jerk=None, section=None):
+        sd = cabi.RkSampleDesc(float(time_start), float(delta_time), int(steps), int(memory_space))
+        so = cabi.RkSampleOut(cabi.ptr(position), cabi.ptr(velocity), cabi.ptr(acceleration), cabi.ptr(jerk), cabi.ptr(section))
+        eng = self._engine
+        cabi.check(eng.lib.rk_at_time_batch(eng.h, self._traj, C.byref(sd), C.byref(so)))
+
+    def sync(self):
+        cabi.check(self._engine.lib.rk_sync(self._engine.h))
+
+    def kernel_launches(self) -> int:
+        return int(self._engine.lib.rk_kernel_launches(self._engine.h))
