@@ -137,6 +137,9 @@ enum {
     RK_FIELD_BRAKE_V,                   /* f64 [2][dof][n] */
     RK_FIELD_BRAKE_P,                   /* f64 [2][dof][n] */
     RK_FIELD_PF_VF_AF,                  /* f64 [3][dof][n]  Profile::pf, vf, af */
+    RK_FIELD_ERROR_DETAIL,              /* int32 [n]: for error statuses (stage << 8) | dof; stage 1 = Step 1,
+                                           2 = synchronisation, 3 = Step 2 (the texts of calculator_target.rs:459-470,
+                                           :509-517, :820-825 are rebuilt from it on the host); 0 otherwise */
     RK_FIELD_COUNT
 };
 /* `source` byte of RK_FIELD_CODES: which stage produced the final profile. */
@@ -176,10 +179,20 @@ rk_status rk_calculate_batch(rk_handle* h, const rk_batch_desc* desc, const rk_b
                              rk_trajectories* traj, const rk_batch_out* out);
 
 /* Ruckig::validate_input(input, check_current, check_target) (ruckig.rs:150-171,
- * input_parameter.rs:251-420): valid[i] = 1 if trajectory i passes. */
+ * input_parameter.rs:251-420): valid[i] = 1 if trajectory i passes. reason[i] (may be NULL) = 0 if valid, else
+ * (check_id << 8) | dof of the FIRST failing check in the reference's order; check ids are RK_INVALID_* below. */
 rk_status rk_validate_batch(rk_handle* h, const rk_batch_desc* desc, const rk_batch_in* in,
                             int32_t check_current_state_within_limits, int32_t check_target_state_within_limits,
-                            uint8_t* valid);
+                            uint8_t* valid, int32_t* reason);
+enum {
+    RK_INVALID_MAX_JERK = 1, RK_INVALID_MAX_ACCELERATION, RK_INVALID_MIN_ACCELERATION, RK_INVALID_CURRENT_ACCELERATION_NAN,
+    RK_INVALID_TARGET_ACCELERATION_NAN, RK_INVALID_CURRENT_ACCELERATION_ABOVE, RK_INVALID_CURRENT_ACCELERATION_BELOW,
+    RK_INVALID_TARGET_ACCELERATION_ABOVE, RK_INVALID_TARGET_ACCELERATION_BELOW, RK_INVALID_CURRENT_VELOCITY_NAN,
+    RK_INVALID_TARGET_VELOCITY_NAN, RK_INVALID_CURRENT_POSITION_NAN, RK_INVALID_TARGET_POSITION_NAN, RK_INVALID_MAX_VELOCITY,
+    RK_INVALID_MIN_VELOCITY, RK_INVALID_CURRENT_VELOCITY_ABOVE, RK_INVALID_CURRENT_VELOCITY_BELOW, RK_INVALID_TARGET_VELOCITY_ABOVE,
+    RK_INVALID_TARGET_VELOCITY_BELOW, RK_INVALID_CURRENT_WILL_EXCEED, RK_INVALID_CURRENT_WILL_UNDERCUT, RK_INVALID_TARGET_WILL_EXCEED,
+    RK_INVALID_TARGET_WILL_UNDERCUT, RK_INVALID_DELTA_TIME
+};
 
 /* Trajectory::at_time for every trajectory and K sample times (trajectory.rs:158-189). */
 rk_status rk_at_time_batch(rk_handle* h, const rk_trajectories* traj, const rk_sample_desc* desc, const rk_sample_out* out);

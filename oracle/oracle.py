@@ -175,7 +175,9 @@ class OracleRuckig:
     def update(self, input: InputParameter, output: OutputParameter):
         self._bind(output)
         self._set(input)
-        r = self._result(self.lib.rko_otg_update(self.h))
+        code = self.lib.rko_otg_update(self.h)
+        output.new_calculation = bool(self.lib.rko_otg_new_calculation(self.h))
+        r = self._result(code)
         D = self.degrees_of_freedom
         for which, name in enumerate(("new_position", "new_velocity", "new_acceleration", "new_jerk")):
             buf = np.zeros(D)

@@ -22,7 +22,7 @@ RK_MAX_DOF = 64
 (RK_FIELD_STATUS, RK_FIELD_DURATION, RK_FIELD_INDEPENDENT_MIN_DURATIONS, RK_FIELD_LIMITING_DOF, RK_FIELD_CODES,
  RK_FIELD_T, RK_FIELD_T_SUM, RK_FIELD_J, RK_FIELD_A, RK_FIELD_V, RK_FIELD_P, RK_FIELD_BRAKE_DURATION,
  RK_FIELD_BRAKE_T, RK_FIELD_BRAKE_J, RK_FIELD_BRAKE_A, RK_FIELD_BRAKE_V, RK_FIELD_BRAKE_P, RK_FIELD_PF_VF_AF,
- RK_FIELD_COUNT) = range(19)
+ RK_FIELD_ERROR_DETAIL, RK_FIELD_COUNT) = range(20)
 
 # slots per (dof, trajectory) of each profile field; 0 = per-trajectory field
 FIELD_SLOTS = {
@@ -139,7 +139,7 @@ def load():
     lib.rk_trajectories_create.argtypes = [vp, C.c_int64, C.c_int32, C.POINTER(vp)]
     lib.rk_trajectories_destroy.argtypes = [vp]
     lib.rk_calculate_batch.argtypes = [vp, C.POINTER(RkBatchDesc), C.POINTER(RkBatchIn), vp, C.POINTER(RkBatchOut)]
-    lib.rk_validate_batch.argtypes = [vp, C.POINTER(RkBatchDesc), C.POINTER(RkBatchIn), C.c_int32, C.c_int32, vp]
+    lib.rk_validate_batch.argtypes = [vp, C.POINTER(RkBatchDesc), C.POINTER(RkBatchIn), C.c_int32, C.c_int32, vp, vp]
     lib.rk_at_time_batch.argtypes = [vp, vp, C.POINTER(RkSampleDesc), C.POINTER(RkSampleOut)]
     lib.rk_trajectories_read.argtypes = [vp, vp, C.c_int32, vp, C.c_int32]
     lib.rk_sync.argtypes = [vp]

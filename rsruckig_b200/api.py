@@ -90,11 +90,50 @@ class IgnoreErrorHandler:  # error.rs:113-122
     throws = False
 
 
-_CALC_MESSAGES = {
-    RuckigResult.ErrorZeroLimits: "zero limits conflict",
-    RuckigResult.ErrorExecutionTimeCalculation: "error in step 1 / step 2",
-    RuckigResult.ErrorSynchronizationCalculation: "error in time synchronization",
+_CALC_CODES = (RuckigResult.ErrorZeroLimits, RuckigResult.ErrorExecutionTimeCalculation, RuckigResult.ErrorSynchronizationCalculation)
+
+# texts of InputParameter::validate (input_parameter.rs:251-420), keyed by the RK_INVALID_* check id the GPU reports
+_VALIDATION_MESSAGES = {
+    1: "Maximum jerk limit of DoF {dof} should be larger than or equal to zero.",
+    2: "maximum acceleration limit of DoF {dof} should be larger than or equal to zero.",
+    3: "minimum acceleration limit of DoF {dof} should be smaller than or equal to zero.",
+    4: "current acceleration of DoF {dof} should be a valid number.",
+    5: "target acceleration of DoF {dof} should be a valid number.",
+    6: "current acceleration of DoF {dof} exceeds its maximum acceleration limit.",
+    7: "current acceleration of DoF {dof} undercuts its minimum acceleration limit.",
+    8: "target acceleration of DoF {dof} exceeds its maximum acceleration limit.",
+    9: "target acceleration of DoF {dof} undercuts its minimum acceleration limit.",
+    10: "current velocity of DoF {dof} should be a valid number.",
+    11: "target velocity of DoF {dof} should be a valid number.",
+    12: "current position of DoF {dof} should be a valid number.",
+    13: "target position of DoF {dof} should be a valid number.",
+    14: "maximum velocity limit of DoF {dof} should be larger than or equal to zero.",
+    15: "minimum velocity limit of DoF {dof} should be smaller than or equal to zero.",
+    16: "current velocity of DoF {dof} exceeds its maximum velocity limit.",
+    17: "current velocity of DoF {dof} undercuts its minimum velocity limit.",
+    18: "target velocity of DoF {dof} exceeds its maximum velocity limit.",
+    19: "target velocity of DoF {dof} undercuts its minimum velocity limit.",
+    20: "DoF {dof} will inevitably reach a velocity from the current kinematic state that will exceed its maximum velocity limit.",
+    21: "DoF {dof} will inevitably reach a velocity from the current kinematic state that will undercut its minimum velocity limit.",
+    22: "DoF {dof} will inevitably have reached a velocity from the target kinematic state that will exceed its maximum velocity limit.",
+    23: "DoF {dof} will inevitably have reached a velocity from the target kinematic state that will undercut its minimum velocity limit.",
+    24: "delta time (control rate) parameter should be larger than zero.",
 }
+
+
+def validation_message(reason: int) -> str:
+    return _VALIDATION_MESSAGES.get(reason >> 8, "invalid input").format(dof=reason & 0xFF)
+
+
+def calculator_message(code: int, detail: int) -> str:
+    """Texts of calculator_target.rs:459-470, :509-517, :820-825 rebuilt from the status and the error-detail word."""
+    stage, dof = detail >> 8, detail & 0xFF
+    if stage == 1:
+        return (f"zero limits conflict in step 1, dof: {dof}" if code == RuckigResult.ErrorZeroLimits else f"error in step 1, dof: {dof}")
+    if stage == 2:
+        return ("zero limits conflict with other degrees of freedom in time synchronization" if code == RuckigResult.ErrorZeroLimits
+                else "error in time synchronization")
+    return f"error in step 2, dof: {dof}"
 
 
 class InputParameter:
@@ -281,7 +320,7 @@ class _Engine:
             self.lib.rk_trajectories_destroy(t)
 
     def read(self, traj, field: int, n: int, dof: int) -> np.ndarray:
-        if field in (cabi.RK_FIELD_STATUS, cabi.RK_FIELD_LIMITING_DOF):
+        if field in (cabi.RK_FIELD_STATUS, cabi.RK_FIELD_LIMITING_DOF, cabi.RK_FIELD_ERROR_DETAIL):
             out = np.empty(n, dtype=np.int32)
         elif field == cabi.RK_FIELD_DURATION:
             out = np.empty(n, dtype=np.float64)
@@ -324,11 +363,12 @@ class Ruckig:
         """ruckig.rs:150-171. Raises ValidationError under ThrowErrorHandler; returns validity otherwise."""
         desc, bin_, keep = input.as_batch(self.delta_time, cabi.RK_ERRORS_THROW)
         valid = np.zeros(1, dtype=np.uint8)
+        reason = np.zeros(1, dtype=np.int32)
         cabi.check(self._engine.lib.rk_validate_batch(self._engine.h, C.byref(desc), C.byref(bin_),
                                                       int(check_current_state_within_limits),
-                                                      int(check_target_state_within_limits), valid.ctypes.data))
+                                                      int(check_target_state_within_limits), valid.ctypes.data, reason.ctypes.data))
         if not valid[0] and self.error_handler.throws:
-            raise ValidationError("input does not pass InputParameter::validate")
+            raise ValidationError(validation_message(int(reason[0])))
         return bool(valid[0])
 
     def calculate(self, input: InputParameter, traj: Trajectory) -> RuckigResult:
@@ -346,11 +386,13 @@ class Ruckig:
         cabi.check(eng.lib.rk_calculate_batch(eng.h, C.byref(desc), C.byref(bin_), traj._dev, C.byref(out)))
         code = RuckigResult(int(status[0]))
         if throws and code == RuckigResult.ErrorInvalidInput:
-            raise ValidationError("input does not pass InputParameter::validate")
+            detail = int(eng.read(traj._dev, cabi.RK_FIELD_ERROR_DETAIL, 1, self.degrees_of_freedom)[0])
+            raise ValidationError(validation_message(detail))
         traj.duration = float(duration[0])
         traj.independent_min_durations = imd[:, 0].copy()
-        if throws and code in _CALC_MESSAGES:
-            raise CalculatorError(_CALC_MESSAGES[code])
+        if throws and code in _CALC_CODES:
+            detail = int(eng.read(traj._dev, cabi.RK_FIELD_ERROR_DETAIL, 1, self.degrees_of_freedom)[0])
+            raise CalculatorError(calculator_message(code, detail))
         return code
 
     def update(self, input: InputParameter, output: OutputParameter) -> RuckigResult:
@@ -418,9 +460,11 @@ class BatchRuckig:
         desc, keep = cabi.make_desc(n, self.degrees_of_freedom, memory_space=cabi.RK_MEM_HOST, delta_time=self.delta_time, **kw)
         bin_ = cabi.make_in(fields)
         valid = np.zeros(n, dtype=np.uint8)
+        reason = np.zeros(n, dtype=np.int32)
         eng = self._engine
-        cabi.check(eng.lib.rk_validate_batch(eng.h, C.byref(desc), C.byref(bin_), int(check_current), int(check_target), valid.ctypes.data))
-        return valid
+        cabi.check(eng.lib.rk_validate_batch(eng.h, C.byref(desc), C.byref(bin_), int(check_current), int(check_target),
+                                             valid.ctypes.data, reason.ctypes.data))
+        return valid, reason
 
     def read(self, field: int) -> np.ndarray:
         return self._engine.read(self._traj, field, self._n, self.degrees_of_freedom)

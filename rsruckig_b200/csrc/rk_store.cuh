@@ -1,0 +1,125 @@
+// rk_store.cuh — HBM layout of the batch and the routines that expand a compact
+// candidate (t[7] + control value + codes) into the full Profile arrays the
+// reference keeps (profile.rs:76-118), bit-identical to what its check*
+// functions leave behind.
+//
+// Layout: everything is structure-of-arrays with the trajectory index fastest.
+//   profile field slot s of DoF d, trajectory i : prof[(s * dof + d) * n + i]
+//   slots: T 0..6 | T_SUM 7..13 | J 14..20 | A 21..28 | V 29..36 | P 37..44 |
+//          BRAKE_DURATION 45 | BRAKE_T 46,47 | BRAKE_J 48,49 | BRAKE_A 50,51 |
+//          BRAKE_V 52,53 | BRAKE_P 54,55 | PF,VF,AF 56..58           (59 slots)
+// A warp handles 32 consecutive trajectories of one DoF, so every load and
+// store below is a fully coalesced 256-byte row.
+#pragma once
+#include "rk_step1.cuh"
+
+namespace rk {
+
+enum : int { S_T = 0, S_TSUM = 7, S_J = 14, S_A = 21, S_V = 29, S_P = 37, S_BRAKE_DUR = 45, S_BRAKE_T = 46, S_BRAKE_J = 48, S_BRAKE_A = 50,
+             S_BRAKE_V = 52, S_BRAKE_P = 54, S_PF = 56, S_VF = 57, S_AF = 58, PROFILE_SLOTS = 59 };
+
+// Which reference solver family an item belongs to (calculator_target.rs:389-452).
+enum : int { K_POS3 = 0, K_POS2 = 1, K_POS1 = 2, K_VEL3 = 3, K_VEL2 = 4, K_NONE = 5 };
+
+// Scratch written by the Step-1 kernel (ws doubles, slot-major like the profiles).
+enum : int { W_P0 = 0, W_V0 = 1, W_A0 = 2, W_TMIN = 3, W_ALEFT = 4, W_ARIGHT = 5, W_BLEFT = 6, W_BRIGHT = 7, W_CAND = 8, W_CAND_STRIDE = 9,
+             W_BRAKE_DUR = 35, WS_SLOTS = 36 };
+// meta word bits
+enum : uint32_t { M_KIND_MASK = 0xFu, M_FOUND = 1u << 4, M_HAS_A = 1u << 5, M_HAS_B = 1u << 6, M_ZERO_LIMITS = 1u << 8, M_ENABLED = 1u << 9,
+                  M_VCODE_SHIFT = 16 };
+
+struct ProfileSink {
+    double* prof;  // base of the trajectory storage
+    int64_t stride;  // dof * n
+    int64_t idx;     // d * n + i
+    __device__ __forceinline__ void put(int slot, double v) const { prof[(int64_t)slot * stride + idx] = v; }
+};
+
+__device__ __forceinline__ uint32_t pack_codes(int lim, int cs, int dir, int src) {
+    return (uint32_t)lim | ((uint32_t)cs << 8) | ((uint32_t)dir << 16) | ((uint32_t)src << 24);
+}
+
+// Expand and store one profile. `lim_check` is the limits value the reference passed to its check function (it decides
+// whether a[3] is forced to zero); the label stored in the codes may differ after phase synchronisation (Q25).
+// Returns p[7] (the velocity-interface / second-order Step 2 sets pf = p[7] afterwards).
+__device__ __forceinline__ double store_profile(const ProfileSink& o, int kind, const double (&t)[7], double ctrl, double ctrl2, int cs, int lim_check,
+                                                double p0, double v0, double a0, double vf, double af) {
+    double ts[7], j[7], a[8], v[8], p[8];
+    a[0] = a0; v[0] = v0; p[0] = p0;
+    if (kind == K_POS3 || kind == K_VEL3) {
+        ts[0] = t[0];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) ts[i + 1] = ts[i] + t[i + 1];
+        if (kind == K_POS3) {
+            jerk_pattern_pos(t, cs, ctrl, j);
+        } else {  // profile.rs:146-170
+            j[0] = (t[0] > 0.0) ? ctrl : 0.0; j[1] = 0.0; j[2] = (t[2] > 0.0) ? -ctrl : 0.0; j[3] = 0.0; j[5] = 0.0;
+            if (cs == UDDU) { j[4] = (t[4] > 0.0) ? -ctrl : 0.0; j[6] = (t[6] > 0.0) ? ctrl : 0.0; }
+            else { j[4] = (t[4] > 0.0) ? ctrl : 0.0; j[6] = (t[6] > 0.0) ? ctrl : 0.0; }
+        }
+        const bool zero_a3 = (kind == K_POS3) && forces_a3_zero(lim_check);
+#pragma unroll
+        for (int i = 0; i < 7; ++i) {
+            a[i + 1] = a[i] + t[i] * j[i];
+            v[i + 1] = v[i] + t[i] * (a[i] + t[i] * j[i] / 2.0);
+            p[i + 1] = p[i] + t[i] * (v[i] + t[i] * (a[i] / 2.0 + t[i] * j[i] / 6.0));
+            if (i == 2 && zero_a3) a[3] = 0.0;
+        }
+    } else if (kind == K_POS2) {  // profile.rs:549-637
+        ts[0] = t[0];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) ts[i + 1] = ts[i] + t[i + 1];
+#pragma unroll
+        for (int i = 0; i < 7; ++i) j[i] = 0.0;
+        a[0] = (t[0] > 0.0) ? ctrl : 0.0; a[1] = 0.0; a[2] = (t[2] > 0.0) ? ctrl2 : 0.0; a[3] = 0.0; a[5] = 0.0;
+        if (cs == UDDU) { a[4] = (t[4] > 0.0) ? ctrl2 : 0.0; a[6] = (t[6] > 0.0) ? ctrl : 0.0; }
+        else { a[4] = (t[4] > 0.0) ? ctrl : 0.0; a[6] = (t[6] > 0.0) ? ctrl2 : 0.0; }
+        a[7] = af;
+#pragma unroll
+        for (int i = 0; i < 7; ++i) {
+            v[i + 1] = v[i] + t[i] * a[i];
+            p[i + 1] = p[i] + t[i] * (v[i] + t[i] * a[i] / 2.0);
+        }
+    } else if (kind == K_VEL2) {  // profile.rs:256-294
+        ts[0] = 0.0;
+#pragma unroll
+        for (int i = 1; i < 7; ++i) ts[i] = t[1];
+#pragma unroll
+        for (int i = 0; i < 7; ++i) j[i] = 0.0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a[i] = 0.0;
+        a[1] = (t[1] > 0.0) ? ctrl : 0.0;
+        a[7] = af;
+#pragma unroll
+        for (int i = 0; i < 7; ++i) {
+            v[i + 1] = v[i] + t[i] * a[i];
+            p[i + 1] = p[i] + t[i] * (v[i] + t[i] * a[i] / 2.0);
+        }
+    } else {  // K_POS1, profile.rs:685-726
+        ts[0] = 0.0; ts[1] = 0.0; ts[2] = 0.0; ts[3] = t[3]; ts[4] = t[3]; ts[5] = t[3]; ts[6] = t[3];
+#pragma unroll
+        for (int i = 0; i < 7; ++i) { j[i] = 0.0; a[i] = 0.0; v[i] = 0.0; }
+        a[7] = af;
+        v[3] = (t[3] > 0.0) ? ctrl : 0.0;
+        v[7] = vf;
+#pragma unroll
+        for (int i = 0; i < 7; ++i) p[i + 1] = p[i] + t[i] * (v[i] + t[i] * a[i] / 2.0);
+    }
+#pragma unroll
+    for (int i = 0; i < 7; ++i) { o.put(S_T + i, t[i]); o.put(S_TSUM + i, ts[i]); o.put(S_J + i, j[i]); }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { o.put(S_A + i, a[i]); o.put(S_V + i, v[i]); o.put(S_P + i, p[i]); }
+    return p[7];
+}
+
+// A profile the calculation never touched (disabled DoF, calculator_target.rs:313-323, or an error status): the fields of a
+// fresh Profile::default() except the end state, which at_time extrapolates from (trajectory.rs:122-132).
+__device__ __forceinline__ void store_idle_profile(const ProfileSink& o, double p7, double v7, double a7) {
+#pragma unroll
+    for (int i = 0; i < 7; ++i) { o.put(S_T + i, 0.0); o.put(S_TSUM + i, 0.0); o.put(S_J + i, 0.0); }
+#pragma unroll
+    for (int i = 0; i < 7; ++i) { o.put(S_A + i, 0.0); o.put(S_V + i, 0.0); o.put(S_P + i, 0.0); }
+    o.put(S_A + 7, a7); o.put(S_V + 7, v7); o.put(S_P + 7, p7);
+}
+
+}  // namespace rk

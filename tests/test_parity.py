@@ -1,0 +1,214 @@
+"""Parity of the CUDA path with the oracle on seeded random batches (-m gpu), through the C ABI.
+
+Bar (north_star): RuckigResult codes, profile type (limits + control signs) and direction exact; durations and sampled
+p/v/a within 1e-9 relative. The device restates the oracle's *portable* math flavour bit for bit, so against that
+flavour the tests demand exact equality of every stored double; against the glibc flavour (what a Linux build of the
+Rust reference links) they apply the 1e-9 bar and require zero code mismatches.
+"""
+import numpy as np
+import pytest
+
+from rsruckig_b200 import _cabi as cabi
+from rsruckig_b200 import workloads
+
+pytestmark = pytest.mark.gpu
+
+PROFILE_FIELDS = (cabi.RK_FIELD_T, cabi.RK_FIELD_T_SUM, cabi.RK_FIELD_J, cabi.RK_FIELD_A, cabi.RK_FIELD_V, cabi.RK_FIELD_P,
+                  cabi.RK_FIELD_BRAKE_DURATION, cabi.RK_FIELD_BRAKE_T, cabi.RK_FIELD_BRAKE_J, cabi.RK_FIELD_BRAKE_A,
+                  cabi.RK_FIELD_BRAKE_V, cabi.RK_FIELD_BRAKE_P, cabi.RK_FIELD_PF_VF_AF)
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from rsruckig_b200 import BatchRuckig
+    return BatchRuckig
+
+
+def run_both(BatchRuckig, fields, n, dof, *, delta_time=0.005, flavour="portable", threads=8, **kw):
+    from oracle.oracle import OracleBatch
+    from rsruckig_b200 import IgnoreErrorHandler, ThrowErrorHandler
+    error_mode = kw.pop("error_mode", cabi.RK_ERRORS_THROW)
+    otg = BatchRuckig(dof, delta_time, ThrowErrorHandler if error_mode == cabi.RK_ERRORS_THROW else IgnoreErrorHandler)
+    otg.calculate(fields, n=n, memory_space=cabi.RK_MEM_HOST, **kw)
+    ob = OracleBatch(n, dof, flavour)
+    ob.calculate(fields, delta_time=delta_time, threads=threads, error_mode=error_mode, **kw)
+    return otg, ob
+
+
+def assert_exact(otg, ob, *, label=""):
+    st_g, st_o = otg.read(cabi.RK_FIELD_STATUS), ob.read(cabi.RK_FIELD_STATUS)
+    bad = np.nonzero(st_g != st_o)[0]
+    assert bad.size == 0, f"{label}: {bad.size} status mismatches, first at {bad[:5]}: gpu {st_g[bad[:5]]} oracle {st_o[bad[:5]]}"
+    ok = st_o == 0
+    du_g, du_o = otg.read(cabi.RK_FIELD_DURATION), ob.read(cabi.RK_FIELD_DURATION)
+    keep = ok | (st_o == -101)
+    bad = np.nonzero((du_g != du_o) & keep)[0]
+    assert bad.size == 0, f"{label}: {bad.size} duration mismatches, first at {bad[:5]}: {du_g[bad[:5]]} vs {du_o[bad[:5]]}"
+    assert np.array_equal(otg.read(cabi.RK_FIELD_LIMITING_DOF)[ok], ob.read(cabi.RK_FIELD_LIMITING_DOF)[ok]), f"{label}: limiting DoF"
+    im_g, im_o = otg.read(cabi.RK_FIELD_INDEPENDENT_MIN_DURATIONS), ob.read(cabi.RK_FIELD_INDEPENDENT_MIN_DURATIONS)
+    assert np.array_equal(im_g[:, ok], im_o[:, ok]), f"{label}: independent_min_durations"
+    c_g, c_o = otg.read(cabi.RK_FIELD_CODES), ob.read(cabi.RK_FIELD_CODES)
+    bad = np.argwhere((c_g != c_o) & ok[None, :])
+    assert bad.shape[0] == 0, f"{label}: {bad.shape[0]} profile-code mismatches, first {bad[:5].tolist()}: {[hex(c_g[tuple(b)]) for b in bad[:5]]} vs {[hex(c_o[tuple(b)]) for b in bad[:5]]}"
+    for f in PROFILE_FIELDS:
+        a, b = otg.read(f)[:, :, ok], ob.read(f)[:, :, ok]
+        same = (a == b) | (np.isnan(a) & np.isnan(b))
+        bad = np.argwhere(~same)
+        assert bad.shape[0] == 0, f"{label}: field {f}: {bad.shape[0]} differing doubles, first {bad[:5].tolist()}"
+    return int(ok.sum())
+
+
+def test_bench_distribution_7dof_exact(gpu):
+    n, dof = 100_000, 7
+    f = workloads.bench_inputs(n, dof, seed=1)
+    otg, ob = run_both(gpu, f, n, dof)
+    n_ok = assert_exact(otg, ob, label="7dof")
+    assert n_ok > 0.9 * n
+
+
+def test_config2_6dof_exact(gpu):
+    n = 100_000
+    f = workloads.config2_inputs(n, seed=2)
+    otg, ob = run_both(gpu, f, n, 6)
+    assert_exact(otg, ob, label="6dof")
+
+
+@pytest.mark.parametrize("dof", [1, 2, 3, 8, 38])
+def test_other_dof_counts_exact(gpu, dof):
+    n = 20_000 if dof < 38 else 3_000
+    f = workloads.bench_inputs(n, dof, seed=10 + dof)
+    otg, ob = run_both(gpu, f, n, dof)
+    assert_exact(otg, ob, label=f"dof{dof}")
+
+
+def test_edge_cases_exact(gpu):
+    """Start states outside the limits (brake), rest-to-rest, zero displacement, tiny / huge limits, asymmetric minimum
+    limits, disabled DoFs — under both error handlers."""
+    n, dof = 60_000, 4
+    f = workloads.edge_case_inputs(n, dof, seed=3)
+    for mode in (cabi.RK_ERRORS_THROW, cabi.RK_ERRORS_IGNORE):
+        otg, ob = run_both(gpu, f, n, dof, error_mode=mode)
+        assert_exact(otg, ob, label=f"edge mode {mode}")
+
+
+def test_config3_velocity_phase_minimum_duration_discrete_exact(gpu):
+    """BASELINE.json configs[2]: 3-DoF velocity interface + Phase synchronisation, thirds of the batch with no extra /
+    minimum_duration / (separately) Discrete durations."""
+    from rsruckig_b200 import ControlInterface, DurationDiscretization, Synchronization
+    n = 60_000
+    f = workloads.config3_inputs(n, seed=4)
+    md = np.full(n, np.nan)
+    rng = np.random.default_rng(5)
+    third = np.arange(n) % 3 == 1
+    md[third] = rng.uniform(0.5, 8.0, int(third.sum()))
+    f["minimum_duration"] = md
+    for disc in (DurationDiscretization.Continuous, DurationDiscretization.Discrete):
+        otg, ob = run_both(gpu, f, n, 3, control_interface=ControlInterface.Velocity, synchronization=Synchronization.Phase,
+                           duration_discretization=disc)
+        assert_exact(otg, ob, label=f"config3 disc={int(disc)}")
+    src = otg.read(cabi.RK_FIELD_CODES) >> 24
+    assert (src == 3).sum() > 0, "no trajectory took the phase-synchronised path"
+
+
+def test_position_phase_and_mixed_sync_exact(gpu):
+    from rsruckig_b200 import ControlInterface, Synchronization
+    n, dof = 40_000, 3
+    f = workloads.bench_inputs(n, dof, seed=6)
+    # collinear quarter: scaled copies of DoF 0 so that phase synchronisation succeeds
+    col = np.arange(n) % 4 == 0
+    rng = np.random.default_rng(7)
+    scale = rng.uniform(0.25, 2.0, (dof, n))
+    scale[0] = 1.0
+    pd = f["target_position"] - f["current_position"]
+    f["target_position"][:, col] = (f["current_position"] + pd[0:1] * scale)[:, col]
+    for k in ("current_velocity", "current_acceleration", "target_velocity", "target_acceleration", "max_velocity", "max_acceleration", "max_jerk"):
+        f[k][:, col] = (f[k][0:1] * scale)[:, col]
+    otg, ob = run_both(gpu, f, n, dof, synchronization=Synchronization.Phase)
+    assert_exact(otg, ob, label="phase")
+    src = otg.read(cabi.RK_FIELD_CODES) >> 24
+    assert (src == 3).sum() > 0, "no trajectory took the phase-synchronised path"
+    otg, ob = run_both(gpu, f, n, dof, per_dof_synchronization=[Synchronization.Phase, Synchronization.None_, Synchronization.TimeIfNecessary],
+                       per_dof_control_interface=[ControlInterface.Position, ControlInterface.Velocity, ControlInterface.Position])
+    assert_exact(otg, ob, label="mixed")
+
+
+def test_second_and_first_order_exact(gpu):
+    """max_jerk = inf (acceleration-limited) and max_acceleration = inf as well (velocity-limited)."""
+    from rsruckig_b200 import ControlInterface
+    n, dof = 30_000, 3
+    f = workloads.bench_inputs(n, dof, seed=8)
+    f["max_jerk"][:] = np.inf
+    f["current_acceleration"][:] = 0.0
+    f["target_acceleration"][:] = 0.0
+    otg, ob = run_both(gpu, f, n, dof)
+    assert_exact(otg, ob, label="second order position")
+    otg, ob = run_both(gpu, f, n, dof, control_interface=ControlInterface.Velocity)
+    assert_exact(otg, ob, label="second order velocity")
+    f["max_acceleration"][:] = np.inf
+    f["current_velocity"][:] = 0.0
+    f["target_velocity"][:] = 0.0
+    otg, ob = run_both(gpu, f, n, dof)
+    assert_exact(otg, ob, label="first order position")
+
+
+def test_at_time_sampling_exact(gpu):
+    """BASELINE.json configs[3] in small: calculate + K control cycles of Trajectory::at_time."""
+    n, dof, K = 4096, 7, 200
+    f = workloads.edge_case_inputs(n, dof, seed=9)
+    otg, ob = run_both(gpu, f, n, dof)
+    ok = ob.read(cabi.RK_FIELD_STATUS) == 0
+    pos, vel, acc, jerk = (np.zeros((K, dof, n)) for _ in range(4))
+    sec = np.zeros((K, n), dtype=np.int32)
+    otg.at_time(time_start=0.0, delta_time=0.02, steps=K, memory_space=cabi.RK_MEM_HOST, position=pos, velocity=vel, acceleration=acc,
+                jerk=jerk, section=sec)
+    opos, ovel, oacc, ojerk, osec = ob.at_time(time_start=0.0, delta_time=0.02, steps=K, threads=8)
+    for a, b, name in ((pos, opos, "position"), (vel, ovel, "velocity"), (acc, oacc, "acceleration"), (jerk, ojerk, "jerk")):
+        assert np.array_equal(a[:, :, ok], b[:, :, ok]), name
+    assert np.array_equal(sec[:, ok], osec[:, ok])
+
+
+def test_against_glibc_flavour_within_tolerance(gpu):
+    """The 1e-9 bar of north_star against the reference-faithful (glibc libm) oracle build: zero code mismatches."""
+    n, dof = 200_000, 7
+    f = workloads.bench_inputs(n, dof, seed=11)
+    otg, ob = run_both(gpu, f, n, dof, flavour="glibc")
+    st_g, st_o = otg.read(cabi.RK_FIELD_STATUS), ob.read(cabi.RK_FIELD_STATUS)
+    assert np.array_equal(st_g, st_o)
+    ok = st_o == 0
+    assert np.array_equal((otg.read(cabi.RK_FIELD_CODES) & 0xFFFFFF)[:, ok], (ob.read(cabi.RK_FIELD_CODES) & 0xFFFFFF)[:, ok])
+    du_g, du_o = otg.read(cabi.RK_FIELD_DURATION)[ok], ob.read(cabi.RK_FIELD_DURATION)[ok]
+    assert np.max(np.abs(du_g - du_o) / np.maximum(np.abs(du_o), 1e-12)) <= 1e-9
+    t_g, t_o = otg.read(cabi.RK_FIELD_T)[:, :, ok], ob.read(cabi.RK_FIELD_T)[:, :, ok]
+    assert np.max(np.abs(t_g - t_o) - 1e-9 * np.abs(t_o)) <= 1e-12
+
+
+def test_device_buffers_and_full_size_properties(gpu):
+    """BASELINE.json configs[1] at full size (1M x 6-DoF) on device buffers, checked through size-independent
+    properties: every Working trajectory reaches its target state (|dp|,|dv| <= 1e-8, |da| <= 1e-10, the reference's
+    guarantees, README.md:418-423) at t = duration, all DoFs end together, and duration >= every independent minimum."""
+    import torch
+    n, dof = 1 << 20, 6
+    f = workloads.config2_inputs(n, seed=12)
+    d = {k: torch.from_numpy(v).cuda() for k, v in f.items()}
+    from rsruckig_b200 import ThrowErrorHandler
+    otg = gpu(dof, 0.005, ThrowErrorHandler)
+    status = torch.zeros(n, dtype=torch.int32, device="cuda")
+    duration = torch.zeros(n, dtype=torch.float64, device="cuda")
+    imd = torch.zeros((dof, n), dtype=torch.float64, device="cuda")
+    otg.calculate(d, n=n, memory_space=cabi.RK_MEM_DEVICE, status=status, duration=duration, independent_min_durations=imd)
+    otg.sync()
+    ok = status == 0
+    assert ok.float().mean() > 0.9
+    assert set(torch.unique(status).tolist()) <= {0, -100, -101, -110, -111}
+    assert bool((duration[ok][None, :] >= imd[:, ok] - 1e-12).all())
+    P = torch.from_numpy(otg.read(cabi.RK_FIELD_P)).cuda()
+    V = torch.from_numpy(otg.read(cabi.RK_FIELD_V)).cuda()
+    A = torch.from_numpy(otg.read(cabi.RK_FIELD_A)).cuda()
+    assert float((P[7] - d["target_position"]).abs()[:, ok].max()) <= 1e-8
+    assert float((V[7] - d["target_velocity"]).abs()[:, ok].max()) <= 1e-8
+    assert float((A[7] - d["target_acceleration"]).abs()[:, ok].max()) <= 1e-10
+    ts6 = torch.from_numpy(otg.read(cabi.RK_FIELD_T_SUM)).cuda()[6] + torch.from_numpy(otg.read(cabi.RK_FIELD_BRAKE_DURATION)).cuda()[0]
+    assert float((ts6 - duration[None, :]).abs()[:, ok].max()) <= 1e-9 * float(duration[ok].max())
