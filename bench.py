@@ -1,0 +1,333 @@
+#!/usr/bin/env python
+"""bench.py — throughput of the batched Ruckig calculation (BASELINE.json metric) on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # the CUDA path (this repo)
+    python bench.py --impl reference --gpus N --steps K --warmup W   # the reference algorithm on the host cores
+
+A "step" is one pass of Ruckig::calculate over one synthetic batch: `--n` 7-DoF position-interface, Time-synchronised
+problems per GPU drawn from the reference bench's input distribution (bench/src/benchmark_target.rs:115-153). The
+default batch is BASELINE.json configs[4] sharded over 8 GPUs (64 Mi / 8 = 8 Mi trajectories per GPU), so per-GPU work
+is fixed as N grows ("weak" scaling); trajectories are independent, ranks never exchange data.
+
+value  = trajectories/s, inputs and outputs resident in HBM, CUDA events on the library's stream, max over ranks.
+e2e    = the same through the C ABI with HOST buffers (pinned): H2D of the nine input arrays, the three kernels, D2H of
+         status + duration — all inside the timed region.
+roofline: the path is FP64-pipe bound, so `bound` is "fp64": achieved = algorithmic flop per trajectory
+         (measured by the op-counting build of the oracle, see profiles/) x trajectories/s; peak = a DFMA probe run on
+         the same GPU right before the timed region (MEASURED_PEAKS.json has no FP64 entry). The HBM side is reported
+         next to it against MEASURED_PEAKS.json's copy bandwidth.
+cpu_baseline: the C++ restatement of the reference (oracle/, glibc libm) on this box's host cores, on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+DOF = 7
+METRIC = "7-DoF trajectory calculations/s (position interface, Time sync)"
+UNIT = "trajectories/s"
+DELTA_TIME = 0.005
+BYTES_IN = 9 * DOF * 8                 # nine mandatory f64 arrays
+BYTES_OUT = (16 * DOF + 3) * 8         # compact result record of §8d (status, duration, t[7] + codes + jf ... per DoF)
+
+
+def algorithmic_flop_per_trajectory() -> tuple[float, str]:
+    p = os.path.join(ROOT, "profiles", "algorithmic_ops.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["flop_per_trajectory_7dof"]), d.get("how", "op-counting oracle")
+    return 60e3, "a-priori static estimate of SURVEY.md §8d (lower end); the op-counting oracle has not been run"
+
+
+def measured_peaks() -> dict:
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        d["_source"] = "measured"
+        return d
+    return {"hbm_gbs": 6650.0, "_source": "fallback"}
+
+
+def config(n_per_gpu: int, n_gpus: int) -> dict:
+    return {"workload": f"{n_per_gpu} x 7-DoF position interface per GPU, Time sync, reference bench input distribution "
+                        f"(BASELINE.json configs[4]: 64Mi sharded over 8 GPUs -> 8Mi per GPU)",
+            "n_per_gpu": n_per_gpu, "n_total": n_per_gpu * n_gpus, "dof": DOF, "delta_time": DELTA_TIME,
+            "l2": "inputs (4.0 GB per GPU at the default size) exceed the 126 MB L2, no flush needed",
+            "sharding": "contiguous index ranges, no collective"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for r in self.rows:
+            parts = [x.strip() for x in r.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1])); pw.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def run_reference(args):
+    """The reference's CPU algorithm (C++ restatement, glibc libm) on all host cores; rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle
+    from rsruckig_b200 import workloads
+    cores = os.cpu_count() or 1
+    threads = cores
+    n = args.cpu_sample or 131072 * max(1, min(threads, 64))
+    f = workloads.bench_inputs(n, DOF, seed=0)
+    for _ in range(args.warmup):
+        oracle.bench_calculate(f, n=min(n, 65536), dof=DOF, threads=threads, flavour="glibc", delta_time=DELTA_TIME)
+    secs = []
+    for _ in range(args.steps):
+        s, _, _ = oracle.bench_calculate(f, n=n, dof=DOF, threads=threads, flavour="glibc", delta_time=DELTA_TIME)
+        secs.append(s)
+    total = sum(secs)
+    value = n * args.steps / total
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": config(args.n, args.gpus),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                             "sample": f"{n} trajectories of the same distribution per step; C++17 restatement of rsruckig v2.1.2 (oracle/, "
+                                       f"g++ -O2 -ffp-contract=off, glibc libm), one reused calculator per thread, static partition over {threads} threads; "
+                                       "the Rust reference itself cannot be built here (no cargo/rustc)"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline_sample(threads_all: int) -> dict:
+    """Bounded CPU sample next to the GPU number: single thread and all cores, ~10-20 s of CPU work in total."""
+    from oracle import oracle
+    from rsruckig_b200 import workloads
+    n1 = 131072
+    f1 = workloads.bench_inputs(n1, DOF, seed=0)
+    oracle.bench_calculate(f1, n=16384, dof=DOF, threads=1, flavour="glibc", delta_time=DELTA_TIME)
+    s1, _, _ = oracle.bench_calculate(f1, n=n1, dof=DOF, threads=1, flavour="glibc", delta_time=DELTA_TIME)
+    nall = 131072 * max(1, min(threads_all, 64))
+    fall = workloads.bench_inputs(nall, DOF, seed=0) if nall != n1 else f1
+    sall, _, _ = oracle.bench_calculate(fall, n=nall, dof=DOF, threads=threads_all, flavour="glibc", delta_time=DELTA_TIME)
+    return {"value": nall / sall, "unit": UNIT, "cores": threads_all, "kind": "port",
+            "single_thread": {"value": n1 / s1, "us_per_trajectory": 1e6 * s1 / n1, "sample": f"{n1} trajectories"},
+            "sample": f"{nall} trajectories of the bench distribution, C++17 restatement of rsruckig (oracle/, glibc libm), "
+                      f"{threads_all} threads; reported baseline, not the target"}
+
+
+def gen_inputs_device(torch, n: int, device, seed: int):
+    """The reference bench distribution generated on the device (same recipe as workloads.bench_inputs)."""
+    g = torch.Generator(device=device)
+    g.manual_seed(1234 + seed)
+    shape = (DOF, n)
+    f64 = torch.float64
+    normal = lambda std: torch.empty(shape, dtype=f64, device=device).normal_(0.0, std, generator=g)
+    uniform = lambda lo, hi: torch.empty(shape, dtype=f64, device=device).uniform_(lo, hi, generator=g)
+
+    def fill_or_zero(p):
+        keep = torch.empty(shape, dtype=f64, device=device).uniform_(0.0, 1.0, generator=g) < p
+        return torch.where(keep, normal(0.8), torch.zeros((), dtype=f64, device=device))
+
+    f = {"current_position": normal(4.0), "current_velocity": fill_or_zero(0.9), "current_acceleration": fill_or_zero(0.8),
+         "target_position": normal(4.0), "target_velocity": fill_or_zero(0.7), "target_acceleration": fill_or_zero(0.6)}
+    f["max_velocity"] = uniform(0.1, 12.0) + f["target_velocity"].abs()
+    f["max_acceleration"] = uniform(0.1, 12.0) + f["target_acceleration"].abs()
+    f["max_jerk"] = uniform(0.1, 12.0)
+    return {k: v.contiguous() for k, v in f.items()}
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as entry
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU path; use --impl reference for the CPU baseline)"
+    if rank == 0:
+        entry.build()
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.barrier()
+    from rsruckig_b200 import BatchRuckig, ThrowErrorHandler, _cabi as cabi
+    import ctypes as C
+
+    n = args.n
+    dev = torch.device("cuda", local)
+    otg = BatchRuckig(DOF, DELTA_TIME, ThrowErrorHandler, device=local)
+    lib = otg._engine.lib
+    stream = torch.cuda.ExternalStream(lib.rk_stream(otg.handle), device=dev)
+
+    # FP64 peak probe on this GPU
+    peak = C.c_double(0.0)
+    cabi.check(lib.rk_measure_fp64_peak(otg.handle, 50.0, C.byref(peak)))
+    fp64_peak_tflops = float(peak.value)
+
+    f = gen_inputs_device(torch, n, dev, seed=rank)
+    status = torch.zeros(n, dtype=torch.int32, device=dev)
+    duration = torch.zeros(n, dtype=torch.float64, device=dev)
+    torch.cuda.synchronize()
+
+    def step_device():
+        otg.calculate(f, n=n, memory_space=cabi.RK_MEM_DEVICE, status=status, duration=duration)
+
+    launches0 = otg.kernel_launches()
+    for _ in range(args.warmup):
+        step_device()
+    otg.sync()
+    launches_per_step = (otg.kernel_launches() - launches0) // max(1, args.warmup)
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches1 = otg.kernel_launches()
+    with torch.cuda.stream(stream):
+        e0.record(stream)
+        for _ in range(args.steps):
+            step_device()
+        e1.record(stream)
+    otg.sync()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    gpu_launches = otg.kernel_launches() - launches1
+    clocks = sampler.stop() if rank == 0 else None
+    t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.barrier()
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms_max = float(t_ms.item())
+    value = n * world * args.steps / (ms_max * 1e-3)
+    n_working = int((status == 0).sum().item())
+
+    # ---- e2e: host (pinned) buffers through the C ABI, H2D + kernels + D2H inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        hf = {k: torch.empty(v.shape, dtype=v.dtype, pin_memory=True) for k, v in f.items()}
+        for k in hf:
+            hf[k].copy_(f[k])
+        h_status = torch.empty(n, dtype=torch.int32, pin_memory=True)
+        h_duration = torch.empty(n, dtype=torch.float64, pin_memory=True)
+        torch.cuda.synchronize()
+
+        def step_host():
+            otg.calculate(hf, n=n, memory_space=cabi.RK_MEM_HOST, status=h_status, duration=h_duration)
+
+        for _ in range(max(1, min(args.warmup, 2))):
+            step_host()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        k_e2e = max(1, min(args.steps, 3))
+        t0 = time.perf_counter()
+        for _ in range(k_e2e):
+            step_host()
+        otg.sync()
+        dt = time.perf_counter() - t0
+        t_e = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.barrier()
+            dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+        assert bool((h_status == status.cpu()).all()), "host-buffer and device-buffer runs disagree"
+        e2e = {"value": n * world * k_e2e / float(t_e.item()), "unit": UNIT, "steps": k_e2e,
+               "h2d_bytes_per_step": int(sum(v.numel() * v.element_size() for v in hf.values())),
+               "d2h_bytes_per_step": int(h_status.numel() * 4 + h_duration.numel() * 8),
+               "note": "rk_calculate_batch with RK_MEM_HOST on pinned buffers; trajectories stay device-resident for rk_at_time_batch"}
+
+    if rank == 0:
+        flop, flop_how = algorithmic_flop_per_trajectory()
+        peaks = measured_peaks()
+        per_gpu = value / world
+        achieved_tflops = flop * per_gpu / 1e12
+        hbm_gbs = (BYTES_IN + BYTES_OUT) * per_gpu / 1e9
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic", "config": config(n, world), "gpu_launches": int(gpu_launches), "launches_per_step": int(launches_per_step),
+                "working_fraction": n_working / n, "clocks": clocks, "e2e": e2e,
+                "roofline": {"bound": "fp64", "achieved": achieved_tflops, "peak": fp64_peak_tflops, "unit": "TFLOP/s",
+                             "frac": achieved_tflops / fp64_peak_tflops if fp64_peak_tflops else None, "traffic": None,
+                             "kernels": "k_step1 + k_sync + k_step2 (one step); per-kernel shares in profiles/",
+                             "flop_per_trajectory": flop, "flop_how": flop_how,
+                             "peak_how": "DFMA probe (rk_measure_fp64_peak) on this GPU before the timed region, FMA = 2 flop; the kernels run "
+                                         "with --fmad=false, so an add or a mul fills a DFMA issue slot with 1 flop",
+                             "hbm": {"achieved": hbm_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": hbm_gbs / peaks["hbm_gbs"],
+                                     "of": peaks["_source"], "bytes_per_trajectory": BYTES_IN + BYTES_OUT}}}
+        if not args.no_cpu:
+            line["cpu_baseline"] = cpu_baseline_sample(os.cpu_count() or 1)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n", type=int, default=8 << 20, help="trajectories per GPU")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="trajectories per step of the reference arm (0 = 131072 per thread)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -204,6 +204,9 @@ rk_status rk_trajectories_read(rk_handle* h, const rk_trajectories* traj, int32_
 rk_status rk_sync(rk_handle* h);                      /* wait for the handle's stream */
 void* rk_stream(rk_handle* h);                        /* the cudaStream_t, for event timing by the caller */
 int64_t rk_kernel_launches(const rk_handle* h);       /* kernels launched through this handle so far */
+/* Roofline denominator for this path (it is FP64-pipe bound): runs a register-resident chain of
+ * dependent-free DFMAs on every SM for about `milliseconds` and reports the sustained rate, an FMA counted as 2 flop. */
+rk_status rk_measure_fp64_peak(rk_handle* h, double milliseconds, double* tflops);
 const char* rk_status_string(rk_status s);
 const char* rk_last_error(void);
 const char* rk_version(void);

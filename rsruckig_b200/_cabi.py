@@ -120,7 +120,7 @@ LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "lib
 EXPORTS = (
     "rk_create", "rk_destroy", "rk_trajectories_create", "rk_trajectories_destroy", "rk_calculate_batch",
     "rk_validate_batch", "rk_at_time_batch", "rk_trajectories_read", "rk_sync", "rk_stream", "rk_kernel_launches",
-    "rk_status_string", "rk_last_error", "rk_version",
+    "rk_status_string", "rk_last_error", "rk_version", "rk_measure_fp64_peak",
 )
 
 
@@ -147,6 +147,8 @@ def load():
     lib.rk_stream.restype = vp
     lib.rk_kernel_launches.argtypes = [vp]
     lib.rk_kernel_launches.restype = C.c_int64
+    lib.rk_measure_fp64_peak.argtypes = [vp, C.c_double, C.POINTER(C.c_double)]
+    lib.rk_measure_fp64_peak.restype = C.c_int32
     lib.rk_status_string.argtypes = [C.c_int32]
     lib.rk_status_string.restype = C.c_char_p
     lib.rk_last_error.restype = C.c_char_p
