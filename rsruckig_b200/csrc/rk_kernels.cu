@@ -26,608 +26,10 @@
 #include <string>
 
 #include "../../include/ruckig_b200.h"
-#include "rk_step1.cuh"
-#include "rk_step_misc.cuh"
-#include "rk_step2.cuh"
-#include "rk_step2_vel.cuh"
-#include "rk_step2_acc.cuh"
-#include "rk_step2_none.cuh"
-#include "rk_store.cuh"
+#include "rk_pipeline.cuh"
+
 
 namespace rk {
-
-struct Params {
-    int64_t n;        // trajectories in the batch (stride of the caller's arrays and of the trajectory storage)
-    int64_t off;      // first trajectory of this chunk
-    int64_t cn;       // trajectories in this chunk (stride of the scratch arrays)
-    int32_t dof;
-    int32_t discrete;
-    int32_t throw_mode;
-    int32_t check_current, check_target;
-    double delta_time;
-    int8_t ci[RK_MAX_DOF];
-    int8_t sync[RK_MAX_DOF];
-    // inputs, [dof][n]
-    const double *p0, *v0, *a0, *pf, *vf, *af, *v_max, *a_max, *j_max, *v_min, *a_min, *min_dur;
-    const uint8_t* enabled;
-    // scratch, chunk-local
-    double* ws;       // [WS_SLOTS][dof][cn]
-    uint32_t* wmeta;  // [4][dof][cn]
-    uint8_t* wsrc;    // [dof][cn]
-    // trajectory storage
-    double* prof;     // [PROFILE_SLOTS][dof][n]
-    uint32_t* codes;  // [dof][n]
-    int32_t* status;  // [n]
-    double* duration; // [n]
-    double* imd;      // [dof][n]
-    int32_t* limiting;  // [n]
-    int32_t* detail;    // [n]
-};
-
-struct DofIn {
-    double p0, v0, a0, pf, vf, af, v_max, v_min, a_max, a_min, j_max;
-    bool enabled;
-};
-
-__device__ __forceinline__ DofIn load_dof(const Params& P, int d, int64_t ig) {
-    const int64_t g = (int64_t)d * P.n + ig;
-    DofIn x;
-    x.p0 = P.p0[g]; x.v0 = P.v0[g]; x.a0 = P.a0[g];
-    x.pf = P.pf[g]; x.vf = P.vf[g]; x.af = P.af[g];
-    x.v_max = P.v_max[g]; x.a_max = P.a_max[g]; x.j_max = P.j_max[g];
-    x.v_min = P.v_min ? P.v_min[g] : -x.v_max;
-    x.a_min = P.a_min ? P.a_min[g] : -x.a_max;
-    x.enabled = P.enabled ? (P.enabled[g] != 0) : true;
-    return x;
-}
-
-// InputParameter::validate for one DoF (input_parameter.rs:251-420); returns 0 or the id of the first failing check.
-__device__ __forceinline__ int validate_dof(const DofIn& x, int ci, bool check_current, bool check_target) {
-    const double j_max = x.j_max, a_max = x.a_max, a_min = x.a_min, a0 = x.a0, af = x.af, v0 = x.v0, vf = x.vf;
-    if (j_max != j_max || j_max < 0.0) return RK_INVALID_MAX_JERK;
-    if (a_max != a_max || a_max < 0.0) return RK_INVALID_MAX_ACCELERATION;
-    if (a_min != a_min || a_min > 0.0) return RK_INVALID_MIN_ACCELERATION;
-    if (a0 != a0) return RK_INVALID_CURRENT_ACCELERATION_NAN;
-    if (af != af) return RK_INVALID_TARGET_ACCELERATION_NAN;
-    if (check_current) {
-        if (a0 > a_max) return RK_INVALID_CURRENT_ACCELERATION_ABOVE;
-        if (a0 < a_min) return RK_INVALID_CURRENT_ACCELERATION_BELOW;
-    }
-    if (check_target) {
-        if (af > a_max) return RK_INVALID_TARGET_ACCELERATION_ABOVE;
-        if (af < a_min) return RK_INVALID_TARGET_ACCELERATION_BELOW;
-    }
-    if (v0 != v0) return RK_INVALID_CURRENT_VELOCITY_NAN;
-    if (vf != vf) return RK_INVALID_TARGET_VELOCITY_NAN;
-    if (ci == RK_POSITION) {
-        if (x.p0 != x.p0) return RK_INVALID_CURRENT_POSITION_NAN;
-        if (x.pf != x.pf) return RK_INVALID_TARGET_POSITION_NAN;
-        const double v_max = x.v_max, v_min = x.v_min;
-        if (v_max != v_max || v_max < 0.0) return RK_INVALID_MAX_VELOCITY;
-        if (v_min != v_min || v_min > 0.0) return RK_INVALID_MIN_VELOCITY;
-        if (check_current) {
-            if (v0 > v_max) return RK_INVALID_CURRENT_VELOCITY_ABOVE;
-            if (v0 < v_min) return RK_INVALID_CURRENT_VELOCITY_BELOW;
-        }
-        if (check_target) {
-            if (vf > v_max) return RK_INVALID_TARGET_VELOCITY_ABOVE;
-            if (vf < v_min) return RK_INVALID_TARGET_VELOCITY_BELOW;
-        }
-        if (check_current) {
-            if (a0 > 0.0 && j_max > 0.0 && v_at_a_zero(v0, a0, j_max) > v_max) return RK_INVALID_CURRENT_WILL_EXCEED;
-            if (a0 < 0.0 && j_max > 0.0 && v_at_a_zero(v0, a0, -j_max) < v_min) return RK_INVALID_CURRENT_WILL_UNDERCUT;
-        }
-        if (check_target) {
-            if (af < 0.0 && j_max > 0.0 && v_at_a_zero(vf, af, j_max) > v_max) return RK_INVALID_TARGET_WILL_EXCEED;
-            if (af > 0.0 && j_max > 0.0 && v_at_a_zero(vf, af, -j_max) < v_min) return RK_INVALID_TARGET_WILL_UNDERCUT;
-        }
-    }
-    return 0;
-}
-
-__device__ __forceinline__ int kind_of(int ci, double a_max, double j_max) {
-    const bool jinf = isinf(j_max), ainf = isinf(a_max);
-    if (ci == RK_POSITION) return !jinf ? K_POS3 : (!ainf ? K_POS2 : K_POS1);
-    if (ci == RK_VELOCITY) return !jinf ? K_VEL3 : K_VEL2;
-    return K_NONE;  // ControlInterface::Acceleration is not implemented by the reference (Q20)
-}
-
-__device__ __forceinline__ void ws_put_cand(const Params& P, int64_t wi, int64_t wstride, int slot, const Cand& c) {
-    double* base = P.ws + (int64_t)(W_CAND + slot * W_CAND_STRIDE) * wstride + wi;
-#pragma unroll
-    for (int k = 0; k < 7; ++k) base[(int64_t)k * wstride] = c.t[k];
-    base[7 * wstride] = c.ctrl;
-    base[8 * wstride] = c.ctrl2;
-    P.wmeta[(int64_t)(1 + slot) * wstride + wi] = pack_codes(c.lim, c.cs, c.dir, 0);
-}
-
-__device__ __forceinline__ void ws_get_cand(const Params& P, int64_t wi, int64_t wstride, int slot, double (&t)[7], double& ctrl, double& ctrl2, uint32_t& codes) {
-    const double* base = P.ws + (int64_t)(W_CAND + slot * W_CAND_STRIDE) * wstride + wi;
-#pragma unroll
-    for (int k = 0; k < 7; ++k) t[k] = base[(int64_t)k * wstride];
-    ctrl = base[7 * wstride];
-    ctrl2 = base[8 * wstride];
-    codes = P.wmeta[(int64_t)(1 + slot) * wstride + wi];
-}
-
-// ------------------------------------------------------------------------------------------------ k_step1
-__global__ void __launch_bounds__(128) k_step1(const Params P) {
-    const int64_t wstride = (int64_t)P.dof * P.cn;
-    const int64_t wi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (wi >= wstride) return;
-    const int d = (int)(wi / P.cn);
-    const int64_t il = wi - (int64_t)d * P.cn;
-    const int64_t ig = P.off + il;
-
-    const DofIn x = load_dof(P, d, ig);
-    const int ci = P.ci[d];
-    const int vcode = validate_dof(x, ci, false, true);  // Ruckig::calculate validates with (false, true), ruckig.rs:215
-    const int kind = kind_of(ci, x.a_max, x.j_max);
-
-    ProfileSink out{P.prof, (int64_t)P.dof * P.n, (int64_t)d * P.n + ig};
-    uint32_t meta = (uint32_t)kind | ((uint32_t)vcode << M_VCODE_SHIFT);
-    if (x.enabled) meta |= M_ENABLED;
-    if (x.a_max == 0.0 || x.a_min == 0.0 || x.j_max == 0.0) meta |= M_ZERO_LIMITS;
-
-    // fresh Profile: brake and boundary
-    double bdur = 0.0, bt0 = 0.0, bt1 = 0.0, bj0 = 0.0, bj1 = 0.0, ba0 = 0.0, ba1 = 0.0, bv0 = 0.0, bv1 = 0.0, bp0 = 0.0, bp1 = 0.0;
-    double ps = x.p0, vs = x.v0, as = x.a0;
-    double pf_store = 0.0, vf_store = 0.0, af_store = 0.0;
-    double t_min = 0.0;
-    BlockRec blk;
-    blk.has_a = 0; blk.has_b = 0; blk.t_min = 0.0; blk.a_left = 0.0; blk.a_right = 0.0; blk.b_left = 0.0; blk.b_right = 0.0;
-    bool found = false;
-
-    if (x.enabled && (vcode == 0 || !P.throw_mode)) {
-        // brake pre-trajectory (calculator_target.rs:330-387)
-        Brake br;
-        br.t[0] = 0.0; br.t[1] = 0.0; br.j[0] = 0.0; br.j[1] = 0.0; br.a0 = 0.0;
-        if (kind == K_POS3) position_brake(br, x.v0, x.a0, x.v_max, x.v_min, x.a_max, x.a_min, x.j_max);
-        else if (kind == K_POS2) position_brake_second_order(br, x.v0, x.v_max, x.v_min, x.a_max, x.a_min);
-        else if (kind == K_VEL3) velocity_brake_third_order(br, x.a0, x.a_max, x.a_min, x.j_max);
-        if (ci == RK_POSITION) { pf_store = x.pf; vf_store = x.vf; af_store = x.af; }
-        else if (ci == RK_VELOCITY) { vf_store = x.vf; af_store = x.af; }
-        bt0 = br.t[0]; bt1 = br.t[1]; bj0 = br.j[0]; bj1 = br.j[1];
-        if (kind == K_POS3 || kind == K_VEL3) {  // brake.rs:195-220
-            if (!(bt0 <= 0.0 && bt1 <= 0.0)) {
-                bdur = bt0;
-                bp0 = ps; bv0 = vs; ba0 = as;
-                integrate(bt0, ps, vs, as, bj0, ps, vs, as);
-                if (bt1 > 0.0) {
-                    bdur += bt1;
-                    bp1 = ps; bv1 = vs; ba1 = as;
-                    integrate(bt1, ps, vs, as, bj1, ps, vs, as);
-                }
-            }
-        } else if (kind == K_POS2) {  // brake.rs:222-235
-            ba0 = br.a0;
-            if (!(bt0 <= 0.0)) {
-                bdur = bt0;
-                bp0 = ps; bv0 = vs;
-                integrate(bt0, ps, vs, ba0, 0.0, ps, vs, as);
-            }
-        }
-
-        Bound b{ps, vs, as, x.pf, x.vf, x.af};
-        switch (kind) {
-            case K_POS3: found = step1_pos3(b, x.v_max, x.v_min, x.a_max, x.a_min, x.j_max, bdur, blk); break;
-            case K_POS2: found = step1_pos2(b, x.v_max, x.v_min, x.a_max, x.a_min, bdur, blk); break;
-            case K_POS1: found = step1_pos1(b, x.v_max, x.v_min, bdur, blk); break;
-            case K_VEL3: found = step1_vel3(b, x.a_max, x.a_min, x.j_max, bdur, blk); break;
-            case K_VEL2: found = step1_vel2(b, x.a_max, x.a_min, bdur, blk); break;
-            default: found = false; break;
-        }
-        if (found) { meta |= M_FOUND; t_min = blk.t_min; }
-    }
-    if (found && blk.has_a) meta |= M_HAS_A;
-    if (found && blk.has_b) meta |= M_HAS_B;
-
-    // scratch for the synchronisation / Step-2 kernels
-    double* w = P.ws + wi;
-    w[(int64_t)W_P0 * wstride] = ps; w[(int64_t)W_V0 * wstride] = vs; w[(int64_t)W_A0 * wstride] = as;
-    w[(int64_t)W_TMIN * wstride] = t_min;
-    w[(int64_t)W_ALEFT * wstride] = blk.a_left; w[(int64_t)W_ARIGHT * wstride] = blk.a_right;
-    w[(int64_t)W_BLEFT * wstride] = blk.b_left; w[(int64_t)W_BRIGHT * wstride] = blk.b_right;
-    w[(int64_t)W_BRAKE_DUR * wstride] = bdur;
-    if (found) {
-        ws_put_cand(P, wi, wstride, 0, blk.p_min);
-        if (blk.has_a) ws_put_cand(P, wi, wstride, 1, blk.pa);
-        if (blk.has_b) ws_put_cand(P, wi, wstride, 2, blk.pb);
-    }
-    P.wmeta[wi] = meta;
-
-    // the parts of the final Profile that do not depend on the later stages
-    out.put(S_BRAKE_DUR, bdur);
-    out.put(S_BRAKE_T, bt0); out.put(S_BRAKE_T + 1, bt1);
-    out.put(S_BRAKE_J, bj0); out.put(S_BRAKE_J + 1, bj1);
-    out.put(S_BRAKE_A, ba0); out.put(S_BRAKE_A + 1, ba1);
-    out.put(S_BRAKE_V, bv0); out.put(S_BRAKE_V + 1, bv1);
-    out.put(S_BRAKE_P, bp0); out.put(S_BRAKE_P + 1, bp1);
-    out.put(S_PF, pf_store); out.put(S_VF, vf_store); out.put(S_AF, af_store);
-    P.imd[(int64_t)d * P.n + ig] = found ? t_min : 0.0;
-}
-
-// ------------------------------------------------------------------------------------------------ k_sync
-// block.rs:157-172
-__device__ __forceinline__ bool is_blocked(double t, double t_min, bool has_a, double a_left, double a_right, bool has_b, double b_left, double b_right) {
-    if (t < t_min) return true;
-    if (has_a && t > a_left && t < a_right) return true;
-    if (has_b && t > b_left && t < b_right) return true;
-    return false;
-}
-
-__global__ void __launch_bounds__(128) k_sync(const Params P) {
-    const int64_t il = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (il >= P.cn) return;
-    const int64_t ig = P.off + il;
-    const int D = P.dof;
-    const int64_t wstride = (int64_t)D * P.cn;
-    const double* W = P.ws;
-#define WS(slot, d) W[(int64_t)(slot) * wstride + (int64_t)(d) * P.cn + il]
-#define META(d) P.wmeta[(int64_t)(d) * P.cn + il]
-#define SRC(d) P.wsrc[(int64_t)(d) * P.cn + il]
-
-    for (int d = 0; d < D; ++d) SRC(d) = RK_SRC_NONE;
-    int status = RK_RESULT_WORKING;
-    int detail = 0;
-    double duration = 0.0;
-    int limiting = -1;
-
-    // Err(ValidationError): first failing DoF (input_parameter.rs:251-420), then the delta_time rule (ruckig.rs:161-168)
-    if (P.throw_mode) {
-        for (int d = 0; d < D && status == 0; ++d) {
-            const uint32_t vc = (META(d) >> M_VCODE_SHIFT) & 0xFFu;
-            if (vc) { status = RK_RESULT_ERROR_INVALID_INPUT; detail = (int)(vc << 8) | d; }
-        }
-        if (status == 0 && P.delta_time <= 0.0 && P.discrete) { status = RK_RESULT_ERROR_INVALID_INPUT; detail = RK_INVALID_DELTA_TIME << 8; }
-    }
-    // Step-1 failure: lowest DoF index decides (calculator_target.rs:454-471)
-    if (status == 0) {
-        for (int d = 0; d < D && status == 0; ++d) {
-            const uint32_t m = META(d);
-            if ((m & M_ENABLED) && !(m & M_FOUND)) {
-                status = (m & M_ZERO_LIMITS) ? RK_RESULT_ERROR_ZERO_LIMITS : RK_RESULT_ERROR_EXECUTION_TIME_CALCULATION;
-                detail = (1 << 8) | d;
-            }
-        }
-    }
-
-    const double md_raw = P.min_dur ? P.min_dur[ig] : __longlong_as_double(0x7ff8000000000000LL);
-    const bool has_md = md_raw == md_raw;
-    const double md = has_md ? md_raw : 0.0;
-
-    bool done = status != 0;
-    if (!done && D == 1 && !has_md && !P.discrete) {  // :475-481
-        duration = WS(W_TMIN, 0);
-        if (META(0) & M_ENABLED) SRC(0) = RK_SRC_STEP1_MIN;
-        done = true;
-    }
-
-    if (!done) {
-        // ---- synchronize (:150-275)
-        double cand[3 * RK_MAX_DOF + 1];
-        int16_t idx[3 * RK_MAX_DOF + 1];
-        const int NC = 3 * D + 1;
-        bool any_interval = false;
-        for (int d = 0; d < D; ++d) {
-            if (P.sync[d] == RK_SYNC_NONE) {
-                cand[d] = 0.0; cand[D + d] = RK_INF; cand[2 * D + d] = RK_INF;
-                continue;
-            }
-            const uint32_t m = META(d);
-            cand[d] = WS(W_TMIN, d);
-            cand[D + d] = (m & M_HAS_A) ? WS(W_ARIGHT, d) : RK_INF;
-            cand[2 * D + d] = (m & M_HAS_B) ? WS(W_BRIGHT, d) : RK_INF;
-            any_interval |= (m & (M_HAS_A | M_HAS_B)) != 0;
-        }
-        cand[3 * D] = has_md ? md : RK_INF;
-        any_interval |= has_md;
-
-        if (P.discrete) {
-            for (int i = 0; i < NC; ++i) {
-                if (isinf(cand[i])) continue;
-                const double remainder = fmod(cand[i], P.delta_time);
-                if (remainder > EPS) cand[i] += P.delta_time - remainder;
-            }
-        }
-
-        const int idx_end = any_interval ? NC : D;
-        for (int i = 0; i < NC; ++i) idx[i] = (i < idx_end) ? (int16_t)i : (int16_t)0;  // fresh scratch: the tail is zero (Q4)
-        for (int i = 1; i < idx_end; ++i) {  // stable insertion sort == slice::sort_by
-            const int16_t key = idx[i];
-            const double kv = cand[key];
-            int k = i - 1;
-            while (k >= 0 && cand[idx[k]] > kv) { idx[k + 1] = idx[k]; --k; }
-            idx[k + 1] = key;
-        }
-
-        bool found_sync = false;
-        int which = -1;
-        for (int k = D - 1; k < NC && !found_sync; ++k) {
-            const int i = idx[k];
-            const double ts = cand[i];
-            bool blocked = false;
-            for (int d = 0; d < D && !blocked; ++d) {
-                if (P.sync[d] == RK_SYNC_NONE) continue;
-                const uint32_t m = META(d);
-                blocked = is_blocked(ts, WS(W_TMIN, d), (m & M_HAS_A) != 0, WS(W_ALEFT, d), WS(W_ARIGHT, d), (m & M_HAS_B) != 0, WS(W_BLEFT, d), WS(W_BRIGHT, d));
-            }
-            if (blocked || ts < (has_md ? md : 0.0) || isinf(ts)) continue;
-            duration = ts;
-            found_sync = true;
-            which = i;
-        }
-
-        if (!found_sync) {  // :492-518
-            bool zero_limits = false;
-            for (int d = 0; d < D; ++d) zero_limits |= (META(d) & M_ZERO_LIMITS) != 0;
-            status = zero_limits ? RK_RESULT_ERROR_ZERO_LIMITS : RK_RESULT_ERROR_SYNCHRONIZATION_CALCULATION;
-            detail = 2 << 8;
-            done = true;
-        } else {
-            if (which != 3 * D) {
-                limiting = which % D;
-                SRC(limiting) = (uint8_t)(which / D);  // 0 p_min, 1 a.profile, 2 b.profile
-            }
-            // None synchronisation (:520-528)
-            for (int d = 0; d < D; ++d) {
-                if ((META(d) & M_ENABLED) && P.sync[d] == RK_SYNC_NONE) {
-                    SRC(d) = RK_SRC_STEP1_MIN;
-                    const double tm = WS(W_TMIN, d);
-                    if (tm > duration) { duration = tm; limiting = d; }
-                }
-            }
-            if (duration > 7.6e3) {  // :531-533
-                status = RK_RESULT_ERROR_TRAJECTORY_DURATION;
-                done = true;
-            } else if (fabs(duration - 0.0) < EPS) {  // :535-541
-                for (int d = 0; d < D; ++d) SRC(d) = (META(d) & M_ENABLED) ? RK_SRC_STEP1_MIN : RK_SRC_NONE;
-                done = true;
-            } else {
-                bool all_none = true, any_phase = false, all_phase_or_none = true;
-                for (int d = 0; d < D; ++d) {
-                    const int s = P.sync[d];
-                    all_none &= (s == RK_SYNC_NONE);
-                    any_phase |= (s == RK_SYNC_PHASE);
-                    all_phase_or_none &= (s == RK_SYNC_PHASE || s == RK_SYNC_NONE);
-                }
-                if (!P.discrete && all_none) done = true;  // :543-550
-
-                // ---- phase synchronisation (:552-711, is_input_collinear :60-148)
-                if (!done && limiting >= 0 && any_phase) {
-                    double lt[7], lctrl, lctrl2;
-                    uint32_t lcodes;
-                    ws_get_cand(P, (int64_t)limiting * P.cn + il, wstride, SRC(limiting), lt, lctrl, lctrl2, lcodes);
-                    const int l_lim = lcodes & 0xFF, l_cs = (lcodes >> 8) & 0xFF, l_dir = (lcodes >> 16) & 0xFF;
-
-                    // scale vector selection
-                    int scale_dof = -1, scale_vec = -1;  // 0 pd, 1 v0, 2 a0, 3 vf, 4 af
-                    for (int d = 0; d < D && scale_dof < 0; ++d) {
-                        if (P.sync[d] != RK_SYNC_PHASE) continue;
-                        const DofIn x = load_dof(P, d, ig);
-                        const double pd = x.pf - x.p0;
-                        if (P.ci[d] == RK_POSITION && fabs(pd) > EPS) { scale_vec = 0; scale_dof = d; }
-                        else if (fabs(x.v0) > EPS) { scale_vec = 1; scale_dof = d; }
-                        else if (fabs(x.a0) > EPS) { scale_vec = 2; scale_dof = d; }
-                        else if (fabs(x.vf) > EPS) { scale_vec = 3; scale_dof = d; }
-                        else if (fabs(x.af) > EPS) { scale_vec = 4; scale_dof = d; }
-                    }
-                    bool collinear = scale_dof >= 0;
-                    double pd_scale = 0.0, v0_scale = 0.0, vf_scale = 0.0, a0_scale = 0.0, af_scale = 0.0, scale_limiting = 0.0, control_limiting = 0.0;
-                    auto pick = [&](const DofIn& x) {
-                        return scale_vec == 0 ? (x.pf - x.p0) : (scale_vec == 1 ? x.v0 : (scale_vec == 2 ? x.a0 : (scale_vec == 3 ? x.vf : x.af)));
-                    };
-                    if (collinear) {
-                        const DofIn xs = load_dof(P, scale_dof, ig);
-                        const double scale = pick(xs);
-                        pd_scale = (xs.pf - xs.p0) / scale;
-                        v0_scale = xs.v0 / scale;
-                        vf_scale = xs.vf / scale;
-                        a0_scale = xs.a0 / scale;
-                        af_scale = xs.af / scale;
-                        const DofIn xl = load_dof(P, limiting, ig);
-                        scale_limiting = pick(xl);
-                        control_limiting = (l_dir == DIR_UP) ? xl.j_max : -xl.j_max;
-                        if (isinf(xl.j_max)) control_limiting = (l_dir == DIR_UP) ? xl.a_max : xl.a_min;
-                        for (int d = 0; d < D && collinear; ++d) {
-                            if (P.sync[d] != RK_SYNC_PHASE) continue;
-                            const DofIn x = load_dof(P, d, ig);
-                            const double cs_ = pick(x);
-                            if ((P.ci[d] == RK_POSITION && fabs((x.pf - x.p0) - pd_scale * cs_) > EPS) || fabs(x.v0 - v0_scale * cs_) > EPS
-                                || fabs(x.a0 - a0_scale * cs_) > EPS || fabs(x.vf - vf_scale * cs_) > EPS || fabs(x.af - af_scale * cs_) > EPS)
-                                collinear = false;
-                        }
-                    }
-                    if (collinear && all_phase_or_none) {
-                        // Pass 0 validates every phase DoF with the limiting DoF's timing; only if all pass (and every DoF is
-                        // Phase or None, :701-708) pass 1 commits the scaled profiles. Otherwise nothing is kept: the
-                        // reference overwrites its partial results in the time-synchronisation loop.
-                        bool found_phase = true;
-                        for (int pass = 0; pass < 2 && found_phase; ++pass) {
-                            for (int d = 0; d < D; ++d) {
-                                const uint32_t m = META(d);
-                                if (!(m & M_ENABLED) || d == limiting || P.sync[d] != RK_SYNC_PHASE) continue;
-                                const DofIn x = load_dof(P, d, ig);
-                                const double npc = control_limiting * pick(x) / scale_limiting;
-                                int kind = m & M_KIND_MASK;
-                                // the reference routes a first-order DoF with a UDUD limiting profile to the second-order check (:629-641)
-                                if (kind == K_POS1 && l_cs == UDUD) kind = K_POS2;
-                                int dir = DIR_UP;
-                                switch (kind) {
-                                    case K_POS3: case K_POS2: dir = (x.v_max > 0.0) ? DIR_UP : DIR_DOWN; break;
-                                    case K_VEL3: dir = (x.a_max > 0.0) ? DIR_UP : DIR_DOWN; break;
-                                    default: dir = (npc > 0.0) ? DIR_UP : DIR_DOWN; break;
-                                }
-                                if (pass == 0) {
-                                    const Bound b{WS(W_P0, d), WS(W_V0, d), WS(W_A0, d), x.pf, x.vf, x.af};
-                                    bool ok = true;
-                                    switch (kind) {
-                                        case K_POS3: {
-                                            const Lim L{x.v_max, x.v_min, x.a_max, x.a_min, x.j_max};
-                                            ok = check_pos3_full(lt, l_cs, L_NONE, npc, L, b, x.j_max);
-                                            break;
-                                        }
-                                        case K_POS2:
-                                            ok = (x.a_min - A_EPS < npc) && (npc < x.a_max + A_EPS) && (x.a_min - A_EPS < -npc) && (-npc < x.a_max + A_EPS)
-                                                 && check_pos2(lt, l_cs, npc, -npc, x.v_max, x.v_min, b);
-                                            break;
-                                        case K_POS1: ok = (x.v_min - V_EPS < npc) && (npc < x.v_max + V_EPS) && check_pos1(lt, npc, b); break;
-                                        case K_VEL3: ok = (fabs(npc) < fabs(x.j_max) + J_EPS) && check_vel3(lt, l_cs, L_NONE, npc, x.a_max, x.a_min, b); break;
-                                        case K_VEL2: ok = (x.a_min - A_EPS < npc) && (npc < x.a_max + A_EPS) && check_vel2(lt, npc, b); break;
-                                        default: break;
-                                    }
-                                    found_phase &= ok;
-                                } else {
-                                    // slot 2 (the b-profile) of this DoF is free now: the trajectory is decided
-                                    Cand c;
-                                    copy_t(c.t, lt);
-                                    c.ctrl = npc; c.ctrl2 = -npc; c.lim = l_lim; c.cs = l_cs; c.dir = dir; c.dur = 0.0;
-                                    const int64_t wd = (int64_t)d * P.cn + il;
-                                    ws_put_cand(P, wd, wstride, 2, c);
-                                    P.wmeta[(int64_t)3 * wstride + wd] |= (uint32_t)(kind + 1) << 24;  // kind the profile is expanded with
-                                    SRC(d) = RK_SRC_PHASE;
-                                }
-                            }
-                        }
-                        if (found_phase) done = true;
-                    }
-                }
-
-                // ---- time synchronisation dispatch (:714-747)
-                if (!done) {
-                    for (int d = 0; d < D; ++d) {
-                        const uint32_t m = META(d);
-                        const bool skip = (d == limiting || P.sync[d] == RK_SYNC_NONE) && !P.discrete;
-                        if (!(m & M_ENABLED) || skip) continue;
-                        const double t_profile = duration - WS(W_BRAKE_DUR, d) - 0.0;
-                        if (P.sync[d] == RK_SYNC_TIME_IF_NECESSARY) {
-                            const DofIn x = load_dof(P, d, ig);
-                            if (fabs(x.vf) < EPS && fabs(x.af) < EPS) { SRC(d) = RK_SRC_STEP1_MIN; continue; }
-                        }
-                        // extremal profile re-use; b is only looked at when a is absent (Q3), i.e. never (b implies a)
-                        if (fabs(t_profile - WS(W_TMIN, d)) < 2.0 * EPS) { SRC(d) = RK_SRC_STEP1_MIN; continue; }
-                        if (m & M_HAS_A) {
-                            if (fabs(t_profile - WS(W_ARIGHT, d)) < 2.0 * EPS) { SRC(d) = RK_SRC_STEP1_A; continue; }
-                        } else if (m & M_HAS_B) {
-                            if (fabs(t_profile - WS(W_BRIGHT, d)) < 2.0 * EPS) { SRC(d) = RK_SRC_STEP1_B; continue; }
-                        }
-                        SRC(d) = RK_SRC_STEP2;
-                    }
-                }
-            }
-        }
-    }
-    P.status[ig] = status;
-    P.duration[ig] = duration;
-    P.limiting[ig] = limiting;
-    P.detail[ig] = detail;
-#undef WS
-#undef META
-#undef SRC
-}
-
-// ------------------------------------------------------------------------------------------------ k_step2
-// position_third_step2.rs:2449-2482: 16 (family, direction) stages, first valid candidate wins.
-__device__ __forceinline__ bool step2_pos3(const Bound& b, double tf, double v_max, double v_min, double a_max, double a_min, double j_max, Hit& h) {
-    S2 s;
-    s.init(b, tf, j_max);
-    const bool up_first = s.pd > tf * b.v0;
-    const Lim La = lim_dir(up_first, v_max, v_min, a_max, a_min, j_max);
-    const Lim Lb = lim_dir(!up_first, v_max, v_min, a_max, a_min, j_max);
-#pragma unroll 1
-    for (int stage = 0; stage < 16; ++stage) {
-        const Lim& L = ((stage >> 2) & 1) ? Lb : La;
-        bool ok;
-        switch (stage & 3) {
-            case 0: ok = (stage < 8) ? s2_acc0_acc1_vel(s, L, h) : s2_acc0_acc1(s, L, h); break;
-            case 1: ok = (stage < 8) ? s2_vel(s, L, h) : s2_acc0(s, L, h); break;
-            case 2: ok = (stage < 8) ? s2_acc0_vel(s, L, h) : s2_acc1(s, L, h); break;
-            default: ok = (stage < 8) ? s2_acc1_vel(s, L, h) : s2_none(s, L, h); break;
-        }
-        if (ok) return true;
-    }
-    return false;
-}
-
-__global__ void __launch_bounds__(128) k_step2(const Params P) {
-    const int64_t wstride = (int64_t)P.dof * P.cn;
-    const int64_t wi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (wi >= wstride) return;
-    const int d = (int)(wi / P.cn);
-    const int64_t il = wi - (int64_t)d * P.cn;
-    const int64_t ig = P.off + il;
-    const int64_t gi = (int64_t)d * P.n + ig;
-
-    const uint32_t meta = P.wmeta[wi];
-    const int kind = meta & M_KIND_MASK;
-    const int src = P.wsrc[wi];
-    ProfileSink out{P.prof, (int64_t)P.dof * P.n, gi};
-    const double* w = P.ws + wi;
-    const double ps = w[(int64_t)W_P0 * wstride], vs = w[(int64_t)W_V0 * wstride], as = w[(int64_t)W_A0 * wstride];
-
-    if (src == RK_SRC_NONE || kind == K_NONE) {
-        // disabled DoF (calculator_target.rs:313-323) or a trajectory that ended with an error status
-        const DofIn x = load_dof(P, d, ig);
-        store_idle_profile(out, x.p0, x.v0, x.a0);
-        P.codes[gi] = pack_codes(L_NONE, UDDU, DIR_UP, RK_SRC_NONE);
-        return;
-    }
-
-    double t[7], ctrl, ctrl2;
-    int lim, cs, dir, lim_check, store_kind = kind;
-    const DofIn x = load_dof(P, d, ig);
-    bool pf_from_p7 = false;
-
-    if (src == RK_SRC_STEP2) {
-        const double duration = P.duration[ig];
-        const double tf = duration - w[(int64_t)W_BRAKE_DUR * wstride] - 0.0;
-        const Bound b{ps, vs, as, x.pf, x.vf, x.af};
-        bool ok = false;
-        if (kind == K_POS3) {
-            Hit h;
-            ok = step2_pos3(b, tf, x.v_max, x.v_min, x.a_max, x.a_min, x.j_max, h);
-            copy_t(t, h.t);
-            ctrl = h.jf; ctrl2 = 0.0; lim = h.lim; cs = h.cs; dir = h.dir;
-        } else {
-            Cand c;
-            if (kind == K_POS2) { ok = step2_pos2(b, tf, x.v_max, x.v_min, x.a_max, x.a_min, c); pf_from_p7 = true; }
-            else if (kind == K_POS1) ok = step2_pos1(b, tf, c);
-            else if (kind == K_VEL3) { ok = step2_vel3(b, tf, x.a_max, x.a_min, x.j_max, c); pf_from_p7 = true; }
-            else { ok = step2_vel2(b, tf, x.a_max, x.a_min, c); pf_from_p7 = true; }
-            copy_t(t, c.t);
-            ctrl = c.ctrl; ctrl2 = c.ctrl2; lim = c.lim; cs = c.cs; dir = c.dir;
-        }
-        if (!ok) {  // :819-826 — every failing DoF stores the same value; the lowest index is reported in the detail word
-            P.status[ig] = RK_RESULT_ERROR_EXECUTION_TIME_CALCULATION;
-            const int mine = (3 << 8) | d;
-            int seen = P.detail[ig];
-            while (seen == 0 || mine < seen) {
-                const int prev = atomicCAS(&P.detail[ig], seen, mine);
-                if (prev == seen) break;
-                seen = prev;
-            }
-            store_idle_profile(out, 0.0, 0.0, 0.0);
-            P.codes[gi] = pack_codes(L_NONE, UDDU, DIR_UP, RK_SRC_STEP2);
-            return;
-        }
-        lim_check = lim;
-    } else {
-        int slot = src;
-        if (slot == RK_SRC_PHASE) slot = 2;
-        uint32_t c;
-        ws_get_cand(P, wi, wstride, slot, t, ctrl, ctrl2, c);
-        lim = c & 0xFF; cs = (c >> 8) & 0xFF; dir = (c >> 16) & 0xFF;
-        lim_check = lim;
-        if (src == RK_SRC_PHASE) {  // validated with ReachedLimits::None, labelled with the limiting DoF's limits (Q25)
-            lim_check = L_NONE;
-            store_kind = (int)(c >> 24) - 1;
-        }
-    }
-
-    const double p7 = store_profile(out, store_kind, t, ctrl, ctrl2, cs, lim_check, ps, vs, as, x.vf, x.af);
-    if (pf_from_p7) out.put(S_PF, p7);
-    P.codes[gi] = pack_codes(lim, cs, dir, src);
-}
 
 // ------------------------------------------------------------------------------------------------ k_validate
 __global__ void __launch_bounds__(128) k_validate(const Params P, uint8_t* valid, int32_t* reason) {
@@ -778,6 +180,9 @@ struct rk_handle {
     double* ws = nullptr;
     uint32_t* wmeta = nullptr;
     uint8_t* wsrc = nullptr;
+    uint32_t* list[2] = {nullptr, nullptr};
+    uint32_t* counters = nullptr;
+    int sm_count = 148;
     // staging for host-memory calls
     void* stage_dev = nullptr;
     size_t stage_dev_bytes = 0;
@@ -800,10 +205,16 @@ struct rk_trajectories {
 
 static rk_status ensure_scratch(rk_handle* h, int64_t items) {
     if (items <= h->ws_items) return RK_OK;
-    if (h->ws) { cudaFree(h->ws); cudaFree(h->wmeta); cudaFree(h->wsrc); h->ws = nullptr; h->ws_items = 0; }
+    if (h->ws) {
+        cudaFree(h->ws); cudaFree(h->wmeta); cudaFree(h->wsrc); cudaFree(h->list[0]); cudaFree(h->list[1]); cudaFree(h->counters);
+        h->ws = nullptr; h->ws_items = 0;
+    }
     RK_CUDA(cudaMalloc(&h->ws, sizeof(double) * rk::WS_SLOTS * items));
-    RK_CUDA(cudaMalloc(&h->wmeta, sizeof(uint32_t) * 4 * items));
+    RK_CUDA(cudaMalloc(&h->wmeta, sizeof(uint32_t) * rk::WM_WORDS * items));
     RK_CUDA(cudaMalloc(&h->wsrc, items));
+    RK_CUDA(cudaMalloc(&h->list[0], sizeof(uint32_t) * items));
+    RK_CUDA(cudaMalloc(&h->list[1], sizeof(uint32_t) * items));
+    RK_CUDA(cudaMalloc(&h->counters, sizeof(uint32_t) * 32));
     h->ws_items = items;
     return RK_OK;
 }
@@ -891,6 +302,7 @@ rk_status rk_create(int32_t device, rk_handle** out) {
     rk_handle* h = new rk_handle();
     h->device = device;
     RK_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    RK_CUDA(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device));
     *out = h;
     return RK_OK;
 }
@@ -899,7 +311,7 @@ rk_status rk_destroy(rk_handle* h) {
     if (!h) return RK_OK;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    if (h->ws) { cudaFree(h->ws); cudaFree(h->wmeta); cudaFree(h->wsrc); }
+    if (h->ws) { cudaFree(h->ws); cudaFree(h->wmeta); cudaFree(h->wsrc); cudaFree(h->list[0]); cudaFree(h->list[1]); cudaFree(h->counters); }
     if (h->stage_dev) cudaFree(h->stage_dev);
     if (h->stage_pinned) cudaFreeHost(h->stage_pinned);
     cudaStreamDestroy(h->stream);
@@ -957,15 +369,38 @@ rk_status rk_calculate_batch(rk_handle* h, const rk_batch_desc* desc, const rk_b
     st = ensure_scratch(h, cn_max * desc->dof);
     if (st != RK_OK) return st;
     P.ws = h->ws; P.wmeta = h->wmeta; P.wsrc = h->wsrc;
+    P.list[0] = h->list[0]; P.list[1] = h->list[1]; P.counters = h->counters;
 
     for (int64_t off = 0; off < desc->n; off += cn_max) {
         P.off = off;
         P.cn = (desc->n - off < cn_max) ? (desc->n - off) : cn_max;
         const int64_t items = P.cn * P.dof;
-        rk::k_step1<<<(unsigned)((items + 127) / 128), 128, 0, h->stream>>>(P);
+        const unsigned grid_items = (unsigned)((items + 127) / 128);
+        // list-driven stages: a few resident waves per SM, grid-stride over the (device-side) list length
+        unsigned grid_list = (unsigned)h->sm_count * 16u;
+        if (grid_list > grid_items) grid_list = grid_items;
+        RK_CUDA(cudaMemsetAsync(h->counters, 0, sizeof(uint32_t) * 32, h->stream));
+        rk::k1_setup<<<grid_items, 128, 0, h->stream>>>(P);
+        rk::k1_family<0><<<grid_items, 128, 0, h->stream>>>(P);
+        rk::k1_family<1><<<grid_items, 128, 0, h->stream>>>(P);
+        rk::k1_family<2><<<grid_items, 128, 0, h->stream>>>(P);
+        rk::k1_block<<<grid_items, 128, 0, h->stream>>>(P);
         rk::k_sync<<<(unsigned)((P.cn + 127) / 128), 128, 0, h->stream>>>(P);
-        rk::k_step2<<<(unsigned)((items + 127) / 128), 128, 0, h->stream>>>(P);
-        h->launches += 3;
+        rk::k2_first<<<grid_items, 128, 0, h->stream>>>(P);
+        for (int stage = 1; stage < 16; ++stage) {
+            switch (((stage >> 3) << 2) | (stage & 3)) {
+                case 0: rk::k2_stage<0><<<grid_list, 128, 0, h->stream>>>(P, stage); break;
+                case 1: rk::k2_stage<1><<<grid_list, 128, 0, h->stream>>>(P, stage); break;
+                case 2: rk::k2_stage<2><<<grid_list, 128, 0, h->stream>>>(P, stage); break;
+                case 3: rk::k2_stage<3><<<grid_list, 128, 0, h->stream>>>(P, stage); break;
+                case 4: rk::k2_stage<4><<<grid_list, 128, 0, h->stream>>>(P, stage); break;
+                case 5: rk::k2_stage<5><<<grid_list, 128, 0, h->stream>>>(P, stage); break;
+                case 6: rk::k2_stage<6><<<grid_list, 128, 0, h->stream>>>(P, stage); break;
+                default: rk::k2_stage<7><<<grid_list, 128, 0, h->stream>>>(P, stage); break;
+            }
+        }
+        rk::k2_fail<<<(unsigned)h->sm_count, 128, 0, h->stream>>>(P);
+        h->launches += 23;
     }
     RK_CUDA(cudaGetLastError());
 
@@ -1140,3 +575,4 @@ const char* rk_last_error(void) { return g_last_error.c_str(); }
 const char* rk_version(void) { return "ruckig_b200 0.1.0 (sm_100a; parity target rsruckig 2.1.2)"; }
 
 }  // extern "C"
+

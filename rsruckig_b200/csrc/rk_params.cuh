@@ -1,0 +1,129 @@
+// rk_params.cuh — kernel parameter block, per-DoF input loading, input validation and the scratch (workspace) accessors
+// shared by all kernels of the pipeline.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "../../include/ruckig_b200.h"
+#include "rk_step1.cuh"
+#include "rk_store.cuh"
+
+namespace rk {
+
+struct Params {
+    int64_t n;        // trajectories in the batch (stride of the caller's arrays and of the trajectory storage)
+    int64_t off;      // first trajectory of this chunk
+    int64_t cn;       // trajectories in this chunk (stride of the scratch arrays)
+    int32_t dof;
+    int32_t discrete;
+    int32_t throw_mode;
+    int32_t check_current, check_target;
+    double delta_time;
+    int8_t ci[RK_MAX_DOF];
+    int8_t sync[RK_MAX_DOF];
+    // inputs, [dof][n]
+    const double *p0, *v0, *a0, *pf, *vf, *af, *v_max, *a_max, *j_max, *v_min, *a_min, *min_dur;
+    const uint8_t* enabled;
+    // scratch, chunk-local
+    double* ws;       // [WS_SLOTS][dof][cn]
+    uint32_t* wmeta;  // [WM_WORDS][dof][cn]
+    uint8_t* wsrc;    // [dof][cn]
+    uint32_t* list[2];   // ping-pong work lists of item indices for the Step-2 stages, [dof * cn] each
+    uint32_t* counters;  // [17] list lengths per Step-2 stage
+    // trajectory storage
+    double* prof;     // [PROFILE_SLOTS][dof][n]
+    uint32_t* codes;  // [dof][n]
+    int32_t* status;  // [n]
+    double* duration; // [n]
+    double* imd;      // [dof][n]
+    int32_t* limiting;  // [n]
+    int32_t* detail;    // [n]
+};
+
+struct DofIn {
+    double p0, v0, a0, pf, vf, af, v_max, v_min, a_max, a_min, j_max;
+    bool enabled;
+};
+
+__device__ __forceinline__ DofIn load_dof(const Params& P, int d, int64_t ig) {
+    const int64_t g = (int64_t)d * P.n + ig;
+    DofIn x;
+    x.p0 = P.p0[g]; x.v0 = P.v0[g]; x.a0 = P.a0[g];
+    x.pf = P.pf[g]; x.vf = P.vf[g]; x.af = P.af[g];
+    x.v_max = P.v_max[g]; x.a_max = P.a_max[g]; x.j_max = P.j_max[g];
+    x.v_min = P.v_min ? P.v_min[g] : -x.v_max;
+    x.a_min = P.a_min ? P.a_min[g] : -x.a_max;
+    x.enabled = P.enabled ? (P.enabled[g] != 0) : true;
+    return x;
+}
+
+// InputParameter::validate for one DoF (input_parameter.rs:251-420); returns 0 or the id of the first failing check.
+__device__ __forceinline__ int validate_dof(const DofIn& x, int ci, bool check_current, bool check_target) {
+    const double j_max = x.j_max, a_max = x.a_max, a_min = x.a_min, a0 = x.a0, af = x.af, v0 = x.v0, vf = x.vf;
+    if (j_max != j_max || j_max < 0.0) return RK_INVALID_MAX_JERK;
+    if (a_max != a_max || a_max < 0.0) return RK_INVALID_MAX_ACCELERATION;
+    if (a_min != a_min || a_min > 0.0) return RK_INVALID_MIN_ACCELERATION;
+    if (a0 != a0) return RK_INVALID_CURRENT_ACCELERATION_NAN;
+    if (af != af) return RK_INVALID_TARGET_ACCELERATION_NAN;
+    if (check_current) {
+        if (a0 > a_max) return RK_INVALID_CURRENT_ACCELERATION_ABOVE;
+        if (a0 < a_min) return RK_INVALID_CURRENT_ACCELERATION_BELOW;
+    }
+    if (check_target) {
+        if (af > a_max) return RK_INVALID_TARGET_ACCELERATION_ABOVE;
+        if (af < a_min) return RK_INVALID_TARGET_ACCELERATION_BELOW;
+    }
+    if (v0 != v0) return RK_INVALID_CURRENT_VELOCITY_NAN;
+    if (vf != vf) return RK_INVALID_TARGET_VELOCITY_NAN;
+    if (ci == RK_POSITION) {
+        if (x.p0 != x.p0) return RK_INVALID_CURRENT_POSITION_NAN;
+        if (x.pf != x.pf) return RK_INVALID_TARGET_POSITION_NAN;
+        const double v_max = x.v_max, v_min = x.v_min;
+        if (v_max != v_max || v_max < 0.0) return RK_INVALID_MAX_VELOCITY;
+        if (v_min != v_min || v_min > 0.0) return RK_INVALID_MIN_VELOCITY;
+        if (check_current) {
+            if (v0 > v_max) return RK_INVALID_CURRENT_VELOCITY_ABOVE;
+            if (v0 < v_min) return RK_INVALID_CURRENT_VELOCITY_BELOW;
+        }
+        if (check_target) {
+            if (vf > v_max) return RK_INVALID_TARGET_VELOCITY_ABOVE;
+            if (vf < v_min) return RK_INVALID_TARGET_VELOCITY_BELOW;
+        }
+        if (check_current) {
+            if (a0 > 0.0 && j_max > 0.0 && v_at_a_zero(v0, a0, j_max) > v_max) return RK_INVALID_CURRENT_WILL_EXCEED;
+            if (a0 < 0.0 && j_max > 0.0 && v_at_a_zero(v0, a0, -j_max) < v_min) return RK_INVALID_CURRENT_WILL_UNDERCUT;
+        }
+        if (check_target) {
+            if (af < 0.0 && j_max > 0.0 && v_at_a_zero(vf, af, j_max) > v_max) return RK_INVALID_TARGET_WILL_EXCEED;
+            if (af > 0.0 && j_max > 0.0 && v_at_a_zero(vf, af, -j_max) < v_min) return RK_INVALID_TARGET_WILL_UNDERCUT;
+        }
+    }
+    return 0;
+}
+
+__device__ __forceinline__ int kind_of(int ci, double a_max, double j_max) {
+    const bool jinf = isinf(j_max), ainf = isinf(a_max);
+    if (ci == RK_POSITION) return !jinf ? K_POS3 : (!ainf ? K_POS2 : K_POS1);
+    if (ci == RK_VELOCITY) return !jinf ? K_VEL3 : K_VEL2;
+    return K_NONE;  // ControlInterface::Acceleration is not implemented by the reference (Q20)
+}
+
+__device__ __forceinline__ void ws_put_cand(const Params& P, int64_t wi, int64_t wstride, int slot, const Cand& c) {
+    double* base = P.ws + (int64_t)(W_CAND + slot * W_CAND_STRIDE) * wstride + wi;
+#pragma unroll
+    for (int k = 0; k < 7; ++k) base[(int64_t)k * wstride] = c.t[k];
+    base[7 * wstride] = c.ctrl;
+    base[8 * wstride] = c.ctrl2;
+    P.wmeta[(int64_t)(WM_CAND + slot) * wstride + wi] = pack_codes(c.lim, c.cs, c.dir, 0);
+}
+
+__device__ __forceinline__ void ws_get_cand(const Params& P, int64_t wi, int64_t wstride, int slot, double (&t)[7], double& ctrl, double& ctrl2, uint32_t& codes) {
+    const double* base = P.ws + (int64_t)(W_CAND + slot * W_CAND_STRIDE) * wstride + wi;
+#pragma unroll
+    for (int k = 0; k < 7; ++k) t[k] = base[(int64_t)k * wstride];
+    ctrl = base[7 * wstride];
+    ctrl2 = base[8 * wstride];
+    codes = P.wmeta[(int64_t)(WM_CAND + slot) * wstride + wi];
+}
+
+
+}  // namespace rk

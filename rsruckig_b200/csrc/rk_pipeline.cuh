@@ -1,0 +1,720 @@
+// rk_pipeline.cuh — the calculation as a pipeline of small kernels.
+//
+// The monolithic "one thread does everything for its (DoF, trajectory)" form of this code ran at ~2 % FP64 utilisation:
+// 300-390 KB of SASS per kernel thrashed the instruction cache (ncu: `no_instruction` was the top stall) and warps
+// averaged 5-7 active lanes. The pipeline below keeps every kernel's code small and every warp on one solver family:
+//
+//   k1_setup            validation, brake pre-trajectory, zero-limit and non-third-order Step 1 (cheap closed forms)
+//   k1_family<0,1,2>    the three Step-1 candidate families of the third-order position interface, both directions each,
+//                       appending validated candidates to a per-item list in HBM
+//   k1_block            candidate list -> block of feasible durations (block.rs), numerical rescues
+//   k_sync              one thread per trajectory: status, common duration, limiting DoF, phase sync, per-DoF decision
+//   k2_first            everything that needs no Step-2 chain is finalised; Step-2 items run stage 0 of the chain
+//   k2_stage<F> x15     stage s of the chain (position_third_step2.rs:2449-2482) over the compacted list of items that
+//                       are still unsolved; solved items are expanded and stored at once, the rest move to the next list
+//   k2_fail             items that survive all 16 stages -> ErrorExecutionTimeCalculation
+//
+// Lists are compacted with warp-aggregated atomics; ordering inside a list does not matter (items are independent).
+#pragma once
+#include "rk_params.cuh"
+#include "rk_step_misc.cuh"
+#include "rk_step2.cuh"
+#include "rk_step2_vel.cuh"
+#include "rk_step2_acc.cuh"
+#include "rk_step2_none.cuh"
+
+namespace rk {
+
+// ------------------------------------------------------------------------------------------------ candidate list in scratch
+__device__ __forceinline__ void vlist_put(const Params& P, int64_t wi, int64_t wstride, int slot, const Cand& c) {
+    double* base = P.ws + (int64_t)(W_VLIST + slot * W_VLIST_STRIDE) * wstride + wi;
+#pragma unroll
+    for (int k = 0; k < 7; ++k) base[(int64_t)k * wstride] = c.t[k];
+    base[7 * wstride] = c.ctrl;
+}
+
+__device__ __forceinline__ void vlist_get(const Params& P, int64_t wi, int64_t wstride, int slot, uint32_t vcodes, Cand& c) {
+    const double* base = P.ws + (int64_t)(W_VLIST + slot * W_VLIST_STRIDE) * wstride + wi;
+#pragma unroll
+    for (int k = 0; k < 7; ++k) c.t[k] = base[(int64_t)k * wstride];
+    c.ctrl = base[7 * wstride];
+    c.ctrl2 = 0.0;
+    c.dur = t_sum6(c.t);
+    const uint32_t code = (vcodes >> (4 * slot)) & 0xFu;
+    c.lim = code & 7; c.dir = (code >> 3) & 1; c.cs = UDDU;
+}
+
+__device__ __forceinline__ uint32_t vcode_of(const Cand& c) { return (uint32_t)c.lim | ((uint32_t)c.dir << 3); }
+
+__device__ __forceinline__ void write_block(const Params& P, int64_t wi, int64_t wstride, const BlockRec& blk, bool found, uint32_t& meta) {
+    double* w = P.ws + wi;
+    w[(int64_t)W_TMIN * wstride] = found ? blk.t_min : 0.0;
+    w[(int64_t)W_ALEFT * wstride] = blk.a_left; w[(int64_t)W_ARIGHT * wstride] = blk.a_right;
+    w[(int64_t)W_BLEFT * wstride] = blk.b_left; w[(int64_t)W_BRIGHT * wstride] = blk.b_right;
+    if (found) {
+        meta |= M_FOUND;
+        ws_put_cand(P, wi, wstride, 0, blk.p_min);
+        if (blk.has_a) { meta |= M_HAS_A; ws_put_cand(P, wi, wstride, 1, blk.pa); }
+        if (blk.has_b) { meta |= M_HAS_B; ws_put_cand(P, wi, wstride, 2, blk.pb); }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ k1_setup
+__global__ void __launch_bounds__(128) k1_setup(const Params P) {
+    const int64_t wstride = (int64_t)P.dof * P.cn;
+    const int64_t wi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (wi >= wstride) return;
+    const int d = (int)(wi / P.cn);
+    const int64_t il = wi - (int64_t)d * P.cn;
+    const int64_t ig = P.off + il;
+
+    const DofIn x = load_dof(P, d, ig);
+    const int ci = P.ci[d];
+    const int vcode = validate_dof(x, ci, false, true);  // Ruckig::calculate validates with (false, true), ruckig.rs:215
+    const int kind = kind_of(ci, x.a_max, x.j_max);
+
+    ProfileSink out{P.prof, (int64_t)P.dof * P.n, (int64_t)d * P.n + ig};
+    uint32_t meta = (uint32_t)kind | ((uint32_t)vcode << M_VCODE_SHIFT);
+    if (x.enabled) meta |= M_ENABLED;
+    if (x.a_max == 0.0 || x.a_min == 0.0 || x.j_max == 0.0) meta |= M_ZERO_LIMITS;
+
+    // fresh Profile: brake and boundary
+    double bdur = 0.0, bt0 = 0.0, bt1 = 0.0, bj0 = 0.0, bj1 = 0.0, ba0 = 0.0, ba1 = 0.0, bv0 = 0.0, bv1 = 0.0, bp0 = 0.0, bp1 = 0.0;
+    double ps = x.p0, vs = x.v0, as = x.a0;
+    double pf_store = 0.0, vf_store = 0.0, af_store = 0.0;
+    BlockRec blk;
+    blk.has_a = 0; blk.has_b = 0; blk.t_min = 0.0; blk.a_left = 0.0; blk.a_right = 0.0; blk.b_left = 0.0; blk.b_right = 0.0;
+    bool found = false;
+
+    if (x.enabled && (vcode == 0 || !P.throw_mode)) {
+        // brake pre-trajectory (calculator_target.rs:330-387)
+        Brake br;
+        br.t[0] = 0.0; br.t[1] = 0.0; br.j[0] = 0.0; br.j[1] = 0.0; br.a0 = 0.0;
+        if (kind == K_POS3) position_brake(br, x.v0, x.a0, x.v_max, x.v_min, x.a_max, x.a_min, x.j_max);
+        else if (kind == K_POS2) position_brake_second_order(br, x.v0, x.v_max, x.v_min, x.a_max, x.a_min);
+        else if (kind == K_VEL3) velocity_brake_third_order(br, x.a0, x.a_max, x.a_min, x.j_max);
+        if (ci == RK_POSITION) { pf_store = x.pf; vf_store = x.vf; af_store = x.af; }
+        else if (ci == RK_VELOCITY) { vf_store = x.vf; af_store = x.af; }
+        bt0 = br.t[0]; bt1 = br.t[1]; bj0 = br.j[0]; bj1 = br.j[1];
+        if (kind == K_POS3 || kind == K_VEL3) {  // brake.rs:195-220
+            if (!(bt0 <= 0.0 && bt1 <= 0.0)) {
+                bdur = bt0;
+                bp0 = ps; bv0 = vs; ba0 = as;
+                integrate(bt0, ps, vs, as, bj0, ps, vs, as);
+                if (bt1 > 0.0) {
+                    bdur += bt1;
+                    bp1 = ps; bv1 = vs; ba1 = as;
+                    integrate(bt1, ps, vs, as, bj1, ps, vs, as);
+                }
+            }
+        } else if (kind == K_POS2) {  // brake.rs:222-235
+            ba0 = br.a0;
+            if (!(bt0 <= 0.0)) {
+                bdur = bt0;
+                bp0 = ps; bv0 = vs;
+                integrate(bt0, ps, vs, ba0, 0.0, ps, vs, as);
+            }
+        }
+
+        const Bound b{ps, vs, as, x.pf, x.vf, x.af};
+        if (kind == K_POS3 && !(x.j_max == 0.0 || x.a_max == 0.0 || x.a_min == 0.0)) {
+            meta |= M_S1_PENDING;  // the three family kernels and k1_block take over
+        } else {
+            switch (kind) {
+                case K_POS3: found = step1_pos3_zero_limits(b, x.v_max, x.v_min, x.a_max, x.a_min, x.j_max, bdur, blk); break;
+                case K_POS2: found = step1_pos2(b, x.v_max, x.v_min, x.a_max, x.a_min, bdur, blk); break;
+                case K_POS1: found = step1_pos1(b, x.v_max, x.v_min, bdur, blk); break;
+                case K_VEL3: found = step1_vel3(b, x.a_max, x.a_min, x.j_max, bdur, blk); break;
+                case K_VEL2: found = step1_vel2(b, x.a_max, x.a_min, bdur, blk); break;
+                default: found = false; break;
+            }
+        }
+    }
+
+    double* w = P.ws + wi;
+    w[(int64_t)W_P0 * wstride] = ps; w[(int64_t)W_V0 * wstride] = vs; w[(int64_t)W_A0 * wstride] = as;
+    w[(int64_t)W_BRAKE_DUR * wstride] = bdur;
+    if (!(meta & M_S1_PENDING)) {
+        write_block(P, wi, wstride, blk, found, meta);
+        P.imd[(int64_t)d * P.n + ig] = found ? blk.t_min : 0.0;
+    }
+    P.wmeta[(int64_t)WM_META * wstride + wi] = meta;
+    P.wmeta[(int64_t)WM_VINFO * wstride + wi] = 0u;
+    P.wmeta[(int64_t)WM_VCODES * wstride + wi] = 0u;
+
+    // the parts of the final Profile that do not depend on the later stages
+    out.put(S_BRAKE_DUR, bdur);
+    out.put(S_BRAKE_T, bt0); out.put(S_BRAKE_T + 1, bt1);
+    out.put(S_BRAKE_J, bj0); out.put(S_BRAKE_J + 1, bj1);
+    out.put(S_BRAKE_A, ba0); out.put(S_BRAKE_A + 1, ba1);
+    out.put(S_BRAKE_V, bv0); out.put(S_BRAKE_V + 1, bv1);
+    out.put(S_BRAKE_P, bp0); out.put(S_BRAKE_P + 1, bp1);
+    out.put(S_PF, pf_store); out.put(S_VF, vf_store); out.put(S_AF, af_store);
+}
+
+// ------------------------------------------------------------------------------------------------ k1_family
+// F = 0: NONE / ACC0 / ACC1 quartics, 1: ACC0_ACC1, 2: the VEL family (position_third_step1.rs:329-601, :241-327, :97-240).
+// General items append to their list in the reference's enumeration order; rest-target items (vf ~ 0 && af ~ 0) run the
+// same code with first direction = sign(pd) and park the first hit of stage 2F + k in slot 2F + k (k1_block picks by the
+// reference's priority).
+template <int F>
+__global__ void __launch_bounds__(128) k1_family(const Params P) {
+    const int64_t wstride = (int64_t)P.dof * P.cn;
+    const int64_t wi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (wi >= wstride) return;
+    const uint32_t meta = P.wmeta[(int64_t)WM_META * wstride + wi];
+    if (!(meta & M_S1_PENDING)) return;
+    const int d = (int)(wi / P.cn);
+    const int64_t ig = P.off + (wi - (int64_t)d * P.cn);
+    const DofIn x = load_dof(P, d, ig);
+    const double* w = P.ws + wi;
+    const Bound b{w[(int64_t)W_P0 * wstride], w[(int64_t)W_V0 * wstride], w[(int64_t)W_A0 * wstride], x.pf, x.vf, x.af};
+
+    Step1Pos3 s;
+    s.init(b, x.j_max);
+    const bool rest_target = fabs(b.vf) < EPS && fabs(b.af) < EPS;
+    const bool d_up = s.pd >= 0.0;
+    const bool trivial = rest_target && fabs(b.v0) < EPS && fabs(b.a0) < EPS && fabs(s.pd) < EPS;
+    s.first_only = rest_target;
+    if (trivial && F > 0) return;  // :1015-1025 only the quartics of the first direction are tried
+
+    uint32_t vinfo = P.wmeta[(int64_t)WM_VINFO * wstride + wi];
+    uint32_t vcodes = P.wmeta[(int64_t)WM_VCODES * wstride + wi];
+    int count = vinfo & 7;
+    const int count0 = count;
+    s.count = count;
+
+#pragma unroll 1
+    for (int k = 0; k < 2; ++k) {
+        if (trivial && k > 0) break;
+        const bool up = rest_target ? ((k == 0) == d_up) : (k == 0);
+        const Lim L = lim_dir(up, x.v_max, x.v_min, x.a_max, x.a_min, x.j_max);
+        if (rest_target) s.count = 0;
+        if (F == 0) s.family_quartics(L);
+        else if (F == 1) s.family_acc0_acc1(L);
+        else s.family_vel(L);
+        if (rest_target && s.count > 0) {
+            const int slot = 2 * F + k;
+            vlist_put(P, wi, wstride, slot, s.vp[0]);
+            vcodes |= vcode_of(s.vp[0]) << (4 * slot);
+            vinfo |= 1u << (8 + slot);
+        }
+    }
+    if (!rest_target) {
+        count = s.count;
+        for (int c = count0; c < count; ++c) {
+            vlist_put(P, wi, wstride, c, s.vp[c]);
+            vcodes |= vcode_of(s.vp[c]) << (4 * c);
+        }
+        vinfo = (vinfo & ~7u) | (uint32_t)count;
+    }
+    P.wmeta[(int64_t)WM_VINFO * wstride + wi] = vinfo;
+    P.wmeta[(int64_t)WM_VCODES * wstride + wi] = vcodes;
+}
+
+// ------------------------------------------------------------------------------------------------ k1_block
+__global__ void __launch_bounds__(128) k1_block(const Params P) {
+    const int64_t wstride = (int64_t)P.dof * P.cn;
+    const int64_t wi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (wi >= wstride) return;
+    uint32_t meta = P.wmeta[(int64_t)WM_META * wstride + wi];
+    if (!(meta & M_S1_PENDING)) return;
+    const int d = (int)(wi / P.cn);
+    const int64_t ig = P.off + (wi - (int64_t)d * P.cn);
+    const uint32_t vinfo = P.wmeta[(int64_t)WM_VINFO * wstride + wi];
+    const uint32_t vcodes = P.wmeta[(int64_t)WM_VCODES * wstride + wi];
+    const double* w = P.ws + wi;
+    const double bdur = w[(int64_t)W_BRAKE_DUR * wstride];
+
+    Cand vp[6];
+    int count = vinfo & 7;
+    const uint32_t have = (vinfo >> 8) & 0x3Fu;
+    if (have) {  // rest-target schedule: priority VEL(d), quartics(d), ACC0_ACC1(d), then the same for -d (:1026-1089)
+        const int order[6] = {4, 0, 2, 5, 1, 3};
+        int pick = -1;
+#pragma unroll
+        for (int q = 0; q < 6; ++q)
+            if (pick < 0 && (have & (1u << order[q]))) pick = order[q];
+        vlist_get(P, wi, wstride, pick, vcodes, vp[0]);
+        count = 1;
+    } else {
+        for (int c = 0; c < count; ++c) vlist_get(P, wi, wstride, c, vcodes, vp[c]);
+    }
+
+    if (count == 0) {
+        // :1142-1255 — numerical rescues; the first one that yields a candidate wins
+        const DofIn x = load_dof(P, d, ig);
+        const Bound b{w[(int64_t)W_P0 * wstride], w[(int64_t)W_V0 * wstride], w[(int64_t)W_A0 * wstride], x.pf, x.vf, x.af};
+        Step1Pos3 s;
+        s.init(b, x.j_max);
+        s.first_only = false;
+#pragma unroll 1
+        for (int k = 0; k < 8 && s.count == 0; ++k) {
+            const Lim L = lim_dir((k & 1) == 0, x.v_max, x.v_min, x.a_max, x.a_min, x.j_max);
+            if (k < 2) s.rescue_none(L);
+            else if (k < 4) s.rescue_acc0(L);
+            else if (k < 6) s.rescue_vel(L);
+            else s.rescue_acc1_vel(L);
+        }
+        count = s.count;
+        for (int c = 0; c < count; ++c) vp[c] = s.vp[c];
+    }
+
+    BlockRec blk;
+    blk.a_left = 0.0; blk.a_right = 0.0; blk.b_left = 0.0; blk.b_right = 0.0; blk.t_min = 0.0;
+    const bool found = calculate_block(blk, vp, count, bdur);
+    meta &= ~M_S1_PENDING;
+    write_block(P, wi, wstride, blk, found, meta);
+    P.wmeta[(int64_t)WM_META * wstride + wi] = meta;
+    P.imd[(int64_t)d * P.n + ig] = found ? blk.t_min : 0.0;
+}
+
+// ------------------------------------------------------------------------------------------------ k_sync
+// block.rs:157-172
+__device__ __forceinline__ bool is_blocked(double t, double t_min, bool has_a, double a_left, double a_right, bool has_b, double b_left, double b_right) {
+    if (t < t_min) return true;
+    if (has_a && t > a_left && t < a_right) return true;
+    if (has_b && t > b_left && t < b_right) return true;
+    return false;
+}
+
+__global__ void __launch_bounds__(128) k_sync(const Params P) {
+    const int64_t il = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (il >= P.cn) return;
+    const int64_t ig = P.off + il;
+    const int D = P.dof;
+    const int64_t wstride = (int64_t)D * P.cn;
+    const double* W = P.ws;
+#define WS(slot, d) W[(int64_t)(slot) * wstride + (int64_t)(d) * P.cn + il]
+#define META(d) P.wmeta[(int64_t)(d) * P.cn + il]
+#define SRC(d) P.wsrc[(int64_t)(d) * P.cn + il]
+
+    for (int d = 0; d < D; ++d) SRC(d) = RK_SRC_NONE;
+    int status = RK_RESULT_WORKING;
+    int detail = 0;
+    double duration = 0.0;
+    int limiting = -1;
+
+    // Err(ValidationError): first failing DoF (input_parameter.rs:251-420), then the delta_time rule (ruckig.rs:161-168)
+    if (P.throw_mode) {
+        for (int d = 0; d < D && status == 0; ++d) {
+            const uint32_t vc = (META(d) >> M_VCODE_SHIFT) & 0xFFu;
+            if (vc) { status = RK_RESULT_ERROR_INVALID_INPUT; detail = (int)(vc << 8) | d; }
+        }
+        if (status == 0 && P.delta_time <= 0.0 && P.discrete) { status = RK_RESULT_ERROR_INVALID_INPUT; detail = RK_INVALID_DELTA_TIME << 8; }
+    }
+    // Step-1 failure: lowest DoF index decides (calculator_target.rs:454-471)
+    if (status == 0) {
+        for (int d = 0; d < D && status == 0; ++d) {
+            const uint32_t m = META(d);
+            if ((m & M_ENABLED) && !(m & M_FOUND)) {
+                status = (m & M_ZERO_LIMITS) ? RK_RESULT_ERROR_ZERO_LIMITS : RK_RESULT_ERROR_EXECUTION_TIME_CALCULATION;
+                detail = (1 << 8) | d;
+            }
+        }
+    }
+
+    const double md_raw = P.min_dur ? P.min_dur[ig] : __longlong_as_double(0x7ff8000000000000LL);
+    const bool has_md = md_raw == md_raw;
+    const double md = has_md ? md_raw : 0.0;
+
+    bool done = status != 0;
+    if (!done && D == 1 && !has_md && !P.discrete) {  // :475-481
+        duration = WS(W_TMIN, 0);
+        if (META(0) & M_ENABLED) SRC(0) = RK_SRC_STEP1_MIN;
+        done = true;
+    }
+
+    if (!done) {
+        // ---- synchronize (:150-275)
+        double cand[3 * RK_MAX_DOF + 1];
+        int16_t idx[3 * RK_MAX_DOF + 1];
+        const int NC = 3 * D + 1;
+        bool any_interval = false;
+        for (int d = 0; d < D; ++d) {
+            if (P.sync[d] == RK_SYNC_NONE) {
+                cand[d] = 0.0; cand[D + d] = RK_INF; cand[2 * D + d] = RK_INF;
+                continue;
+            }
+            const uint32_t m = META(d);
+            cand[d] = WS(W_TMIN, d);
+            cand[D + d] = (m & M_HAS_A) ? WS(W_ARIGHT, d) : RK_INF;
+            cand[2 * D + d] = (m & M_HAS_B) ? WS(W_BRIGHT, d) : RK_INF;
+            any_interval |= (m & (M_HAS_A | M_HAS_B)) != 0;
+        }
+        cand[3 * D] = has_md ? md : RK_INF;
+        any_interval |= has_md;
+
+        if (P.discrete) {
+            for (int i = 0; i < NC; ++i) {
+                if (isinf(cand[i])) continue;
+                const double remainder = fmod(cand[i], P.delta_time);
+                if (remainder > EPS) cand[i] += P.delta_time - remainder;
+            }
+        }
+
+        const int idx_end = any_interval ? NC : D;
+        for (int i = 0; i < NC; ++i) idx[i] = (i < idx_end) ? (int16_t)i : (int16_t)0;  // fresh scratch: the tail is zero (Q4)
+        for (int i = 1; i < idx_end; ++i) {  // stable insertion sort == slice::sort_by
+            const int16_t key = idx[i];
+            const double kv = cand[key];
+            int k = i - 1;
+            while (k >= 0 && cand[idx[k]] > kv) { idx[k + 1] = idx[k]; --k; }
+            idx[k + 1] = key;
+        }
+
+        bool found_sync = false;
+        int which = -1;
+        for (int k = D - 1; k < NC && !found_sync; ++k) {
+            const int i = idx[k];
+            const double ts = cand[i];
+            bool blocked = false;
+            for (int d = 0; d < D && !blocked; ++d) {
+                if (P.sync[d] == RK_SYNC_NONE) continue;
+                const uint32_t m = META(d);
+                blocked = is_blocked(ts, WS(W_TMIN, d), (m & M_HAS_A) != 0, WS(W_ALEFT, d), WS(W_ARIGHT, d), (m & M_HAS_B) != 0, WS(W_BLEFT, d), WS(W_BRIGHT, d));
+            }
+            if (blocked || ts < (has_md ? md : 0.0) || isinf(ts)) continue;
+            duration = ts;
+            found_sync = true;
+            which = i;
+        }
+
+        if (!found_sync) {  // :492-518
+            bool zero_limits = false;
+            for (int d = 0; d < D; ++d) zero_limits |= (META(d) & M_ZERO_LIMITS) != 0;
+            status = zero_limits ? RK_RESULT_ERROR_ZERO_LIMITS : RK_RESULT_ERROR_SYNCHRONIZATION_CALCULATION;
+            detail = 2 << 8;
+            done = true;
+        } else {
+            if (which != 3 * D) {
+                limiting = which % D;
+                SRC(limiting) = (uint8_t)(which / D);  // 0 p_min, 1 a.profile, 2 b.profile
+            }
+            // None synchronisation (:520-528)
+            for (int d = 0; d < D; ++d) {
+                if ((META(d) & M_ENABLED) && P.sync[d] == RK_SYNC_NONE) {
+                    SRC(d) = RK_SRC_STEP1_MIN;
+                    const double tm = WS(W_TMIN, d);
+                    if (tm > duration) { duration = tm; limiting = d; }
+                }
+            }
+            if (duration > 7.6e3) {  // :531-533
+                status = RK_RESULT_ERROR_TRAJECTORY_DURATION;
+                done = true;
+            } else if (fabs(duration - 0.0) < EPS) {  // :535-541
+                for (int d = 0; d < D; ++d) SRC(d) = (META(d) & M_ENABLED) ? RK_SRC_STEP1_MIN : RK_SRC_NONE;
+                done = true;
+            } else {
+                bool all_none = true, any_phase = false, all_phase_or_none = true;
+                for (int d = 0; d < D; ++d) {
+                    const int s = P.sync[d];
+                    all_none &= (s == RK_SYNC_NONE);
+                    any_phase |= (s == RK_SYNC_PHASE);
+                    all_phase_or_none &= (s == RK_SYNC_PHASE || s == RK_SYNC_NONE);
+                }
+                if (!P.discrete && all_none) done = true;  // :543-550
+
+                // ---- phase synchronisation (:552-711, is_input_collinear :60-148)
+                if (!done && limiting >= 0 && any_phase) {
+                    double lt[7], lctrl, lctrl2;
+                    uint32_t lcodes;
+                    ws_get_cand(P, (int64_t)limiting * P.cn + il, wstride, SRC(limiting), lt, lctrl, lctrl2, lcodes);
+                    const int l_lim = lcodes & 0xFF, l_cs = (lcodes >> 8) & 0xFF, l_dir = (lcodes >> 16) & 0xFF;
+
+                    // scale vector selection
+                    int scale_dof = -1, scale_vec = -1;  // 0 pd, 1 v0, 2 a0, 3 vf, 4 af
+                    for (int d = 0; d < D && scale_dof < 0; ++d) {
+                        if (P.sync[d] != RK_SYNC_PHASE) continue;
+                        const DofIn x = load_dof(P, d, ig);
+                        const double pd = x.pf - x.p0;
+                        if (P.ci[d] == RK_POSITION && fabs(pd) > EPS) { scale_vec = 0; scale_dof = d; }
+                        else if (fabs(x.v0) > EPS) { scale_vec = 1; scale_dof = d; }
+                        else if (fabs(x.a0) > EPS) { scale_vec = 2; scale_dof = d; }
+                        else if (fabs(x.vf) > EPS) { scale_vec = 3; scale_dof = d; }
+                        else if (fabs(x.af) > EPS) { scale_vec = 4; scale_dof = d; }
+                    }
+                    bool collinear = scale_dof >= 0;
+                    double pd_scale = 0.0, v0_scale = 0.0, vf_scale = 0.0, a0_scale = 0.0, af_scale = 0.0, scale_limiting = 0.0, control_limiting = 0.0;
+                    auto pick = [&](const DofIn& x) {
+                        return scale_vec == 0 ? (x.pf - x.p0) : (scale_vec == 1 ? x.v0 : (scale_vec == 2 ? x.a0 : (scale_vec == 3 ? x.vf : x.af)));
+                    };
+                    if (collinear) {
+                        const DofIn xs = load_dof(P, scale_dof, ig);
+                        const double scale = pick(xs);
+                        pd_scale = (xs.pf - xs.p0) / scale;
+                        v0_scale = xs.v0 / scale;
+                        vf_scale = xs.vf / scale;
+                        a0_scale = xs.a0 / scale;
+                        af_scale = xs.af / scale;
+                        const DofIn xl = load_dof(P, limiting, ig);
+                        scale_limiting = pick(xl);
+                        control_limiting = (l_dir == DIR_UP) ? xl.j_max : -xl.j_max;
+                        if (isinf(xl.j_max)) control_limiting = (l_dir == DIR_UP) ? xl.a_max : xl.a_min;
+                        for (int d = 0; d < D && collinear; ++d) {
+                            if (P.sync[d] != RK_SYNC_PHASE) continue;
+                            const DofIn x = load_dof(P, d, ig);
+                            const double cs_ = pick(x);
+                            if ((P.ci[d] == RK_POSITION && fabs((x.pf - x.p0) - pd_scale * cs_) > EPS) || fabs(x.v0 - v0_scale * cs_) > EPS
+                                || fabs(x.a0 - a0_scale * cs_) > EPS || fabs(x.vf - vf_scale * cs_) > EPS || fabs(x.af - af_scale * cs_) > EPS)
+                                collinear = false;
+                        }
+                    }
+                    if (collinear && all_phase_or_none) {
+                        // Pass 0 validates every phase DoF with the limiting DoF's timing; only if all pass (and every DoF is
+                        // Phase or None, :701-708) pass 1 commits the scaled profiles. Otherwise nothing is kept: the
+                        // reference overwrites its partial results in the time-synchronisation loop.
+                        bool found_phase = true;
+                        for (int pass = 0; pass < 2 && found_phase; ++pass) {
+                            for (int d = 0; d < D; ++d) {
+                                const uint32_t m = META(d);
+                                if (!(m & M_ENABLED) || d == limiting || P.sync[d] != RK_SYNC_PHASE) continue;
+                                const DofIn x = load_dof(P, d, ig);
+                                const double npc = control_limiting * pick(x) / scale_limiting;
+                                int kind = m & M_KIND_MASK;
+                                // the reference routes a first-order DoF with a UDUD limiting profile to the second-order check (:629-641)
+                                if (kind == K_POS1 && l_cs == UDUD) kind = K_POS2;
+                                int dir = DIR_UP;
+                                switch (kind) {
+                                    case K_POS3: case K_POS2: dir = (x.v_max > 0.0) ? DIR_UP : DIR_DOWN; break;
+                                    case K_VEL3: dir = (x.a_max > 0.0) ? DIR_UP : DIR_DOWN; break;
+                                    default: dir = (npc > 0.0) ? DIR_UP : DIR_DOWN; break;
+                                }
+                                if (pass == 0) {
+                                    const Bound b{WS(W_P0, d), WS(W_V0, d), WS(W_A0, d), x.pf, x.vf, x.af};
+                                    bool ok = true;
+                                    switch (kind) {
+                                        case K_POS3: {
+                                            const Lim L{x.v_max, x.v_min, x.a_max, x.a_min, x.j_max};
+                                            ok = check_pos3_full(lt, l_cs, L_NONE, npc, L, b, x.j_max);
+                                            break;
+                                        }
+                                        case K_POS2:
+                                            ok = (x.a_min - A_EPS < npc) && (npc < x.a_max + A_EPS) && (x.a_min - A_EPS < -npc) && (-npc < x.a_max + A_EPS)
+                                                 && check_pos2(lt, l_cs, npc, -npc, x.v_max, x.v_min, b);
+                                            break;
+                                        case K_POS1: ok = (x.v_min - V_EPS < npc) && (npc < x.v_max + V_EPS) && check_pos1(lt, npc, b); break;
+                                        case K_VEL3: ok = (fabs(npc) < fabs(x.j_max) + J_EPS) && check_vel3(lt, l_cs, L_NONE, npc, x.a_max, x.a_min, b); break;
+                                        case K_VEL2: ok = (x.a_min - A_EPS < npc) && (npc < x.a_max + A_EPS) && check_vel2(lt, npc, b); break;
+                                        default: break;
+                                    }
+                                    found_phase &= ok;
+                                } else {
+                                    // slot 2 (the b-profile) of this DoF is free now: the trajectory is decided
+                                    Cand c;
+                                    copy_t(c.t, lt);
+                                    c.ctrl = npc; c.ctrl2 = -npc; c.lim = l_lim; c.cs = l_cs; c.dir = dir; c.dur = 0.0;
+                                    const int64_t wd = (int64_t)d * P.cn + il;
+                                    ws_put_cand(P, wd, wstride, 2, c);
+                                    P.wmeta[(int64_t)3 * wstride + wd] |= (uint32_t)(kind + 1) << 24;  // kind the profile is expanded with
+                                    SRC(d) = RK_SRC_PHASE;
+                                }
+                            }
+                        }
+                        if (found_phase) done = true;
+                    }
+                }
+
+                // ---- time synchronisation dispatch (:714-747)
+                if (!done) {
+                    for (int d = 0; d < D; ++d) {
+                        const uint32_t m = META(d);
+                        const bool skip = (d == limiting || P.sync[d] == RK_SYNC_NONE) && !P.discrete;
+                        if (!(m & M_ENABLED) || skip) continue;
+                        const double t_profile = duration - WS(W_BRAKE_DUR, d) - 0.0;
+                        if (P.sync[d] == RK_SYNC_TIME_IF_NECESSARY) {
+                            const DofIn x = load_dof(P, d, ig);
+                            if (fabs(x.vf) < EPS && fabs(x.af) < EPS) { SRC(d) = RK_SRC_STEP1_MIN; continue; }
+                        }
+                        // extremal profile re-use; b is only looked at when a is absent (Q3), i.e. never (b implies a)
+                        if (fabs(t_profile - WS(W_TMIN, d)) < 2.0 * EPS) { SRC(d) = RK_SRC_STEP1_MIN; continue; }
+                        if (m & M_HAS_A) {
+                            if (fabs(t_profile - WS(W_ARIGHT, d)) < 2.0 * EPS) { SRC(d) = RK_SRC_STEP1_A; continue; }
+                        } else if (m & M_HAS_B) {
+                            if (fabs(t_profile - WS(W_BRIGHT, d)) < 2.0 * EPS) { SRC(d) = RK_SRC_STEP1_B; continue; }
+                        }
+                        SRC(d) = RK_SRC_STEP2;
+                    }
+                }
+            }
+        }
+    }
+    P.status[ig] = status;
+    P.duration[ig] = duration;
+    P.limiting[ig] = limiting;
+    P.detail[ig] = detail;
+#undef WS
+#undef META
+#undef SRC
+}
+
+// ------------------------------------------------------------------------------------------------ Step-2 chain
+struct ItemS2 {
+    DofIn x;
+    Bound b;
+    double tf;
+    int d;
+    int64_t ig, gi;
+};
+
+__device__ __forceinline__ ItemS2 load_item_s2(const Params& P, int64_t wi, int64_t wstride) {
+    ItemS2 it;
+    it.d = (int)(wi / P.cn);
+    it.ig = P.off + (wi - (int64_t)it.d * P.cn);
+    it.gi = (int64_t)it.d * P.n + it.ig;
+    it.x = load_dof(P, it.d, it.ig);
+    const double* w = P.ws + wi;
+    it.b = Bound{w[(int64_t)W_P0 * wstride], w[(int64_t)W_V0 * wstride], w[(int64_t)W_A0 * wstride], it.x.pf, it.x.vf, it.x.af};
+    it.tf = P.duration[it.ig] - w[(int64_t)W_BRAKE_DUR * wstride] - 0.0;  // :723 (accel duration is always 0)
+    return it;
+}
+
+// One stage of the chain position_third_step2.rs:2449-2482 for one item. stage = 4 * group + family slot; groups 0, 2 use the
+// first direction (up_first = pd > tf * v0), groups 1, 3 the other one.
+template <int F>
+__device__ __forceinline__ bool run_family(const S2& s, const Lim& L, Hit& h) {
+    if (F == 0) return s2_acc0_acc1_vel(s, L, h);
+    if (F == 1) return s2_vel(s, L, h);
+    if (F == 2) return s2_acc0_vel(s, L, h);
+    if (F == 3) return s2_acc1_vel(s, L, h);
+    if (F == 4) return s2_acc0_acc1(s, L, h);
+    if (F == 5) return s2_acc0(s, L, h);
+    if (F == 6) return s2_acc1(s, L, h);
+    return s2_none(s, L, h);
+}
+
+template <int F>
+__device__ __forceinline__ bool run_stage(const Params& P, const ItemS2& it, bool second_direction) {
+    S2 s;
+    s.init(it.b, it.tf, it.x.j_max);
+    const bool up_first = s.pd > it.tf * it.b.v0;
+    const Lim L = lim_dir(up_first != second_direction, it.x.v_max, it.x.v_min, it.x.a_max, it.x.a_min, it.x.j_max);
+    Hit h;
+    if (!run_family<F>(s, L, h)) return false;
+    ProfileSink out{P.prof, (int64_t)P.dof * P.n, it.gi};
+    store_profile(out, K_POS3, h.t, h.jf, 0.0, h.cs, h.lim, it.b.p0, it.b.v0, it.b.a0, it.x.vf, it.x.af);
+    P.codes[it.gi] = pack_codes(h.lim, h.cs, h.dir, RK_SRC_STEP2);
+    return true;
+}
+
+// Append the items of this warp that are still unsolved to the next list (one atomic per warp).
+__device__ __forceinline__ void append_unsolved(uint32_t* list, uint32_t* counter, bool unsolved, uint32_t item) {
+    const unsigned mask = __ballot_sync(0xffffffffu, unsolved);
+    if (mask == 0) return;
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(mask) - 1;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(counter, (uint32_t)__popc(mask));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (unsolved) list[base + __popc(mask & ((1u << lane) - 1u))] = item;
+}
+
+__device__ __forceinline__ void report_step2_failure(const Params& P, int d, int64_t ig) {
+    P.status[ig] = RK_RESULT_ERROR_EXECUTION_TIME_CALCULATION;  // :819-826; every failing DoF stores the same value
+    const int mine = (3 << 8) | d;                              // the lowest failing DoF index is kept in the detail word
+    int seen = P.detail[ig];
+    while (seen == 0 || mine < seen) {
+        const int prev = atomicCAS(&P.detail[ig], seen, mine);
+        if (prev == seen) break;
+        seen = prev;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ k2_first
+// Every item: profiles that need no chain are expanded and stored (re-used extremal profile, phase-synchronised profile,
+// disabled DoF, the cheap non-third-order Step 2 variants); third-order position items that need Step 2 run stage 0.
+__global__ void __launch_bounds__(128) k2_first(const Params P) {
+    const int64_t wstride = (int64_t)P.dof * P.cn;
+    const int64_t wi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool unsolved = false;
+    if (wi < wstride) {
+        const uint32_t meta = P.wmeta[(int64_t)WM_META * wstride + wi];
+        const int kind = meta & M_KIND_MASK;
+        const int src = P.wsrc[wi];
+        const ItemS2 it = load_item_s2(P, wi, wstride);
+        ProfileSink out{P.prof, (int64_t)P.dof * P.n, it.gi};
+        if (src == RK_SRC_NONE || kind == K_NONE) {
+            // disabled DoF (calculator_target.rs:313-323) or a trajectory that ended with an error status
+            store_idle_profile(out, it.x.p0, it.x.v0, it.x.a0);
+            P.codes[it.gi] = pack_codes(L_NONE, UDDU, DIR_UP, RK_SRC_NONE);
+        } else if (src == RK_SRC_STEP2 && kind == K_POS3) {
+            unsolved = !run_stage<0>(P, it, false);
+        } else {
+            double t[7], ctrl, ctrl2;
+            int lim, cs, dir, lim_check, store_kind = kind;
+            bool pf_from_p7 = false, ok = true;
+            if (src == RK_SRC_STEP2) {
+                Cand c;
+                if (kind == K_POS2) { ok = step2_pos2(it.b, it.tf, it.x.v_max, it.x.v_min, it.x.a_max, it.x.a_min, c); pf_from_p7 = true; }
+                else if (kind == K_POS1) ok = step2_pos1(it.b, it.tf, c);
+                else if (kind == K_VEL3) { ok = step2_vel3(it.b, it.tf, it.x.a_max, it.x.a_min, it.x.j_max, c); pf_from_p7 = true; }
+                else { ok = step2_vel2(it.b, it.tf, it.x.a_max, it.x.a_min, c); pf_from_p7 = true; }
+                copy_t(t, c.t);
+                ctrl = c.ctrl; ctrl2 = c.ctrl2; lim = c.lim; cs = c.cs; dir = c.dir;
+                lim_check = lim;
+            } else {
+                const int slot = (src == RK_SRC_PHASE) ? 2 : src;
+                uint32_t c;
+                ws_get_cand(P, wi, wstride, slot, t, ctrl, ctrl2, c);
+                lim = c & 0xFF; cs = (c >> 8) & 0xFF; dir = (c >> 16) & 0xFF;
+                lim_check = lim;
+                if (src == RK_SRC_PHASE) {  // validated with ReachedLimits::None, labelled with the limiting DoF's limits (Q25)
+                    lim_check = L_NONE;
+                    store_kind = (int)(c >> 24) - 1;
+                }
+            }
+            if (ok) {
+                const double p7 = store_profile(out, store_kind, t, ctrl, ctrl2, cs, lim_check, it.b.p0, it.b.v0, it.b.a0, it.x.vf, it.x.af);
+                if (pf_from_p7) out.put(S_PF, p7);
+                P.codes[it.gi] = pack_codes(lim, cs, dir, src);
+            } else {
+                report_step2_failure(P, it.d, it.ig);
+                store_idle_profile(out, 0.0, 0.0, 0.0);
+                P.codes[it.gi] = pack_codes(L_NONE, UDDU, DIR_UP, RK_SRC_STEP2);
+            }
+        }
+    }
+    append_unsolved(P.list[1], P.counters + 1, unsolved, (uint32_t)wi);
+}
+
+// ------------------------------------------------------------------------------------------------ k2_stage
+template <int F>
+__global__ void __launch_bounds__(128) k2_stage(const Params P, int stage) {
+    const int64_t wstride = (int64_t)P.dof * P.cn;
+    const uint32_t* list_in = P.list[stage & 1];
+    uint32_t* list_out = P.list[(stage + 1) & 1];
+    const uint32_t count = P.counters[stage];
+    const bool second_direction = ((stage >> 2) & 1) != 0;
+    // whole warps iterate together so that the ballot in append_unsolved sees all 32 lanes
+    const uint32_t stride = gridDim.x * blockDim.x;
+    const uint32_t rounds = (count + stride - 1) / stride;
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    for (uint32_t r = 0; r < rounds; ++r, k += stride) {
+        bool unsolved = false;
+        uint32_t wi = 0;
+        if (k < count) {
+            wi = list_in[k];
+            const ItemS2 it = load_item_s2(P, wi, wstride);
+            unsolved = !run_stage<F>(P, it, second_direction);
+        }
+        append_unsolved(list_out, P.counters + stage + 1, unsolved, wi);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ k2_fail
+__global__ void __launch_bounds__(128) k2_fail(const Params P) {
+    const int64_t wstride = (int64_t)P.dof * P.cn;
+    const uint32_t count = P.counters[16];
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < count; k += gridDim.x * blockDim.x) {
+        const uint32_t wi = P.list[0][k];
+        const int d = (int)(wi / P.cn);
+        const int64_t ig = P.off + (wi - (int64_t)d * P.cn);
+        report_step2_failure(P, d, ig);
+        ProfileSink out{P.prof, (int64_t)P.dof * P.n, (int64_t)d * P.n + ig};
+        store_idle_profile(out, 0.0, 0.0, 0.0);
+        P.codes[(int64_t)d * P.n + ig] = pack_codes(L_NONE, UDDU, DIR_UP, RK_SRC_STEP2);
+    }
+    (void)wstride;
+}
+
+}  // namespace rk

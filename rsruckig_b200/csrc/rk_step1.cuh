@@ -496,14 +496,14 @@ __device__ __forceinline__ Lim lim_dir(bool up, double v_max, double v_min, doub
     return L;
 }
 
-// position_third_step1.rs:982-1263. bd = brake duration. Returns found; fills blk.
-__device__ __noinline__ bool step1_pos3(const Bound& b, double v_max, double v_min, double a_max, double a_min, double j_max, double bd, BlockRec& blk) {
+// The zero-limit special case of position_third_step1.rs:982-1004 (+ time_all_single_step :897-980): one
+// constant-acceleration phase. bd = brake duration. Returns found; fills blk. (The general case runs as the kernel
+// pipeline k1_family<0..2> + k1_block.)
+__device__ __noinline__ bool step1_pos3_zero_limits(const Bound& b, double v_max, double v_min, double a_max, double a_min, double j_max, double bd, BlockRec& blk) {
     Step1Pos3 s;
     s.init(b, j_max);
     blk.has_a = 0; blk.has_b = 0;
-
-    // zero-limit special case: one constant-acceleration phase (:984-1004, :897-980)
-    if (j_max == 0.0 || a_max == 0.0 || a_min == 0.0) {
+    {
         if (fabs(b.af - b.a0) > EPS) return false;
         const Lim L = lim_dir(true, v_max, v_min, a_max, a_min, j_max);
         double t[7] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
@@ -533,58 +533,6 @@ __device__ __noinline__ bool step1_pos3(const Bound& b, double v_max, double v_m
         }
         return true;
     }
-
-    const bool rest_target = fabs(b.vf) < EPS && fabs(b.af) < EPS;
-    const bool d_up = s.pd >= 0.0;
-    const bool trivial = rest_target && fabs(b.v0) < EPS && fabs(b.a0) < EPS && fabs(s.pd) < EPS;
-    s.first_only = rest_target;
-
-    if (!rest_target) {
-        // general case (:1091-1140): collect everything, in the reference's enumeration order
-#pragma unroll 1
-        for (int k = 0; k < 6; ++k) {
-            const Lim L = lim_dir((k & 1) == 0, v_max, v_min, a_max, a_min, j_max);
-            if (k < 2) s.family_quartics(L);
-            else if (k < 4) s.family_acc0_acc1(L);
-            else s.family_vel(L);
-        }
-    } else {
-        // target at rest (:1009-1090): same schedule, first direction = sign of pd; every stage is run from an
-        // empty list and the winner is chosen by the reference's priority VEL(d), quartics(d), ACC0_ACC1(d), then -d.
-        Cand found[6];
-        int have = 0;
-#pragma unroll 1
-        for (int k = 0; k < 6; ++k) {
-            if (trivial && k > 0) break;
-            const Lim L = lim_dir(((k & 1) == 0) == d_up, v_max, v_min, a_max, a_min, j_max);
-            s.count = 0;
-            if (k < 2) s.family_quartics(L);
-            else if (k < 4) s.family_acc0_acc1(L);
-            else s.family_vel(L);
-            if (s.count > 0) { found[k] = s.vp[0]; have |= (1 << k); }
-        }
-        s.count = 0;
-        const int order[6] = {4, 0, 2, 5, 1, 3};
-#pragma unroll
-        for (int q = 0; q < 6; ++q) {
-            const int k = order[q];
-            if (s.count == 0 && (have & (1 << k))) { s.vp[0] = found[k]; s.count = 1; }
-        }
-        if (s.count > 0) return calculate_block(blk, s.vp, s.count, bd);
-    }
-
-    if (s.count == 0) {
-        // :1142-1255 — first rescue that yields a candidate wins
-#pragma unroll 1
-        for (int k = 0; k < 8 && s.count == 0; ++k) {
-            const Lim L = lim_dir((k & 1) == 0, v_max, v_min, a_max, a_min, j_max);
-            if (k < 2) s.rescue_none(L);
-            else if (k < 4) s.rescue_acc0(L);
-            else if (k < 6) s.rescue_vel(L);
-            else s.rescue_acc1_vel(L);
-        }
-    }
-    return calculate_block(blk, s.vp, s.count, bd);
 }
 
 }  // namespace rk

@@ -22,7 +22,7 @@ def lib():
 def declared_symbols():
     text = open(os.path.join(ROOT, "include", "ruckig_b200.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(rk_[a-z_]+)\s*\(", text)))
+    return sorted(set(re.findall(r"\b(rk_[a-z0-9_]+)\s*\(", text)))
 
 
 def test_header_symbols_are_exported(lib):
