@@ -167,7 +167,7 @@ rk_status fail(rk_status s, const std::string& m) {
         }                                                                                               \
     } while (0)
 
-constexpr int64_t CHUNK_ITEMS = 8ll << 20;  // (DoF, trajectory) items per chunk of scratch: 8 Mi items = 2.3 GB
+constexpr int64_t CHUNK_ITEMS = 4ll << 20;  // (DoF, trajectory) items per chunk of scratch: 4 Mi items = 8.4 GB of scratch
 
 }  // namespace
 
@@ -180,6 +180,7 @@ struct rk_handle {
     double* ws = nullptr;
     uint32_t* wmeta = nullptr;
     uint8_t* wsrc = nullptr;
+    uint8_t* wcnt = nullptr;
     uint32_t* list[2] = {nullptr, nullptr};
     uint32_t* counters = nullptr;
     int sm_count = 148;
@@ -206,12 +207,13 @@ struct rk_trajectories {
 static rk_status ensure_scratch(rk_handle* h, int64_t items) {
     if (items <= h->ws_items) return RK_OK;
     if (h->ws) {
-        cudaFree(h->ws); cudaFree(h->wmeta); cudaFree(h->wsrc); cudaFree(h->list[0]); cudaFree(h->list[1]); cudaFree(h->counters);
+        cudaFree(h->ws); cudaFree(h->wmeta); cudaFree(h->wsrc); cudaFree(h->wcnt); cudaFree(h->list[0]); cudaFree(h->list[1]); cudaFree(h->counters);
         h->ws = nullptr; h->ws_items = 0;
     }
     RK_CUDA(cudaMalloc(&h->ws, sizeof(double) * rk::WS_SLOTS * items));
     RK_CUDA(cudaMalloc(&h->wmeta, sizeof(uint32_t) * rk::WM_WORDS * items));
     RK_CUDA(cudaMalloc(&h->wsrc, items));
+    RK_CUDA(cudaMalloc(&h->wcnt, 10 * items));
     RK_CUDA(cudaMalloc(&h->list[0], sizeof(uint32_t) * items));
     RK_CUDA(cudaMalloc(&h->list[1], sizeof(uint32_t) * items));
     RK_CUDA(cudaMalloc(&h->counters, sizeof(uint32_t) * 32));
@@ -311,7 +313,7 @@ rk_status rk_destroy(rk_handle* h) {
     if (!h) return RK_OK;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    if (h->ws) { cudaFree(h->ws); cudaFree(h->wmeta); cudaFree(h->wsrc); cudaFree(h->list[0]); cudaFree(h->list[1]); cudaFree(h->counters); }
+    if (h->ws) { cudaFree(h->ws); cudaFree(h->wmeta); cudaFree(h->wsrc); cudaFree(h->wcnt); cudaFree(h->list[0]); cudaFree(h->list[1]); cudaFree(h->counters); }
     if (h->stage_dev) cudaFree(h->stage_dev);
     if (h->stage_pinned) cudaFreeHost(h->stage_pinned);
     cudaStreamDestroy(h->stream);
@@ -368,7 +370,7 @@ rk_status rk_calculate_batch(rk_handle* h, const rk_batch_desc* desc, const rk_b
     if (cn_max > desc->n) cn_max = desc->n;
     st = ensure_scratch(h, cn_max * desc->dof);
     if (st != RK_OK) return st;
-    P.ws = h->ws; P.wmeta = h->wmeta; P.wsrc = h->wsrc;
+    P.ws = h->ws; P.wmeta = h->wmeta; P.wsrc = h->wsrc; P.wcnt = h->wcnt;
     P.list[0] = h->list[0]; P.list[1] = h->list[1]; P.counters = h->counters;
 
     for (int64_t off = 0; off < desc->n; off += cn_max) {
@@ -381,26 +383,32 @@ rk_status rk_calculate_batch(rk_handle* h, const rk_batch_desc* desc, const rk_b
         if (grid_list > grid_items) grid_list = grid_items;
         RK_CUDA(cudaMemsetAsync(h->counters, 0, sizeof(uint32_t) * 32, h->stream));
         rk::k1_setup<<<grid_items, 128, 0, h->stream>>>(P);
-        rk::k1_family<0><<<grid_items, 128, 0, h->stream>>>(P);
-        rk::k1_family<1><<<grid_items, 128, 0, h->stream>>>(P);
-        rk::k1_family<2><<<grid_items, 128, 0, h->stream>>>(P);
+        const unsigned grid_fam = (unsigned)((2 * items + 127) / 128);
+        rk::k1_family<0><<<grid_fam, 128, 0, h->stream>>>(P);
+        rk::k1_family<1><<<grid_fam, 128, 0, h->stream>>>(P);
+        rk::k1_family<2><<<grid_fam, 128, 0, h->stream>>>(P);
+        rk::k1_family<3><<<grid_fam, 128, 0, h->stream>>>(P);
+        rk::k1_family<4><<<grid_fam, 128, 0, h->stream>>>(P);
         rk::k1_block<<<grid_items, 128, 0, h->stream>>>(P);
         rk::k_sync<<<(unsigned)((P.cn + 127) / 128), 128, 0, h->stream>>>(P);
         rk::k2_first<<<grid_items, 128, 0, h->stream>>>(P);
-        for (int stage = 1; stage < 16; ++stage) {
-            switch (((stage >> 3) << 2) | (stage & 3)) {
-                case 0: rk::k2_stage<0><<<grid_list, 128, 0, h->stream>>>(P, stage); break;
-                case 1: rk::k2_stage<1><<<grid_list, 128, 0, h->stream>>>(P, stage); break;
-                case 2: rk::k2_stage<2><<<grid_list, 128, 0, h->stream>>>(P, stage); break;
-                case 3: rk::k2_stage<3><<<grid_list, 128, 0, h->stream>>>(P, stage); break;
-                case 4: rk::k2_stage<4><<<grid_list, 128, 0, h->stream>>>(P, stage); break;
-                case 5: rk::k2_stage<5><<<grid_list, 128, 0, h->stream>>>(P, stage); break;
-                case 6: rk::k2_stage<6><<<grid_list, 128, 0, h->stream>>>(P, stage); break;
-                default: rk::k2_stage<7><<<grid_list, 128, 0, h->stream>>>(P, stage); break;
+        static const int fam[RK_S2_STEPS] = {0, 1, 8, 2, 3, 0, 1, 8, 2, 3, 4, 5, 6, 7, 4, 5, 6, 7};
+        static const int dir2[RK_S2_STEPS] = {0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 0, 0, 0, 0, 1, 1, 1, 1};
+        for (int step = 1; step < RK_S2_STEPS; ++step) {
+            switch (fam[step]) {
+                case 0: rk::k2_stage<0><<<grid_list, 128, 0, h->stream>>>(P, step, dir2[step]); break;
+                case 1: rk::k2_stage<1><<<grid_list, 128, 0, h->stream>>>(P, step, dir2[step]); break;
+                case 2: rk::k2_stage<2><<<grid_list, 128, 0, h->stream>>>(P, step, dir2[step]); break;
+                case 3: rk::k2_stage<3><<<grid_list, 128, 0, h->stream>>>(P, step, dir2[step]); break;
+                case 4: rk::k2_stage<4><<<grid_list, 128, 0, h->stream>>>(P, step, dir2[step]); break;
+                case 5: rk::k2_stage<5><<<grid_list, 128, 0, h->stream>>>(P, step, dir2[step]); break;
+                case 6: rk::k2_stage<6><<<grid_list, 128, 0, h->stream>>>(P, step, dir2[step]); break;
+                case 7: rk::k2_stage<7><<<grid_list, 128, 0, h->stream>>>(P, step, dir2[step]); break;
+                default: rk::k2_stage<8><<<grid_list, 128, 0, h->stream>>>(P, step, dir2[step]); break;
             }
         }
         rk::k2_fail<<<(unsigned)h->sm_count, 128, 0, h->stream>>>(P);
-        h->launches += 23;
+        h->launches += 9 + RK_S2_STEPS;
     }
     RK_CUDA(cudaGetLastError());
 

@@ -27,6 +27,7 @@ struct Params {
     double* ws;       // [WS_SLOTS][dof][cn]
     uint32_t* wmeta;  // [WM_WORDS][dof][cn]
     uint8_t* wsrc;    // [dof][cn]
+    uint8_t* wcnt;    // [10][dof][cn] lengths of the Step-1 candidate sub-lists
     uint32_t* list[2];   // ping-pong work lists of item indices for the Step-2 stages, [dof * cn] each
     uint32_t* counters;  // [17] list lengths per Step-2 stage
     // trajectory storage

@@ -5,8 +5,8 @@
 // averaged 5-7 active lanes. The pipeline below keeps every kernel's code small and every warp on one solver family:
 //
 //   k1_setup            validation, brake pre-trajectory, zero-limit and non-third-order Step 1 (cheap closed forms)
-//   k1_family<0,1,2>    the three Step-1 candidate families of the third-order position interface, both directions each,
-//                       appending validated candidates to a per-item list in HBM
+//   k1_family<0..4>     the Step-1 candidate families of the third-order position interface (three quartics, ACC0_ACC1, VEL),
+//                       one thread per (direction, DoF, trajectory), validated candidates go to per-family sub-lists in HBM
 //   k1_block            candidate list -> block of feasible durations (block.rs), numerical rescues
 //   k_sync              one thread per trajectory: status, common duration, limiting DoF, phase sync, per-DoF decision
 //   k2_first            everything that needs no Step-2 chain is finalised; Step-2 items run stage 0 of the chain
@@ -25,26 +25,22 @@
 
 namespace rk {
 
-// ------------------------------------------------------------------------------------------------ candidate list in scratch
-__device__ __forceinline__ void vlist_put(const Params& P, int64_t wi, int64_t wstride, int slot, const Cand& c) {
-    double* base = P.ws + (int64_t)(W_VLIST + slot * W_VLIST_STRIDE) * wstride + wi;
-#pragma unroll
-    for (int k = 0; k < 7; ++k) base[(int64_t)k * wstride] = c.t[k];
-    base[7 * wstride] = c.ctrl;
-}
+// ------------------------------------------------------------------------------------------------ candidate sub-lists in scratch
+// Step-1 candidates of a third-order position item live in ten sub-lists, one per (family, direction slot):
+//   sub 0..5 = quartic type (NONE, ACC0, ACC1) * 2 + slot, up to 4 candidates each; sub 6,7 = ACC0_ACC1, up to 2; sub 8,9 = VEL, 1.
+// Direction slot 0 is UP for general items and sign(pd) for rest-target items (vf ~ 0 && af ~ 0). Only t[7] is stored.
+__device__ __forceinline__ int sub_slot_base(int sub) { return sub < 6 ? sub * 4 : (sub < 8 ? 24 + (sub - 6) * 2 : 28 + (sub - 8)); }
+__device__ __forceinline__ int sub_limits(int sub) { return sub < 2 ? (int)L_NONE : (sub < 4 ? (int)L_ACC0 : (sub < 6 ? (int)L_ACC1 : (sub < 8 ? (int)L_ACC0_ACC1 : (int)L_VEL))); }
 
-__device__ __forceinline__ void vlist_get(const Params& P, int64_t wi, int64_t wstride, int slot, uint32_t vcodes, Cand& c) {
-    const double* base = P.ws + (int64_t)(W_VLIST + slot * W_VLIST_STRIDE) * wstride + wi;
+__device__ __forceinline__ void sublist_get(const Params& P, int64_t wi, int64_t wstride, int sub, int k, const Lim& L, Cand& c) {
+    const double* base = P.ws + (int64_t)(W_VLIST + (sub_slot_base(sub) + k) * 7) * wstride + wi;
 #pragma unroll
-    for (int k = 0; k < 7; ++k) c.t[k] = base[(int64_t)k * wstride];
-    c.ctrl = base[7 * wstride];
+    for (int q = 0; q < 7; ++q) c.t[q] = base[(int64_t)q * wstride];
+    c.ctrl = L.j_max;
     c.ctrl2 = 0.0;
     c.dur = t_sum6(c.t);
-    const uint32_t code = (vcodes >> (4 * slot)) & 0xFu;
-    c.lim = code & 7; c.dir = (code >> 3) & 1; c.cs = UDDU;
+    c.lim = sub_limits(sub); c.dir = (L.v_max > 0.0) ? DIR_UP : DIR_DOWN; c.cs = UDDU;
 }
-
-__device__ __forceinline__ uint32_t vcode_of(const Cand& c) { return (uint32_t)c.lim | ((uint32_t)c.dir << 3); }
 
 __device__ __forceinline__ void write_block(const Params& P, int64_t wi, int64_t wstride, const BlockRec& blk, bool found, uint32_t& meta) {
     double* w = P.ws + wi;
@@ -139,8 +135,6 @@ __global__ void __launch_bounds__(128) k1_setup(const Params P) {
         P.imd[(int64_t)d * P.n + ig] = found ? blk.t_min : 0.0;
     }
     P.wmeta[(int64_t)WM_META * wstride + wi] = meta;
-    P.wmeta[(int64_t)WM_VINFO * wstride + wi] = 0u;
-    P.wmeta[(int64_t)WM_VCODES * wstride + wi] = 0u;
 
     // the parts of the final Profile that do not depend on the later stages
     out.put(S_BRAKE_DUR, bdur);
@@ -153,15 +147,17 @@ __global__ void __launch_bounds__(128) k1_setup(const Params P) {
 }
 
 // ------------------------------------------------------------------------------------------------ k1_family
-// F = 0: NONE / ACC0 / ACC1 quartics, 1: ACC0_ACC1, 2: the VEL family (position_third_step1.rs:329-601, :241-327, :97-240).
-// General items append to their list in the reference's enumeration order; rest-target items (vf ~ 0 && af ~ 0) run the
-// same code with first direction = sign(pd) and park the first hit of stage 2F + k in slot 2F + k (k1_block picks by the
-// reference's priority).
+// One thread per (direction slot, DoF, trajectory); F = 0 NONE quartic, 1 ACC0 quartic, 2 ACC1 quartic
+// (position_third_step1.rs:329-601), 3 ACC0_ACC1 (:241-327), 4 the VEL family (:97-240). Every thread validates its
+// candidates and writes the valid ones to its own sub-list; the order in which the reference would have met them is
+// restored by k1_block.
 template <int F>
 __global__ void __launch_bounds__(128) k1_family(const Params P) {
     const int64_t wstride = (int64_t)P.dof * P.cn;
-    const int64_t wi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (wi >= wstride) return;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= 2 * wstride) return;
+    const int ds = (int)(tid / wstride);
+    const int64_t wi = tid - (int64_t)ds * wstride;
     const uint32_t meta = P.wmeta[(int64_t)WM_META * wstride + wi];
     if (!(meta & M_S1_PENDING)) return;
     const int d = (int)(wi / P.cn);
@@ -169,47 +165,26 @@ __global__ void __launch_bounds__(128) k1_family(const Params P) {
     const DofIn x = load_dof(P, d, ig);
     const double* w = P.ws + wi;
     const Bound b{w[(int64_t)W_P0 * wstride], w[(int64_t)W_V0 * wstride], w[(int64_t)W_A0 * wstride], x.pf, x.vf, x.af};
+    const int sub = (F < 3) ? (F * 2 + ds) : (F == 3 ? 6 + ds : 8 + ds);
 
-    Step1Pos3 s;
+    Step1Pos3<GlobalSink> s;
     s.init(b, x.j_max);
+    s.sink.base = P.ws + (int64_t)(W_VLIST + sub_slot_base(sub) * 7) * wstride + wi;
+    s.sink.wstride = wstride;
     const bool rest_target = fabs(b.vf) < EPS && fabs(b.af) < EPS;
-    const bool d_up = s.pd >= 0.0;
     const bool trivial = rest_target && fabs(b.v0) < EPS && fabs(b.a0) < EPS && fabs(s.pd) < EPS;
     s.first_only = rest_target;
-    if (trivial && F > 0) return;  // :1015-1025 only the quartics of the first direction are tried
-
-    uint32_t vinfo = P.wmeta[(int64_t)WM_VINFO * wstride + wi];
-    uint32_t vcodes = P.wmeta[(int64_t)WM_VCODES * wstride + wi];
-    int count = vinfo & 7;
-    const int count0 = count;
-    s.count = count;
-
-#pragma unroll 1
-    for (int k = 0; k < 2; ++k) {
-        if (trivial && k > 0) break;
-        const bool up = rest_target ? ((k == 0) == d_up) : (k == 0);
+    // :1015-1025 — nothing moves: only the quartics of the first direction are tried
+    if (!(trivial && (F >= 3 || ds == 1))) {
+        const bool up = rest_target ? ((ds == 0) == (s.pd >= 0.0)) : (ds == 0);
         const Lim L = lim_dir(up, x.v_max, x.v_min, x.a_max, x.a_min, x.j_max);
-        if (rest_target) s.count = 0;
-        if (F == 0) s.family_quartics(L);
-        else if (F == 1) s.family_acc0_acc1(L);
+        if (F == 0) s.quartic_none(L);
+        else if (F == 1) s.quartic_acc0(L);
+        else if (F == 2) s.quartic_acc1(L);
+        else if (F == 3) s.family_acc0_acc1(L);
         else s.family_vel(L);
-        if (rest_target && s.count > 0) {
-            const int slot = 2 * F + k;
-            vlist_put(P, wi, wstride, slot, s.vp[0]);
-            vcodes |= vcode_of(s.vp[0]) << (4 * slot);
-            vinfo |= 1u << (8 + slot);
-        }
     }
-    if (!rest_target) {
-        count = s.count;
-        for (int c = count0; c < count; ++c) {
-            vlist_put(P, wi, wstride, c, s.vp[c]);
-            vcodes |= vcode_of(s.vp[c]) << (4 * c);
-        }
-        vinfo = (vinfo & ~7u) | (uint32_t)count;
-    }
-    P.wmeta[(int64_t)WM_VINFO * wstride + wi] = vinfo;
-    P.wmeta[(int64_t)WM_VCODES * wstride + wi] = vcodes;
+    P.wcnt[(int64_t)sub * wstride + wi] = (uint8_t)s.sink.count;
 }
 
 // ------------------------------------------------------------------------------------------------ k1_block
@@ -221,43 +196,58 @@ __global__ void __launch_bounds__(128) k1_block(const Params P) {
     if (!(meta & M_S1_PENDING)) return;
     const int d = (int)(wi / P.cn);
     const int64_t ig = P.off + (wi - (int64_t)d * P.cn);
-    const uint32_t vinfo = P.wmeta[(int64_t)WM_VINFO * wstride + wi];
-    const uint32_t vcodes = P.wmeta[(int64_t)WM_VCODES * wstride + wi];
     const double* w = P.ws + wi;
     const double bdur = w[(int64_t)W_BRAKE_DUR * wstride];
+    const DofIn x = load_dof(P, d, ig);
+    const Bound b{w[(int64_t)W_P0 * wstride], w[(int64_t)W_V0 * wstride], w[(int64_t)W_A0 * wstride], x.pf, x.vf, x.af};
+    const double pd = b.pf - b.p0;
+    const bool rest_target = fabs(b.vf) < EPS && fabs(b.af) < EPS;
+    const bool trivial = rest_target && fabs(b.v0) < EPS && fabs(b.a0) < EPS && fabs(pd) < EPS;
+
+    int cnt[10];
+#pragma unroll
+    for (int sub = 0; sub < 10; ++sub) cnt[sub] = P.wcnt[(int64_t)sub * wstride + wi];
+    Lim Ls[2];
+    Ls[0] = lim_dir(rest_target ? (pd >= 0.0) : true, x.v_max, x.v_min, x.a_max, x.a_min, x.j_max);
+    Ls[1] = lim_dir(rest_target ? !(pd >= 0.0) : false, x.v_max, x.v_min, x.a_max, x.a_min, x.j_max);
 
     Cand vp[6];
-    int count = vinfo & 7;
-    const uint32_t have = (vinfo >> 8) & 0x3Fu;
-    if (have) {  // rest-target schedule: priority VEL(d), quartics(d), ACC0_ACC1(d), then the same for -d (:1026-1089)
-        const int order[6] = {4, 0, 2, 5, 1, 3};
+    int count = 0;
+    if (rest_target) {
+        // first hit in the reference's order (:1026-1089): VEL(d), quartics(d) = NONE, ACC0, ACC1, ACC0_ACC1(d), then the same for -d
         int pick = -1;
+        for (int ds = 0; ds < 2 && pick < 0; ++ds) {
+            if (trivial && ds == 1) break;
+            const int order[5] = {8 + ds, 0 + ds, 2 + ds, 4 + ds, 6 + ds};
 #pragma unroll
-        for (int q = 0; q < 6; ++q)
-            if (pick < 0 && (have & (1u << order[q]))) pick = order[q];
-        vlist_get(P, wi, wstride, pick, vcodes, vp[0]);
-        count = 1;
+            for (int q = 0; q < 5; ++q)
+                if (pick < 0 && cnt[order[q]] > 0) pick = order[q];
+        }
+        if (pick >= 0) { sublist_get(P, wi, wstride, pick, 0, Ls[pick & 1], vp[0]); count = 1; }
     } else {
-        for (int c = 0; c < count; ++c) vlist_get(P, wi, wstride, c, vcodes, vp[c]);
+        // enumeration order of :1091-1140: quartics(UP), quartics(DOWN), ACC0_ACC1(UP), (DOWN), VEL(UP), (DOWN); five are kept (Q11)
+        const int order[10] = {0, 2, 4, 1, 3, 5, 6, 7, 8, 9};
+        for (int q = 0; q < 10 && count < 5; ++q) {
+            const int sub = order[q];
+            for (int k = 0; k < cnt[sub] && count < 5; ++k) sublist_get(P, wi, wstride, sub, k, Ls[sub & 1], vp[count++]);
+        }
     }
 
     if (count == 0) {
         // :1142-1255 — numerical rescues; the first one that yields a candidate wins
-        const DofIn x = load_dof(P, d, ig);
-        const Bound b{w[(int64_t)W_P0 * wstride], w[(int64_t)W_V0 * wstride], w[(int64_t)W_A0 * wstride], x.pf, x.vf, x.af};
-        Step1Pos3 s;
+        Step1Pos3<LocalSink> s;
         s.init(b, x.j_max);
         s.first_only = false;
 #pragma unroll 1
-        for (int k = 0; k < 8 && s.count == 0; ++k) {
+        for (int k = 0; k < 8 && s.sink.count == 0; ++k) {
             const Lim L = lim_dir((k & 1) == 0, x.v_max, x.v_min, x.a_max, x.a_min, x.j_max);
             if (k < 2) s.rescue_none(L);
             else if (k < 4) s.rescue_acc0(L);
             else if (k < 6) s.rescue_vel(L);
             else s.rescue_acc1_vel(L);
         }
-        count = s.count;
-        for (int c = 0; c < count; ++c) vp[c] = s.vp[c];
+        count = s.sink.count;
+        for (int c = 0; c < count; ++c) vp[c] = s.sink.vp[c];
     }
 
     BlockRec blk;
@@ -549,6 +539,11 @@ __global__ void __launch_bounds__(128) k_sync(const Params P) {
 }
 
 // ------------------------------------------------------------------------------------------------ Step-2 chain
+// The 16 stages of position_third_step2.rs:2449-2482, with the VEL family split into its UDDU and UDUD halves (each half
+// is a pure function of the inputs; UDUD only runs for items the UDDU half did not solve): 18 launches, families
+// 0 ACC0_ACC1_VEL, 1 VEL/UDDU, 8 VEL/UDUD, 2 ACC0_VEL, 3 ACC1_VEL, 4 ACC0_ACC1, 5 ACC0, 6 ACC1, 7 NONE.
+#define RK_S2_STEPS 18
+
 struct ItemS2 {
     DofIn x;
     Bound b;
@@ -574,7 +569,8 @@ __device__ __forceinline__ ItemS2 load_item_s2(const Params& P, int64_t wi, int6
 template <int F>
 __device__ __forceinline__ bool run_family(const S2& s, const Lim& L, Hit& h) {
     if (F == 0) return s2_acc0_acc1_vel(s, L, h);
-    if (F == 1) return s2_vel(s, L, h);
+    if (F == 1) return s2_vel_uddu(s, L, h);
+    if (F == 8) return s2_vel_udud(s, L, h);
     if (F == 2) return s2_acc0_vel(s, L, h);
     if (F == 3) return s2_acc1_vel(s, L, h);
     if (F == 4) return s2_acc0_acc1(s, L, h);
@@ -678,13 +674,14 @@ __global__ void __launch_bounds__(128) k2_first(const Params P) {
 }
 
 // ------------------------------------------------------------------------------------------------ k2_stage
+// `step` numbers the launches of the chain (0 = the stage run inside k2_first); list `step & 1` is read, the other written.
 template <int F>
-__global__ void __launch_bounds__(128) k2_stage(const Params P, int stage) {
+__global__ void __launch_bounds__(128) k2_stage(const Params P, int step, int second_dir) {
     const int64_t wstride = (int64_t)P.dof * P.cn;
-    const uint32_t* list_in = P.list[stage & 1];
-    uint32_t* list_out = P.list[(stage + 1) & 1];
-    const uint32_t count = P.counters[stage];
-    const bool second_direction = ((stage >> 2) & 1) != 0;
+    const uint32_t* list_in = P.list[step & 1];
+    uint32_t* list_out = P.list[(step + 1) & 1];
+    const uint32_t count = P.counters[step];
+    const bool second_direction = second_dir != 0;
     // whole warps iterate together so that the ballot in append_unsolved sees all 32 lanes
     const uint32_t stride = gridDim.x * blockDim.x;
     const uint32_t rounds = (count + stride - 1) / stride;
@@ -697,16 +694,16 @@ __global__ void __launch_bounds__(128) k2_stage(const Params P, int stage) {
             const ItemS2 it = load_item_s2(P, wi, wstride);
             unsolved = !run_stage<F>(P, it, second_direction);
         }
-        append_unsolved(list_out, P.counters + stage + 1, unsolved, wi);
+        append_unsolved(list_out, P.counters + step + 1, unsolved, wi);
     }
 }
 
 // ------------------------------------------------------------------------------------------------ k2_fail
 __global__ void __launch_bounds__(128) k2_fail(const Params P) {
     const int64_t wstride = (int64_t)P.dof * P.cn;
-    const uint32_t count = P.counters[16];
+    const uint32_t count = P.counters[RK_S2_STEPS];
     for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < count; k += gridDim.x * blockDim.x) {
-        const uint32_t wi = P.list[0][k];
+        const uint32_t wi = P.list[RK_S2_STEPS & 1][k];
         const int d = (int)(wi / P.cn);
         const int64_t ig = P.off + (wi - (int64_t)d * P.cn);
         report_step2_failure(P, d, ig);

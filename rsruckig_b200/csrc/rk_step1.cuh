@@ -107,13 +107,39 @@ __device__ __noinline__ bool calculate_block(BlockRec& blk, Cand* vp, int n, dou
 }
 
 // ===================================================== third-order position interface
+// Where validated candidates go: a local list (numerical rescues, zero-limit case) ...
+struct LocalSink {
+    Cand vp[6];
+    int count;
+    __device__ __forceinline__ void put(const double (&t)[7], int lim, const Lim& L) {
+        Cand& c = vp[count];
+        copy_t(c.t, t);
+        c.dur = t_sum6(t);
+        c.ctrl = L.j_max; c.ctrl2 = 0.0;
+        c.lim = lim; c.dir = (L.v_max > 0.0) ? DIR_UP : DIR_DOWN; c.cs = UDDU;
+        if (count < 5) ++count;  // the list saturates at five entries (Q11)
+    }
+};
+// ... or the per-item sub-list of one (family, direction) in HBM scratch: only t[7] is stored, the codes follow from the
+// sub-list the candidate sits in.
+struct GlobalSink {
+    double* base;     // slot 0, t[0] of this sub-list for this item
+    int64_t wstride;
+    int count;
+    __device__ __forceinline__ void put(const double (&t)[7], int, const Lim&) {
+        double* q = base + (int64_t)(count * 7) * wstride;
+#pragma unroll
+        for (int k = 0; k < 7; ++k) q[(int64_t)k * wstride] = t[k];
+        ++count;
+    }
+};
+
+template <class Sink>
 struct Step1Pos3 {
     // inputs (post-brake) and the products the reference precomputes (position_third_step1.rs:39-86)
     Bound b;
     double pd, v0_v0, vf_vf, a0_a0, a0_p3, a0_p4, af_af, af_p3, af_p4, jj;
-    // candidate list
-    Cand vp[6];
-    int count;
+    Sink sink;
     bool first_only;  // reference's return_after_found
 
     __device__ __forceinline__ void init(const Bound& bb, double j_max) {
@@ -124,18 +150,13 @@ struct Step1Pos3 {
         a0_p3 = b.a0 * a0_a0; a0_p4 = a0_a0 * a0_a0;
         af_p3 = b.af * af_af; af_p4 = af_af * af_af;
         jj = j_max * j_max;
-        count = 0;
+        sink.count = 0;
     }
 
-    // Validate t; on success append (the list saturates at five entries, Q11). Returns validity.
+    // Validate t; on success hand it to the sink. Returns validity.
     __device__ __forceinline__ bool emit(const double (&t)[7], int lim, const Lim& L) {
         if (!check_pos3(t, UDDU, lim, L.j_max, L, b)) return false;
-        Cand& c = vp[count];
-        copy_t(c.t, t);
-        c.dur = t_sum6(t);
-        c.ctrl = L.j_max; c.ctrl2 = 0.0;
-        c.lim = lim; c.dir = (L.v_max > 0.0) ? DIR_UP : DIR_DOWN; c.cs = UDDU;
-        if (count < 5) ++count;
+        sink.put(t, lim, L);
         return true;
     }
 
@@ -246,12 +267,13 @@ struct Step1Pos3 {
         }
     }
 
-    // position_third_step1.rs:329-601: three monic quartics (NONE, ACC0, ACC1), each root polished by Newton steps.
-    __device__ __forceinline__ void family_quartics(const Lim& L) {
+    // position_third_step1.rs:329-601 computes three monic quartics (NONE, ACC0, ACC1) per direction and polishes each
+    // root with Newton steps. Here each quartic is its own function (and its own kernel, one thread per direction): the
+    // three are independent of one another, and the candidate order NONE, ACC0, ACC1 is restored when the lists are read.
+    __device__ __forceinline__ void quartic_none(const Lim& L) {
         const double v0 = b.v0, a0 = b.a0, vf = b.vf, af = b.af;
         const double a_max = L.a_max, a_min = L.a_min, j_max = L.j_max;
         const double jl = j_max * j_max;  // the reference mixes this local with the member computed from the UP jerk; equal values
-
         const double h2_none = (a0_a0 - af_af) / (2.0 * j_max) + (vf - v0);
         const double h2_h2 = h2_none * h2_none;
         const double t_min_none = (a0 - af) / j_max;
@@ -259,54 +281,21 @@ struct Step1Pos3 {
         const double pn1 = -2.0 * (a0_a0 + af_af - 2.0 * j_max * (v0 + vf)) / (jl);
         const double pn2 = 4.0 * (a0_p3 - af_p3 + 3.0 * j_max * (af * vf - a0 * v0)) / (3.0 * jl * j_max) - 4.0 * pd / j_max;
         const double pn3 = -h2_h2 / (jl);
-
-        // ACC0
-        const double h3_acc0 = (a0_a0 - af_af) / (2.0 * a_max * j_max) + (vf - v0) / a_max;
-        const double t_min_acc0 = (a_max - af) / j_max;
-        const double t_max_acc0 = (a_max - a_min) / j_max;
-        const double h0_acc0 = 3.0 * (af_p4 - a0_p4)
-                               + 8.0 * (a0_p3 - af_p3) * a_max
-                               + 24.0 * a_max * j_max * (af * vf - a0 * v0)
-                               - 6.0 * a0_a0 * (a_max * a_max - 2.0 * j_max * v0)
-                               + 6.0 * af_af * (a_max * a_max - 2.0 * j_max * vf)
-                               + 12.0 * j_max * (j_max * (vf_vf - v0_v0 - 2.0 * a_max * pd) - a_max * a_max * (vf - v0));
-        const double h2_acc0 = -af_af + a_max * a_max + 2.0 * j_max * vf;
-        const double pa0 = -2.0 * a_max / j_max;
-        const double pa1 = h2_acc0 / (jl);
-        const double pa2 = 0.0;
-        const double pa3 = h0_acc0 / (12.0 * jj * jj);
-
-        // ACC1
-        const double h3_acc1 = -(a0_a0 + af_af) / (2.0 * j_max * a_min) + a_min / j_max + (vf - v0) / a_min;
-        const double t_min_acc1 = (a_min - a0) / j_max;
-        const double t_max_acc1 = (a_max - a0) / j_max;
-        const double h0_acc1 = (a0_p4 - af_p4) / 4.0
-                               + 2.0 * (af_p3 - a0_p3) * a_min / 3.0
-                               + (a0_a0 - af_af) * a_min * a_min / 2.0
-                               + j_max * (af_af * vf + a0_a0 * v0 + 2.0 * a_min * (j_max * pd - a0 * v0 - af * vf)
-                                          + a_min * a_min * (v0 + vf) + j_max * (v0_v0 - vf_vf));
-        const double h2_acc1 = a0_a0 - a0 * a_min + 2.0 * j_max * v0;
-        const double pb0 = 2.0 * (2.0 * a0 - a_min) / j_max;
-        const double pb1 = (5.0 * a0_a0 + a_min * (a_min - 6.0 * a0) + 2.0 * j_max * v0) / (jl);
-        const double pb2 = 2.0 * (a0 - a_min) * h2_acc1 / (jl * j_max);
-        const double pb3 = h0_acc1 / (jj * jj);
-
-        // Sign pre-screen of the ACC0 quartic shifted to t_min_acc0, and of the ACC1 quartic (:404-422)
-        const double m0 = pa0 + 4.0 * t_min_acc0;
-        const double m1 = pa1 + (3.0 * pa0 + 6.0 * t_min_acc0) * t_min_acc0;
-        const double m2 = pa2 + (2.0 * pa1 + (3.0 * pa0 + 4.0 * t_min_acc0) * t_min_acc0) * t_min_acc0;
-        const double m3 = pa3 + (pa2 + (pa1 + (pa0 + t_min_acc0) * t_min_acc0) * t_min_acc0) * t_min_acc0;
-        const bool acc0_has_solution = (m0 < 0.0) || (m1 < 0.0) || (m2 < 0.0) || (m3 <= 0.0);
-        const bool acc1_has_solution = (pb0 < 0.0) || (pb1 < 0.0) || (pb2 < 0.0) || (pb3 <= 0.0);
-
         double t[7];
-        // ---- NONE
         {
             const Roots roots = solve_quart_monic(0.0, pn1, pn2, pn3);
+            // Lanes skip their out-of-range roots first, so that the warp runs the Newton polish + validation below once
+            // per in-range root of its busiest lane instead of once per root slot.
+            int ri = 0;
 #pragma unroll 1
-            for (int ri = 0; ri < roots.n; ++ri) {
-                double tt = roots.get(ri);
-                if (tt < t_min_none || tt > t_max_none) continue;
+            while (true) {
+                double tt = 0.0;
+                bool have = false;
+                while (ri < roots.n) {
+                    tt = roots.get(ri++);
+                    if (!(tt < t_min_none || tt > t_max_none)) { have = true; break; }
+                }
+                if (!have) break;
                 if (tt > EPS) {  // single Newton step (regarding pd)
                     const double h1 = j_max * tt * tt;
                     const double orig = -h2_h2 / (4.0 * j_max * tt) + h2_none * (af / j_max + tt)
@@ -325,13 +314,49 @@ struct Step1Pos3 {
                 if (emit(t, L_NONE, L) && first_only) return;
             }
         }
-        // ---- ACC0
-        if (acc0_has_solution) {
+    }
+
+    __device__ __forceinline__ void quartic_acc0(const Lim& L) {
+        const double v0 = b.v0, a0 = b.a0, vf = b.vf, af = b.af;
+        const double a_max = L.a_max, a_min = L.a_min, j_max = L.j_max;
+        const double jl = j_max * j_max;  // the reference mixes this local with the member computed from the UP jerk; equal values
+        // ACC0
+        const double h3_acc0 = (a0_a0 - af_af) / (2.0 * a_max * j_max) + (vf - v0) / a_max;
+        const double t_min_acc0 = (a_max - af) / j_max;
+        const double t_max_acc0 = (a_max - a_min) / j_max;
+        const double h0_acc0 = 3.0 * (af_p4 - a0_p4)
+                               + 8.0 * (a0_p3 - af_p3) * a_max
+                               + 24.0 * a_max * j_max * (af * vf - a0 * v0)
+                               - 6.0 * a0_a0 * (a_max * a_max - 2.0 * j_max * v0)
+                               + 6.0 * af_af * (a_max * a_max - 2.0 * j_max * vf)
+                               + 12.0 * j_max * (j_max * (vf_vf - v0_v0 - 2.0 * a_max * pd) - a_max * a_max * (vf - v0));
+        const double h2_acc0 = -af_af + a_max * a_max + 2.0 * j_max * vf;
+        const double pa0 = -2.0 * a_max / j_max;
+        const double pa1 = h2_acc0 / (jl);
+        const double pa2 = 0.0;
+        const double pa3 = h0_acc0 / (12.0 * jj * jj);
+        // sign pre-screen of the quartic shifted to t_min_acc0 (:404-415)
+        const double m0 = pa0 + 4.0 * t_min_acc0;
+        const double m1 = pa1 + (3.0 * pa0 + 6.0 * t_min_acc0) * t_min_acc0;
+        const double m2 = pa2 + (2.0 * pa1 + (3.0 * pa0 + 4.0 * t_min_acc0) * t_min_acc0) * t_min_acc0;
+        const double m3 = pa3 + (pa2 + (pa1 + (pa0 + t_min_acc0) * t_min_acc0) * t_min_acc0) * t_min_acc0;
+        const bool acc0_has_solution = (m0 < 0.0) || (m1 < 0.0) || (m2 < 0.0) || (m3 <= 0.0);
+        if (!acc0_has_solution) return;
+        double t[7];
+        {
             const Roots roots = solve_quart_monic(pa0, pa1, pa2, pa3);
+            // Lanes skip their out-of-range roots first, so that the warp runs the Newton polish + validation below once
+            // per in-range root of its busiest lane instead of once per root slot.
+            int ri = 0;
 #pragma unroll 1
-            for (int ri = 0; ri < roots.n; ++ri) {
-                double tt = roots.get(ri);
-                if (tt < t_min_acc0 || tt > t_max_acc0) continue;
+            while (true) {
+                double tt = 0.0;
+                bool have = false;
+                while (ri < roots.n) {
+                    tt = roots.get(ri++);
+                    if (!(tt < t_min_acc0 || tt > t_max_acc0)) { have = true; break; }
+                }
+                if (!have) break;
                 if (tt > EPS) {  // single Newton step (regarding pd)
                     const double h1 = j_max * tt;
                     const double orig = h0_acc0 / (12.0 * jj * tt) + tt * (h2_acc0 + h1 * (h1 - 2.0 * a_max));
@@ -346,13 +371,43 @@ struct Step1Pos3 {
                 if (emit(t, L_ACC0, L) && first_only) return;
             }
         }
-        // ---- ACC1
-        if (acc1_has_solution) {
+    }
+
+    __device__ __forceinline__ void quartic_acc1(const Lim& L) {
+        const double v0 = b.v0, a0 = b.a0, vf = b.vf, af = b.af;
+        const double a_max = L.a_max, a_min = L.a_min, j_max = L.j_max;
+        const double jl = j_max * j_max;  // the reference mixes this local with the member computed from the UP jerk; equal values
+        // ACC1
+        const double h3_acc1 = -(a0_a0 + af_af) / (2.0 * j_max * a_min) + a_min / j_max + (vf - v0) / a_min;
+        const double t_min_acc1 = (a_min - a0) / j_max;
+        const double t_max_acc1 = (a_max - a0) / j_max;
+        const double h0_acc1 = (a0_p4 - af_p4) / 4.0
+                               + 2.0 * (af_p3 - a0_p3) * a_min / 3.0
+                               + (a0_a0 - af_af) * a_min * a_min / 2.0
+                               + j_max * (af_af * vf + a0_a0 * v0 + 2.0 * a_min * (j_max * pd - a0 * v0 - af * vf)
+                                          + a_min * a_min * (v0 + vf) + j_max * (v0_v0 - vf_vf));
+        const double h2_acc1 = a0_a0 - a0 * a_min + 2.0 * j_max * v0;
+        const double pb0 = 2.0 * (2.0 * a0 - a_min) / j_max;
+        const double pb1 = (5.0 * a0_a0 + a_min * (a_min - 6.0 * a0) + 2.0 * j_max * v0) / (jl);
+        const double pb2 = 2.0 * (a0 - a_min) * h2_acc1 / (jl * j_max);
+        const double pb3 = h0_acc1 / (jj * jj);
+        const bool acc1_has_solution = (pb0 < 0.0) || (pb1 < 0.0) || (pb2 < 0.0) || (pb3 <= 0.0);
+        if (!acc1_has_solution) return;
+        double t[7];
+        {
             const Roots roots = solve_quart_monic(pb0, pb1, pb2, pb3);
+            // Lanes skip their out-of-range roots first, so that the warp runs the Newton polish + validation below once
+            // per in-range root of its busiest lane instead of once per root slot.
+            int ri = 0;
 #pragma unroll 1
-            for (int ri = 0; ri < roots.n; ++ri) {
-                double tt = roots.get(ri);
-                if (tt < t_min_acc1 || tt > t_max_acc1) continue;
+            while (true) {
+                double tt = 0.0;
+                bool have = false;
+                while (ri < roots.n) {
+                    tt = roots.get(ri++);
+                    if (!(tt < t_min_acc1 || tt > t_max_acc1)) { have = true; break; }
+                }
+                if (!have) break;
                 if (tt > EPS) {  // up to three Newton steps (regarding pd)
                     const double h5 = a0_p3 + 2.0 * j_max * a0 * v0;
                     double h1 = j_max * tt;
@@ -393,6 +448,7 @@ struct Step1Pos3 {
             }
         }
     }
+
 
     // ---- rare numerical rescues (position_third_step1.rs:603-895); each stops at its first valid candidate
     __device__ __forceinline__ void rescue_none(const Lim& L) {  // :843-895
@@ -500,7 +556,7 @@ __device__ __forceinline__ Lim lim_dir(bool up, double v_max, double v_min, doub
 // constant-acceleration phase. bd = brake duration. Returns found; fills blk. (The general case runs as the kernel
 // pipeline k1_family<0..2> + k1_block.)
 __device__ __noinline__ bool step1_pos3_zero_limits(const Bound& b, double v_max, double v_min, double a_max, double a_min, double j_max, double bd, BlockRec& blk) {
-    Step1Pos3 s;
+    Step1Pos3<LocalSink> s;
     s.init(b, j_max);
     blk.has_a = 0; blk.has_b = 0;
     {

@@ -128,28 +128,36 @@ __device__ __noinline__ bool s2_vel_uddu(const S2& s, const Lim& L, Hit& h) {
     // extrema of the quintic: roots of its quartic derivative, closed form
     const Roots d_extremas = solve_quart_monic(deriv[1], deriv[2], deriv[3], deriv[4]);
 
+    // One loop over the extrema plus a last pass for the interval that ends at tz_max (:778-823). Each pass decides
+    // whether it has a root candidate (directly at the extremum, or bracketed between the previous extremum and this
+    // one); the bracketing iteration and the candidate validation then have a single call site each, so the lanes of a
+    // warp re-converge there instead of running four inlined copies one after the other.
     double tz_current = tz_min;
+    double val_current = poly_eval<6>(pol, tz_current);
 #pragma unroll 1
-    for (int ri = 0; ri < d_extremas.n; ++ri) {
-        double tz = d_extremas.get(ri);
-        if (tz >= tz_max) continue;
-
-        const double orig = poly_eval<5>(deriv, tz);
-        if (fabs(orig) > ROOT_TOLERANCE) tz -= orig / poly_eval<4>(dderiv, tz);
-
-        const double val_new = poly_eval<6>(pol, tz);
-        if (fabs(val_new) < 64.0 * fabs(poly_eval<4>(dderiv, tz)) * ROOT_TOLERANCE) {
-            if (vel_uddu_root(s, L, h, tz)) return true;
-        } else if (poly_eval<6>(pol, tz_current) * val_new < 0.0 && vel_uddu_root(s, L, h, shrink_interval<6>(pol, tz_current, tz))) {
-            return true;
+    for (int ri = 0; ri <= d_extremas.n; ++ri) {
+        const bool last = ri == d_extremas.n;
+        double tz = last ? tz_max : d_extremas.get(ri);
+        if (!last && tz >= tz_max) continue;
+        bool direct = false, bracket = false;
+        double val_new;
+        if (!last) {
+            const double orig = poly_eval<5>(deriv, tz);
+            if (fabs(orig) > ROOT_TOLERANCE) tz -= orig / poly_eval<4>(dderiv, tz);
+            val_new = poly_eval<6>(pol, tz);
+            if (fabs(val_new) < 64.0 * fabs(poly_eval<4>(dderiv, tz)) * ROOT_TOLERANCE) direct = true;
+            else if (val_current * val_new < 0.0) bracket = true;
+        } else {
+            val_new = poly_eval<6>(pol, tz_max);
+            if (val_current * val_new < 0.0) bracket = true;
+            else if (fabs(val_new) < 8.0 * EPS) direct = true;
+        }
+        if (direct || bracket) {
+            const double root = bracket ? shrink_interval<6>(pol, tz_current, tz) : tz;
+            if (vel_uddu_root(s, L, h, root)) return true;
         }
         tz_current = tz;
-    }
-    const double val_max = poly_eval<6>(pol, tz_max);
-    if (poly_eval<6>(pol, tz_current) * val_max < 0.0) {
-        if (vel_uddu_root(s, L, h, shrink_interval<6>(pol, tz_current, tz_max))) return true;
-    } else if (fabs(val_max) < 8.0 * EPS && vel_uddu_root(s, L, h, tz_max)) {
-        return true;
+        val_current = val_new;
     }
     return false;
 }
@@ -211,22 +219,24 @@ __device__ __noinline__ bool s2_vel_udud(const S2& s, const Lim& L, Hit& h) {
         if (!dup && n_iv < 6) { iv_l[n_iv] = dd_tz_current; iv_r[n_iv] = tz_max; ++n_iv; }
     }
 
+    // same single-call-site arrangement as the UDDU half: pass k == n_iv is the interval that ends at tz_max (:947-970)
     double tz_current = tz_min;
+    double val_current = poly_eval<7>(pol, tz_current);
 #pragma unroll 1
-    for (int k = 0; k < n_iv; ++k) {
-        const double tz = shrink_interval<6>(deriv, iv_l[k], iv_r[k]);
-        if (tz >= tz_max) continue;
-
+    for (int k = 0; k <= n_iv; ++k) {
+        const bool last = k == n_iv;
+        const double tz = last ? tz_max : shrink_interval<6>(deriv, iv_l[last ? 0 : k], iv_r[last ? 0 : k]);
+        if (!last && tz >= tz_max) continue;
         const double p_val = poly_eval<7>(pol, tz);
-        if (fabs(p_val) < 64.0 * fabs(poly_eval<5>(dderiv, tz)) * ROOT_TOLERANCE) {
-            if (vel_udud_root(s, L, h, tz)) return true;
-        } else if (poly_eval<7>(pol, tz_current) * p_val < 0.0 && vel_udud_root(s, L, h, shrink_interval<7>(pol, tz_current, tz))) {
-            return true;
+        bool direct = false, bracket = false;
+        if (!last && fabs(p_val) < 64.0 * fabs(poly_eval<5>(dderiv, tz)) * ROOT_TOLERANCE) direct = true;
+        else if (val_current * p_val < 0.0) bracket = true;
+        if (direct || bracket) {
+            const double root = bracket ? shrink_interval<7>(pol, tz_current, tz) : tz;
+            if (vel_udud_root(s, L, h, root)) return true;
         }
         tz_current = tz;
-    }
-    if (poly_eval<7>(pol, tz_current) * poly_eval<7>(pol, tz_max) < 0.0 && vel_udud_root(s, L, h, shrink_interval<7>(pol, tz_current, tz_max))) {
-        return true;
+        val_current = p_val;
     }
     return false;
 }

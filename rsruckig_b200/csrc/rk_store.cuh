@@ -24,11 +24,10 @@ enum : int { K_POS3 = 0, K_POS2 = 1, K_POS1 = 2, K_VEL3 = 3, K_VEL2 = 4, K_NONE 
 // Scratch written by the Step-1 kernel (ws doubles, slot-major like the profiles).
 enum : int { W_P0 = 0, W_V0 = 1, W_A0 = 2, W_TMIN = 3, W_ALEFT = 4, W_ARIGHT = 5, W_BLEFT = 6, W_BRIGHT = 7, W_CAND = 8, W_CAND_STRIDE = 9,
              W_BRAKE_DUR = 35,
-             // Step-1 candidate list filled by the family kernels: 6 slots of (t[7], jf)
-             W_VLIST = 36, W_VLIST_STRIDE = 8, WS_SLOTS = 84 };
-// meta words per item: [0] flags below, [1..3] codes of the three block profiles, [4] candidate-list count (bits 0-2) and
-// found-mask of the rest-target schedule (bits 8-13), [5] 6 x 4-bit candidate codes (limits | direction << 3)
-enum : int { WM_META = 0, WM_CAND = 1, WM_VINFO = 4, WM_VCODES = 5, WM_WORDS = 6 };
+             // Step-1 candidate sub-lists filled by the family kernels: 30 slots of t[7] (see rk_pipeline.cuh)
+             W_VLIST = 36, W_VLIST_SLOTS = 30, WS_SLOTS = 36 + 30 * 7 };
+// meta words per item: [0] flags below, [1..3] codes of the three block profiles
+enum : int { WM_META = 0, WM_CAND = 1, WM_WORDS = 4 };
 enum : uint32_t { M_KIND_MASK = 0xFu, M_FOUND = 1u << 4, M_HAS_A = 1u << 5, M_HAS_B = 1u << 6, M_S1_PENDING = 1u << 7, M_ZERO_LIMITS = 1u << 8,
                   M_ENABLED = 1u << 9, M_VCODE_SHIFT = 16 };
 
