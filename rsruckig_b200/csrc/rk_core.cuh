@@ -37,7 +37,7 @@ struct Bound {
 
 // util.rs:27-33
 __device__ __forceinline__ void integrate(double t, double p0, double v0, double a0, double j, double& p, double& v, double& a) {
-    p = p0 + t * (v0 + t * (a0 / 2.0 + t * j / 6.0));
+    p = p0 + t * (v0 + t * (a0 / 2.0 + sdiv(t * j, 6.0)));
     v = v0 + t * (a0 + t * j / 2.0);
     a = a0 + t * j;
 }
@@ -94,14 +94,16 @@ __device__ __noinline__ bool check_pos3(double t0, double t1, double t2, double 
     v[0] = v0;
 #pragma unroll
     for (int i = 0; i < 7; ++i) {
-        a[i + 1] = a[i] + t[i] * j[i];
-        v[i + 1] = v[i] + t[i] * (a[i] + t[i] * j[i] / 2.0);
-        p = p + t[i] * (v[i] + t[i] * (a[i] / 2.0 + t[i] * j[i] / 6.0));
+        // j[1], j[3], j[5] are exactly 0: t * 0 is +-0 (or NaN), and +-0 / 6 is that same +-0, so the division is skipped there
+        const double tj = t[i] * j[i];
+        a[i + 1] = a[i] + tj;
+        v[i + 1] = v[i] + t[i] * (a[i] + tj / 2.0);
+        p = p + t[i] * (v[i] + t[i] * (a[i] / 2.0 + ((i & 1) ? tj : sdiv(tj, 6.0))));
 
         if (i == 2 && zero_a3) a[3] = 0.0;
 
         if (i > 1 && a[i + 1] * a[i] < -EPS) {
-            const double v_a_zero = v[i] - (a[i] * a[i]) / (2.0 * j[i]);
+            const double v_a_zero = v[i] - sdiv(a[i] * a[i], 2.0 * j[i]);
             if (v_a_zero > v_upp_lim || v_a_zero < v_low_lim) return false;
         }
     }
@@ -220,15 +222,15 @@ struct Brake {
 };
 
 __device__ __forceinline__ double v_at_t(double v0, double a0, double j, double t) { return v0 + t * (a0 + j * t / 2.0); }  // brake.rs:15
-__device__ __forceinline__ double v_at_a_zero(double v0, double a0, double j) { return v0 + (a0 * a0) / (2.0 * j); }       // brake.rs:20
+__device__ __forceinline__ double v_at_a_zero(double v0, double a0, double j) { return v0 + sdiv(a0 * a0, 2.0 * j); }       // brake.rs:20
 constexpr double BRAKE_EPS = 2.2e-14;                                                                                       // brake.rs:12
 
 // brake.rs:77-105
 __device__ __forceinline__ void velocity_brake(Brake& b, double v0, double a0, double v_max, double v_min, double a_min, double j_max) {
     b.j[0] = -j_max;
-    const double t_to_a_min = (a0 - a_min) / j_max;
-    const double t_to_v_max = a0 / j_max + sqrt(a0 * a0 + 2.0 * j_max * (v0 - v_max)) / fabs(j_max);
-    const double t_to_v_min = a0 / j_max + sqrt(a0 * a0 / 2.0 + j_max * (v0 - v_min)) / fabs(j_max);
+    const double t_to_a_min = sdiv(a0 - a_min, j_max);
+    const double t_to_v_max = sdiv(a0, j_max) + sqrt(a0 * a0 + 2.0 * j_max * (v0 - v_max)) / fabs(j_max);
+    const double t_to_v_min = sdiv(a0, j_max) + sqrt(a0 * a0 / 2.0 + j_max * (v0 - v_min)) / fabs(j_max);
     const double t_min_to_v_max = rmin(t_to_v_max, t_to_v_min);
     if (t_to_a_min < t_min_to_v_max) {
         const double v_at_a_min = v_at_t(v0, a0, -j_max, t_to_a_min);
@@ -244,8 +246,8 @@ __device__ __forceinline__ void velocity_brake(Brake& b, double v0, double a0, d
 // brake.rs:46-75
 __device__ __forceinline__ void acceleration_brake(Brake& b, double v0, double a0, double v_max, double v_min, double a_max, double a_min, double j_max) {
     b.j[0] = -j_max;
-    const double t_to_a_max = (a0 - a_max) / j_max;
-    const double t_to_a_zero = a0 / j_max;
+    const double t_to_a_max = sdiv(a0 - a_max, j_max);
+    const double t_to_a_zero = sdiv(a0, j_max);
     const double v_at_a_max = v_at_t(v0, a0, -j_max, t_to_a_max);
     const double v_at_a_zero_ = v_at_t(v0, a0, -j_max, t_to_a_zero);
     if ((v_at_a_zero_ > v_max && j_max > 0.0) || (v_at_a_zero_ < v_max && j_max < 0.0)) {
@@ -287,8 +289,8 @@ __device__ __forceinline__ void position_brake_second_order(Brake& b, double v0,
 __device__ __forceinline__ void velocity_brake_third_order(Brake& b, double a0, double a_max, double a_min, double j_max) {
     b.t[0] = 0.0; b.t[1] = 0.0; b.j[0] = 0.0; b.j[1] = 0.0;
     if (j_max == 0.0) return;
-    if (a0 > a_max) { b.j[0] = -j_max; b.t[0] = (a0 - a_max) / j_max + EPS; }
-    else if (a0 < a_min) { b.j[0] = j_max; b.t[0] = -(a0 - a_min) / j_max + EPS; }
+    if (a0 > a_max) { b.j[0] = -j_max; b.t[0] = sdiv(a0 - a_max, j_max) + EPS; }
+    else if (a0 < a_min) { b.j[0] = j_max; b.t[0] = -sdiv(a0 - a_min, j_max) + EPS; }
 }
 
 // ------------------------------------------------------------------ roots.rs
@@ -391,9 +393,9 @@ __device__ __noinline__ Roots solve_cub(double a, double b, double c, double d) 
 
 // roots.rs:237-274
 __device__ __forceinline__ int solve_resolvent(double (&x)[3], double a, double b, double c) {
-    a = a / 3.0;
+    a = sdiv(a, 3.0);
     const double a2 = a * a;
-    double q = a2 - b / 3.0;
+    double q = a2 - sdiv(b, 3.0);
     const double r = (a * (2.0 * a2 - b) + c) / 2.0;
     const double r2 = r * r;
     const double q3 = q * q * q;
@@ -413,7 +415,7 @@ __device__ __forceinline__ int solve_resolvent(double (&x)[3], double a, double 
     }
     double a_ = m_cbrt(-fabs(r) - sqrt(r2 - q3));
     if (r < 0.0) a_ = -a_;
-    const double b_ = (a_ == 0.0) ? 0.0 : q / a_;
+    const double b_ = (a_ == 0.0) ? 0.0 : sdiv(q, a_);
     x[0] = (a_ + b_) - a;
     x[1] = -(a_ + b_) / 2.0 - a;
     x[2] = sqrt(3.0) * (a_ - b_) / 2.0;
@@ -483,8 +485,8 @@ __device__ __noinline__ Roots solve_quart_monic(double a, double b, double c, do
         const double sqrt_d = sqrt(d_);
         q1 = (y + sqrt_d) / 2.0;
         q2 = (y - sqrt_d) / 2.0;
-        p1 = (a * q1 - c) / (q1 - q2);
-        p2 = (c - a * q2) / (q1 - q2);
+        p1 = sdiv(a * q1 - c, q1 - q2);
+        p2 = sdiv(c - a * q2, q1 - q2);
     }
 
     const double EPS16 = 16.0 * EPS;
@@ -541,7 +543,7 @@ template <int N>
 __device__ __forceinline__ void poly_monic_deri(const double (&c)[N], double (&d)[N - 1]) {
     d[0] = 1.0;
 #pragma unroll
-    for (int i = 1; i < N - 1; ++i) d[i] = (double)(N - 1 - i) * c[i] / (double)(N - 1);
+    for (int i = 1; i < N - 1; ++i) d[i] = sdiv((double)(N - 1 - i) * c[i], (double)(N - 1));
 }
 
 // roots.rs:424-481: safeguarded Newton / bisection, at most 128 iterations, tolerance 1e-14.
@@ -568,7 +570,7 @@ __device__ __forceinline__ double shrink_interval(const double (&p)[N], double l
             if (fabs(l - rts) < EPS) break;
         } else {
             dxold = dx;
-            dx = f / df;
+            dx = sdiv(f, df);
             const double temp = rts;
             rts -= dx;
             if (fabs(temp - rts) < EPS) break;

@@ -38,9 +38,9 @@ __device__ __forceinline__ void copy_t(double (&dst)[7], const double (&src)[7])
 }
 
 // block.rs:220-239 (brake duration bd is common to all profiles of the DoF; accel duration is always 0, Q21)
-__device__ __forceinline__ void make_interval(const Cand& pl, const Cand& pr, double bd, double& left, double& right, Cand& prof) {
-    const double ld = pl.dur + bd + 0.0;
-    const double rd = pr.dur + bd + 0.0;
+__device__ __forceinline__ void make_interval(const Cand& pl, const Cand& pr, real bd, double& left, double& right, Cand& prof) {
+    const real ld = pl.dur + bd + 0.0;
+    const real rd = pr.dur + bd + 0.0;
     if (ld < rd) { left = ld; right = rd; prof = pr; }
     else { left = rd; right = ld; prof = pl; }
 }
@@ -138,7 +138,7 @@ template <class Sink>
 struct Step1Pos3 {
     // inputs (post-brake) and the products the reference precomputes (position_third_step1.rs:39-86)
     Bound b;
-    double pd, v0_v0, vf_vf, a0_a0, a0_p3, a0_p4, af_af, af_p3, af_p4, jj;
+    real pd, v0_v0, vf_vf, a0_a0, a0_p3, a0_p4, af_af, af_p3, af_p4, jj;
     Sink sink;
     bool first_only;  // reference's return_after_found
 
@@ -162,8 +162,8 @@ struct Step1Pos3 {
 
     // position_third_step1.rs:97-240. All four variants are validated as ReachedLimits::Vel (Q6); at most one is kept.
     __device__ __forceinline__ void family_vel(const Lim& L) {
-        const double v0 = b.v0, a0 = b.a0, vf = b.vf, af = b.af;
-        const double v_max = L.v_max, a_max = L.a_max, a_min = L.a_min, j_max = L.j_max;
+        const real v0 = b.v0, a0 = b.a0, vf = b.vf, af = b.af;
+        const real v_max = L.v_max, a_max = L.a_max, a_min = L.a_min, j_max = L.j_max;
         double t[7];
         // ACC0_ACC1_VEL
         t[0] = (-a0 + a_max) / j_max;
@@ -183,7 +183,7 @@ struct Step1Pos3 {
         if (emit(t, L_VEL, L)) return;
 
         // ACC1_VEL (t[4..6] carry over)
-        const double t_acc0 = sqrt(a0_a0 / (2.0 * jj) + (v_max - v0) / j_max);
+        const real t_acc0 = sqrt(a0_a0 / (2.0 * jj) + (v_max - v0) / j_max);
         t[0] = t_acc0 - a0 / j_max;
         t[1] = 0.0;
         t[2] = t_acc0;
@@ -199,7 +199,7 @@ struct Step1Pos3 {
         if (emit(t, L_VEL, L)) return;
 
         // ACC0_VEL
-        const double t_acc1 = sqrt(af_af / (2.0 * jj) + (v_max - vf) / j_max);
+        const real t_acc1 = sqrt(af_af / (2.0 * jj) + (v_max - vf) / j_max);
         t[0] = (-a0 + a_max) / j_max;
         t[1] = (a0_a0 / 2.0 - a_max * a_max - j_max * (v0 - v_max)) / (a_max * j_max);
         t[2] = a_max / j_max;
@@ -231,17 +231,17 @@ struct Step1Pos3 {
 
     // position_third_step1.rs:241-327
     __device__ __forceinline__ void family_acc0_acc1(const Lim& L) {
-        const double v0 = b.v0, a0 = b.a0, vf = b.vf, af = b.af;
-        const double a_max = L.a_max, a_min = L.a_min, j_max = L.j_max;
-        double h1 = (3. * (af_p4 * a_max - a0_p4 * a_min)
+        const real v0 = b.v0, a0 = b.a0, vf = b.vf, af = b.af;
+        const real a_max = L.a_max, a_min = L.a_min, j_max = L.j_max;
+        real h1 = (3. * (af_p4 * a_max - a0_p4 * a_min)
                      + a_max * a_min * (8. * (a0_p3 - af_p3) + 3. * a_max * a_min * (a_max - a_min) + 6. * a_min * af_af - 6. * a_max * a0_a0)
                      + 12. * j_max * (a_max * a_min * ((a_max - 2. * a0) * v0 - (a_min - 2. * af) * vf) + a_min * a0_a0 * v0 - a_max * af_af * vf))
                     / (3. * (a_max - a_min) * jj)
                     + 4. * (a_max * vf_vf - a_min * v0_v0 - 2. * a_min * a_max * pd) / (a_max - a_min);
         if (!(h1 >= 0.)) return;
         h1 = sqrt(h1) / 2.;
-        const double h2 = a0_a0 / (2. * a_max * j_max) + (a_min - 2. * a_max) / (2. * j_max) - v0 / a_max;
-        const double h3 = -af_af / (2. * a_min * j_max) - (a_max - 2. * a_min) / (2. * j_max) + vf / a_min;
+        const real h2 = a0_a0 / (2. * a_max * j_max) + (a_min - 2. * a_max) / (2. * j_max) - v0 / a_max;
+        const real h3 = -af_af / (2. * a_min * j_max) - (a_max - 2. * a_min) / (2. * j_max) + vf / a_min;
         double t[7];
         // UDDU: Solution 2
         if (h2 > h1 / a_max && h3 > -h1 / a_min) {
@@ -271,16 +271,16 @@ struct Step1Pos3 {
     // root with Newton steps. Here each quartic is its own function (and its own kernel, one thread per direction): the
     // three are independent of one another, and the candidate order NONE, ACC0, ACC1 is restored when the lists are read.
     __device__ __forceinline__ void quartic_none(const Lim& L) {
-        const double v0 = b.v0, a0 = b.a0, vf = b.vf, af = b.af;
-        const double a_max = L.a_max, a_min = L.a_min, j_max = L.j_max;
-        const double jl = j_max * j_max;  // the reference mixes this local with the member computed from the UP jerk; equal values
-        const double h2_none = (a0_a0 - af_af) / (2.0 * j_max) + (vf - v0);
-        const double h2_h2 = h2_none * h2_none;
-        const double t_min_none = (a0 - af) / j_max;
-        const double t_max_none = (a_max - a_min) / j_max;
-        const double pn1 = -2.0 * (a0_a0 + af_af - 2.0 * j_max * (v0 + vf)) / (jl);
-        const double pn2 = 4.0 * (a0_p3 - af_p3 + 3.0 * j_max * (af * vf - a0 * v0)) / (3.0 * jl * j_max) - 4.0 * pd / j_max;
-        const double pn3 = -h2_h2 / (jl);
+        const real v0 = b.v0, a0 = b.a0, vf = b.vf, af = b.af;
+        const real a_max = L.a_max, a_min = L.a_min, j_max = L.j_max;
+        const real jl = j_max * j_max;  // the reference mixes this local with the member computed from the UP jerk; equal values
+        const real h2_none = (a0_a0 - af_af) / (2.0 * j_max) + (vf - v0);
+        const real h2_h2 = h2_none * h2_none;
+        const real t_min_none = (a0 - af) / j_max;
+        const real t_max_none = (a_max - a_min) / j_max;
+        const real pn1 = -2.0 * (a0_a0 + af_af - 2.0 * j_max * (v0 + vf)) / (jl);
+        const real pn2 = 4.0 * (a0_p3 - af_p3 + 3.0 * j_max * (af * vf - a0 * v0)) / (3.0 * jl * j_max) - 4.0 * pd / j_max;
+        const real pn3 = -h2_h2 / (jl);
         double t[7];
         {
             const Roots roots = solve_quart_monic(0.0, pn1, pn2, pn3);
@@ -289,7 +289,7 @@ struct Step1Pos3 {
             int ri = 0;
 #pragma unroll 1
             while (true) {
-                double tt = 0.0;
+                real tt = 0.0;
                 bool have = false;
                 while (ri < roots.n) {
                     tt = roots.get(ri++);
@@ -297,15 +297,15 @@ struct Step1Pos3 {
                 }
                 if (!have) break;
                 if (tt > EPS) {  // single Newton step (regarding pd)
-                    const double h1 = j_max * tt * tt;
-                    const double orig = -h2_h2 / (4.0 * j_max * tt) + h2_none * (af / j_max + tt)
+                    const real h1 = j_max * tt * tt;
+                    const real orig = -h2_h2 / (4.0 * j_max * tt) + h2_none * (af / j_max + tt)
                                         + (4.0 * a0_p3 + 2.0 * af_p3 - 6.0 * a0_a0 * (af + 2.0 * j_max * tt) + 12.0 * (af - a0) * j_max * v0
                                            + 3.0 * jj * (-4.0 * pd + (h1 + 8.0 * v0) * tt))
                                           / (12.0 * jj);
-                    const double deriv = h2_none + 2.0 * v0 - a0_a0 / j_max + h2_h2 / (4.0 * h1) + (3.0 * h1) / 4.0;
+                    const real deriv = h2_none + 2.0 * v0 - a0_a0 / j_max + h2_h2 / (4.0 * h1) + (3.0 * h1) / 4.0;
                     tt -= orig / deriv;
                 }
-                const double h0 = h2_none / (2.0 * j_max * tt);
+                const real h0 = h2_none / (2.0 * j_max * tt);
                 t[0] = h0 + tt / 2.0 - a0 / j_max;
                 t[1] = 0.0;
                 t[2] = tt;
@@ -317,29 +317,29 @@ struct Step1Pos3 {
     }
 
     __device__ __forceinline__ void quartic_acc0(const Lim& L) {
-        const double v0 = b.v0, a0 = b.a0, vf = b.vf, af = b.af;
-        const double a_max = L.a_max, a_min = L.a_min, j_max = L.j_max;
-        const double jl = j_max * j_max;  // the reference mixes this local with the member computed from the UP jerk; equal values
+        const real v0 = b.v0, a0 = b.a0, vf = b.vf, af = b.af;
+        const real a_max = L.a_max, a_min = L.a_min, j_max = L.j_max;
+        const real jl = j_max * j_max;  // the reference mixes this local with the member computed from the UP jerk; equal values
         // ACC0
-        const double h3_acc0 = (a0_a0 - af_af) / (2.0 * a_max * j_max) + (vf - v0) / a_max;
-        const double t_min_acc0 = (a_max - af) / j_max;
-        const double t_max_acc0 = (a_max - a_min) / j_max;
-        const double h0_acc0 = 3.0 * (af_p4 - a0_p4)
+        const real h3_acc0 = (a0_a0 - af_af) / (2.0 * a_max * j_max) + (vf - v0) / a_max;
+        const real t_min_acc0 = (a_max - af) / j_max;
+        const real t_max_acc0 = (a_max - a_min) / j_max;
+        const real h0_acc0 = 3.0 * (af_p4 - a0_p4)
                                + 8.0 * (a0_p3 - af_p3) * a_max
                                + 24.0 * a_max * j_max * (af * vf - a0 * v0)
                                - 6.0 * a0_a0 * (a_max * a_max - 2.0 * j_max * v0)
                                + 6.0 * af_af * (a_max * a_max - 2.0 * j_max * vf)
                                + 12.0 * j_max * (j_max * (vf_vf - v0_v0 - 2.0 * a_max * pd) - a_max * a_max * (vf - v0));
-        const double h2_acc0 = -af_af + a_max * a_max + 2.0 * j_max * vf;
-        const double pa0 = -2.0 * a_max / j_max;
-        const double pa1 = h2_acc0 / (jl);
-        const double pa2 = 0.0;
-        const double pa3 = h0_acc0 / (12.0 * jj * jj);
+        const real h2_acc0 = -af_af + a_max * a_max + 2.0 * j_max * vf;
+        const real pa0 = -2.0 * a_max / j_max;
+        const real pa1 = h2_acc0 / (jl);
+        const real pa2 = 0.0;
+        const real pa3 = h0_acc0 / (12.0 * jj * jj);
         // sign pre-screen of the quartic shifted to t_min_acc0 (:404-415)
-        const double m0 = pa0 + 4.0 * t_min_acc0;
-        const double m1 = pa1 + (3.0 * pa0 + 6.0 * t_min_acc0) * t_min_acc0;
-        const double m2 = pa2 + (2.0 * pa1 + (3.0 * pa0 + 4.0 * t_min_acc0) * t_min_acc0) * t_min_acc0;
-        const double m3 = pa3 + (pa2 + (pa1 + (pa0 + t_min_acc0) * t_min_acc0) * t_min_acc0) * t_min_acc0;
+        const real m0 = pa0 + 4.0 * t_min_acc0;
+        const real m1 = pa1 + (3.0 * pa0 + 6.0 * t_min_acc0) * t_min_acc0;
+        const real m2 = pa2 + (2.0 * pa1 + (3.0 * pa0 + 4.0 * t_min_acc0) * t_min_acc0) * t_min_acc0;
+        const real m3 = pa3 + (pa2 + (pa1 + (pa0 + t_min_acc0) * t_min_acc0) * t_min_acc0) * t_min_acc0;
         const bool acc0_has_solution = (m0 < 0.0) || (m1 < 0.0) || (m2 < 0.0) || (m3 <= 0.0);
         if (!acc0_has_solution) return;
         double t[7];
@@ -350,7 +350,7 @@ struct Step1Pos3 {
             int ri = 0;
 #pragma unroll 1
             while (true) {
-                double tt = 0.0;
+                real tt = 0.0;
                 bool have = false;
                 while (ri < roots.n) {
                     tt = roots.get(ri++);
@@ -358,9 +358,9 @@ struct Step1Pos3 {
                 }
                 if (!have) break;
                 if (tt > EPS) {  // single Newton step (regarding pd)
-                    const double h1 = j_max * tt;
-                    const double orig = h0_acc0 / (12.0 * jj * tt) + tt * (h2_acc0 + h1 * (h1 - 2.0 * a_max));
-                    const double deriv = 2.0 * (h2_acc0 + h1 * (2.0 * h1 - 3.0 * a_max));
+                    const real h1 = j_max * tt;
+                    const real orig = h0_acc0 / (12.0 * jj * tt) + tt * (h2_acc0 + h1 * (h1 - 2.0 * a_max));
+                    const real deriv = 2.0 * (h2_acc0 + h1 * (2.0 * h1 - 3.0 * a_max));
                     tt -= orig / deriv;
                 }
                 t[0] = (-a0 + a_max) / j_max;
@@ -374,23 +374,23 @@ struct Step1Pos3 {
     }
 
     __device__ __forceinline__ void quartic_acc1(const Lim& L) {
-        const double v0 = b.v0, a0 = b.a0, vf = b.vf, af = b.af;
-        const double a_max = L.a_max, a_min = L.a_min, j_max = L.j_max;
-        const double jl = j_max * j_max;  // the reference mixes this local with the member computed from the UP jerk; equal values
+        const real v0 = b.v0, a0 = b.a0, vf = b.vf, af = b.af;
+        const real a_max = L.a_max, a_min = L.a_min, j_max = L.j_max;
+        const real jl = j_max * j_max;  // the reference mixes this local with the member computed from the UP jerk; equal values
         // ACC1
-        const double h3_acc1 = -(a0_a0 + af_af) / (2.0 * j_max * a_min) + a_min / j_max + (vf - v0) / a_min;
-        const double t_min_acc1 = (a_min - a0) / j_max;
-        const double t_max_acc1 = (a_max - a0) / j_max;
-        const double h0_acc1 = (a0_p4 - af_p4) / 4.0
+        const real h3_acc1 = -(a0_a0 + af_af) / (2.0 * j_max * a_min) + a_min / j_max + (vf - v0) / a_min;
+        const real t_min_acc1 = (a_min - a0) / j_max;
+        const real t_max_acc1 = (a_max - a0) / j_max;
+        const real h0_acc1 = (a0_p4 - af_p4) / 4.0
                                + 2.0 * (af_p3 - a0_p3) * a_min / 3.0
                                + (a0_a0 - af_af) * a_min * a_min / 2.0
                                + j_max * (af_af * vf + a0_a0 * v0 + 2.0 * a_min * (j_max * pd - a0 * v0 - af * vf)
                                           + a_min * a_min * (v0 + vf) + j_max * (v0_v0 - vf_vf));
-        const double h2_acc1 = a0_a0 - a0 * a_min + 2.0 * j_max * v0;
-        const double pb0 = 2.0 * (2.0 * a0 - a_min) / j_max;
-        const double pb1 = (5.0 * a0_a0 + a_min * (a_min - 6.0 * a0) + 2.0 * j_max * v0) / (jl);
-        const double pb2 = 2.0 * (a0 - a_min) * h2_acc1 / (jl * j_max);
-        const double pb3 = h0_acc1 / (jj * jj);
+        const real h2_acc1 = a0_a0 - a0 * a_min + 2.0 * j_max * v0;
+        const real pb0 = 2.0 * (2.0 * a0 - a_min) / j_max;
+        const real pb1 = (5.0 * a0_a0 + a_min * (a_min - 6.0 * a0) + 2.0 * j_max * v0) / (jl);
+        const real pb2 = 2.0 * (a0 - a_min) * h2_acc1 / (jl * j_max);
+        const real pb3 = h0_acc1 / (jj * jj);
         const bool acc1_has_solution = (pb0 < 0.0) || (pb1 < 0.0) || (pb2 < 0.0) || (pb3 <= 0.0);
         if (!acc1_has_solution) return;
         double t[7];
@@ -401,7 +401,7 @@ struct Step1Pos3 {
             int ri = 0;
 #pragma unroll 1
             while (true) {
-                double tt = 0.0;
+                real tt = 0.0;
                 bool have = false;
                 while (ri < roots.n) {
                     tt = roots.get(ri++);
@@ -409,13 +409,13 @@ struct Step1Pos3 {
                 }
                 if (!have) break;
                 if (tt > EPS) {  // up to three Newton steps (regarding pd)
-                    const double h5 = a0_p3 + 2.0 * j_max * a0 * v0;
-                    double h1 = j_max * tt;
-                    double orig = -(h0_acc1 / 2.0
+                    const real h5 = a0_p3 + 2.0 * j_max * a0 * v0;
+                    real h1 = j_max * tt;
+                    real orig = -(h0_acc1 / 2.0
                                     + h1 * (h5 + a0 * (a_min - 2.0 * h1) * (a_min - h1) + a0_a0 * (5.0 * h1 / 2.0 - 2.0 * a_min)
                                             + a_min * a_min * h1 / 2.0 + j_max * (h1 / 2.0 - a_min) * (h1 * tt + 2.0 * v0)))
                                   / j_max;
-                    double deriv = (a_min - a0 - h1) * (h2_acc1 + h1 * (4.0 * a0 - a_min + 2.0 * h1));
+                    real deriv = (a_min - a0 - h1) * (h2_acc1 + h1 * (4.0 * a0 - a_min + 2.0 * h1));
                     tt -= rmin(orig / deriv, tt);
 
                     h1 = j_max * tt;
@@ -452,9 +452,9 @@ struct Step1Pos3 {
 
     // ---- rare numerical rescues (position_third_step1.rs:603-895); each stops at its first valid candidate
     __device__ __forceinline__ void rescue_none(const Lim& L) {  // :843-895
-        const double j_max = L.j_max;
+        const real j_max = L.j_max;
         double t[7] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-        const double h0 = sqrt((a0_a0 + af_af) / 2.0 + j_max * (b.vf - b.v0)) * fabs(j_max) / j_max;
+        const real h0 = sqrt((a0_a0 + af_af) / 2.0 + j_max * (b.vf - b.v0)) * fabs(j_max) / j_max;
         t[0] = (h0 - b.a0) / j_max;
         t[2] = (h0 - b.af) / j_max;
         if (emit(t, L_NONE, L)) return;
@@ -464,8 +464,8 @@ struct Step1Pos3 {
     }
 
     __device__ __forceinline__ void rescue_acc0(const Lim& L) {  // :644-778
-        const double v0 = b.v0, a0 = b.a0, vf = b.vf, af = b.af;
-        const double a_max = L.a_max, a_min = L.a_min, j_max = L.j_max;
+        const real v0 = b.v0, a0 = b.a0, vf = b.vf, af = b.af;
+        const real a_max = L.a_max, a_min = L.a_min, j_max = L.j_max;
         double t[7] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
         // two step
         t[1] = (af_af - a0_a0 + 2.0 * j_max * (vf - v0)) / (2.0 * a0 * j_max);
@@ -478,9 +478,9 @@ struct Step1Pos3 {
         if (emit(t, L_ACC0, L)) return;
         // three step, a_max removed
         {
-            const double h0 = 3.0 * (af_af - a0_a0 + 2.0 * j_max * (v0 + vf));
-            const double h2 = a0_p3 + 2.0 * af_p3 + 6.0 * jj * pd + 6.0 * (af - a0) * j_max * vf - 3.0 * a0 * af_af;
-            const double h1 = sqrt(2.0 * (2.0 * h2 * h2
+            const real h0 = 3.0 * (af_af - a0_a0 + 2.0 * j_max * (v0 + vf));
+            const real h2 = a0_p3 + 2.0 * af_p3 + 6.0 * jj * pd + 6.0 * (af - a0) * j_max * vf - 3.0 * a0 * af_af;
+            const real h1 = sqrt(2.0 * (2.0 * h2 * h2
                                           + h0 * (a0_p4 - 6.0 * a0_a0 * (af_af + 2.0 * j_max * vf)
                                                   + 8.0 * a0 * (af_p3 + 3.0 * jj * pd + 3.0 * af * j_max * vf)
                                                   - 3.0 * (af_p4 + 4.0 * af_af * j_max * vf + 4.0 * jj * (vf_vf - v0_v0)))))
@@ -492,7 +492,7 @@ struct Step1Pos3 {
         }
         // three step with t = (a_max - a_min) / j_max
         {
-            const double tt = (a_max - a_min) / j_max;
+            const real tt = (a_max - a_min) / j_max;
             t[0] = (-a0 + a_max) / j_max;
             t[1] = (a0_a0 - af_af) / (2.0 * a_max * j_max) + (vf - v0 + j_max * tt * tt) / a_max - 2.0 * tt;
             t[2] = tt;
@@ -502,9 +502,9 @@ struct Step1Pos3 {
     }
 
     __device__ __forceinline__ void rescue_vel(const Lim& L) {  // :780-841
-        const double v0 = b.v0, a0 = b.a0, vf = b.vf, af = b.af;
-        const double v_max = L.v_max, j_max = L.j_max;
-        const double h1 = sqrt(af_af / (2.0 * jj) + (v_max - vf) / j_max);
+        const real v0 = b.v0, a0 = b.a0, vf = b.vf, af = b.af;
+        const real v_max = L.v_max, j_max = L.j_max;
+        const real h1 = sqrt(af_af / (2.0 * jj) + (v_max - vf) / j_max);
         double t[7];
         t[0] = -a0 / j_max;
         t[1] = 0.0;
@@ -526,8 +526,8 @@ struct Step1Pos3 {
     }
 
     __device__ __forceinline__ void rescue_acc1_vel(const Lim& L) {  // :603-642
-        const double v0 = b.v0, a0 = b.a0, vf = b.vf, af = b.af;
-        const double v_max = L.v_max, a_min = L.a_min, j_max = L.j_max;
+        const real v0 = b.v0, a0 = b.a0, vf = b.vf, af = b.af;
+        const real v_max = L.v_max, a_min = L.a_min, j_max = L.j_max;
         double t[7];
         t[0] = 0.0;
         t[1] = 0.0;
@@ -544,7 +544,7 @@ struct Step1Pos3 {
     }
 };
 
-__device__ __forceinline__ Lim lim_dir(bool up, double v_max, double v_min, double a_max, double a_min, double j_max) {
+__device__ __forceinline__ Lim lim_dir(bool up, real v_max, real v_min, real a_max, real a_min, double j_max) {
     Lim L;
     L.v_max = up ? v_max : v_min; L.v_min = up ? v_min : v_max;
     L.a_max = up ? a_max : a_min; L.a_min = up ? a_min : a_max;
@@ -555,7 +555,7 @@ __device__ __forceinline__ Lim lim_dir(bool up, double v_max, double v_min, doub
 // The zero-limit special case of position_third_step1.rs:982-1004 (+ time_all_single_step :897-980): one
 // constant-acceleration phase. bd = brake duration. Returns found; fills blk. (The general case runs as the kernel
 // pipeline k1_family<0..2> + k1_block.)
-__device__ __noinline__ bool step1_pos3_zero_limits(const Bound& b, double v_max, double v_min, double a_max, double a_min, double j_max, double bd, BlockRec& blk) {
+__device__ __noinline__ bool step1_pos3_zero_limits(const Bound& b, real v_max, real v_min, real a_max, real a_min, real j_max, real bd, BlockRec& blk) {
     Step1Pos3<LocalSink> s;
     s.init(b, j_max);
     blk.has_a = 0; blk.has_b = 0;
@@ -565,7 +565,7 @@ __device__ __noinline__ bool step1_pos3_zero_limits(const Bound& b, double v_max
         double t[7] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
         bool ok = false;
         if (fabs(b.a0) > EPS) {
-            const double q = sqrt(2.0 * b.a0 * s.pd + s.v0_v0);
+            const real q = sqrt(2.0 * b.a0 * s.pd + s.v0_v0);
             t[3] = (-b.v0 + q) / b.a0;
             ok = t[3] >= 0.0 && check_pos3(t, UDDU, L_NONE, 0.0, L, b);
             if (!ok) {

@@ -14,11 +14,11 @@ namespace rk {
 
 struct S2 {
     Bound b;
-    double tf;
+    real tf;
     // products precomputed by the reference (position_third_step2.rs:51-128)
-    double pd, tf_tf, tf_p3, tf_p4, vd, vd_vd, vf_vf, ad, ad_ad, a0_a0, af_af, a0_p3, a0_p4, a0_p5, a0_p6, af_p3, af_p4, af_p5, af_p6, jj, g1, g2;
+    real pd, tf_tf, tf_p3, tf_p4, vd, vd_vd, vf_vf, ad, ad_ad, a0_a0, af_af, a0_p3, a0_p4, a0_p5, a0_p6, af_p3, af_p4, af_p5, af_p6, jj, g1, g2;
 
-    __device__ __forceinline__ void init(const Bound& bb, double tf_, double j_max) {
+    __device__ __forceinline__ void init(const Bound& bb, real tf_, double j_max) {
         b = bb;
         tf = tf_;
         pd = b.pf - b.p0;
@@ -37,15 +37,15 @@ struct S2 {
 // Result slot of a family.
 struct Hit {
     double t[7];
-    double jf;
+    real jf;
     int lim, cs, dir;
 };
 
 #define RK_S2_LOCALS                                                                                                        \
-    const double v0 = s.b.v0, a0 = s.b.a0, vf = s.b.vf, af = s.b.af, tf = s.tf, pd = s.pd, vd = s.vd, ad = s.ad;            \
-    const double a0_a0 = s.a0_a0, af_af = s.af_af, a0_p3 = s.a0_p3, af_p3 = s.af_p3, a0_p4 = s.a0_p4, af_p4 = s.af_p4;      \
-    const double vd_vd = s.vd_vd, ad_ad = s.ad_ad, tf_tf = s.tf_tf, g1 = s.g1, g2 = s.g2, j_max_j_max = s.jj;               \
-    const double v_max = L.v_max, v_min = L.v_min, a_max = L.a_max, a_min = L.a_min, j_max = L.j_max;                       \
+    const real v0 = s.b.v0, a0 = s.b.a0, vf = s.b.vf, af = s.b.af, tf = s.tf, pd = s.pd, vd = s.vd, ad = s.ad;            \
+    const real a0_a0 = s.a0_a0, af_af = s.af_af, a0_p3 = s.a0_p3, af_p3 = s.af_p3, a0_p4 = s.a0_p4, af_p4 = s.af_p4;      \
+    const real vd_vd = s.vd_vd, ad_ad = s.ad_ad, tf_tf = s.tf_tf, g1 = s.g1, g2 = s.g2, j_max_j_max = s.jj;               \
+    const real v_max = L.v_max, v_min = L.v_min, a_max = L.a_max, a_min = L.a_min, j_max = L.j_max;                       \
     (void)v0; (void)vf; (void)pd; (void)vd; (void)ad; (void)a0_p3; (void)af_p3; (void)a0_p4; (void)af_p4; (void)vd_vd;     \
     (void)ad_ad; (void)tf_tf; (void)g1; (void)g2; (void)j_max_j_max; (void)v_max; (void)v_min; (void)a_min; (void)a0_a0;   \
     (void)af_af; (void)a0; (void)af; (void)tf; (void)a_max; (void)j_max;                                                    \
@@ -63,7 +63,7 @@ __device__ __noinline__ bool s2_acc0_acc1_vel(const S2& s, const Lim& L, Hit& h)
     RK_S2_LOCALS
     // Profile UDDU, Solution 1
     if ((2.0 * (a_max - a_min) + ad) / j_max < tf) {
-        const double h1 = sqrt((a0_p4 + af_p4 - 4.0 * a0_p3 * (2.0 * a_max + a_min) / 3.0 - 4.0 * af_p3 * (a_max + 2.0 * a_min) / 3.0
+        const real h1 = sqrt((a0_p4 + af_p4 - 4.0 * a0_p3 * (2.0 * a_max + a_min) / 3.0 - 4.0 * af_p3 * (a_max + 2.0 * a_min) / 3.0
                                 + 2.0 * (a0_a0 - af_af) * a_max * a_max
                                 + (4.0 * a0 * a_max - 2.0 * a0_a0) * (af_af - 2.0 * af * a_min + (a_min - a_max) * a_min + 2.0 * j_max * (a_min * tf - vd))
                                 + 2.0 * af_af * (a_min * a_min + 2.0 * j_max * (a_max * tf - vd))
@@ -107,26 +107,26 @@ __device__ __noinline__ bool s2_acc1_vel(const S2& s, const Lim& L, Hit& h) {
     RK_S2_LOCALS
     // Profile UDDU
     {
-        const double ph1 = a0_a0 + af_af - a_min * (a0 + 2.0 * af - a_min) - 2.0 * j_max * (vd - a_min * tf);
-        const double ph2 = 2.0 * a_min * (j_max * g1 + af * vd) - a_min * a_min * vd + j_max * vd_vd;
-        const double ph3 = af_af + a_min * (a_min - 2.0 * af) - 2.0 * j_max * (vd - a_min * tf);
-        const double c0 = (2.0 * (2.0 * a0 - a_min)) / j_max;
-        const double c1 = (4.0 * a0_a0 + ph1 - 3.0 * a0 * a_min) / j_max_j_max;
-        const double c2 = (2.0 * a0 * ph1) / (j_max_j_max * j_max);
-        const double c3 = (3.0 * (a0_p4 + af_p4) - 4.0 * (a0_p3 + 2.0 * af_p3) * a_min + 6.0 * af_af * (a_min * a_min - 2.0 * j_max * vd)
+        const real ph1 = a0_a0 + af_af - a_min * (a0 + 2.0 * af - a_min) - 2.0 * j_max * (vd - a_min * tf);
+        const real ph2 = 2.0 * a_min * (j_max * g1 + af * vd) - a_min * a_min * vd + j_max * vd_vd;
+        const real ph3 = af_af + a_min * (a_min - 2.0 * af) - 2.0 * j_max * (vd - a_min * tf);
+        const real c0 = (2.0 * (2.0 * a0 - a_min)) / j_max;
+        const real c1 = (4.0 * a0_a0 + ph1 - 3.0 * a0 * a_min) / j_max_j_max;
+        const real c2 = (2.0 * a0 * ph1) / (j_max_j_max * j_max);
+        const real c3 = (3.0 * (a0_p4 + af_p4) - 4.0 * (a0_p3 + 2.0 * af_p3) * a_min + 6.0 * af_af * (a_min * a_min - 2.0 * j_max * vd)
                            + 12.0 * j_max * ph2 + 6.0 * a0_a0 * ph3)
                           / (12.0 * j_max_j_max * j_max_j_max);
-        const double t_min = -a0 / j_max;
-        const double t_max = rmin((tf + 2.0 * a_min / j_max - (a0 + af) / j_max) / 2.0, (a_max - a0) / j_max);
+        const real t_min = -a0 / j_max;
+        const real t_max = rmin((tf + 2.0 * a_min / j_max - (a0 + af) / j_max) / 2.0, (a_max - a0) / j_max);
         const Roots roots = solve_quart_monic(c0, c1, c2, c3);
 #pragma unroll 1
         for (int ri = 0; ri < roots.n; ++ri) {
-            double tt = roots.get(ri);
+            real tt = roots.get(ri);
             if (tt < t_min || tt > t_max) continue;
             // Single Newton step (regarding pd)
             if (fabs(a0 + j_max * tt) > 16.0 * EPS) {
-                const double h0 = j_max * tt * tt;
-                const double orig = -pd
+                const real h0 = j_max * tt * tt;
+                const real orig = -pd
                                     + (3.0 * (a0_p4 + af_p4) - 8.0 * af_p3 * a_min - 4.0 * a0_p3 * a_min
                                        + 6.0 * af_af * (a_min * a_min + 2.0 * j_max * (h0 - vd))
                                        + 6.0 * a0_a0 * (af_af - 2.0 * af * a_min + a_min * a_min + 2.0 * a_min * j_max * (-2.0 * tt + tf) + 2.0 * j_max * (5.0 * h0 - vd))
@@ -135,11 +135,11 @@ __device__ __noinline__ bool s2_acc1_vel(const S2& s, const Lim& L, Hit& h) {
                                        + 12.0 * j_max * (a_min * a_min * (h0 - vd) + j_max * (h0 - vd) * (h0 - vd)))
                                           / (24.0 * a_min * j_max_j_max)
                                     + h0 * (tf - tt) + tf * v0;
-                const double deriv = (a0 + j_max * tt)
+                const real deriv = (a0 + j_max * tt)
                                      * ((a0_a0 + af_af) / (a_min * j_max) + (a_min - a0 - 2.0 * af) / j_max + (4.0 * a0 * tt + 2.0 * h0 - 2.0 * vd) / a_min + 2.0 * tf - 3.0 * tt);
                 tt -= orig / deriv;
             }
-            const double h1 = -((a0_a0 + af_af) / 2.0 + j_max * (-vd + 2.0 * a0 * tt + j_max * tt * tt)) / a_min;
+            const real h1 = -((a0_a0 + af_af) / 2.0 + j_max * (-vd + 2.0 * a0 * tt + j_max * tt * tt)) / a_min;
             t[0] = tt;
             t[1] = 0.0;
             t[2] = a0 / j_max + tt;
@@ -152,24 +152,24 @@ __device__ __noinline__ bool s2_acc1_vel(const S2& s, const Lim& L, Hit& h) {
     }
     // Profile UDUD
     {
-        const double ph1 = a0_a0 - af_af + (2.0 * af - a0) * a_max - a_max * a_max - 2.0 * j_max * (vd - a_max * tf);
-        const double ph2 = a_max * a_max + 2.0 * j_max * vd;
-        const double ph3 = af_af + ph2 - 2.0 * a_max * (af + j_max * tf);
-        const double ph4 = 2.0 * a_max * j_max * g1 + a_max * a_max * vd + j_max * vd_vd;
-        const double c0 = (4.0 * a0 - 2.0 * a_max) / j_max;
-        const double c1 = (4.0 * a0_a0 - 3.0 * a0 * a_max + ph1) / j_max_j_max;
-        const double c2 = (2.0 * a0 * ph1) / (j_max_j_max * j_max);
-        const double c3 = (3.0 * (a0_p4 + af_p4) - 4.0 * (a0_p3 + 2.0 * af_p3) * a_max - 24.0 * af * a_max * j_max * vd + 12.0 * j_max * ph4
+        const real ph1 = a0_a0 - af_af + (2.0 * af - a0) * a_max - a_max * a_max - 2.0 * j_max * (vd - a_max * tf);
+        const real ph2 = a_max * a_max + 2.0 * j_max * vd;
+        const real ph3 = af_af + ph2 - 2.0 * a_max * (af + j_max * tf);
+        const real ph4 = 2.0 * a_max * j_max * g1 + a_max * a_max * vd + j_max * vd_vd;
+        const real c0 = (4.0 * a0 - 2.0 * a_max) / j_max;
+        const real c1 = (4.0 * a0_a0 - 3.0 * a0 * a_max + ph1) / j_max_j_max;
+        const real c2 = (2.0 * a0 * ph1) / (j_max_j_max * j_max);
+        const real c3 = (3.0 * (a0_p4 + af_p4) - 4.0 * (a0_p3 + 2.0 * af_p3) * a_max - 24.0 * af * a_max * j_max * vd + 12.0 * j_max * ph4
                            - 6.0 * a0_a0 * ph3 + 6.0 * af_af * ph2)
                           / (12.0 * j_max_j_max * j_max_j_max);
-        const double t_min = -a0 / j_max;
-        const double t_max = rmin((tf + ad / j_max - 2.0 * a_max / j_max) / 2.0, (a_max - a0) / j_max);
+        const real t_min = -a0 / j_max;
+        const real t_max = rmin((tf + ad / j_max - 2.0 * a_max / j_max) / 2.0, (a_max - a0) / j_max);
         const Roots roots = solve_quart_monic(c0, c1, c2, c3);
 #pragma unroll 1
         for (int ri = 0; ri < roots.n; ++ri) {
-            const double tt = roots.get(ri);
+            const real tt = roots.get(ri);
             if (tt > t_max || tt < t_min) continue;
-            const double h1 = ((a0_a0 - af_af) / 2.0 + j_max_j_max * tt * tt - j_max * (vd - 2.0 * a0 * tt)) / a_max;
+            const real h1 = ((a0_a0 - af_af) / 2.0 + j_max_j_max * tt * tt - j_max * (vd - 2.0 * a0 * tt)) / a_max;
             t[0] = tt;
             t[1] = 0.0;
             t[2] = tt + a0 / j_max;
@@ -188,36 +188,36 @@ __device__ __noinline__ bool s2_acc0_vel(const S2& s, const Lim& L, Hit& h) {
     RK_S2_LOCALS
     if (tf < rmax((-a0 + a_max) / j_max, 0.0) + rmax(a_max / j_max, 0.0)) return false;
 
-    const double ph1 = 12.0 * j_max * (-a_max * a_max * vd - j_max * vd_vd + 2.0 * a_max * j_max * (-pd + tf * vf));
+    const real ph1 = 12.0 * j_max * (-a_max * a_max * vd - j_max * vd_vd + 2.0 * a_max * j_max * (-pd + tf * vf));
     // Profile UDDU
     {
-        const double c0 = (2.0 * a_max) / j_max;
-        const double c1 = (a0_a0 - af_af + 2.0 * ad * a_max + a_max * a_max + 2.0 * j_max * (vd - a_max * tf)) / j_max_j_max;
-        const double c2 = 0.0;
-        const double c3 = -(-3.0 * (a0_p4 + af_p4) + 4.0 * (af_p3 + 2.0 * a0_p3) * a_max - 12.0 * a0 * a_max * (af_af - 2.0 * j_max * vd)
+        const real c0 = (2.0 * a_max) / j_max;
+        const real c1 = (a0_a0 - af_af + 2.0 * ad * a_max + a_max * a_max + 2.0 * j_max * (vd - a_max * tf)) / j_max_j_max;
+        const real c2 = 0.0;
+        const real c3 = -(-3.0 * (a0_p4 + af_p4) + 4.0 * (af_p3 + 2.0 * a0_p3) * a_max - 12.0 * a0 * a_max * (af_af - 2.0 * j_max * vd)
                             + 6.0 * a0_a0 * (af_af - a_max * a_max - 2.0 * j_max * vd)
                             + 6.0 * af_af * (a_max * a_max - 2.0 * a_max * j_max * tf + 2.0 * j_max * vd) + ph1)
                           / (12.0 * j_max_j_max * j_max_j_max);
-        const double t_min = -af / j_max;
-        const double t_max = rmin(tf - (2.0 * a_max - a0) / j_max, -a_min / j_max);
+        const real t_min = -af / j_max;
+        const real t_max = rmin(tf - (2.0 * a_max - a0) / j_max, -a_min / j_max);
         const Roots roots = solve_quart_monic(c0, c1, c2, c3);
 #pragma unroll 1
         for (int ri = 0; ri < roots.n; ++ri) {
-            double tt = roots.get(ri);
+            real tt = roots.get(ri);
             if (tt < t_min || tt > t_max) continue;
             // Single Newton step (regarding pd)
             if (tt > EPS) {
-                const double h1 = j_max * tt * tt + vd;
-                const double orig = (-3.0 * (a0_p4 + af_p4) + 4.0 * (af_p3 + 2.0 * a0_p3) * a_max - 24.0 * af * a_max * j_max_j_max * tt * tt
+                const real h1 = j_max * tt * tt + vd;
+                const real orig = (-3.0 * (a0_p4 + af_p4) + 4.0 * (af_p3 + 2.0 * a0_p3) * a_max - 24.0 * af * a_max * j_max_j_max * tt * tt
                                      - 12.0 * a0 * a_max * (af_af - 2.0 * j_max * h1)
                                      + 6.0 * a0_a0 * (af_af - a_max * a_max - 2.0 * j_max * h1)
                                      + 6.0 * af_af * (a_max * a_max - 2.0 * a_max * j_max * tf + 2.0 * j_max * h1)
                                      - 12.0 * j_max * (a_max * a_max * h1 + j_max * h1 * h1 + 2.0 * a_max * j_max * (pd + j_max * tt * tt * (tt - tf) - tf * vf)))
                                     / (24.0 * a_max * j_max_j_max);
-                const double deriv = -tt * (a0_a0 - af_af + 2.0 * a_max * (ad - j_max * tf) + a_max * a_max + 3.0 * a_max * j_max * tt + 2.0 * j_max * h1) / a_max;
+                const real deriv = -tt * (a0_a0 - af_af + 2.0 * a_max * (ad - j_max * tf) + a_max * a_max + 3.0 * a_max * j_max * tt + 2.0 * j_max * h1) / a_max;
                 tt -= orig / deriv;
             }
-            const double h1 = ((a0_a0 - af_af) / 2.0 + j_max * (j_max * tt * tt + vd)) / a_max;
+            const real h1 = ((a0_a0 - af_af) / 2.0 + j_max * (j_max * tt * tt + vd)) / a_max;
             t[0] = (-a0 + a_max) / j_max;
             t[1] = (h1 - a_max) / j_max;
             t[2] = a_max / j_max;
@@ -230,33 +230,33 @@ __device__ __noinline__ bool s2_acc0_vel(const S2& s, const Lim& L, Hit& h) {
     }
     // Profile UDUD
     {
-        const double c0 = (-2.0 * a_max) / j_max;
-        const double c1 = -(a0_a0 + af_af - 2.0 * (a0 + af) * a_max + a_max * a_max + 2.0 * j_max * (vd - a_max * tf)) / j_max_j_max;
-        const double c2 = 0.0;
-        const double c3 = (3.0 * (a0_p4 + af_p4) - 4.0 * (af_p3 + 2.0 * a0_p3) * a_max + 6.0 * a0_a0 * (af_af + a_max * a_max + 2.0 * j_max * vd)
+        const real c0 = (-2.0 * a_max) / j_max;
+        const real c1 = -(a0_a0 + af_af - 2.0 * (a0 + af) * a_max + a_max * a_max + 2.0 * j_max * (vd - a_max * tf)) / j_max_j_max;
+        const real c2 = 0.0;
+        const real c3 = (3.0 * (a0_p4 + af_p4) - 4.0 * (af_p3 + 2.0 * a0_p3) * a_max + 6.0 * a0_a0 * (af_af + a_max * a_max + 2.0 * j_max * vd)
                            - 12.0 * a0 * a_max * (af_af + 2.0 * j_max * vd)
                            + 6.0 * af_af * (a_max * a_max - 2.0 * a_max * j_max * tf + 2.0 * j_max * vd) - ph1)
                           / (12.0 * j_max_j_max * j_max_j_max);
-        const double t_min = af / j_max;
-        const double t_max = rmin(tf - a_max / j_max, a_max / j_max);
+        const real t_min = af / j_max;
+        const real t_max = rmin(tf - a_max / j_max, a_max / j_max);
         const Roots roots = solve_quart_monic(c0, c1, c2, c3);
 #pragma unroll 1
         for (int ri = 0; ri < roots.n; ++ri) {
-            double tt = roots.get(ri);
+            real tt = roots.get(ri);
             if (tt < t_min || tt > t_max) continue;
             // Single Newton step (regarding pd)
             {
-                const double h1 = j_max * tt * tt - vd;
-                const double orig = -(3.0 * (a0_p4 + af_p4) - 4.0 * (2.0 * a0_p3 + af_p3) * a_max + 24.0 * af * a_max * j_max_j_max * tt * tt
+                const real h1 = j_max * tt * tt - vd;
+                const real orig = -(3.0 * (a0_p4 + af_p4) - 4.0 * (2.0 * a0_p3 + af_p3) * a_max + 24.0 * af * a_max * j_max_j_max * tt * tt
                                       - 12.0 * a0 * a_max * (af_af - 2.0 * j_max * h1)
                                       + 6.0 * a0_a0 * (af_af + a_max * a_max - 2.0 * j_max * h1)
                                       + 6.0 * af_af * (a_max * a_max - 2.0 * j_max * (tf * a_max + h1))
                                       + 12.0 * j_max * (-a_max * a_max * h1 + j_max * h1 * h1 - 2.0 * a_max * j_max * (-pd + j_max * tt * tt * (tt - tf) + tf * vf)))
                                     / (24.0 * a_max * j_max_j_max);
-                const double deriv = tt * (a0_a0 + af_af - 2.0 * j_max * h1 - 2.0 * (a0 + af + j_max * tf) * a_max + a_max * a_max + 3.0 * a_max * j_max * tt) / a_max;
+                const real deriv = tt * (a0_a0 + af_af - 2.0 * j_max * h1 - 2.0 * (a0 + af + j_max * tf) * a_max + a_max * a_max + 3.0 * a_max * j_max * tt) / a_max;
                 tt -= orig / deriv;
             }
-            const double h1 = ((a0_a0 + af_af) / 2.0 + j_max * (vd - j_max * tt * tt)) / a_max;
+            const real h1 = ((a0_a0 + af_af) / 2.0 + j_max * (vd - j_max * tt * tt)) / a_max;
             t[0] = (-a0 + a_max) / j_max;
             t[1] = (h1 - a_max) / j_max;
             t[2] = a_max / j_max;

@@ -12,9 +12,9 @@ __device__ __forceinline__ double sq(double x) { return x * x; }  // roots.rs:14
 __device__ __noinline__ bool s2_acc0_acc1(const S2& s, const Lim& L, Hit& h) {
     RK_S2_LOCALS
     if (fabs(a0) < EPS && fabs(af) < EPS) {
-        const double h1 = 2.0 * a_min * g1 + vd_vd + a_max * (2.0 * pd + a_min * tf_tf - 2.0 * tf * vf);
-        const double h2 = (a_max - a_min) * (-a_min * vd + a_max * (a_min * tf - vd));
-        const double jf = h2 / h1;
+        const real h1 = 2.0 * a_min * g1 + vd_vd + a_max * (2.0 * pd + a_min * tf_tf - 2.0 * tf * vf);
+        const real h2 = (a_max - a_min) * (-a_min * vd + a_max * (a_min * tf - vd));
+        const real jf = h2 / h1;
         t[0] = a_max / jf;
         t[1] = (-2.0 * a_max * h1 + a_min * a_min * g2) / h2;
         t[2] = t[0];
@@ -27,7 +27,7 @@ __device__ __noinline__ bool s2_acc0_acc1(const S2& s, const Lim& L, Hit& h) {
     }
     // UDDU
     {
-        const double h1 = sqrt(144.0 * sq((a_max - a_min) * (-a_min * vd + a_max * (a_min * tf - vd)) - af_af * (a_max * tf - vd)
+        const real h1 = sqrt(144.0 * sq((a_max - a_min) * (-a_min * vd + a_max * (a_min * tf - vd)) - af_af * (a_max * tf - vd)
                                           + 2.0 * af * a_min * (a_max * tf - vd) + a0_a0 * (a_min * tf + v0 - vf) - 2.0 * a0 * a_max * (a_min * tf - vd))
                                + 48.0 * ad
                                      * (3.0 * a0_p3 - 3.0 * af_p3 + 12.0 * a_max * a_min * (-a_max + a_min) + 4.0 * af_af * (a_max + 2.0 * a_min)
@@ -35,7 +35,7 @@ __device__ __noinline__ bool s2_acc0_acc1(const S2& s, const Lim& L, Hit& h) {
                                         + 6.0 * af * (a_max * a_max - 2.0 * a_max * a_min - a_min * a_min)
                                         + a0_a0 * (3.0 * af - 4.0 * (2.0 * a_max + a_min)))
                                      * (2.0 * a_min * g1 + vd * vd + a_max * (2.0 * pd + a_min * tf * tf - 2.0 * tf * vf)));
-        const double jf = -(3.0 * af_af * a_max * tf - 3.0 * a0_a0 * a_min * tf - 6.0 * ad * a_max * a_min * tf + 3.0 * a_max * a_min * (a_min - a_max) * tf
+        const real jf = -(3.0 * af_af * a_max * tf - 3.0 * a0_a0 * a_min * tf - 6.0 * ad * a_max * a_min * tf + 3.0 * a_max * a_min * (a_min - a_max) * tf
                             + 3.0 * (a0_a0 - af_af) * vd + 6.0 * vd * (af * a_min - a0 * a_max) + 3.0 * (a_max * a_max - a_min * a_min) * vd + h1 / 4.0)
                           / (6.0 * (2.0 * a_min * g1 + vd * vd + a_max * (2.0 * pd + a_min * tf_tf - 2.0 * tf * vf)));
         t[0] = (a_max - a0) / jf;
@@ -56,14 +56,14 @@ __device__ __noinline__ bool s2_acc1(const S2& s, const Lim& L, Hit& h) {
     RK_S2_LOCALS
     // a3 != 0, case UDDU
     {
-        const double h0 = sqrt(j_max_j_max
+        const real h0 = sqrt(j_max_j_max
                                * (a0_p4 + af_p4 - 4.0 * af_p3 * j_max * tf + 6.0 * af_af * j_max_j_max * tf_tf - 4.0 * a0_p3 * (af - j_max * tf)
                                   + 6.0 * a0_a0 * (af - j_max * tf) * (af - j_max * tf) + 24.0 * af * j_max_j_max * g1
                                   - 4.0 * a0 * (af_p3 - 3.0 * af_af * j_max * tf + 6.0 * j_max_j_max * (-pd + tf * vf))
                                   - 12.0 * j_max_j_max * (-vd_vd + j_max * tf * g2))
                                / 3.0)
                           / j_max;
-        const double h1 = sqrt((a0_a0 + af_af - 2.0 * a0 * af - 2.0 * ad * j_max * tf + 2.0 * h0) / j_max_j_max + tf_tf);
+        const real h1 = sqrt((a0_a0 + af_af - 2.0 * a0 * af - 2.0 * ad * j_max * tf + 2.0 * h0) / j_max_j_max + tf_tf);
         t[0] = -(a0_a0 + af_af + 2.0 * a0 * (j_max * tf - af) - 2.0 * j_max * vd + h0) / (2.0 * j_max * (-ad + j_max * tf));
         t[1] = 0.0;
         t[2] = (tf - h1) / 2.0 - ad / (2.0 * j_max);
@@ -75,14 +75,14 @@ __device__ __noinline__ bool s2_acc1(const S2& s, const Lim& L, Hit& h) {
     }
     // case UDUD
     {
-        const double h0 = sqrt(j_max_j_max
+        const real h0 = sqrt(j_max_j_max
                                * (a0_p4 + af_p4 + 4.0 * (af_p3 - a0_p3) * j_max * tf + 6.0 * af_af * j_max_j_max * tf_tf
                                   + 6.0 * a0_a0 * (af + j_max * tf) * (af + j_max * tf) + 24.0 * af * j_max_j_max * g1
                                   - 4.0 * a0 * (a0_a0 * af + af_p3 + 3.0 * af_af * j_max * tf + 6.0 * j_max_j_max * (-pd + tf * vf))
                                   + 12.0 * j_max_j_max * (vd_vd + j_max * tf * g2))
                                / 3.0)
                           / j_max;
-        const double h1 = sqrt((a0_a0 + af_af - 2.0 * a0 * af + 2.0 * ad * j_max * tf + 2.0 * h0) / j_max_j_max + tf_tf);
+        const real h1 = sqrt((a0_a0 + af_af - 2.0 * a0 * af + 2.0 * ad * j_max * tf + 2.0 * h0) / j_max_j_max + tf_tf);
         t[0] = 0.0;
         t[1] = 0.0;
         t[2] = -(a0_a0 + af_af - 2.0 * a0 * af + 2.0 * j_max * (vd - a0 * tf) + h0) / (2.0 * j_max * (ad + j_max * tf));
@@ -94,17 +94,17 @@ __device__ __noinline__ bool s2_acc1(const S2& s, const Lim& L, Hit& h) {
     }
     // case UDDU, solution 2
     {
-        const double h0a = a0_p3 - af_p3 - 3.0 * a0_a0 * a_min + 3.0 * a_min * a_min * (a0 + j_max * tf) + 3.0 * af * a_min * (-a_min - 2.0 * j_max * tf)
+        const real h0a = a0_p3 - af_p3 - 3.0 * a0_a0 * a_min + 3.0 * a_min * a_min * (a0 + j_max * tf) + 3.0 * af * a_min * (-a_min - 2.0 * j_max * tf)
                            - 3.0 * af_af * (-a_min - j_max * tf) - 3.0 * j_max_j_max * (-2.0 * pd - a_min * tf_tf + 2.0 * tf * vf);
-        const double h0b = a0_a0 + af_af - 2.0 * (a0 + af) * a_min + 2.0 * (a_min * a_min - j_max * (-a_min * tf + vd));
-        const double h0c = a0_p4 + 3.0 * af_p4 - 4.0 * (a0_p3 + 2.0 * af_p3) * a_min + 6.0 * a0_a0 * a_min * a_min
+        const real h0b = a0_a0 + af_af - 2.0 * (a0 + af) * a_min + 2.0 * (a_min * a_min - j_max * (-a_min * tf + vd));
+        const real h0c = a0_p4 + 3.0 * af_p4 - 4.0 * (a0_p3 + 2.0 * af_p3) * a_min + 6.0 * a0_a0 * a_min * a_min
                            + 6.0 * af_af * (a_min * a_min - 2.0 * j_max * vd)
                            + 12.0 * j_max * (2.0 * a_min * j_max * g1 - a_min * a_min * vd + j_max * vd_vd) + 24.0 * af * a_min * j_max * vd
                            - 4.0 * a0
                                  * (af_p3 - 3.0 * af * a_min * (-a_min - 2.0 * j_max * tf) + 3.0 * af_af * (-a_min - j_max * tf)
                                     + 3.0 * j_max * (-a_min * a_min * tf + j_max * (-2.0 * pd - a_min * tf_tf + 2.0 * tf * vf)));
-        const double h1 = fabs(j_max) / j_max * sqrt(4.0 * h0a * h0a - 6.0 * h0b * h0c);
-        const double h2 = 6.0 * j_max * h0b;
+        const real h1 = fabs(j_max) / j_max * sqrt(4.0 * h0a * h0a - 6.0 * h0b * h0c);
+        const real h2 = 6.0 * j_max * h0b;
         t[0] = 0.0;
         t[1] = 0.0;
         t[2] = (2.0 * h0a + h1) / h2;
@@ -116,16 +116,16 @@ __device__ __noinline__ bool s2_acc1(const S2& s, const Lim& L, Hit& h) {
     }
     // case UDUD, solution 1
     {
-        const double h0a = -a0_p3 + af_p3 + 3.0 * (a0_a0 - af_af) * a_max - 3.0 * ad * a_max * a_max - 6.0 * af * a_max * j_max * tf + 3.0 * af_af * j_max * tf
+        const real h0a = -a0_p3 + af_p3 + 3.0 * (a0_a0 - af_af) * a_max - 3.0 * ad * a_max * a_max - 6.0 * af * a_max * j_max * tf + 3.0 * af_af * j_max * tf
                            + 3.0 * j_max * (a_max * a_max * tf + j_max * (-2.0 * pd - a_max * tf_tf + 2.0 * tf * vf));
-        const double h0b = a0_a0 - af_af + 2.0 * ad * a_max + 2.0 * j_max * (a_max * tf - vd);
-        const double h0c = a0_p4 + 3.0 * af_p4 - 4.0 * (a0_p3 + 2.0 * af_p3) * a_max + 6.0 * a0_a0 * a_max * a_max - 24.0 * af * a_max * j_max * vd
+        const real h0b = a0_a0 - af_af + 2.0 * ad * a_max + 2.0 * j_max * (a_max * tf - vd);
+        const real h0c = a0_p4 + 3.0 * af_p4 - 4.0 * (a0_p3 + 2.0 * af_p3) * a_max + 6.0 * a0_a0 * a_max * a_max - 24.0 * af * a_max * j_max * vd
                            + 12.0 * j_max * (2.0 * a_max * j_max * g1 + j_max * vd_vd + a_max * a_max * vd) + 6.0 * af_af * (a_max * a_max + 2.0 * j_max * vd)
                            - 4.0 * a0
                                  * (af_p3 + 3.0 * af * a_max * (a_max - 2.0 * j_max * tf) - 3.0 * af_af * (a_max - j_max * tf)
                                     + 3.0 * j_max * (a_max * a_max * tf + j_max * (-2.0 * pd - a_max * tf_tf + 2.0 * tf * vf)));
-        const double h1 = fabs(j_max) / j_max * sqrt(4.0 * h0a * h0a - 6.0 * h0b * h0c);
-        const double h2 = 6.0 * j_max * h0b;
+        const real h1 = fabs(j_max) / j_max * sqrt(4.0 * h0a * h0a - 6.0 * h0b * h0c);
+        const real h2 = 6.0 * j_max * h0b;
         t[0] = 0.0;
         t[1] = 0.0;
         t[2] = -(2.0 * h0a + h1) / h2;
@@ -143,7 +143,7 @@ __device__ __noinline__ bool s2_acc0(const S2& s, const Lim& L, Hit& h) {
     RK_S2_LOCALS
     // UDUD
     {
-        const double h1 = sqrt(ad_ad / (2.0 * j_max_j_max) - ad * (a_max - a0) / (j_max_j_max) + (a_max * tf - vd) / j_max);
+        const real h1 = sqrt(ad_ad / (2.0 * j_max_j_max) - ad * (a_max - a0) / (j_max_j_max) + (a_max * tf - vd) / j_max);
         t[0] = (a_max - a0) / j_max;
         t[1] = tf - ad / j_max - 2.0 * h1;
         t[2] = h1;
@@ -155,12 +155,12 @@ __device__ __noinline__ bool s2_acc0(const S2& s, const Lim& L, Hit& h) {
     }
     // UDUD
     {
-        const double h0a = -a0_a0 + af_af - 2.0 * ad * a_max + 2.0 * j_max * (a_max * tf - vd);
-        const double h0b = a0_p3 + 2.0 * af_p3 - 6.0 * af_af * a_max - 3.0 * a0_a0 * (af - j_max * tf) - 3.0 * a0 * a_max * (a_max - 2.0 * af + 2.0 * j_max * tf)
+        const real h0a = -a0_a0 + af_af - 2.0 * ad * a_max + 2.0 * j_max * (a_max * tf - vd);
+        const real h0b = a0_p3 + 2.0 * af_p3 - 6.0 * af_af * a_max - 3.0 * a0_a0 * (af - j_max * tf) - 3.0 * a0 * a_max * (a_max - 2.0 * af + 2.0 * j_max * tf)
                            - 3.0 * j_max * (j_max * (-2.0 * pd + a_max * tf_tf + 2.0 * tf * v0) + a_max * (a_max * tf - 2.0 * vd))
                            + 3.0 * af * (a_max * a_max + 2.0 * a_max * j_max * tf - 2.0 * j_max * vd);
-        const double h0 = fabs(j_max) * sqrt(4.0 * h0b * h0b - 18.0 * h0a * h0a * h0a);
-        const double h1 = 3.0 * j_max * h0a;
+        const real h0 = fabs(j_max) * sqrt(4.0 * h0b * h0b - 18.0 * h0a * h0a * h0a);
+        const real h1 = 3.0 * j_max * h0a;
         t[0] = (-a0 + a_max) / j_max;
         t[1] = (-a0_p3 + af_p3 + af_af * (-6.0 * a_max + 3.0 * j_max * tf) + a0_a0 * (-3.0 * af + 6.0 * a_max + 3.0 * j_max * tf)
                 + 6.0 * af * (a_max * a_max - j_max * vd) + 3.0 * a0 * (af_af - 2.0 * (a_max * a_max + j_max * vd))
@@ -175,12 +175,12 @@ __device__ __noinline__ bool s2_acc0(const S2& s, const Lim& L, Hit& h) {
     }
     // a3 != 0, UDDU solution 1
     {
-        const double h0a = a0_p3 + 2.0 * af_p3 - 6.0 * (af_af + a_max * a_max) * a_max - 6.0 * (a0 + af) * a_max * j_max * tf + 9.0 * a_max * a_max * (af + j_max * tf)
+        const real h0a = a0_p3 + 2.0 * af_p3 - 6.0 * (af_af + a_max * a_max) * a_max - 6.0 * (a0 + af) * a_max * j_max * tf + 9.0 * a_max * a_max * (af + j_max * tf)
                            + 3.0 * a0 * a_max * (-2.0 * af + 3.0 * a_max) + 3.0 * a0_a0 * (af - 2.0 * a_max + j_max * tf) - 6.0 * j_max_j_max * g1
                            + 6.0 * (af - a_max) * j_max * vd - 3.0 * a_max * j_max_j_max * tf_tf;
-        const double h0b = a0_a0 + af_af + 2.0 * (a_max * a_max - (a0 + af) * a_max + j_max * (vd - a_max * tf));
-        const double h1 = fabs(j_max) / j_max * sqrt(4.0 * h0a * h0a - 18.0 * h0b * h0b * h0b);
-        const double h2 = 6.0 * j_max * h0b;
+        const real h0b = a0_a0 + af_af + 2.0 * (a_max * a_max - (a0 + af) * a_max + j_max * (vd - a_max * tf));
+        const real h1 = fabs(j_max) / j_max * sqrt(4.0 * h0a * h0a - 18.0 * h0b * h0b * h0b);
+        const real h2 = 6.0 * j_max * h0b;
         t[0] = (-a0 + a_max) / j_max;
         t[1] = ad / j_max - 2.0 * t[0] - (2.0 * h0a - h1) / h2 + tf;
         t[2] = -(2.0 * h0a + h1) / h2;

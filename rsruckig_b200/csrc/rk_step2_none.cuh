@@ -9,11 +9,11 @@ namespace rk {
 
 __device__ __noinline__ bool s2_none(const S2& s, const Lim& L, Hit& h) {
     RK_S2_LOCALS
-    const double vf_vf = s.vf_vf, tf_p3 = s.tf_p3, tf_p4 = s.tf_p4, a0_p5 = s.a0_p5, a0_p6 = s.a0_p6, af_p5 = s.af_p5, af_p6 = s.af_p6;
+    const real vf_vf = s.vf_vf, tf_p3 = s.tf_p3, tf_p4 = s.tf_p4, a0_p5 = s.a0_p5, a0_p6 = s.a0_p6, af_p5 = s.af_p5, af_p6 = s.af_p6;
 
     if (fabs(v0) < EPS && fabs(a0) < EPS && fabs(af) < EPS) {
-        const double h1 = sqrt(tf_tf * vf_vf + sq(4.0 * pd - tf * vf));
-        const double jf = 4.0 * (4.0 * pd - 2.0 * tf * vf + h1) / tf_p3;
+        const real h1 = sqrt(tf_tf * vf_vf + sq(4.0 * pd - tf * vf));
+        const real jf = 4.0 * (4.0 * pd - 2.0 * tf * vf + h1) / tf_p3;
         t[0] = tf / 4.0;
         t[1] = 0.0;
         t[2] = 2.0 * t[0];
@@ -26,21 +26,21 @@ __device__ __noinline__ bool s2_none(const S2& s, const Lim& L, Hit& h) {
 
     if (fabs(a0) < EPS && fabs(af) < EPS) {
         // a3 != 0, UDDU: first acc, then constant
-        const double c0 = -2.0 * tf;
-        const double c1 = 2.0 * vd / j_max + tf_tf;
-        const double c2 = 4.0 * (pd - tf * vf) / j_max;
-        const double c3 = (vd_vd + j_max * tf * g2) / (j_max_j_max);
+        const real c0 = -2.0 * tf;
+        const real c1 = 2.0 * vd / j_max + tf_tf;
+        const real c2 = 4.0 * (pd - tf * vf) / j_max;
+        const real c3 = (vd_vd + j_max * tf * g2) / (j_max_j_max);
         const Roots roots = solve_quart_monic(c0, c1, c2, c3);
 #pragma unroll 1
         for (int ri = 0; ri < roots.n; ++ri) {
-            double tt = roots.get(ri);
+            real tt = roots.get(ri);
             if (tt > tf / 2.0 || tt > (a_max - a0) / j_max) continue;
             // Single Newton step (regarding pd)
             {
-                const double h1 = (j_max * tt * (tt - tf) + vd) / (j_max * (2.0 * tt - tf));
-                const double h2 = (2.0 * j_max * tt * (tt - tf) + j_max * tf_tf - 2.0 * vd) / (j_max * (2.0 * tt - tf) * (2.0 * tt - tf));
-                const double orig = (-2.0 * pd + 2.0 * tf * v0 + h1 * h1 * j_max * (tf - 2.0 * tt) + j_max * tf * (2.0 * h1 * tt - tt * tt - (h1 - tt) * tf)) / 2.0;
-                const double deriv = (j_max * tf * (2.0 * tt - tf) * (h2 - 1.0)) / 2.0 + h1 * j_max * (tf - (2.0 * tt - tf) * h2 - h1);
+                const real h1 = (j_max * tt * (tt - tf) + vd) / (j_max * (2.0 * tt - tf));
+                const real h2 = (2.0 * j_max * tt * (tt - tf) + j_max * tf_tf - 2.0 * vd) / (j_max * (2.0 * tt - tf) * (2.0 * tt - tf));
+                const real orig = (-2.0 * pd + 2.0 * tf * v0 + h1 * h1 * j_max * (tf - 2.0 * tt) + j_max * tf * (2.0 * h1 * tt - tt * tt - (h1 - tt) * tf)) / 2.0;
+                const real deriv = (j_max * tf * (2.0 * tt - tf) * (h2 - 1.0)) / 2.0 + h1 * j_max * (tf - (2.0 * tt - tf) * h2 - h1);
                 tt -= orig / deriv;
             }
             t[0] = tt;
@@ -56,7 +56,7 @@ __device__ __noinline__ bool s2_none(const S2& s, const Lim& L, Hit& h) {
 
     // UDUD T 0246
     {
-        const double h0 = sqrt(2.0 * j_max_j_max
+        const real h0 = sqrt(2.0 * j_max_j_max
                                * (2.0 * sq(a0_p3 - af_p3 - 3.0 * af_af * j_max * tf + 9.0 * af * j_max_j_max * tf_tf - 3.0 * a0_a0 * (af + j_max * tf)
                                            + 3.0 * a0 * sq(af + j_max * tf) + 3.0 * j_max_j_max * (8.0 * pd + j_max * tf_tf * tf - 8.0 * tf * vf))
                                   - 3.0 * (a0_a0 + af_af - 2.0 * af * j_max * tf - 2.0 * a0 * (af + j_max * tf) - j_max * (j_max * tf_tf + 4.0 * v0 - 4.0 * vf))
@@ -67,10 +67,10 @@ __device__ __noinline__ bool s2_none(const S2& s, const Lim& L, Hit& h) {
                                            - 4.0 * a0 * (af_p3 + 3.0 * af_af * j_max * tf - 9.0 * af * j_max_j_max * tf_tf
                                                          - 3.0 * j_max_j_max * (8.0 * pd + j_max * tf_tf * tf - 8.0 * tf * vf)))))
                           / j_max;
-        const double h1 = 12.0 * j_max * (-a0_a0 - af_af + 2.0 * af * j_max * tf + 2.0 * a0 * (af + j_max * tf) + j_max * (j_max * tf_tf + 4.0 * v0 - 4.0 * vf));
-        const double h2 = -4.0 * a0_p3 + 4.0 * af_p3 + 12.0 * a0_a0 * af - 12.0 * a0 * af_af + 48.0 * j_max_j_max * pd + 12.0 * (a0_a0 - af_af) * j_max * tf
+        const real h1 = 12.0 * j_max * (-a0_a0 - af_af + 2.0 * af * j_max * tf + 2.0 * a0 * (af + j_max * tf) + j_max * (j_max * tf_tf + 4.0 * v0 - 4.0 * vf));
+        const real h2 = -4.0 * a0_p3 + 4.0 * af_p3 + 12.0 * a0_a0 * af - 12.0 * a0 * af_af + 48.0 * j_max_j_max * pd + 12.0 * (a0_a0 - af_af) * j_max * tf
                           - 24.0 * j_max_j_max * tf * (v0 + vf) + 24.0 * ad * j_max * vd;
-        const double h3 = 2.0 * a0_p3 - 2.0 * af_p3 - 6.0 * a0_a0 * af + 6.0 * a0 * af_af;
+        const real h3 = 2.0 * a0_p3 - 2.0 * af_p3 - 6.0 * a0_a0 * af + 6.0 * a0 * af_af;
         t[0] = (h3 - 48.0 * j_max_j_max * (tf * vf - pd) - 6.0 * (a0_a0 + af_af) * j_max * tf + 12.0 * a0 * af * j_max * tf
                 + 6.0 * (a0 + 3.0 * af + j_max * tf) * tf_tf * j_max_j_max - h0)
                / h1;
@@ -87,32 +87,32 @@ __device__ __noinline__ bool s2_none(const S2& s, const Lim& L, Hit& h) {
 
     // a3 != 0, UDDU — T 0234
     {
-        const double ph1 = af + j_max * tf;
-        const double c0 = -2.0 * (ad + j_max * tf) / j_max;
-        const double c1 = 2.0 * (a0_a0 + af_af + j_max * (af * tf + vd) - 2.0 * a0 * ph1) / j_max_j_max + tf_tf;
-        const double c2 = 2.0 * (a0_p3 - af_p3 - 3.0 * af_af * j_max * tf + 3.0 * a0 * ph1 * (ph1 - a0) - 6.0 * j_max_j_max * (-pd + tf * vf)) / (3.0 * j_max_j_max * j_max);
-        const double c3 = (a0_p4 + af_p4 + 4.0 * af_p3 * j_max * tf - 4.0 * a0_p3 * ph1 + 6.0 * a0_a0 * ph1 * ph1 + 24.0 * j_max_j_max * af * g1
+        const real ph1 = af + j_max * tf;
+        const real c0 = -2.0 * (ad + j_max * tf) / j_max;
+        const real c1 = 2.0 * (a0_a0 + af_af + j_max * (af * tf + vd) - 2.0 * a0 * ph1) / j_max_j_max + tf_tf;
+        const real c2 = 2.0 * (a0_p3 - af_p3 - 3.0 * af_af * j_max * tf + 3.0 * a0 * ph1 * (ph1 - a0) - 6.0 * j_max_j_max * (-pd + tf * vf)) / (3.0 * j_max_j_max * j_max);
+        const real c3 = (a0_p4 + af_p4 + 4.0 * af_p3 * j_max * tf - 4.0 * a0_p3 * ph1 + 6.0 * a0_a0 * ph1 * ph1 + 24.0 * j_max_j_max * af * g1
                            - 4.0 * a0 * (af_p3 + 3.0 * af_af * j_max * tf + 6.0 * j_max_j_max * (-pd + tf * vf)) + 6.0 * j_max_j_max * af_af * tf_tf
                            + 12.0 * j_max_j_max * (vd_vd + j_max * tf * g2))
                           / (12.0 * j_max_j_max * j_max_j_max);
-        const double t_min = ad / j_max;
-        const double t_max = rmin((a_max - a0) / j_max, (ad / j_max + tf) / 2.0);
+        const real t_min = ad / j_max;
+        const real t_max = rmin((a_max - a0) / j_max, (ad / j_max + tf) / 2.0);
         const Roots roots = solve_quart_monic(c0, c1, c2, c3);
 #pragma unroll 1
         for (int ri = 0; ri < roots.n; ++ri) {
-            double tt = roots.get(ri);
+            real tt = roots.get(ri);
             if (tt < t_min || tt > t_max) continue;
             // Single Newton step (regarding pd)
             {
-                const double h0 = j_max * (2.0 * tt - tf) - ad;
-                const double h1 = (ad_ad - 2.0 * af * j_max * tt + 2.0 * a0 * j_max * (tt - tf) + 2.0 * j_max * (j_max * tt * (tt - tf) + vd)) / (2.0 * j_max * h0);
-                const double h2 = (-ad_ad + 2.0 * j_max_j_max * (tf_tf + tt * (tt - tf)) + (a0 + af) * j_max * tf - ad * h0 - 2.0 * j_max * vd) / (h0 * h0);
-                const double orig = (-a0_p3 + af_p3 + 3.0 * ad_ad * j_max * (h1 - tt) + 3.0 * ad * j_max_j_max * (h1 - tt) * (h1 - tt) - 3.0 * a0 * af * ad
+                const real h0 = j_max * (2.0 * tt - tf) - ad;
+                const real h1 = (ad_ad - 2.0 * af * j_max * tt + 2.0 * a0 * j_max * (tt - tf) + 2.0 * j_max * (j_max * tt * (tt - tf) + vd)) / (2.0 * j_max * h0);
+                const real h2 = (-ad_ad + 2.0 * j_max_j_max * (tf_tf + tt * (tt - tf)) + (a0 + af) * j_max * tf - ad * h0 - 2.0 * j_max * vd) / (h0 * h0);
+                const real orig = (-a0_p3 + af_p3 + 3.0 * ad_ad * j_max * (h1 - tt) + 3.0 * ad * j_max_j_max * (h1 - tt) * (h1 - tt) - 3.0 * a0 * af * ad
                                      + 3.0 * j_max_j_max
                                            * (a0 * tf_tf - 2.0 * pd + 2.0 * tf * v0 + h1 * h1 * j_max * (tf - 2.0 * tt)
                                               + j_max * tf * (2.0 * h1 * tt - tt * tt - (h1 - tt) * tf)))
                                     / (6.0 * j_max_j_max);
-                const double deriv = (h0 * (-ad + j_max * tf) * (h2 - 1.0)) / (2.0 * j_max) + h1 * (-ad + j_max * (tf - h1) - h0 * h2);
+                const real deriv = (h0 * (-ad + j_max * tf) * (h2 - 1.0)) / (2.0 * j_max) + h1 * (-ad + j_max * (tf - h1) - h0 * h2);
                 tt -= orig / deriv;
             }
             t[0] = tt;
@@ -128,9 +128,9 @@ __device__ __noinline__ bool s2_none(const S2& s, const Lim& L, Hit& h) {
 
     // T 3456
     {
-        const double h1 = 3.0 * j_max * (ad_ad + 2.0 * j_max * (a0 * tf - vd));
-        const double h2 = ad_ad + 2.0 * j_max * (a0 * tf - vd);
-        const double h0 = sqrt(4.0 * sq(2.0 * (a0_p3 - af_p3) - 6.0 * a0_a0 * (af - j_max * tf) + 6.0 * j_max_j_max * g1
+        const real h1 = 3.0 * j_max * (ad_ad + 2.0 * j_max * (a0 * tf - vd));
+        const real h2 = ad_ad + 2.0 * j_max * (a0 * tf - vd);
+        const real h0 = sqrt(4.0 * sq(2.0 * (a0_p3 - af_p3) - 6.0 * a0_a0 * (af - j_max * tf) + 6.0 * j_max_j_max * g1
                                         + 3.0 * a0 * (2.0 * af_af - 2.0 * j_max * af * tf + j_max_j_max * tf_tf) + 6.0 * ad * j_max * vd)
                                - 18.0 * h2 * h2 * h2)
                           / h1 * fabs(j_max) / j_max;
@@ -146,29 +146,29 @@ __device__ __noinline__ bool s2_none(const S2& s, const Lim& L, Hit& h) {
 
     // T 2346
     {
-        const double ph1 = ad_ad + 2.0 * (af + a0) * j_max * tf - j_max * (j_max * tf_tf + 4.0 * vd);
-        const double ph2 = j_max * tf_tf * g1 - vd * (-2.0 * pd - tf * v0 + 3.0 * tf * vf);
-        const double ph3 = 5.0 * af_af - 8.0 * af * j_max * tf + 2.0 * j_max * (2.0 * j_max * tf_tf - vd);
-        const double ph4 = j_max_j_max * tf_p4 - 2.0 * vd_vd + 8.0 * j_max * tf * (-pd + tf * vf);
-        const double ph5 = 5.0 * af_p4 - 8.0 * af_p3 * j_max * tf - 12.0 * af_af * j_max * (j_max * tf_tf + vd)
+        const real ph1 = ad_ad + 2.0 * (af + a0) * j_max * tf - j_max * (j_max * tf_tf + 4.0 * vd);
+        const real ph2 = j_max * tf_tf * g1 - vd * (-2.0 * pd - tf * v0 + 3.0 * tf * vf);
+        const real ph3 = 5.0 * af_af - 8.0 * af * j_max * tf + 2.0 * j_max * (2.0 * j_max * tf_tf - vd);
+        const real ph4 = j_max_j_max * tf_p4 - 2.0 * vd_vd + 8.0 * j_max * tf * (-pd + tf * vf);
+        const real ph5 = 5.0 * af_p4 - 8.0 * af_p3 * j_max * tf - 12.0 * af_af * j_max * (j_max * tf_tf + vd)
                            + 24.0 * af * j_max_j_max * (-2.0 * pd + j_max * tf_p3 + 2.0 * tf * vf) - 6.0 * j_max_j_max * ph4;
-        const double ph6 = -vd_vd + j_max * tf * (-2.0 * pd + 3.0 * tf * v0 - tf * vf) - af * g2;
+        const real ph6 = -vd_vd + j_max * tf * (-2.0 * pd + 3.0 * tf * v0 - tf * vf) - af * g2;
 
-        const double c0 = -(4.0 * (a0_p3 - af_p3) - 12.0 * a0_a0 * (af - j_max * tf) + 6.0 * a0 * (2.0 * af_af - 2.0 * af * j_max * tf + j_max * (j_max * tf_tf - 2.0 * vd))
+        const real c0 = -(4.0 * (a0_p3 - af_p3) - 12.0 * a0_a0 * (af - j_max * tf) + 6.0 * a0 * (2.0 * af_af - 2.0 * af * j_max * tf + j_max * (j_max * tf_tf - 2.0 * vd))
                             + 6.0 * af * j_max * (3.0 * j_max * tf_tf + 2.0 * vd) - 6.0 * j_max_j_max * (-4.0 * pd + j_max * tf_p3 - 2.0 * tf * v0 + 6.0 * tf * vf))
                           / (3.0 * j_max * ph1);
-        const double c1 = -(-a0_p4 - af_p4 + 4.0 * a0_p3 * (af - j_max * tf) + a0_a0 * (-6.0 * af_af + 8.0 * af * j_max * tf - 4.0 * j_max * (j_max * tf_tf - vd))
+        const real c1 = -(-a0_p4 - af_p4 + 4.0 * a0_p3 * (af - j_max * tf) + a0_a0 * (-6.0 * af_af + 8.0 * af * j_max * tf - 4.0 * j_max * (j_max * tf_tf - vd))
                             + 2.0 * af_af * j_max * (j_max * tf_tf + 2.0 * vd) - 4.0 * af * j_max_j_max * (-3.0 * pd + j_max * tf_p3 + 2.0 * tf * v0 + tf * vf)
                             + j_max_j_max * (j_max_j_max * tf_p4 - 8.0 * vd_vd + 4.0 * j_max * tf * (-3.0 * pd + tf * v0 + 2.0 * tf * vf))
                             + 2.0 * a0 * (2.0 * af_p3 - 2.0 * af_af * j_max * tf + af * j_max * (-3.0 * j_max * tf_tf - 4.0 * vd)
                                           + j_max_j_max * (-6.0 * pd + j_max * tf_p3 - 4.0 * tf * v0 + 10.0 * tf * vf)))
                           / (j_max_j_max * ph1);
-        const double c2 = -(a0_p5 - af_p5 + af_p4 * j_max * tf - 5.0 * a0_p4 * (af - j_max * tf) + 2.0 * a0_p3 * ph3 + 4.0 * af_p3 * j_max * (j_max * tf_tf + vd)
+        const real c2 = -(a0_p5 - af_p5 + af_p4 * j_max * tf - 5.0 * a0_p4 * (af - j_max * tf) + 2.0 * a0_p3 * ph3 + 4.0 * af_p3 * j_max * (j_max * tf_tf + vd)
                             + 12.0 * j_max_j_max * af * ph6
                             - 2.0 * a0_a0 * (5.0 * af_p3 - 9.0 * af_af * j_max * tf - 6.0 * af * j_max * vd + 6.0 * j_max_j_max * (-2.0 * pd - tf * v0 + 3.0 * tf * vf))
                             - 12.0 * j_max_j_max * j_max * ph2 + a0 * ph5)
                           / (3.0 * j_max_j_max * j_max * ph1);
-        const double c3 = -(-a0_p6 - af_p6 + 6.0 * a0_p5 * (af - j_max * tf) - 48.0 * af_p3 * j_max_j_max * g1
+        const real c3 = -(-a0_p6 - af_p6 + 6.0 * a0_p5 * (af - j_max * tf) - 48.0 * af_p3 * j_max_j_max * g1
                             + 72.0 * j_max_j_max * j_max * (j_max * g1 * g1 + vd_vd * vd + 2.0 * af * g1 * vd) - 3.0 * a0_p4 * ph3
                             - 36.0 * af_af * j_max_j_max * vd_vd + 6.0 * af_p4 * j_max * vd
                             + 4.0 * a0_p3 * (5.0 * af_p3 - 9.0 * af_af * j_max * tf - 6.0 * af * j_max * vd + 6.0 * j_max_j_max * (-2.0 * pd - tf * v0 + 3.0 * tf * vf))
@@ -176,29 +176,29 @@ __device__ __noinline__ bool s2_none(const S2& s, const Lim& L, Hit& h) {
                             + 6.0 * a0 * (af_p5 - af_p4 * j_max * tf - 4.0 * af_p3 * j_max * (j_max * tf_tf + vd) + 12.0 * j_max_j_max * (-af * ph6 + j_max * ph2)))
                           / (18.0 * j_max_j_max * j_max_j_max * ph1);
 
-        const double t_max = (a0 - a_min) / j_max;
+        const real t_max = (a0 - a_min) / j_max;
         const Roots roots = solve_quart_monic(c0, c1, c2, c3);
 #pragma unroll 1
         for (int ri = 0; ri < roots.n; ++ri) {
-            double tt = roots.get(ri);
+            real tt = roots.get(ri);
             if (tt > t_max) continue;
             // Single Newton step (regarding pd)
             {
-                const double h1 = ad_ad / 2.0 + j_max * (af * tt + (j_max * tt - a0) * (tt - tf) - vd);
-                const double h2 = -ad + j_max * (tf - 2.0 * tt);
-                const double h3 = sqrt(h1);
-                const double orig = (af_p3 - a0_p3 + 3.0 * af * j_max * tt * (af + j_max * tt) + 3.0 * a0_a0 * (af + j_max * tt)
+                const real h1 = ad_ad / 2.0 + j_max * (af * tt + (j_max * tt - a0) * (tt - tf) - vd);
+                const real h2 = -ad + j_max * (tf - 2.0 * tt);
+                const real h3 = sqrt(h1);
+                const real orig = (af_p3 - a0_p3 + 3.0 * af * j_max * tt * (af + j_max * tt) + 3.0 * a0_a0 * (af + j_max * tt)
                                      - 3.0 * a0 * (af_af + 2.0 * af * j_max * tt + j_max_j_max * (tt * tt - tf_tf))
                                      + 3.0 * j_max_j_max * (-2.0 * pd + j_max * tt * (tt - tf) * tf + 2.0 * tf * v0))
                                         / (6.0 * j_max_j_max)
                                     - h3 * h3 * h3 / (j_max * fabs(j_max)) + ((-ad - j_max * tt) * h1) / (j_max_j_max);
-                const double deriv = (6.0 * j_max * h2 * h3 / fabs(j_max) + 2.0 * (-ad - j_max * tf) * h2
+                const real deriv = (6.0 * j_max * h2 * h3 / fabs(j_max) + 2.0 * (-ad - j_max * tf) * h2
                                       - 2.0 * (3.0 * ad_ad + af * j_max * (8.0 * tt - 2.0 * tf) + 4.0 * a0 * j_max * (-2.0 * tt + tf)
                                                + 2.0 * j_max * (j_max * tt * (3.0 * tt - 2.0 * tf) - vd)))
                                      / (4.0 * j_max);
                 tt -= orig / deriv;
             }
-            const double h1 = sqrt(2.0 * ad_ad + 4.0 * j_max * (ad * tt + a0 * tf + j_max * tt * (tt - tf) - vd)) / fabs(j_max);
+            const real h1 = sqrt(2.0 * ad_ad + 4.0 * j_max * (ad * tt + a0 * tf + j_max * tt * (tt - tf) - vd)) / fabs(j_max);
             // Solution 2 with aPlat
             t[0] = 0.0;
             t[1] = 0.0;
@@ -213,31 +213,31 @@ __device__ __noinline__ bool s2_none(const S2& s, const Lim& L, Hit& h) {
 
     // a3 != 0, UDUD — T 0124
     {
-        const double ph0 = -2.0 * pd - tf * v0 + 3.0 * tf * vf;
-        const double ph1 = -ad + j_max * tf;
-        const double ph2 = j_max * tf_tf * g1 - vd * ph0;
-        const double ph3 = 5.0 * af_af + 2.0 * j_max * (2.0 * j_max * tf_tf - vd - 4.0 * af * tf);
-        const double ph4 = j_max_j_max * tf_p4 - 2.0 * vd_vd + 8.0 * j_max * tf * (-pd + tf * vf);
-        const double ph5 = 5.0 * af_p4 - 8.0 * af_p3 * j_max * tf - 12.0 * af_af * j_max * (j_max * tf_tf + vd)
+        const real ph0 = -2.0 * pd - tf * v0 + 3.0 * tf * vf;
+        const real ph1 = -ad + j_max * tf;
+        const real ph2 = j_max * tf_tf * g1 - vd * ph0;
+        const real ph3 = 5.0 * af_af + 2.0 * j_max * (2.0 * j_max * tf_tf - vd - 4.0 * af * tf);
+        const real ph4 = j_max_j_max * tf_p4 - 2.0 * vd_vd + 8.0 * j_max * tf * (-pd + tf * vf);
+        const real ph5 = 5.0 * af_p4 - 8.0 * af_p3 * j_max * tf - 12.0 * af_af * j_max * (j_max * tf_tf + vd)
                            + 24.0 * af * j_max_j_max * (-2.0 * pd + j_max * tf_p3 + 2.0 * tf * vf) - 6.0 * j_max_j_max * ph4;
-        const double ph6 = -vd_vd + j_max * tf * (-2.0 * pd + 3.0 * tf * v0 - tf * vf);
-        const double ph7 = 3.0 * j_max_j_max * ph1 * ph1;
+        const real ph6 = -vd_vd + j_max * tf * (-2.0 * pd + 3.0 * tf * v0 - tf * vf);
+        const real ph7 = 3.0 * j_max_j_max * ph1 * ph1;
 
-        const double c0 = (4.0 * af * tf - 2.0 * j_max * tf_tf - 4.0 * vd) / ph1;
-        const double c1 = (-2.0 * (a0_p4 + af_p4) + 8.0 * af_p3 * j_max * tf + 6.0 * af_af * j_max_j_max * tf_tf + 8.0 * a0_p3 * (af - j_max * tf)
+        const real c0 = (4.0 * af * tf - 2.0 * j_max * tf_tf - 4.0 * vd) / ph1;
+        const real c1 = (-2.0 * (a0_p4 + af_p4) + 8.0 * af_p3 * j_max * tf + 6.0 * af_af * j_max_j_max * tf_tf + 8.0 * a0_p3 * (af - j_max * tf)
                            - 12.0 * a0_a0 * (af - j_max * tf) * (af - j_max * tf)
                            - 12.0 * af * j_max_j_max * (-pd + j_max * tf_p3 - 2.0 * tf * v0 + 3.0 * tf * vf)
                            + 2.0 * a0 * (4.0 * af_p3 - 12.0 * af_af * j_max * tf + 9.0 * af * j_max_j_max * tf_tf - 3.0 * j_max_j_max * (2.0 * pd + j_max * tf_p3 - 2.0 * tf * vf))
                            + 3.0 * j_max_j_max * (j_max_j_max * tf_p4 + 4.0 * vd_vd - 4.0 * j_max * tf * (pd + tf * v0 - 2.0 * tf * vf)))
                           / ph7;
-        const double c2 = (-a0_p5 + af_p5 - af_p4 * j_max * tf + 5.0 * a0_p4 * (af - j_max * tf) - 2.0 * a0_p3 * ph3 - 4.0 * af_p3 * j_max * (j_max * tf_tf + vd)
+        const real c2 = (-a0_p5 + af_p5 - af_p4 * j_max * tf + 5.0 * a0_p4 * (af - j_max * tf) - 2.0 * a0_p3 * ph3 - 4.0 * af_p3 * j_max * (j_max * tf_tf + vd)
                            + 12.0 * af_af * j_max_j_max * g2 - 12.0 * af * j_max_j_max * ph6
                            + 2.0 * a0_a0 * (5.0 * af_p3 - 9.0 * af_af * j_max * tf - 6.0 * af * j_max * vd + 6.0 * j_max_j_max * ph0)
                            + 12.0 * j_max_j_max * j_max * ph2
                            + a0 * (-5.0 * af_p4 + 8.0 * af_p3 * j_max * tf + 12.0 * af_af * j_max * (j_max * tf_tf + vd)
                                    - 24.0 * af * j_max_j_max * (-2.0 * pd + j_max * tf_p3 + 2.0 * tf * vf) + 6.0 * j_max_j_max * ph4))
                           / (j_max * ph7);
-        const double c3 = -(a0_p6 + af_p6 - 6.0 * a0_p5 * (af - j_max * tf) + 48.0 * af_p3 * j_max_j_max * g1
+        const real c3 = -(a0_p6 + af_p6 - 6.0 * a0_p5 * (af - j_max * tf) + 48.0 * af_p3 * j_max_j_max * g1
                             - 72.0 * j_max_j_max * j_max * (j_max * g1 * g1 + vd_vd * vd + 2.0 * af * g1 * vd) + 3.0 * a0_p4 * ph3 - 6.0 * af_p4 * j_max * vd
                             + 36.0 * af_af * j_max_j_max * vd_vd
                             - 4.0 * a0_p3 * (5.0 * af_p3 - 9.0 * af_af * j_max * tf - 6.0 * af * j_max * vd + 6.0 * j_max_j_max * ph0) + 3.0 * a0_a0 * ph5
@@ -248,9 +248,9 @@ __device__ __noinline__ bool s2_none(const S2& s, const Lim& L, Hit& h) {
         const Roots roots = solve_quart_monic(c0, c1, c2, c3);
 #pragma unroll 1
         for (int ri = 0; ri < roots.n; ++ri) {
-            const double tt = roots.get(ri);
+            const real tt = roots.get(ri);
             if (tt > tf || tt > (a_max - a0) / j_max) continue;
-            const double h1 = sqrt(ad_ad / (2.0 * j_max_j_max) + (a0 * (tt + tf) - af * tt + j_max * tt * tf - vd) / j_max);
+            const real h1 = sqrt(ad_ad / (2.0 * j_max_j_max) + (a0 * (tt + tf) - af * tt + j_max * tt * tf - vd) / j_max);
             t[0] = tt;
             t[1] = tf - ad / j_max - 2.0 * h1;
             t[2] = h1;
@@ -264,7 +264,7 @@ __device__ __noinline__ bool s2_none(const S2& s, const Lim& L, Hit& h) {
 
     // 3 step profile (UZD), T 012
     {
-        const double h1 = sqrt(-ad_ad + j_max * (2.0 * (a0 + af) * tf - 4.0 * vd + j_max * tf_tf)) / fabs(j_max);
+        const real h1 = sqrt(-ad_ad + j_max * (2.0 * (a0 + af) * tf - 4.0 * vd + j_max * tf_tf)) / fabs(j_max);
         t[0] = (tf - h1 + ad / j_max) / 2.0;
         t[1] = h1;
         t[2] = (tf - h1 - ad / j_max) / 2.0;
@@ -277,16 +277,16 @@ __device__ __noinline__ bool s2_none(const S2& s, const Lim& L, Hit& h) {
 
     // 3 step profile (UZU); validated with j_max, not with its own jf (:2164-2171)
     {
-        const double c0 = ad_ad;
-        const double c1 = ad_ad * tf;
-        const double c2 = (a0_a0 + af_af + 10.0 * a0 * af) * tf_tf + 24.0 * (tf * (af * v0 - a0 * vf) - pd * ad) + 12.0 * vd_vd;
-        const double c3 = -3.0 * tf * ((a0_a0 + af_af + 2.0 * a0 * af) * tf_tf - 4.0 * vd * (a0 + af) * tf + 4.0 * vd_vd);
+        const real c0 = ad_ad;
+        const real c1 = ad_ad * tf;
+        const real c2 = (a0_a0 + af_af + 10.0 * a0 * af) * tf_tf + 24.0 * (tf * (af * v0 - a0 * vf) - pd * ad) + 12.0 * vd_vd;
+        const real c3 = -3.0 * tf * ((a0_a0 + af_af + 2.0 * a0 * af) * tf_tf - 4.0 * vd * (a0 + af) * tf + 4.0 * vd_vd);
         const Roots roots = solve_cub(c0, c1, c2, c3);
 #pragma unroll 1
         for (int ri = 0; ri < roots.n; ++ri) {
-            const double tt = roots.get(ri);
+            const real tt = roots.get(ri);
             if (tt > tf) continue;
-            const double jf = ad / (tf - tt);
+            const real jf = ad / (tf - tt);
             t[0] = (2.0 * (vd - a0 * tf) + ad * (tt - tf)) / (2.0 * jf * tt);
             t[1] = tt;
             t[2] = 0.0;

@@ -17,18 +17,18 @@ __device__ __forceinline__ bool vel_uddu_root(const S2& s, const Lim& L, Hit& h,
     RK_S2_LOCALS
     // Single Newton step (regarding pd)
     {
-        const double h1 = sqrt((a0_a0 + af_af) / (2.0 * j_max_j_max) + (2.0 * a0 * tt + j_max * tt * tt - vd) / j_max);
-        const double orig = -pd
+        const real h1 = sqrt((a0_a0 + af_af) / (2.0 * j_max_j_max) + (2.0 * a0 * tt + j_max * tt * tt - vd) / j_max);
+        const real orig = -pd
                             - (2.0 * a0_p3 + 4.0 * af_p3 + 24.0 * a0 * j_max * tt * (af + j_max * (h1 + tt - tf)) + 6.0 * a0_a0 * (af + j_max * (2.0 * tt - tf))
                                + 6.0 * (a0_a0 + af_af) * j_max * h1 + 12.0 * af * j_max * (j_max * tt * tt - vd)
                                + 12.0 * j_max_j_max * (j_max * tt * tt * (h1 + tt - tf) - tf * v0 - h1 * vd))
                                   / (12.0 * j_max_j_max);
-        const double deriv_newton = -(a0 + j_max * tt) * (3.0 * (h1 + tt) - 2.0 * tf + (a0 + 2.0 * af) / j_max);
+        const real deriv_newton = -(a0 + j_max * tt) * (3.0 * (h1 + tt) - 2.0 * tf + (a0 + 2.0 * af) / j_max);
         if (!(orig != orig) && !(deriv_newton != deriv_newton) && fabs(deriv_newton) > EPS) tt -= orig / deriv_newton;
     }
     if (tt > tf || tt != tt) return false;
 
-    const double h1 = sqrt((a0_a0 + af_af) / (2.0 * j_max_j_max) + (tt * (2.0 * a0 + j_max * tt) - vd) / j_max);
+    const real h1 = sqrt((a0_a0 + af_af) / (2.0 * j_max_j_max) + (tt * (2.0 * a0 + j_max * tt) - vd) / j_max);
     t[0] = tt;
     t[1] = 0.0;
     t[2] = tt + a0 / j_max;
@@ -45,10 +45,10 @@ __device__ __forceinline__ bool vel_udud_root(const S2& s, const Lim& L, Hit& h,
     RK_S2_LOCALS
     // Double Newton step (regarding pd)
     {
-        double h1 = sqrt((af_af - a0_a0) / (2.0 * j_max_j_max) - ((2.0 * a0 + j_max * tt) * tt - vd) / j_max);
-        double orig = -pd + (af_p3 - a0_p3 + 3.0 * a0_a0 * j_max * (tf - 2.0 * tt)) / (6.0 * j_max_j_max) + (2.0 * a0 + j_max * tt) * tt * (tf - tt)
+        real h1 = sqrt((af_af - a0_a0) / (2.0 * j_max_j_max) - ((2.0 * a0 + j_max * tt) * tt - vd) / j_max);
+        real orig = -pd + (af_p3 - a0_p3 + 3.0 * a0_a0 * j_max * (tf - 2.0 * tt)) / (6.0 * j_max_j_max) + (2.0 * a0 + j_max * tt) * tt * (tf - tt)
                       + (j_max * h1 - af) * h1 * h1 + tf * v0;
-        double deriv_newton = (a0 + j_max * tt) * (2.0 * (af + j_max * tf) - 3.0 * j_max * (h1 + tt) - a0) / j_max;
+        real deriv_newton = (a0 + j_max * tt) * (2.0 * (af + j_max * tf) - 3.0 * j_max * (h1 + tt) - a0) / j_max;
         tt -= orig / deriv_newton;
 
         h1 = sqrt((af_af - a0_a0) / (2.0 * j_max_j_max) - ((2.0 * a0 + j_max * tt) * tt - vd) / j_max);
@@ -59,7 +59,7 @@ __device__ __forceinline__ bool vel_udud_root(const S2& s, const Lim& L, Hit& h,
             tt -= orig / deriv_newton;
         }
     }
-    const double h1 = sqrt((af_af - a0_a0) / (2.0 * j_max_j_max) - ((2.0 * a0 + j_max * tt) * tt - vd) / j_max);
+    const real h1 = sqrt((af_af - a0_a0) / (2.0 * j_max_j_max) - ((2.0 * a0 + j_max * tt) * tt - vd) / j_max);
     t[0] = tt;
     t[1] = 0.0;
     t[2] = tt + a0 / j_max;
@@ -74,20 +74,20 @@ __device__ __forceinline__ bool vel_udud_root(const S2& s, const Lim& L, Hit& h,
 // UDDU half of time_vel (:619-824)
 __device__ __noinline__ bool s2_vel_uddu(const S2& s, const Lim& L, Hit& h) {
     RK_S2_LOCALS
-    const double a0_p6 = s.a0_p6, af_p6 = s.af_p6;
-    const double tz_min = rmax(0.0, -a0 / j_max);
-    const double tz_max = rmin((tf - a0 / j_max) / 2.0, (a_max - a0) / j_max);
+    const real a0_p6 = s.a0_p6, af_p6 = s.af_p6;
+    const real tz_min = rmax(0.0, -a0 / j_max);
+    const real tz_max = rmin((tf - a0 / j_max) / 2.0, (a_max - a0) / j_max);
 
     if (fabs(v0) < EPS && fabs(a0) < EPS && fabs(vf) < EPS && fabs(af) < EPS) {
         const Roots roots = solve_cub(1.0, -tf / 2.0, 0.0, pd / (2.0 * j_max));
 #pragma unroll 1
         for (int ri = 0; ri < roots.n; ++ri) {
-            double tt = roots.get(ri);
+            real tt = roots.get(ri);
             if (tt > tf / 4.0) continue;
             // Single Newton step (regarding pd)
             if (tt > EPS) {
-                const double orig = -pd + j_max * tt * tt * (tf - 2.0 * tt);
-                const double deriv = 2.0 * j_max * tt * (tf - 3.0 * tt);
+                const real orig = -pd + j_max * tt * tt * (tf - 2.0 * tt);
+                const real deriv = 2.0 * j_max * tt * (tf - 3.0 * tt);
                 tt -= orig / deriv;
             }
             t[0] = tt;
@@ -102,12 +102,12 @@ __device__ __noinline__ bool s2_vel_uddu(const S2& s, const Lim& L, Hit& h) {
         return false;
     }
 
-    const double p1 = af_af - 2.0 * j_max * (-2.0 * af * tf + j_max * tf_tf + 3.0 * vd);
-    const double ph1 = af_p3 - 3.0 * j_max_j_max * g1 - 3.0 * af * j_max * vd;
-    const double ph2 = af_p4 + 8.0 * af_p3 * j_max * tf
+    const real p1 = af_af - 2.0 * j_max * (-2.0 * af * tf + j_max * tf_tf + 3.0 * vd);
+    const real ph1 = af_p3 - 3.0 * j_max_j_max * g1 - 3.0 * af * j_max * vd;
+    const real ph2 = af_p4 + 8.0 * af_p3 * j_max * tf
                        + 12.0 * j_max * (3.0 * j_max * vd_vd - af_af * vd + 2.0 * af * j_max * (g1 - tf * vd) - 2.0 * j_max_j_max * tf * g1);
-    const double ph3 = a0 * (af - j_max * tf);
-    const double ph4 = j_max * (-ad + j_max * tf);
+    const real ph3 = a0 * (af - j_max * tf);
+    const real ph4 = j_max * (-ad + j_max * tf);
 
     // 5th order polynomial, monic
     double pol[6];
@@ -128,21 +128,26 @@ __device__ __noinline__ bool s2_vel_uddu(const S2& s, const Lim& L, Hit& h) {
     // extrema of the quintic: roots of its quartic derivative, closed form
     const Roots d_extremas = solve_quart_monic(deriv[1], deriv[2], deriv[3], deriv[4]);
 
-    // One loop over the extrema plus a last pass for the interval that ends at tz_max (:778-823). Each pass decides
-    // whether it has a root candidate (directly at the extremum, or bracketed between the previous extremum and this
-    // one); the bracketing iteration and the candidate validation then have a single call site each, so the lanes of a
-    // warp re-converge there instead of running four inlined copies one after the other.
-    double tz_current = tz_min;
-    double val_current = poly_eval<6>(pol, tz_current);
+    // Two phases instead of the reference's single loop (:778-823), with the same candidates in the same order:
+    //  1. scan the extrema (plus a last pass for the interval that ends at tz_max) and only RECORD where a root candidate
+    //     sits — directly at an extremum, or bracketed between the previous extremum and this one. Cheap, and all lanes of
+    //     a warp walk it together.
+    //  2. polish and validate the recorded candidates in order. Almost every item has its (usually single) candidate in
+    //     slot 0, so the expensive part — safeguarded Newton bracketing and the profile check — runs with nearly full
+    //     warps, where the interleaved loop ran it with the quarter of the lanes that had a candidate at that extremum.
+    double c_lo[6], c_hi[6];  // bracket [lo, hi]; a direct candidate has lo == hi
+    int n_cand = 0;
+    real tz_current = tz_min;
+    real val_current = poly_eval<6>(pol, tz_current);
 #pragma unroll 1
     for (int ri = 0; ri <= d_extremas.n; ++ri) {
         const bool last = ri == d_extremas.n;
-        double tz = last ? tz_max : d_extremas.get(ri);
+        real tz = last ? tz_max : real(d_extremas.get(ri));
         if (!last && tz >= tz_max) continue;
         bool direct = false, bracket = false;
-        double val_new;
+        real val_new;
         if (!last) {
-            const double orig = poly_eval<5>(deriv, tz);
+            const real orig = poly_eval<5>(deriv, tz);
             if (fabs(orig) > ROOT_TOLERANCE) tz -= orig / poly_eval<4>(dderiv, tz);
             val_new = poly_eval<6>(pol, tz);
             if (fabs(val_new) < 64.0 * fabs(poly_eval<4>(dderiv, tz)) * ROOT_TOLERANCE) direct = true;
@@ -153,11 +158,18 @@ __device__ __noinline__ bool s2_vel_uddu(const S2& s, const Lim& L, Hit& h) {
             else if (fabs(val_new) < 8.0 * EPS) direct = true;
         }
         if (direct || bracket) {
-            const double root = bracket ? shrink_interval<6>(pol, tz_current, tz) : tz;
-            if (vel_uddu_root(s, L, h, root)) return true;
+            c_lo[n_cand] = bracket ? (double)tz_current : (double)tz;
+            c_hi[n_cand] = tz;
+            ++n_cand;
         }
         tz_current = tz;
         val_current = val_new;
+    }
+#pragma unroll 1
+    for (int c = 0; c < n_cand; ++c) {
+        const double lo = c_lo[c], hi = c_hi[c];
+        const double root = (lo != hi) ? shrink_interval<6>(pol, lo, hi) : hi;
+        if (vel_uddu_root(s, L, h, root)) return true;
     }
     return false;
 }
@@ -165,15 +177,15 @@ __device__ __noinline__ bool s2_vel_uddu(const S2& s, const Lim& L, Hit& h) {
 // UDUD half of time_vel (:825-973)
 __device__ __noinline__ bool s2_vel_udud(const S2& s, const Lim& L, Hit& h) {
     RK_S2_LOCALS
-    const double a0_p5 = s.a0_p5, a0_p6 = s.a0_p6, af_p6 = s.af_p6;
-    const double tz_min = rmax(0.0, -a0 / j_max);
-    const double tz_max = rmin((tf - a0 / j_max) / 2.0, (a_max - a0) / j_max);
+    const real a0_p5 = s.a0_p5, a0_p6 = s.a0_p6, af_p6 = s.af_p6;
+    const real tz_min = rmax(0.0, -a0 / j_max);
+    const real tz_max = rmin((tf - a0 / j_max) / 2.0, (a_max - a0) / j_max);
 
-    const double ph1 = af_af - 2.0 * j_max * (2.0 * af * tf + j_max * tf_tf - 3.0 * vd);
-    const double ph2 = af_p3 - 3.0 * j_max_j_max * g1 + 3.0 * af * j_max * vd;
-    const double ph3 = 2.0 * j_max * tf * g1 + 3.0 * vd_vd;
-    const double ph4 = af_p4 - 8.0 * af_p3 * j_max * tf + 12.0 * j_max * (j_max * ph3 + af_af * vd + 2.0 * af * j_max * (g1 - tf * vd));
-    const double ph5 = af + j_max * tf;
+    const real ph1 = af_af - 2.0 * j_max * (2.0 * af * tf + j_max * tf_tf - 3.0 * vd);
+    const real ph2 = af_p3 - 3.0 * j_max_j_max * g1 + 3.0 * af * j_max * vd;
+    const real ph3 = 2.0 * j_max * tf * g1 + 3.0 * vd_vd;
+    const real ph4 = af_p4 - 8.0 * af_p3 * j_max * tf + 12.0 * j_max * (j_max * ph3 + af_af * vd + 2.0 * af * j_max * (g1 - tf * vd));
+    const real ph5 = af + j_max * tf;
 
     // 6th order polynomial, monic
     double pol[7];
@@ -196,14 +208,14 @@ __device__ __noinline__ bool s2_vel_udud(const S2& s, const Lim& L, Hit& h) {
     // sign changes of the first derivative between the extrema of the first derivative
     double iv_l[6], iv_r[6];
     int n_iv = 0;
-    double dd_tz_current = tz_min;
+    real dd_tz_current = tz_min;
     const Roots dd_extremas = solve_quart_monic(dderiv[1], dderiv[2], dderiv[3], dderiv[4]);
 #pragma unroll 1
     for (int ri = 0; ri < dd_extremas.n; ++ri) {
-        double tz = dd_extremas.get(ri);
+        real tz = dd_extremas.get(ri);
         if (tz >= tz_max) continue;
 
-        const double orig = poly_eval<5>(dderiv, tz);
+        const real orig = poly_eval<5>(dderiv, tz);
         if (fabs(orig) > ROOT_TOLERANCE) tz -= orig / poly_eval<4>(ddderiv, tz);
 
         if (poly_eval<6>(deriv, dd_tz_current) * poly_eval<6>(deriv, tz) < 0.0) {
@@ -219,24 +231,34 @@ __device__ __noinline__ bool s2_vel_udud(const S2& s, const Lim& L, Hit& h) {
         if (!dup && n_iv < 6) { iv_l[n_iv] = dd_tz_current; iv_r[n_iv] = tz_max; ++n_iv; }
     }
 
-    // same single-call-site arrangement as the UDDU half: pass k == n_iv is the interval that ends at tz_max (:947-970)
-    double tz_current = tz_min;
-    double val_current = poly_eval<7>(pol, tz_current);
+    // record the candidates first, polish and validate them afterwards (see the UDDU half); pass k == n_iv is the interval
+    // that ends at tz_max (:947-970)
+    double c_lo[7], c_hi[7];
+    int n_cand = 0;
+    real tz_current = tz_min;
+    real val_current = poly_eval<7>(pol, tz_current);
 #pragma unroll 1
     for (int k = 0; k <= n_iv; ++k) {
         const bool last = k == n_iv;
-        const double tz = last ? tz_max : shrink_interval<6>(deriv, iv_l[last ? 0 : k], iv_r[last ? 0 : k]);
+        const real tz = last ? tz_max : real(shrink_interval<6>(deriv, iv_l[last ? 0 : k], iv_r[last ? 0 : k]));
         if (!last && tz >= tz_max) continue;
-        const double p_val = poly_eval<7>(pol, tz);
+        const real p_val = poly_eval<7>(pol, tz);
         bool direct = false, bracket = false;
         if (!last && fabs(p_val) < 64.0 * fabs(poly_eval<5>(dderiv, tz)) * ROOT_TOLERANCE) direct = true;
         else if (val_current * p_val < 0.0) bracket = true;
         if (direct || bracket) {
-            const double root = bracket ? shrink_interval<7>(pol, tz_current, tz) : tz;
-            if (vel_udud_root(s, L, h, root)) return true;
+            c_lo[n_cand] = bracket ? (double)tz_current : (double)tz;
+            c_hi[n_cand] = tz;
+            ++n_cand;
         }
         tz_current = tz;
         val_current = p_val;
+    }
+#pragma unroll 1
+    for (int c = 0; c < n_cand; ++c) {
+        const double lo = c_lo[c], hi = c_hi[c];
+        const double root = (lo != hi) ? shrink_interval<7>(pol, lo, hi) : hi;
+        if (vel_udud_root(s, L, h, root)) return true;
     }
     return false;
 }

@@ -14,7 +14,7 @@ __device__ __forceinline__ void zero_t(double (&t)[7]) {
     for (int i = 0; i < 7; ++i) t[i] = 0.0;
 }
 
-__device__ __forceinline__ void set_cand(Cand& c, const double (&t)[7], double ctrl, double ctrl2, int lim, int dir, int cs) {
+__device__ __forceinline__ void set_cand(Cand& c, const double (&t)[7], real ctrl, real ctrl2, int lim, int dir, int cs) {
     copy_t(c.t, t);
     c.dur = t_sum6(t);
     c.ctrl = ctrl; c.ctrl2 = ctrl2; c.lim = lim; c.dir = dir; c.cs = cs;
@@ -23,18 +23,18 @@ __device__ __forceinline__ void set_cand(Cand& c, const double (&t)[7], double c
 // ---------------------------------------------------------------- velocity interface, third order
 struct Step1Vel3 {
     Bound b;
-    double vd;
+    real vd;
     Cand vp[6];
     int count;
 
-    __device__ __forceinline__ bool emit(const double (&t)[7], int lim, double a_max, double a_min, double j_max) {
+    __device__ __forceinline__ bool emit(const double (&t)[7], int lim, real a_max, real a_min, double j_max) {
         if (!check_vel3(t, UDDU, lim, j_max, a_max, a_min, b)) return false;
         set_cand(vp[count], t, j_max, 0.0, lim, (a_max > 0.0) ? DIR_UP : DIR_DOWN, UDDU);
         if (count < 5) ++count;
         return true;
     }
     // velocity_third_step1.rs:46-62
-    __device__ __forceinline__ void time_acc0(double a_max, double a_min, double j_max) {
+    __device__ __forceinline__ void time_acc0(real a_max, real a_min, double j_max) {
         double t[7];
         zero_t(t);
         t[0] = (-b.a0 + a_max) / j_max;
@@ -43,8 +43,8 @@ struct Step1Vel3 {
         emit(t, L_ACC0, a_max, a_min, j_max);
     }
     // velocity_third_step1.rs:64-117
-    __device__ __forceinline__ void time_none(double a_max, double a_min, double j_max, bool first_only) {
-        double h1 = (b.a0 * b.a0 + b.af * b.af) / 2.0 + j_max * vd;
+    __device__ __forceinline__ void time_none(real a_max, real a_min, real j_max, bool first_only) {
+        real h1 = (b.a0 * b.a0 + b.af * b.af) / 2.0 + j_max * vd;
         if (!(h1 >= 0.0)) return;
         h1 = sqrt(h1);
         double t[7];
@@ -59,7 +59,7 @@ struct Step1Vel3 {
 };
 
 // velocity_third_step1.rs:163-242
-__device__ __noinline__ bool step1_vel3(const Bound& b, double a_max, double a_min, double j_max, double bd, BlockRec& blk) {
+__device__ __noinline__ bool step1_vel3(const Bound& b, real a_max, real a_min, real j_max, real bd, BlockRec& blk) {
     Step1Vel3 s;
     s.b = b;
     s.vd = b.vf - b.v0;
@@ -86,7 +86,7 @@ __device__ __noinline__ bool step1_vel3(const Bound& b, double a_max, double a_m
 
     if (fabs(b.af) < EPS) {
         const bool up = s.vd >= 0.0;
-        const double am = up ? a_max : a_min, an = up ? a_min : a_max, jm = up ? j_max : -j_max;
+        const real am = up ? a_max : a_min, an = up ? a_min : a_max, jm = up ? j_max : -j_max;
         s.time_none(am, an, jm, true);
         if (s.count > 0) return calculate_block(blk, s.vp, s.count, bd);
         s.time_acc0(am, an, jm);
@@ -104,12 +104,12 @@ __device__ __noinline__ bool step1_vel3(const Bound& b, double a_max, double a_m
 }
 
 // velocity_third_step2.rs:42-191. On success c holds the profile; the reference then sets pf = p[7].
-__device__ __forceinline__ bool step2_vel3_dir(const Bound& b, double tf, double vd, double ad, double a_max, double a_min, double j_max, Cand& c) {
+__device__ __forceinline__ bool step2_vel3_dir(const Bound& b, real tf, real vd, real ad, real a_max, real a_min, real j_max, Cand& c) {
     const int dir = (a_max > 0.0) ? DIR_UP : DIR_DOWN;
     double t[7];
     // time_acc0 — UD solution 1/2
     {
-        const double h1 = sqrt((-ad * ad + 2.0 * j_max * ((b.a0 + b.af) * tf - 2.0 * vd)) / (j_max * j_max) + tf * tf);
+        const real h1 = sqrt((-ad * ad + 2.0 * j_max * ((b.a0 + b.af) * tf - 2.0 * vd)) / (j_max * j_max) + tf * tf);
         zero_t(t);
         t[0] = ad / (2.0 * j_max) + (tf - h1) / 2.0;
         t[1] = h1;
@@ -118,7 +118,7 @@ __device__ __forceinline__ bool step2_vel3_dir(const Bound& b, double tf, double
     }
     // UU solution
     {
-        const double h1 = -ad + j_max * tf;
+        const real h1 = -ad + j_max * tf;
         zero_t(t);
         t[0] = -ad * ad / (2.0 * j_max * h1) + (vd - b.a0 * tf) / h1;
         t[1] = -ad / j_max + tf;
@@ -139,18 +139,18 @@ __device__ __forceinline__ bool step2_vel3_dir(const Bound& b, double tf, double
         if (check_vel3(t, UDDU, L_NONE, j_max, a_max, a_min, b)) { set_cand(c, t, j_max, 0.0, L_NONE, dir, UDDU); return true; }
     }
     {
-        const double h1 = 2.0 * (b.af * tf - vd);
+        const real h1 = 2.0 * (b.af * tf - vd);
         zero_t(t);
         t[0] = h1 / ad;
         t[1] = tf - t[0];
-        const double jf = ad * ad / h1;  // not compared with j_max (Q10)
+        const real jf = ad * ad / h1;  // not compared with j_max (Q10)
         if (check_vel3(t, UDDU, L_NONE, jf, a_max, a_min, b)) { set_cand(c, t, jf, 0.0, L_NONE, dir, UDDU); return true; }
     }
     return false;
 }
 
-__device__ __noinline__ bool step2_vel3(const Bound& b, double tf, double a_max, double a_min, double j_max, Cand& c) {
-    const double vd = b.vf - b.v0, ad = b.af - b.a0;
+__device__ __noinline__ bool step2_vel3(const Bound& b, real tf, real a_max, real a_min, real j_max, Cand& c) {
+    const real vd = b.vf - b.v0, ad = b.af - b.a0;
     if (vd > 0.0) return step2_vel3_dir(b, tf, vd, ad, a_max, a_min, j_max, c) || step2_vel3_dir(b, tf, vd, ad, a_min, a_max, -j_max, c);
     return step2_vel3_dir(b, tf, vd, ad, a_min, a_max, -j_max, c) || step2_vel3_dir(b, tf, vd, ad, a_max, a_min, j_max, c);
 }
@@ -158,12 +158,12 @@ __device__ __noinline__ bool step2_vel3(const Bound& b, double tf, double a_max,
 // ---------------------------------------------------------------- position interface, second order
 struct Step1Pos2 {
     Bound b;
-    double pd;
+    real pd;
     Cand vp[6];
     int count;
 
     // position_second_step1.rs:49-55: stores at most three (Q12)
-    __device__ __forceinline__ bool emit(const double (&t)[7], int lim, double v_max, double v_min, double a_max, double a_min) {
+    __device__ __forceinline__ bool emit(const double (&t)[7], int lim, real v_max, real v_min, real a_max, double a_min) {
         if (!check_pos2(t, UDDU, a_max, a_min, v_max, v_min, b)) return false;
         if (count < 3) {
             set_cand(vp[count], t, a_max, a_min, lim, (v_max > 0.0) ? DIR_UP : DIR_DOWN, UDDU);
@@ -172,7 +172,7 @@ struct Step1Pos2 {
         return true;
     }
     // :57-88
-    __device__ __forceinline__ void time_acc0(double v_max, double v_min, double a_max, double a_min) {
+    __device__ __forceinline__ void time_acc0(real v_max, real v_min, real a_max, double a_min) {
         double t[7];
         zero_t(t);
         t[0] = (-b.v0 + v_max) / a_max;
@@ -181,8 +181,8 @@ struct Step1Pos2 {
         emit(t, L_ACC0, v_max, v_min, a_max, a_min);
     }
     // :90-154
-    __device__ __forceinline__ void time_none(double v_max, double v_min, double a_max, double a_min, bool first_only) {
-        double h1 = (a_max * b.vf * b.vf - a_min * b.v0 * b.v0 - 2.0 * a_max * a_min * pd) / (a_max - a_min);
+    __device__ __forceinline__ void time_none(real v_max, real v_min, real a_max, real a_min, bool first_only) {
+        real h1 = (a_max * b.vf * b.vf - a_min * b.v0 * b.v0 - 2.0 * a_max * a_min * pd) / (a_max - a_min);
         if (!(h1 >= 0.0)) return;
         h1 = sqrt(h1);
         double t[7];
@@ -197,7 +197,7 @@ struct Step1Pos2 {
 };
 
 // position_second_step1.rs:212-312
-__device__ __noinline__ bool step1_pos2(const Bound& b, double v_max, double v_min, double a_max, double a_min, double bd, BlockRec& blk) {
+__device__ __noinline__ bool step1_pos2(const Bound& b, real v_max, real v_min, real a_max, real a_min, real bd, BlockRec& blk) {
     Step1Pos2 s;
     s.b = b;
     s.pd = b.pf - b.p0;
@@ -226,7 +226,7 @@ __device__ __noinline__ bool step1_pos2(const Bound& b, double v_max, double v_m
 
     if (fabs(b.vf) < EPS) {
         const bool up = s.pd >= 0.0;
-        const double vm = up ? v_max : v_min, vn = up ? v_min : v_max, am = up ? a_max : a_min, an = up ? a_min : a_max;
+        const real vm = up ? v_max : v_min, vn = up ? v_min : v_max, am = up ? a_max : a_min, an = up ? a_min : a_max;
         s.time_none(vm, vn, am, an, true);
         if (s.count > 0) return calculate_block(blk, s.vp, s.count, bd);
         s.time_acc0(vm, vn, am, an);
@@ -244,11 +244,11 @@ __device__ __noinline__ bool step1_pos2(const Bound& b, double v_max, double v_m
 }
 
 // position_second_step2.rs:48-216; on success the reference sets pf = p[7].
-__device__ __forceinline__ bool step2_pos2_dir(const Bound& b, double tf, double pd, double vd, double v_max, double v_min, double a_max, double a_min, Cand& c) {
+__device__ __forceinline__ bool step2_pos2_dir(const Bound& b, real tf, real pd, real vd, real v_max, real v_min, real a_max, real a_min, Cand& c) {
     const int dir = (v_max > 0.0) ? DIR_UP : DIR_DOWN;
     double t[7];
     {
-        const double h1 = sqrt((2.0 * a_max * (pd - tf * b.vf) - 2.0 * a_min * (pd - tf * b.v0) + vd * vd) / (a_max * a_min) + tf * tf);
+        const real h1 = sqrt((2.0 * a_max * (pd - tf * b.vf) - 2.0 * a_min * (pd - tf * b.v0) + vd * vd) / (a_max * a_min) + tf * tf);
         zero_t(t);
         t[0] = (a_max * vd - a_max * a_min * (tf - h1)) / (a_max * (a_max - a_min));
         t[1] = h1;
@@ -256,7 +256,7 @@ __device__ __forceinline__ bool step2_pos2_dir(const Bound& b, double tf, double
         if (check_pos2(t, UDDU, a_max, a_min, v_max, v_min, b)) { set_cand(c, t, a_max, a_min, L_ACC0, dir, UDDU); return true; }
     }
     {
-        const double h1 = -vd + a_max * tf;
+        const real h1 = -vd + a_max * tf;
         zero_t(t);
         t[0] = -vd * vd / (2.0 * a_max * h1) + (pd - b.v0 * tf) / h1;
         t[1] = -vd / a_max + tf;
@@ -275,11 +275,11 @@ __device__ __forceinline__ bool step2_pos2_dir(const Bound& b, double tf, double
         if (check_pos2(t, UDDU, a_max, a_min, v_max, v_min, b)) { set_cand(c, t, a_max, a_min, L_NONE, dir, UDDU); return true; }
     }
     {
-        const double h1 = 2.0 * (b.vf * tf - pd);
+        const real h1 = 2.0 * (b.vf * tf - pd);
         zero_t(t);
         t[0] = h1 / vd;
         t[1] = tf - t[0];
-        const double af = vd * vd / h1;
+        const real af = vd * vd / h1;
         if ((a_min - 1e-12 < af) && (af < a_max + 1e-12) && check_pos2(t, UDDU, af, -af, v_max, v_min, b)) {
             set_cand(c, t, af, -af, L_NONE, dir, UDDU);
             return true;
@@ -288,17 +288,17 @@ __device__ __forceinline__ bool step2_pos2_dir(const Bound& b, double tf, double
     return false;
 }
 
-__device__ __noinline__ bool step2_pos2(const Bound& b, double tf, double v_max, double v_min, double a_max, double a_min, Cand& c) {
-    const double pd = b.pf - b.p0, vd = b.vf - b.v0;
+__device__ __noinline__ bool step2_pos2(const Bound& b, real tf, real v_max, real v_min, real a_max, real a_min, Cand& c) {
+    const real pd = b.pf - b.p0, vd = b.vf - b.v0;
     if (pd > 0.0) return step2_pos2_dir(b, tf, pd, vd, v_max, v_min, a_max, a_min, c) || step2_pos2_dir(b, tf, pd, vd, v_min, v_max, a_min, a_max, c);
     return step2_pos2_dir(b, tf, pd, vd, v_min, v_max, a_min, a_max, c) || step2_pos2_dir(b, tf, pd, vd, v_max, v_min, a_max, a_min, c);
 }
 
 // ---------------------------------------------------------------- velocity interface, second order
 // velocity_second_step1.rs:23-46
-__device__ __forceinline__ bool step1_vel2(const Bound& b, double a_max, double a_min, double bd, BlockRec& blk) {
-    const double vd = b.vf - b.v0;
-    const double af = (vd > 0.0) ? a_max : a_min;
+__device__ __forceinline__ bool step1_vel2(const Bound& b, real a_max, real a_min, real bd, BlockRec& blk) {
+    const real vd = b.vf - b.v0;
+    const real af = (vd > 0.0) ? a_max : a_min;
     double t[7];
     zero_t(t);
     t[1] = vd / af;
@@ -311,9 +311,9 @@ __device__ __forceinline__ bool step1_vel2(const Bound& b, double a_max, double 
 }
 
 // velocity_second_step2.rs:23-46 (+ profile.rs:308-320)
-__device__ __forceinline__ bool step2_vel2(const Bound& b, double tf, double a_max, double a_min, Cand& c) {
-    const double vd = b.vf - b.v0;
-    const double af = vd / tf;
+__device__ __forceinline__ bool step2_vel2(const Bound& b, real tf, real a_max, real a_min, Cand& c) {
+    const real vd = b.vf - b.v0;
+    const real af = vd / tf;
     double t[7];
     zero_t(t);
     t[1] = tf;
@@ -325,9 +325,9 @@ __device__ __forceinline__ bool step2_vel2(const Bound& b, double tf, double a_m
 
 // ---------------------------------------------------------------- position interface, first order
 // position_first_step1.rs:20-42
-__device__ __forceinline__ bool step1_pos1(const Bound& b, double v_max, double v_min, double bd, BlockRec& blk) {
-    const double pd = b.pf - b.p0;
-    const double vf = (pd > 0.0) ? v_max : v_min;
+__device__ __forceinline__ bool step1_pos1(const Bound& b, real v_max, real v_min, real bd, BlockRec& blk) {
+    const real pd = b.pf - b.p0;
+    const real vf = (pd > 0.0) ? v_max : v_min;
     double t[7];
     zero_t(t);
     t[3] = pd / vf;
@@ -340,9 +340,9 @@ __device__ __forceinline__ bool step1_pos1(const Bound& b, double v_max, double 
 }
 
 // position_first_step2.rs:22-34
-__device__ __forceinline__ bool step2_pos1(const Bound& b, double tf, Cand& c) {
-    const double pd = b.pf - b.p0;
-    const double vf = pd / tf;
+__device__ __forceinline__ bool step2_pos1(const Bound& b, real tf, Cand& c) {
+    const real pd = b.pf - b.p0;
+    const real vf = pd / tf;
     double t[7];
     zero_t(t);
     t[3] = tf;
