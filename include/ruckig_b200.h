@@ -207,6 +207,10 @@ int64_t rk_kernel_launches(const rk_handle* h);       /* kernels launched throug
 /* Roofline denominator for this path (it is FP64-pipe bound): runs a register-resident chain of
  * dependent-free DFMAs on every SM for about `milliseconds` and reports the sustained rate, an FMA counted as 2 flop. */
 rk_status rk_measure_fp64_peak(rk_handle* h, double milliseconds, double* tflops);
+/* Self-test of the library's own fp64 division paths (shared-reciprocal division, zero-safe division; rk_math.cuh)
+ * against the compiler's IEEE division on n pseudo-random operand pairs that include zeros, infinities, NaNs,
+ * subnormals and extreme exponents; *mismatches = number of pairs whose result bits differ (NaN == NaN). */
+rk_status rk_selftest_division(rk_handle* h, int64_t n, uint64_t seed, int64_t* mismatches);
 const char* rk_status_string(rk_status s);
 const char* rk_last_error(void);
 const char* rk_version(void);

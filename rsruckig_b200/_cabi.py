@@ -115,12 +115,12 @@ def make_in(fields: dict) -> RkBatchIn:
 
 
 _LIB = None
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libruckig_b200.so")
+LIB_PATH = os.environ.get("RK_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libruckig_b200.so")
 
 EXPORTS = (
     "rk_create", "rk_destroy", "rk_trajectories_create", "rk_trajectories_destroy", "rk_calculate_batch",
     "rk_validate_batch", "rk_at_time_batch", "rk_trajectories_read", "rk_sync", "rk_stream", "rk_kernel_launches",
-    "rk_status_string", "rk_last_error", "rk_version", "rk_measure_fp64_peak",
+    "rk_status_string", "rk_last_error", "rk_version", "rk_measure_fp64_peak", "rk_selftest_division",
 )
 
 
@@ -149,6 +149,8 @@ def load():
     lib.rk_kernel_launches.restype = C.c_int64
     lib.rk_measure_fp64_peak.argtypes = [vp, C.c_double, C.POINTER(C.c_double)]
     lib.rk_measure_fp64_peak.restype = C.c_int32
+    lib.rk_selftest_division.argtypes = [vp, C.c_int64, C.c_uint64, C.POINTER(C.c_int64)]
+    lib.rk_selftest_division.restype = C.c_int32
     lib.rk_status_string.argtypes = [C.c_int32]
     lib.rk_status_string.restype = C.c_char_p
     lib.rk_last_error.restype = C.c_char_p

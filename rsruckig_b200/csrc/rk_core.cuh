@@ -118,7 +118,7 @@ __device__ __noinline__ bool check_pos3(double t0, double t1, double t2, double 
 }
 
 struct Lim {  // direction-resolved limits handed to the family functions
-    double v_max, v_min, a_max, a_min, j_max;
+    Den v_max, v_min, a_max, a_min, j_max;
 };
 
 __device__ __forceinline__ bool check_pos3(const double (&t)[7], int cs, int lim, double jf, const Lim& L, const Bound& b) {

@@ -146,6 +146,53 @@ __global__ void __launch_bounds__(256) k_fp64_peak(double* sink, int iters, doub
     if (s == 123.456) sink[0] = s;  // keeps the chains alive
 }
 
+// ------------------------------------------------------------------------------------------------ division self-test
+__device__ __forceinline__ uint64_t mix64(uint64_t z) {  // splitmix64
+    z += 0x9e3779b97f4a7c15ull;
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+    return z ^ (z >> 31);
+}
+
+// Operand generator: half of the draws are "ordinary" magnitudes (2^-40 .. 2^40), the rest are raw bit patterns, values
+// at the edges of the fast-path window, and the special values the solvers produce on purpose (0, inf, NaN).
+__device__ __forceinline__ double test_operand(uint64_t r) {
+    const uint64_t kind = r & 15u;
+    const uint64_t mant = (r >> 12) & 0x000fffffffffffffull;
+    const uint64_t sign = (r >> 11) & 1ull;
+    uint64_t e;
+    if (kind < 8) e = 1023 - 40 + ((r >> 4) % 81);
+    else if (kind < 10) e = (r >> 4) % 2047;                       // any finite exponent incl. subnormals
+    else if (kind == 10) e = 523 - 3 + ((r >> 4) % 7);             // lower edge of the window
+    else if (kind == 11) e = 1523 - 3 + ((r >> 4) % 7);            // upper edge
+    else if (kind == 12) return sign ? -0.0 : 0.0;
+    else if (kind == 13) return __longlong_as_double((long long)((sign << 63) | 0x7ff0000000000000ull));
+    else if (kind == 14) return __longlong_as_double(0x7ff8000000000000LL);
+    else { e = 1023; return __longlong_as_double((long long)((sign << 63) | (e << 52) | ((r >> 4) & 0xff)));  }  // near +-1 with few bits
+    return __longlong_as_double((long long)((sign << 63) | (e << 52) | mant));
+}
+
+__global__ void __launch_bounds__(256) k_selftest_division(int64_t n, uint64_t seed, unsigned long long* mismatches) {
+    unsigned long long bad = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double a = test_operand(mix64(seed + 2 * (uint64_t)i));
+        const double b = test_operand(mix64(seed + 2 * (uint64_t)i + 1));
+        const double ref = a / b;
+        const Den d(b);
+        const double q1 = ddiv(a, d);
+        const double q2 = sdiv(a, b);
+        const Den dn(-b);
+        const double q3 = ddiv(a, dn);
+        const double ref3 = a / (-b);
+        const bool nan_ref = ref != ref;
+        const bool ok1 = nan_ref ? (q1 != q1) : (__double_as_longlong(q1) == __double_as_longlong(ref));
+        const bool ok2 = nan_ref ? (q2 != q2) : (__double_as_longlong(q2) == __double_as_longlong(ref));
+        const bool ok3 = (ref3 != ref3) ? (q3 != q3) : (__double_as_longlong(q3) == __double_as_longlong(ref3));
+        bad += (ok1 ? 0 : 1) + (ok2 ? 0 : 1) + (ok3 ? 0 : 1);
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+
 }  // namespace rk
 
 // ================================================================================================ host side / C ABI
@@ -562,6 +609,22 @@ rk_status rk_measure_fp64_peak(rk_handle* h, double milliseconds, double* tflops
     cudaEventDestroy(e1);
     h->launches += 6;
     *tflops = best;
+    return RK_OK;
+}
+
+rk_status rk_selftest_division(rk_handle* h, int64_t n, uint64_t seed, int64_t* mismatches) {
+    if (!h || !mismatches || n < 0) return fail(RK_ERR_INVALID_ARGUMENT, "bad argument to rk_selftest_division");
+    RK_CUDA(cudaSetDevice(h->device));
+    rk_status st = ensure_stage(h, 256, 0);
+    if (st != RK_OK) return st;
+    RK_CUDA(cudaMemsetAsync(h->stage_dev, 0, 8, h->stream));
+    rk::k_selftest_division<<<h->sm_count * 8, 256, 0, h->stream>>>(n, seed, (unsigned long long*)h->stage_dev);
+    h->launches += 1;
+    RK_CUDA(cudaGetLastError());
+    unsigned long long bad = 0;
+    RK_CUDA(cudaMemcpyAsync(&bad, h->stage_dev, 8, cudaMemcpyDeviceToHost, h->stream));
+    RK_CUDA(cudaStreamSynchronize(h->stream));
+    *mismatches = (int64_t)bad;
     return RK_OK;
 }
 

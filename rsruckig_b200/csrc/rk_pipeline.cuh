@@ -23,6 +23,10 @@
 #include "rk_step2_acc.cuh"
 #include "rk_step2_none.cuh"
 
+#ifndef RK_MIN_BLOCKS
+#define RK_MIN_BLOCKS 4
+#endif
+
 namespace rk {
 
 // ------------------------------------------------------------------------------------------------ candidate sub-lists in scratch
@@ -152,7 +156,7 @@ __global__ void __launch_bounds__(128) k1_setup(const Params P) {
 // candidates and writes the valid ones to its own sub-list; the order in which the reference would have met them is
 // restored by k1_block.
 template <int F>
-__global__ void __launch_bounds__(128) k1_family(const Params P) {
+__global__ void __launch_bounds__(128, RK_MIN_BLOCKS) k1_family(const Params P) {
     const int64_t wstride = (int64_t)P.dof * P.cn;
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (tid >= 2 * wstride) return;
@@ -676,7 +680,7 @@ __global__ void __launch_bounds__(128) k2_first(const Params P) {
 // ------------------------------------------------------------------------------------------------ k2_stage
 // `step` numbers the launches of the chain (0 = the stage run inside k2_first); list `step & 1` is read, the other written.
 template <int F>
-__global__ void __launch_bounds__(128) k2_stage(const Params P, int step, int second_dir) {
+__global__ void __launch_bounds__(128, RK_MIN_BLOCKS) k2_stage(const Params P, int step, int second_dir) {
     const int64_t wstride = (int64_t)P.dof * P.cn;
     const uint32_t* list_in = P.list[step & 1];
     uint32_t* list_out = P.list[(step + 1) & 1];

@@ -138,7 +138,8 @@ template <class Sink>
 struct Step1Pos3 {
     // inputs (post-brake) and the products the reference precomputes (position_third_step1.rs:39-86)
     Bound b;
-    real pd, v0_v0, vf_vf, a0_a0, a0_p3, a0_p4, af_af, af_p3, af_p4, jj;
+    real pd, v0_v0, vf_vf, a0_a0, a0_p3, a0_p4, af_af, af_p3, af_p4;
+    Den jj;
     Sink sink;
     bool first_only;  // reference's return_after_found
 
@@ -149,7 +150,7 @@ struct Step1Pos3 {
         a0_a0 = b.a0 * b.a0; af_af = b.af * b.af;
         a0_p3 = b.a0 * a0_a0; a0_p4 = a0_a0 * a0_a0;
         af_p3 = b.af * af_af; af_p4 = af_af * af_af;
-        jj = j_max * j_max;
+        jj = Den(j_max * j_max);
         sink.count = 0;
     }
 
@@ -163,7 +164,7 @@ struct Step1Pos3 {
     // position_third_step1.rs:97-240. All four variants are validated as ReachedLimits::Vel (Q6); at most one is kept.
     __device__ __forceinline__ void family_vel(const Lim& L) {
         const real v0 = b.v0, a0 = b.a0, vf = b.vf, af = b.af;
-        const real v_max = L.v_max, a_max = L.a_max, a_min = L.a_min, j_max = L.j_max;
+        const Den v_max = L.v_max, a_max = L.a_max, a_min = L.a_min, j_max = L.j_max;
         double t[7];
         // ACC0_ACC1_VEL
         t[0] = (-a0 + a_max) / j_max;
@@ -232,7 +233,7 @@ struct Step1Pos3 {
     // position_third_step1.rs:241-327
     __device__ __forceinline__ void family_acc0_acc1(const Lim& L) {
         const real v0 = b.v0, a0 = b.a0, vf = b.vf, af = b.af;
-        const real a_max = L.a_max, a_min = L.a_min, j_max = L.j_max;
+        const Den a_max = L.a_max, a_min = L.a_min, j_max = L.j_max;
         real h1 = (3. * (af_p4 * a_max - a0_p4 * a_min)
                      + a_max * a_min * (8. * (a0_p3 - af_p3) + 3. * a_max * a_min * (a_max - a_min) + 6. * a_min * af_af - 6. * a_max * a0_a0)
                      + 12. * j_max * (a_max * a_min * ((a_max - 2. * a0) * v0 - (a_min - 2. * af) * vf) + a_min * a0_a0 * v0 - a_max * af_af * vf))
@@ -272,7 +273,7 @@ struct Step1Pos3 {
     // three are independent of one another, and the candidate order NONE, ACC0, ACC1 is restored when the lists are read.
     __device__ __forceinline__ void quartic_none(const Lim& L) {
         const real v0 = b.v0, a0 = b.a0, vf = b.vf, af = b.af;
-        const real a_max = L.a_max, a_min = L.a_min, j_max = L.j_max;
+        const Den a_max = L.a_max, a_min = L.a_min, j_max = L.j_max;
         const real jl = j_max * j_max;  // the reference mixes this local with the member computed from the UP jerk; equal values
         const real h2_none = (a0_a0 - af_af) / (2.0 * j_max) + (vf - v0);
         const real h2_h2 = h2_none * h2_none;
@@ -318,7 +319,7 @@ struct Step1Pos3 {
 
     __device__ __forceinline__ void quartic_acc0(const Lim& L) {
         const real v0 = b.v0, a0 = b.a0, vf = b.vf, af = b.af;
-        const real a_max = L.a_max, a_min = L.a_min, j_max = L.j_max;
+        const Den a_max = L.a_max, a_min = L.a_min, j_max = L.j_max;
         const real jl = j_max * j_max;  // the reference mixes this local with the member computed from the UP jerk; equal values
         // ACC0
         const real h3_acc0 = (a0_a0 - af_af) / (2.0 * a_max * j_max) + (vf - v0) / a_max;
@@ -375,7 +376,7 @@ struct Step1Pos3 {
 
     __device__ __forceinline__ void quartic_acc1(const Lim& L) {
         const real v0 = b.v0, a0 = b.a0, vf = b.vf, af = b.af;
-        const real a_max = L.a_max, a_min = L.a_min, j_max = L.j_max;
+        const Den a_max = L.a_max, a_min = L.a_min, j_max = L.j_max;
         const real jl = j_max * j_max;  // the reference mixes this local with the member computed from the UP jerk; equal values
         // ACC1
         const real h3_acc1 = -(a0_a0 + af_af) / (2.0 * j_max * a_min) + a_min / j_max + (vf - v0) / a_min;
@@ -452,7 +453,7 @@ struct Step1Pos3 {
 
     // ---- rare numerical rescues (position_third_step1.rs:603-895); each stops at its first valid candidate
     __device__ __forceinline__ void rescue_none(const Lim& L) {  // :843-895
-        const real j_max = L.j_max;
+        const Den j_max = L.j_max;
         double t[7] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
         const real h0 = sqrt((a0_a0 + af_af) / 2.0 + j_max * (b.vf - b.v0)) * fabs(j_max) / j_max;
         t[0] = (h0 - b.a0) / j_max;
@@ -465,7 +466,7 @@ struct Step1Pos3 {
 
     __device__ __forceinline__ void rescue_acc0(const Lim& L) {  // :644-778
         const real v0 = b.v0, a0 = b.a0, vf = b.vf, af = b.af;
-        const real a_max = L.a_max, a_min = L.a_min, j_max = L.j_max;
+        const Den a_max = L.a_max, a_min = L.a_min, j_max = L.j_max;
         double t[7] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
         // two step
         t[1] = (af_af - a0_a0 + 2.0 * j_max * (vf - v0)) / (2.0 * a0 * j_max);
@@ -503,7 +504,7 @@ struct Step1Pos3 {
 
     __device__ __forceinline__ void rescue_vel(const Lim& L) {  // :780-841
         const real v0 = b.v0, a0 = b.a0, vf = b.vf, af = b.af;
-        const real v_max = L.v_max, j_max = L.j_max;
+        const Den v_max = L.v_max, j_max = L.j_max;
         const real h1 = sqrt(af_af / (2.0 * jj) + (v_max - vf) / j_max);
         double t[7];
         t[0] = -a0 / j_max;
@@ -527,7 +528,7 @@ struct Step1Pos3 {
 
     __device__ __forceinline__ void rescue_acc1_vel(const Lim& L) {  // :603-642
         const real v0 = b.v0, a0 = b.a0, vf = b.vf, af = b.af;
-        const real v_max = L.v_max, a_min = L.a_min, j_max = L.j_max;
+        const Den v_max = L.v_max, a_min = L.a_min, j_max = L.j_max;
         double t[7];
         t[0] = 0.0;
         t[1] = 0.0;
@@ -544,11 +545,11 @@ struct Step1Pos3 {
     }
 };
 
-__device__ __forceinline__ Lim lim_dir(bool up, real v_max, real v_min, real a_max, real a_min, double j_max) {
+__device__ __forceinline__ Lim lim_dir(bool up, double v_max, double v_min, double a_max, double a_min, double j_max) {
     Lim L;
-    L.v_max = up ? v_max : v_min; L.v_min = up ? v_min : v_max;
-    L.a_max = up ? a_max : a_min; L.a_min = up ? a_min : a_max;
-    L.j_max = up ? j_max : -j_max;
+    L.v_max = Den(up ? v_max : v_min); L.v_min = Den(up ? v_min : v_max);
+    L.a_max = Den(up ? a_max : a_min); L.a_min = Den(up ? a_min : a_max);
+    L.j_max = Den(up ? j_max : -j_max);
     return L;
 }
 

@@ -16,7 +16,8 @@ struct S2 {
     Bound b;
     real tf;
     // products precomputed by the reference (position_third_step2.rs:51-128)
-    real pd, tf_tf, tf_p3, tf_p4, vd, vd_vd, vf_vf, ad, ad_ad, a0_a0, af_af, a0_p3, a0_p4, a0_p5, a0_p6, af_p3, af_p4, af_p5, af_p6, jj, g1, g2;
+    real pd, tf_tf, tf_p3, tf_p4, vd, vd_vd, vf_vf, ad, ad_ad, a0_a0, af_af, a0_p3, a0_p4, a0_p5, a0_p6, af_p3, af_p4, af_p5, af_p6, g1, g2;
+    Den jj;
 
     __device__ __forceinline__ void init(const Bound& bb, real tf_, double j_max) {
         b = bb;
@@ -28,7 +29,7 @@ struct S2 {
         a0_a0 = b.a0 * b.a0; af_af = b.af * b.af;
         a0_p3 = b.a0 * a0_a0; a0_p4 = a0_a0 * a0_a0; a0_p5 = a0_p3 * a0_a0; a0_p6 = a0_p4 * a0_a0;
         af_p3 = b.af * af_af; af_p4 = af_af * af_af; af_p5 = af_p3 * af_af; af_p6 = af_p4 * af_af;
-        jj = j_max * j_max;
+        jj = Den(j_max * j_max);
         g1 = -pd + tf * b.v0;
         g2 = -2.0 * pd + tf * (b.v0 + b.vf);
     }
@@ -37,15 +38,16 @@ struct S2 {
 // Result slot of a family.
 struct Hit {
     double t[7];
-    real jf;
+    double jf;
     int lim, cs, dir;
 };
 
 #define RK_S2_LOCALS                                                                                                        \
     const real v0 = s.b.v0, a0 = s.b.a0, vf = s.b.vf, af = s.b.af, tf = s.tf, pd = s.pd, vd = s.vd, ad = s.ad;            \
     const real a0_a0 = s.a0_a0, af_af = s.af_af, a0_p3 = s.a0_p3, af_p3 = s.af_p3, a0_p4 = s.a0_p4, af_p4 = s.af_p4;      \
-    const real vd_vd = s.vd_vd, ad_ad = s.ad_ad, tf_tf = s.tf_tf, g1 = s.g1, g2 = s.g2, j_max_j_max = s.jj;               \
-    const real v_max = L.v_max, v_min = L.v_min, a_max = L.a_max, a_min = L.a_min, j_max = L.j_max;                       \
+    const real vd_vd = s.vd_vd, ad_ad = s.ad_ad, tf_tf = s.tf_tf, g1 = s.g1, g2 = s.g2;                                     \
+    const Den j_max_j_max = s.jj;                                                                                            \
+    const Den v_max = L.v_max, v_min = L.v_min, a_max = L.a_max, a_min = L.a_min, j_max = L.j_max;                         \
     (void)v0; (void)vf; (void)pd; (void)vd; (void)ad; (void)a0_p3; (void)af_p3; (void)a0_p4; (void)af_p4; (void)vd_vd;     \
     (void)ad_ad; (void)tf_tf; (void)g1; (void)g2; (void)j_max_j_max; (void)v_max; (void)v_min; (void)a_min; (void)a0_a0;   \
     (void)af_af; (void)a0; (void)af; (void)tf; (void)a_max; (void)j_max;                                                    \
@@ -53,7 +55,7 @@ struct Hit {
 
 #define RK_TRY(CS, LIM, JF)                                      \
     if (check_pos3(t, (CS), (LIM), (JF), L, s.b)) {              \
-        h.jf = (JF); h.lim = (LIM); h.cs = (CS);                 \
+        h.jf = (double)(JF); h.lim = (LIM); h.cs = (CS);         \
         h.dir = (L.v_max > 0.0) ? DIR_UP : DIR_DOWN;             \
         return true;                                             \
     }

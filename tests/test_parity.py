@@ -61,6 +61,18 @@ def assert_exact(otg, ob, *, label=""):
     return int(ok.sum())
 
 
+def test_division_paths_are_ieee_exact(gpu):
+    """The kernels divide through their own routines (shared refined reciprocal, zero-safe division; rk_math.cuh). Both
+    must return the compiler's correctly rounded IEEE quotient bit for bit, special values included."""
+    import ctypes as C
+    otg = gpu(1, 0.005)
+    lib = otg._engine.lib
+    bad = C.c_int64(-1)
+    for seed in (1, 2, 3):
+        cabi.check(lib.rk_selftest_division(otg.handle, 200_000_000, seed * 0x9E3779B97F4A7C15 % (1 << 64), C.byref(bad)))
+        assert bad.value == 0, f"{bad.value} division results differ from IEEE a / b (seed {seed})"
+
+
 def test_bench_distribution_7dof_exact(gpu):
     n, dof = 100_000, 7
     f = workloads.bench_inputs(n, dof, seed=1)
