@@ -236,6 +236,11 @@ struct rk_handle {
     size_t stage_dev_bytes = 0;
     void* stage_pinned = nullptr;
     size_t stage_pinned_bytes = 0;
+    // host-buffer calculate: input chunks are copied on a second stream while the previous chunk is computed
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_computed[2] = {nullptr, nullptr};
+    void* chunk_in[2] = {nullptr, nullptr};
+    size_t chunk_in_bytes = 0;
 };
 
 struct rk_trajectories {
@@ -305,6 +310,7 @@ static rk_status fill_params(rk::Params& P, const rk_batch_desc* desc, const rk_
     P.v_max = in->max_velocity; P.a_max = in->max_acceleration; P.j_max = in->max_jerk;
     P.v_min = in->min_velocity; P.a_min = in->min_acceleration;
     P.enabled = in->enabled; P.min_dur = in->minimum_duration;
+    P.in_n = desc->n; P.in_shift = 0;
     return RK_OK;
 }
 
@@ -352,6 +358,11 @@ rk_status rk_create(int32_t device, rk_handle** out) {
     h->device = device;
     RK_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     RK_CUDA(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device));
+    RK_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    for (int k = 0; k < 2; ++k) {
+        RK_CUDA(cudaEventCreateWithFlags(&h->ev_copied[k], cudaEventDisableTiming));
+        RK_CUDA(cudaEventCreateWithFlags(&h->ev_computed[k], cudaEventDisableTiming));
+    }
     *out = h;
     return RK_OK;
 }
@@ -363,6 +374,12 @@ rk_status rk_destroy(rk_handle* h) {
     if (h->ws) { cudaFree(h->ws); cudaFree(h->wmeta); cudaFree(h->wsrc); cudaFree(h->wcnt); cudaFree(h->list[0]); cudaFree(h->list[1]); cudaFree(h->counters); }
     if (h->stage_dev) cudaFree(h->stage_dev);
     if (h->stage_pinned) cudaFreeHost(h->stage_pinned);
+    for (int k = 0; k < 2; ++k) {
+        if (h->chunk_in[k]) cudaFree(h->chunk_in[k]);
+        if (h->ev_copied[k]) cudaEventDestroy(h->ev_copied[k]);
+        if (h->ev_computed[k]) cudaEventDestroy(h->ev_computed[k]);
+    }
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     cudaStreamDestroy(h->stream);
     delete h;
     return RK_OK;
@@ -406,10 +423,6 @@ rk_status rk_calculate_batch(rk_handle* h, const rk_batch_desc* desc, const rk_b
     if (desc->n == 0) return RK_OK;
     RK_CUDA(cudaSetDevice(h->device));
     const bool host = desc->memory_space == RK_MEM_HOST;
-    if (host) {
-        st = stage_inputs(h, P, 0, nullptr);
-        if (st != RK_OK) return st;
-    }
     P.prof = traj->prof; P.codes = traj->codes; P.status = traj->status; P.duration = traj->duration; P.imd = traj->imd;
     P.limiting = traj->limiting; P.detail = traj->detail;
 
@@ -420,9 +433,59 @@ rk_status rk_calculate_batch(rk_handle* h, const rk_batch_desc* desc, const rk_b
     P.ws = h->ws; P.wmeta = h->wmeta; P.wsrc = h->wsrc; P.wcnt = h->wcnt;
     P.list[0] = h->list[0]; P.list[1] = h->list[1]; P.counters = h->counters;
 
-    for (int64_t off = 0; off < desc->n; off += cn_max) {
+    // host buffers: per-chunk staging, double buffered
+    const rk::Params host_ptrs = P;
+    const double* rk::Params::*dslots[11] = {&rk::Params::p0, &rk::Params::v0, &rk::Params::a0, &rk::Params::pf, &rk::Params::vf, &rk::Params::af,
+                                             &rk::Params::v_max, &rk::Params::a_max, &rk::Params::j_max, &rk::Params::v_min, &rk::Params::a_min};
+    if (host) {
+        const size_t per = sizeof(double) * (size_t)desc->dof * (size_t)cn_max;
+        size_t bytes = 0;
+        for (auto m : dslots) if (host_ptrs.*m) bytes += per;
+        if (host_ptrs.min_dur) bytes += sizeof(double) * (size_t)cn_max;
+        if (host_ptrs.enabled) bytes += (((size_t)desc->dof * (size_t)cn_max + 255) / 256) * 256;
+        if (bytes > h->chunk_in_bytes) {
+            for (int k = 0; k < 2; ++k) {
+                if (h->chunk_in[k]) cudaFree(h->chunk_in[k]);
+                h->chunk_in[k] = nullptr;
+            }
+            h->chunk_in_bytes = 0;
+            for (int k = 0; k < 2; ++k) RK_CUDA(cudaMalloc(&h->chunk_in[k], bytes));
+            h->chunk_in_bytes = bytes;
+        }
+    }
+
+    int chunk_index = 0;
+    for (int64_t off = 0; off < desc->n; off += cn_max, ++chunk_index) {
         P.off = off;
         P.cn = (desc->n - off < cn_max) ? (desc->n - off) : cn_max;
+        if (host) {
+            const int buf = chunk_index & 1;
+            // the buffer may still be read by the chunk computed two iterations ago
+            if (chunk_index >= 2) RK_CUDA(cudaStreamWaitEvent(h->copy_stream, h->ev_computed[buf], 0));
+            char* dev = (char*)h->chunk_in[buf];
+            const size_t per = sizeof(double) * (size_t)desc->dof * (size_t)P.cn;
+            for (auto m : dslots) {
+                if (!(host_ptrs.*m)) continue;
+                RK_CUDA(cudaMemcpy2DAsync(dev, sizeof(double) * P.cn, host_ptrs.*m + off, sizeof(double) * desc->n, sizeof(double) * P.cn,
+                                          (size_t)desc->dof, cudaMemcpyHostToDevice, h->copy_stream));
+                P.*m = (const double*)dev;
+                dev += per;
+            }
+            if (host_ptrs.min_dur) {
+                RK_CUDA(cudaMemcpyAsync(dev, host_ptrs.min_dur + off, sizeof(double) * P.cn, cudaMemcpyHostToDevice, h->copy_stream));
+                P.min_dur = (const double*)dev;
+                dev += sizeof(double) * (size_t)P.cn;
+            }
+            if (host_ptrs.enabled) {
+                RK_CUDA(cudaMemcpy2DAsync(dev, (size_t)P.cn, host_ptrs.enabled + off, (size_t)desc->n, (size_t)P.cn, (size_t)desc->dof,
+                                          cudaMemcpyHostToDevice, h->copy_stream));
+                P.enabled = (const uint8_t*)dev;
+            }
+            RK_CUDA(cudaEventRecord(h->ev_copied[buf], h->copy_stream));
+            RK_CUDA(cudaStreamWaitEvent(h->stream, h->ev_copied[buf], 0));
+            P.in_n = P.cn;
+            P.in_shift = -off;
+        }
         const int64_t items = P.cn * P.dof;
         const unsigned grid_items = (unsigned)((items + 127) / 128);
         // list-driven stages: a few resident waves per SM, grid-stride over the (device-side) list length
@@ -456,6 +519,7 @@ rk_status rk_calculate_batch(rk_handle* h, const rk_batch_desc* desc, const rk_b
         }
         rk::k2_fail<<<(unsigned)h->sm_count, 128, 0, h->stream>>>(P);
         h->launches += 9 + RK_S2_STEPS;
+        if (host) RK_CUDA(cudaEventRecord(h->ev_computed[chunk_index & 1], h->stream));
     }
     RK_CUDA(cudaGetLastError());
 

@@ -10,8 +10,10 @@
 namespace rk {
 
 struct Params {
-    int64_t n;        // trajectories in the batch (stride of the caller's arrays and of the trajectory storage)
+    int64_t n;        // trajectories in the batch (stride of the trajectory storage)
     int64_t off;      // first trajectory of this chunk
+    int64_t in_n;     // stride of the input arrays: n for caller-resident device arrays, cn for a staged chunk
+    int64_t in_shift; // input index of trajectory ig is ig + in_shift (0, or -off for a staged chunk)
     int64_t cn;       // trajectories in this chunk (stride of the scratch arrays)
     int32_t dof;
     int32_t discrete;
@@ -46,7 +48,7 @@ struct DofIn {
 };
 
 __device__ __forceinline__ DofIn load_dof(const Params& P, int d, int64_t ig) {
-    const int64_t g = (int64_t)d * P.n + ig;
+    const int64_t g = (int64_t)d * P.in_n + (ig + P.in_shift);
     DofIn x;
     x.p0 = P.p0[g]; x.v0 = P.v0[g]; x.a0 = P.a0[g];
     x.pf = P.pf[g]; x.vf = P.vf[g]; x.af = P.af[g];

@@ -308,7 +308,7 @@ __global__ void __launch_bounds__(128) k_sync(const Params P) {
         }
     }
 
-    const double md_raw = P.min_dur ? P.min_dur[ig] : __longlong_as_double(0x7ff8000000000000LL);
+    const double md_raw = P.min_dur ? P.min_dur[ig + P.in_shift] : __longlong_as_double(0x7ff8000000000000LL);
     const bool has_md = md_raw == md_raw;
     const double md = has_md ? md_raw : 0.0;
 
