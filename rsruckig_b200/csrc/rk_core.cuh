@@ -70,9 +70,9 @@ __device__ __forceinline__ bool forces_a3_zero(int lim) {
 // Profile::check for the third-order position interface (profile.rs:323-482,
 // set_limits == false as in every call of the reference, :498). Returns
 // validity only; nothing is stored.
-__device__ __noinline__ bool check_pos3(double t0, double t1, double t2, double t3, double t4, double t5, double t6, int cs, int lim,
-                                        double jf, double v_max, double v_min, double a_max, double a_min, double p0, double v0,
-                                        double a0, double pf, double vf, double af) {
+__device__ __forceinline__ bool check_pos3_body(double t0, double t1, double t2, double t3, double t4, double t5, double t6, int cs, int lim,
+                                                double jf, double v_max, double v_min, double a_max, double a_min, double p0, double v0,
+                                                double a0, double pf, double vf, double af) {
     if (t0 < 0.0 || t1 < 0.0 || t2 < 0.0 || t3 < 0.0 || t4 < 0.0 || t5 < 0.0 || t6 < 0.0) return false;
     const double t[7] = {t0, t1, t2, t3, t4, t5, t6};
 
@@ -117,12 +117,24 @@ __device__ __noinline__ bool check_pos3(double t0, double t1, double t2, double 
         && v[5] <= v_upp_lim && v[5] >= v_low_lim && v[6] <= v_upp_lim && v[6] >= v_low_lim;
 }
 
+// Out-of-line copy for the families with many candidates (one body in the kernel instead of one per call site) ...
+__device__ __noinline__ bool check_pos3(double t0, double t1, double t2, double t3, double t4, double t5, double t6, int cs, int lim,
+                                        double jf, double v_max, double v_min, double a_max, double a_min, double p0, double v0,
+                                        double a0, double pf, double vf, double af) {
+    return check_pos3_body(t0, t1, t2, t3, t4, t5, t6, cs, lim, jf, v_max, v_min, a_max, a_min, p0, v0, a0, pf, vf, af);
+}
+
 struct Lim {  // direction-resolved limits handed to the family functions
     Den v_max, v_min, a_max, a_min, j_max;
 };
 
 __device__ __forceinline__ bool check_pos3(const double (&t)[7], int cs, int lim, double jf, const Lim& L, const Bound& b) {
     return check_pos3(t[0], t[1], t[2], t[3], t[4], t[5], t[6], cs, lim, jf, L.v_max, L.v_min, L.a_max, L.a_min, b.p0, b.v0, b.a0, b.pf, b.vf, b.af);
+}
+
+// ... and the inlined form for kernels with a single call site: no argument shuffling, and `cs` / `lim` fold to constants.
+__device__ __forceinline__ bool check_pos3_inline(const double (&t)[7], int cs, int lim, double jf, const Lim& L, const Bound& b) {
+    return check_pos3_body(t[0], t[1], t[2], t[3], t[4], t[5], t[6], cs, lim, jf, L.v_max, L.v_min, L.a_max, L.a_min, b.p0, b.v0, b.a0, b.pf, b.vf, b.af);
 }
 
 // profile.rs:502-516 check_with_timing_full

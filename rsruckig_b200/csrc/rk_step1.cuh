@@ -109,6 +109,7 @@ __device__ __noinline__ bool calculate_block(BlockRec& blk, Cand* vp, int n, dou
 // ===================================================== third-order position interface
 // Where validated candidates go: a local list (numerical rescues, zero-limit case) ...
 struct LocalSink {
+    static constexpr bool inline_check = false;
     Cand vp[6];
     int count;
     __device__ __forceinline__ void put(const double (&t)[7], int lim, const Lim& L) {
@@ -123,6 +124,7 @@ struct LocalSink {
 // ... or the per-item sub-list of one (family, direction) in HBM scratch: only t[7] is stored, the codes follow from the
 // sub-list the candidate sits in.
 struct GlobalSink {
+    static constexpr bool inline_check = true;  // the family kernels have one to four emit sites each
     double* base;     // slot 0, t[0] of this sub-list for this item
     int64_t wstride;
     int count;
@@ -156,7 +158,7 @@ struct Step1Pos3 {
 
     // Validate t; on success hand it to the sink. Returns validity.
     __device__ __forceinline__ bool emit(const double (&t)[7], int lim, const Lim& L) {
-        if (!check_pos3(t, UDDU, lim, L.j_max, L, b)) return false;
+        if (!(Sink::inline_check ? check_pos3_inline(t, UDDU, lim, L.j_max, L, b) : check_pos3(t, UDDU, lim, L.j_max, L, b))) return false;
         sink.put(t, lim, L);
         return true;
     }

@@ -53,6 +53,13 @@ struct Hit {
     (void)af_af; (void)a0; (void)af; (void)tf; (void)a_max; (void)j_max;                                                    \
     double (&t)[7] = h.t;
 
+#define RK_TRY_INLINE(CS, LIM, JF)                               \
+    if (check_pos3_inline(t, (CS), (LIM), (JF), L, s.b)) {       \
+        h.jf = (double)(JF); h.lim = (LIM); h.cs = (CS);         \
+        h.dir = (L.v_max > 0.0) ? DIR_UP : DIR_DOWN;             \
+        return true;                                             \
+    }
+
 #define RK_TRY(CS, LIM, JF)                                      \
     if (check_pos3(t, (CS), (LIM), (JF), L, s.b)) {              \
         h.jf = (double)(JF); h.lim = (LIM); h.cs = (CS);         \

@@ -36,7 +36,7 @@ __device__ __forceinline__ bool vel_uddu_root(const S2& s, const Lim& L, Hit& h,
     t[4] = h1;
     t[5] = 0.0;
     t[6] = h1 + af / j_max;
-    RK_TRY(UDDU, L_VEL, j_max)
+    RK_TRY_INLINE(UDDU, L_VEL, j_max)
     return false;
 }
 
@@ -67,7 +67,7 @@ __device__ __forceinline__ bool vel_udud_root(const S2& s, const Lim& L, Hit& h,
     t[4] = h1;
     t[5] = 0.0;
     t[6] = h1 - af / j_max;
-    RK_TRY(UDUD, L_VEL, j_max)
+    RK_TRY_INLINE(UDUD, L_VEL, j_max)
     return false;
 }
 
