@@ -12,10 +12,11 @@ is fixed as N grows ("weak" scaling); trajectories are independent, ranks never 
 value  = trajectories/s, inputs and outputs resident in HBM, CUDA events on the library's stream, max over ranks.
 e2e    = the same through the C ABI with HOST buffers (pinned): H2D of the nine input arrays, the three kernels, D2H of
          status + duration — all inside the timed region.
-roofline: the path is FP64-pipe bound, so `bound` is "fp64": achieved = algorithmic flop per trajectory
-         (measured by the op-counting build of the oracle, see profiles/) x trajectories/s; peak = a DFMA probe run on
-         the same GPU right before the timed region (MEASURED_PEAKS.json has no FP64 entry). The HBM side is reported
-         next to it against MEASURED_PEAKS.json's copy bandwidth.
+roofline: the path is FP64-pipe bound, so `bound` is "fp64": achieved = FP64 flop per trajectory
+         (profiles/algorithmic_ops.json: adds + muls + 2 x FMAs the algorithm executes for the bench distribution, counted
+         with ncu) x trajectories/s; peak = a DFMA probe run on the same GPU right before the timed region
+         (MEASURED_PEAKS.json has no FP64 entry). The HBM side is reported next to it against MEASURED_PEAKS.json's copy
+         bandwidth. `latency_64k` (p50 of one 64Ki batch) and `at_time` (configs[3] rollout, HBM-write bound) ride along.
 cpu_baseline: the C++ restatement of the reference (oracle/, glibc libm) on this box's host cores, on a bounded sample.
 """
 from __future__ import annotations
@@ -38,7 +39,7 @@ METRIC = "7-DoF trajectory calculations/s (position interface, Time sync)"
 UNIT = "trajectories/s"
 DELTA_TIME = 0.005
 BYTES_IN = 9 * DOF * 8                 # nine mandatory f64 arrays
-BYTES_OUT = (16 * DOF + 3) * 8         # compact result record of §8d (status, duration, t[7] + codes + jf ... per DoF)
+BYTES_OUT = (16 * DOF + 3) * 8         # compact result record of SURVEY.md §8d; the kernels store the full 472 B Profile per DoF
 
 
 def algorithmic_flop_per_trajectory() -> tuple[float, str]:
@@ -285,22 +286,84 @@ def run_b200(args):
                "d2h_bytes_per_step": int(h_status.numel() * 4 + h_duration.numel() * 8),
                "note": "rk_calculate_batch with RK_MEM_HOST on pinned buffers; trajectories stay device-resident for rk_at_time_batch"}
 
+    # ---- p50 latency of one 64Ki batch (the second half of BASELINE.json's metric) and the at_time rollout of configs[3]
+    latency = None
+    sampling = None
+    if not args.no_extras and rank == 0:
+        n64 = 65536
+        f64k = {k: v[:, :n64].contiguous() for k, v in f.items()}
+        otg64 = BatchRuckig(DOF, DELTA_TIME, ThrowErrorHandler, device=local)
+        st64 = torch.zeros(n64, dtype=torch.int32, device=dev)
+        du64 = torch.zeros(n64, dtype=torch.float64, device=dev)
+        run64 = lambda: otg64.calculate(f64k, n=n64, memory_space=cabi.RK_MEM_DEVICE, status=st64, duration=du64)
+        for _ in range(5):
+            run64()
+        otg64.sync()
+        times = []
+        with torch.cuda.stream(stream):
+            for _ in range(50):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(stream)
+                run64()
+                b.record(stream)
+                b.synchronize()
+                times.append(a.elapsed_time(b))
+        times.sort()
+        latency = {"batch": n64, "p50_ms": times[len(times) // 2], "p99_ms": times[-1], "runs": len(times),
+                   "note": "one rk_calculate_batch on device-resident buffers, CUDA events on the library's stream"}
+        # 64Ki environments x 7 DoF x K control cycles of Trajectory::at_time (p, v, a): HBM-write bound
+        K = args.sample_steps
+        out_bytes = 3 * 8 * DOF * n64 * K
+        pos = torch.empty((K, DOF, n64), dtype=torch.float64, device=dev)
+        vel = torch.empty_like(pos)
+        acc = torch.empty_like(pos)
+        sample = lambda: otg64.at_time(time_start=0.0, delta_time=DELTA_TIME, steps=K, memory_space=cabi.RK_MEM_DEVICE,
+                                       position=pos, velocity=vel, acceleration=acc)
+        for _ in range(3):
+            sample()
+        otg64.sync()
+        with torch.cuda.stream(stream):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            for _ in range(5):
+                sample()
+            b.record(stream)
+            b.synchronize()
+        ms_s = a.elapsed_time(b) / 5
+        peaks_ = measured_peaks()
+        sampling = {"workload": f"{n64} x {DOF}-DoF trajectories, {K} control cycles of Trajectory::at_time (position, velocity, acceleration)",
+                    "ms_per_rollout": ms_s, "samples_per_s": n64 * K / (ms_s * 1e-3),
+                    "roofline": {"bound": "hbm", "achieved": out_bytes / (ms_s * 1e-3) / 1e9, "peak": peaks_["hbm_gbs"], "unit": "GB/s",
+                                 "frac": out_bytes / (ms_s * 1e-3) / 1e9 / peaks_["hbm_gbs"], "of": peaks_["_source"],
+                                 "bytes_per_launch": out_bytes, "note": "algorithmic bytes = 3 x 8 B x DoF per sample written; the 472 B profile per (DoF, trajectory) read once is amortised over K"}}
+        del pos, vel, acc
+
     if rank == 0:
         flop, flop_how = algorithmic_flop_per_trajectory()
         peaks = measured_peaks()
         per_gpu = value / world
         achieved_tflops = flop * per_gpu / 1e12
         hbm_gbs = (BYTES_IN + BYTES_OUT) * per_gpu / 1e9
+        ops = {}
+        ops_path = os.path.join(ROOT, "profiles", "algorithmic_ops.json")
+        if os.path.exists(ops_path):
+            ops = json.load(open(ops_path))
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic", "config": config(n, world), "gpu_launches": int(gpu_launches), "launches_per_step": int(launches_per_step),
-                "working_fraction": n_working / n, "clocks": clocks, "e2e": e2e,
+                "working_fraction": n_working / n, "clocks": clocks, "e2e": e2e, "latency_64k": latency, "at_time": sampling,
                 "roofline": {"bound": "fp64", "achieved": achieved_tflops, "peak": fp64_peak_tflops, "unit": "TFLOP/s",
-                             "frac": achieved_tflops / fp64_peak_tflops if fp64_peak_tflops else None, "traffic": None,
-                             "kernels": "k_step1 + k_sync + k_step2 (one step); per-kernel shares in profiles/",
+                             "frac": achieved_tflops / fp64_peak_tflops if fp64_peak_tflops else None,
+                             "traffic": (ops.get("dram_bytes_per_trajectory") or 0) * n or None,
+                             "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum over the 27 kernels of one step (ncu, profiles/), per GPU",
+                             "kernels": "one step = k1_setup, k1_family<0..4>, k1_block, k_sync, k2_first, 17 x k2_stage, k2_fail per chunk of "
+                                        "4Mi (DoF, trajectory) items; the FP64 work is spread over the k1_family and k2_stage kernels, per-kernel "
+                                        "shares and ncu metrics in profiles/",
                              "flop_per_trajectory": flop, "flop_how": flop_how,
+                             "fp64_issue_frac": (ops.get("fp64_instructions") or 0) * per_gpu / (fp64_peak_tflops * 1e12 / 2) if fp64_peak_tflops else None,
                              "peak_how": "DFMA probe (rk_measure_fp64_peak) on this GPU before the timed region, FMA = 2 flop; the kernels run "
-                                         "with --fmad=false, so an add or a mul fills a DFMA issue slot with 1 flop",
+                                         "with --fmad=false, so an add or a mul fills a DFMA issue slot with 1 flop (fp64_issue_frac = FP64 "
+                                         "instructions issued / DFMA issue peak)",
                              "hbm": {"achieved": hbm_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": hbm_gbs / peaks["hbm_gbs"],
                                      "of": peaks["_source"], "bytes_per_trajectory": BYTES_IN + BYTES_OUT}}}
         if not args.no_cpu:
@@ -320,6 +383,8 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=0, help="trajectories per step of the reference arm (0 = 131072 per thread)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the 64Ki-batch latency and the at_time rollout")
+    ap.add_argument("--sample-steps", type=int, default=1000, help="control cycles of the at_time rollout (configs[3])")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

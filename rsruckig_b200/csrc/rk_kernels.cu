@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(128) k_validate(const Params P, uint8_t* valid
 // ------------------------------------------------------------------------------------------------ k_at_time
 struct SampleParams {
     int64_t n;
-    int32_t dof, steps;
+    int32_t dof, steps, k_chunk;
     double time_start, delta_time;
     const double* prof;
     const double* duration;
@@ -82,9 +82,15 @@ __global__ void __launch_bounds__(256) k_at_time(const SampleParams S) {
         ba[k] = q[(int64_t)(S_BRAKE_A + k) * st]; bj[k] = q[(int64_t)(S_BRAKE_J + k) * st];
     }
 
+    // blockIdx.y picks a slice of the K sample times; the time of sample k is k + 1 repeated additions of delta_time
+    // (ruckig.rs:293), so a slice first replays the additions of the samples before it (no memory traffic).
+    const int k_begin = blockIdx.y * S.k_chunk;
+    const int k_end = (k_begin + S.k_chunk < S.steps) ? (k_begin + S.k_chunk) : S.steps;
     double time = S.time_start;
 #pragma unroll 1
-    for (int k = 0; k < S.steps; ++k) {
+    for (int k = 0; k < k_begin; ++k) time += S.delta_time;
+#pragma unroll 1
+    for (int k = k_begin; k < k_end; ++k) {
         time += S.delta_time;
         double t0, p0, v0, a0, j0;
         int section;
@@ -591,7 +597,9 @@ rk_status rk_at_time_batch(rk_handle* h, const rk_trajectories* traj, const rk_s
     }
     S.pos = dev[0]; S.vel = dev[1]; S.acc = dev[2]; S.jerk = dev[3]; S.section = dsec;
     const int64_t total = (int64_t)traj->dof * traj->n;
-    rk::k_at_time<<<(unsigned)((total + 255) / 256), 256, 0, h->stream>>>(S);
+    S.k_chunk = 50;
+    const dim3 grid((unsigned)((total + 255) / 256), (unsigned)((desc->steps + S.k_chunk - 1) / S.k_chunk), 1);
+    rk::k_at_time<<<grid, 256, 0, h->stream>>>(S);
     h->launches += 1;
     RK_CUDA(cudaGetLastError());
     if (host) {
