@@ -330,12 +330,25 @@ def run_b200(args):
             b.record(stream)
             b.synchronize()
         ms_s = a.elapsed_time(b) / 5
+        # pure-write reference on the same buffers (torch fill): what a write-only stream reaches on this GPU
+        for t_ in (pos, vel, acc):
+            t_.zero_()
+        torch.cuda.synchronize()
+        a2, b2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a2.record()
+        for _ in range(3):
+            for t_ in (pos, vel, acc):
+                t_.zero_()
+        b2.record()
+        b2.synchronize()
+        fill_gbs = 3 * out_bytes / (a2.elapsed_time(b2) * 1e-3) / 1e9
         peaks_ = measured_peaks()
         sampling = {"workload": f"{n64} x {DOF}-DoF trajectories, {K} control cycles of Trajectory::at_time (position, velocity, acceleration)",
                     "ms_per_rollout": ms_s, "samples_per_s": n64 * K / (ms_s * 1e-3),
                     "roofline": {"bound": "hbm", "achieved": out_bytes / (ms_s * 1e-3) / 1e9, "peak": peaks_["hbm_gbs"], "unit": "GB/s",
                                  "frac": out_bytes / (ms_s * 1e-3) / 1e9 / peaks_["hbm_gbs"], "of": peaks_["_source"],
-                                 "bytes_per_launch": out_bytes, "note": "algorithmic bytes = 3 x 8 B x DoF per sample written; the 472 B profile per (DoF, trajectory) read once is amortised over K"}}
+                                 "bytes_per_launch": out_bytes, "write_only_fill_gbs": fill_gbs,
+                                 "frac_of_write_only_fill": out_bytes / (ms_s * 1e-3) / 1e9 / fill_gbs, "note": "algorithmic bytes = 3 x 8 B x DoF per sample written; the 472 B profile per (DoF, trajectory) read once is amortised over K"}}
         del pos, vel, acc
 
     if rank == 0:

@@ -68,19 +68,17 @@ __global__ void __launch_bounds__(256) k_at_time(const SampleParams S) {
     const int64_t st = total;
 
     const double duration = S.duration[i];
-    double ts[7], pp[8], pv[8], pa[8], pj[7];
-#pragma unroll
-    for (int k = 0; k < 7; ++k) { ts[k] = q[(int64_t)(S_TSUM + k) * st]; pj[k] = q[(int64_t)(S_J + k) * st]; }
-#pragma unroll
-    for (int k = 0; k < 8; ++k) { pp[k] = q[(int64_t)(S_P + k) * st]; pv[k] = q[(int64_t)(S_V + k) * st]; pa[k] = q[(int64_t)(S_A + k) * st]; }
+    const double ts6 = q[(int64_t)(S_TSUM + 6) * st];
+    const double p7 = q[(int64_t)(S_P + 7) * st], v7 = q[(int64_t)(S_V + 7) * st], a7 = q[(int64_t)(S_A + 7) * st];
     const double bdur = q[(int64_t)S_BRAKE_DUR * st];
     const double bt0 = q[(int64_t)S_BRAKE_T * st];
-    double bp[2], bv[2], ba[2], bj[2];
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-        bp[k] = q[(int64_t)(S_BRAKE_P + k) * st]; bv[k] = q[(int64_t)(S_BRAKE_V + k) * st];
-        ba[k] = q[(int64_t)(S_BRAKE_A + k) * st]; bj[k] = q[(int64_t)(S_BRAKE_J + k) * st];
-    }
+
+    // Sample times only grow, so the phase index of trajectory.rs:134-140 ("first i with t_sum[i] > t", default 6) only
+    // grows too: the current phase lives in registers and is re-read from HBM (L2) only when a sample crosses its end.
+    int index = 0;
+    double t_hi = q[(int64_t)(S_TSUM + 0) * st];  // t_sum[index]
+    double t_lo = 0.0;                            // t_sum[index - 1]
+    double cp = q[(int64_t)(S_P + 0) * st], cv = q[(int64_t)(S_V + 0) * st], ca = q[(int64_t)(S_A + 0) * st], cj = q[(int64_t)(S_J + 0) * st];
 
     // blockIdx.y picks a slice of the K sample times; the time of sample k is k + 1 repeated additions of delta_time
     // (ruckig.rs:293), so a slice first replays the additions of the samples before it (no memory traffic).
@@ -96,32 +94,38 @@ __global__ void __launch_bounds__(256) k_at_time(const SampleParams S) {
         int section;
         if (time >= duration) {  // :60-83
             section = 1;
-            t0 = time - (bdur + ts[6]);
-            p0 = pp[7]; v0 = pv[7]; a0 = pa[7]; j0 = 0.0;
+            t0 = time - (bdur + ts6);
+            p0 = p7; v0 = v7; a0 = a7; j0 = 0.0;
         } else {
             // cumulative_times[0] == duration > time, so the section index is 0 and t_diff == time (:85-99, Q13)
             section = 0;
             double td = time;
             bool set = false;
             if (bdur > 0.0) {
-                if (td < bdur) {
-                    const int index = (td < bt0) ? 0 : 1;
-                    if (index > 0) td -= bt0;
-                    t0 = td; p0 = bp[index]; v0 = bv[index]; a0 = ba[index]; j0 = bj[index];
+                if (td < bdur) {  // brake pre-trajectory (:103-121)
+                    const int bi = (td < bt0) ? 0 : 1;
+                    if (bi > 0) td -= bt0;
+                    t0 = td;
+                    p0 = q[(int64_t)(S_BRAKE_P + bi) * st]; v0 = q[(int64_t)(S_BRAKE_V + bi) * st];
+                    a0 = q[(int64_t)(S_BRAKE_A + bi) * st]; j0 = q[(int64_t)(S_BRAKE_J + bi) * st];
                     set = true;
                 } else {
                     td -= bdur;
                 }
             }
             if (!set) {
-                if (td >= ts[6]) {
-                    t0 = td - ts[6]; p0 = pp[7]; v0 = pv[7]; a0 = pa[7]; j0 = 0.0;
+                if (td >= ts6) {  // past this DoF's own end (:122-132)
+                    t0 = td - ts6; p0 = p7; v0 = v7; a0 = a7; j0 = 0.0;
                 } else {
-                    int index = 6;
-#pragma unroll
-                    for (int m = 6; m >= 0; --m) if (ts[m] > td) index = m;
-                    if (index > 0) td -= ts[index - 1];
-                    t0 = td; p0 = pp[index]; v0 = pv[index]; a0 = pa[index]; j0 = pj[index];
+                    while (index < 6 && !(t_hi > td)) {
+                        ++index;
+                        t_lo = t_hi;
+                        t_hi = q[(int64_t)(S_TSUM + index) * st];
+                        cp = q[(int64_t)(S_P + index) * st]; cv = q[(int64_t)(S_V + index) * st];
+                        ca = q[(int64_t)(S_A + index) * st]; cj = q[(int64_t)(S_J + index) * st];
+                    }
+                    if (index > 0) td -= t_lo;
+                    t0 = td; p0 = cp; v0 = cv; a0 = ca; j0 = cj;
                 }
             }
         }
@@ -597,7 +601,13 @@ rk_status rk_at_time_batch(rk_handle* h, const rk_trajectories* traj, const rk_s
     }
     S.pos = dev[0]; S.vel = dev[1]; S.acc = dev[2]; S.jerk = dev[3]; S.section = dsec;
     const int64_t total = (int64_t)traj->dof * traj->n;
-    S.k_chunk = 50;
+    // K is sliced over blockIdx.y only when (DoF x n) alone cannot fill the GPU: every slice re-reads the 45-double profile
+    // and replays the time additions, which costs more than it hides once ~300 k threads exist (measured: 64 Ki x 7-DoF x
+    // 1000 cycles runs at 3.1 TB/s unsliced, 2.4 TB/s in slices of 50).
+    int64_t slices = (300000 + total - 1) / total;
+    if (slices < 1) slices = 1;
+    if (slices > (desc->steps + 31) / 32) slices = (desc->steps + 31) / 32;
+    S.k_chunk = (int32_t)((desc->steps + slices - 1) / slices);
     const dim3 grid((unsigned)((total + 255) / 256), (unsigned)((desc->steps + S.k_chunk - 1) / S.k_chunk), 1);
     rk::k_at_time<<<grid, 256, 0, h->stream>>>(S);
     h->launches += 1;
