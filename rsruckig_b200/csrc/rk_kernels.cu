@@ -238,6 +238,9 @@ struct rk_handle {
     uint32_t* wmeta = nullptr;
     uint8_t* wsrc = nullptr;
     uint8_t* wcnt = nullptr;
+    uint32_t* wqmask = nullptr;
+    uint2* rq_item = nullptr;
+    double* rq_root = nullptr;
     uint32_t* list[2] = {nullptr, nullptr};
     uint32_t* counters = nullptr;
     int sm_count = 148;
@@ -269,13 +272,16 @@ struct rk_trajectories {
 static rk_status ensure_scratch(rk_handle* h, int64_t items) {
     if (items <= h->ws_items) return RK_OK;
     if (h->ws) {
-        cudaFree(h->ws); cudaFree(h->wmeta); cudaFree(h->wsrc); cudaFree(h->wcnt); cudaFree(h->list[0]); cudaFree(h->list[1]); cudaFree(h->counters);
+        cudaFree(h->ws); cudaFree(h->wmeta); cudaFree(h->wsrc); cudaFree(h->wcnt); cudaFree(h->wqmask); cudaFree(h->rq_item); cudaFree(h->rq_root); cudaFree(h->list[0]); cudaFree(h->list[1]); cudaFree(h->counters);
         h->ws = nullptr; h->ws_items = 0;
     }
     RK_CUDA(cudaMalloc(&h->ws, sizeof(double) * rk::WS_SLOTS * items));
     RK_CUDA(cudaMalloc(&h->wmeta, sizeof(uint32_t) * rk::WM_WORDS * items));
     RK_CUDA(cudaMalloc(&h->wsrc, items));
     RK_CUDA(cudaMalloc(&h->wcnt, 10 * items));
+    RK_CUDA(cudaMalloc(&h->wqmask, sizeof(uint32_t) * 6 * items));
+    RK_CUDA(cudaMalloc(&h->rq_item, sizeof(uint2) * 8 * items));
+    RK_CUDA(cudaMalloc(&h->rq_root, sizeof(double) * 8 * items));
     RK_CUDA(cudaMalloc(&h->list[0], sizeof(uint32_t) * items));
     RK_CUDA(cudaMalloc(&h->list[1], sizeof(uint32_t) * items));
     RK_CUDA(cudaMalloc(&h->counters, sizeof(uint32_t) * 32));
@@ -381,7 +387,7 @@ rk_status rk_destroy(rk_handle* h) {
     if (!h) return RK_OK;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    if (h->ws) { cudaFree(h->ws); cudaFree(h->wmeta); cudaFree(h->wsrc); cudaFree(h->wcnt); cudaFree(h->list[0]); cudaFree(h->list[1]); cudaFree(h->counters); }
+    if (h->ws) { cudaFree(h->ws); cudaFree(h->wmeta); cudaFree(h->wsrc); cudaFree(h->wcnt); cudaFree(h->wqmask); cudaFree(h->rq_item); cudaFree(h->rq_root); cudaFree(h->list[0]); cudaFree(h->list[1]); cudaFree(h->counters); }
     if (h->stage_dev) cudaFree(h->stage_dev);
     if (h->stage_pinned) cudaFreeHost(h->stage_pinned);
     for (int k = 0; k < 2; ++k) {
@@ -440,7 +446,7 @@ rk_status rk_calculate_batch(rk_handle* h, const rk_batch_desc* desc, const rk_b
     if (cn_max > desc->n) cn_max = desc->n;
     st = ensure_scratch(h, cn_max * desc->dof);
     if (st != RK_OK) return st;
-    P.ws = h->ws; P.wmeta = h->wmeta; P.wsrc = h->wsrc; P.wcnt = h->wcnt;
+    P.ws = h->ws; P.wmeta = h->wmeta; P.wsrc = h->wsrc; P.wcnt = h->wcnt; P.wqmask = h->wqmask; P.rq_item = h->rq_item; P.rq_root = h->rq_root;
     P.list[0] = h->list[0]; P.list[1] = h->list[1]; P.counters = h->counters;
 
     // host buffers: per-chunk staging, double buffered
@@ -504,9 +510,12 @@ rk_status rk_calculate_batch(rk_handle* h, const rk_batch_desc* desc, const rk_b
         RK_CUDA(cudaMemsetAsync(h->counters, 0, sizeof(uint32_t) * 32, h->stream));
         rk::k1_setup<<<grid_items, 128, 0, h->stream>>>(P);
         const unsigned grid_fam = (unsigned)((2 * items + 127) / 128);
-        rk::k1_family<0><<<grid_fam, 128, 0, h->stream>>>(P);
-        rk::k1_family<1><<<grid_fam, 128, 0, h->stream>>>(P);
-        rk::k1_family<2><<<grid_fam, 128, 0, h->stream>>>(P);
+        rk::k1_quartic_roots<0><<<grid_fam, 128, 0, h->stream>>>(P);
+        rk::k1_quartic_check<0><<<grid_list, 128, 0, h->stream>>>(P);
+        rk::k1_quartic_roots<1><<<grid_fam, 128, 0, h->stream>>>(P);
+        rk::k1_quartic_check<1><<<grid_list, 128, 0, h->stream>>>(P);
+        rk::k1_quartic_roots<2><<<grid_fam, 128, 0, h->stream>>>(P);
+        rk::k1_quartic_check<2><<<grid_list, 128, 0, h->stream>>>(P);
         rk::k1_family<3><<<grid_fam, 128, 0, h->stream>>>(P);
         rk::k1_family<4><<<grid_fam, 128, 0, h->stream>>>(P);
         rk::k1_block<<<grid_items, 128, 0, h->stream>>>(P);
@@ -528,7 +537,7 @@ rk_status rk_calculate_batch(rk_handle* h, const rk_batch_desc* desc, const rk_b
             }
         }
         rk::k2_fail<<<(unsigned)h->sm_count, 128, 0, h->stream>>>(P);
-        h->launches += 9 + RK_S2_STEPS;
+        h->launches += 12 + RK_S2_STEPS;
         if (host) RK_CUDA(cudaEventRecord(h->ev_computed[chunk_index & 1], h->stream));
     }
     RK_CUDA(cudaGetLastError());

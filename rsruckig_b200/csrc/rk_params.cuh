@@ -29,7 +29,10 @@ struct Params {
     double* ws;       // [WS_SLOTS][dof][cn]
     uint32_t* wmeta;  // [WM_WORDS][dof][cn]
     uint8_t* wsrc;    // [dof][cn]
-    uint8_t* wcnt;    // [10][dof][cn] lengths of the Step-1 candidate sub-lists
+    uint8_t* wcnt;    // [10][dof][cn] lengths of the Step-1 candidate sub-lists (ACC0_ACC1, VEL)
+    uint32_t* wqmask; // [6][dof][cn] valid-slot masks (one byte per slot) of the quartic sub-lists
+    uint2* rq_item;   // root queue of the quartic kernels: (item, direction | rank << 1)
+    double* rq_root;  //   ... and the root itself; 8 entries per item at most
     uint32_t* list[2];   // ping-pong work lists of item indices for the Step-2 stages, [dof * cn] each
     uint32_t* counters;  // [17] list lengths per Step-2 stage
     // trajectory storage

@@ -151,8 +151,8 @@ __global__ void __launch_bounds__(128) k1_setup(const Params P) {
 }
 
 // ------------------------------------------------------------------------------------------------ k1_family
-// One thread per (direction slot, DoF, trajectory); F = 0 NONE quartic, 1 ACC0 quartic, 2 ACC1 quartic
-// (position_third_step1.rs:329-601), 3 ACC0_ACC1 (:241-327), 4 the VEL family (:97-240). Every thread validates its
+// One thread per (direction slot, DoF, trajectory); F = 3 ACC0_ACC1 (position_third_step1.rs:241-327), 4 the VEL family
+// (:97-240); the quartic families F = 0..2 run as k1_quartic_roots / k1_quartic_check below. Every thread validates its
 // candidates and writes the valid ones to its own sub-list; the order in which the reference would have met them is
 // restored by k1_block.
 template <int F>
@@ -182,13 +182,110 @@ __global__ void __launch_bounds__(128, RK_MIN_BLOCKS) k1_family(const Params P) 
     if (!(trivial && (F >= 3 || ds == 1))) {
         const bool up = rest_target ? ((ds == 0) == (s.pd >= 0.0)) : (ds == 0);
         const Lim L = lim_dir(up, x.v_max, x.v_min, x.a_max, x.a_min, x.j_max);
-        if (F == 0) s.quartic_none(L);
-        else if (F == 1) s.quartic_acc0(L);
-        else if (F == 2) s.quartic_acc1(L);
-        else if (F == 3) s.family_acc0_acc1(L);
+        if (F == 3) s.family_acc0_acc1(L);
         else s.family_vel(L);
     }
     P.wcnt[(int64_t)sub * wstride + wi] = (uint8_t)s.sink.count;
+}
+
+// ------------------------------------------------------------------------------------------------ k1_quartic_roots / _check
+// The three quartic families in two phases. Phase A (one thread per (direction, DoF, trajectory)) builds the quartic,
+// pre-screens it, solves it in closed form and queues every root inside [t_min, t_max]; phase B (one thread per queued
+// root) does the Newton polish, builds t[7] and validates the profile. A (DoF, direction) has 0-4 in-range roots and most
+// candidates die in the check, so phase B runs the expensive part with full warps instead of the few lanes that happened
+// to have a root in the same loop iteration. Root k of a sub-list writes slot k, which keeps the ascending order.
+__device__ __forceinline__ Lim family_limits(const DofIn& x, const Bound& b, int ds, bool& rest_target, bool& trivial) {
+    const double pd = b.pf - b.p0;
+    rest_target = fabs(b.vf) < EPS && fabs(b.af) < EPS;
+    trivial = rest_target && fabs(b.v0) < EPS && fabs(b.a0) < EPS && fabs(pd) < EPS;
+    const bool up = rest_target ? ((ds == 0) == (pd >= 0.0)) : (ds == 0);
+    return lim_dir(up, x.v_max, x.v_min, x.a_max, x.a_min, x.j_max);
+}
+
+template <int TYPE>
+__global__ void __launch_bounds__(128, RK_MIN_BLOCKS) k1_quartic_roots(const Params P) {
+    const int64_t wstride = (int64_t)P.dof * P.cn;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    double roots[4];
+    int n_roots = 0;
+    int ds = 0;
+    int64_t wi = 0;
+    if (tid < 2 * wstride) {
+        ds = (int)(tid / wstride);
+        wi = tid - (int64_t)ds * wstride;
+        const uint32_t meta = P.wmeta[(int64_t)WM_META * wstride + wi];
+        if (meta & M_S1_PENDING) {
+            const int d = (int)(wi / P.cn);
+            const int64_t ig = P.off + (wi - (int64_t)d * P.cn);
+            const DofIn x = load_dof(P, d, ig);
+            const double* w = P.ws + wi;
+            const Bound b{w[(int64_t)W_P0 * wstride], w[(int64_t)W_V0 * wstride], w[(int64_t)W_A0 * wstride], x.pf, x.vf, x.af};
+            bool rest_target, trivial;
+            const Lim L = family_limits(x, b, ds, rest_target, trivial);
+            P.wqmask[(int64_t)(TYPE * 2 + ds) * wstride + wi] = 0u;
+            if (!(trivial && ds == 1)) {  // :1015-1025 — nothing moves: only the first direction is tried
+                Step1Pos3<QuarticSink> s;
+                s.init(b, x.j_max);
+                s.sink.n_roots = 0;
+                s.first_only = false;
+                if (TYPE == 0) s.template quartic_none<QUARTIC_ROOTS>(L, 0.0);
+                else if (TYPE == 1) s.template quartic_acc0<QUARTIC_ROOTS>(L, 0.0);
+                else s.template quartic_acc1<QUARTIC_ROOTS>(L, 0.0);
+                n_roots = s.sink.n_roots;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) roots[k] = s.sink.roots[k];
+            }
+        }
+    }
+    // warp-aggregated append of a variable number of entries per lane
+    const int lane = threadIdx.x & 31;
+    int incl = n_roots;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int up = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += up;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    if (total == 0) return;
+    uint32_t base = 0;
+    if (lane == 31) base = atomicAdd(P.counters + 20 + TYPE, (uint32_t)total);
+    base = __shfl_sync(0xffffffffu, base, 31) + (uint32_t)(incl - n_roots);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (k < n_roots) {
+            P.rq_item[base + k] = make_uint2((uint32_t)wi, (uint32_t)ds | ((uint32_t)k << 1));
+            P.rq_root[base + k] = roots[k];
+        }
+    }
+}
+
+template <int TYPE>
+__global__ void __launch_bounds__(128, RK_MIN_BLOCKS) k1_quartic_check(const Params P) {
+    const int64_t wstride = (int64_t)P.dof * P.cn;
+    const uint32_t count = P.counters[20 + TYPE];
+    for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < count; e += gridDim.x * blockDim.x) {
+        const uint2 it = P.rq_item[e];
+        const double root = P.rq_root[e];
+        const int64_t wi = it.x;
+        const int ds = it.y & 1, rank = it.y >> 1;
+        const int d = (int)(wi / P.cn);
+        const int64_t ig = P.off + (wi - (int64_t)d * P.cn);
+        const DofIn x = load_dof(P, d, ig);
+        const double* w = P.ws + wi;
+        const Bound b{w[(int64_t)W_P0 * wstride], w[(int64_t)W_V0 * wstride], w[(int64_t)W_A0 * wstride], x.pf, x.vf, x.af};
+        bool rest_target, trivial;
+        const Lim L = family_limits(x, b, ds, rest_target, trivial);
+        const int sub = TYPE * 2 + ds;
+        Step1Pos3<QuarticSink> s;
+        s.init(b, x.j_max);
+        s.first_only = false;
+        s.sink.slot = P.ws + (int64_t)(W_VLIST + (sub_slot_base(sub) + rank) * 7) * wstride + wi;
+        s.sink.wstride = wstride;
+        if (TYPE == 0) s.template quartic_none<QUARTIC_CANDIDATE>(L, root);
+        else if (TYPE == 1) s.template quartic_acc0<QUARTIC_CANDIDATE>(L, root);
+        else s.template quartic_acc1<QUARTIC_CANDIDATE>(L, root);
+        if (s.sink.count > 0) reinterpret_cast<uint8_t*>(P.wqmask + (int64_t)sub * wstride + wi)[rank] = 1;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ k1_block
@@ -208,9 +305,13 @@ __global__ void __launch_bounds__(128) k1_block(const Params P) {
     const bool rest_target = fabs(b.vf) < EPS && fabs(b.af) < EPS;
     const bool trivial = rest_target && fabs(b.v0) < EPS && fabs(b.a0) < EPS && fabs(pd) < EPS;
 
+    // quartic sub-lists (0..5) are sparse: byte k of the mask word says whether slot k holds a validated candidate
+    uint32_t qmask[6];
     int cnt[10];
 #pragma unroll
-    for (int sub = 0; sub < 10; ++sub) cnt[sub] = P.wcnt[(int64_t)sub * wstride + wi];
+    for (int sub = 0; sub < 6; ++sub) { qmask[sub] = P.wqmask[(int64_t)sub * wstride + wi]; cnt[sub] = qmask[sub] ? 1 : 0; }
+#pragma unroll
+    for (int sub = 6; sub < 10; ++sub) cnt[sub] = P.wcnt[(int64_t)sub * wstride + wi];
     Lim Ls[2];
     Ls[0] = lim_dir(rest_target ? (pd >= 0.0) : true, x.v_max, x.v_min, x.a_max, x.a_min, x.j_max);
     Ls[1] = lim_dir(rest_target ? !(pd >= 0.0) : false, x.v_max, x.v_min, x.a_max, x.a_min, x.j_max);
@@ -227,13 +328,23 @@ __global__ void __launch_bounds__(128) k1_block(const Params P) {
             for (int q = 0; q < 5; ++q)
                 if (pick < 0 && cnt[order[q]] > 0) pick = order[q];
         }
-        if (pick >= 0) { sublist_get(P, wi, wstride, pick, 0, Ls[pick & 1], vp[0]); count = 1; }
+        if (pick >= 0) {
+            int k = 0;
+            if (pick < 6) k = (qmask[pick] & 0xFFu) ? 0 : ((qmask[pick] & 0xFF00u) ? 1 : ((qmask[pick] & 0xFF0000u) ? 2 : 3));
+            sublist_get(P, wi, wstride, pick, k, Ls[pick & 1], vp[0]);
+            count = 1;
+        }
     } else {
         // enumeration order of :1091-1140: quartics(UP), quartics(DOWN), ACC0_ACC1(UP), (DOWN), VEL(UP), (DOWN); five are kept (Q11)
         const int order[10] = {0, 2, 4, 1, 3, 5, 6, 7, 8, 9};
         for (int q = 0; q < 10 && count < 5; ++q) {
             const int sub = order[q];
-            for (int k = 0; k < cnt[sub] && count < 5; ++k) sublist_get(P, wi, wstride, sub, k, Ls[sub & 1], vp[count++]);
+            if (sub < 6) {
+                for (int k = 0; k < 4 && count < 5; ++k)
+                    if ((qmask[sub] >> (8 * k)) & 1u) sublist_get(P, wi, wstride, sub, k, Ls[sub & 1], vp[count++]);
+            } else {
+                for (int k = 0; k < cnt[sub] && count < 5; ++k) sublist_get(P, wi, wstride, sub, k, Ls[sub & 1], vp[count++]);
+            }
         }
     }
 

@@ -107,9 +107,12 @@ __device__ __noinline__ bool calculate_block(BlockRec& blk, Cand* vp, int n, dou
 }
 
 // ===================================================== third-order position interface
+enum : int { QUARTIC_ROOTS = 0, QUARTIC_CANDIDATE = 1 };
+
 // Where validated candidates go: a local list (numerical rescues, zero-limit case) ...
 struct LocalSink {
     static constexpr bool inline_check = false;
+    __device__ __forceinline__ void push_root(double) {}
     Cand vp[6];
     int count;
     __device__ __forceinline__ void put(const double (&t)[7], int lim, const Lim& L) {
@@ -125,6 +128,7 @@ struct LocalSink {
 // sub-list the candidate sits in.
 struct GlobalSink {
     static constexpr bool inline_check = true;  // the family kernels have one to four emit sites each
+    __device__ __forceinline__ void push_root(double) {}
     double* base;     // slot 0, t[0] of this sub-list for this item
     int64_t wstride;
     int count;
@@ -132,6 +136,26 @@ struct GlobalSink {
         double* q = base + (int64_t)(count * 7) * wstride;
 #pragma unroll
         for (int k = 0; k < 7; ++k) q[(int64_t)k * wstride] = t[k];
+        ++count;
+    }
+};
+
+// Sink of the two-phase quartic kernels: phase A collects in-range roots, phase B stores the validated candidate of ONE
+// root into the sub-list slot that root owns (slot = rank of the root, so the ascending order survives).
+struct QuarticSink {
+    static constexpr bool inline_check = true;
+    double roots[4];
+    int n_roots;
+    double* slot;
+    int64_t wstride;
+    int count;
+    __device__ __forceinline__ void push_root(double r) {
+        if (n_roots == 0) roots[0] = r; else if (n_roots == 1) roots[1] = r; else if (n_roots == 2) roots[2] = r; else roots[3] = r;
+        ++n_roots;
+    }
+    __device__ __forceinline__ void put(const double (&t)[7], int, const Lim&) {
+#pragma unroll
+        for (int k = 0; k < 7; ++k) slot[(int64_t)k * wstride] = t[k];
         ++count;
     }
 };
@@ -273,7 +297,8 @@ struct Step1Pos3 {
     // position_third_step1.rs:329-601 computes three monic quartics (NONE, ACC0, ACC1) per direction and polishes each
     // root with Newton steps. Here each quartic is its own function (and its own kernel, one thread per direction): the
     // three are independent of one another, and the candidate order NONE, ACC0, ACC1 is restored when the lists are read.
-    __device__ __forceinline__ void quartic_none(const Lim& L) {
+    template <int MODE>
+    __device__ __forceinline__ void quartic_none(const Lim& L, double tt_in) {
         const real v0 = b.v0, a0 = b.a0, vf = b.vf, af = b.af;
         const Den a_max = L.a_max, a_min = L.a_min, j_max = L.j_max;
         const real jl = j_max * j_max;  // the reference mixes this local with the member computed from the UP jerk; equal values
@@ -285,20 +310,18 @@ struct Step1Pos3 {
         const real pn2 = 4.0 * (a0_p3 - af_p3 + 3.0 * j_max * (af * vf - a0 * v0)) / (3.0 * jl * j_max) - 4.0 * pd / j_max;
         const real pn3 = -h2_h2 / (jl);
         double t[7];
-        {
+        if (MODE == QUARTIC_ROOTS) {  // phase A: closed-form roots, keep the ones inside [t_min, t_max] in ascending order
             const Roots roots = solve_quart_monic(0.0, pn1, pn2, pn3);
-            // Lanes skip their out-of-range roots first, so that the warp runs the Newton polish + validation below once
-            // per in-range root of its busiest lane instead of once per root slot.
-            int ri = 0;
-#pragma unroll 1
-            while (true) {
-                real tt = 0.0;
-                bool have = false;
-                while (ri < roots.n) {
-                    tt = roots.get(ri++);
-                    if (!(tt < t_min_none || tt > t_max_none)) { have = true; break; }
-                }
-                if (!have) break;
+#pragma unroll
+            for (int ri = 0; ri < 4; ++ri) {
+                const double r = roots.get(ri);
+                if (ri < roots.n && !(r < t_min_none || r > t_max_none)) sink.push_root(r);
+            }
+            return;
+        }
+        {
+            {  // phase B: one in-range root -> Newton polish -> t[7] -> profile check
+                real tt = tt_in;
                 if (tt > EPS) {  // single Newton step (regarding pd)
                     const real h1 = j_max * tt * tt;
                     const real orig = -h2_h2 / (4.0 * j_max * tt) + h2_none * (af / j_max + tt)
@@ -314,12 +337,13 @@ struct Step1Pos3 {
                 t[2] = tt;
                 t[3] = 0.0; t[4] = 0.0; t[5] = 0.0;
                 t[6] = -h0 + tt / 2.0 + af / j_max;
-                if (emit(t, L_NONE, L) && first_only) return;
+                emit(t, L_NONE, L);
             }
         }
     }
 
-    __device__ __forceinline__ void quartic_acc0(const Lim& L) {
+    template <int MODE>
+    __device__ __forceinline__ void quartic_acc0(const Lim& L, double tt_in) {
         const real v0 = b.v0, a0 = b.a0, vf = b.vf, af = b.af;
         const Den a_max = L.a_max, a_min = L.a_min, j_max = L.j_max;
         const real jl = j_max * j_max;  // the reference mixes this local with the member computed from the UP jerk; equal values
@@ -344,22 +368,20 @@ struct Step1Pos3 {
         const real m2 = pa2 + (2.0 * pa1 + (3.0 * pa0 + 4.0 * t_min_acc0) * t_min_acc0) * t_min_acc0;
         const real m3 = pa3 + (pa2 + (pa1 + (pa0 + t_min_acc0) * t_min_acc0) * t_min_acc0) * t_min_acc0;
         const bool acc0_has_solution = (m0 < 0.0) || (m1 < 0.0) || (m2 < 0.0) || (m3 <= 0.0);
-        if (!acc0_has_solution) return;
+        if (MODE == QUARTIC_ROOTS && !acc0_has_solution) return;
         double t[7];
-        {
+        if (MODE == QUARTIC_ROOTS) {  // phase A: closed-form roots, keep the ones inside [t_min, t_max] in ascending order
             const Roots roots = solve_quart_monic(pa0, pa1, pa2, pa3);
-            // Lanes skip their out-of-range roots first, so that the warp runs the Newton polish + validation below once
-            // per in-range root of its busiest lane instead of once per root slot.
-            int ri = 0;
-#pragma unroll 1
-            while (true) {
-                real tt = 0.0;
-                bool have = false;
-                while (ri < roots.n) {
-                    tt = roots.get(ri++);
-                    if (!(tt < t_min_acc0 || tt > t_max_acc0)) { have = true; break; }
-                }
-                if (!have) break;
+#pragma unroll
+            for (int ri = 0; ri < 4; ++ri) {
+                const double r = roots.get(ri);
+                if (ri < roots.n && !(r < t_min_acc0 || r > t_max_acc0)) sink.push_root(r);
+            }
+            return;
+        }
+        {
+            {  // phase B: one in-range root -> Newton polish -> t[7] -> profile check
+                real tt = tt_in;
                 if (tt > EPS) {  // single Newton step (regarding pd)
                     const real h1 = j_max * tt;
                     const real orig = h0_acc0 / (12.0 * jj * tt) + tt * (h2_acc0 + h1 * (h1 - 2.0 * a_max));
@@ -371,12 +393,13 @@ struct Step1Pos3 {
                 t[2] = tt;
                 t[3] = 0.0; t[4] = 0.0; t[5] = 0.0;
                 t[6] = (af - a_max) / j_max + tt;
-                if (emit(t, L_ACC0, L) && first_only) return;
+                emit(t, L_ACC0, L);
             }
         }
     }
 
-    __device__ __forceinline__ void quartic_acc1(const Lim& L) {
+    template <int MODE>
+    __device__ __forceinline__ void quartic_acc1(const Lim& L, double tt_in) {
         const real v0 = b.v0, a0 = b.a0, vf = b.vf, af = b.af;
         const Den a_max = L.a_max, a_min = L.a_min, j_max = L.j_max;
         const real jl = j_max * j_max;  // the reference mixes this local with the member computed from the UP jerk; equal values
@@ -395,22 +418,20 @@ struct Step1Pos3 {
         const real pb2 = 2.0 * (a0 - a_min) * h2_acc1 / (jl * j_max);
         const real pb3 = h0_acc1 / (jj * jj);
         const bool acc1_has_solution = (pb0 < 0.0) || (pb1 < 0.0) || (pb2 < 0.0) || (pb3 <= 0.0);
-        if (!acc1_has_solution) return;
+        if (MODE == QUARTIC_ROOTS && !acc1_has_solution) return;
         double t[7];
-        {
+        if (MODE == QUARTIC_ROOTS) {  // phase A: closed-form roots, keep the ones inside [t_min, t_max] in ascending order
             const Roots roots = solve_quart_monic(pb0, pb1, pb2, pb3);
-            // Lanes skip their out-of-range roots first, so that the warp runs the Newton polish + validation below once
-            // per in-range root of its busiest lane instead of once per root slot.
-            int ri = 0;
-#pragma unroll 1
-            while (true) {
-                real tt = 0.0;
-                bool have = false;
-                while (ri < roots.n) {
-                    tt = roots.get(ri++);
-                    if (!(tt < t_min_acc1 || tt > t_max_acc1)) { have = true; break; }
-                }
-                if (!have) break;
+#pragma unroll
+            for (int ri = 0; ri < 4; ++ri) {
+                const double r = roots.get(ri);
+                if (ri < roots.n && !(r < t_min_acc1 || r > t_max_acc1)) sink.push_root(r);
+            }
+            return;
+        }
+        {
+            {  // phase B: one in-range root -> Newton polish -> t[7] -> profile check
+                real tt = tt_in;
                 if (tt > EPS) {  // up to three Newton steps (regarding pd)
                     const real h5 = a0_p3 + 2.0 * j_max * a0 * v0;
                     real h1 = j_max * tt;
@@ -447,7 +468,7 @@ struct Step1Pos3 {
                 t[3] = 0.0; t[4] = 0.0;
                 t[5] = h3_acc1 - (2.0 * a0 + j_max * tt) * tt / a_min;
                 t[6] = (af - a_min) / j_max;
-                if (emit(t, L_ACC1, L) && first_only) return;
+                emit(t, L_ACC1, L);
             }
         }
     }
