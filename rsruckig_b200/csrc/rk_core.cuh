@@ -439,7 +439,7 @@ __device__ __forceinline__ int solve_resolvent(double (&x)[3], double a, double 
 }
 
 // roots.rs:278-370: real roots >= 0 of x^4 + a x^3 + b x^2 + c x + d, sorted ascending on return.
-__device__ __noinline__ Roots solve_quart_monic(double a, double b, double c, double d) {
+__device__ RK_QUART_FN Roots solve_quart_monic(double a, double b, double c, double d) {
     Roots roots;
     const double a_squared = a * a;
     const double four_b = 4.0 * b;

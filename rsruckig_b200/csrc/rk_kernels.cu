@@ -507,6 +507,7 @@ rk_status rk_calculate_batch(rk_handle* h, const rk_batch_desc* desc, const rk_b
         // list-driven stages: a few resident waves per SM, grid-stride over the (device-side) list length
         unsigned grid_list = (unsigned)h->sm_count * 16u;
         if (grid_list > grid_items) grid_list = grid_items;
+        const unsigned grid_vel = (grid_list * 128u + RK_LS_BLOCK - 1u) / RK_LS_BLOCK;
         RK_CUDA(cudaMemsetAsync(h->counters, 0, sizeof(uint32_t) * 32, h->stream));
         rk::k1_setup<<<grid_items, 128, 0, h->stream>>>(P);
         const unsigned grid_fam = (unsigned)((2 * items + 127) / 128);
@@ -526,14 +527,14 @@ rk_status rk_calculate_batch(rk_handle* h, const rk_batch_desc* desc, const rk_b
         for (int step = 1; step < RK_S2_STEPS; ++step) {
             switch (fam[step]) {
                 case 0: rk::k2_stage<0><<<grid_list, 128, 0, h->stream>>>(P, step, dir2[step]); break;
-                case 1: rk::k2_stage<1><<<grid_list, 128, 0, h->stream>>>(P, step, dir2[step]); break;
+                case 1: rk::k2_vel<1><<<grid_vel, RK_LS_BLOCK, 0, h->stream>>>(P, step, dir2[step]); break;
                 case 2: rk::k2_stage<2><<<grid_list, 128, 0, h->stream>>>(P, step, dir2[step]); break;
                 case 3: rk::k2_stage<3><<<grid_list, 128, 0, h->stream>>>(P, step, dir2[step]); break;
                 case 4: rk::k2_stage<4><<<grid_list, 128, 0, h->stream>>>(P, step, dir2[step]); break;
                 case 5: rk::k2_stage<5><<<grid_list, 128, 0, h->stream>>>(P, step, dir2[step]); break;
                 case 6: rk::k2_stage<6><<<grid_list, 128, 0, h->stream>>>(P, step, dir2[step]); break;
                 case 7: rk::k2_stage<7><<<grid_list, 128, 0, h->stream>>>(P, step, dir2[step]); break;
-                default: rk::k2_stage<8><<<grid_list, 128, 0, h->stream>>>(P, step, dir2[step]); break;
+                default: rk::k2_vel<8><<<grid_vel, RK_LS_BLOCK, 0, h->stream>>>(P, step, dir2[step]); break;
             }
         }
         rk::k2_fail<<<(unsigned)h->sm_count, 128, 0, h->stream>>>(P);

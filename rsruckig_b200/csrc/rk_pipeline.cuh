@@ -813,6 +813,45 @@ __global__ void __launch_bounds__(128, RK_MIN_BLOCKS) k2_stage(const Params P, i
     }
 }
 
+// ------------------------------------------------------------------------------------------------ k2_vel
+// The two VEL halves in lockstep form (rk_step2_vel.cuh): same list protocol as k2_stage, every thread of the block takes
+// part in every round (inactive threads carry item 0 of the list and do no work between the barriers).
+#ifndef RK_LS_BLOCK
+#define RK_LS_BLOCK 128
+#endif
+#ifndef RK_LS_MINB
+#define RK_LS_MINB (512 / RK_LS_BLOCK)
+#endif
+template <int F>
+__global__ void __launch_bounds__(RK_LS_BLOCK, RK_LS_MINB) k2_vel(const Params P, int step, int second_dir) {
+    const int64_t wstride = (int64_t)P.dof * P.cn;
+    const uint32_t* list_in = P.list[step & 1];
+    uint32_t* list_out = P.list[(step + 1) & 1];
+    const uint32_t count = P.counters[step];
+    const bool second_direction = second_dir != 0;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    const uint32_t rounds = (count + stride - 1) / stride;
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    for (uint32_t r = 0; r < rounds; ++r, k += stride) {
+        const bool active = k < count;
+        const uint32_t wi = active ? list_in[k] : list_in[0];
+        const ItemS2 it = load_item_s2(P, wi, wstride);
+        S2 s;
+        s.init(it.b, it.tf, it.x.j_max);
+        const bool up_first = s.pd > it.tf * it.b.v0;
+        const Lim L = lim_dir(up_first != second_direction, it.x.v_max, it.x.v_min, it.x.a_max, it.x.a_min, it.x.j_max);
+        Hit h;
+        const bool found = (F == 1) ? s2_vel_uddu_lockstep(s, L, h, active) : s2_vel_udud_lockstep(s, L, h, active);
+        RK_PHASE_BARRIER();
+        if (found) {
+            ProfileSink out{P.prof, (int64_t)P.dof * P.n, it.gi};
+            store_profile(out, K_POS3, h.t, h.jf, 0.0, h.cs, h.lim, it.b.p0, it.b.v0, it.b.a0, it.x.vf, it.x.af);
+            P.codes[it.gi] = pack_codes(h.lim, h.cs, h.dir, RK_SRC_STEP2);
+        }
+        append_unsolved(list_out, P.counters + step + 1, active && !found, wi);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ k2_fail
 __global__ void __launch_bounds__(128) k2_fail(const Params P) {
     const int64_t wstride = (int64_t)P.dof * P.cn;

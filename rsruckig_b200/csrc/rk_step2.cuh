@@ -68,7 +68,7 @@ struct Hit {
     }
 
 // position_third_step2.rs:130-245
-__device__ __noinline__ bool s2_acc0_acc1_vel(const S2& s, const Lim& L, Hit& h) {
+__device__ RK_S2_FN bool s2_acc0_acc1_vel(const S2& s, const Lim& L, Hit& h) {
     RK_S2_LOCALS
     // Profile UDDU, Solution 1
     if ((2.0 * (a_max - a_min) + ad) / j_max < tf) {
@@ -112,7 +112,7 @@ __device__ __noinline__ bool s2_acc0_acc1_vel(const S2& s, const Lim& L, Hit& h)
 }
 
 // position_third_step2.rs:247-414
-__device__ __noinline__ bool s2_acc1_vel(const S2& s, const Lim& L, Hit& h) {
+__device__ RK_S2_FN bool s2_acc1_vel(const S2& s, const Lim& L, Hit& h) {
     RK_S2_LOCALS
     // Profile UDDU
     {
@@ -193,7 +193,7 @@ __device__ __noinline__ bool s2_acc1_vel(const S2& s, const Lim& L, Hit& h) {
 }
 
 // position_third_step2.rs:416-605
-__device__ __noinline__ bool s2_acc0_vel(const S2& s, const Lim& L, Hit& h) {
+__device__ RK_S2_FN bool s2_acc0_vel(const S2& s, const Lim& L, Hit& h) {
     RK_S2_LOCALS
     if (tf < rmax((-a0 + a_max) / j_max, 0.0) + rmax(a_max / j_max, 0.0)) return false;
 

@@ -9,7 +9,7 @@ namespace rk {
 __device__ __forceinline__ double sq(double x) { return x * x; }  // roots.rs:14 pow2
 
 // position_third_step2.rs:976-1079
-__device__ __noinline__ bool s2_acc0_acc1(const S2& s, const Lim& L, Hit& h) {
+__device__ RK_S2_FN bool s2_acc0_acc1(const S2& s, const Lim& L, Hit& h) {
     RK_S2_LOCALS
     if (fabs(a0) < EPS && fabs(af) < EPS) {
         const real h1 = 2.0 * a_min * g1 + vd_vd + a_max * (2.0 * pd + a_min * tf_tf - 2.0 * tf * vf);
@@ -52,7 +52,7 @@ __device__ __noinline__ bool s2_acc0_acc1(const S2& s, const Lim& L, Hit& h) {
 }
 
 // position_third_step2.rs:1081-1310
-__device__ __noinline__ bool s2_acc1(const S2& s, const Lim& L, Hit& h) {
+__device__ RK_S2_FN bool s2_acc1(const S2& s, const Lim& L, Hit& h) {
     RK_S2_LOCALS
     // a3 != 0, case UDDU
     {
@@ -139,7 +139,7 @@ __device__ __noinline__ bool s2_acc1(const S2& s, const Lim& L, Hit& h) {
 }
 
 // position_third_step2.rs:1312-1437
-__device__ __noinline__ bool s2_acc0(const S2& s, const Lim& L, Hit& h) {
+__device__ RK_S2_FN bool s2_acc0(const S2& s, const Lim& L, Hit& h) {
     RK_S2_LOCALS
     // UDUD
     {

@@ -7,7 +7,7 @@
 
 namespace rk {
 
-__device__ __noinline__ bool s2_none(const S2& s, const Lim& L, Hit& h) {
+__device__ RK_S2_FN bool s2_none(const S2& s, const Lim& L, Hit& h) {
     RK_S2_LOCALS
     const real vf_vf = s.vf_vf, tf_p3 = s.tf_p3, tf_p4 = s.tf_p4, a0_p5 = s.a0_p5, a0_p6 = s.a0_p6, af_p5 = s.af_p5, af_p6 = s.af_p6;
 

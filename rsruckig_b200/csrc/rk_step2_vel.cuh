@@ -72,7 +72,7 @@ __device__ __forceinline__ bool vel_udud_root(const S2& s, const Lim& L, Hit& h,
 }
 
 // UDDU half of time_vel (:619-824)
-__device__ __noinline__ bool s2_vel_uddu(const S2& s, const Lim& L, Hit& h) {
+__device__ RK_S2_FN bool s2_vel_uddu(const S2& s, const Lim& L, Hit& h) {
     RK_S2_LOCALS
     const real a0_p6 = s.a0_p6, af_p6 = s.af_p6;
     const real tz_min = rmax(0.0, -a0 / j_max);
@@ -174,8 +174,124 @@ __device__ __noinline__ bool s2_vel_uddu(const S2& s, const Lim& L, Hit& h) {
     return false;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Lockstep form of the UDDU half: the same arithmetic, cut into phases separated by block barriers so that all warps of a
+// block walk the instruction stream together. The hot path of this family is ~50 KB of SASS, more than the SM's
+// instruction cache holds, and without the barriers every warp streams it from L2 on its own (the "no instruction" stall
+// was half of all warp time); in lockstep a line fetched for one warp is used by the others while it is still cached.
+// Every thread of the block must call this (inactive ones with active = false).
+#ifndef RK_PHASE_BARRIER
+#define RK_PHASE_BARRIER() __syncthreads()
+#endif
+__device__ __forceinline__ bool s2_vel_uddu_lockstep(const S2& s, const Lim& L, Hit& h, bool active) {
+    RK_S2_LOCALS
+    const real a0_p6 = s.a0_p6, af_p6 = s.af_p6;
+    bool found = false;
+    real tz_min = 0.0, tz_max = 0.0;
+    double pol[6], deriv[5], dderiv[4];
+
+    if (active && fabs(v0) < EPS && fabs(a0) < EPS && fabs(vf) < EPS && fabs(af) < EPS) {  // rare, handled out of step
+        active = false;
+        const Roots roots = solve_cub(1.0, -tf / 2.0, 0.0, pd / (2.0 * j_max));
+#pragma unroll 1
+        for (int ri = 0; ri < roots.n && !found; ++ri) {
+            real tt = roots.get(ri);
+            if (tt > tf / 4.0) continue;
+            if (tt > EPS) {
+                const real orig = -pd + j_max * tt * tt * (tf - 2.0 * tt);
+                const real deriv_ = 2.0 * j_max * tt * (tf - 3.0 * tt);
+                tt -= orig / deriv_;
+            }
+            t[0] = tt; t[1] = 0.0; t[2] = tt; t[3] = tf - 4.0 * tt; t[4] = tt; t[5] = 0.0; t[6] = tt;
+            if (check_pos3(t, UDDU, L_VEL, j_max, L, s.b)) {
+                h.jf = (double)(j_max); h.lim = L_VEL; h.cs = UDDU;
+                h.dir = (L.v_max > 0.0) ? DIR_UP : DIR_DOWN;
+                found = true;
+            }
+        }
+    }
+
+    // phase A: the monic quintic and its derivatives
+    if (active) {
+        tz_min = rmax(0.0, -a0 / j_max);
+        tz_max = rmin((tf - a0 / j_max) / 2.0, (a_max - a0) / j_max);
+        const real p1 = af_af - 2.0 * j_max * (-2.0 * af * tf + j_max * tf_tf + 3.0 * vd);
+        const real ph1 = af_p3 - 3.0 * j_max_j_max * g1 - 3.0 * af * j_max * vd;
+        const real ph2 = af_p4 + 8.0 * af_p3 * j_max * tf
+                           + 12.0 * j_max * (3.0 * j_max * vd_vd - af_af * vd + 2.0 * af * j_max * (g1 - tf * vd) - 2.0 * j_max_j_max * tf * g1);
+        const real ph3 = a0 * (af - j_max * tf);
+        const real ph4 = j_max * (-ad + j_max * tf);
+        pol[0] = 1.0;
+        pol[1] = (15.0 * a0_a0 + af_af + 4.0 * af * j_max * tf - 16.0 * ph3 - 2.0 * j_max * (j_max * tf_tf + 3.0 * vd)) / (4.0 * ph4);
+        pol[2] = (29.0 * a0_p3 - 2.0 * af_p3 - 33.0 * a0 * ph3 + 6.0 * j_max_j_max * g1 + 6.0 * af * j_max * vd + 6.0 * a0 * p1) / (6.0 * j_max * ph4);
+        pol[3] = (61.0 * a0_p4 - 76.0 * a0_a0 * ph3 - 16.0 * a0 * ph1 + 30.0 * a0_a0 * p1 + ph2) / (24.0 * j_max_j_max * ph4);
+        pol[4] = (a0 * (7.0 * a0_p4 - 10.0 * a0_a0 * ph3 - 4.0 * a0 * ph1 + 6.0 * a0_a0 * p1 + ph2)) / (12.0 * j_max_j_max * j_max * ph4);
+        pol[5] = (7.0 * a0_p6 + af_p6 - 12.0 * a0_p4 * ph3 + 48.0 * af_p3 * j_max_j_max * g1 - 8.0 * a0_p3 * ph1
+                  - 72.0 * j_max_j_max * j_max * (j_max * g1 * g1 + vd_vd * vd + 2.0 * af * g1 * vd)
+                  - 6.0 * af_p4 * j_max * vd + 36.0 * af_af * j_max_j_max * vd_vd + 9.0 * a0_p4 * p1 + 3.0 * a0_a0 * ph2)
+                 / (144.0 * j_max_j_max * j_max_j_max * ph4);
+        poly_monic_deri<6>(pol, deriv);
+        poly_deri<5>(deriv, dderiv);
+    }
+    RK_PHASE_BARRIER();
+
+    // phase B: extrema of the quintic in closed form
+    Roots d_extremas;
+    if (active) d_extremas = solve_quart_monic(deriv[1], deriv[2], deriv[3], deriv[4]);
+    RK_PHASE_BARRIER();
+
+    // phase C: record the root candidates (see s2_vel_uddu)
+    double c_lo[6], c_hi[6];
+    int n_cand = 0;
+    if (active) {
+        real tz_current = tz_min;
+        real val_current = poly_eval<6>(pol, tz_current);
+#pragma unroll 1
+        for (int ri = 0; ri <= d_extremas.n; ++ri) {
+            const bool last = ri == d_extremas.n;
+            real tz = last ? tz_max : real(d_extremas.get(ri));
+            if (!last && tz >= tz_max) continue;
+            bool direct = false, bracket = false;
+            real val_new;
+            if (!last) {
+                const real orig = poly_eval<5>(deriv, tz);
+                if (fabs(orig) > ROOT_TOLERANCE) tz -= orig / poly_eval<4>(dderiv, tz);
+                val_new = poly_eval<6>(pol, tz);
+                if (fabs(val_new) < 64.0 * fabs(poly_eval<4>(dderiv, tz)) * ROOT_TOLERANCE) direct = true;
+                else if (val_current * val_new < 0.0) bracket = true;
+            } else {
+                val_new = poly_eval<6>(pol, tz_max);
+                if (val_current * val_new < 0.0) bracket = true;
+                else if (fabs(val_new) < 8.0 * EPS) direct = true;
+            }
+            if (direct || bracket) {
+                c_lo[n_cand] = bracket ? (double)tz_current : (double)tz;
+                c_hi[n_cand] = tz;
+                ++n_cand;
+            }
+            tz_current = tz;
+            val_current = val_new;
+        }
+    }
+
+    // phase D: polish and validate the candidates in order, one candidate index per round of the whole block
+#pragma unroll 1
+    for (int c = 0; c < 6; ++c) {
+        const bool mine = active && !found && c < n_cand;
+        if (!__syncthreads_or(mine)) break;
+        double root = 0.0;
+        if (mine) {
+            const double lo = c_lo[c], hi = c_hi[c];
+            root = (lo != hi) ? shrink_interval<6>(pol, lo, hi) : hi;
+        }
+        RK_PHASE_BARRIER();
+        if (mine) found = vel_uddu_root(s, L, h, root);
+    }
+    return found;
+}
+
 // UDUD half of time_vel (:825-973)
-__device__ __noinline__ bool s2_vel_udud(const S2& s, const Lim& L, Hit& h) {
+__device__ RK_S2_FN bool s2_vel_udud(const S2& s, const Lim& L, Hit& h) {
     RK_S2_LOCALS
     const real a0_p5 = s.a0_p5, a0_p6 = s.a0_p6, af_p6 = s.af_p6;
     const real tz_min = rmax(0.0, -a0 / j_max);
@@ -261,6 +377,114 @@ __device__ __noinline__ bool s2_vel_udud(const S2& s, const Lim& L, Hit& h) {
         if (vel_udud_root(s, L, h, root)) return true;
     }
     return false;
+}
+
+// Lockstep form of the UDUD half (see s2_vel_uddu_lockstep).
+__device__ __forceinline__ bool s2_vel_udud_lockstep(const S2& s, const Lim& L, Hit& h, bool active) {
+    RK_S2_LOCALS
+    const real a0_p5 = s.a0_p5, a0_p6 = s.a0_p6, af_p6 = s.af_p6;
+    bool found = false;
+    real tz_min = 0.0, tz_max = 0.0;
+    double pol[7], deriv[6], dderiv[5], ddderiv[4];
+
+    // phase A: the monic sextic and its derivatives
+    if (active) {
+        tz_min = rmax(0.0, -a0 / j_max);
+        tz_max = rmin((tf - a0 / j_max) / 2.0, (a_max - a0) / j_max);
+        const real ph1 = af_af - 2.0 * j_max * (2.0 * af * tf + j_max * tf_tf - 3.0 * vd);
+        const real ph2 = af_p3 - 3.0 * j_max_j_max * g1 + 3.0 * af * j_max * vd;
+        const real ph3 = 2.0 * j_max * tf * g1 + 3.0 * vd_vd;
+        const real ph4 = af_p4 - 8.0 * af_p3 * j_max * tf + 12.0 * j_max * (j_max * ph3 + af_af * vd + 2.0 * af * j_max * (g1 - tf * vd));
+        const real ph5 = af + j_max * tf;
+        pol[0] = 1.0;
+        pol[1] = (5.0 * a0 - ph5) / j_max;
+        pol[2] = (39.0 * a0_a0 - ph1 - 16.0 * a0 * ph5) / (4.0 * j_max_j_max);
+        pol[3] = (55.0 * a0_p3 - 33.0 * a0_a0 * ph5 - 6.0 * a0 * ph1 + 2.0 * ph2) / (6.0 * j_max_j_max * j_max);
+        pol[4] = (101.0 * a0_p4 + ph4 - 76.0 * a0_p3 * ph5 - 30.0 * a0_a0 * ph1 + 16.0 * a0 * ph2) / (24.0 * j_max_j_max * j_max_j_max);
+        pol[5] = (a0 * (11.0 * a0_p4 + ph4 - 10.0 * a0_p3 * ph5 - 6.0 * a0_a0 * ph1 + 4.0 * a0 * ph2)) / (12.0 * j_max_j_max * j_max_j_max * j_max);
+        pol[6] = (11.0 * a0_p6 - af_p6 - 12.0 * a0_p5 * ph5 - 48.0 * af_p3 * j_max_j_max * g1 - 9.0 * a0_p4 * ph1
+                  + 72.0 * j_max_j_max * j_max * (j_max * g1 * g1 - vd_vd * vd - 2.0 * af * g1 * vd)
+                  - 6.0 * af_p4 * j_max * vd - 36.0 * af_af * j_max_j_max * vd_vd + 8.0 * a0_p3 * ph2 + 3.0 * a0_a0 * ph4)
+                 / (144.0 * j_max_j_max * j_max_j_max * j_max_j_max);
+        poly_monic_deri<7>(pol, deriv);
+        poly_monic_deri<6>(deriv, dderiv);
+        poly_deri<5>(dderiv, ddderiv);
+    }
+    RK_PHASE_BARRIER();
+
+    // phase B: extrema of the first derivative in closed form
+    Roots dd_extremas;
+    if (active) dd_extremas = solve_quart_monic(dderiv[1], dderiv[2], dderiv[3], dderiv[4]);
+    RK_PHASE_BARRIER();
+
+    // phase C: sign changes of the first derivative between its extrema
+    double iv_l[6], iv_r[6];
+    int n_iv = 0;
+    if (active) {
+        real dd_tz_current = tz_min;
+#pragma unroll 1
+        for (int ri = 0; ri < dd_extremas.n; ++ri) {
+            real tz = dd_extremas.get(ri);
+            if (tz >= tz_max) continue;
+            const real orig = poly_eval<5>(dderiv, tz);
+            if (fabs(orig) > ROOT_TOLERANCE) tz -= orig / poly_eval<4>(ddderiv, tz);
+            if (poly_eval<6>(deriv, dd_tz_current) * poly_eval<6>(deriv, tz) < 0.0) {
+                bool dup = false;
+                for (int k = 0; k < n_iv; ++k) dup |= (iv_l[k] == dd_tz_current && iv_r[k] == tz);
+                if (!dup && n_iv < 6) { iv_l[n_iv] = dd_tz_current; iv_r[n_iv] = tz; ++n_iv; }
+            }
+            dd_tz_current = tz;
+        }
+        if (poly_eval<6>(deriv, dd_tz_current) * poly_eval<6>(deriv, tz_max) < 0.0) {
+            bool dup = false;
+            for (int k = 0; k < n_iv; ++k) dup |= (iv_l[k] == dd_tz_current && iv_r[k] == tz_max);
+            if (!dup && n_iv < 6) { iv_l[n_iv] = dd_tz_current; iv_r[n_iv] = tz_max; ++n_iv; }
+        }
+    }
+
+    // phase D: extrema of the sextic by bracketing, candidates recorded; pass k == n_iv is the interval ending at tz_max
+    double c_lo[7], c_hi[7];
+    int n_cand = 0;
+    real tz_current = tz_min;
+    real val_current = 0.0;
+    if (active) val_current = poly_eval<7>(pol, tz_current);
+#pragma unroll 1
+    for (int k = 0; k < 7; ++k) {
+        const bool mine = active && k <= n_iv;
+        if (!__syncthreads_or(mine)) break;
+        if (mine) {
+            const bool last = k == n_iv;
+            const real tz = last ? tz_max : real(shrink_interval<6>(deriv, iv_l[last ? 0 : k], iv_r[last ? 0 : k]));
+            if (last || !(tz >= tz_max)) {
+                const real p_val = poly_eval<7>(pol, tz);
+                bool direct = false, bracket = false;
+                if (!last && fabs(p_val) < 64.0 * fabs(poly_eval<5>(dderiv, tz)) * ROOT_TOLERANCE) direct = true;
+                else if (val_current * p_val < 0.0) bracket = true;
+                if (direct || bracket) {
+                    c_lo[n_cand] = bracket ? (double)tz_current : (double)tz;
+                    c_hi[n_cand] = tz;
+                    ++n_cand;
+                }
+                tz_current = tz;
+                val_current = p_val;
+            }
+        }
+    }
+
+    // phase E: polish and validate the candidates in order
+#pragma unroll 1
+    for (int c = 0; c < 7; ++c) {
+        const bool mine = active && !found && c < n_cand;
+        if (!__syncthreads_or(mine)) break;
+        double root = 0.0;
+        if (mine) {
+            const double lo = c_lo[c], hi = c_hi[c];
+            root = (lo != hi) ? shrink_interval<7>(pol, lo, hi) : hi;
+        }
+        RK_PHASE_BARRIER();
+        if (mine) found = vel_udud_root(s, L, h, root);
+    }
+    return found;
 }
 
 // position_third_step2.rs:607-974
