@@ -520,6 +520,7 @@ rk_status rk_calculate_batch(rk_handle* h, const rk_batch_desc* desc, const rk_b
         rk::k1_family<3><<<grid_fam, 128, 0, h->stream>>>(P);
         rk::k1_family<4><<<grid_fam, 128, 0, h->stream>>>(P);
         rk::k1_block<<<grid_items, 128, 0, h->stream>>>(P);
+        rk::k1_rescue<<<(unsigned)h->sm_count, 128, 0, h->stream>>>(P);
         rk::k_sync<<<(unsigned)((P.cn + 127) / 128), 128, 0, h->stream>>>(P);
         rk::k2_first<<<grid_items, 128, 0, h->stream>>>(P);
         static const int fam[RK_S2_STEPS] = {0, 1, 8, 2, 3, 0, 1, 8, 2, 3, 4, 5, 6, 7, 4, 5, 6, 7};
@@ -538,7 +539,7 @@ rk_status rk_calculate_batch(rk_handle* h, const rk_batch_desc* desc, const rk_b
             }
         }
         rk::k2_fail<<<(unsigned)h->sm_count, 128, 0, h->stream>>>(P);
-        h->launches += 12 + RK_S2_STEPS;
+        h->launches += 13 + RK_S2_STEPS;
         if (host) RK_CUDA(cudaEventRecord(h->ev_computed[chunk_index & 1], h->stream));
     }
     RK_CUDA(cudaGetLastError());

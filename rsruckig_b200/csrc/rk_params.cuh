@@ -122,13 +122,26 @@ __device__ __forceinline__ void ws_put_cand(const Params& P, int64_t wi, int64_t
     P.wmeta[(int64_t)(WM_CAND + slot) * wstride + wi] = pack_codes(c.lim, c.cs, c.dir, 0);
 }
 
-__device__ __forceinline__ void ws_get_cand(const Params& P, int64_t wi, int64_t wstride, int slot, double (&t)[7], double& ctrl, double& ctrl2, uint32_t& codes) {
-    const double* base = P.ws + (int64_t)(W_CAND + slot * W_CAND_STRIDE) * wstride + wi;
-#pragma unroll
-    for (int k = 0; k < 7; ++k) t[k] = base[(int64_t)k * wstride];
-    ctrl = base[7 * wstride];
-    ctrl2 = base[8 * wstride];
+// Read block profile `slot` (0 p_min, 1 a.profile, 2 b.profile). Bits 24..28 of its code word: 0 = the profile was copied
+// into the W_CAND slots, r > 0 = it still sits in Step-1 sub-list slot r - 1 (third-order position interface; the control
+// value is then j_max if bit 23 is set, else -j_max). Bits 29..31 carry the kind of a phase-synchronised profile (k_sync).
+__device__ __forceinline__ void ws_get_cand(const Params& P, int64_t wi, int64_t wstride, int slot, double j_max, double (&t)[7], double& ctrl, double& ctrl2,
+                                            uint32_t& codes) {
     codes = P.wmeta[(int64_t)(WM_CAND + slot) * wstride + wi];
+    const int ref = (int)((codes >> 24) & 0x1Fu);
+    if (ref == 0) {
+        const double* base = P.ws + (int64_t)(W_CAND + slot * W_CAND_STRIDE) * wstride + wi;
+#pragma unroll
+        for (int k = 0; k < 7; ++k) t[k] = base[(int64_t)k * wstride];
+        ctrl = base[7 * wstride];
+        ctrl2 = base[8 * wstride];
+    } else {
+        const double* base = P.ws + (int64_t)(W_VLIST + (ref - 1) * 7) * wstride + wi;
+#pragma unroll
+        for (int k = 0; k < 7; ++k) t[k] = base[(int64_t)k * wstride];
+        ctrl = ((codes >> 23) & 1u) ? j_max : -j_max;
+        ctrl2 = 0.0;
+    }
 }
 
 

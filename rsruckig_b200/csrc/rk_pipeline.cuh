@@ -59,6 +59,18 @@ __device__ __forceinline__ void write_block(const Params& P, int64_t wi, int64_t
     }
 }
 
+// Append the items of this warp that are still unsolved to the next list (one atomic per warp).
+__device__ __forceinline__ void append_unsolved(uint32_t* list, uint32_t* counter, bool unsolved, uint32_t item) {
+    const unsigned mask = __ballot_sync(0xffffffffu, unsolved);
+    if (mask == 0) return;
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(mask) - 1;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(counter, (uint32_t)__popc(mask));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (unsolved) list[base + __popc(mask & ((1u << lane) - 1u))] = item;
+}
+
 // ------------------------------------------------------------------------------------------------ k1_setup
 __global__ void __launch_bounds__(128) k1_setup(const Params P) {
     const int64_t wstride = (int64_t)P.dof * P.cn;
@@ -289,67 +301,230 @@ __global__ void __launch_bounds__(128, RK_MIN_BLOCKS) k1_quartic_check(const Par
 }
 
 // ------------------------------------------------------------------------------------------------ k1_block
-__global__ void __launch_bounds__(128) k1_block(const Params P) {
+// Candidate sub-lists -> block of feasible durations (block.rs:40-154). The candidates are never copied: the kernel works on
+// (duration, sub-list slot) pairs held in registers, and the three profiles a block keeps (p_min, a.profile, b.profile) are
+// recorded as references to their sub-list slots (bits 24..28 of the code word, slot + 1; 0 = the profile sits in the
+// W_CAND slots, which the other Step-1 variants and the rescues still use). Items without any candidate go to k1_rescue.
+struct RefList {
+    double dur[5];
+    int ref[5];  // sub-list slot | sub << 8 | direction << 16 | up << 24
+    int n;
+    __device__ __forceinline__ void push(double d, int r) {
+#pragma unroll
+        for (int q = 0; q < 5; ++q)
+            if (q == n) { dur[q] = d; ref[q] = r; }
+        ++n;
+    }
+    __device__ __forceinline__ double d(int i) const { return i == 0 ? dur[0] : (i == 1 ? dur[1] : (i == 2 ? dur[2] : (i == 3 ? dur[3] : dur[4]))); }
+    __device__ __forceinline__ int r(int i) const { return i == 0 ? ref[0] : (i == 1 ? ref[1] : (i == 2 ? ref[2] : (i == 3 ? ref[3] : ref[4]))); }
+    __device__ __forceinline__ int dir(int i) const { return (r(i) >> 16) & 0xFF; }
+};
+
+struct BlockRefs {
+    double t_min, a_left, a_right, b_left, b_right;
+    int has_a, has_b;
+    int r_min, r_a, r_b;
+};
+
+// block.rs:220-239 on references
+__device__ __forceinline__ void make_interval_ref(const RefList& v, int il, int ir, double bd, double& left, double& right, int& prof) {
+    const double ld = v.d(il) + bd + 0.0;
+    const double rd = v.d(ir) + bd + 0.0;
+    if (ld < rd) { left = ld; right = rd; prof = v.r(ir); }
+    else { left = rd; right = ld; prof = v.r(il); }
+}
+
+// block.rs:40-154 (same decisions as calculate_block in rk_step1.cuh)
+__device__ __forceinline__ bool calculate_block_refs(BlockRefs& blk, RefList& v, double bd) {
+    blk.has_a = 0; blk.has_b = 0;
+    int n = v.n;
+    if (n == 1) {
+        blk.r_min = v.r(0);
+        blk.t_min = v.d(0) + bd + 0.0;
+        return true;
+    } else if (n == 2) {
+        if (fabs(v.d(0) - v.d(1)) < 8.0 * EPS) {
+            blk.r_min = v.r(0);
+            blk.t_min = v.d(0) + bd + 0.0;
+            return true;
+        }
+        const int idx_min = (v.d(0) < v.d(1)) ? 0 : 1;
+        const int idx_else = 1 - idx_min;
+        blk.r_min = v.r(idx_min);
+        blk.t_min = v.d(idx_min) + bd + 0.0;
+        make_interval_ref(v, idx_min, idx_else, bd, blk.a_left, blk.a_right, blk.r_a);
+        blk.has_a = 1;
+        return true;
+    } else if (n == 4) {
+        if (fabs(v.d(0) - v.d(1)) < 32.0 * EPS && v.dir(0) != v.dir(1)) {
+            v.dur[1] = v.dur[2]; v.ref[1] = v.ref[2];
+            v.dur[2] = v.dur[3]; v.ref[2] = v.ref[3];
+        } else if ((fabs(v.d(2) - v.d(3)) < 256.0 * EPS && v.dir(2) != v.dir(3)) || (fabs(v.d(0) - v.d(3)) < 256.0 * EPS && v.dir(0) != v.dir(3))) {
+            // entry 3 is dropped
+        } else {
+            return false;
+        }
+        n = 3;
+    } else if (n % 2 == 0) {
+        return false;
+    }
+
+    int idx_min = 0;
+#pragma unroll
+    for (int i = 1; i < 5; ++i)
+        if (i < n && v.d(i) < v.d(idx_min)) idx_min = i;
+    blk.r_min = v.r(idx_min);
+    blk.t_min = v.d(idx_min) + bd + 0.0;
+
+    if (n == 3) {
+        make_interval_ref(v, (idx_min + 1) % 3, (idx_min + 2) % 3, bd, blk.a_left, blk.a_right, blk.r_a);
+        blk.has_a = 1;
+        return true;
+    } else if (n == 5) {
+        const int e1 = (idx_min + 1) % 5, e2 = (idx_min + 2) % 5, e3 = (idx_min + 3) % 5, e4 = (idx_min + 4) % 5;
+        if (v.dir(e1) == v.dir(e2)) {
+            make_interval_ref(v, e1, e2, bd, blk.a_left, blk.a_right, blk.r_a);
+            make_interval_ref(v, e3, e4, bd, blk.b_left, blk.b_right, blk.r_b);
+        } else {
+            make_interval_ref(v, e1, e4, bd, blk.a_left, blk.a_right, blk.r_a);
+            make_interval_ref(v, e2, e3, bd, blk.b_left, blk.b_right, blk.r_b);
+        }
+        blk.has_a = 1; blk.has_b = 1;
+        return true;
+    }
+    return false;
+}
+
+__device__ __forceinline__ uint32_t ref_codes(int ref) {
+    const int slot = ref & 0xFF, sub = (ref >> 8) & 0xFF, dir = (ref >> 16) & 0xFF, up = (ref >> 24) & 1;
+    return pack_codes(sub_limits(sub), UDDU, dir | (up << 7), slot + 1);
+}
+
+__global__ void __launch_bounds__(128, 4) k1_block(const Params P) {
     const int64_t wstride = (int64_t)P.dof * P.cn;
     const int64_t wi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (wi >= wstride) return;
-    uint32_t meta = P.wmeta[(int64_t)WM_META * wstride + wi];
-    if (!(meta & M_S1_PENDING)) return;
-    const int d = (int)(wi / P.cn);
-    const int64_t ig = P.off + (wi - (int64_t)d * P.cn);
-    const double* w = P.ws + wi;
-    const double bdur = w[(int64_t)W_BRAKE_DUR * wstride];
-    const DofIn x = load_dof(P, d, ig);
-    const Bound b{w[(int64_t)W_P0 * wstride], w[(int64_t)W_V0 * wstride], w[(int64_t)W_A0 * wstride], x.pf, x.vf, x.af};
-    const double pd = b.pf - b.p0;
-    const bool rest_target = fabs(b.vf) < EPS && fabs(b.af) < EPS;
-    const bool trivial = rest_target && fabs(b.v0) < EPS && fabs(b.a0) < EPS && fabs(pd) < EPS;
+    bool rescue = false;
+    if (wi < wstride) {
+        uint32_t meta = P.wmeta[(int64_t)WM_META * wstride + wi];
+        if (meta & M_S1_PENDING) {
+            const int d = (int)(wi / P.cn);
+            const int64_t ig = P.off + (wi - (int64_t)d * P.cn);
+            const double* w = P.ws + wi;
+            const double bdur = w[(int64_t)W_BRAKE_DUR * wstride];
+            const int64_t g = (int64_t)d * P.in_n + ig + P.in_shift;
+            const double pf = P.pf ? P.pf[g] : 0.0, vf = P.vf ? P.vf[g] : 0.0, af = P.af ? P.af[g] : 0.0;
+            const double p0 = w[(int64_t)W_P0 * wstride], v0 = w[(int64_t)W_V0 * wstride], a0 = w[(int64_t)W_A0 * wstride];
+            const double pd = pf - p0;
+            const bool rest_target = fabs(vf) < EPS && fabs(af) < EPS;
+            const bool trivial = rest_target && fabs(v0) < EPS && fabs(a0) < EPS && fabs(pd) < EPS;
+            // direction slot 0 is UP for general items and sign(pd) for rest-target items; the Direction label of a profile
+            // follows the sign of the direction-resolved v_max (profile.rs), the control value follows `up`
+            const double v_max = P.v_max ? P.v_max[g] : 0.0;
+            const double v_min = P.v_min ? P.v_min[g] : -v_max;
+            const bool up0 = rest_target ? (pd >= 0.0) : true;
+            const int tag_slot0 = ((((up0 ? v_max : v_min) > 0.0) ? DIR_UP : DIR_DOWN) << 16) | ((up0 ? 1 : 0) << 24);
+            const int tag_slot1 = ((((up0 ? v_min : v_max) > 0.0) ? DIR_UP : DIR_DOWN) << 16) | ((up0 ? 0 : 1) << 24);
 
-    // quartic sub-lists (0..5) are sparse: byte k of the mask word says whether slot k holds a validated candidate
-    uint32_t qmask[6];
-    int cnt[10];
+            // quartic sub-lists (0..5) are sparse: byte k of the mask word says whether slot k holds a validated candidate
+            uint32_t qmask[6];
+            int cnt[10];
 #pragma unroll
-    for (int sub = 0; sub < 6; ++sub) { qmask[sub] = P.wqmask[(int64_t)sub * wstride + wi]; cnt[sub] = qmask[sub] ? 1 : 0; }
+            for (int sub = 0; sub < 6; ++sub) { qmask[sub] = P.wqmask[(int64_t)sub * wstride + wi]; cnt[sub] = qmask[sub] ? 1 : 0; }
 #pragma unroll
-    for (int sub = 6; sub < 10; ++sub) cnt[sub] = P.wcnt[(int64_t)sub * wstride + wi];
-    Lim Ls[2];
-    Ls[0] = lim_dir(rest_target ? (pd >= 0.0) : true, x.v_max, x.v_min, x.a_max, x.a_min, x.j_max);
-    Ls[1] = lim_dir(rest_target ? !(pd >= 0.0) : false, x.v_max, x.v_min, x.a_max, x.a_min, x.j_max);
+            for (int sub = 6; sub < 10; ++sub) cnt[sub] = P.wcnt[(int64_t)sub * wstride + wi];
 
-    Cand vp[6];
-    int count = 0;
-    if (rest_target) {
-        // first hit in the reference's order (:1026-1089): VEL(d), quartics(d) = NONE, ACC0, ACC1, ACC0_ACC1(d), then the same for -d
-        int pick = -1;
-        for (int ds = 0; ds < 2 && pick < 0; ++ds) {
-            if (trivial && ds == 1) break;
-            const int order[5] = {8 + ds, 0 + ds, 2 + ds, 4 + ds, 6 + ds};
+            RefList v;
+            v.n = 0;
 #pragma unroll
-            for (int q = 0; q < 5; ++q)
-                if (pick < 0 && cnt[order[q]] > 0) pick = order[q];
-        }
-        if (pick >= 0) {
-            int k = 0;
-            if (pick < 6) k = (qmask[pick] & 0xFFu) ? 0 : ((qmask[pick] & 0xFF00u) ? 1 : ((qmask[pick] & 0xFF0000u) ? 2 : 3));
-            sublist_get(P, wi, wstride, pick, k, Ls[pick & 1], vp[0]);
-            count = 1;
-        }
-    } else {
-        // enumeration order of :1091-1140: quartics(UP), quartics(DOWN), ACC0_ACC1(UP), (DOWN), VEL(UP), (DOWN); five are kept (Q11)
-        const int order[10] = {0, 2, 4, 1, 3, 5, 6, 7, 8, 9};
-        for (int q = 0; q < 10 && count < 5; ++q) {
-            const int sub = order[q];
-            if (sub < 6) {
-                for (int k = 0; k < 4 && count < 5; ++k)
-                    if ((qmask[sub] >> (8 * k)) & 1u) sublist_get(P, wi, wstride, sub, k, Ls[sub & 1], vp[count++]);
+            for (int q = 0; q < 5; ++q) { v.dur[q] = 0.0; v.ref[q] = 0; }
+            auto take = [&](int sub, int k) {
+                const int slot = sub_slot_base(sub) + k;
+                const double* base = P.ws + (int64_t)(W_VLIST + slot * 7) * wstride + wi;
+                double t[7];
+#pragma unroll
+                for (int q = 0; q < 7; ++q) t[q] = base[(int64_t)q * wstride];
+                v.push(t_sum6(t), slot | (sub << 8) | ((sub & 1) ? tag_slot1 : tag_slot0));
+            };
+            if (rest_target) {
+                // first hit in the reference's order (:1026-1089): VEL(d), quartics(d) = NONE, ACC0, ACC1, ACC0_ACC1(d), then the same for -d
+                int pick = -1;
+#pragma unroll
+                for (int ds = 0; ds < 2; ++ds) {
+                    if (trivial && ds == 1) break;
+                    const int order[5] = {8 + ds, 0 + ds, 2 + ds, 4 + ds, 6 + ds};
+#pragma unroll
+                    for (int q = 0; q < 5; ++q)
+                        if (pick < 0 && cnt[order[q]] > 0) pick = order[q];
+                }
+                if (pick >= 0) {
+                    int k = 0;
+                    if (pick < 6) {
+                        uint32_t m = 0;
+#pragma unroll
+                        for (int sub = 0; sub < 6; ++sub)
+                            if (sub == pick) m = qmask[sub];
+                        k = (m & 0xFFu) ? 0 : ((m & 0xFF00u) ? 1 : ((m & 0xFF0000u) ? 2 : 3));
+                    }
+                    take(pick, k);
+                }
             } else {
-                for (int k = 0; k < cnt[sub] && count < 5; ++k) sublist_get(P, wi, wstride, sub, k, Ls[sub & 1], vp[count++]);
+                // enumeration order of :1091-1140: quartics(UP), quartics(DOWN), ACC0_ACC1(UP), (DOWN), VEL(UP), (DOWN); five are kept (Q11)
+                const int order[10] = {0, 2, 4, 1, 3, 5, 6, 7, 8, 9};
+#pragma unroll
+                for (int q = 0; q < 10; ++q) {
+                    const int sub = order[q];
+                    if (sub < 6) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            if (v.n < 5 && ((qmask[sub] >> (8 * k)) & 1u)) take(sub, k);
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 2; ++k)
+                            if (v.n < 5 && k < cnt[sub]) take(sub, k);
+                    }
+                }
+            }
+
+            if (v.n == 0) {
+                rescue = true;  // :1142-1255, handled by k1_rescue
+            } else {
+                BlockRefs blk;
+                blk.a_left = 0.0; blk.a_right = 0.0; blk.b_left = 0.0; blk.b_right = 0.0; blk.t_min = 0.0;
+                blk.r_min = 0; blk.r_a = 0; blk.r_b = 0;
+                const bool found = calculate_block_refs(blk, v, bdur);
+                meta &= ~M_S1_PENDING;
+                double* wo = P.ws + wi;
+                wo[(int64_t)W_TMIN * wstride] = found ? blk.t_min : 0.0;
+                wo[(int64_t)W_ALEFT * wstride] = blk.a_left; wo[(int64_t)W_ARIGHT * wstride] = blk.a_right;
+                wo[(int64_t)W_BLEFT * wstride] = blk.b_left; wo[(int64_t)W_BRIGHT * wstride] = blk.b_right;
+                if (found) {
+                    meta |= M_FOUND;
+                    P.wmeta[(int64_t)(WM_CAND + 0) * wstride + wi] = ref_codes(blk.r_min);
+                    if (blk.has_a) { meta |= M_HAS_A; P.wmeta[(int64_t)(WM_CAND + 1) * wstride + wi] = ref_codes(blk.r_a); }
+                    if (blk.has_b) { meta |= M_HAS_B; P.wmeta[(int64_t)(WM_CAND + 2) * wstride + wi] = ref_codes(blk.r_b); }
+                }
+                P.wmeta[(int64_t)WM_META * wstride + wi] = meta;
+                P.imd[(int64_t)d * P.n + ig] = found ? blk.t_min : 0.0;
             }
         }
     }
+    append_unsolved(P.list[0], P.counters + 24, rescue, (uint32_t)wi);
+}
 
-    if (count == 0) {
-        // :1142-1255 — numerical rescues; the first one that yields a candidate wins
+// Numerical rescues (:1142-1255) for the rare items none of the regular families produced a candidate for; the first rescue
+// that yields one wins.
+__global__ void __launch_bounds__(128) k1_rescue(const Params P) {
+    const int64_t wstride = (int64_t)P.dof * P.cn;
+    const uint32_t n_items = P.counters[24];
+    for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < n_items; e += gridDim.x * blockDim.x) {
+        const int64_t wi = P.list[0][e];
+        uint32_t meta = P.wmeta[(int64_t)WM_META * wstride + wi];
+        const int d = (int)(wi / P.cn);
+        const int64_t ig = P.off + (wi - (int64_t)d * P.cn);
+        const double* w = P.ws + wi;
+        const double bdur = w[(int64_t)W_BRAKE_DUR * wstride];
+        const DofIn x = load_dof(P, d, ig);
+        const Bound b{w[(int64_t)W_P0 * wstride], w[(int64_t)W_V0 * wstride], w[(int64_t)W_A0 * wstride], x.pf, x.vf, x.af};
         Step1Pos3<LocalSink> s;
         s.init(b, x.j_max);
         s.first_only = false;
@@ -361,17 +536,14 @@ __global__ void __launch_bounds__(128) k1_block(const Params P) {
             else if (k < 6) s.rescue_vel(L);
             else s.rescue_acc1_vel(L);
         }
-        count = s.sink.count;
-        for (int c = 0; c < count; ++c) vp[c] = s.sink.vp[c];
+        BlockRec blk;
+        blk.a_left = 0.0; blk.a_right = 0.0; blk.b_left = 0.0; blk.b_right = 0.0; blk.t_min = 0.0;
+        const bool found = calculate_block(blk, s.sink.vp, s.sink.count, bdur);
+        meta &= ~M_S1_PENDING;
+        write_block(P, wi, wstride, blk, found, meta);
+        P.wmeta[(int64_t)WM_META * wstride + wi] = meta;
+        P.imd[(int64_t)d * P.n + ig] = found ? blk.t_min : 0.0;
     }
-
-    BlockRec blk;
-    blk.a_left = 0.0; blk.a_right = 0.0; blk.b_left = 0.0; blk.b_right = 0.0; blk.t_min = 0.0;
-    const bool found = calculate_block(blk, vp, count, bdur);
-    meta &= ~M_S1_PENDING;
-    write_block(P, wi, wstride, blk, found, meta);
-    P.wmeta[(int64_t)WM_META * wstride + wi] = meta;
-    P.imd[(int64_t)d * P.n + ig] = found ? blk.t_min : 0.0;
 }
 
 // ------------------------------------------------------------------------------------------------ k_sync
@@ -524,8 +696,8 @@ __global__ void __launch_bounds__(128) k_sync(const Params P) {
                 if (!done && limiting >= 0 && any_phase) {
                     double lt[7], lctrl, lctrl2;
                     uint32_t lcodes;
-                    ws_get_cand(P, (int64_t)limiting * P.cn + il, wstride, SRC(limiting), lt, lctrl, lctrl2, lcodes);
-                    const int l_lim = lcodes & 0xFF, l_cs = (lcodes >> 8) & 0xFF, l_dir = (lcodes >> 16) & 0xFF;
+                    ws_get_cand(P, (int64_t)limiting * P.cn + il, wstride, SRC(limiting), load_dof(P, limiting, ig).j_max, lt, lctrl, lctrl2, lcodes);
+                    const int l_lim = lcodes & 0xFF, l_cs = (lcodes >> 8) & 0xFF, l_dir = (lcodes >> 16) & 0x7F;
 
                     // scale vector selection
                     int scale_dof = -1, scale_vec = -1;  // 0 pd, 1 v0, 2 a0, 3 vf, 4 af
@@ -611,7 +783,7 @@ __global__ void __launch_bounds__(128) k_sync(const Params P) {
                                     c.ctrl = npc; c.ctrl2 = -npc; c.lim = l_lim; c.cs = l_cs; c.dir = dir; c.dur = 0.0;
                                     const int64_t wd = (int64_t)d * P.cn + il;
                                     ws_put_cand(P, wd, wstride, 2, c);
-                                    P.wmeta[(int64_t)3 * wstride + wd] |= (uint32_t)(kind + 1) << 24;  // kind the profile is expanded with
+                                    P.wmeta[(int64_t)3 * wstride + wd] |= (uint32_t)(kind + 1) << 29;  // kind the profile is expanded with
                                     SRC(d) = RK_SRC_PHASE;
                                 }
                             }
@@ -708,18 +880,6 @@ __device__ __forceinline__ bool run_stage(const Params& P, const ItemS2& it, boo
     return true;
 }
 
-// Append the items of this warp that are still unsolved to the next list (one atomic per warp).
-__device__ __forceinline__ void append_unsolved(uint32_t* list, uint32_t* counter, bool unsolved, uint32_t item) {
-    const unsigned mask = __ballot_sync(0xffffffffu, unsolved);
-    if (mask == 0) return;
-    const int lane = threadIdx.x & 31;
-    const int leader = __ffs(mask) - 1;
-    uint32_t base = 0;
-    if (lane == leader) base = atomicAdd(counter, (uint32_t)__popc(mask));
-    base = __shfl_sync(0xffffffffu, base, leader);
-    if (unsolved) list[base + __popc(mask & ((1u << lane) - 1u))] = item;
-}
-
 __device__ __forceinline__ void report_step2_failure(const Params& P, int d, int64_t ig) {
     P.status[ig] = RK_RESULT_ERROR_EXECUTION_TIME_CALCULATION;  // :819-826; every failing DoF stores the same value
     const int mine = (3 << 8) | d;                              // the lowest failing DoF index is kept in the detail word
@@ -766,12 +926,12 @@ __global__ void __launch_bounds__(128) k2_first(const Params P) {
             } else {
                 const int slot = (src == RK_SRC_PHASE) ? 2 : src;
                 uint32_t c;
-                ws_get_cand(P, wi, wstride, slot, t, ctrl, ctrl2, c);
-                lim = c & 0xFF; cs = (c >> 8) & 0xFF; dir = (c >> 16) & 0xFF;
+                ws_get_cand(P, wi, wstride, slot, it.x.j_max, t, ctrl, ctrl2, c);
+                lim = c & 0xFF; cs = (c >> 8) & 0xFF; dir = (c >> 16) & 0x7F;
                 lim_check = lim;
                 if (src == RK_SRC_PHASE) {  // validated with ReachedLimits::None, labelled with the limiting DoF's limits (Q25)
                     lim_check = L_NONE;
-                    store_kind = (int)(c >> 24) - 1;
+                    store_kind = (int)(c >> 29) - 1;
                 }
             }
             if (ok) {
