@@ -522,10 +522,9 @@ rk_status rk_calculate_batch(rk_handle* h, const rk_batch_desc* desc, const rk_b
         rk::k1_block<<<grid_items, 128, 0, h->stream>>>(P);
         rk::k1_rescue<<<(unsigned)h->sm_count, 128, 0, h->stream>>>(P);
         rk::k_sync<<<(unsigned)((P.cn + 127) / 128), 128, 0, h->stream>>>(P);
-        rk::k2_first<<<grid_items, 128, 0, h->stream>>>(P);
         static const int fam[RK_S2_STEPS] = {0, 1, 8, 2, 3, 0, 1, 8, 2, 3, 4, 5, 6, 7, 4, 5, 6, 7};
         static const int dir2[RK_S2_STEPS] = {0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 0, 0, 0, 0, 1, 1, 1, 1};
-        for (int step = 1; step < RK_S2_STEPS; ++step) {
+        for (int step = 0; step < RK_S2_STEPS; ++step) {
             switch (fam[step]) {
                 case 0: rk::k2_stage<0><<<grid_list, 128, 0, h->stream>>>(P, step, dir2[step]); break;
                 case 1: rk::k2_vel<1><<<grid_vel, RK_LS_BLOCK, 0, h->stream>>>(P, step, dir2[step]); break;
@@ -539,7 +538,8 @@ rk_status rk_calculate_batch(rk_handle* h, const rk_batch_desc* desc, const rk_b
             }
         }
         rk::k2_fail<<<(unsigned)h->sm_count, 128, 0, h->stream>>>(P);
-        h->launches += 13 + RK_S2_STEPS;
+        rk::k_expand<<<grid_items, 128, 0, h->stream>>>(P);
+        h->launches += 14 + RK_S2_STEPS;
         if (host) RK_CUDA(cudaEventRecord(h->ev_computed[chunk_index & 1], h->stream));
     }
     RK_CUDA(cudaGetLastError());

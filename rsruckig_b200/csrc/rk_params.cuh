@@ -34,7 +34,7 @@ struct Params {
     uint2* rq_item;   // root queue of the quartic kernels: (item, direction | rank << 1)
     double* rq_root;  //   ... and the root itself; 8 entries per item at most
     uint32_t* list[2];   // ping-pong work lists of item indices for the Step-2 stages, [dof * cn] each
-    uint32_t* counters;  // [17] list lengths per Step-2 stage
+    uint32_t* counters;  // [0..18] list lengths per Step-2 stage, [20..22] quartic root queues, [24] rescue list
     // trajectory storage
     double* prof;     // [PROFILE_SLOTS][dof][n]
     uint32_t* codes;  // [dof][n]

@@ -555,18 +555,26 @@ __device__ __forceinline__ bool is_blocked(double t, double t_min, bool has_a, d
     return false;
 }
 
-__global__ void __launch_bounds__(128) k_sync(const Params P) {
-    const int64_t il = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (il >= P.cn) return;
+__device__ __forceinline__ void sync_trajectory(const Params& P, int64_t il, uint32_t* pm, uint8_t* psrc) {
     const int64_t ig = P.off + il;
     const int D = P.dof;
     const int64_t wstride = (int64_t)D * P.cn;
     const double* W = P.ws;
-#define WS(slot, d) W[(int64_t)(slot) * wstride + (int64_t)(d) * P.cn + il]
-#define META(d) P.wmeta[(int64_t)(d) * P.cn + il]
-#define SRC(d) P.wsrc[(int64_t)(d) * P.cn + il]
-
-    for (int d = 0; d < D; ++d) SRC(d) = RK_SRC_NONE;
+#define WSG(slot, d) W[(int64_t)(slot) * wstride + (int64_t)(d) * P.cn + il]
+    // Everything the decisions below look at, fetched up front with independent loads (the kernel is one thread per
+    // trajectory and would otherwise walk a chain of dependent global loads); local arrays, L1-resident.
+    double pw[6][RK_MAX_DOF];  // W_TMIN, W_ALEFT, W_ARIGHT, W_BLEFT, W_BRIGHT, W_BRAKE_DUR
+#pragma unroll 4
+    for (int d = 0; d < D; ++d) {
+        pm[d] = P.wmeta[(int64_t)d * P.cn + il];
+        pw[0][d] = WSG(W_TMIN, d); pw[1][d] = WSG(W_ALEFT, d); pw[2][d] = WSG(W_ARIGHT, d);
+        pw[3][d] = WSG(W_BLEFT, d); pw[4][d] = WSG(W_BRIGHT, d); pw[5][d] = WSG(W_BRAKE_DUR, d);
+        psrc[d] = RK_SRC_NONE;
+    }
+#define WS(slot, d) ((slot) == W_TMIN ? pw[0][d] : (slot) == W_ALEFT ? pw[1][d] : (slot) == W_ARIGHT ? pw[2][d] : (slot) == W_BLEFT ? pw[3][d] : \
+                     (slot) == W_BRIGHT ? pw[4][d] : (slot) == W_BRAKE_DUR ? pw[5][d] : WSG(slot, d))
+#define META(d) pm[d]
+#define SRC(d) psrc[d]
     int status = RK_RESULT_WORKING;
     int detail = 0;
     double duration = 0.0;
@@ -821,8 +829,25 @@ __global__ void __launch_bounds__(128) k_sync(const Params P) {
     P.limiting[ig] = limiting;
     P.detail[ig] = detail;
 #undef WS
+#undef WSG
 #undef META
 #undef SRC
+}
+
+// One thread per trajectory. After the decision every (DoF, trajectory) item is queued for the kernel that finishes it:
+// third-order position items that need the Step-2 chain go to list[0] (stage 0 reads it); k_expand finishes all items.
+__global__ void __launch_bounds__(128) k_sync(const Params P) {
+    const int64_t il = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = il < P.cn;
+    uint32_t pm[RK_MAX_DOF];
+    uint8_t psrc[RK_MAX_DOF];
+    if (valid) sync_trajectory(P, il, pm, psrc);
+    for (int d = 0; d < P.dof; ++d) {
+        const uint32_t wi = (uint32_t)((int64_t)d * P.cn + il);
+        const bool chain = valid && psrc[d] == RK_SRC_STEP2 && (pm[d] & M_KIND_MASK) == K_POS3;
+        if (valid) P.wsrc[wi] = psrc[d];
+        append_unsolved(P.list[0], P.counters + 0, chain, wi);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ Step-2 chain
@@ -836,11 +861,12 @@ struct ItemS2 {
     Bound b;
     double tf;
     int d;
-    int64_t ig, gi;
+    int64_t ig, gi, wi;
 };
 
 __device__ __forceinline__ ItemS2 load_item_s2(const Params& P, int64_t wi, int64_t wstride) {
     ItemS2 it;
+    it.wi = wi;
     it.d = (int)(wi / P.cn);
     it.ig = P.off + (wi - (int64_t)it.d * P.cn);
     it.gi = (int64_t)it.d * P.n + it.ig;
@@ -866,6 +892,17 @@ __device__ __forceinline__ bool run_family(const S2& s, const Lim& L, Hit& h) {
     return s2_none(s, L, h);
 }
 
+// A solved Step-2 item leaves only its compact solution behind — t[7] and the jerk in block-profile slot 0 of the scratch
+// (unused by third-order position items, whose block profiles are references) and the code word; k_expand integrates it into
+// the full profile arrays later, with full warps and coalesced stores.
+__device__ __forceinline__ void put_solution(const Params& P, const ItemS2& it, int64_t wstride, const Hit& h) {
+    double* base = P.ws + (int64_t)W_CAND * wstride + it.wi;
+#pragma unroll
+    for (int k = 0; k < 7; ++k) base[(int64_t)k * wstride] = h.t[k];
+    base[7 * wstride] = h.jf;
+    P.codes[it.gi] = pack_codes(h.lim, h.cs, h.dir, RK_SRC_STEP2);
+}
+
 template <int F>
 __device__ __forceinline__ bool run_stage(const Params& P, const ItemS2& it, bool second_direction) {
     S2 s;
@@ -874,9 +911,7 @@ __device__ __forceinline__ bool run_stage(const Params& P, const ItemS2& it, boo
     const Lim L = lim_dir(up_first != second_direction, it.x.v_max, it.x.v_min, it.x.a_max, it.x.a_min, it.x.j_max);
     Hit h;
     if (!run_family<F>(s, L, h)) return false;
-    ProfileSink out{P.prof, (int64_t)P.dof * P.n, it.gi};
-    store_profile(out, K_POS3, h.t, h.jf, 0.0, h.cs, h.lim, it.b.p0, it.b.v0, it.b.a0, it.x.vf, it.x.af);
-    P.codes[it.gi] = pack_codes(h.lim, h.cs, h.dir, RK_SRC_STEP2);
+    put_solution(P, it, (int64_t)P.dof * P.cn, h);
     return true;
 }
 
@@ -891,65 +926,8 @@ __device__ __forceinline__ void report_step2_failure(const Params& P, int d, int
     }
 }
 
-// ------------------------------------------------------------------------------------------------ k2_first
-// Every item: profiles that need no chain are expanded and stored (re-used extremal profile, phase-synchronised profile,
-// disabled DoF, the cheap non-third-order Step 2 variants); third-order position items that need Step 2 run stage 0.
-__global__ void __launch_bounds__(128) k2_first(const Params P) {
-    const int64_t wstride = (int64_t)P.dof * P.cn;
-    const int64_t wi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    bool unsolved = false;
-    if (wi < wstride) {
-        const uint32_t meta = P.wmeta[(int64_t)WM_META * wstride + wi];
-        const int kind = meta & M_KIND_MASK;
-        const int src = P.wsrc[wi];
-        const ItemS2 it = load_item_s2(P, wi, wstride);
-        ProfileSink out{P.prof, (int64_t)P.dof * P.n, it.gi};
-        if (src == RK_SRC_NONE || kind == K_NONE) {
-            // disabled DoF (calculator_target.rs:313-323) or a trajectory that ended with an error status
-            store_idle_profile(out, it.x.p0, it.x.v0, it.x.a0);
-            P.codes[it.gi] = pack_codes(L_NONE, UDDU, DIR_UP, RK_SRC_NONE);
-        } else if (src == RK_SRC_STEP2 && kind == K_POS3) {
-            unsolved = !run_stage<0>(P, it, false);
-        } else {
-            double t[7], ctrl, ctrl2;
-            int lim, cs, dir, lim_check, store_kind = kind;
-            bool pf_from_p7 = false, ok = true;
-            if (src == RK_SRC_STEP2) {
-                Cand c;
-                if (kind == K_POS2) { ok = step2_pos2(it.b, it.tf, it.x.v_max, it.x.v_min, it.x.a_max, it.x.a_min, c); pf_from_p7 = true; }
-                else if (kind == K_POS1) ok = step2_pos1(it.b, it.tf, c);
-                else if (kind == K_VEL3) { ok = step2_vel3(it.b, it.tf, it.x.a_max, it.x.a_min, it.x.j_max, c); pf_from_p7 = true; }
-                else { ok = step2_vel2(it.b, it.tf, it.x.a_max, it.x.a_min, c); pf_from_p7 = true; }
-                copy_t(t, c.t);
-                ctrl = c.ctrl; ctrl2 = c.ctrl2; lim = c.lim; cs = c.cs; dir = c.dir;
-                lim_check = lim;
-            } else {
-                const int slot = (src == RK_SRC_PHASE) ? 2 : src;
-                uint32_t c;
-                ws_get_cand(P, wi, wstride, slot, it.x.j_max, t, ctrl, ctrl2, c);
-                lim = c & 0xFF; cs = (c >> 8) & 0xFF; dir = (c >> 16) & 0x7F;
-                lim_check = lim;
-                if (src == RK_SRC_PHASE) {  // validated with ReachedLimits::None, labelled with the limiting DoF's limits (Q25)
-                    lim_check = L_NONE;
-                    store_kind = (int)(c >> 29) - 1;
-                }
-            }
-            if (ok) {
-                const double p7 = store_profile(out, store_kind, t, ctrl, ctrl2, cs, lim_check, it.b.p0, it.b.v0, it.b.a0, it.x.vf, it.x.af);
-                if (pf_from_p7) out.put(S_PF, p7);
-                P.codes[it.gi] = pack_codes(lim, cs, dir, src);
-            } else {
-                report_step2_failure(P, it.d, it.ig);
-                store_idle_profile(out, 0.0, 0.0, 0.0);
-                P.codes[it.gi] = pack_codes(L_NONE, UDDU, DIR_UP, RK_SRC_STEP2);
-            }
-        }
-    }
-    append_unsolved(P.list[1], P.counters + 1, unsolved, (uint32_t)wi);
-}
-
 // ------------------------------------------------------------------------------------------------ k2_stage
-// `step` numbers the launches of the chain (0 = the stage run inside k2_first); list `step & 1` is read, the other written.
+// `step` numbers the launches of the chain (list 0 of step 0 is filled by k_sync); list `step & 1` is read, the other written.
 template <int F>
 __global__ void __launch_bounds__(128, RK_MIN_BLOCKS) k2_stage(const Params P, int step, int second_dir) {
     const int64_t wstride = (int64_t)P.dof * P.cn;
@@ -1003,11 +981,7 @@ __global__ void __launch_bounds__(RK_LS_BLOCK, RK_LS_MINB) k2_vel(const Params P
         Hit h;
         const bool found = (F == 1) ? s2_vel_uddu_lockstep(s, L, h, active) : s2_vel_udud_lockstep(s, L, h, active);
         RK_PHASE_BARRIER();
-        if (found) {
-            ProfileSink out{P.prof, (int64_t)P.dof * P.n, it.gi};
-            store_profile(out, K_POS3, h.t, h.jf, 0.0, h.cs, h.lim, it.b.p0, it.b.v0, it.b.a0, it.x.vf, it.x.af);
-            P.codes[it.gi] = pack_codes(h.lim, h.cs, h.dir, RK_SRC_STEP2);
-        }
+        if (found) put_solution(P, it, wstride, h);
         append_unsolved(list_out, P.counters + step + 1, active && !found, wi);
     }
 }
@@ -1021,11 +995,81 @@ __global__ void __launch_bounds__(128) k2_fail(const Params P) {
         const int d = (int)(wi / P.cn);
         const int64_t ig = P.off + (wi - (int64_t)d * P.cn);
         report_step2_failure(P, d, ig);
-        ProfileSink out{P.prof, (int64_t)P.dof * P.n, (int64_t)d * P.n + ig};
-        store_idle_profile(out, 0.0, 0.0, 0.0);
+        P.wsrc[wi] = 0xFF;  // RK_SRC_FAILED: k_expand stores an idle profile
         P.codes[(int64_t)d * P.n + ig] = pack_codes(L_NONE, UDDU, DIR_UP, RK_SRC_STEP2);
     }
     (void)wstride;
 }
+
+// ------------------------------------------------------------------------------------------------ k_expand
+// Last kernel, one thread per item: the compact result of every item — a Step-2 solution, a re-used extremal profile, a
+// phase-synchronised profile, nothing at all (disabled DoF, error status, failed chain) — is integrated into the profile
+// arrays the reference's check functions leave behind (profile.rs:76-118) and stored. Dense and coalesced: a warp writes 59
+// full 256-byte rows. The cheap non-third-order Step 2 variants are solved right here.
+#define RK_SRC_FAILED 0xFF
+__global__ void __launch_bounds__(128) k_expand(const Params P) {
+    const int64_t wstride = (int64_t)P.dof * P.cn;
+    {
+        const int64_t wi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        if (wi >= wstride) return;
+        const uint32_t meta = P.wmeta[(int64_t)WM_META * wstride + wi];
+        const int kind = meta & M_KIND_MASK;
+        const int src = P.wsrc[wi];
+        const ItemS2 it = load_item_s2(P, wi, wstride);
+        ProfileSink out{P.prof, (int64_t)P.dof * P.n, it.gi};
+        if (src == RK_SRC_NONE || kind == K_NONE) {
+            // disabled DoF (calculator_target.rs:313-323) or a trajectory that ended with an error status
+            store_idle_profile(out, it.x.p0, it.x.v0, it.x.a0);
+            P.codes[it.gi] = pack_codes(L_NONE, UDDU, DIR_UP, RK_SRC_NONE);
+            return;
+        }
+        if (src == RK_SRC_FAILED) {  // k2_fail has set the status and the code word
+            store_idle_profile(out, 0.0, 0.0, 0.0);
+            return;
+        }
+        double t[7], ctrl, ctrl2;
+        int lim, cs, dir, lim_check, store_kind = kind;
+        bool pf_from_p7 = false, ok = true;
+        if (src == RK_SRC_STEP2 && kind == K_POS3) {  // solved by a stage of the chain (put_solution)
+            const double* base = P.ws + (int64_t)W_CAND * wstride + wi;
+#pragma unroll
+            for (int k = 0; k < 7; ++k) t[k] = base[(int64_t)k * wstride];
+            ctrl = base[7 * wstride];
+            ctrl2 = 0.0;
+            const uint32_t c = P.codes[it.gi];
+            lim = c & 0xFF; cs = (c >> 8) & 0xFF; dir = (c >> 16) & 0xFF;
+            lim_check = lim;
+        } else if (src == RK_SRC_STEP2) {
+            Cand c;
+            if (kind == K_POS2) { ok = step2_pos2(it.b, it.tf, it.x.v_max, it.x.v_min, it.x.a_max, it.x.a_min, c); pf_from_p7 = true; }
+            else if (kind == K_POS1) ok = step2_pos1(it.b, it.tf, c);
+            else if (kind == K_VEL3) { ok = step2_vel3(it.b, it.tf, it.x.a_max, it.x.a_min, it.x.j_max, c); pf_from_p7 = true; }
+            else { ok = step2_vel2(it.b, it.tf, it.x.a_max, it.x.a_min, c); pf_from_p7 = true; }
+            copy_t(t, c.t);
+            ctrl = c.ctrl; ctrl2 = c.ctrl2; lim = c.lim; cs = c.cs; dir = c.dir;
+            lim_check = lim;
+        } else {
+            const int slot = (src == RK_SRC_PHASE) ? 2 : src;
+            uint32_t c;
+            ws_get_cand(P, wi, wstride, slot, it.x.j_max, t, ctrl, ctrl2, c);
+            lim = c & 0xFF; cs = (c >> 8) & 0xFF; dir = (c >> 16) & 0x7F;
+            lim_check = lim;
+            if (src == RK_SRC_PHASE) {  // validated with ReachedLimits::None, labelled with the limiting DoF's limits (Q25)
+                lim_check = L_NONE;
+                store_kind = (int)(c >> 29) - 1;
+            }
+        }
+        if (ok) {
+            const double p7 = store_profile(out, store_kind, t, ctrl, ctrl2, cs, lim_check, it.b.p0, it.b.v0, it.b.a0, it.x.vf, it.x.af);
+            if (pf_from_p7) out.put(S_PF, p7);
+            P.codes[it.gi] = pack_codes(lim, cs, dir, src);
+        } else {
+            report_step2_failure(P, it.d, it.ig);
+            store_idle_profile(out, 0.0, 0.0, 0.0);
+            P.codes[it.gi] = pack_codes(L_NONE, UDDU, DIR_UP, RK_SRC_STEP2);
+        }
+    }
+}
+
 
 }  // namespace rk
