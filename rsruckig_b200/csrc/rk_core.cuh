@@ -595,4 +595,52 @@ __device__ __forceinline__ double shrink_interval(const double (&p)[N], double l
     return rts;
 }
 
+// shrink_interval as a resumable state machine: the same operations in the same order, one iteration per step() call, so
+// that a lane can pick up the next bracket as soon as its own has converged (k2_polish).
+template <int N>
+struct ShrinkState {
+    double p[N], deriv[N - 1];
+    double l, h, rts, dxold, dx, f, df;
+    int it;
+    // returns true if the root is known without iterating (then rts holds it)
+    __device__ __forceinline__ bool start(double lo, double hi) {
+        poly_deri<N>(p, deriv);
+        l = lo; h = hi;
+        const double fl = poly_eval<N>(p, l);
+        const double fh = poly_eval<N>(p, h);
+        if (fl == 0.0) { rts = l; return true; }
+        if (fh == 0.0) { rts = h; return true; }
+        if (fl > 0.0) { const double tmp = l; l = h; h = tmp; }
+        rts = (l + h) / 2.0;
+        dxold = fabs(h - l);
+        dx = dxold;
+        f = poly_eval<N>(p, rts);
+        df = poly_eval<N - 1>(deriv, rts);
+        it = 0;
+        return false;
+    }
+    // one pass of the loop body of shrink_interval; returns true when rts is final
+    __device__ __forceinline__ bool step() {
+        if (it >= 128) return true;
+        ++it;
+        if ((((rts - h) * df - f) * ((rts - l) * df - f) > 0.0) || fabs(2.0 * f) > fabs(dxold) * fabs(df)) {
+            dxold = dx;
+            dx = (h - l) / 2.0;
+            rts = l + dx;
+            if (fabs(l - rts) < EPS) return true;
+        } else {
+            dxold = dx;
+            dx = sdiv(f, df);
+            const double temp = rts;
+            rts -= dx;
+            if (fabs(temp - rts) < EPS) return true;
+        }
+        if (fabs(dx) < 1e-14) return true;
+        f = poly_eval<N>(p, rts);
+        df = poly_eval<N - 1>(deriv, rts);
+        if (f < 0.0) l = rts; else h = rts;
+        return false;
+    }
+};
+
 }  // namespace rk

@@ -242,6 +242,7 @@ struct rk_handle {
     uint2* rq_item = nullptr;
     double* rq_root = nullptr;
     uint32_t* list[2] = {nullptr, nullptr};
+    uint32_t* pend = nullptr;
     uint32_t* counters = nullptr;
     int sm_count = 148;
     // staging for host-memory calls
@@ -272,7 +273,7 @@ struct rk_trajectories {
 static rk_status ensure_scratch(rk_handle* h, int64_t items) {
     if (items <= h->ws_items) return RK_OK;
     if (h->ws) {
-        cudaFree(h->ws); cudaFree(h->wmeta); cudaFree(h->wsrc); cudaFree(h->wcnt); cudaFree(h->wqmask); cudaFree(h->rq_item); cudaFree(h->rq_root); cudaFree(h->list[0]); cudaFree(h->list[1]); cudaFree(h->counters);
+        cudaFree(h->ws); cudaFree(h->wmeta); cudaFree(h->wsrc); cudaFree(h->wcnt); cudaFree(h->wqmask); cudaFree(h->rq_item); cudaFree(h->rq_root); cudaFree(h->list[0]); cudaFree(h->list[1]); cudaFree(h->pend); cudaFree(h->counters);
         h->ws = nullptr; h->ws_items = 0;
     }
     RK_CUDA(cudaMalloc(&h->ws, sizeof(double) * rk::WS_SLOTS * items));
@@ -284,7 +285,8 @@ static rk_status ensure_scratch(rk_handle* h, int64_t items) {
     RK_CUDA(cudaMalloc(&h->rq_root, sizeof(double) * 8 * items));
     RK_CUDA(cudaMalloc(&h->list[0], sizeof(uint32_t) * items));
     RK_CUDA(cudaMalloc(&h->list[1], sizeof(uint32_t) * items));
-    RK_CUDA(cudaMalloc(&h->counters, sizeof(uint32_t) * 32));
+    RK_CUDA(cudaMalloc(&h->pend, sizeof(uint32_t) * items));
+    RK_CUDA(cudaMalloc(&h->counters, sizeof(uint32_t) * RK_N_COUNTERS));
     h->ws_items = items;
     return RK_OK;
 }
@@ -387,7 +389,7 @@ rk_status rk_destroy(rk_handle* h) {
     if (!h) return RK_OK;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    if (h->ws) { cudaFree(h->ws); cudaFree(h->wmeta); cudaFree(h->wsrc); cudaFree(h->wcnt); cudaFree(h->wqmask); cudaFree(h->rq_item); cudaFree(h->rq_root); cudaFree(h->list[0]); cudaFree(h->list[1]); cudaFree(h->counters); }
+    if (h->ws) { cudaFree(h->ws); cudaFree(h->wmeta); cudaFree(h->wsrc); cudaFree(h->wcnt); cudaFree(h->wqmask); cudaFree(h->rq_item); cudaFree(h->rq_root); cudaFree(h->list[0]); cudaFree(h->list[1]); cudaFree(h->pend); cudaFree(h->counters); }
     if (h->stage_dev) cudaFree(h->stage_dev);
     if (h->stage_pinned) cudaFreeHost(h->stage_pinned);
     for (int k = 0; k < 2; ++k) {
@@ -447,7 +449,7 @@ rk_status rk_calculate_batch(rk_handle* h, const rk_batch_desc* desc, const rk_b
     st = ensure_scratch(h, cn_max * desc->dof);
     if (st != RK_OK) return st;
     P.ws = h->ws; P.wmeta = h->wmeta; P.wsrc = h->wsrc; P.wcnt = h->wcnt; P.wqmask = h->wqmask; P.rq_item = h->rq_item; P.rq_root = h->rq_root;
-    P.list[0] = h->list[0]; P.list[1] = h->list[1]; P.counters = h->counters;
+    P.list[0] = h->list[0]; P.list[1] = h->list[1]; P.pend = h->pend; P.counters = h->counters;
 
     // host buffers: per-chunk staging, double buffered
     const rk::Params host_ptrs = P;
@@ -508,7 +510,7 @@ rk_status rk_calculate_batch(rk_handle* h, const rk_batch_desc* desc, const rk_b
         unsigned grid_list = (unsigned)h->sm_count * 16u;
         if (grid_list > grid_items) grid_list = grid_items;
         const unsigned grid_vel = (grid_list * 128u + RK_LS_BLOCK - 1u) / RK_LS_BLOCK;
-        RK_CUDA(cudaMemsetAsync(h->counters, 0, sizeof(uint32_t) * 32, h->stream));
+        RK_CUDA(cudaMemsetAsync(h->counters, 0, sizeof(uint32_t) * RK_N_COUNTERS, h->stream));
         rk::k1_setup<<<grid_items, 128, 0, h->stream>>>(P);
         const unsigned grid_fam = (unsigned)((2 * items + 127) / 128);
         rk::k1_quartic_roots<0><<<grid_fam, 128, 0, h->stream>>>(P);
@@ -527,7 +529,12 @@ rk_status rk_calculate_batch(rk_handle* h, const rk_batch_desc* desc, const rk_b
         for (int step = 0; step < RK_S2_STEPS; ++step) {
             switch (fam[step]) {
                 case 0: rk::k2_stage<0><<<grid_list, 128, 0, h->stream>>>(P, step, dir2[step]); break;
-                case 1: rk::k2_vel<1><<<grid_vel, RK_LS_BLOCK, 0, h->stream>>>(P, step, dir2[step]); break;
+                case 1:
+                    rk::k2_vel_scan_uddu<<<grid_vel, RK_LS_BLOCK, 0, h->stream>>>(P, step, dir2[step]);
+                    rk::k2_polish<6, false><<<grid_list, 128, 0, h->stream>>>(P, 33 + 2 * step);
+                    rk::k2_vel_check_uddu<<<grid_list, 128, 0, h->stream>>>(P, step, dir2[step]);
+                    h->launches += 2;
+                    break;
                 case 2: rk::k2_stage<2><<<grid_list, 128, 0, h->stream>>>(P, step, dir2[step]); break;
                 case 3: rk::k2_stage<3><<<grid_list, 128, 0, h->stream>>>(P, step, dir2[step]); break;
                 case 4: rk::k2_stage<4><<<grid_list, 128, 0, h->stream>>>(P, step, dir2[step]); break;

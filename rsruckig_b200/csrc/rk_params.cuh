@@ -9,6 +9,8 @@
 
 namespace rk {
 
+#define RK_N_COUNTERS 72
+
 struct Params {
     int64_t n;        // trajectories in the batch (stride of the trajectory storage)
     int64_t off;      // first trajectory of this chunk
@@ -34,7 +36,8 @@ struct Params {
     uint2* rq_item;   // root queue of the quartic kernels: (item, direction | rank << 1)
     double* rq_root;  //   ... and the root itself; 8 entries per item at most
     uint32_t* list[2];   // ping-pong work lists of item indices for the Step-2 stages, [dof * cn] each
-    uint32_t* counters;  // [0..18] list lengths per Step-2 stage, [20..22] quartic root queues, [24] rescue list
+    uint32_t* pend;      // VEL stage: items whose root candidates are being polished, [dof * cn]
+    uint32_t* counters;  // [0..18] list lengths per Step-2 stage, [20..22] quartic root queues, [24] rescue list, [32 + 2 * step], [33 + 2 * step] pending items / polish tasks of VEL stage `step`
     // trajectory storage
     double* prof;     // [PROFILE_SLOTS][dof][n]
     uint32_t* codes;  // [dof][n]

@@ -986,6 +986,163 @@ __global__ void __launch_bounds__(RK_LS_BLOCK, RK_LS_MINB) k2_vel(const Params P
     }
 }
 
+// ------------------------------------------------------------------------------------------------ VEL as scan -> polish -> check
+// Half of the VEL stage's instructions used to be the safeguarded Newton iteration (shrink_interval), run by the ~10 lanes of a
+// warp that had a bracket, for as long as the slowest of them needed (mean 10 iterations, slowest of 32 about 28). The stage
+// is therefore cut in three:
+//   k2_vel_scan    phases A-C per item (lockstep): polynomial, extrema, root candidates. Items without a candidate go straight
+//                  to the next list; the others park polynomial and brackets in their scratch area, join the pending list,
+//                  and every true bracket becomes a task of the polish queue.
+//   k2_polish<N>   one lane per task, and a lane that has converged takes the next task while its neighbours keep
+//                  iterating (refill in batches), so the iteration runs with nearly full warps.
+//   k2_vel_check   pending items: candidates in order, root -> Newton step -> profile check; first pass wins.
+// Counters: [step + 1] the next list as before, [32 + 2 * step] pending items, [33 + 2 * step] polish tasks.
+__device__ __forceinline__ double* vslot(const Params& P, int64_t wi, int64_t wstride, int slot) {
+    return P.ws + (int64_t)(W_VLIST + slot) * wstride + wi;
+}
+
+// warp-aggregated append of a variable number of entries per lane; returns the lane's first index
+__device__ __forceinline__ uint32_t warp_reserve(uint32_t* counter, int mine) {
+    const int lane = threadIdx.x & 31;
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int up = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += up;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    uint32_t base = 0;
+    if (total > 0 && lane == 31) base = atomicAdd(counter, (uint32_t)total);
+    return __shfl_sync(0xffffffffu, base, 31) + (uint32_t)(incl - mine);
+}
+
+__global__ void __launch_bounds__(RK_LS_BLOCK, RK_LS_MINB) k2_vel_scan_uddu(const Params P, int step, int second_dir) {
+    const int64_t wstride = (int64_t)P.dof * P.cn;
+    const uint32_t* list_in = P.list[step & 1];
+    uint32_t* list_out = P.list[(step + 1) & 1];
+    const uint32_t count = P.counters[step];
+    const bool second_direction = second_dir != 0;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    const uint32_t rounds = (count + stride - 1) / stride;
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    for (uint32_t r = 0; r < rounds; ++r, k += stride) {
+        const bool active = k < count;
+        const uint32_t wi = active ? list_in[k] : list_in[0];
+        const ItemS2 it = load_item_s2(P, wi, wstride);
+        S2 s;
+        s.init(it.b, it.tf, it.x.j_max);
+        const bool up_first = s.pd > it.tf * it.b.v0;
+        const Lim L = lim_dir(up_first != second_direction, it.x.v_max, it.x.v_min, it.x.a_max, it.x.a_min, it.x.j_max);
+        Hit h;
+        double pol[6], c_lo[6], c_hi[6];
+        int n_cand;
+        const bool found = vel_uddu_candidates(s, L, h, active, pol, c_lo, c_hi, n_cand);
+        RK_PHASE_BARRIER();
+        if (found) put_solution(P, it, wstride, h);
+        const bool pending = active && !found && n_cand > 0;
+        int n_task = 0;
+        if (pending) {
+#pragma unroll
+            for (int q = 0; q < 5; ++q) *vslot(P, wi, wstride, V_POL + q) = pol[q + 1];
+#pragma unroll
+            for (int c = 0; c < 6; ++c) {
+                if (c < n_cand) {
+                    *vslot(P, wi, wstride, V_LO + c) = c_lo[c];
+                    *vslot(P, wi, wstride, V_HI + c) = c_hi[c];
+                    if (c_lo[c] != c_hi[c]) ++n_task; else *vslot(P, wi, wstride, V_ROOT + c) = c_hi[c];
+                }
+            }
+            P.wqmask[wi] = (uint32_t)n_cand;
+        }
+        append_unsolved(list_out, P.counters + step + 1, active && !found && n_cand == 0, wi);
+        append_unsolved(P.pend, P.counters + 32 + 2 * step, pending, wi);
+        uint32_t e = warp_reserve(P.counters + 33 + 2 * step, n_task);
+        if (pending) {
+#pragma unroll
+            for (int c = 0; c < 6; ++c)
+                if (c < n_cand && c_lo[c] != c_hi[c]) P.rq_item[e++] = make_uint2(wi, (uint32_t)c);
+        }
+    }
+}
+
+// Polish queue: task (item, c) = bracket [lo[c], hi[c]] of the item's monic polynomial of N coefficients (DERIV: of its monic
+// derivative, the first pass of the UDUD half, slots V1_*). Result: root[c].
+template <int N, bool DERIV>
+__global__ void __launch_bounds__(128, 8) k2_polish(const Params P, int counter_index) {
+    const int64_t wstride = (int64_t)P.dof * P.cn;
+    const uint32_t count = P.counters[counter_index];
+    const uint32_t stride = gridDim.x * blockDim.x;
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    ShrinkState<N> st;
+    bool have = false;
+    double* out = nullptr;
+    while (true) {
+        const bool want = !have && k < count;
+        const unsigned wanting = __ballot_sync(0xffffffffu, want);
+        const unsigned busy = __ballot_sync(0xffffffffu, have);
+        if (wanting == 0 && busy == 0) break;
+        // refill in batches: a quarter of the warp idle, or nobody iterating
+        if (wanting != 0 && (__popc(wanting) >= 8 || busy == 0)) {
+            if (want) {
+                const uint2 task = P.rq_item[k];
+                const int64_t wi = task.x;
+                const int c = (int)task.y;
+                if (DERIV) {
+                    double pol[N + 1];
+                    pol[0] = 1.0;
+#pragma unroll
+                    for (int q = 0; q < N; ++q) pol[q + 1] = *vslot(P, wi, wstride, V_POL + q);
+                    poly_monic_deri<N + 1>(pol, st.p);
+                } else {
+                    st.p[0] = 1.0;
+#pragma unroll
+                    for (int q = 0; q < N - 1; ++q) st.p[q + 1] = *vslot(P, wi, wstride, V_POL + q);
+                }
+                const double lo = *vslot(P, wi, wstride, (DERIV ? V1_LO : V_LO) + c);
+                const double hi = *vslot(P, wi, wstride, (DERIV ? V1_HI : V_HI) + c);
+                out = vslot(P, wi, wstride, (DERIV ? V1_ROOT : V_ROOT) + c);
+                if (st.start(lo, hi)) { *out = st.rts; k += stride; }
+                else have = true;
+            }
+        }
+        if (have && st.step()) {
+            *out = st.rts;
+            have = false;
+            k += stride;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128, RK_MIN_BLOCKS) k2_vel_check_uddu(const Params P, int step, int second_dir) {
+    const int64_t wstride = (int64_t)P.dof * P.cn;
+    uint32_t* list_out = P.list[(step + 1) & 1];
+    const uint32_t count = P.counters[32 + 2 * step];
+    const bool second_direction = second_dir != 0;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    const uint32_t rounds = (count + stride - 1) / stride;
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    for (uint32_t r = 0; r < rounds; ++r, k += stride) {
+        bool unsolved = false;
+        uint32_t wi = 0;
+        if (k < count) {
+            wi = P.pend[k];
+            const ItemS2 it = load_item_s2(P, wi, wstride);
+            S2 s;
+            s.init(it.b, it.tf, it.x.j_max);
+            const bool up_first = s.pd > it.tf * it.b.v0;
+            const Lim L = lim_dir(up_first != second_direction, it.x.v_max, it.x.v_min, it.x.a_max, it.x.a_min, it.x.j_max);
+            const int n_cand = (int)P.wqmask[wi];
+            Hit h;
+            bool found = false;
+#pragma unroll 1
+            for (int c = 0; c < n_cand && !found; ++c) found = vel_uddu_root(s, L, h, *vslot(P, wi, wstride, V_ROOT + c));
+            if (found) put_solution(P, it, wstride, h);
+            unsolved = !found;
+        }
+        append_unsolved(list_out, P.counters + step + 1, unsolved, wi);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ k2_fail
 __global__ void __launch_bounds__(128) k2_fail(const Params P) {
     const int64_t wstride = (int64_t)P.dof * P.cn;

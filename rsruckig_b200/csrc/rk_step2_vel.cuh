@@ -183,12 +183,16 @@ __device__ RK_S2_FN bool s2_vel_uddu(const S2& s, const Lim& L, Hit& h) {
 #ifndef RK_PHASE_BARRIER
 #define RK_PHASE_BARRIER() __syncthreads()
 #endif
-__device__ __forceinline__ bool s2_vel_uddu_lockstep(const S2& s, const Lim& L, Hit& h, bool active) {
+// Phases A-C of the UDDU half: the quintic, its extrema and the root candidates (brackets [lo, hi], lo == hi for a candidate
+// that sits directly at an extremum). The rare all-zero boundary case is solved on the spot (returns true, h filled).
+__device__ __forceinline__ bool vel_uddu_candidates(const S2& s, const Lim& L, Hit& h, bool active, double (&pol)[6], double (&c_lo)[6], double (&c_hi)[6],
+                                                    int& n_cand) {
     RK_S2_LOCALS
     const real a0_p6 = s.a0_p6, af_p6 = s.af_p6;
     bool found = false;
     real tz_min = 0.0, tz_max = 0.0;
-    double pol[6], deriv[5], dderiv[4];
+    double deriv[5], dderiv[4];
+    n_cand = 0;
 
     if (active && fabs(v0) < EPS && fabs(a0) < EPS && fabs(vf) < EPS && fabs(af) < EPS) {  // rare, handled out of step
         active = false;
@@ -241,8 +245,6 @@ __device__ __forceinline__ bool s2_vel_uddu_lockstep(const S2& s, const Lim& L, 
     RK_PHASE_BARRIER();
 
     // phase C: record the root candidates (see s2_vel_uddu)
-    double c_lo[6], c_hi[6];
-    int n_cand = 0;
     if (active) {
         real tz_current = tz_min;
         real val_current = poly_eval<6>(pol, tz_current);
@@ -274,6 +276,13 @@ __device__ __forceinline__ bool s2_vel_uddu_lockstep(const S2& s, const Lim& L, 
         }
     }
 
+    return found;
+}
+
+__device__ __forceinline__ bool s2_vel_uddu_lockstep(const S2& s, const Lim& L, Hit& h, bool active) {
+    double pol[6], c_lo[6], c_hi[6];
+    int n_cand;
+    bool found = vel_uddu_candidates(s, L, h, active, pol, c_lo, c_hi, n_cand);
     // phase D: polish and validate the candidates in order, one candidate index per round of the whole block
 #pragma unroll 1
     for (int c = 0; c < 6; ++c) {

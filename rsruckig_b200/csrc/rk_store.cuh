@@ -26,6 +26,9 @@ enum : int { W_P0 = 0, W_V0 = 1, W_A0 = 2, W_TMIN = 3, W_ALEFT = 4, W_ARIGHT = 5
              W_BRAKE_DUR = 35,
              // Step-1 candidate sub-lists filled by the family kernels: 30 slots of t[7] (see rk_pipeline.cuh)
              W_VLIST = 36, W_VLIST_SLOTS = 30, WS_SLOTS = 36 + 30 * 7 };
+// Step 2, VEL family: a chain item re-uses its own (no longer needed) sub-list area for the polynomial, the root brackets and
+// the polished roots that travel between the scan, polish and check kernels (slots relative to W_VLIST).
+enum : int { V_POL = 0, V_LO = 8, V_HI = 16, V_ROOT = 24, V_TZ = 32, V1_LO = 40, V1_HI = 48, V1_ROOT = 56 };
 // meta words per item: [0] flags below, [1..3] codes of the three block profiles
 enum : int { WM_META = 0, WM_CAND = 1, WM_WORDS = 4 };
 enum : uint32_t { M_KIND_MASK = 0xFu, M_FOUND = 1u << 4, M_HAS_A = 1u << 5, M_HAS_B = 1u << 6, M_S1_PENDING = 1u << 7, M_ZERO_LIMITS = 1u << 8,

@@ -10,7 +10,7 @@ hdr = [r for r in rows if "Kernel Name" in r][0]
 ki, vi, mi, ii, ui = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Name"), hdr.index("ID"), hdr.index("Metric Unit")
 d = {}
 for r in rows:
-    if len(r) == len(hdr) and r[0].isdigit() and any(t in r[ki] for t in ("k1_", "k2_", "k_sync", "k_at_time", "k_validate")):
+    if len(r) == len(hdr) and r[0].isdigit() and any(t in r[ki] for t in ("k1_", "k2_", "k_sync", "k_expand", "k_at_time", "k_validate")):
         v = float(r[vi].replace(",", ""))
         u = r[ui]
         if u in ("Gbyte", "GB"): v *= 1e9
