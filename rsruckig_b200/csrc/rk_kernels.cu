@@ -224,7 +224,13 @@ rk_status fail(rk_status s, const std::string& m) {
         }                                                                                               \
     } while (0)
 
-constexpr int64_t CHUNK_ITEMS = 4ll << 20;  // (DoF, trajectory) items per chunk of scratch: 4 Mi items = 8.4 GB of scratch
+#ifndef RK_CHUNK_MI
+#define RK_CHUNK_MI 4
+#endif
+#ifndef RK_LANES
+#define RK_LANES 2
+#endif
+constexpr int64_t CHUNK_ITEMS = (int64_t)RK_CHUNK_MI << 20;  // (DoF, trajectory) items per chunk of scratch: 4 Mi items = 8.4 GB of scratch
 
 }  // namespace
 
@@ -232,18 +238,23 @@ struct rk_handle {
     int device = 0;
     cudaStream_t stream = nullptr;
     int64_t launches = 0;
-    // scratch
-    int64_t ws_items = 0;
-    double* ws = nullptr;
-    uint32_t* wmeta = nullptr;
-    uint8_t* wsrc = nullptr;
-    uint8_t* wcnt = nullptr;
-    uint32_t* wqmask = nullptr;
-    uint2* rq_item = nullptr;
-    double* rq_root = nullptr;
-    uint32_t* list[2] = {nullptr, nullptr};
-    uint32_t* pend = nullptr;
-    uint32_t* counters = nullptr;
+    // scratch: two sets, so that consecutive chunks of a large batch run on two streams (the many short, latency-bound
+    // kernels of one chunk overlap with the long ones of the other)
+    struct Scratch {
+        int64_t ws_items = 0;
+        double* ws = nullptr;
+        uint32_t* wmeta = nullptr;
+        uint8_t* wsrc = nullptr;
+        uint8_t* wcnt = nullptr;
+        uint32_t* wqmask = nullptr;
+        uint2* rq_item = nullptr;
+        double* rq_root = nullptr;
+        uint32_t* list[2] = {nullptr, nullptr};
+        uint32_t* pend = nullptr;
+        uint32_t* counters = nullptr;
+    } sc[RK_LANES];
+    cudaStream_t lane_stream[RK_LANES] = {};  // [0] is `stream`
+    cudaEvent_t ev_fork = nullptr, ev_join[RK_LANES] = {};
     int sm_count = 148;
     // staging for host-memory calls
     void* stage_dev = nullptr;
@@ -252,8 +263,8 @@ struct rk_handle {
     size_t stage_pinned_bytes = 0;
     // host-buffer calculate: input chunks are copied on a second stream while the previous chunk is computed
     cudaStream_t copy_stream = nullptr;
-    cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_computed[2] = {nullptr, nullptr};
-    void* chunk_in[2] = {nullptr, nullptr};
+    cudaEvent_t ev_copied[RK_LANES] = {}, ev_computed[RK_LANES] = {};
+    void* chunk_in[RK_LANES] = {};
     size_t chunk_in_bytes = 0;
 };
 
@@ -270,24 +281,29 @@ struct rk_trajectories {
     int32_t* detail = nullptr;
 };
 
-static rk_status ensure_scratch(rk_handle* h, int64_t items) {
-    if (items <= h->ws_items) return RK_OK;
-    if (h->ws) {
-        cudaFree(h->ws); cudaFree(h->wmeta); cudaFree(h->wsrc); cudaFree(h->wcnt); cudaFree(h->wqmask); cudaFree(h->rq_item); cudaFree(h->rq_root); cudaFree(h->list[0]); cudaFree(h->list[1]); cudaFree(h->pend); cudaFree(h->counters);
-        h->ws = nullptr; h->ws_items = 0;
-    }
-    RK_CUDA(cudaMalloc(&h->ws, sizeof(double) * rk::WS_SLOTS * items));
-    RK_CUDA(cudaMalloc(&h->wmeta, sizeof(uint32_t) * rk::WM_WORDS * items));
-    RK_CUDA(cudaMalloc(&h->wsrc, items));
-    RK_CUDA(cudaMalloc(&h->wcnt, 10 * items));
-    RK_CUDA(cudaMalloc(&h->wqmask, sizeof(uint32_t) * 6 * items));
-    RK_CUDA(cudaMalloc(&h->rq_item, sizeof(uint2) * 8 * items));
-    RK_CUDA(cudaMalloc(&h->rq_root, sizeof(double) * 8 * items));
-    RK_CUDA(cudaMalloc(&h->list[0], sizeof(uint32_t) * items));
-    RK_CUDA(cudaMalloc(&h->list[1], sizeof(uint32_t) * items));
-    RK_CUDA(cudaMalloc(&h->pend, sizeof(uint32_t) * items));
-    RK_CUDA(cudaMalloc(&h->counters, sizeof(uint32_t) * RK_N_COUNTERS));
-    h->ws_items = items;
+static void free_scratch(rk_handle::Scratch& c) {
+    if (!c.ws) return;
+    cudaFree(c.ws); cudaFree(c.wmeta); cudaFree(c.wsrc); cudaFree(c.wcnt); cudaFree(c.wqmask); cudaFree(c.rq_item); cudaFree(c.rq_root);
+    cudaFree(c.list[0]); cudaFree(c.list[1]); cudaFree(c.pend); cudaFree(c.counters);
+    c = rk_handle::Scratch();
+}
+
+static rk_status ensure_scratch(rk_handle* h, int set, int64_t items) {
+    rk_handle::Scratch& c = h->sc[set];
+    if (items <= c.ws_items) return RK_OK;
+    free_scratch(c);
+    RK_CUDA(cudaMalloc(&c.ws, sizeof(double) * rk::WS_SLOTS * items));
+    RK_CUDA(cudaMalloc(&c.wmeta, sizeof(uint32_t) * rk::WM_WORDS * items));
+    RK_CUDA(cudaMalloc(&c.wsrc, items));
+    RK_CUDA(cudaMalloc(&c.wcnt, 10 * items));
+    RK_CUDA(cudaMalloc(&c.wqmask, sizeof(uint32_t) * 6 * items));
+    RK_CUDA(cudaMalloc(&c.rq_item, sizeof(uint2) * 8 * items));
+    RK_CUDA(cudaMalloc(&c.rq_root, sizeof(double) * 8 * items));
+    RK_CUDA(cudaMalloc(&c.list[0], sizeof(uint32_t) * items));
+    RK_CUDA(cudaMalloc(&c.list[1], sizeof(uint32_t) * items));
+    RK_CUDA(cudaMalloc(&c.pend, sizeof(uint32_t) * items));
+    RK_CUDA(cudaMalloc(&c.counters, sizeof(uint32_t) * RK_N_COUNTERS));
+    c.ws_items = items;
     return RK_OK;
 }
 
@@ -377,7 +393,11 @@ rk_status rk_create(int32_t device, rk_handle** out) {
     RK_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     RK_CUDA(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device));
     RK_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
-    for (int k = 0; k < 2; ++k) {
+    h->lane_stream[0] = h->stream;
+    for (int k = 1; k < RK_LANES; ++k) RK_CUDA(cudaStreamCreateWithFlags(&h->lane_stream[k], cudaStreamNonBlocking));
+    RK_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    for (int k = 0; k < RK_LANES; ++k) RK_CUDA(cudaEventCreateWithFlags(&h->ev_join[k], cudaEventDisableTiming));
+    for (int k = 0; k < RK_LANES; ++k) {
         RK_CUDA(cudaEventCreateWithFlags(&h->ev_copied[k], cudaEventDisableTiming));
         RK_CUDA(cudaEventCreateWithFlags(&h->ev_computed[k], cudaEventDisableTiming));
     }
@@ -389,10 +409,15 @@ rk_status rk_destroy(rk_handle* h) {
     if (!h) return RK_OK;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    if (h->ws) { cudaFree(h->ws); cudaFree(h->wmeta); cudaFree(h->wsrc); cudaFree(h->wcnt); cudaFree(h->wqmask); cudaFree(h->rq_item); cudaFree(h->rq_root); cudaFree(h->list[0]); cudaFree(h->list[1]); cudaFree(h->pend); cudaFree(h->counters); }
+    for (int k = 0; k < RK_LANES; ++k) {
+        free_scratch(h->sc[k]);
+        if (k > 0 && h->lane_stream[k]) cudaStreamDestroy(h->lane_stream[k]);
+        if (h->ev_join[k]) cudaEventDestroy(h->ev_join[k]);
+    }
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->stage_dev) cudaFree(h->stage_dev);
     if (h->stage_pinned) cudaFreeHost(h->stage_pinned);
-    for (int k = 0; k < 2; ++k) {
+    for (int k = 0; k < RK_LANES; ++k) {
         if (h->chunk_in[k]) cudaFree(h->chunk_in[k]);
         if (h->ev_copied[k]) cudaEventDestroy(h->ev_copied[k]);
         if (h->ev_computed[k]) cudaEventDestroy(h->ev_computed[k]);
@@ -446,10 +471,17 @@ rk_status rk_calculate_batch(rk_handle* h, const rk_batch_desc* desc, const rk_b
 
     int64_t cn_max = CHUNK_ITEMS / desc->dof;
     if (cn_max > desc->n) cn_max = desc->n;
-    st = ensure_scratch(h, cn_max * desc->dof);
-    if (st != RK_OK) return st;
-    P.ws = h->ws; P.wmeta = h->wmeta; P.wsrc = h->wsrc; P.wcnt = h->wcnt; P.wqmask = h->wqmask; P.rq_item = h->rq_item; P.rq_root = h->rq_root;
-    P.list[0] = h->list[0]; P.list[1] = h->list[1]; P.pend = h->pend; P.counters = h->counters;
+    // more than one chunk: consecutive chunks rotate over RK_LANES scratch sets and streams
+    const int64_t n_chunks = (desc->n + cn_max - 1) / cn_max;
+    const int lanes = (int)(n_chunks < RK_LANES ? n_chunks : RK_LANES);
+    for (int k = 0; k < lanes; ++k) {
+        st = ensure_scratch(h, k, cn_max * desc->dof);
+        if (st != RK_OK) return st;
+    }
+    if (lanes > 1) {  // the extra streams join the caller-visible one at both ends
+        RK_CUDA(cudaEventRecord(h->ev_fork, h->stream));
+        for (int k = 1; k < lanes; ++k) RK_CUDA(cudaStreamWaitEvent(h->lane_stream[k], h->ev_fork, 0));
+    }
 
     // host buffers: per-chunk staging, double buffered
     const rk::Params host_ptrs = P;
@@ -462,12 +494,12 @@ rk_status rk_calculate_batch(rk_handle* h, const rk_batch_desc* desc, const rk_b
         if (host_ptrs.min_dur) bytes += sizeof(double) * (size_t)cn_max;
         if (host_ptrs.enabled) bytes += (((size_t)desc->dof * (size_t)cn_max + 255) / 256) * 256;
         if (bytes > h->chunk_in_bytes) {
-            for (int k = 0; k < 2; ++k) {
+            for (int k = 0; k < RK_LANES; ++k) {
                 if (h->chunk_in[k]) cudaFree(h->chunk_in[k]);
                 h->chunk_in[k] = nullptr;
             }
             h->chunk_in_bytes = 0;
-            for (int k = 0; k < 2; ++k) RK_CUDA(cudaMalloc(&h->chunk_in[k], bytes));
+            for (int k = 0; k < RK_LANES; ++k) RK_CUDA(cudaMalloc(&h->chunk_in[k], bytes));
             h->chunk_in_bytes = bytes;
         }
     }
@@ -476,10 +508,15 @@ rk_status rk_calculate_batch(rk_handle* h, const rk_batch_desc* desc, const rk_b
     for (int64_t off = 0; off < desc->n; off += cn_max, ++chunk_index) {
         P.off = off;
         P.cn = (desc->n - off < cn_max) ? (desc->n - off) : cn_max;
+        const int lane_set = chunk_index % lanes;
+        cudaStream_t cs = h->lane_stream[lane_set];
+        const rk_handle::Scratch& c = h->sc[lane_set];
+        P.ws = c.ws; P.wmeta = c.wmeta; P.wsrc = c.wsrc; P.wcnt = c.wcnt; P.wqmask = c.wqmask; P.rq_item = c.rq_item; P.rq_root = c.rq_root;
+        P.list[0] = c.list[0]; P.list[1] = c.list[1]; P.pend = c.pend; P.counters = c.counters;
         if (host) {
-            const int buf = chunk_index & 1;
+            const int buf = chunk_index % RK_LANES;
             // the buffer may still be read by the chunk computed two iterations ago
-            if (chunk_index >= 2) RK_CUDA(cudaStreamWaitEvent(h->copy_stream, h->ev_computed[buf], 0));
+            if (chunk_index >= RK_LANES) RK_CUDA(cudaStreamWaitEvent(h->copy_stream, h->ev_computed[buf], 0));
             char* dev = (char*)h->chunk_in[buf];
             const size_t per = sizeof(double) * (size_t)desc->dof * (size_t)P.cn;
             for (auto m : dslots) {
@@ -500,7 +537,7 @@ rk_status rk_calculate_batch(rk_handle* h, const rk_batch_desc* desc, const rk_b
                 P.enabled = (const uint8_t*)dev;
             }
             RK_CUDA(cudaEventRecord(h->ev_copied[buf], h->copy_stream));
-            RK_CUDA(cudaStreamWaitEvent(h->stream, h->ev_copied[buf], 0));
+            RK_CUDA(cudaStreamWaitEvent(cs, h->ev_copied[buf], 0));
             P.in_n = P.cn;
             P.in_shift = -off;
         }
@@ -510,44 +547,48 @@ rk_status rk_calculate_batch(rk_handle* h, const rk_batch_desc* desc, const rk_b
         unsigned grid_list = (unsigned)h->sm_count * 16u;
         if (grid_list > grid_items) grid_list = grid_items;
         const unsigned grid_vel = (grid_list * 128u + RK_LS_BLOCK - 1u) / RK_LS_BLOCK;
-        RK_CUDA(cudaMemsetAsync(h->counters, 0, sizeof(uint32_t) * RK_N_COUNTERS, h->stream));
-        rk::k1_setup<<<grid_items, 128, 0, h->stream>>>(P);
+        RK_CUDA(cudaMemsetAsync(c.counters, 0, sizeof(uint32_t) * RK_N_COUNTERS, cs));
+        rk::k1_setup<<<grid_items, 128, 0, cs>>>(P);
         const unsigned grid_fam = (unsigned)((2 * items + 127) / 128);
-        rk::k1_quartic_roots<0><<<grid_fam, 128, 0, h->stream>>>(P);
-        rk::k1_quartic_check<0><<<grid_list, 128, 0, h->stream>>>(P);
-        rk::k1_quartic_roots<1><<<grid_fam, 128, 0, h->stream>>>(P);
-        rk::k1_quartic_check<1><<<grid_list, 128, 0, h->stream>>>(P);
-        rk::k1_quartic_roots<2><<<grid_fam, 128, 0, h->stream>>>(P);
-        rk::k1_quartic_check<2><<<grid_list, 128, 0, h->stream>>>(P);
-        rk::k1_family<3><<<grid_fam, 128, 0, h->stream>>>(P);
-        rk::k1_family<4><<<grid_fam, 128, 0, h->stream>>>(P);
-        rk::k1_block<<<grid_items, 128, 0, h->stream>>>(P);
-        rk::k1_rescue<<<(unsigned)h->sm_count, 128, 0, h->stream>>>(P);
-        rk::k_sync<<<(unsigned)((P.cn + 127) / 128), 128, 0, h->stream>>>(P);
+        rk::k1_quartic_roots<0><<<grid_fam, 128, 0, cs>>>(P);
+        rk::k1_quartic_check<0><<<grid_list, 128, 0, cs>>>(P);
+        rk::k1_quartic_roots<1><<<grid_fam, 128, 0, cs>>>(P);
+        rk::k1_quartic_check<1><<<grid_list, 128, 0, cs>>>(P);
+        rk::k1_quartic_roots<2><<<grid_fam, 128, 0, cs>>>(P);
+        rk::k1_quartic_check<2><<<grid_list, 128, 0, cs>>>(P);
+        rk::k1_family<3><<<grid_fam, 128, 0, cs>>>(P);
+        rk::k1_family<4><<<grid_fam, 128, 0, cs>>>(P);
+        rk::k1_block<<<grid_items, 128, 0, cs>>>(P);
+        rk::k1_rescue<<<(unsigned)h->sm_count, 128, 0, cs>>>(P);
+        rk::k_sync<<<(unsigned)((P.cn + 127) / 128), 128, 0, cs>>>(P);
         static const int fam[RK_S2_STEPS] = {0, 1, 8, 2, 3, 0, 1, 8, 2, 3, 4, 5, 6, 7, 4, 5, 6, 7};
         static const int dir2[RK_S2_STEPS] = {0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 0, 0, 0, 0, 1, 1, 1, 1};
         for (int step = 0; step < RK_S2_STEPS; ++step) {
             switch (fam[step]) {
-                case 0: rk::k2_stage<0><<<grid_list, 128, 0, h->stream>>>(P, step, dir2[step]); break;
+                case 0: rk::k2_stage<0><<<grid_list, 128, 0, cs>>>(P, step, dir2[step]); break;
                 case 1:
-                    rk::k2_vel_scan_uddu<<<grid_vel, RK_LS_BLOCK, 0, h->stream>>>(P, step, dir2[step]);
-                    rk::k2_polish<6, false><<<grid_list, 128, 0, h->stream>>>(P, 33 + 2 * step);
-                    rk::k2_vel_check_uddu<<<grid_list, 128, 0, h->stream>>>(P, step, dir2[step]);
+                    rk::k2_vel_scan_uddu<<<grid_vel, RK_LS_BLOCK, 0, cs>>>(P, step, dir2[step]);
+                    rk::k2_polish<6, false><<<grid_list, 128, 0, cs>>>(P, 33 + 2 * step);
+                    rk::k2_vel_check_uddu<<<grid_list, 128, 0, cs>>>(P, step, dir2[step]);
                     h->launches += 2;
                     break;
-                case 2: rk::k2_stage<2><<<grid_list, 128, 0, h->stream>>>(P, step, dir2[step]); break;
-                case 3: rk::k2_stage<3><<<grid_list, 128, 0, h->stream>>>(P, step, dir2[step]); break;
-                case 4: rk::k2_stage<4><<<grid_list, 128, 0, h->stream>>>(P, step, dir2[step]); break;
-                case 5: rk::k2_stage<5><<<grid_list, 128, 0, h->stream>>>(P, step, dir2[step]); break;
-                case 6: rk::k2_stage<6><<<grid_list, 128, 0, h->stream>>>(P, step, dir2[step]); break;
-                case 7: rk::k2_stage<7><<<grid_list, 128, 0, h->stream>>>(P, step, dir2[step]); break;
-                default: rk::k2_vel<8><<<grid_vel, RK_LS_BLOCK, 0, h->stream>>>(P, step, dir2[step]); break;
+                case 2: rk::k2_stage<2><<<grid_list, 128, 0, cs>>>(P, step, dir2[step]); break;
+                case 3: rk::k2_stage<3><<<grid_list, 128, 0, cs>>>(P, step, dir2[step]); break;
+                case 4: rk::k2_stage<4><<<grid_list, 128, 0, cs>>>(P, step, dir2[step]); break;
+                case 5: rk::k2_stage<5><<<grid_list, 128, 0, cs>>>(P, step, dir2[step]); break;
+                case 6: rk::k2_stage<6><<<grid_list, 128, 0, cs>>>(P, step, dir2[step]); break;
+                case 7: rk::k2_stage<7><<<grid_list, 128, 0, cs>>>(P, step, dir2[step]); break;
+                default: rk::k2_vel<8><<<grid_vel, RK_LS_BLOCK, 0, cs>>>(P, step, dir2[step]); break;
             }
         }
-        rk::k2_fail<<<(unsigned)h->sm_count, 128, 0, h->stream>>>(P);
-        rk::k_expand<<<grid_items, 128, 0, h->stream>>>(P);
+        rk::k2_fail<<<(unsigned)h->sm_count, 128, 0, cs>>>(P);
+        rk::k_expand<<<grid_items, 128, 0, cs>>>(P);
         h->launches += 14 + RK_S2_STEPS;
-        if (host) RK_CUDA(cudaEventRecord(h->ev_computed[chunk_index & 1], h->stream));
+        if (host) RK_CUDA(cudaEventRecord(h->ev_computed[chunk_index % RK_LANES], cs));
+    }
+    for (int k = 1; k < lanes; ++k) {
+        RK_CUDA(cudaEventRecord(h->ev_join[k], h->lane_stream[k]));
+        RK_CUDA(cudaStreamWaitEvent(h->stream, h->ev_join[k], 0));
     }
     RK_CUDA(cudaGetLastError());
 
