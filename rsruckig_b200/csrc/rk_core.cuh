@@ -73,7 +73,9 @@ __device__ __forceinline__ bool forces_a3_zero(int lim) {
 __device__ __forceinline__ bool check_pos3_body(double t0, double t1, double t2, double t3, double t4, double t5, double t6, int cs, int lim,
                                                 double jf, double v_max, double v_min, double a_max, double a_min, double p0, double v0,
                                                 double a0, double pf, double vf, double af) {
-    if (t0 < 0.0 || t1 < 0.0 || t2 < 0.0 || t3 < 0.0 || t4 < 0.0 || t5 < 0.0 || t6 < 0.0) return false;
+    // The reference tests t < 0 (profile.rs:336-340). A NaN duration passes that test there, poisons p[7] and fails the final
+    // comparison, so it is rejected here at once as well: NaN operands would take the slow path of every division below.
+    if (!(t0 >= 0.0) || !(t1 >= 0.0) || !(t2 >= 0.0) || !(t3 >= 0.0) || !(t4 >= 0.0) || !(t5 >= 0.0) || !(t6 >= 0.0)) return false;
     const double t[7] = {t0, t1, t2, t3, t4, t5, t6};
 
     if ((lim == L_ACC0_ACC1_VEL || lim == L_ACC0_VEL || lim == L_ACC1_VEL || lim == L_VEL) && t3 < EPS) return false;
@@ -494,6 +496,9 @@ __device__ RK_QUART_FN Roots solve_quart_monic(double a, double b, double c, dou
             p2 = (a - sqrt_d) / 2.0;
         }
     } else {
+        // d_ < 0 (or NaN): the reference carries NaN through q1, q2, p1, p2 and both discriminant tests below then fail, i.e.
+        // no roots. Leave here instead of sending NaN operands down the slow path of the division.
+        if (!(d_ > 0.0)) return roots;
         const double sqrt_d = sqrt(d_);
         q1 = (y + sqrt_d) / 2.0;
         q2 = (y - sqrt_d) / 2.0;

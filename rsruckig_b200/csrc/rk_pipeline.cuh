@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(128) k1_setup(const Params P) {
 // candidates and writes the valid ones to its own sub-list; the order in which the reference would have met them is
 // restored by k1_block.
 template <int F>
-__global__ void __launch_bounds__(128, RK_MIN_BLOCKS) k1_family(const Params P) {
+__global__ void __launch_bounds__(128, 8) k1_family(const Params P) {
     const int64_t wstride = (int64_t)P.dof * P.cn;
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (tid >= 2 * wstride) return;
@@ -272,7 +272,7 @@ __global__ void __launch_bounds__(128, RK_MIN_BLOCKS) k1_quartic_roots(const Par
 }
 
 template <int TYPE>
-__global__ void __launch_bounds__(128, RK_MIN_BLOCKS) k1_quartic_check(const Params P) {
+__global__ void __launch_bounds__(128, TYPE == 0 ? 6 : 8) k1_quartic_check(const Params P) {
     const int64_t wstride = (int64_t)P.dof * P.cn;
     const uint32_t count = P.counters[20 + TYPE];
     for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < count; e += gridDim.x * blockDim.x) {
@@ -929,7 +929,7 @@ __device__ __forceinline__ void report_step2_failure(const Params& P, int d, int
 // ------------------------------------------------------------------------------------------------ k2_stage
 // `step` numbers the launches of the chain (list 0 of step 0 is filled by k_sync); list `step & 1` is read, the other written.
 template <int F>
-__global__ void __launch_bounds__(128, RK_MIN_BLOCKS) k2_stage(const Params P, int step, int second_dir) {
+__global__ void __launch_bounds__(128, F == 0 ? 6 : RK_MIN_BLOCKS) k2_stage(const Params P, int step, int second_dir) {
     const int64_t wstride = (int64_t)P.dof * P.cn;
     const uint32_t* list_in = P.list[step & 1];
     uint32_t* list_out = P.list[(step + 1) & 1];
@@ -958,7 +958,7 @@ __global__ void __launch_bounds__(128, RK_MIN_BLOCKS) k2_stage(const Params P, i
 #define RK_LS_BLOCK 128
 #endif
 #ifndef RK_LS_MINB
-#define RK_LS_MINB (512 / RK_LS_BLOCK)
+#define RK_LS_MINB 6
 #endif
 template <int F>
 __global__ void __launch_bounds__(RK_LS_BLOCK, RK_LS_MINB) k2_vel(const Params P, int step, int second_dir) {
@@ -1113,7 +1113,7 @@ __global__ void __launch_bounds__(128, 8) k2_polish(const Params P, int counter_
     }
 }
 
-__global__ void __launch_bounds__(128, RK_MIN_BLOCKS) k2_vel_check_uddu(const Params P, int step, int second_dir) {
+__global__ void __launch_bounds__(128, 6) k2_vel_check_uddu(const Params P, int step, int second_dir) {
     const int64_t wstride = (int64_t)P.dof * P.cn;
     uint32_t* list_out = P.list[(step + 1) & 1];
     const uint32_t count = P.counters[32 + 2 * step];
