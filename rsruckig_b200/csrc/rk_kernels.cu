@@ -245,7 +245,6 @@ struct rk_handle {
         double* ws = nullptr;
         uint32_t* wmeta = nullptr;
         uint8_t* wsrc = nullptr;
-        uint8_t* wcnt = nullptr;
         uint32_t* wqmask = nullptr;
         uint2* rq_item = nullptr;
         double* rq_root = nullptr;
@@ -283,7 +282,7 @@ struct rk_trajectories {
 
 static void free_scratch(rk_handle::Scratch& c) {
     if (!c.ws) return;
-    cudaFree(c.ws); cudaFree(c.wmeta); cudaFree(c.wsrc); cudaFree(c.wcnt); cudaFree(c.wqmask); cudaFree(c.rq_item); cudaFree(c.rq_root);
+    cudaFree(c.ws); cudaFree(c.wmeta); cudaFree(c.wsrc); cudaFree(c.wqmask); cudaFree(c.rq_item); cudaFree(c.rq_root);
     cudaFree(c.list[0]); cudaFree(c.list[1]); cudaFree(c.pend); cudaFree(c.counters);
     c = rk_handle::Scratch();
 }
@@ -295,9 +294,8 @@ static rk_status ensure_scratch(rk_handle* h, int set, int64_t items) {
     RK_CUDA(cudaMalloc(&c.ws, sizeof(double) * rk::WS_SLOTS * items));
     RK_CUDA(cudaMalloc(&c.wmeta, sizeof(uint32_t) * rk::WM_WORDS * items));
     RK_CUDA(cudaMalloc(&c.wsrc, items));
-    RK_CUDA(cudaMalloc(&c.wcnt, 10 * items));
-    RK_CUDA(cudaMalloc(&c.wqmask, sizeof(uint32_t) * 6 * items));
-    RK_CUDA(cudaMalloc(&c.rq_item, sizeof(uint2) * 8 * items));
+    RK_CUDA(cudaMalloc(&c.wqmask, sizeof(uint32_t) * 10 * items));
+    RK_CUDA(cudaMalloc(&c.rq_item, sizeof(uint2) * 12 * items));
     RK_CUDA(cudaMalloc(&c.rq_root, sizeof(double) * 8 * items));
     RK_CUDA(cudaMalloc(&c.list[0], sizeof(uint32_t) * items));
     RK_CUDA(cudaMalloc(&c.list[1], sizeof(uint32_t) * items));
@@ -511,7 +509,7 @@ rk_status rk_calculate_batch(rk_handle* h, const rk_batch_desc* desc, const rk_b
         const int lane_set = chunk_index % lanes;
         cudaStream_t cs = h->lane_stream[lane_set];
         const rk_handle::Scratch& c = h->sc[lane_set];
-        P.ws = c.ws; P.wmeta = c.wmeta; P.wsrc = c.wsrc; P.wcnt = c.wcnt; P.wqmask = c.wqmask; P.rq_item = c.rq_item; P.rq_root = c.rq_root;
+        P.ws = c.ws; P.wmeta = c.wmeta; P.wsrc = c.wsrc; P.wqmask = c.wqmask; P.rq_item = c.rq_item; P.rq_root = c.rq_root;
         P.list[0] = c.list[0]; P.list[1] = c.list[1]; P.pend = c.pend; P.counters = c.counters;
         if (host) {
             const int buf = chunk_index % RK_LANES;
@@ -556,8 +554,8 @@ rk_status rk_calculate_batch(rk_handle* h, const rk_batch_desc* desc, const rk_b
         rk::k1_quartic_check<1><<<grid_list, 128, 0, cs>>>(P);
         rk::k1_quartic_roots<2><<<grid_fam, 128, 0, cs>>>(P);
         rk::k1_quartic_check<2><<<grid_list, 128, 0, cs>>>(P);
-        rk::k1_family<3><<<grid_fam, 128, 0, cs>>>(P);
-        rk::k1_family<4><<<grid_fam, 128, 0, cs>>>(P);
+        rk::k1_closed_cands<<<grid_fam, 128, 0, cs>>>(P);
+        rk::k1_cand_check<<<grid_list, 128, 0, cs>>>(P);
         rk::k1_block<<<grid_items, 128, 0, cs>>>(P);
         rk::k1_rescue<<<(unsigned)h->sm_count, 128, 0, cs>>>(P);
         rk::k_sync<<<(unsigned)((P.cn + 127) / 128), 128, 0, cs>>>(P);

@@ -31,10 +31,9 @@ struct Params {
     double* ws;       // [WS_SLOTS][dof][cn]
     uint32_t* wmeta;  // [WM_WORDS][dof][cn]
     uint8_t* wsrc;    // [dof][cn]
-    uint8_t* wcnt;    // [10][dof][cn] lengths of the Step-1 candidate sub-lists (ACC0_ACC1, VEL)
-    uint32_t* wqmask; // [6][dof][cn] valid-slot masks (one byte per slot) of the quartic sub-lists
-    uint2* rq_item;   // root queue of the quartic kernels: (item, direction | rank << 1)
-    double* rq_root;  //   ... and the root itself; 8 entries per item at most
+    uint32_t* wqmask; // [10][dof][cn] valid-slot masks (one byte per slot) of the Step-1 candidate sub-lists
+    uint2* rq_item;   // work queue of the two-phase Step-1 kernels: (item, direction | rank << 1) / (item, direction | sub << 1 | slot << 8)
+    double* rq_root;  //   ... and the root itself (quartics); 8 resp. 12 entries per item at most
     uint32_t* list[2];   // ping-pong work lists of item indices for the Step-2 stages, [dof * cn] each
     uint32_t* pend;      // VEL stage: items whose root candidates are being polished, [dof * cn]
     uint32_t* counters;  // [0..18] list lengths per Step-2 stage, [20..22] quartic root queues, [24] rescue list, [32 + 2 * step], [33 + 2 * step] pending items / polish tasks of VEL stage `step`
@@ -125,13 +124,13 @@ __device__ __forceinline__ void ws_put_cand(const Params& P, int64_t wi, int64_t
     P.wmeta[(int64_t)(WM_CAND + slot) * wstride + wi] = pack_codes(c.lim, c.cs, c.dir, 0);
 }
 
-// Read block profile `slot` (0 p_min, 1 a.profile, 2 b.profile). Bits 24..28 of its code word: 0 = the profile was copied
+// Read block profile `slot` (0 p_min, 1 a.profile, 2 b.profile). Bits 24..31 of its code word: 0 = the profile was copied
 // into the W_CAND slots, r > 0 = it still sits in Step-1 sub-list slot r - 1 (third-order position interface; the control
-// value is then j_max if bit 23 is set, else -j_max). Bits 29..31 carry the kind of a phase-synchronised profile (k_sync).
+// value is then j_max if bit 23 is set, else -j_max). Bits 12..15 carry the kind of a phase-synchronised profile (k_sync).
 __device__ __forceinline__ void ws_get_cand(const Params& P, int64_t wi, int64_t wstride, int slot, double j_max, double (&t)[7], double& ctrl, double& ctrl2,
                                             uint32_t& codes) {
     codes = P.wmeta[(int64_t)(WM_CAND + slot) * wstride + wi];
-    const int ref = (int)((codes >> 24) & 0x1Fu);
+    const int ref = (int)(codes >> 24);
     if (ref == 0) {
         const double* base = P.ws + (int64_t)(W_CAND + slot * W_CAND_STRIDE) * wstride + wi;
 #pragma unroll

@@ -31,9 +31,10 @@ namespace rk {
 
 // ------------------------------------------------------------------------------------------------ candidate sub-lists in scratch
 // Step-1 candidates of a third-order position item live in ten sub-lists, one per (family, direction slot):
-//   sub 0..5 = quartic type (NONE, ACC0, ACC1) * 2 + slot, up to 4 candidates each; sub 6,7 = ACC0_ACC1, up to 2; sub 8,9 = VEL, 1.
+//   sub 0..5 = quartic type (NONE, ACC0, ACC1) * 2 + slot, up to 4 candidates each; sub 6,7 = ACC0_ACC1, up to 2; sub 8,9 = VEL, one
+//   slot per variant (4), of which the first valid one counts. Byte k of the sub-list's mask word: slot k holds a valid candidate.
 // Direction slot 0 is UP for general items and sign(pd) for rest-target items (vf ~ 0 && af ~ 0). Only t[7] is stored.
-__device__ __forceinline__ int sub_slot_base(int sub) { return sub < 6 ? sub * 4 : (sub < 8 ? 24 + (sub - 6) * 2 : 28 + (sub - 8)); }
+__device__ __forceinline__ int sub_slot_base(int sub) { return sub < 6 ? sub * 4 : (sub < 8 ? 24 + (sub - 6) * 2 : 28 + (sub - 8) * 4); }
 __device__ __forceinline__ int sub_limits(int sub) { return sub < 2 ? (int)L_NONE : (sub < 4 ? (int)L_ACC0 : (sub < 6 ? (int)L_ACC1 : (sub < 8 ? (int)L_ACC0_ACC1 : (int)L_VEL))); }
 
 __device__ __forceinline__ void sublist_get(const Params& P, int64_t wi, int64_t wstride, int sub, int k, const Lim& L, Cand& c) {
@@ -162,50 +163,21 @@ __global__ void __launch_bounds__(128) k1_setup(const Params P) {
     out.put(S_PF, pf_store); out.put(S_VF, vf_store); out.put(S_AF, af_store);
 }
 
-// ------------------------------------------------------------------------------------------------ k1_family
-// One thread per (direction slot, DoF, trajectory); F = 3 ACC0_ACC1 (position_third_step1.rs:241-327), 4 the VEL family
-// (:97-240); the quartic families F = 0..2 run as k1_quartic_roots / k1_quartic_check below. Every thread validates its
-// candidates and writes the valid ones to its own sub-list; the order in which the reference would have met them is
-// restored by k1_block.
-template <int F>
-__global__ void __launch_bounds__(128, 8) k1_family(const Params P) {
-    const int64_t wstride = (int64_t)P.dof * P.cn;
-    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (tid >= 2 * wstride) return;
-    const int ds = (int)(tid / wstride);
-    const int64_t wi = tid - (int64_t)ds * wstride;
-    const uint32_t meta = P.wmeta[(int64_t)WM_META * wstride + wi];
-    if (!(meta & M_S1_PENDING)) return;
-    const int d = (int)(wi / P.cn);
-    const int64_t ig = P.off + (wi - (int64_t)d * P.cn);
-    const DofIn x = load_dof(P, d, ig);
-    const double* w = P.ws + wi;
-    const Bound b{w[(int64_t)W_P0 * wstride], w[(int64_t)W_V0 * wstride], w[(int64_t)W_A0 * wstride], x.pf, x.vf, x.af};
-    const int sub = (F < 3) ? (F * 2 + ds) : (F == 3 ? 6 + ds : 8 + ds);
-
-    Step1Pos3<GlobalSink> s;
-    s.init(b, x.j_max);
-    s.sink.base = P.ws + (int64_t)(W_VLIST + sub_slot_base(sub) * 7) * wstride + wi;
-    s.sink.wstride = wstride;
-    const bool rest_target = fabs(b.vf) < EPS && fabs(b.af) < EPS;
-    const bool trivial = rest_target && fabs(b.v0) < EPS && fabs(b.a0) < EPS && fabs(s.pd) < EPS;
-    s.first_only = rest_target;
-    // :1015-1025 — nothing moves: only the quartics of the first direction are tried
-    if (!(trivial && (F >= 3 || ds == 1))) {
-        const bool up = rest_target ? ((ds == 0) == (s.pd >= 0.0)) : (ds == 0);
-        const Lim L = lim_dir(up, x.v_max, x.v_min, x.a_max, x.a_min, x.j_max);
-        if (F == 3) s.family_acc0_acc1(L);
-        else s.family_vel(L);
+// warp-aggregated append of a variable number of entries per lane; returns the lane's first index
+__device__ __forceinline__ uint32_t warp_reserve(uint32_t* counter, int mine) {
+    const int lane = threadIdx.x & 31;
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int up = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += up;
     }
-    P.wcnt[(int64_t)sub * wstride + wi] = (uint8_t)s.sink.count;
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    uint32_t base = 0;
+    if (total > 0 && lane == 31) base = atomicAdd(counter, (uint32_t)total);
+    return __shfl_sync(0xffffffffu, base, 31) + (uint32_t)(incl - mine);
 }
 
-// ------------------------------------------------------------------------------------------------ k1_quartic_roots / _check
-// The three quartic families in two phases. Phase A (one thread per (direction, DoF, trajectory)) builds the quartic,
-// pre-screens it, solves it in closed form and queues every root inside [t_min, t_max]; phase B (one thread per queued
-// root) does the Newton polish, builds t[7] and validates the profile. A (DoF, direction) has 0-4 in-range roots and most
-// candidates die in the check, so phase B runs the expensive part with full warps instead of the few lanes that happened
-// to have a root in the same loop iteration. Root k of a sub-list writes slot k, which keeps the ascending order.
 __device__ __forceinline__ Lim family_limits(const DofIn& x, const Bound& b, int ds, bool& rest_target, bool& trivial) {
     const double pd = b.pf - b.p0;
     rest_target = fabs(b.vf) < EPS && fabs(b.af) < EPS;
@@ -214,6 +186,86 @@ __device__ __forceinline__ Lim family_limits(const DofIn& x, const Bound& b, int
     return lim_dir(up, x.v_max, x.v_min, x.a_max, x.a_min, x.j_max);
 }
 
+// ------------------------------------------------------------------------------------------------ k1_closed_cands / k1_cand_check
+// The closed-form families ACC0_ACC1 (position_third_step1.rs:241-327) and VEL (:97-240) in two phases, like the quartics
+// below. Phase A, one thread per (direction slot, DoF, trajectory): the up to 2 + 4 candidate t[7] vectors, screened with the
+// tests of the profile check that need no integration, parked in their sub-list slots and queued. Phase B, one thread per
+// queued candidate: the full profile check, a valid candidate sets its byte of the sub-list's mask word. The order in which
+// the reference would have met the candidates is restored by k1_block (for VEL only the first valid variant counts).
+__global__ void __launch_bounds__(128, 8) k1_closed_cands(const Params P) {
+    const int64_t wstride = (int64_t)P.dof * P.cn;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t parked3 = 0, parked4 = 0;
+    int ds = 0;
+    int64_t wi = 0;
+    if (tid < 2 * wstride) {
+        ds = (int)(tid / wstride);
+        wi = tid - (int64_t)ds * wstride;
+        const uint32_t meta = P.wmeta[(int64_t)WM_META * wstride + wi];
+        if (meta & M_S1_PENDING) {
+            const int d = (int)(wi / P.cn);
+            const int64_t ig = P.off + (wi - (int64_t)d * P.cn);
+            const DofIn x = load_dof(P, d, ig);
+            const double* w = P.ws + wi;
+            const Bound b{w[(int64_t)W_P0 * wstride], w[(int64_t)W_V0 * wstride], w[(int64_t)W_A0 * wstride], x.pf, x.vf, x.af};
+            bool rest_target, trivial;
+            const Lim L = family_limits(x, b, ds, rest_target, trivial);
+            P.wqmask[(int64_t)(6 + ds) * wstride + wi] = 0u;
+            P.wqmask[(int64_t)(8 + ds) * wstride + wi] = 0u;
+            if (!trivial) {  // :1015-1025 — nothing moves: only the quartics of the first direction are tried
+                Step1Pos3<CandSink> s;
+                s.init(b, x.j_max);
+                s.first_only = false;
+                s.sink.wstride = wstride;
+                s.sink.parked = 0;
+                s.sink.base = P.ws + (int64_t)(W_VLIST + sub_slot_base(6 + ds) * 7) * wstride + wi;
+                s.family_acc0_acc1(L);
+                parked3 = s.sink.parked;
+                s.sink.parked = 0;
+                s.sink.base = P.ws + (int64_t)(W_VLIST + sub_slot_base(8 + ds) * 7) * wstride + wi;
+                s.family_vel(L);
+                parked4 = s.sink.parked;
+            }
+        }
+    }
+    const int mine = __popc(parked3) + __popc(parked4);
+    uint32_t e = warp_reserve(P.counters + 23, mine);
+#pragma unroll
+    for (int v = 0; v < 2; ++v)
+        if ((parked3 >> v) & 1u) P.rq_item[e++] = make_uint2((uint32_t)wi, (uint32_t)ds | (uint32_t)((6 + ds) << 1) | ((uint32_t)v << 8));
+#pragma unroll
+    for (int v = 0; v < 4; ++v)
+        if ((parked4 >> v) & 1u) P.rq_item[e++] = make_uint2((uint32_t)wi, (uint32_t)ds | (uint32_t)((8 + ds) << 1) | ((uint32_t)v << 8));
+}
+
+__global__ void __launch_bounds__(128, 8) k1_cand_check(const Params P) {
+    const int64_t wstride = (int64_t)P.dof * P.cn;
+    const uint32_t count = P.counters[23];
+    for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < count; e += gridDim.x * blockDim.x) {
+        const uint2 it = P.rq_item[e];
+        const int64_t wi = it.x;
+        const int ds = it.y & 1, sub = (it.y >> 1) & 0x7F, v = it.y >> 8;
+        const int d = (int)(wi / P.cn);
+        const int64_t ig = P.off + (wi - (int64_t)d * P.cn);
+        const DofIn x = load_dof(P, d, ig);
+        const double* w = P.ws + wi;
+        const Bound b{w[(int64_t)W_P0 * wstride], w[(int64_t)W_V0 * wstride], w[(int64_t)W_A0 * wstride], x.pf, x.vf, x.af};
+        bool rest_target, trivial;
+        const Lim L = family_limits(x, b, ds, rest_target, trivial);
+        const double* slot = P.ws + (int64_t)(W_VLIST + (sub_slot_base(sub) + v) * 7) * wstride + wi;
+        double t[7];
+#pragma unroll
+        for (int q = 0; q < 7; ++q) t[q] = slot[(int64_t)q * wstride];
+        if (check_pos3_inline(t, UDDU, sub_limits(sub), L.j_max, L, b)) reinterpret_cast<uint8_t*>(P.wqmask + (int64_t)sub * wstride + wi)[v] = 1;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ k1_quartic_roots / _check
+// The three quartic families in two phases. Phase A (one thread per (direction, DoF, trajectory)) builds the quartic,
+// pre-screens it, solves it in closed form and queues every root inside [t_min, t_max]; phase B (one thread per queued
+// root) does the Newton polish, builds t[7] and validates the profile. A (DoF, direction) has 0-4 in-range roots and most
+// candidates die in the check, so phase B runs the expensive part with full warps instead of the few lanes that happened
+// to have a root in the same loop iteration. Root k of a sub-list writes slot k, which keeps the ascending order.
 template <int TYPE>
 __global__ void __launch_bounds__(128, RK_MIN_BLOCKS) k1_quartic_roots(const Params P) {
     const int64_t wstride = (int64_t)P.dof * P.cn;
@@ -303,7 +355,7 @@ __global__ void __launch_bounds__(128, TYPE == 0 ? 6 : 8) k1_quartic_check(const
 // ------------------------------------------------------------------------------------------------ k1_block
 // Candidate sub-lists -> block of feasible durations (block.rs:40-154). The candidates are never copied: the kernel works on
 // (duration, sub-list slot) pairs held in registers, and the three profiles a block keeps (p_min, a.profile, b.profile) are
-// recorded as references to their sub-list slots (bits 24..28 of the code word, slot + 1; 0 = the profile sits in the
+// recorded as references to their sub-list slots (bits 24..31 of the code word, slot + 1; 0 = the profile sits in the
 // W_CAND slots, which the other Step-1 variants and the rescues still use). Items without any candidate go to k1_rescue.
 struct RefList {
     double dur[5];
@@ -425,13 +477,18 @@ __global__ void __launch_bounds__(128, 4) k1_block(const Params P) {
             const int tag_slot0 = ((((up0 ? v_max : v_min) > 0.0) ? DIR_UP : DIR_DOWN) << 16) | ((up0 ? 1 : 0) << 24);
             const int tag_slot1 = ((((up0 ? v_min : v_max) > 0.0) ? DIR_UP : DIR_DOWN) << 16) | ((up0 ? 0 : 1) << 24);
 
-            // quartic sub-lists (0..5) are sparse: byte k of the mask word says whether slot k holds a validated candidate
-            uint32_t qmask[6];
+            // byte k of a sub-list's mask word says whether slot k holds a validated candidate
+            uint32_t qmask[10];
             int cnt[10];
 #pragma unroll
-            for (int sub = 0; sub < 6; ++sub) { qmask[sub] = P.wqmask[(int64_t)sub * wstride + wi]; cnt[sub] = qmask[sub] ? 1 : 0; }
+            for (int sub = 0; sub < 10; ++sub) qmask[sub] = P.wqmask[(int64_t)sub * wstride + wi];
 #pragma unroll
-            for (int sub = 6; sub < 10; ++sub) cnt[sub] = P.wcnt[(int64_t)sub * wstride + wi];
+            for (int sub = 8; sub < 10; ++sub) {  // VEL keeps the first valid variant only (:97-240 returns after the first)
+                const uint32_t m = qmask[sub];
+                qmask[sub] = (m & 0xFFu) ? 0x1u : ((m & 0xFF00u) ? 0x100u : ((m & 0xFF0000u) ? 0x10000u : (m & 0xFF000000u)));
+            }
+#pragma unroll
+            for (int sub = 0; sub < 10; ++sub) cnt[sub] = qmask[sub] ? 1 : 0;
 
             RefList v;
             v.n = 0;
@@ -457,15 +514,11 @@ __global__ void __launch_bounds__(128, 4) k1_block(const Params P) {
                         if (pick < 0 && cnt[order[q]] > 0) pick = order[q];
                 }
                 if (pick >= 0) {
-                    int k = 0;
-                    if (pick < 6) {
-                        uint32_t m = 0;
+                    uint32_t m = 0;
 #pragma unroll
-                        for (int sub = 0; sub < 6; ++sub)
-                            if (sub == pick) m = qmask[sub];
-                        k = (m & 0xFFu) ? 0 : ((m & 0xFF00u) ? 1 : ((m & 0xFF0000u) ? 2 : 3));
-                    }
-                    take(pick, k);
+                    for (int sub = 0; sub < 10; ++sub)
+                        if (sub == pick) m = qmask[sub];
+                    take(pick, (m & 0xFFu) ? 0 : ((m & 0xFF00u) ? 1 : ((m & 0xFF0000u) ? 2 : 3)));
                 }
             } else {
                 // enumeration order of :1091-1140: quartics(UP), quartics(DOWN), ACC0_ACC1(UP), (DOWN), VEL(UP), (DOWN); five are kept (Q11)
@@ -473,15 +526,9 @@ __global__ void __launch_bounds__(128, 4) k1_block(const Params P) {
 #pragma unroll
                 for (int q = 0; q < 10; ++q) {
                     const int sub = order[q];
-                    if (sub < 6) {
 #pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            if (v.n < 5 && ((qmask[sub] >> (8 * k)) & 1u)) take(sub, k);
-                    } else {
-#pragma unroll
-                        for (int k = 0; k < 2; ++k)
-                            if (v.n < 5 && k < cnt[sub]) take(sub, k);
-                    }
+                    for (int k = 0; k < 4; ++k)
+                        if (v.n < 5 && ((qmask[sub] >> (8 * k)) & 1u)) take(sub, k);
                 }
             }
 
@@ -705,7 +752,7 @@ __device__ __forceinline__ void sync_trajectory(const Params& P, int64_t il, uin
                     double lt[7], lctrl, lctrl2;
                     uint32_t lcodes;
                     ws_get_cand(P, (int64_t)limiting * P.cn + il, wstride, SRC(limiting), load_dof(P, limiting, ig).j_max, lt, lctrl, lctrl2, lcodes);
-                    const int l_lim = lcodes & 0xFF, l_cs = (lcodes >> 8) & 0xFF, l_dir = (lcodes >> 16) & 0x7F;
+                    const int l_lim = lcodes & 0xFF, l_cs = (lcodes >> 8) & 0xF, l_dir = (lcodes >> 16) & 0x7F;
 
                     // scale vector selection
                     int scale_dof = -1, scale_vec = -1;  // 0 pd, 1 v0, 2 a0, 3 vf, 4 af
@@ -791,7 +838,7 @@ __device__ __forceinline__ void sync_trajectory(const Params& P, int64_t il, uin
                                     c.ctrl = npc; c.ctrl2 = -npc; c.lim = l_lim; c.cs = l_cs; c.dir = dir; c.dur = 0.0;
                                     const int64_t wd = (int64_t)d * P.cn + il;
                                     ws_put_cand(P, wd, wstride, 2, c);
-                                    P.wmeta[(int64_t)3 * wstride + wd] |= (uint32_t)(kind + 1) << 29;  // kind the profile is expanded with
+                                    P.wmeta[(int64_t)3 * wstride + wd] |= (uint32_t)(kind + 1) << 12;  // kind the profile is expanded with
                                     SRC(d) = RK_SRC_PHASE;
                                 }
                             }
@@ -1001,21 +1048,6 @@ __device__ __forceinline__ double* vslot(const Params& P, int64_t wi, int64_t ws
     return P.ws + (int64_t)(W_VLIST + slot) * wstride + wi;
 }
 
-// warp-aggregated append of a variable number of entries per lane; returns the lane's first index
-__device__ __forceinline__ uint32_t warp_reserve(uint32_t* counter, int mine) {
-    const int lane = threadIdx.x & 31;
-    int incl = mine;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int up = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += up;
-    }
-    const int total = __shfl_sync(0xffffffffu, incl, 31);
-    uint32_t base = 0;
-    if (total > 0 && lane == 31) base = atomicAdd(counter, (uint32_t)total);
-    return __shfl_sync(0xffffffffu, base, 31) + (uint32_t)(incl - mine);
-}
-
 __global__ void __launch_bounds__(RK_LS_BLOCK, RK_LS_MINB) k2_vel_scan_uddu(const Params P, int step, int second_dir) {
     const int64_t wstride = (int64_t)P.dof * P.cn;
     const uint32_t* list_in = P.list[step & 1];
@@ -1209,11 +1241,11 @@ __global__ void __launch_bounds__(128) k_expand(const Params P) {
             const int slot = (src == RK_SRC_PHASE) ? 2 : src;
             uint32_t c;
             ws_get_cand(P, wi, wstride, slot, it.x.j_max, t, ctrl, ctrl2, c);
-            lim = c & 0xFF; cs = (c >> 8) & 0xFF; dir = (c >> 16) & 0x7F;
+            lim = c & 0xFF; cs = (c >> 8) & 0xF; dir = (c >> 16) & 0x7F;
             lim_check = lim;
             if (src == RK_SRC_PHASE) {  // validated with ReachedLimits::None, labelled with the limiting DoF's limits (Q25)
                 lim_check = L_NONE;
-                store_kind = (int)(c >> 29) - 1;
+                store_kind = (int)((c >> 12) & 0xFu) - 1;
             }
         }
         if (ok) {

@@ -112,6 +112,8 @@ enum : int { QUARTIC_ROOTS = 0, QUARTIC_CANDIDATE = 1 };
 // Where validated candidates go: a local list (numerical rescues, zero-limit case) ...
 struct LocalSink {
     static constexpr bool inline_check = false;
+    static constexpr bool screen_only = false;
+    int variant;
     __device__ __forceinline__ void push_root(double) {}
     Cand vp[6];
     int count;
@@ -128,6 +130,8 @@ struct LocalSink {
 // sub-list the candidate sits in.
 struct GlobalSink {
     static constexpr bool inline_check = true;  // the family kernels have one to four emit sites each
+    static constexpr bool screen_only = false;
+    int variant;
     __device__ __forceinline__ void push_root(double) {}
     double* base;     // slot 0, t[0] of this sub-list for this item
     int64_t wstride;
@@ -144,6 +148,8 @@ struct GlobalSink {
 // root into the sub-list slot that root owns (slot = rank of the root, so the ascending order survives).
 struct QuarticSink {
     static constexpr bool inline_check = true;
+    static constexpr bool screen_only = false;
+    int variant;
     double roots[4];
     int n_roots;
     double* slot;
@@ -159,6 +165,35 @@ struct QuarticSink {
         ++count;
     }
 };
+
+// Sink of the closed-form families (ACC0_ACC1, VEL) in their candidate phase: `emit` only applies the cheap screens of the
+// profile check, parks t[7] in the slot of this variant and notes the slot for the check kernel.
+struct CandSink {
+    static constexpr bool inline_check = true;
+    static constexpr bool screen_only = true;
+    __device__ __forceinline__ void push_root(double) {}
+    double* base;     // slot 0, t[0] of this sub-list for this item
+    int64_t wstride;
+    int variant;      // slot inside the sub-list the next candidate goes to
+    uint32_t parked;  // bit v set: slot v holds a candidate to be checked
+    int count;
+    __device__ __forceinline__ void put(const double (&t)[7], int, const Lim&) {
+        double* q = base + (int64_t)(variant * 7) * wstride;
+#pragma unroll
+        for (int k = 0; k < 7; ++k) q[(int64_t)k * wstride] = t[k];
+        parked |= 1u << variant;
+    }
+};
+
+// the tests of the profile check that need no integration (profile.rs:336-349)
+__device__ __forceinline__ bool screen_pos3(const double (&t)[7], int lim) {
+    if (!(t[0] >= 0.0) || !(t[1] >= 0.0) || !(t[2] >= 0.0) || !(t[3] >= 0.0) || !(t[4] >= 0.0) || !(t[5] >= 0.0) || !(t[6] >= 0.0)) return false;
+    if ((lim == L_ACC0_ACC1_VEL || lim == L_ACC0_VEL || lim == L_ACC1_VEL || lim == L_VEL) && t[3] < EPS) return false;
+    if ((lim == L_ACC0 || lim == L_ACC0_ACC1) && t[1] < EPS) return false;
+    if ((lim == L_ACC1 || lim == L_ACC0_ACC1) && t[5] < EPS) return false;
+    if (t_sum6(t) > T_MAX) return false;
+    return true;
+}
 
 template <class Sink>
 struct Step1Pos3 {
@@ -180,8 +215,14 @@ struct Step1Pos3 {
         sink.count = 0;
     }
 
+    __device__ __forceinline__ void set_variant(int v) { sink.variant = v; }
+
     // Validate t; on success hand it to the sink. Returns validity.
     __device__ __forceinline__ bool emit(const double (&t)[7], int lim, const Lim& L) {
+        if (Sink::screen_only) {  // candidate phase: never "found", every variant is parked for the check kernel
+            if (screen_pos3(t, lim)) sink.put(t, lim, L);
+            return false;
+        }
         if (!(Sink::inline_check ? check_pos3_inline(t, UDDU, lim, L.j_max, L, b) : check_pos3(t, UDDU, lim, L.j_max, L, b))) return false;
         sink.put(t, lim, L);
         return true;
@@ -207,6 +248,7 @@ struct Step1Pos3 {
         t[4] = -a_min / j_max;
         t[5] = -(af_af / 2.0 - a_min * a_min - j_max * (vf - v_max)) / (a_min * j_max);
         t[6] = t[4] + af / j_max;
+        set_variant(0);
         if (emit(t, L_VEL, L)) return;
 
         // ACC1_VEL (t[4..6] carry over)
@@ -223,6 +265,7 @@ struct Step1Pos3 {
                                    + j_max * (v_max * v_max - vf_vf)
                                    + a_min * t_acc0 * (a0_a0 - 2.0 * j_max * (v0 + v_max))))
                / (24.0 * a_min * jj * v_max);
+        set_variant(1);
         if (emit(t, L_VEL, L)) return;
 
         // ACC0_VEL
@@ -242,6 +285,7 @@ struct Step1Pos3 {
         t[4] = t_acc1;
         t[5] = 0.0;
         t[6] = t_acc1 + af / j_max;
+        set_variant(2);
         if (emit(t, L_VEL, L)) return;
 
         // VEL (t[4..6] carry over)
@@ -253,6 +297,7 @@ struct Step1Pos3 {
                - (v0 / v_max + 1.0) * t_acc0
                - (vf / v_max + 1.0) * t_acc1
                + pd / v_max;
+        set_variant(3);
         emit(t, L_VEL, L);
     }
 
@@ -279,6 +324,7 @@ struct Step1Pos3 {
             t[4] = -a_min / j_max;
             t[5] = h3 + h1 / a_min;
             t[6] = t[4] + af / j_max;
+            set_variant(0);
             if (emit(t, L_ACC0_ACC1, L) && first_only) return;
         }
         // UDDU: Solution 1
@@ -290,6 +336,7 @@ struct Step1Pos3 {
             t[4] = -a_min / j_max;
             t[5] = h3 - h1 / a_min;
             t[6] = t[4] + af / j_max;
+            set_variant(1);
             emit(t, L_ACC0_ACC1, L);
         }
     }
