@@ -29,6 +29,7 @@ struct Params {
     const uint8_t* enabled;
     // scratch, chunk-local
     double* ws;       // [WS_SLOTS][dof][cn]
+    double2* rec;     // [dof * cn][6] packed per-item record written by k1_setup (load_rec): one 96-byte read instead of 14 sectors
     uint32_t* wmeta;  // [WM_WORDS][dof][cn]
     uint8_t* wsrc;    // [dof][cn]
     uint32_t* wqmask; // [10][dof][cn] valid-slot masks (one byte per slot) of the Step-1 candidate sub-lists
@@ -61,6 +62,33 @@ __device__ __forceinline__ DofIn load_dof(const Params& P, int d, int64_t ig) {
     x.v_min = P.v_min ? P.v_min[g] : -x.v_max;
     x.a_min = P.a_min ? P.a_min[g] : -x.a_max;
     x.enabled = P.enabled ? (P.enabled[g] != 0) : true;
+    return x;
+}
+
+// The per-item record every kernel after k1_setup works from: post-brake boundary state, direction-neutral limits, brake
+// duration. Packed (array of structures, 6 x 16 bytes) because most readers run over compacted lists, where a
+// structure-of-arrays read costs one 32-byte sector per 8-byte value.
+__device__ __forceinline__ void store_rec(const Params& P, int64_t wi, double ps, double vs, double as, const DofIn& x, double bdur) {
+    double2* r = P.rec + wi * 6;
+    r[0] = make_double2(ps, vs);
+    r[1] = make_double2(as, x.pf);
+    r[2] = make_double2(x.vf, x.af);
+    r[3] = make_double2(x.v_max, x.v_min);
+    r[4] = make_double2(x.a_max, x.a_min);
+    r[5] = make_double2(x.j_max, bdur);
+}
+
+// x.p0 / v0 / a0 of the returned DofIn are the POST-brake values (b.p0 ...), bdur the brake duration.
+__device__ __forceinline__ DofIn load_rec(const Params& P, int64_t wi, Bound& b, double& bdur) {
+    const double2* r = P.rec + wi * 6;
+    const double2 r0 = r[0], r1 = r[1], r2 = r[2], r3 = r[3], r4 = r[4], r5 = r[5];
+    DofIn x;
+    x.p0 = r0.x; x.v0 = r0.y; x.a0 = r1.x;
+    x.pf = r1.y; x.vf = r2.x; x.af = r2.y;
+    x.v_max = r3.x; x.v_min = r3.y; x.a_max = r4.x; x.a_min = r4.y; x.j_max = r5.x;
+    x.enabled = true;
+    b = Bound{r0.x, r0.y, r1.x, r1.y, r2.x, r2.y};
+    bdur = r5.y;
     return x;
 }
 

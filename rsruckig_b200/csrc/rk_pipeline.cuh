@@ -147,6 +147,7 @@ __global__ void __launch_bounds__(128) k1_setup(const Params P) {
     double* w = P.ws + wi;
     w[(int64_t)W_P0 * wstride] = ps; w[(int64_t)W_V0 * wstride] = vs; w[(int64_t)W_A0 * wstride] = as;
     w[(int64_t)W_BRAKE_DUR * wstride] = bdur;
+    store_rec(P, wi, ps, vs, as, x, bdur);
     if (!(meta & M_S1_PENDING)) {
         write_block(P, wi, wstride, blk, found, meta);
         P.imd[(int64_t)d * P.n + ig] = found ? blk.t_min : 0.0;
@@ -203,11 +204,9 @@ __global__ void __launch_bounds__(128, 8) k1_closed_cands(const Params P) {
         wi = tid - (int64_t)ds * wstride;
         const uint32_t meta = P.wmeta[(int64_t)WM_META * wstride + wi];
         if (meta & M_S1_PENDING) {
-            const int d = (int)(wi / P.cn);
-            const int64_t ig = P.off + (wi - (int64_t)d * P.cn);
-            const DofIn x = load_dof(P, d, ig);
-            const double* w = P.ws + wi;
-            const Bound b{w[(int64_t)W_P0 * wstride], w[(int64_t)W_V0 * wstride], w[(int64_t)W_A0 * wstride], x.pf, x.vf, x.af};
+            Bound b;
+            double bdur_;
+            const DofIn x = load_rec(P, wi, b, bdur_);
             bool rest_target, trivial;
             const Lim L = family_limits(x, b, ds, rest_target, trivial);
             P.wqmask[(int64_t)(6 + ds) * wstride + wi] = 0u;
@@ -245,11 +244,9 @@ __global__ void __launch_bounds__(128, 8) k1_cand_check(const Params P) {
         const uint2 it = P.rq_item[e];
         const int64_t wi = it.x;
         const int ds = it.y & 1, sub = (it.y >> 1) & 0x7F, v = it.y >> 8;
-        const int d = (int)(wi / P.cn);
-        const int64_t ig = P.off + (wi - (int64_t)d * P.cn);
-        const DofIn x = load_dof(P, d, ig);
-        const double* w = P.ws + wi;
-        const Bound b{w[(int64_t)W_P0 * wstride], w[(int64_t)W_V0 * wstride], w[(int64_t)W_A0 * wstride], x.pf, x.vf, x.af};
+        Bound b;
+        double bdur_;
+        const DofIn x = load_rec(P, wi, b, bdur_);
         bool rest_target, trivial;
         const Lim L = family_limits(x, b, ds, rest_target, trivial);
         const double* slot = P.ws + (int64_t)(W_VLIST + (sub_slot_base(sub) + v) * 7) * wstride + wi;
@@ -279,11 +276,9 @@ __global__ void __launch_bounds__(128, RK_MIN_BLOCKS) k1_quartic_roots(const Par
         wi = tid - (int64_t)ds * wstride;
         const uint32_t meta = P.wmeta[(int64_t)WM_META * wstride + wi];
         if (meta & M_S1_PENDING) {
-            const int d = (int)(wi / P.cn);
-            const int64_t ig = P.off + (wi - (int64_t)d * P.cn);
-            const DofIn x = load_dof(P, d, ig);
-            const double* w = P.ws + wi;
-            const Bound b{w[(int64_t)W_P0 * wstride], w[(int64_t)W_V0 * wstride], w[(int64_t)W_A0 * wstride], x.pf, x.vf, x.af};
+            Bound b;
+            double bdur_;
+            const DofIn x = load_rec(P, wi, b, bdur_);
             bool rest_target, trivial;
             const Lim L = family_limits(x, b, ds, rest_target, trivial);
             P.wqmask[(int64_t)(TYPE * 2 + ds) * wstride + wi] = 0u;
@@ -332,11 +327,9 @@ __global__ void __launch_bounds__(128, TYPE == 0 ? 6 : 8) k1_quartic_check(const
         const double root = P.rq_root[e];
         const int64_t wi = it.x;
         const int ds = it.y & 1, rank = it.y >> 1;
-        const int d = (int)(wi / P.cn);
-        const int64_t ig = P.off + (wi - (int64_t)d * P.cn);
-        const DofIn x = load_dof(P, d, ig);
-        const double* w = P.ws + wi;
-        const Bound b{w[(int64_t)W_P0 * wstride], w[(int64_t)W_V0 * wstride], w[(int64_t)W_A0 * wstride], x.pf, x.vf, x.af};
+        Bound b;
+        double bdur_;
+        const DofIn x = load_rec(P, wi, b, bdur_);
         bool rest_target, trivial;
         const Lim L = family_limits(x, b, ds, rest_target, trivial);
         const int sub = TYPE * 2 + ds;
@@ -461,18 +454,16 @@ __global__ void __launch_bounds__(128, 4) k1_block(const Params P) {
         if (meta & M_S1_PENDING) {
             const int d = (int)(wi / P.cn);
             const int64_t ig = P.off + (wi - (int64_t)d * P.cn);
-            const double* w = P.ws + wi;
-            const double bdur = w[(int64_t)W_BRAKE_DUR * wstride];
-            const int64_t g = (int64_t)d * P.in_n + ig + P.in_shift;
-            const double pf = P.pf ? P.pf[g] : 0.0, vf = P.vf ? P.vf[g] : 0.0, af = P.af ? P.af[g] : 0.0;
-            const double p0 = w[(int64_t)W_P0 * wstride], v0 = w[(int64_t)W_V0 * wstride], a0 = w[(int64_t)W_A0 * wstride];
+            Bound b;
+            double bdur;
+            const DofIn x = load_rec(P, wi, b, bdur);
+            const double pf = b.pf, vf = b.vf, af = b.af, p0 = b.p0, v0 = b.v0, a0 = b.a0;
             const double pd = pf - p0;
             const bool rest_target = fabs(vf) < EPS && fabs(af) < EPS;
             const bool trivial = rest_target && fabs(v0) < EPS && fabs(a0) < EPS && fabs(pd) < EPS;
             // direction slot 0 is UP for general items and sign(pd) for rest-target items; the Direction label of a profile
             // follows the sign of the direction-resolved v_max (profile.rs), the control value follows `up`
-            const double v_max = P.v_max ? P.v_max[g] : 0.0;
-            const double v_min = P.v_min ? P.v_min[g] : -v_max;
+            const double v_max = x.v_max, v_min = x.v_min;
             const bool up0 = rest_target ? (pd >= 0.0) : true;
             const int tag_slot0 = ((((up0 ? v_max : v_min) > 0.0) ? DIR_UP : DIR_DOWN) << 16) | ((up0 ? 1 : 0) << 24);
             const int tag_slot1 = ((((up0 ? v_min : v_max) > 0.0) ? DIR_UP : DIR_DOWN) << 16) | ((up0 ? 0 : 1) << 24);
@@ -917,10 +908,10 @@ __device__ __forceinline__ ItemS2 load_item_s2(const Params& P, int64_t wi, int6
     it.d = (int)(wi / P.cn);
     it.ig = P.off + (wi - (int64_t)it.d * P.cn);
     it.gi = (int64_t)it.d * P.n + it.ig;
-    it.x = load_dof(P, it.d, it.ig);
-    const double* w = P.ws + wi;
-    it.b = Bound{w[(int64_t)W_P0 * wstride], w[(int64_t)W_V0 * wstride], w[(int64_t)W_A0 * wstride], it.x.pf, it.x.vf, it.x.af};
-    it.tf = P.duration[it.ig] - w[(int64_t)W_BRAKE_DUR * wstride] - 0.0;  // :723 (accel duration is always 0)
+    double bdur;
+    it.x = load_rec(P, wi, it.b, bdur);  // NB: it.x.p0 / v0 / a0 are the post-brake values
+    it.tf = P.duration[it.ig] - bdur - 0.0;  // :723 (accel duration is always 0)
+    (void)wstride;
     return it;
 }
 
@@ -1208,7 +1199,8 @@ __global__ void __launch_bounds__(128) k_expand(const Params P) {
         ProfileSink out{P.prof, (int64_t)P.dof * P.n, it.gi};
         if (src == RK_SRC_NONE || kind == K_NONE) {
             // disabled DoF (calculator_target.rs:313-323) or a trajectory that ended with an error status
-            store_idle_profile(out, it.x.p0, it.x.v0, it.x.a0);
+            const int64_t g = (int64_t)it.d * P.in_n + (it.ig + P.in_shift);
+            store_idle_profile(out, P.p0[g], P.v0[g], P.a0[g]);
             P.codes[it.gi] = pack_codes(L_NONE, UDDU, DIR_UP, RK_SRC_NONE);
             return;
         }
