@@ -244,6 +244,7 @@ struct rk_handle {
         int64_t ws_items = 0;
         double* ws = nullptr;
         double2* rec = nullptr;
+        double* vl = nullptr;
         uint32_t* wmeta = nullptr;
         uint8_t* wsrc = nullptr;
         uint32_t* wqmask = nullptr;
@@ -283,7 +284,7 @@ struct rk_trajectories {
 
 static void free_scratch(rk_handle::Scratch& c) {
     if (!c.ws) return;
-    cudaFree(c.ws); cudaFree(c.rec); cudaFree(c.wmeta); cudaFree(c.wsrc); cudaFree(c.wqmask); cudaFree(c.rq_item); cudaFree(c.rq_root);
+    cudaFree(c.ws); cudaFree(c.rec); cudaFree(c.vl); cudaFree(c.wmeta); cudaFree(c.wsrc); cudaFree(c.wqmask); cudaFree(c.rq_item); cudaFree(c.rq_root);
     cudaFree(c.list[0]); cudaFree(c.list[1]); cudaFree(c.pend); cudaFree(c.counters);
     c = rk_handle::Scratch();
 }
@@ -293,6 +294,7 @@ static rk_status ensure_scratch(rk_handle* h, int set, int64_t items) {
     if (items <= c.ws_items) return RK_OK;
     free_scratch(c);
     RK_CUDA(cudaMalloc(&c.ws, sizeof(double) * rk::WS_SLOTS * items));
+    RK_CUDA(cudaMalloc(&c.vl, sizeof(double) * rk::VL_ITEM_DOUBLES * items));
     RK_CUDA(cudaMalloc(&c.rec, sizeof(double2) * 6 * items));
     RK_CUDA(cudaMalloc(&c.wmeta, sizeof(uint32_t) * rk::WM_WORDS * items));
     RK_CUDA(cudaMalloc(&c.wsrc, items));
@@ -511,7 +513,7 @@ rk_status rk_calculate_batch(rk_handle* h, const rk_batch_desc* desc, const rk_b
         const int lane_set = chunk_index % lanes;
         cudaStream_t cs = h->lane_stream[lane_set];
         const rk_handle::Scratch& c = h->sc[lane_set];
-        P.ws = c.ws; P.rec = c.rec; P.wmeta = c.wmeta; P.wsrc = c.wsrc; P.wqmask = c.wqmask; P.rq_item = c.rq_item; P.rq_root = c.rq_root;
+        P.ws = c.ws; P.rec = c.rec; P.vl = c.vl; P.wmeta = c.wmeta; P.wsrc = c.wsrc; P.wqmask = c.wqmask; P.rq_item = c.rq_item; P.rq_root = c.rq_root;
         P.list[0] = c.list[0]; P.list[1] = c.list[1]; P.pend = c.pend; P.counters = c.counters;
         if (host) {
             const int buf = chunk_index % RK_LANES;

@@ -29,6 +29,7 @@ struct Params {
     const uint8_t* enabled;
     // scratch, chunk-local
     double* ws;       // [WS_SLOTS][dof][cn]
+    double* vl;       // [dof * cn][36][8] Step-1 candidate slots (t[7] + duration), array of structures: 64-byte slots
     double2* rec;     // [dof * cn][6] packed per-item record written by k1_setup (load_rec): one 96-byte read instead of 14 sectors
     uint32_t* wmeta;  // [WM_WORDS][dof][cn]
     uint8_t* wsrc;    // [dof][cn]
@@ -90,6 +91,11 @@ __device__ __forceinline__ DofIn load_rec(const Params& P, int64_t wi, Bound& b,
     b = Bound{r0.x, r0.y, r1.x, r1.y, r2.x, r2.y};
     bdur = r5.y;
     return x;
+}
+
+// Candidate slot `slot` of item wi: t[0..6], duration (t_sum6) in [7].
+__device__ __forceinline__ double* vl_slot(const Params& P, int64_t wi, int slot) {
+    return P.vl + (wi * VL_SLOTS + slot) * VL_SLOT_DOUBLES;
 }
 
 // InputParameter::validate for one DoF (input_parameter.rs:251-420); returns 0 or the id of the first failing check.
@@ -166,9 +172,9 @@ __device__ __forceinline__ void ws_get_cand(const Params& P, int64_t wi, int64_t
         ctrl = base[7 * wstride];
         ctrl2 = base[8 * wstride];
     } else {
-        const double* base = P.ws + (int64_t)(W_VLIST + (ref - 1) * 7) * wstride + wi;
+        const double* base = vl_slot(P, wi, ref - 1);
 #pragma unroll
-        for (int k = 0; k < 7; ++k) t[k] = base[(int64_t)k * wstride];
+        for (int k = 0; k < 7; ++k) t[k] = base[k];
         ctrl = ((codes >> 23) & 1u) ? j_max : -j_max;
         ctrl2 = 0.0;
     }

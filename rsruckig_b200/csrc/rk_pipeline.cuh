@@ -33,14 +33,14 @@ namespace rk {
 // Step-1 candidates of a third-order position item live in ten sub-lists, one per (family, direction slot):
 //   sub 0..5 = quartic type (NONE, ACC0, ACC1) * 2 + slot, up to 4 candidates each; sub 6,7 = ACC0_ACC1, up to 2; sub 8,9 = VEL, one
 //   slot per variant (4), of which the first valid one counts. Byte k of the sub-list's mask word: slot k holds a valid candidate.
-// Direction slot 0 is UP for general items and sign(pd) for rest-target items (vf ~ 0 && af ~ 0). Only t[7] is stored.
+// Direction slot 0 is UP for general items and sign(pd) for rest-target items (vf ~ 0 && af ~ 0). A slot holds t[7] and the duration.
 __device__ __forceinline__ int sub_slot_base(int sub) { return sub < 6 ? sub * 4 : (sub < 8 ? 24 + (sub - 6) * 2 : 28 + (sub - 8) * 4); }
 __device__ __forceinline__ int sub_limits(int sub) { return sub < 2 ? (int)L_NONE : (sub < 4 ? (int)L_ACC0 : (sub < 6 ? (int)L_ACC1 : (sub < 8 ? (int)L_ACC0_ACC1 : (int)L_VEL))); }
 
 __device__ __forceinline__ void sublist_get(const Params& P, int64_t wi, int64_t wstride, int sub, int k, const Lim& L, Cand& c) {
-    const double* base = P.ws + (int64_t)(W_VLIST + (sub_slot_base(sub) + k) * 7) * wstride + wi;
+    const double* base = vl_slot(P, wi, sub_slot_base(sub) + k);
 #pragma unroll
-    for (int q = 0; q < 7; ++q) c.t[q] = base[(int64_t)q * wstride];
+    for (int q = 0; q < 7; ++q) c.t[q] = base[q];
     c.ctrl = L.j_max;
     c.ctrl2 = 0.0;
     c.dur = t_sum6(c.t);
@@ -215,13 +215,12 @@ __global__ void __launch_bounds__(128, 8) k1_closed_cands(const Params P) {
                 Step1Pos3<CandSink> s;
                 s.init(b, x.j_max);
                 s.first_only = false;
-                s.sink.wstride = wstride;
                 s.sink.parked = 0;
-                s.sink.base = P.ws + (int64_t)(W_VLIST + sub_slot_base(6 + ds) * 7) * wstride + wi;
+                s.sink.base = vl_slot(P, wi, sub_slot_base(6 + ds));
                 s.family_acc0_acc1(L);
                 parked3 = s.sink.parked;
                 s.sink.parked = 0;
-                s.sink.base = P.ws + (int64_t)(W_VLIST + sub_slot_base(8 + ds) * 7) * wstride + wi;
+                s.sink.base = vl_slot(P, wi, sub_slot_base(8 + ds));
                 s.family_vel(L);
                 parked4 = s.sink.parked;
             }
@@ -249,10 +248,9 @@ __global__ void __launch_bounds__(128, 8) k1_cand_check(const Params P) {
         const DofIn x = load_rec(P, wi, b, bdur_);
         bool rest_target, trivial;
         const Lim L = family_limits(x, b, ds, rest_target, trivial);
-        const double* slot = P.ws + (int64_t)(W_VLIST + (sub_slot_base(sub) + v) * 7) * wstride + wi;
-        double t[7];
-#pragma unroll
-        for (int q = 0; q < 7; ++q) t[q] = slot[(int64_t)q * wstride];
+        const double2* slot = reinterpret_cast<const double2*>(vl_slot(P, wi, sub_slot_base(sub) + v));
+        const double2 s0 = slot[0], s1 = slot[1], s2 = slot[2], s3 = slot[3];
+        const double t[7] = {s0.x, s0.y, s1.x, s1.y, s2.x, s2.y, s3.x};
         if (check_pos3_inline(t, UDDU, sub_limits(sub), L.j_max, L, b)) reinterpret_cast<uint8_t*>(P.wqmask + (int64_t)sub * wstride + wi)[v] = 1;
     }
 }
@@ -336,8 +334,7 @@ __global__ void __launch_bounds__(128, TYPE == 0 ? 6 : 8) k1_quartic_check(const
         Step1Pos3<QuarticSink> s;
         s.init(b, x.j_max);
         s.first_only = false;
-        s.sink.slot = P.ws + (int64_t)(W_VLIST + (sub_slot_base(sub) + rank) * 7) * wstride + wi;
-        s.sink.wstride = wstride;
+        s.sink.slot = vl_slot(P, wi, sub_slot_base(sub) + rank);
         if (TYPE == 0) s.template quartic_none<QUARTIC_CANDIDATE>(L, root);
         else if (TYPE == 1) s.template quartic_acc0<QUARTIC_CANDIDATE>(L, root);
         else s.template quartic_acc1<QUARTIC_CANDIDATE>(L, root);
@@ -487,11 +484,7 @@ __global__ void __launch_bounds__(128, 4) k1_block(const Params P) {
             for (int q = 0; q < 5; ++q) { v.dur[q] = 0.0; v.ref[q] = 0; }
             auto take = [&](int sub, int k) {
                 const int slot = sub_slot_base(sub) + k;
-                const double* base = P.ws + (int64_t)(W_VLIST + slot * 7) * wstride + wi;
-                double t[7];
-#pragma unroll
-                for (int q = 0; q < 7; ++q) t[q] = base[(int64_t)q * wstride];
-                v.push(t_sum6(t), slot | (sub << 8) | ((sub & 1) ? tag_slot1 : tag_slot0));
+                v.push(vl_slot(P, wi, slot)[7], slot | (sub << 8) | ((sub & 1) ? tag_slot1 : tag_slot0));  // [7] = t_sum6(t)
             };
             if (rest_target) {
                 // first hit in the reference's order (:1026-1089): VEL(d), quartics(d) = NONE, ACC0, ACC1, ACC0_ACC1(d), then the same for -d
@@ -1036,7 +1029,8 @@ __global__ void __launch_bounds__(RK_LS_BLOCK, RK_LS_MINB) k2_vel(const Params P
 //   k2_vel_check   pending items: candidates in order, root -> Newton step -> profile check; first pass wins.
 // Counters: [step + 1] the next list as before, [32 + 2 * step] pending items, [33 + 2 * step] polish tasks.
 __device__ __forceinline__ double* vslot(const Params& P, int64_t wi, int64_t wstride, int slot) {
-    return P.ws + (int64_t)(W_VLIST + slot) * wstride + wi;
+    (void)wstride;
+    return P.vl + wi * VL_ITEM_DOUBLES + slot;
 }
 
 __global__ void __launch_bounds__(RK_LS_BLOCK, RK_LS_MINB) k2_vel_scan_uddu(const Params P, int step, int second_dir) {

@@ -126,24 +126,6 @@ struct LocalSink {
         if (count < 5) ++count;  // the list saturates at five entries (Q11)
     }
 };
-// ... or the per-item sub-list of one (family, direction) in HBM scratch: only t[7] is stored, the codes follow from the
-// sub-list the candidate sits in.
-struct GlobalSink {
-    static constexpr bool inline_check = true;  // the family kernels have one to four emit sites each
-    static constexpr bool screen_only = false;
-    int variant;
-    __device__ __forceinline__ void push_root(double) {}
-    double* base;     // slot 0, t[0] of this sub-list for this item
-    int64_t wstride;
-    int count;
-    __device__ __forceinline__ void put(const double (&t)[7], int, const Lim&) {
-        double* q = base + (int64_t)(count * 7) * wstride;
-#pragma unroll
-        for (int k = 0; k < 7; ++k) q[(int64_t)k * wstride] = t[k];
-        ++count;
-    }
-};
-
 // Sink of the two-phase quartic kernels: phase A collects in-range roots, phase B stores the validated candidate of ONE
 // root into the sub-list slot that root owns (slot = rank of the root, so the ascending order survives).
 struct QuarticSink {
@@ -152,8 +134,7 @@ struct QuarticSink {
     int variant;
     double roots[4];
     int n_roots;
-    double* slot;
-    int64_t wstride;
+    double* slot;  // the 64-byte candidate slot this root owns: t[7] + duration
     int count;
     __device__ __forceinline__ void push_root(double r) {
         if (n_roots == 0) roots[0] = r; else if (n_roots == 1) roots[1] = r; else if (n_roots == 2) roots[2] = r; else roots[3] = r;
@@ -161,7 +142,8 @@ struct QuarticSink {
     }
     __device__ __forceinline__ void put(const double (&t)[7], int, const Lim&) {
 #pragma unroll
-        for (int k = 0; k < 7; ++k) slot[(int64_t)k * wstride] = t[k];
+        for (int k = 0; k < 7; ++k) slot[k] = t[k];
+        slot[7] = t_sum6(t);
         ++count;
     }
 };
@@ -172,15 +154,15 @@ struct CandSink {
     static constexpr bool inline_check = true;
     static constexpr bool screen_only = true;
     __device__ __forceinline__ void push_root(double) {}
-    double* base;     // slot 0, t[0] of this sub-list for this item
-    int64_t wstride;
+    double* base;     // slot 0 of this sub-list for this item (64-byte slots: t[7] + duration)
     int variant;      // slot inside the sub-list the next candidate goes to
     uint32_t parked;  // bit v set: slot v holds a candidate to be checked
     int count;
     __device__ __forceinline__ void put(const double (&t)[7], int, const Lim&) {
-        double* q = base + (int64_t)(variant * 7) * wstride;
+        double* q = base + variant * 8;
 #pragma unroll
-        for (int k = 0; k < 7; ++k) q[(int64_t)k * wstride] = t[k];
+        for (int k = 0; k < 7; ++k) q[k] = t[k];
+        q[7] = t_sum6(t);
         parked |= 1u << variant;
     }
 };

@@ -24,10 +24,11 @@ enum : int { K_POS3 = 0, K_POS2 = 1, K_POS1 = 2, K_VEL3 = 3, K_VEL2 = 4, K_NONE 
 // Scratch written by the Step-1 kernel (ws doubles, slot-major like the profiles).
 enum : int { W_P0 = 0, W_V0 = 1, W_A0 = 2, W_TMIN = 3, W_ALEFT = 4, W_ARIGHT = 5, W_BLEFT = 6, W_BRIGHT = 7, W_CAND = 8, W_CAND_STRIDE = 9,
              W_BRAKE_DUR = 35,
-             // Step-1 candidate sub-lists filled by the family kernels: 36 slots of t[7] (see rk_pipeline.cuh)
-             W_VLIST = 36, W_VLIST_SLOTS = 36, WS_SLOTS = 36 + 36 * 7 };
+             WS_SLOTS = 36,
+             // Step-1 candidate sub-lists: 36 slots per item in their own array of structures (Params::vl), slot = t[7] + duration
+             VL_SLOTS = 36, VL_SLOT_DOUBLES = 8, VL_ITEM_DOUBLES = 36 * 8 };
 // Step 2, VEL family: a chain item re-uses its own (no longer needed) sub-list area for the polynomial, the root brackets and
-// the polished roots that travel between the scan, polish and check kernels (slots relative to W_VLIST).
+// the polished roots that travel between the scan, polish and check kernels (double offsets into the item's vl area).
 enum : int { V_POL = 0, V_LO = 8, V_HI = 16, V_ROOT = 24, V_TZ = 32, V1_LO = 40, V1_HI = 48, V1_ROOT = 56 };
 // meta words per item: [0] flags below, [1..3] codes of the three block profiles
 enum : int { WM_META = 0, WM_CAND = 1, WM_WORDS = 4 };
