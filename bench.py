@@ -368,10 +368,13 @@ def run_b200(args):
                 "roofline": {"bound": "fp64", "achieved": achieved_tflops, "peak": fp64_peak_tflops, "unit": "TFLOP/s",
                              "frac": achieved_tflops / fp64_peak_tflops if fp64_peak_tflops else None,
                              "traffic": (ops.get("dram_bytes_per_trajectory") or 0) * n or None,
-                             "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum over the 27 kernels of one step (ncu, profiles/), per GPU",
-                             "kernels": "one step = k1_setup, k1_family<0..4>, k1_block, k_sync, k2_first, 17 x k2_stage, k2_fail per chunk of "
-                                        "4Mi (DoF, trajectory) items; the FP64 work is spread over the k1_family and k2_stage kernels, per-kernel "
-                                        "shares and ncu metrics in profiles/",
+                             "traffic_note": f"dram__bytes_read.sum + dram__bytes_write.sum over the {ops.get('kernel_launches_per_step', '?')} kernel launches of one step "
+                                             "(ncu, profiles/r1_ops_per_kernel.csv), per GPU; = "
+                                             f"{(ops.get('dram_bytes_per_trajectory') or 0) * per_gpu / 1e9:.0f} GB/s at the measured rate",
+                             "kernels": "one step per chunk of 4Mi (DoF, trajectory) items = k1_setup, 3 x (k1_quartic_roots, k1_quartic_check), "
+                                        "k1_closed_cands, k1_cand_check, k1_block, k1_rescue, k_sync, 18 chain stages (k2_stage<F>; VEL/UDDU as "
+                                        "k2_vel_scan_uddu + k2_polish + k2_vel_check_uddu, VEL/UDUD as k2_vel<8>), k2_fail, k_expand; no single kernel "
+                                        "holds more than 11 % of the step (profiles/r1_ncu_summary.md), so the roofline is quoted for the whole step",
                              "flop_per_trajectory": flop, "flop_how": flop_how,
                              "fp64_issue_frac": (ops.get("fp64_instructions") or 0) * per_gpu / (fp64_peak_tflops * 1e12 / 2) if fp64_peak_tflops else None,
                              "peak_how": "DFMA probe (rk_measure_fp64_peak) on this GPU before the timed region, FMA = 2 flop; the kernels run "

@@ -230,6 +230,9 @@ rk_status fail(rk_status s, const std::string& m) {
 #ifndef RK_LANES
 #define RK_LANES 2
 #endif
+#ifndef RK_STAGE_BUFS
+#define RK_STAGE_BUFS 4  // host-buffer calls: input chunks are copied this many chunks ahead of the kernels
+#endif
 constexpr int64_t CHUNK_ITEMS = (int64_t)RK_CHUNK_MI << 20;  // (DoF, trajectory) items per chunk of scratch: 4 Mi items = 8.4 GB of scratch
 
 }  // namespace
@@ -264,8 +267,8 @@ struct rk_handle {
     size_t stage_pinned_bytes = 0;
     // host-buffer calculate: input chunks are copied on a second stream while the previous chunk is computed
     cudaStream_t copy_stream = nullptr;
-    cudaEvent_t ev_copied[RK_LANES] = {}, ev_computed[RK_LANES] = {};
-    void* chunk_in[RK_LANES] = {};
+    cudaEvent_t ev_copied[RK_STAGE_BUFS] = {}, ev_computed[RK_STAGE_BUFS] = {};
+    void* chunk_in[RK_STAGE_BUFS] = {};
     size_t chunk_in_bytes = 0;
 };
 
@@ -399,7 +402,7 @@ rk_status rk_create(int32_t device, rk_handle** out) {
     for (int k = 1; k < RK_LANES; ++k) RK_CUDA(cudaStreamCreateWithFlags(&h->lane_stream[k], cudaStreamNonBlocking));
     RK_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
     for (int k = 0; k < RK_LANES; ++k) RK_CUDA(cudaEventCreateWithFlags(&h->ev_join[k], cudaEventDisableTiming));
-    for (int k = 0; k < RK_LANES; ++k) {
+    for (int k = 0; k < RK_STAGE_BUFS; ++k) {
         RK_CUDA(cudaEventCreateWithFlags(&h->ev_copied[k], cudaEventDisableTiming));
         RK_CUDA(cudaEventCreateWithFlags(&h->ev_computed[k], cudaEventDisableTiming));
     }
@@ -419,7 +422,7 @@ rk_status rk_destroy(rk_handle* h) {
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->stage_dev) cudaFree(h->stage_dev);
     if (h->stage_pinned) cudaFreeHost(h->stage_pinned);
-    for (int k = 0; k < RK_LANES; ++k) {
+    for (int k = 0; k < RK_STAGE_BUFS; ++k) {
         if (h->chunk_in[k]) cudaFree(h->chunk_in[k]);
         if (h->ev_copied[k]) cudaEventDestroy(h->ev_copied[k]);
         if (h->ev_computed[k]) cudaEventDestroy(h->ev_computed[k]);
@@ -496,12 +499,12 @@ rk_status rk_calculate_batch(rk_handle* h, const rk_batch_desc* desc, const rk_b
         if (host_ptrs.min_dur) bytes += sizeof(double) * (size_t)cn_max;
         if (host_ptrs.enabled) bytes += (((size_t)desc->dof * (size_t)cn_max + 255) / 256) * 256;
         if (bytes > h->chunk_in_bytes) {
-            for (int k = 0; k < RK_LANES; ++k) {
+            for (int k = 0; k < RK_STAGE_BUFS; ++k) {
                 if (h->chunk_in[k]) cudaFree(h->chunk_in[k]);
                 h->chunk_in[k] = nullptr;
             }
             h->chunk_in_bytes = 0;
-            for (int k = 0; k < RK_LANES; ++k) RK_CUDA(cudaMalloc(&h->chunk_in[k], bytes));
+            for (int k = 0; k < RK_STAGE_BUFS; ++k) RK_CUDA(cudaMalloc(&h->chunk_in[k], bytes));
             h->chunk_in_bytes = bytes;
         }
     }
@@ -516,9 +519,9 @@ rk_status rk_calculate_batch(rk_handle* h, const rk_batch_desc* desc, const rk_b
         P.ws = c.ws; P.rec = c.rec; P.vl = c.vl; P.wmeta = c.wmeta; P.wsrc = c.wsrc; P.wqmask = c.wqmask; P.rq_item = c.rq_item; P.rq_root = c.rq_root;
         P.list[0] = c.list[0]; P.list[1] = c.list[1]; P.pend = c.pend; P.counters = c.counters;
         if (host) {
-            const int buf = chunk_index % RK_LANES;
+            const int buf = chunk_index % RK_STAGE_BUFS;
             // the buffer may still be read by the chunk computed two iterations ago
-            if (chunk_index >= RK_LANES) RK_CUDA(cudaStreamWaitEvent(h->copy_stream, h->ev_computed[buf], 0));
+            if (chunk_index >= RK_STAGE_BUFS) RK_CUDA(cudaStreamWaitEvent(h->copy_stream, h->ev_computed[buf], 0));
             char* dev = (char*)h->chunk_in[buf];
             const size_t per = sizeof(double) * (size_t)desc->dof * (size_t)P.cn;
             for (auto m : dslots) {
@@ -570,7 +573,7 @@ rk_status rk_calculate_batch(rk_handle* h, const rk_batch_desc* desc, const rk_b
                 case 0: rk::k2_stage<0><<<grid_list, 128, 0, cs>>>(P, step, dir2[step]); break;
                 case 1:
                     rk::k2_vel_scan_uddu<<<grid_vel, RK_LS_BLOCK, 0, cs>>>(P, step, dir2[step]);
-                    rk::k2_polish<6, false><<<grid_list, 128, 0, cs>>>(P, 33 + 2 * step);
+                    rk::k2_polish<6, false><<<(unsigned)h->sm_count * 8u, 128, 0, cs>>>(P, 33 + 4 * step, 34 + 4 * step);
                     rk::k2_vel_check_uddu<<<grid_list, 128, 0, cs>>>(P, step, dir2[step]);
                     h->launches += 2;
                     break;
@@ -586,7 +589,7 @@ rk_status rk_calculate_batch(rk_handle* h, const rk_batch_desc* desc, const rk_b
         rk::k2_fail<<<(unsigned)h->sm_count, 128, 0, cs>>>(P);
         rk::k_expand<<<grid_items, 128, 0, cs>>>(P);
         h->launches += 14 + RK_S2_STEPS;
-        if (host) RK_CUDA(cudaEventRecord(h->ev_computed[chunk_index % RK_LANES], cs));
+        if (host) RK_CUDA(cudaEventRecord(h->ev_computed[chunk_index % RK_STAGE_BUFS], cs));
     }
     for (int k = 1; k < lanes; ++k) {
         RK_CUDA(cudaEventRecord(h->ev_join[k], h->lane_stream[k]));

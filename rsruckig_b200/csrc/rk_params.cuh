@@ -9,7 +9,7 @@
 
 namespace rk {
 
-#define RK_N_COUNTERS 72
+#define RK_N_COUNTERS 112
 
 struct Params {
     int64_t n;        // trajectories in the batch (stride of the trajectory storage)

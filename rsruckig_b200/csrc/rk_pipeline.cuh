@@ -73,7 +73,10 @@ __device__ __forceinline__ void append_unsolved(uint32_t* list, uint32_t* counte
 }
 
 // ------------------------------------------------------------------------------------------------ k1_setup
-__global__ void __launch_bounds__(128) k1_setup(const Params P) {
+#ifndef RK_SU_MINB
+#define RK_SU_MINB 4
+#endif
+__global__ void __launch_bounds__(128, RK_SU_MINB) k1_setup(const Params P) {
     const int64_t wstride = (int64_t)P.dof * P.cn;
     const int64_t wi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (wi >= wstride) return;
@@ -867,7 +870,10 @@ __device__ __forceinline__ void sync_trajectory(const Params& P, int64_t il, uin
 
 // One thread per trajectory. After the decision every (DoF, trajectory) item is queued for the kernel that finishes it:
 // third-order position items that need the Step-2 chain go to list[0] (stage 0 reads it); k_expand finishes all items.
-__global__ void __launch_bounds__(128) k_sync(const Params P) {
+#ifndef RK_SY_MINB
+#define RK_SY_MINB 8
+#endif
+__global__ void __launch_bounds__(128, RK_SY_MINB) k_sync(const Params P) {
     const int64_t il = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = il < P.cn;
     uint32_t pm[RK_MAX_DOF];
@@ -1027,7 +1033,7 @@ __global__ void __launch_bounds__(RK_LS_BLOCK, RK_LS_MINB) k2_vel(const Params P
 //   k2_polish<N>   one lane per task, and a lane that has converged takes the next task while its neighbours keep
 //                  iterating (refill in batches), so the iteration runs with nearly full warps.
 //   k2_vel_check   pending items: candidates in order, root -> Newton step -> profile check; first pass wins.
-// Counters: [step + 1] the next list as before, [32 + 2 * step] pending items, [33 + 2 * step] polish tasks.
+// Counters: [step + 1] the next list as before, [32 + 4 * step + {0, 1, 2}] = pending items, polish tasks, polish cursor.
 __device__ __forceinline__ double* vslot(const Params& P, int64_t wi, int64_t wstride, int slot) {
     (void)wstride;
     return P.vl + wi * VL_ITEM_DOUBLES + slot;
@@ -1072,8 +1078,8 @@ __global__ void __launch_bounds__(RK_LS_BLOCK, RK_LS_MINB) k2_vel_scan_uddu(cons
             P.wqmask[wi] = (uint32_t)n_cand;
         }
         append_unsolved(list_out, P.counters + step + 1, active && !found && n_cand == 0, wi);
-        append_unsolved(P.pend, P.counters + 32 + 2 * step, pending, wi);
-        uint32_t e = warp_reserve(P.counters + 33 + 2 * step, n_task);
+        append_unsolved(P.pend, P.counters + 32 + 4 * step, pending, wi);
+        uint32_t e = warp_reserve(P.counters + 33 + 4 * step, n_task);
         if (pending) {
 #pragma unroll
             for (int c = 0; c < 6; ++c)
@@ -1084,23 +1090,32 @@ __global__ void __launch_bounds__(RK_LS_BLOCK, RK_LS_MINB) k2_vel_scan_uddu(cons
 
 // Polish queue: task (item, c) = bracket [lo[c], hi[c]] of the item's monic polynomial of N coefficients (DERIV: of its monic
 // derivative, the first pass of the UDUD half, slots V1_*). Result: root[c].
+#ifndef RK_REFILL
+#define RK_REFILL 16
+#endif
 template <int N, bool DERIV>
-__global__ void __launch_bounds__(128, 8) k2_polish(const Params P, int counter_index) {
+__global__ void __launch_bounds__(128, 8) k2_polish(const Params P, int counter_index, int cursor_index) {
     const int64_t wstride = (int64_t)P.dof * P.cn;
     const uint32_t count = P.counters[counter_index];
-    const uint32_t stride = gridDim.x * blockDim.x;
-    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t* cursor = P.counters + cursor_index;  // tasks are claimed dynamically: the lanes of the whole grid stay balanced
+    const int lane = threadIdx.x & 31;
     ShrinkState<N> st;
-    bool have = false;
+    bool have = false, exhausted = false;
     double* out = nullptr;
     while (true) {
-        const bool want = !have && k < count;
+        const bool want = !have && !exhausted;
         const unsigned wanting = __ballot_sync(0xffffffffu, want);
         const unsigned busy = __ballot_sync(0xffffffffu, have);
         if (wanting == 0 && busy == 0) break;
         // refill in batches: a quarter of the warp idle, or nobody iterating
-        if (wanting != 0 && (__popc(wanting) >= 8 || busy == 0)) {
-            if (want) {
+        if (wanting != 0 && (__popc(wanting) >= RK_REFILL || busy == 0)) {
+            uint32_t base = 0;
+            const int leader = __ffs(wanting) - 1;
+            if (lane == leader) base = atomicAdd(cursor, (uint32_t)__popc(wanting));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            const uint32_t k = base + (uint32_t)__popc(wanting & ((1u << lane) - 1u));
+            if (want && k >= count) exhausted = true;
+            if (want && k < count) {
                 const uint2 task = P.rq_item[k];
                 const int64_t wi = task.x;
                 const int c = (int)task.y;
@@ -1118,14 +1133,13 @@ __global__ void __launch_bounds__(128, 8) k2_polish(const Params P, int counter_
                 const double lo = *vslot(P, wi, wstride, (DERIV ? V1_LO : V_LO) + c);
                 const double hi = *vslot(P, wi, wstride, (DERIV ? V1_HI : V_HI) + c);
                 out = vslot(P, wi, wstride, (DERIV ? V1_ROOT : V_ROOT) + c);
-                if (st.start(lo, hi)) { *out = st.rts; k += stride; }
+                if (st.start(lo, hi)) *out = st.rts;
                 else have = true;
             }
         }
         if (have && st.step()) {
             *out = st.rts;
             have = false;
-            k += stride;
         }
     }
 }
@@ -1133,7 +1147,7 @@ __global__ void __launch_bounds__(128, 8) k2_polish(const Params P, int counter_
 __global__ void __launch_bounds__(128, 6) k2_vel_check_uddu(const Params P, int step, int second_dir) {
     const int64_t wstride = (int64_t)P.dof * P.cn;
     uint32_t* list_out = P.list[(step + 1) & 1];
-    const uint32_t count = P.counters[32 + 2 * step];
+    const uint32_t count = P.counters[32 + 4 * step];
     const bool second_direction = second_dir != 0;
     const uint32_t stride = gridDim.x * blockDim.x;
     const uint32_t rounds = (count + stride - 1) / stride;
@@ -1181,7 +1195,10 @@ __global__ void __launch_bounds__(128) k2_fail(const Params P) {
 // arrays the reference's check functions leave behind (profile.rs:76-118) and stored. Dense and coalesced: a warp writes 59
 // full 256-byte rows. The cheap non-third-order Step 2 variants are solved right here.
 #define RK_SRC_FAILED 0xFF
-__global__ void __launch_bounds__(128) k_expand(const Params P) {
+#ifndef RK_EX_MINB
+#define RK_EX_MINB 1
+#endif
+__global__ void __launch_bounds__(128, RK_EX_MINB) k_expand(const Params P) {
     const int64_t wstride = (int64_t)P.dof * P.cn;
     {
         const int64_t wi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -1,0 +1,15 @@
+"""Pinned host -> device copy bandwidth of this box (context for the e2e number)."""
+import torch
+n = 1 << 30
+h = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+d = torch.empty(n, dtype=torch.uint8, device="cuda")
+for _ in range(2):
+    d.copy_(h, non_blocking=True)
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(5):
+    d.copy_(h, non_blocking=True)
+e1.record()
+torch.cuda.synchronize()
+print(f"H2D pinned: {5 * n / (e0.elapsed_time(e1) * 1e-3) / 1e9:.1f} GB/s")
