@@ -415,9 +415,9 @@ __device__ __forceinline__ int solve_resolvent(double (&x)[3], double a, double 
     const double q3 = q * q * q;
     if (r2 < q3) {
         const double q_sqrt = sqrt(q);
-        const double t = rmax(rmin(r / (q * q_sqrt), 1.0), -1.0);
+        const double t = rmax(rmin(sdiv(r, q * q_sqrt), 1.0), -1.0);
         q = -2.0 * q_sqrt;
-        const double theta = m_acos(t) / 3.0;
+        const double theta = sdiv(m_acos(t), 3.0);  // acos(1) = 0 is common after the clamp
         double sn, cs;
         m_sincos(theta, sn, cs);
         const double ux = cs * q;

@@ -215,72 +215,84 @@ struct Step1Pos3 {
         const real v0 = b.v0, a0 = b.a0, vf = b.vf, af = b.af;
         const Den v_max = L.v_max, a_max = L.a_max, a_min = L.a_min, j_max = L.j_max;
         double t[7];
+        // A variant whose cheap durations are already negative (or NaN: t_acc0 / t_acc1 are square roots) fails the profile
+        // check whatever t[3] is, so the long t[3] expression is only evaluated for the others — with NaN operands it
+        // would also take the slow path of its division.
+        auto rest_ok = [&]() { return t[0] >= 0.0 && t[1] >= 0.0 && t[2] >= 0.0 && t[4] >= 0.0 && t[5] >= 0.0 && t[6] >= 0.0; };
         // ACC0_ACC1_VEL
         t[0] = (-a0 + a_max) / j_max;
         t[1] = (a0_a0 / 2.0 - a_max * a_max - j_max * (v0 - v_max)) / (a_max * j_max);
         t[2] = a_max / j_max;
-        t[3] = (3.0 * (a0_p4 * a_min - af_p4 * a_max)
-                + 8.0 * a_max * a_min * (af_p3 - a0_p3 + 3.0 * j_max * (a0 * v0 - af * vf))
-                + 6.0 * a0_a0 * a_min * (a_max * a_max - 2.0 * j_max * v0)
-                - 6.0 * af_af * a_max * (a_min * a_min - 2.0 * j_max * vf)
-                - 12.0 * j_max * (a_max * a_min * (a_max * (v0 + v_max) - a_min * (vf + v_max) - 2.0 * j_max * pd)
-                                  + (a_min - a_max) * j_max * v_max * v_max
-                                  + j_max * (a_max * vf_vf - a_min * v0_v0)))
-               / (24.0 * a_max * a_min * jj * v_max);
         t[4] = -a_min / j_max;
         t[5] = -(af_af / 2.0 - a_min * a_min - j_max * (vf - v_max)) / (a_min * j_max);
         t[6] = t[4] + af / j_max;
-        set_variant(0);
-        if (emit(t, L_VEL, L)) return;
+        if (rest_ok()) {
+            t[3] = (3.0 * (a0_p4 * a_min - af_p4 * a_max)
+                    + 8.0 * a_max * a_min * (af_p3 - a0_p3 + 3.0 * j_max * (a0 * v0 - af * vf))
+                    + 6.0 * a0_a0 * a_min * (a_max * a_max - 2.0 * j_max * v0)
+                    - 6.0 * af_af * a_max * (a_min * a_min - 2.0 * j_max * vf)
+                    - 12.0 * j_max * (a_max * a_min * (a_max * (v0 + v_max) - a_min * (vf + v_max) - 2.0 * j_max * pd)
+                                      + (a_min - a_max) * j_max * v_max * v_max
+                                      + j_max * (a_max * vf_vf - a_min * v0_v0)))
+                   / (24.0 * a_max * a_min * jj * v_max);
+            set_variant(0);
+            if (emit(t, L_VEL, L)) return;
+        }
 
         // ACC1_VEL (t[4..6] carry over)
         const real t_acc0 = sqrt(a0_a0 / (2.0 * jj) + (v_max - v0) / j_max);
         t[0] = t_acc0 - a0 / j_max;
         t[1] = 0.0;
         t[2] = t_acc0;
-        t[3] = -(3.0 * af_p4
-                 - 8.0 * a_min * (af_p3 - a0_p3)
-                 - 24.0 * a_min * j_max * (a0 * v0 - af * vf)
-                 + 6.0 * af_af * (a_min * a_min - 2.0 * j_max * vf)
-                 - 12.0 * j_max * (2.0 * a_min * j_max * pd
-                                   + a_min * a_min * (vf + v_max)
-                                   + j_max * (v_max * v_max - vf_vf)
-                                   + a_min * t_acc0 * (a0_a0 - 2.0 * j_max * (v0 + v_max))))
-               / (24.0 * a_min * jj * v_max);
-        set_variant(1);
-        if (emit(t, L_VEL, L)) return;
+        if (rest_ok()) {
+            t[3] = -(3.0 * af_p4
+                     - 8.0 * a_min * (af_p3 - a0_p3)
+                     - 24.0 * a_min * j_max * (a0 * v0 - af * vf)
+                     + 6.0 * af_af * (a_min * a_min - 2.0 * j_max * vf)
+                     - 12.0 * j_max * (2.0 * a_min * j_max * pd
+                                       + a_min * a_min * (vf + v_max)
+                                       + j_max * (v_max * v_max - vf_vf)
+                                       + a_min * t_acc0 * (a0_a0 - 2.0 * j_max * (v0 + v_max))))
+                   / (24.0 * a_min * jj * v_max);
+            set_variant(1);
+            if (emit(t, L_VEL, L)) return;
+        }
 
         // ACC0_VEL
         const real t_acc1 = sqrt(af_af / (2.0 * jj) + (v_max - vf) / j_max);
         t[0] = (-a0 + a_max) / j_max;
         t[1] = (a0_a0 / 2.0 - a_max * a_max - j_max * (v0 - v_max)) / (a_max * j_max);
         t[2] = a_max / j_max;
-        t[3] = (3.0 * a0_p4
-                + 8.0 * a_max * (af_p3 - a0_p3)
-                + 24.0 * a_max * j_max * (a0 * v0 - af * vf)
-                + 6.0 * a0_a0 * (a_max * a_max - 2.0 * j_max * v0)
-                - 12.0 * j_max * (-2.0 * a_max * j_max * pd
-                                  + a_max * a_max * (v0 + v_max)
-                                  + j_max * (v_max * v_max - v0_v0)
-                                  + a_max * t_acc1 * (-af_af + 2.0 * (vf + v_max) * j_max)))
-               / (24.0 * a_max * jj * v_max);
         t[4] = t_acc1;
         t[5] = 0.0;
         t[6] = t_acc1 + af / j_max;
-        set_variant(2);
-        if (emit(t, L_VEL, L)) return;
+        if (rest_ok()) {
+            t[3] = (3.0 * a0_p4
+                    + 8.0 * a_max * (af_p3 - a0_p3)
+                    + 24.0 * a_max * j_max * (a0 * v0 - af * vf)
+                    + 6.0 * a0_a0 * (a_max * a_max - 2.0 * j_max * v0)
+                    - 12.0 * j_max * (-2.0 * a_max * j_max * pd
+                                      + a_max * a_max * (v0 + v_max)
+                                      + j_max * (v_max * v_max - v0_v0)
+                                      + a_max * t_acc1 * (-af_af + 2.0 * (vf + v_max) * j_max)))
+                   / (24.0 * a_max * jj * v_max);
+            set_variant(2);
+            if (emit(t, L_VEL, L)) return;
+        }
 
         // VEL (t[4..6] carry over)
         t[0] = t_acc0 - a0 / j_max;
         t[1] = 0.0;
         t[2] = t_acc0;
-        t[3] = (af_p3 - a0_p3) / (3.0 * jj * v_max)
-               + (a0 * v0 - af * vf + (af_af * t_acc1 + a0_a0 * t_acc0) / 2.0) / (j_max * v_max)
-               - (v0 / v_max + 1.0) * t_acc0
-               - (vf / v_max + 1.0) * t_acc1
-               + pd / v_max;
-        set_variant(3);
-        emit(t, L_VEL, L);
+        if (rest_ok()) {
+            t[3] = (af_p3 - a0_p3) / (3.0 * jj * v_max)
+                   + (a0 * v0 - af * vf + (af_af * t_acc1 + a0_a0 * t_acc0) / 2.0) / (j_max * v_max)
+                   - (v0 / v_max + 1.0) * t_acc0
+                   - (vf / v_max + 1.0) * t_acc1
+                   + pd / v_max;
+            set_variant(3);
+            emit(t, L_VEL, L);
+        }
     }
 
     // position_third_step1.rs:241-327

@@ -18,17 +18,20 @@ __device__ __forceinline__ bool vel_uddu_root(const S2& s, const Lim& L, Hit& h,
     // Single Newton step (regarding pd)
     {
         const real h1 = sqrt((a0_a0 + af_af) / (2.0 * j_max_j_max) + (2.0 * a0 * tt + j_max * tt * tt - vd) / j_max);
-        const real orig = -pd
-                            - (2.0 * a0_p3 + 4.0 * af_p3 + 24.0 * a0 * j_max * tt * (af + j_max * (h1 + tt - tf)) + 6.0 * a0_a0 * (af + j_max * (2.0 * tt - tf))
-                               + 6.0 * (a0_a0 + af_af) * j_max * h1 + 12.0 * af * j_max * (j_max * tt * tt - vd)
-                               + 12.0 * j_max_j_max * (j_max * tt * tt * (h1 + tt - tf) - tf * v0 - h1 * vd))
-                                  / (12.0 * j_max_j_max);
-        const real deriv_newton = -(a0 + j_max * tt) * (3.0 * (h1 + tt) - 2.0 * tf + (a0 + 2.0 * af) / j_max);
-        if (!(orig != orig) && !(deriv_newton != deriv_newton) && fabs(deriv_newton) > EPS) tt -= orig / deriv_newton;
+        if (h1 == h1) {  // a NaN h1 makes orig NaN and the reference's guard below skips the step: skip the arithmetic as well
+            const real orig = -pd
+                                - (2.0 * a0_p3 + 4.0 * af_p3 + 24.0 * a0 * j_max * tt * (af + j_max * (h1 + tt - tf)) + 6.0 * a0_a0 * (af + j_max * (2.0 * tt - tf))
+                                   + 6.0 * (a0_a0 + af_af) * j_max * h1 + 12.0 * af * j_max * (j_max * tt * tt - vd)
+                                   + 12.0 * j_max_j_max * (j_max * tt * tt * (h1 + tt - tf) - tf * v0 - h1 * vd))
+                                      / (12.0 * j_max_j_max);
+            const real deriv_newton = -(a0 + j_max * tt) * (3.0 * (h1 + tt) - 2.0 * tf + (a0 + 2.0 * af) / j_max);
+            if (!(orig != orig) && !(deriv_newton != deriv_newton) && fabs(deriv_newton) > EPS) tt -= orig / deriv_newton;
+        }
     }
     if (tt > tf || tt != tt) return false;
 
     const real h1 = sqrt((a0_a0 + af_af) / (2.0 * j_max_j_max) + (tt * (2.0 * a0 + j_max * tt) - vd) / j_max);
+    if (h1 != h1) return false;  // t[4] = NaN fails the profile check
     t[0] = tt;
     t[1] = 0.0;
     t[2] = tt + a0 / j_max;
@@ -46,6 +49,7 @@ __device__ __forceinline__ bool vel_udud_root(const S2& s, const Lim& L, Hit& h,
     // Double Newton step (regarding pd)
     {
         real h1 = sqrt((af_af - a0_a0) / (2.0 * j_max_j_max) - ((2.0 * a0 + j_max * tt) * tt - vd) / j_max);
+        if (h1 != h1) return false;  // NaN poisons tt and with it every duration: the check fails
         real orig = -pd + (af_p3 - a0_p3 + 3.0 * a0_a0 * j_max * (tf - 2.0 * tt)) / (6.0 * j_max_j_max) + (2.0 * a0 + j_max * tt) * tt * (tf - tt)
                       + (j_max * h1 - af) * h1 * h1 + tf * v0;
         real deriv_newton = (a0 + j_max * tt) * (2.0 * (af + j_max * tf) - 3.0 * j_max * (h1 + tt) - a0) / j_max;
