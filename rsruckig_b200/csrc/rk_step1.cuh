@@ -214,7 +214,7 @@ struct Step1Pos3 {
     __device__ __forceinline__ void family_vel(const Lim& L) {
         const real v0 = b.v0, a0 = b.a0, vf = b.vf, af = b.af;
         const Den v_max = L.v_max, a_max = L.a_max, a_min = L.a_min, j_max = L.j_max;
-        double t[7];
+        double t[7] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
         // A variant whose cheap durations are already negative (or NaN: t_acc0 / t_acc1 are square roots) fails the profile
         // check whatever t[3] is, so the long t[3] expression is only evaluated for the others — with NaN operands it
         // would also take the slow path of its division.
