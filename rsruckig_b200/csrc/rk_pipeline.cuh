@@ -640,7 +640,7 @@ __device__ __forceinline__ void sync_trajectory(const Params& P, int64_t il, uin
     bool done = status != 0;
     if (!done && D == 1 && !has_md && !P.discrete) {  // :475-481
         duration = WS(W_TMIN, 0);
-        if (META(0) & M_ENABLED) SRC(0) = RK_SRC_STEP1_MIN;
+        SRC(0) = RK_SRC_STEP1_MIN;  // also for a disabled DoF: the reference copies blocks[0].p_min unconditionally (:478)
         done = true;
     }
 
@@ -722,7 +722,7 @@ __device__ __forceinline__ void sync_trajectory(const Params& P, int64_t il, uin
                 status = RK_RESULT_ERROR_TRAJECTORY_DURATION;
                 done = true;
             } else if (fabs(duration - 0.0) < EPS) {  // :535-541
-                for (int d = 0; d < D; ++d) SRC(d) = (META(d) & M_ENABLED) ? RK_SRC_STEP1_MIN : RK_SRC_NONE;
+                for (int d = 0; d < D; ++d) SRC(d) = RK_SRC_STEP1_MIN;  // every DoF, disabled ones included (:537-539)
                 done = true;
             } else {
                 bool all_none = true, any_phase = false, all_phase_or_none = true;
@@ -1213,6 +1213,14 @@ __global__ void __launch_bounds__(128, RK_EX_MINB) k_expand(const Params P) {
             const int64_t g = (int64_t)it.d * P.in_n + (it.ig + P.in_shift);
             store_idle_profile(out, P.p0[g], P.v0[g], P.a0[g]);
             P.codes[it.gi] = pack_codes(L_NONE, UDDU, DIR_UP, RK_SRC_NONE);
+            return;
+        }
+        if (!(meta & M_ENABLED)) {
+            // A disabled DoF whose profile the reference overwrites with its block's p_min (zero duration :535-541, the
+            // single-DoF shortcut :475-481, a disabled limiting DoF): the block of a disabled DoF on a fresh calculator holds
+            // Profile::default().
+            store_idle_profile(out, 0.0, 0.0, 0.0);
+            P.codes[it.gi] = pack_codes(L_NONE, UDDU, DIR_UP, src);
             return;
         }
         if (src == RK_SRC_FAILED) {  // k2_fail has set the status and the code word

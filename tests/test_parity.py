@@ -106,6 +106,29 @@ def test_edge_cases_exact(gpu):
         assert_exact(otg, ob, label=f"edge mode {mode}")
 
 
+def test_disabled_dofs_in_zero_duration_and_single_dof_trajectories_exact(gpu):
+    """calculator_target.rs:475-481 and :535-541 copy blocks[dof].p_min into the trajectory for EVERY DoF, disabled ones
+    included, when the trajectory has a single DoF or zero duration — a disabled DoF then holds Profile::default() instead
+    of the current state that :313-323 had put there (found by tools/parity_sweep.py, seed 16)."""
+    n, dof = 4096, 4
+    f = workloads.edge_case_inputs(n, dof, seed=16)
+    f["enabled"][:, ::3] = 0                      # every third trajectory: all DoFs disabled -> duration 0
+    at_target = slice(1, None, 3)                 # every third: already at the target, one DoF disabled -> duration 0
+    for k in ("velocity", "acceleration"):
+        f[f"current_{k}"][:, at_target] = 0.0
+        f[f"target_{k}"][:, at_target] = 0.0
+    f["target_position"][:, at_target] = f["current_position"][:, at_target]
+    f["enabled"][:, at_target] = 1
+    f["enabled"][2, at_target] = 0
+    otg, ob = run_both(gpu, f, n, dof)
+    assert assert_exact(otg, ob, label="zero duration, disabled DoFs") > n // 2
+    assert np.all(ob.read(cabi.RK_FIELD_DURATION)[::3] == 0.0)
+    f1 = workloads.edge_case_inputs(n, 1, seed=17)
+    f1["enabled"][0, ::2] = 0
+    otg, ob = run_both(gpu, f1, n, 1)
+    assert_exact(otg, ob, label="single DoF, disabled")
+
+
 def test_config3_velocity_phase_minimum_duration_discrete_exact(gpu):
     """BASELINE.json configs[2]: 3-DoF velocity interface + Phase synchronisation, thirds of the batch with no extra /
     minimum_duration / (separately) Discrete durations."""
