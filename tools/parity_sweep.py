@@ -32,5 +32,56 @@ for seed in range(10, 10 + int(sys.argv[1]) if len(sys.argv) > 1 else 18):
     otg, ob = run_both(BatchRuckig, f, 50_000, 4, threads=16)
     total += assert_exact(otg, ob, label=f"edge seed {seed}")
     del otg, ob
+    # configs[2]: velocity interface + Phase, minimum_duration on a third, continuous and discrete durations
+    from rsruckig_b200 import ControlInterface, DurationDiscretization, Synchronization
+    n = 100_000
+    f = workloads.config3_inputs(n, seed=seed)
+    md = np.full(n, np.nan)
+    rng = np.random.default_rng(seed)
+    third = np.arange(n) % 3 == 1
+    md[third] = rng.uniform(0.5, 8.0, int(third.sum()))
+    f["minimum_duration"] = md
+    for disc in (DurationDiscretization.Continuous, DurationDiscretization.Discrete):
+        otg, ob = run_both(BatchRuckig, f, n, 3, threads=16, control_interface=ControlInterface.Velocity, synchronization=Synchronization.Phase,
+                           duration_discretization=disc)
+        total += assert_exact(otg, ob, label=f"config3 disc={int(disc)} seed {seed}")
+        del otg, ob
+    # position interface: Phase with a collinear quarter, mixed per-DoF settings, edge cases with Phase / both handlers
+    f = workloads.bench_inputs(n, 3, seed=seed)
+    col = np.arange(n) % 4 == 0
+    scale = rng.uniform(0.25, 2.0, (3, n))
+    scale[0] = 1.0
+    pd = f["target_position"] - f["current_position"]
+    f["target_position"][:, col] = (f["current_position"] + pd[0:1] * scale)[:, col]
+    for k in ("current_velocity", "current_acceleration", "target_velocity", "target_acceleration", "max_velocity", "max_acceleration", "max_jerk"):
+        f[k][:, col] = (f[k][0:1] * scale)[:, col]
+    otg, ob = run_both(BatchRuckig, f, n, 3, threads=16, synchronization=Synchronization.Phase)
+    total += assert_exact(otg, ob, label=f"phase seed {seed}")
+    del otg, ob
+    otg, ob = run_both(BatchRuckig, f, n, 3, threads=16,
+                       per_dof_synchronization=[Synchronization.Phase, Synchronization.None_, Synchronization.TimeIfNecessary],
+                       per_dof_control_interface=[ControlInterface.Position, ControlInterface.Velocity, ControlInterface.Position])
+    total += assert_exact(otg, ob, label=f"mixed seed {seed}")
+    del otg, ob
+    f = workloads.edge_case_inputs(50_000, 5, seed=100 + seed)
+    for sync in (Synchronization.Phase, Synchronization.TimeIfNecessary, Synchronization.None_):
+        otg, ob = run_both(BatchRuckig, f, 50_000, 5, threads=16, synchronization=sync, error_mode=1)
+        total += assert_exact(otg, ob, label=f"edge sync={int(sync)} ignore-errors seed {seed}")
+        del otg, ob
+    # second and first order
+    f = workloads.bench_inputs(n, 3, seed=200 + seed)
+    f["max_jerk"][:] = np.inf
+    f["current_acceleration"][:] = 0.0
+    f["target_acceleration"][:] = 0.0
+    for ci in (ControlInterface.Position, ControlInterface.Velocity):
+        otg, ob = run_both(BatchRuckig, f, n, 3, threads=16, control_interface=ci)
+        total += assert_exact(otg, ob, label=f"second order ci={int(ci)} seed {seed}")
+        del otg, ob
+    f["max_acceleration"][:] = np.inf
+    f["current_velocity"][:] = 0.0
+    f["target_velocity"][:] = 0.0
+    otg, ob = run_both(BatchRuckig, f, n, 3, threads=16)
+    total += assert_exact(otg, ob, label=f"first order seed {seed}")
+    del otg, ob
     print(f"seed {seed} ok, {total} Working trajectories compared so far, {time.time() - t0:.0f} s", flush=True)
 print(f"PARITY SWEEP OK: {total} trajectories bit-identical (status, duration, limiting DoF, codes, all profile arrays)")
