@@ -58,6 +58,14 @@ struct SampleParams {
 };
 
 // trajectory.rs:52-189 for K sample times; time accumulates by repeated addition (ruckig.rs:293).
+//
+// Sample times only grow, so a thread spends long runs of samples inside one segment of its profile (one of the seven
+// phases, the rest after its own end, the rest after the trajectory's end). The state to integrate from and the offsets to
+// subtract live in registers per segment; a sample first re-evaluates the reference's own conditions for STAYING in the
+// segment (three compares) and only falls back to the general search of trajectory.rs:60-140 when one of them fails. The
+// first version ran the general search for every sample: 186 instructions per sample, 84 % of the issue slots busy at
+// 3.2 TB/s; this form is bound by the output stream.
+template <bool PVA_ONLY>  // true: position, velocity and acceleration are all requested, jerk and section are not
 __global__ void __launch_bounds__(256) k_at_time(const SampleParams S) {
     const int64_t total = (int64_t)S.dof * S.n;
     const int64_t gi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -72,13 +80,19 @@ __global__ void __launch_bounds__(256) k_at_time(const SampleParams S) {
     const double p7 = q[(int64_t)(S_P + 7) * st], v7 = q[(int64_t)(S_V + 7) * st], a7 = q[(int64_t)(S_A + 7) * st];
     const double bdur = q[(int64_t)S_BRAKE_DUR * st];
     const double bt0 = q[(int64_t)S_BRAKE_T * st];
+    double bsub = (bdur > 0.0) ? bdur : 0.0;  // x - 0.0 == x: the reference subtracts bdur only if it is positive
+    const double end_off = bdur + ts6;
+    const Den six(6.0);                       // integrate() divides t * j by 6: one refined reciprocal for all samples
 
-    // Sample times only grow, so the phase index of trajectory.rs:134-140 ("first i with t_sum[i] > t", default 6) only
-    // grows too: the current phase lives in registers and is re-read from HBM (L2) only when a sample crosses its end.
+    // profile phase `index` ("first i with t_sum[i] > t", default 6, trajectory.rs:134-140; only grows)
     int index = 0;
     double t_hi = q[(int64_t)(S_TSUM + 0) * st];  // t_sum[index]
-    double t_lo = 0.0;                            // t_sum[index - 1]
-    double cp = q[(int64_t)(S_P + 0) * st], cv = q[(int64_t)(S_V + 0) * st], ca = q[(int64_t)(S_A + 0) * st], cj = q[(int64_t)(S_J + 0) * st];
+    double lsub = 0.0;                            // t_sum[index - 1] if index > 0 (else nothing is subtracted: 0.0)
+
+    enum { SEG_SEARCH = 0, SEG_PHASE = 1, SEG_OWN_END = 2, SEG_END = 3 };
+    int seg = SEG_SEARCH;
+    double sp = 0.0, sv = 0.0, sa = 0.0, sj = 0.0;  // state the current segment integrates from
+    int section = 0;
 
     // blockIdx.y picks a slice of the K sample times; the time of sample k is k + 1 repeated additions of delta_time
     // (ruckig.rs:293), so a slice first replays the additions of the samples before it (no memory traffic).
@@ -87,56 +101,89 @@ __global__ void __launch_bounds__(256) k_at_time(const SampleParams S) {
     double time = S.time_start;
 #pragma unroll 1
     for (int k = 0; k < k_begin; ++k) time += S.delta_time;
+    int64_t stride = total * (int64_t)sizeof(double);
+    asm volatile("" : "+l"(stride), "+d"(bsub));  // keep both in registers: the compiler otherwise rebuilds them per sample
+    const int64_t o0 = (int64_t)k_begin * total + gi;
+    char* out_p = S.pos ? (char*)(S.pos + o0) : nullptr;
+    char* out_v = S.vel ? (char*)(S.vel + o0) : nullptr;
+    char* out_a = S.acc ? (char*)(S.acc + o0) : nullptr;
+    char* out_j = S.jerk ? (char*)(S.jerk + o0) : nullptr;
+    int32_t* out_s = (S.section && d == 0) ? S.section + (int64_t)k_begin * S.n + i : nullptr;
 #pragma unroll 1
     for (int k = k_begin; k < k_end; ++k) {
         time += S.delta_time;
-        double t0, p0, v0, a0, j0;
-        int section;
-        if (time >= duration) {  // :60-83
-            section = 1;
-            t0 = time - (bdur + ts6);
-            p0 = p7; v0 = v7; a0 = a7; j0 = 0.0;
-        } else {
-            // cumulative_times[0] == duration > time, so the section index is 0 and t_diff == time (:85-99, Q13)
-            section = 0;
-            double td = time;
-            bool set = false;
-            if (bdur > 0.0) {
-                if (td < bdur) {  // brake pre-trajectory (:103-121)
-                    const int bi = (td < bt0) ? 0 : 1;
-                    if (bi > 0) td -= bt0;
-                    t0 = td;
-                    p0 = q[(int64_t)(S_BRAKE_P + bi) * st]; v0 = q[(int64_t)(S_BRAKE_V + bi) * st];
-                    a0 = q[(int64_t)(S_BRAKE_A + bi) * st]; j0 = q[(int64_t)(S_BRAKE_J + bi) * st];
-                    set = true;
-                } else {
-                    td -= bdur;
-                }
-            }
-            if (!set) {
-                if (td >= ts6) {  // past this DoF's own end (:122-132)
-                    t0 = td - ts6; p0 = p7; v0 = v7; a0 = a7; j0 = 0.0;
-                } else {
-                    while (index < 6 && !(t_hi > td)) {
-                        ++index;
-                        t_lo = t_hi;
-                        t_hi = q[(int64_t)(S_TSUM + index) * st];
-                        cp = q[(int64_t)(S_P + index) * st]; cv = q[(int64_t)(S_V + index) * st];
-                        ca = q[(int64_t)(S_A + index) * st]; cj = q[(int64_t)(S_J + index) * st];
+        double t0 = 0.0;
+        bool stay = false;
+        if (seg == SEG_END) {  // time >= duration holds from here on (:60-83)
+            t0 = time - end_off;
+            stay = true;
+        } else if (seg != SEG_SEARCH && !(time >= duration)) {
+            const double td = time - bsub;  // the brake pre-trajectory is behind us (td >= bdur held and time grows)
+            if (seg == SEG_OWN_END) { t0 = td - ts6; stay = true; }               // td >= ts6 held and td grows (:122-132)
+            else if (!(td >= ts6) && t_hi > td) { t0 = td - lsub; stay = true; }   // still inside phase `index`
+        }
+        if (!stay) {
+            if (time >= duration) {  // :60-83
+                section = 1;
+                seg = SEG_END;
+                t0 = time - end_off;
+                sp = p7; sv = v7; sa = a7; sj = 0.0;
+            } else {
+                // cumulative_times[0] == duration > time, so the section index is 0 and t_diff == time (:85-99, Q13)
+                section = 0;
+                double td = time;
+                bool set = false;
+                if (bdur > 0.0) {
+                    if (td < bdur) {  // brake pre-trajectory (:103-121); stays in SEG_SEARCH, it lasts a few samples at most
+                        const int bi = (td < bt0) ? 0 : 1;
+                        if (bi > 0) td -= bt0;
+                        t0 = td;
+                        sp = q[(int64_t)(S_BRAKE_P + bi) * st]; sv = q[(int64_t)(S_BRAKE_V + bi) * st];
+                        sa = q[(int64_t)(S_BRAKE_A + bi) * st]; sj = q[(int64_t)(S_BRAKE_J + bi) * st];
+                        seg = SEG_SEARCH;
+                        set = true;
+                    } else {
+                        td -= bdur;
                     }
-                    if (index > 0) td -= t_lo;
-                    t0 = td; p0 = cp; v0 = cv; a0 = ca; j0 = cj;
+                }
+                if (!set) {
+                    if (td >= ts6) {  // past this DoF's own end (:122-132)
+                        t0 = td - ts6;
+                        sp = p7; sv = v7; sa = a7; sj = 0.0;
+                        seg = SEG_OWN_END;
+                    } else {
+                        while (index < 6 && !(t_hi > td)) {
+                            ++index;
+                            lsub = t_hi;
+                            t_hi = q[(int64_t)(S_TSUM + index) * st];
+                        }
+                        t0 = td - lsub;
+                        sp = q[(int64_t)(S_P + index) * st]; sv = q[(int64_t)(S_V + index) * st];
+                        sa = q[(int64_t)(S_A + index) * st]; sj = q[(int64_t)(S_J + index) * st];
+                        // index == 6 is the default of the search, not a test of t_sum[6] > td: stay only on the reference's terms
+                        seg = (t_hi > td) ? SEG_PHASE : SEG_SEARCH;
+                    }
                 }
             }
         }
-        double p, v, a;
-        integrate(t0, p0, v0, a0, j0, p, v, a);
-        const int64_t o = (int64_t)k * total + gi;
-        if (S.pos) __stcs(S.pos + o, p);
-        if (S.vel) __stcs(S.vel + o, v);
-        if (S.acc) __stcs(S.acc + o, a);
-        if (S.jerk) __stcs(S.jerk + o, j0);
-        if (S.section && d == 0) S.section[(int64_t)k * S.n + i] = section;
+        // util.rs:27-33; t * j / 6 through the shared reciprocal (IEEE-exact, rk_math.cuh), +-0 numerators pass through
+        const double tj = t0 * sj;
+        const bool tj_zero = tj == 0.0;
+        const double sixth = ddiv(tj_zero ? 1.0 : tj, six);
+        const double p = sp + t0 * (sv + t0 * (sa / 2.0 + (tj_zero ? tj : sixth)));
+        const double v = sv + t0 * (sa + tj / 2.0);
+        const double a = sa + tj;
+        if (PVA_ONLY) {
+            __stcs((double*)out_p, p); out_p += stride;
+            __stcs((double*)out_v, v); out_v += stride;
+            __stcs((double*)out_a, a); out_a += stride;
+        } else {
+            if (out_p) { __stcs((double*)out_p, p); out_p += stride; }
+            if (out_v) { __stcs((double*)out_v, v); out_v += stride; }
+            if (out_a) { __stcs((double*)out_a, a); out_a += stride; }
+            if (out_j) { __stcs((double*)out_j, sj); out_j += stride; }
+            if (out_s) { *out_s = section; out_s += S.n; }
+        }
     }
 }
 
@@ -670,10 +717,24 @@ rk_status rk_at_time_batch(rk_handle* h, const rk_trajectories* traj, const rk_s
     // 1000 cycles runs at 3.1 TB/s unsliced, 2.4 TB/s in slices of 50).
     int64_t slices = (300000 + total - 1) / total;
     if (slices < 1) slices = 1;
+    {   // ... and a few slices more when that evens out the last wave of blocks (64 Ki x 7 DoF alone is 1.5 waves of 2048
+        // threads per SM): pick the slice count whose last wave is fullest, charging 1.5 % per extra slice for the re-read
+        const double wave = (double)h->sm_count * 2048.0;
+        double best = -1.0;
+        int64_t best_s = slices;
+        for (int64_t sl = slices; sl <= slices + 7; ++sl) {
+            const double waves = (double)total * (double)sl / wave;
+            const double eff = waves / (double)(int64_t)(waves + 0.999999) - 0.015 * (double)(sl - slices);
+            if (eff > best + 1e-9) { best = eff; best_s = sl; }
+        }
+        slices = best_s;
+    }
     if (slices > (desc->steps + 31) / 32) slices = (desc->steps + 31) / 32;
+    if (slices < 1) slices = 1;
     S.k_chunk = (int32_t)((desc->steps + slices - 1) / slices);
     const dim3 grid((unsigned)((total + 255) / 256), (unsigned)((desc->steps + S.k_chunk - 1) / S.k_chunk), 1);
-    rk::k_at_time<<<grid, 256, 0, h->stream>>>(S);
+    if (S.pos && S.vel && S.acc && !S.jerk && !S.section) rk::k_at_time<true><<<grid, 256, 0, h->stream>>>(S);
+    else rk::k_at_time<false><<<grid, 256, 0, h->stream>>>(S);
     h->launches += 1;
     RK_CUDA(cudaGetLastError());
     if (host) {

@@ -203,6 +203,15 @@ def test_at_time_sampling_exact(gpu):
     for a, b, name in ((pos, opos, "position"), (vel, ovel, "velocity"), (acc, oacc, "acceleration"), (jerk, ojerk, "jerk")):
         assert np.array_equal(a[:, :, ok], b[:, :, ok]), name
     assert np.array_equal(sec[:, ok], osec[:, ok])
+    # the position / velocity / acceleration-only form (its own kernel instantiation, the one the RL rollout uses), a longer
+    # horizon with a coarser cycle so that every segment kind (brake, phases, own end, trajectory end) is crossed, and a
+    # sliced rollout (time_start > 0 continues an earlier one)
+    for K2, dt2, t_start in ((300, 0.05, 0.0), (64, 0.013, 0.731)):
+        p2, v2, a2 = (np.zeros((K2, dof, n)) for _ in range(3))
+        otg.at_time(time_start=t_start, delta_time=dt2, steps=K2, memory_space=cabi.RK_MEM_HOST, position=p2, velocity=v2, acceleration=a2)
+        opos, ovel, oacc, _, _ = ob.at_time(time_start=t_start, delta_time=dt2, steps=K2, threads=8)
+        for a, b, name in ((p2, opos, "position"), (v2, ovel, "velocity"), (a2, oacc, "acceleration")):
+            assert np.array_equal(a[:, :, ok], b[:, :, ok]), f"{name} (p/v/a only, K={K2})"
 
 
 def test_against_glibc_flavour_within_tolerance(gpu):
