@@ -289,6 +289,7 @@ def run_b200(args):
     # ---- p50 latency of one 64Ki batch (the second half of BASELINE.json's metric) and the at_time rollout of configs[3]
     latency = None
     sampling = None
+    closed_loop = None
     if not args.no_extras and rank == 0:
         n64 = 65536
         f64k = {k: v[:, :n64].contiguous() for k, v in f.items()}
@@ -350,6 +351,38 @@ def run_b200(args):
                                  "bytes_per_launch": out_bytes, "write_only_fill_gbs": fill_gbs,
                                  "frac_of_write_only_fill": out_bytes / (ms_s * 1e-3) / 1e9 / fill_gbs, "note": "algorithmic bytes = 3 x 8 B x DoF per sample written; the 472 B profile per (DoF, trajectory) read once is amortised over K"}}
         del pos, vel, acc
+        # closed control loops: rk_update_batch, 64Ki environments, every 10th cycle a tenth of them is
+        # re-targeted mid-motion and re-solved from its current state; all advance one cycle and pass the state on
+        from rsruckig_b200 import BatchRollout
+        ro = BatchRollout(n64, DOF, DELTA_TIME, ThrowErrorHandler, device=local)
+        fl = {k: v.clone() for k, v in f64k.items()}
+        new_p = torch.empty((DOF, n64), dtype=torch.float64, device=dev)
+        new_v, new_a = torch.empty_like(new_p), torch.empty_like(new_p)
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(7)
+        cycles, resolved = 200, 0
+        ro.update(fl, new_position=new_p, new_velocity=new_v, new_acceleration=new_a)  # first cycle solves everything
+        ro.sync()
+        with torch.cuda.stream(stream):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            for c in range(cycles):
+                if c % 10 == 0:
+                    pick = torch.rand(n64, generator=gen, device=dev) < 0.1
+                    fl["target_position"] = torch.where(pick[None, :], torch.randn((DOF, n64), generator=gen, device=dev, dtype=torch.float64) * 4.0,
+                                                        fl["target_position"]).contiguous()
+                resolved += ro.update(fl, new_position=new_p, new_velocity=new_v, new_acceleration=new_a)
+            b.record(stream)
+            b.synchronize()
+        ms_c = a.elapsed_time(b)
+        closed_loop = {"workload": f"{n64} x {DOF}-DoF closed control loops, {cycles} cycles of rk_update_batch (Ruckig::update), a tenth of the "
+                                   "environments re-targeted every 10th cycle",
+                       "cycles_per_s": cycles / (ms_c * 1e-3), "environment_steps_per_s": cycles * n64 / (ms_c * 1e-3),
+                       "recalculations": int(resolved), "ms_per_cycle": ms_c / cycles,
+                       "note": "includes the torch ops that draw the new targets and one device-to-host read per cycle (the number of environments to "
+                               "re-solve); the ~2 % of environments whose input fails validation are re-solved every cycle, as Ruckig::update "
+                               "does under the throwing error handler"}
+        del ro
 
     if rank == 0:
         flop, flop_how = algorithmic_flop_per_trajectory()
@@ -364,7 +397,7 @@ def run_b200(args):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic", "config": config(n, world), "gpu_launches": int(gpu_launches), "launches_per_step": int(launches_per_step),
-                "working_fraction": n_working / n, "clocks": clocks, "e2e": e2e, "latency_64k": latency, "at_time": sampling,
+                "working_fraction": n_working / n, "clocks": clocks, "e2e": e2e, "latency_64k": latency, "at_time": sampling, "closed_loop": closed_loop,
                 "roofline": {"bound": "fp64", "achieved": achieved_tflops, "peak": fp64_peak_tflops, "unit": "TFLOP/s",
                              "frac": achieved_tflops / fp64_peak_tflops if fp64_peak_tflops else None,
                              "traffic": (ops.get("dram_bytes_per_trajectory") or 0) * n or None,

@@ -197,6 +197,39 @@ enum {
 /* Trajectory::at_time for every trajectory and K sample times (trajectory.rs:158-189). */
 rk_status rk_at_time_batch(rk_handle* h, const rk_trajectories* traj, const rk_sample_desc* desc, const rk_sample_out* out);
 
+/* ---- closed-loop control cycles: the batched Ruckig::update (ruckig.rs:266-321) ------------------------------------------
+ * An rk_rollout is n independent (Ruckig, OutputParameter) pairs: per environment the input of its last calculation
+ * (Ruckig::current_input), its trajectory and OutputParameter::time. One rk_update_batch call is one control cycle for all
+ * of them: environments that were never calculated or whose input differs from their current_input (the PartialEq of
+ * input_parameter.rs:190-211, batch-level settings included) are re-solved — only those —, then every environment advances
+ * its time by desc->delta_time and samples its trajectory (Trajectory::at_time), and the new state is written into
+ * current_input (output.pass_to_input(&mut self.current_input), ruckig.rs:314) and, if asked, into the caller's
+ * current_* arrays. As in the reference, time is NOT reset by a new calculation unless
+ * reset_time_on_new_calculation is set, and Ok(Error*) results of the calculation are dropped (Q1); under RK_ERRORS_THROW a
+ * validation / calculator error is returned as the environment's result and its cycle is not advanced (the `?` of :285).
+ * Device pointers only (desc->memory_space must be RK_MEM_DEVICE); stream-ordered on rk_stream(h) except for one small
+ * device-to-host read per cycle (the number of environments to re-solve). */
+typedef struct rk_rollout rk_rollout;
+
+typedef struct rk_update_out {
+    double* new_position;       /* [dof][n], nullable */
+    double* new_velocity;       /* [dof][n], nullable */
+    double* new_acceleration;   /* [dof][n], nullable */
+    double* new_jerk;           /* [dof][n], nullable */
+    int32_t* result;            /* [n], nullable: 0 Working, 1 Finished, < 0 error of the calculation (throw semantics) */
+    uint8_t* new_calculation;   /* [n], nullable: OutputParameter::new_calculation */
+    double* time;               /* [n], nullable: OutputParameter::time after the cycle */
+    int32_t pass_to_input;      /* != 0: also write the new state into in->current_* (OutputParameter::pass_to_input) */
+    int32_t reset_time_on_new_calculation; /* 0 = the reference's behaviour (Q1) */
+} rk_update_out;
+
+rk_status rk_rollout_create(rk_handle* h, int64_t n, int32_t dof, rk_rollout** out);
+rk_status rk_rollout_destroy(rk_rollout* r);
+rk_status rk_rollout_reset(rk_handle* h, rk_rollout* r);          /* Ruckig::reset (ruckig.rs:125-127) + a fresh OutputParameter */
+rk_trajectories* rk_rollout_trajectories(rk_rollout* r);          /* the trajectories of the n environments (owned by r) */
+rk_status rk_update_batch(rk_handle* h, const rk_batch_desc* desc, const rk_batch_in* in, rk_rollout* r, const rk_update_out* out,
+                          int64_t* recalculated /* nullable: number of environments re-solved in this cycle */);
+
 /* Copy one field of the device-resident trajectories to `dst`. */
 rk_status rk_trajectories_read(rk_handle* h, const rk_trajectories* traj, int32_t field, void* dst, int32_t dst_memory_space);
 

@@ -72,6 +72,12 @@ class RkSampleOut(C.Structure):
                 ("section", C.c_void_p)]
 
 
+class RkUpdateOut(C.Structure):
+    _fields_ = [("new_position", C.c_void_p), ("new_velocity", C.c_void_p), ("new_acceleration", C.c_void_p), ("new_jerk", C.c_void_p),
+                ("result", C.c_void_p), ("new_calculation", C.c_void_p), ("time", C.c_void_p), ("pass_to_input", C.c_int32),
+                ("reset_time_on_new_calculation", C.c_int32)]
+
+
 def ptr(a) -> int | None:
     """Address of a numpy array (host) / torch tensor (host or device) / int / None."""
     if a is None:
@@ -121,6 +127,7 @@ EXPORTS = (
     "rk_create", "rk_destroy", "rk_trajectories_create", "rk_trajectories_destroy", "rk_calculate_batch",
     "rk_validate_batch", "rk_at_time_batch", "rk_trajectories_read", "rk_sync", "rk_stream", "rk_kernel_launches",
     "rk_status_string", "rk_last_error", "rk_version", "rk_measure_fp64_peak", "rk_selftest_division",
+    "rk_rollout_create", "rk_rollout_destroy", "rk_rollout_reset", "rk_rollout_trajectories", "rk_update_batch",
 )
 
 
@@ -155,8 +162,15 @@ def load():
     lib.rk_status_string.restype = C.c_char_p
     lib.rk_last_error.restype = C.c_char_p
     lib.rk_version.restype = C.c_char_p
+    lib.rk_rollout_create.argtypes = [vp, C.c_int64, C.c_int32, C.POINTER(vp)]
+    lib.rk_rollout_destroy.argtypes = [vp]
+    lib.rk_rollout_reset.argtypes = [vp, vp]
+    lib.rk_rollout_trajectories.argtypes = [vp]
+    lib.rk_rollout_trajectories.restype = vp
+    lib.rk_update_batch.argtypes = [vp, C.POINTER(RkBatchDesc), C.POINTER(RkBatchIn), vp, C.POINTER(RkUpdateOut), C.POINTER(C.c_int64)]
     for f in ("rk_create", "rk_destroy", "rk_trajectories_create", "rk_trajectories_destroy", "rk_calculate_batch",
-              "rk_validate_batch", "rk_at_time_batch", "rk_trajectories_read", "rk_sync"):
+              "rk_validate_batch", "rk_at_time_batch", "rk_trajectories_read", "rk_sync", "rk_rollout_create", "rk_rollout_destroy",
+              "rk_rollout_reset", "rk_update_batch"):
         getattr(lib, f).restype = C.c_int32
     _LIB = lib
     return lib

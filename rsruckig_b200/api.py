@@ -479,5 +479,61 @@ class BatchRuckig:
     def sync(self):
         cabi.check(self._engine.lib.rk_sync(self._engine.h))
 
+
     def kernel_launches(self) -> int:
         return int(self._engine.lib.rk_kernel_launches(self._engine.h))
+
+class BatchRollout:
+    """n independent closed control loops on the device: the batched `Ruckig::update` (ruckig.rs:266-321).
+
+    `update(fields, ...)` is one control cycle for every environment: those whose input changed (or that were never
+    calculated) are re-solved, all advance their time by `delta_time`, sample their trajectory and — with
+    `pass_to_input=True` — get the new state written into `fields["current_*"]`, ready for the next cycle
+    (`OutputParameter::pass_to_input`). All buffers are device tensors `[dof][n]` / `[n]`.
+    """
+
+    def __init__(self, n: int, dofs: int, delta_time: float, error_handler=ThrowErrorHandler, device: int = 0):
+        self.n, self.degrees_of_freedom, self.delta_time = int(n), int(dofs), float(delta_time)
+        self.error_handler = error_handler
+        self._engine = _Engine.get(device)
+        r = C.c_void_p()
+        cabi.check(self._engine.lib.rk_rollout_create(self._engine.h, self.n, self.degrees_of_freedom, C.byref(r)))
+        self._r = r
+
+    def __del__(self):
+        try:
+            if getattr(self, "_r", None):
+                self._engine.lib.rk_rollout_destroy(self._r)
+                self._r = None
+        except Exception:
+            pass
+
+    def reset(self):
+        cabi.check(self._engine.lib.rk_rollout_reset(self._engine.h, self._r))
+
+    def update(self, fields: dict, *, control_interface=ControlInterface.Position, synchronization=Synchronization.Time,
+               duration_discretization=DurationDiscretization.Continuous, per_dof_control_interface=None, per_dof_synchronization=None,
+               new_position=None, new_velocity=None, new_acceleration=None, new_jerk=None, result=None, new_calculation=None,
+               time=None, pass_to_input=True, reset_time_on_new_calculation=False) -> int:
+        """One control cycle; returns the number of environments that were re-solved."""
+        desc, keep = cabi.make_desc(self.n, self.degrees_of_freedom, control_interface=control_interface,
+                                    synchronization=synchronization, duration_discretization=duration_discretization,
+                                    error_mode=cabi.RK_ERRORS_THROW if self.error_handler.throws else cabi.RK_ERRORS_IGNORE,
+                                    memory_space=cabi.RK_MEM_DEVICE, delta_time=self.delta_time,
+                                    per_dof_control_interface=per_dof_control_interface,
+                                    per_dof_synchronization=per_dof_synchronization)
+        bin_ = cabi.make_in(fields)
+        out = cabi.RkUpdateOut(cabi.ptr(new_position), cabi.ptr(new_velocity), cabi.ptr(new_acceleration), cabi.ptr(new_jerk),
+                               cabi.ptr(result), cabi.ptr(new_calculation), cabi.ptr(time), int(bool(pass_to_input)),
+                               int(bool(reset_time_on_new_calculation)))
+        m = C.c_int64(0)
+        eng = self._engine
+        cabi.check(eng.lib.rk_update_batch(eng.h, C.byref(desc), C.byref(bin_), self._r, C.byref(out), C.byref(m)))
+        return int(m.value)
+
+    def read(self, field: int) -> np.ndarray:
+        return self._engine.read(self._engine.lib.rk_rollout_trajectories(self._r), field, self.n, self.degrees_of_freedom)
+
+    def sync(self):
+        cabi.check(self._engine.lib.rk_sync(self._engine.h))
+

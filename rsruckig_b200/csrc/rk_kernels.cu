@@ -187,6 +187,210 @@ __global__ void __launch_bounds__(256) k_at_time(const SampleParams S) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------ closed-loop update (rk_update_batch)
+struct UpdateParams {
+    int64_t n;
+    int32_t dof;
+    // the caller's inputs ([dof][n]; v_min / a_min / enabled / min_dur may be null) and the copies of the last calculation
+    const double* in[11];
+    double* last[11];
+    const uint8_t* enabled; uint8_t* last_enabled;
+    const double* min_dur; double* last_min_dur;
+    int32_t force_all;              // batch-level settings changed (or different optional arrays): everything is dirty
+    uint8_t* initialized;           // [n]
+    uint8_t* dirty;                 // [n]
+    uint32_t* idx;                  // [n] compacted indices of the dirty environments
+    uint32_t* count;                // [1]
+    // gathered inputs of the dirty environments, [dof][m]
+    double* gin[11];
+    uint8_t* g_enabled; double* g_min_dur;
+};
+
+// Which environments must be re-solved: never calculated, or input != current_input (input_parameter.rs:190-211; f64 ==, so a
+// NaN never compares equal).
+__global__ void __launch_bounds__(256) k_upd_dirty(const UpdateParams U) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool dirty = false;
+    if (i < U.n) {
+        dirty = U.force_all != 0 || U.initialized[i] == 0;
+        for (int d = 0; d < U.dof && !dirty; ++d) {
+            const int64_t g = (int64_t)d * U.n + i;
+#pragma unroll
+            for (int f = 0; f < 11; ++f)
+                if (U.in[f] && !(U.in[f][g] == U.last[f][g])) dirty = true;
+            if (U.enabled && U.enabled[g] != U.last_enabled[g]) dirty = true;
+        }
+        if (!dirty && U.min_dur) {
+            const double a = U.min_dur[i], b = U.last_min_dur[i];
+            // Option<f64>: None == None, Some(x) == Some(y) iff x == y; NaN encodes None at this boundary
+            if (!((a != a && b != b) || a == b)) dirty = true;
+        }
+        U.dirty[i] = dirty ? 1 : 0;
+    }
+    const unsigned mask = __ballot_sync(0xffffffffu, dirty);
+    if (mask == 0) return;
+    const int lane = threadIdx.x & 31, leader = __ffs(mask) - 1;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(U.count, (uint32_t)__popc(mask));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (dirty) U.idx[base + __popc(mask & ((1u << lane) - 1u))] = (uint32_t)i;
+}
+
+// The order in which the warps appended is arbitrary; environments are independent, so it only has to be the same order for
+// gather and scatter.
+__global__ void __launch_bounds__(256) k_upd_gather(const UpdateParams U, int64_t m) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= m * U.dof) return;
+    const int d = (int)(t / m);
+    const int64_t j = t - (int64_t)d * m;
+    const int64_t g = (int64_t)d * U.n + U.idx[j];
+#pragma unroll
+    for (int f = 0; f < 11; ++f)
+        if (U.in[f]) U.gin[f][t] = U.in[f][g];
+    if (U.enabled) U.g_enabled[t] = U.enabled[g];
+    if (d == 0 && U.min_dur) U.g_min_dur[j] = U.min_dur[U.idx[j]];
+}
+
+struct ScatterParams {
+    int64_t n, m;
+    int32_t dof, throw_mode;
+    const uint32_t* idx;
+    const double* s_prof; const uint32_t* s_codes; const int32_t* s_status; const double* s_duration; const double* s_imd;
+    const int32_t* s_limiting; const int32_t* s_detail;
+    double* prof; uint32_t* codes; int32_t* status; double* duration; double* imd; int32_t* limiting; int32_t* detail;
+};
+
+// Results of the re-solved subset -> the environments' own trajectories; the input they were solved for becomes current_input.
+__global__ void __launch_bounds__(256) k_upd_scatter(const ScatterParams C, const UpdateParams U) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= C.m * C.dof) return;
+    const int d = (int)(t / C.m);
+    const int64_t j = t - (int64_t)d * C.m;
+    const int64_t i = C.idx[j];
+    const int64_t g = (int64_t)d * C.n + i;
+    const int64_t s_stride = (int64_t)C.dof * C.m, stride = (int64_t)C.dof * C.n;
+#pragma unroll 1
+    for (int r = 0; r < PROFILE_SLOTS; ++r) C.prof[(int64_t)r * stride + g] = C.s_prof[(int64_t)r * s_stride + t];
+    C.codes[g] = C.s_codes[t];
+    C.imd[g] = C.s_imd[t];
+    const int st = C.s_status[j];
+    // Err(..) under the throwing handler leaves current_input untouched (the `?` of ruckig.rs:285): the environment is solved
+    // again next cycle
+    const bool thrown = C.throw_mode && (st == RK_RESULT_ERROR_INVALID_INPUT || st == RK_RESULT_ERROR_ZERO_LIMITS
+                                         || st == RK_RESULT_ERROR_EXECUTION_TIME_CALCULATION || st == RK_RESULT_ERROR_SYNCHRONIZATION_CALCULATION);
+    if (!thrown) {
+#pragma unroll
+        for (int f = 0; f < 11; ++f)
+            if (U.in[f]) U.last[f][g] = U.gin[f][t];
+        if (U.enabled) U.last_enabled[g] = U.g_enabled[t];
+    }
+    if (d == 0) {
+        C.status[i] = st;
+        C.duration[i] = C.s_duration[j];
+        C.limiting[i] = C.s_limiting[j];
+        C.detail[i] = C.s_detail[j];
+        if (!thrown) {
+            if (U.min_dur) U.last_min_dur[i] = U.g_min_dur[j];
+            U.initialized[i] = 1;
+        }
+    }
+}
+
+struct StepParams {
+    int64_t n;
+    int32_t dof, throw_mode, reset_time;
+    double delta_time;
+    const double* prof; const double* duration; const int32_t* status;
+    const uint8_t* dirty;
+    const double* time_in; double* time_out;
+    double* last_p; double* last_v; double* last_a;      // current_input.current_* (pass_to_input, ruckig.rs:314)
+    double* in_p; double* in_v; double* in_a;            // the caller's arrays, or null
+    double *new_p, *new_v, *new_a, *new_j;
+    int32_t* result; uint8_t* new_calc; double* time_user;
+};
+
+// Trajectory::at_time (trajectory.rs:52-189) for one sample time.
+__device__ __forceinline__ void sample_once(const double* q, int64_t st, double duration, double time, double& p, double& v, double& a, double& j) {
+    const double ts6 = q[(int64_t)(S_TSUM + 6) * st];
+    const double bdur = q[(int64_t)S_BRAKE_DUR * st];
+    double t0, p0, v0, a0, j0;
+    if (time >= duration) {  // :60-83
+        t0 = time - (bdur + ts6);
+        p0 = q[(int64_t)(S_P + 7) * st]; v0 = q[(int64_t)(S_V + 7) * st]; a0 = q[(int64_t)(S_A + 7) * st]; j0 = 0.0;
+    } else {
+        double td = time;
+        bool set = false;
+        if (bdur > 0.0) {
+            if (td < bdur) {  // :103-121
+                const int bi = (td < q[(int64_t)S_BRAKE_T * st]) ? 0 : 1;
+                if (bi > 0) td -= q[(int64_t)S_BRAKE_T * st];
+                t0 = td;
+                p0 = q[(int64_t)(S_BRAKE_P + bi) * st]; v0 = q[(int64_t)(S_BRAKE_V + bi) * st];
+                a0 = q[(int64_t)(S_BRAKE_A + bi) * st]; j0 = q[(int64_t)(S_BRAKE_J + bi) * st];
+                set = true;
+            } else {
+                td -= bdur;
+            }
+        }
+        if (!set) {
+            if (td >= ts6) {  // :122-132
+                t0 = td - ts6;
+                p0 = q[(int64_t)(S_P + 7) * st]; v0 = q[(int64_t)(S_V + 7) * st]; a0 = q[(int64_t)(S_A + 7) * st]; j0 = 0.0;
+            } else {  // :134-140
+                int index = 0;
+                while (index < 6 && !(q[(int64_t)(S_TSUM + index) * st] > td)) ++index;
+                if (index > 0) td -= q[(int64_t)(S_TSUM + index - 1) * st];
+                t0 = td;
+                p0 = q[(int64_t)(S_P + index) * st]; v0 = q[(int64_t)(S_V + index) * st];
+                a0 = q[(int64_t)(S_A + index) * st]; j0 = q[(int64_t)(S_J + index) * st];
+            }
+        }
+    }
+    integrate(t0, p0, v0, a0, j0, p, v, a);
+    j = j0;
+}
+
+// One control cycle of every environment: time += delta_time, at_time, pass_to_input, Working / Finished (ruckig.rs:292-321).
+__global__ void __launch_bounds__(256) k_upd_step(const StepParams T) {
+    const int64_t total = (int64_t)T.dof * T.n;
+    const int64_t gi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gi >= total) return;
+    const int d = (int)(gi / T.n);
+    const int64_t i = gi - (int64_t)d * T.n;
+    const int st = T.status[i];
+    const bool fresh = T.dirty[i] != 0;
+    const bool thrown = fresh && T.throw_mode && (st == RK_RESULT_ERROR_INVALID_INPUT || st == RK_RESULT_ERROR_ZERO_LIMITS
+                                                  || st == RK_RESULT_ERROR_EXECUTION_TIME_CALCULATION
+                                                  || st == RK_RESULT_ERROR_SYNCHRONIZATION_CALCULATION);
+    double time = T.time_in[i];
+    if (thrown) {  // Err(..): update returned before touching the output
+        if (d == 0) {
+            T.time_out[i] = time;
+            if (T.result) T.result[i] = st;
+            if (T.new_calc) T.new_calc[i] = 0;
+            if (T.time_user) T.time_user[i] = time;
+        }
+        return;
+    }
+    if (fresh && T.reset_time) time = 0.0;
+    time += T.delta_time;
+    const double duration = T.duration[i];
+    double p, v, a, j;
+    sample_once(T.prof + gi, total, duration, time, p, v, a, j);
+    if (T.new_p) T.new_p[gi] = p;
+    if (T.new_v) T.new_v[gi] = v;
+    if (T.new_a) T.new_a[gi] = a;
+    if (T.new_j) T.new_j[gi] = j;
+    T.last_p[gi] = p; T.last_v[gi] = v; T.last_a[gi] = a;
+    if (T.in_p) { T.in_p[gi] = p; T.in_v[gi] = v; T.in_a[gi] = a; }
+    if (d == 0) {
+        T.time_out[i] = time;
+        if (T.result) T.result[i] = (time > duration) ? RK_RESULT_FINISHED : RK_RESULT_WORKING;
+        if (T.new_calc) T.new_calc[i] = fresh ? 1 : 0;
+        if (T.time_user) T.time_user[i] = time;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ FP64 peak probe
 // 8 independent DFMA chains per thread, all in registers; `iters` x 8 x 2 flop per thread.
 __global__ void __launch_bounds__(256) k_fp64_peak(double* sink, int iters, double a, double b) {
@@ -742,6 +946,166 @@ rk_status rk_at_time_batch(rk_handle* h, const rk_trajectories* traj, const rk_s
         if (out->section) RK_CUDA(cudaMemcpyAsync(out->section, dsec, sec, cudaMemcpyDeviceToHost, h->stream));
         RK_CUDA(cudaStreamSynchronize(h->stream));
     }
+    return RK_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ rk_update_batch
+struct rk_rollout {
+    rk_handle* h = nullptr;
+    int64_t n = 0;
+    int32_t dof = 0;
+    rk_trajectories* traj = nullptr;  // the environments' trajectories
+    rk_trajectories* tmp = nullptr;   // results of the re-solved subset, compact [..][dof][m] inside buffers of capacity n
+    double* last[11] = {};            // current_input, [dof][n] each
+    double* gin[11] = {};             // gathered inputs of the subset
+    uint8_t *last_enabled = nullptr, *g_enabled = nullptr;
+    double *last_min_dur = nullptr, *g_min_dur = nullptr;
+    double* time[2] = {nullptr, nullptr};
+    int time_cur = 0;
+    uint8_t *initialized = nullptr, *dirty = nullptr;
+    uint32_t *idx = nullptr, *count = nullptr;
+    uint32_t* count_host = nullptr;   // pinned
+    // batch-level part of the last calculated input
+    bool have_desc = false;
+    rk_batch_desc last_desc{};
+    int8_t last_ci[RK_MAX_DOF] = {}, last_sync[RK_MAX_DOF] = {};
+    bool last_present[13] = {};
+};
+
+rk_status rk_rollout_create(rk_handle* h, int64_t n, int32_t dof, rk_rollout** out) {
+    if (!h || !out || n < 1 || dof < 1 || dof > RK_MAX_DOF) return fail(RK_ERR_INVALID_ARGUMENT, "bad arguments to rk_rollout_create");
+    RK_CUDA(cudaSetDevice(h->device));
+    rk_rollout* r = new rk_rollout();
+    r->h = h; r->n = n; r->dof = dof;
+    rk_status st = rk_trajectories_create(h, n, dof, &r->traj);
+    if (st == RK_OK) st = rk_trajectories_create(h, n, dof, &r->tmp);
+    if (st != RK_OK) return st;
+    const size_t items = (size_t)n * dof;
+    for (int f = 0; f < 11; ++f) {
+        RK_CUDA(cudaMalloc(&r->last[f], sizeof(double) * items));
+        RK_CUDA(cudaMalloc(&r->gin[f], sizeof(double) * items));
+        RK_CUDA(cudaMemsetAsync(r->last[f], 0, sizeof(double) * items, h->stream));
+    }
+    RK_CUDA(cudaMalloc(&r->last_enabled, items)); RK_CUDA(cudaMalloc(&r->g_enabled, items));
+    RK_CUDA(cudaMalloc(&r->last_min_dur, sizeof(double) * n)); RK_CUDA(cudaMalloc(&r->g_min_dur, sizeof(double) * n));
+    RK_CUDA(cudaMalloc(&r->time[0], sizeof(double) * n)); RK_CUDA(cudaMalloc(&r->time[1], sizeof(double) * n));
+    RK_CUDA(cudaMalloc(&r->initialized, n)); RK_CUDA(cudaMalloc(&r->dirty, n));
+    RK_CUDA(cudaMalloc(&r->idx, sizeof(uint32_t) * n)); RK_CUDA(cudaMalloc(&r->count, sizeof(uint32_t)));
+    RK_CUDA(cudaMallocHost(&r->count_host, sizeof(uint32_t)));
+    *out = r;
+    return rk_rollout_reset(h, r);
+}
+
+rk_status rk_rollout_reset(rk_handle* h, rk_rollout* r) {
+    if (!h || !r) return fail(RK_ERR_INVALID_ARGUMENT, "NULL argument to rk_rollout_reset");
+    RK_CUDA(cudaSetDevice(h->device));
+    RK_CUDA(cudaMemsetAsync(r->initialized, 0, r->n, h->stream));
+    RK_CUDA(cudaMemsetAsync(r->time[0], 0, sizeof(double) * r->n, h->stream));
+    RK_CUDA(cudaMemsetAsync(r->time[1], 0, sizeof(double) * r->n, h->stream));
+    r->time_cur = 0;
+    r->have_desc = false;
+    return RK_OK;
+}
+
+rk_status rk_rollout_destroy(rk_rollout* r) {
+    if (!r) return RK_OK;
+    cudaSetDevice(r->h->device);
+    cudaStreamSynchronize(r->h->stream);
+    rk_trajectories_destroy(r->traj); rk_trajectories_destroy(r->tmp);
+    for (int f = 0; f < 11; ++f) { cudaFree(r->last[f]); cudaFree(r->gin[f]); }
+    cudaFree(r->last_enabled); cudaFree(r->g_enabled); cudaFree(r->last_min_dur); cudaFree(r->g_min_dur);
+    cudaFree(r->time[0]); cudaFree(r->time[1]); cudaFree(r->initialized); cudaFree(r->dirty); cudaFree(r->idx); cudaFree(r->count);
+    cudaFreeHost(r->count_host);
+    delete r;
+    return RK_OK;
+}
+
+rk_trajectories* rk_rollout_trajectories(rk_rollout* r) { return r ? r->traj : nullptr; }
+
+rk_status rk_update_batch(rk_handle* h, const rk_batch_desc* desc, const rk_batch_in* in, rk_rollout* r, const rk_update_out* out,
+                          int64_t* recalculated) {
+    if (!h || !r || !out) return fail(RK_ERR_INVALID_ARGUMENT, "NULL argument to rk_update_batch");
+    rk::Params P;
+    rk_status st = fill_params(P, desc, in);
+    if (st != RK_OK) return st;
+    if (desc->n != r->n || desc->dof != r->dof) return fail(RK_ERR_INVALID_ARGUMENT, "the rollout was created for another (n, dof)");
+    if (desc->memory_space != RK_MEM_DEVICE) return fail(RK_ERR_INVALID_ARGUMENT, "rk_update_batch takes device pointers");
+    RK_CUDA(cudaSetDevice(h->device));
+    const int64_t n = r->n;
+    const int dof = r->dof;
+
+    // batch-level fields of InputParameter's PartialEq, and which optional arrays are present
+    const bool present[13] = {true, true, true, true, true, true, true, true, true, in->min_velocity != nullptr, in->min_acceleration != nullptr,
+                              in->enabled != nullptr, in->minimum_duration != nullptr};
+    bool force_all = !r->have_desc || r->last_desc.duration_discretization != desc->duration_discretization;
+    for (int d = 0; d < dof && !force_all; ++d) force_all = r->last_ci[d] != P.ci[d] || r->last_sync[d] != P.sync[d];
+    for (int f = 0; f < 13 && !force_all; ++f) force_all = r->last_present[f] != present[f];
+
+    rk::UpdateParams U{};
+    U.n = n; U.dof = dof;
+    const double* ins[11] = {in->current_position, in->current_velocity, in->current_acceleration, in->target_position, in->target_velocity,
+                             in->target_acceleration, in->max_velocity, in->max_acceleration, in->max_jerk, in->min_velocity, in->min_acceleration};
+    for (int f = 0; f < 11; ++f) { U.in[f] = ins[f]; U.last[f] = r->last[f]; U.gin[f] = r->gin[f]; }
+    U.enabled = in->enabled; U.last_enabled = r->last_enabled; U.g_enabled = r->g_enabled;
+    U.min_dur = in->minimum_duration; U.last_min_dur = r->last_min_dur; U.g_min_dur = r->g_min_dur;
+    U.force_all = force_all ? 1 : 0;
+    U.initialized = r->initialized; U.dirty = r->dirty; U.idx = r->idx; U.count = r->count;
+
+    RK_CUDA(cudaMemsetAsync(r->count, 0, sizeof(uint32_t), h->stream));
+    rk::k_upd_dirty<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(U);
+    RK_CUDA(cudaMemcpyAsync(r->count_host, r->count, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    RK_CUDA(cudaStreamSynchronize(h->stream));
+    const int64_t m = (int64_t)*r->count_host;
+    h->launches += 1;
+    if (recalculated) *recalculated = m;
+
+    if (m > 0) {
+        rk::k_upd_gather<<<(unsigned)((m * dof + 255) / 256), 256, 0, h->stream>>>(U, m);
+        h->launches += 1;
+        rk_batch_desc sub = *desc;
+        sub.n = m;
+        rk_batch_in gi{};
+        gi.current_position = r->gin[0]; gi.current_velocity = r->gin[1]; gi.current_acceleration = r->gin[2];
+        gi.target_position = r->gin[3]; gi.target_velocity = r->gin[4]; gi.target_acceleration = r->gin[5];
+        gi.max_velocity = r->gin[6]; gi.max_acceleration = r->gin[7]; gi.max_jerk = r->gin[8];
+        gi.min_velocity = in->min_velocity ? r->gin[9] : nullptr;
+        gi.min_acceleration = in->min_acceleration ? r->gin[10] : nullptr;
+        gi.enabled = in->enabled ? r->g_enabled : nullptr;
+        gi.minimum_duration = in->minimum_duration ? r->g_min_dur : nullptr;
+        rk_trajectories view = *r->tmp;  // the same buffers, laid out for m trajectories
+        view.n = m;
+        st = rk_calculate_batch(h, &sub, &gi, &view, nullptr);
+        if (st != RK_OK) return st;
+        rk::ScatterParams C{};
+        C.n = n; C.m = m; C.dof = dof; C.throw_mode = desc->error_mode == RK_ERRORS_THROW; C.idx = r->idx;
+        C.s_prof = view.prof; C.s_codes = view.codes; C.s_status = view.status; C.s_duration = view.duration; C.s_imd = view.imd;
+        C.s_limiting = view.limiting; C.s_detail = view.detail;
+        C.prof = r->traj->prof; C.codes = r->traj->codes; C.status = r->traj->status; C.duration = r->traj->duration; C.imd = r->traj->imd;
+        C.limiting = r->traj->limiting; C.detail = r->traj->detail;
+        rk::k_upd_scatter<<<(unsigned)((m * dof + 255) / 256), 256, 0, h->stream>>>(C, U);
+        h->launches += 1;
+    }
+    r->have_desc = true;
+    r->last_desc = *desc;
+    for (int d = 0; d < dof; ++d) { r->last_ci[d] = P.ci[d]; r->last_sync[d] = P.sync[d]; }
+    for (int f = 0; f < 13; ++f) r->last_present[f] = present[f];
+
+    rk::StepParams T{};
+    T.n = n; T.dof = dof; T.throw_mode = desc->error_mode == RK_ERRORS_THROW; T.reset_time = out->reset_time_on_new_calculation;
+    T.delta_time = desc->delta_time;
+    T.prof = r->traj->prof; T.duration = r->traj->duration; T.status = r->traj->status; T.dirty = r->dirty;
+    T.time_in = r->time[r->time_cur]; T.time_out = r->time[r->time_cur ^ 1];
+    T.last_p = r->last[0]; T.last_v = r->last[1]; T.last_a = r->last[2];
+    if (out->pass_to_input) {
+        T.in_p = const_cast<double*>(in->current_position); T.in_v = const_cast<double*>(in->current_velocity);
+        T.in_a = const_cast<double*>(in->current_acceleration);
+    }
+    T.new_p = out->new_position; T.new_v = out->new_velocity; T.new_a = out->new_acceleration; T.new_j = out->new_jerk;
+    T.result = out->result; T.new_calc = out->new_calculation; T.time_user = out->time;
+    rk::k_upd_step<<<(unsigned)((n * dof + 255) / 256), 256, 0, h->stream>>>(T);
+    h->launches += 1;
+    r->time_cur ^= 1;
+    RK_CUDA(cudaGetLastError());
     return RK_OK;
 }
 
