@@ -90,7 +90,7 @@ __device__ RK_S2_FN bool s2_acc0_acc1_vel(const S2& s, const Lim& L, Hit& h) {
         t[4] = -a_min / j_max;
         t[5] = tf - (t[0] + t[1] + t[2] + t[3] + 2.0 * t[4] + af / j_max);
         t[6] = t[4] + af / j_max;
-        RK_TRY(UDDU, L_ACC0_ACC1_VEL, j_max)
+        RK_TRY_INLINE(UDDU, L_ACC0_ACC1_VEL, j_max)
     }
     // Profile UDUD
     if ((-a0 + 4.0 * a_max - af) / j_max < tf) {
@@ -106,7 +106,7 @@ __device__ RK_S2_FN bool s2_acc0_acc1_vel(const S2& s, const Lim& L, Hit& h) {
         t[4] = t[2];
         t[5] = tf - (t[0] + t[1] + t[2] + t[3] + 2.0 * t[4] - af / j_max);
         t[6] = t[4] - af / j_max;
-        RK_TRY(UDUD, L_ACC0_ACC1_VEL, j_max)
+        RK_TRY_INLINE(UDUD, L_ACC0_ACC1_VEL, j_max)
     }
     return false;
 }
