@@ -197,6 +197,16 @@ enum {
 /* Trajectory::at_time for every trajectory and K sample times (trajectory.rs:158-189). */
 rk_status rk_at_time_batch(rk_handle* h, const rk_trajectories* traj, const rk_sample_desc* desc, const rk_sample_out* out);
 
+/* Trajectory::get_position_extrema (trajectory.rs:211-231, profile.rs:754-863): per (DoF, trajectory) the smallest and largest
+ * position of the whole motion and the times at which they are reached. [dof][n] arrays, each nullable. */
+rk_status rk_position_extrema_batch(rk_handle* h, const rk_trajectories* traj, double* p_min, double* p_max, double* t_min, double* t_max,
+                                    int32_t memory_space);
+
+/* Trajectory::get_first_time_at_position (trajectory.rs:233-246, profile.rs:865-895) for one query position per (DoF,
+ * trajectory): position[dof][n] -> time[dof][n], NaN where the reference returns None. */
+rk_status rk_first_time_at_position_batch(rk_handle* h, const rk_trajectories* traj, const double* position, double* time,
+                                          int32_t memory_space);
+
 /* ---- closed-loop control cycles: the batched Ruckig::update (ruckig.rs:266-321) ------------------------------------------
  * An rk_rollout is n independent (Ruckig, OutputParameter) pairs: per environment the input of its last calculation
  * (Ruckig::current_input), its trajectory and OutputParameter::time. One rk_update_batch call is one control cycle for all

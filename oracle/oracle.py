@@ -44,6 +44,8 @@ def load(flavour: str = "portable"):
     lib.rko_batch_validate.argtypes = [C.POINTER(cabi.RkBatchDesc), C.POINTER(cabi.RkBatchIn), C.c_int32, C.c_int32, vp]
     lib.rko_batch_read.argtypes = [vp, C.c_int32, vp]
     lib.rko_batch_read.restype = C.c_int32
+    lib.rko_batch_position_extrema.argtypes = [vp, vp]
+    lib.rko_batch_first_time_at_position.argtypes = [vp, vp, vp]
     lib.rko_batch_at_time.argtypes = [vp, C.POINTER(cabi.RkSampleDesc), C.POINTER(cabi.RkSampleOut), C.c_int32]
     lib.rko_batch_at_time.restype = C.c_double
     lib.rko_otg_new.argtypes = [C.c_int32, C.c_double, C.c_int32]
@@ -232,6 +234,19 @@ class OracleBatch:
         else:
             out = np.empty((cabi.FIELD_SLOTS[field], dof, n), dtype=np.float64)
         assert self.lib.rko_batch_read(self.h, field, out.ctypes.data) == 0
+        return out
+
+    def position_extrema(self) -> np.ndarray:
+        """Trajectory::get_position_extrema: [4][dof][n] = min, max, t_min, t_max."""
+        out = np.zeros((4, self.dof, self.n))
+        self.lib.rko_batch_position_extrema(self.h, out.ctypes.data)
+        return out
+
+    def first_time_at_position(self, positions: np.ndarray) -> np.ndarray:
+        """Trajectory::get_first_time_at_position for one query per (dof, trajectory); NaN = None."""
+        positions = np.ascontiguousarray(positions, dtype=np.float64)
+        out = np.zeros((self.dof, self.n))
+        self.lib.rko_batch_first_time_at_position(self.h, positions.ctypes.data, out.ctypes.data)
         return out
 
     def at_time(self, *, time_start: float, delta_time: float, steps: int, threads=1, want_jerk=True):

@@ -206,6 +206,30 @@ int32_t rko_batch_read(void* pb, int32_t field, void* dst) {
 
 // Trajectory::at_time for K samples per trajectory; sample times accumulate by
 // repeated addition like Ruckig::update does (ruckig.rs:293). Returns seconds.
+// Trajectory::get_position_extrema (trajectory.rs:211-231, one section): out = [4][dof][n] = min, max, t_min, t_max
+void rko_batch_position_extrema(void* pb, double* out) {
+    Batch* b = (Batch*)pb;
+    const int64_t n = b->n, stride = (int64_t)b->dof * n;
+    for (int64_t i = 0; i < n; ++i)
+        for (int d = 0; d < b->dof; ++d) {
+            const PositionExtrema e = get_position_extrema(b->traj[i].profiles[d]);
+            const int64_t o = (int64_t)d * n + i;
+            out[o] = e.min; out[stride + o] = e.max; out[2 * stride + o] = e.t_min; out[3 * stride + o] = e.t_max;
+        }
+}
+
+// Trajectory::get_first_time_at_position (trajectory.rs:233-246) for one query position per (dof, trajectory); NaN = None
+void rko_batch_first_time_at_position(void* pb, const double* positions, double* times) {
+    Batch* b = (Batch*)pb;
+    const int64_t n = b->n;
+    for (int64_t i = 0; i < n; ++i)
+        for (int d = 0; d < b->dof; ++d) {
+            const int64_t o = (int64_t)d * n + i;
+            double t, v, a;
+            times[o] = get_first_state_at_position(b->traj[i].profiles[d], positions[o], 0.0, t, v, a) ? t : std::nan("");
+        }
+}
+
 double rko_batch_at_time(void* pb, const rk_sample_desc* sd, const rk_sample_out* out, int32_t threads) {
     Batch* b = (Batch*)pb;
     const int64_t n = b->n;

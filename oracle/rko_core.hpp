@@ -760,6 +760,86 @@ static inline double shrink_interval(const Poly& p, double l, double h) {
 
 }  // namespace roots
 
+// ------------------------------------------------------------------ profile.rs:754-895 (trajectory query helpers)
+struct PositionExtrema { double min, max, t_min, t_max; };
+
+// profile.rs:754-776
+static inline void check_position_extremum(double t_ext, double t_sum, double t, double p, double v, double a, double j, PositionExtrema& ext) {
+    if (0.0 < t_ext && t_ext < t) {
+        double p_ext, v_ext, a_ext;
+        integrate(t_ext, p, v, a, j, p_ext, v_ext, a_ext);
+        if (a_ext > 0.0 && p_ext < ext.min) {
+            ext.min = p_ext;
+            ext.t_min = t_sum + t_ext;
+        } else if (a_ext < 0.0 && p_ext > ext.max) {
+            ext.max = p_ext;
+            ext.t_max = t_sum + t_ext;
+        }
+    }
+}
+
+// profile.rs:778-806
+static inline void check_step_for_position_extremum(double t_sum, double t, double p, double v, double a, double j, PositionExtrema& ext) {
+    if (p < ext.min) { ext.min = p; ext.t_min = t_sum; }
+    if (p > ext.max) { ext.max = p; ext.t_max = t_sum; }
+    if (j != 0.0) {
+        const double d = a * a - 2.0 * j * v;
+        if (std::fabs(d) < EPS) {
+            check_position_extremum(-a / j, t_sum, t, p, v, a, j, ext);
+        } else if (d > 0.0) {
+            const double d_sqrt = std::sqrt(d);
+            check_position_extremum((-a - d_sqrt) / j, t_sum, t, p, v, a, j, ext);
+            check_position_extremum((-a + d_sqrt) / j, t_sum, t, p, v, a, j, ext);
+        }
+    }
+}
+
+// profile.rs:808-863
+static inline PositionExtrema get_position_extrema(const Profile& q) {
+    PositionExtrema ext{INF, -INF, 0.0, 0.0};
+    if (q.brake.duration > 0.0 && q.brake.t[0] > 0.0) {
+        check_step_for_position_extremum(0.0, q.brake.t[0], q.brake.p[0], q.brake.v[0], q.brake.a[0], q.brake.j[0], ext);
+        if (q.brake.t[1] > 0.0)
+            check_step_for_position_extremum(q.brake.t[0], q.brake.t[1], q.brake.p[1], q.brake.v[1], q.brake.a[1], q.brake.j[1], ext);
+    }
+    double t_current_sum = 0.0;
+    for (int i = 0; i < 7; ++i) {
+        if (i > 0) t_current_sum = q.t_sum[i - 1];
+        check_step_for_position_extremum(t_current_sum + q.brake.duration, q.t[i], q.p[i], q.v[i], q.a[i], q.j[i], ext);
+    }
+    if (q.pf < ext.min) { ext.min = q.pf; ext.t_min = q.t_sum[6] + q.brake.duration; }
+    if (q.pf > ext.max) { ext.max = q.pf; ext.t_max = q.t_sum[6] + q.brake.duration; }
+    return ext;
+}
+
+// profile.rs:865-895. The roots of the cubic are visited in INSERTION order (get_data(), Q9), not ascending.
+static inline bool get_first_state_at_position(const Profile& q, double pt, double offset, double& time, double& vt, double& at) {
+    for (int i = 0; i < 7; ++i) {
+        if (std::fabs(q.p[i] - pt) < EPS) {
+            time = offset + (i > 0 ? q.t_sum[i - 1] : 0.0);
+            vt = q.v[i]; at = q.a[i];
+            return true;
+        }
+        if (q.t[i] == 0.0) continue;
+        const roots::PositiveSet<3> r = roots::solve_cub(q.j[i] / 6.0, q.a[i] / 2.0, q.v[i], q.p[i] - pt);
+        for (int k = 0; k < r.size; ++k) {
+            const double t_ = r.data[k];
+            if (0.0 < t_ && t_ <= q.t[i]) {
+                time = offset + t_ + (i > 0 ? q.t_sum[i - 1] : 0.0);
+                double pp;
+                integrate(t_, q.p[i], q.v[i], q.a[i], q.j[i], pp, vt, at);
+                return true;
+            }
+        }
+    }
+    if (std::fabs(q.pf - pt) < 1e-9) {
+        time = offset + q.t_sum[6];
+        vt = q.vf; at = q.af;
+        return true;
+    }
+    return false;
+}
+
 // ------------------------------------------------------------------ block.rs
 struct Interval {
     double left = 0.0, right = 0.0;

@@ -127,6 +127,7 @@ EXPORTS = (
     "rk_create", "rk_destroy", "rk_trajectories_create", "rk_trajectories_destroy", "rk_calculate_batch",
     "rk_validate_batch", "rk_at_time_batch", "rk_trajectories_read", "rk_sync", "rk_stream", "rk_kernel_launches",
     "rk_status_string", "rk_last_error", "rk_version", "rk_measure_fp64_peak", "rk_selftest_division",
+    "rk_position_extrema_batch", "rk_first_time_at_position_batch",
     "rk_rollout_create", "rk_rollout_destroy", "rk_rollout_reset", "rk_rollout_trajectories", "rk_update_batch",
 )
 
@@ -162,6 +163,8 @@ def load():
     lib.rk_status_string.restype = C.c_char_p
     lib.rk_last_error.restype = C.c_char_p
     lib.rk_version.restype = C.c_char_p
+    lib.rk_position_extrema_batch.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int32]
+    lib.rk_first_time_at_position_batch.argtypes = [vp, vp, vp, vp, C.c_int32]
     lib.rk_rollout_create.argtypes = [vp, C.c_int64, C.c_int32, C.POINTER(vp)]
     lib.rk_rollout_destroy.argtypes = [vp]
     lib.rk_rollout_reset.argtypes = [vp, vp]
@@ -170,7 +173,7 @@ def load():
     lib.rk_update_batch.argtypes = [vp, C.POINTER(RkBatchDesc), C.POINTER(RkBatchIn), vp, C.POINTER(RkUpdateOut), C.POINTER(C.c_int64)]
     for f in ("rk_create", "rk_destroy", "rk_trajectories_create", "rk_trajectories_destroy", "rk_calculate_batch",
               "rk_validate_batch", "rk_at_time_batch", "rk_trajectories_read", "rk_sync", "rk_rollout_create", "rk_rollout_destroy",
-              "rk_rollout_reset", "rk_update_batch"):
+              "rk_rollout_reset", "rk_update_batch", "rk_position_extrema_batch", "rk_first_time_at_position_batch"):
         getattr(lib, f).restype = C.c_int32
     _LIB = lib
     return lib

@@ -476,12 +476,30 @@ class BatchRuckig:
         eng = self._engine
         cabi.check(eng.lib.rk_at_time_batch(eng.h, self._traj, C.byref(sd), C.byref(so)))
 
+    def position_extrema(self) -> np.ndarray:
+        """Trajectory::get_position_extrema for every (DoF, trajectory): [4][dof][n] = min, max, t_min, t_max (host array)."""
+        out = np.zeros((4, self.degrees_of_freedom, self._n))
+        eng = self._engine
+        cabi.check(eng.lib.rk_position_extrema_batch(eng.h, self._traj, out[0].ctypes.data, out[1].ctypes.data, out[2].ctypes.data,
+                                                     out[3].ctypes.data, cabi.RK_MEM_HOST))
+        return out
+
+    def first_time_at_position(self, positions: np.ndarray) -> np.ndarray:
+        """Trajectory::get_first_time_at_position for one query position per (DoF, trajectory); NaN where the reference
+        returns None."""
+        positions = np.ascontiguousarray(positions, dtype=np.float64)
+        assert positions.shape == (self.degrees_of_freedom, self._n)
+        out = np.zeros_like(positions)
+        eng = self._engine
+        cabi.check(eng.lib.rk_first_time_at_position_batch(eng.h, self._traj, positions.ctypes.data, out.ctypes.data, cabi.RK_MEM_HOST))
+        return out
+
     def sync(self):
         cabi.check(self._engine.lib.rk_sync(self._engine.h))
 
-
     def kernel_launches(self) -> int:
         return int(self._engine.lib.rk_kernel_launches(self._engine.h))
+
 
 class BatchRollout:
     """n independent closed control loops on the device: the batched `Ruckig::update` (ruckig.rs:266-321).

@@ -332,6 +332,7 @@ constexpr double COS_120 = -0.50;
 constexpr double SIN_120 = 0.866025403784438600;  // roots.rs:12
 
 // roots.rs:132-231. Note the reference's shadowing in the d ~ 0 branch: the quadratic solved is a x^2 + b x + d.
+template <bool SORTED = true>  // false: roots in insertion order (Set::get_data, Q9), for the position query of profile.rs:876
 __device__ __noinline__ Roots solve_cub(double a, double b, double c, double d) {
     Roots roots;
     if (fabs(d) < EPS) {
@@ -401,7 +402,7 @@ __device__ __noinline__ Roots solve_cub(double a, double b, double c, double d) 
             roots.insert(w * COS_120 - bover3a);
         }
     }
-    roots.sort();
+    if (SORTED) roots.sort();
     return roots;
 }
 

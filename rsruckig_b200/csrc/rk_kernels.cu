@@ -391,6 +391,111 @@ __global__ void __launch_bounds__(256) k_upd_step(const StepParams T) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------ trajectory query helpers
+// profile.rs:754-776
+__device__ __forceinline__ void check_position_extremum(double t_ext, double t_sum, double t, double p, double v, double a, double j,
+                                                        double& e_min, double& e_max, double& e_tmin, double& e_tmax) {
+    if (0.0 < t_ext && t_ext < t) {
+        double p_ext, v_ext, a_ext;
+        integrate(t_ext, p, v, a, j, p_ext, v_ext, a_ext);
+        if (a_ext > 0.0 && p_ext < e_min) { e_min = p_ext; e_tmin = t_sum + t_ext; }
+        else if (a_ext < 0.0 && p_ext > e_max) { e_max = p_ext; e_tmax = t_sum + t_ext; }
+    }
+}
+
+// profile.rs:778-806
+__device__ __forceinline__ void check_step_for_position_extremum(double t_sum, double t, double p, double v, double a, double j,
+                                                                 double& e_min, double& e_max, double& e_tmin, double& e_tmax) {
+    if (p < e_min) { e_min = p; e_tmin = t_sum; }
+    if (p > e_max) { e_max = p; e_tmax = t_sum; }
+    if (j != 0.0) {
+        const double dsc = a * a - 2.0 * j * v;
+        if (fabs(dsc) < EPS) {
+            check_position_extremum(sdiv(-a, j), t_sum, t, p, v, a, j, e_min, e_max, e_tmin, e_tmax);
+        } else if (dsc > 0.0) {
+            const double d_sqrt = sqrt(dsc);
+            check_position_extremum(sdiv(-a - d_sqrt, j), t_sum, t, p, v, a, j, e_min, e_max, e_tmin, e_tmax);
+            check_position_extremum(sdiv(-a + d_sqrt, j), t_sum, t, p, v, a, j, e_min, e_max, e_tmin, e_tmax);
+        }
+    }
+}
+
+struct QueryParams {
+    int64_t n;
+    int32_t dof;
+    const double* prof;
+    double *e_min, *e_max, *e_tmin, *e_tmax;   // position extrema, [dof][n], nullable
+    const double* position; double* time;      // first time at position, [dof][n]
+};
+
+// Trajectory::get_position_extrema (trajectory.rs:211-231, profile.rs:808-863), one thread per (DoF, trajectory)
+__global__ void __launch_bounds__(256) k_position_extrema(const QueryParams Q) {
+    const int64_t total = (int64_t)Q.dof * Q.n;
+    const int64_t gi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gi >= total) return;
+    const double* q = Q.prof + gi;
+    const int64_t st = total;
+    double e_min = RK_INF, e_max = -RK_INF, e_tmin = 0.0, e_tmax = 0.0;
+    const double bdur = q[(int64_t)S_BRAKE_DUR * st];
+    const double bt0 = q[(int64_t)S_BRAKE_T * st], bt1 = q[(int64_t)(S_BRAKE_T + 1) * st];
+    if (bdur > 0.0 && bt0 > 0.0) {
+        check_step_for_position_extremum(0.0, bt0, q[(int64_t)S_BRAKE_P * st], q[(int64_t)S_BRAKE_V * st], q[(int64_t)S_BRAKE_A * st],
+                                         q[(int64_t)S_BRAKE_J * st], e_min, e_max, e_tmin, e_tmax);
+        if (bt1 > 0.0)
+            check_step_for_position_extremum(bt0, bt1, q[(int64_t)(S_BRAKE_P + 1) * st], q[(int64_t)(S_BRAKE_V + 1) * st],
+                                             q[(int64_t)(S_BRAKE_A + 1) * st], q[(int64_t)(S_BRAKE_J + 1) * st], e_min, e_max, e_tmin, e_tmax);
+    }
+    double t_current_sum = 0.0;
+#pragma unroll 1
+    for (int i = 0; i < 7; ++i) {
+        if (i > 0) t_current_sum = q[(int64_t)(S_TSUM + i - 1) * st];
+        check_step_for_position_extremum(t_current_sum + bdur, q[(int64_t)(S_T + i) * st], q[(int64_t)(S_P + i) * st], q[(int64_t)(S_V + i) * st],
+                                         q[(int64_t)(S_A + i) * st], q[(int64_t)(S_J + i) * st], e_min, e_max, e_tmin, e_tmax);
+    }
+    const double pf = q[(int64_t)S_PF * st], ts6 = q[(int64_t)(S_TSUM + 6) * st];
+    if (pf < e_min) { e_min = pf; e_tmin = ts6 + bdur; }
+    if (pf > e_max) { e_max = pf; e_tmax = ts6 + bdur; }
+    if (Q.e_min) Q.e_min[gi] = e_min;
+    if (Q.e_max) Q.e_max[gi] = e_max;
+    if (Q.e_tmin) Q.e_tmin[gi] = e_tmin;
+    if (Q.e_tmax) Q.e_tmax[gi] = e_tmax;
+}
+
+// Trajectory::get_first_time_at_position (trajectory.rs:233-246, profile.rs:865-895) for one query position per (DoF,
+// trajectory); NaN = None. The cubic's roots are visited in insertion order (Q9).
+__global__ void __launch_bounds__(256) k_first_time_at_position(const QueryParams Q) {
+    const int64_t total = (int64_t)Q.dof * Q.n;
+    const int64_t gi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gi >= total) return;
+    const double* q = Q.prof + gi;
+    const int64_t st = total;
+    const double pt = Q.position[gi];
+    double result = __longlong_as_double(0x7ff8000000000000LL);
+    bool found = false;
+#pragma unroll 1
+    for (int i = 0; i < 7 && !found; ++i) {
+        const double pi = q[(int64_t)(S_P + i) * st];
+        const double before = (i > 0) ? q[(int64_t)(S_TSUM + i - 1) * st] : 0.0;
+        if (fabs(pi - pt) < EPS) {
+            result = 0.0 + before;
+            found = true;
+            break;
+        }
+        const double ti = q[(int64_t)(S_T + i) * st];
+        if (ti == 0.0) continue;
+        const Roots r = solve_cub<false>(sdiv(q[(int64_t)(S_J + i) * st], 6.0), q[(int64_t)(S_A + i) * st] / 2.0, q[(int64_t)(S_V + i) * st], pi - pt);
+        for (int k = 0; k < r.n && !found; ++k) {
+            const double t_ = r.get(k);
+            if (0.0 < t_ && t_ <= ti) {
+                result = 0.0 + t_ + before;
+                found = true;
+            }
+        }
+    }
+    if (!found && fabs(q[(int64_t)S_PF * st] - pt) < 1e-9) result = 0.0 + q[(int64_t)(S_TSUM + 6) * st];
+    Q.time[gi] = result;
+}
+
 // ------------------------------------------------------------------------------------------------ FP64 peak probe
 // 8 independent DFMA chains per thread, all in registers; `iters` x 8 x 2 flop per thread.
 __global__ void __launch_bounds__(256) k_fp64_peak(double* sink, int iters, double a, double b) {
@@ -1106,6 +1211,61 @@ rk_status rk_update_batch(rk_handle* h, const rk_batch_desc* desc, const rk_batc
     h->launches += 1;
     r->time_cur ^= 1;
     RK_CUDA(cudaGetLastError());
+    return RK_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ trajectory query helpers (host)
+rk_status rk_position_extrema_batch(rk_handle* h, const rk_trajectories* traj, double* p_min, double* p_max, double* t_min, double* t_max,
+                                    int32_t memory_space) {
+    if (!h || !traj) return fail(RK_ERR_INVALID_ARGUMENT, "NULL argument to rk_position_extrema_batch");
+    if (traj->n == 0) return RK_OK;
+    RK_CUDA(cudaSetDevice(h->device));
+    const bool host = memory_space == RK_MEM_HOST;
+    const size_t per = sizeof(double) * (size_t)traj->n * (size_t)traj->dof;
+    double* dst[4] = {p_min, p_max, t_min, t_max};
+    double* dev[4] = {p_min, p_max, t_min, t_max};
+    if (host) {
+        rk_status st = ensure_stage(h, 4 * per, 0);
+        if (st != RK_OK) return st;
+        for (int k = 0; k < 4; ++k) dev[k] = dst[k] ? (double*)((char*)h->stage_dev + k * per) : nullptr;
+    }
+    rk::QueryParams Q{};
+    Q.n = traj->n; Q.dof = traj->dof; Q.prof = traj->prof;
+    Q.e_min = dev[0]; Q.e_max = dev[1]; Q.e_tmin = dev[2]; Q.e_tmax = dev[3];
+    rk::k_position_extrema<<<(unsigned)(((int64_t)traj->n * traj->dof + 255) / 256), 256, 0, h->stream>>>(Q);
+    h->launches += 1;
+    RK_CUDA(cudaGetLastError());
+    if (host) {
+        for (int k = 0; k < 4; ++k) if (dst[k]) RK_CUDA(cudaMemcpyAsync(dst[k], dev[k], per, cudaMemcpyDeviceToHost, h->stream));
+        RK_CUDA(cudaStreamSynchronize(h->stream));
+    }
+    return RK_OK;
+}
+
+rk_status rk_first_time_at_position_batch(rk_handle* h, const rk_trajectories* traj, const double* position, double* time, int32_t memory_space) {
+    if (!h || !traj || !position || !time) return fail(RK_ERR_INVALID_ARGUMENT, "NULL argument to rk_first_time_at_position_batch");
+    if (traj->n == 0) return RK_OK;
+    RK_CUDA(cudaSetDevice(h->device));
+    const bool host = memory_space == RK_MEM_HOST;
+    const size_t per = sizeof(double) * (size_t)traj->n * (size_t)traj->dof;
+    const double* d_pos = position;
+    double* d_time = time;
+    if (host) {
+        rk_status st = ensure_stage(h, 2 * per, 0);
+        if (st != RK_OK) return st;
+        RK_CUDA(cudaMemcpyAsync(h->stage_dev, position, per, cudaMemcpyHostToDevice, h->stream));
+        d_pos = (const double*)h->stage_dev;
+        d_time = (double*)((char*)h->stage_dev + per);
+    }
+    rk::QueryParams Q{};
+    Q.n = traj->n; Q.dof = traj->dof; Q.prof = traj->prof; Q.position = d_pos; Q.time = d_time;
+    rk::k_first_time_at_position<<<(unsigned)(((int64_t)traj->n * traj->dof + 255) / 256), 256, 0, h->stream>>>(Q);
+    h->launches += 1;
+    RK_CUDA(cudaGetLastError());
+    if (host) {
+        RK_CUDA(cudaMemcpyAsync(time, d_time, per, cudaMemcpyDeviceToHost, h->stream));
+        RK_CUDA(cudaStreamSynchronize(h->stream));
+    }
     return RK_OK;
 }
 

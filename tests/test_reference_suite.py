@@ -1,8 +1,8 @@
 """Ports of the reference's integration tests (test_suite/tests/tests.rs), replayed against the oracle (CPU, both math
 flavours — this pins the oracle) and against the CUDA path (-m gpu). Tolerances are the reference's (abs <= 1e-4).
 
-Not ported: the `get_position_extrema` / `get_first_time_at_position` assertions of test_secondary (tests.rs:190-237);
-those query helpers are outside the hot path.
+The `get_position_extrema` / `get_first_time_at_position` assertions of test_secondary (tests.rs:190-237) live in
+tests/test_queries.py (batched helpers).
 """
 import numpy as np
 import pytest
