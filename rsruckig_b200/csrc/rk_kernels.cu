@@ -21,6 +21,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -641,6 +642,11 @@ struct rk_trajectories {
     int32_t* detail = nullptr;
 };
 
+static bool poison_scratch() {
+    static const bool on = [] { const char* e = std::getenv("RK_B200_POISON"); return e && e[0] == '1'; }();
+    return on;
+}
+
 static void free_scratch(rk_handle::Scratch& c) {
     if (!c.ws) return;
     cudaFree(c.ws); cudaFree(c.rec); cudaFree(c.vl); cudaFree(c.wmeta); cudaFree(c.wsrc); cudaFree(c.wqmask); cudaFree(c.rq_item); cudaFree(c.rq_root);
@@ -908,6 +914,20 @@ rk_status rk_calculate_batch(rk_handle* h, const rk_batch_desc* desc, const rk_b
         unsigned grid_list = (unsigned)h->sm_count * 16u;
         if (grid_list > grid_items) grid_list = grid_items;
         const unsigned grid_vel = (grid_list * 128u + RK_LS_BLOCK - 1u) / RK_LS_BLOCK;
+        if (poison_scratch()) {  // debugging aid (RK_B200_POISON=1): no kernel may depend on what an earlier call left behind
+            const size_t it = (size_t)c.ws_items;
+            RK_CUDA(cudaMemsetAsync(c.ws, 0xFF, sizeof(double) * rk::WS_SLOTS * it, cs));
+            RK_CUDA(cudaMemsetAsync(c.vl, 0xFF, sizeof(double) * rk::VL_ITEM_DOUBLES * it, cs));
+            RK_CUDA(cudaMemsetAsync(c.rec, 0xFF, sizeof(double2) * 6 * it, cs));
+            RK_CUDA(cudaMemsetAsync(c.wmeta, 0xFF, sizeof(uint32_t) * rk::WM_WORDS * it, cs));
+            RK_CUDA(cudaMemsetAsync(c.wsrc, 0xFF, it, cs));
+            RK_CUDA(cudaMemsetAsync(c.wqmask, 0xFF, sizeof(uint32_t) * 10 * it, cs));
+            RK_CUDA(cudaMemsetAsync(c.rq_item, 0xFF, sizeof(uint2) * 12 * it, cs));
+            RK_CUDA(cudaMemsetAsync(c.rq_root, 0xFF, sizeof(double) * 8 * it, cs));
+            RK_CUDA(cudaMemsetAsync(c.list[0], 0xFF, sizeof(uint32_t) * it, cs));
+            RK_CUDA(cudaMemsetAsync(c.list[1], 0xFF, sizeof(uint32_t) * it, cs));
+            RK_CUDA(cudaMemsetAsync(c.pend, 0xFF, sizeof(uint32_t) * it, cs));
+        }
         RK_CUDA(cudaMemsetAsync(c.counters, 0, sizeof(uint32_t) * RK_N_COUNTERS, cs));
         rk::k1_setup<<<grid_items, 128, 0, cs>>>(P);
         const unsigned grid_fam = (unsigned)((2 * items + 127) / 128);
