@@ -836,10 +836,11 @@ rk_status rk_calculate_batch(rk_handle* h, const rk_batch_desc* desc, const rk_b
     P.prof = traj->prof; P.codes = traj->codes; P.status = traj->status; P.duration = traj->duration; P.imd = traj->imd;
     P.limiting = traj->limiting; P.detail = traj->detail;
 
-    int64_t cn_max = CHUNK_ITEMS / desc->dof;
-    if (cn_max > desc->n) cn_max = desc->n;
+    // chunks of about CHUNK_ITEMS (DoF, trajectory) items, equally sized (8 Mi x 7 DoF = exactly 14 x 4 Mi items must not
+    // become 14 chunks and a 15th of four trajectories)
+    const int64_t n_chunks = ((int64_t)desc->n * desc->dof + CHUNK_ITEMS - 1) / CHUNK_ITEMS;
+    const int64_t cn_max = (desc->n + n_chunks - 1) / n_chunks;
     // more than one chunk: consecutive chunks rotate over RK_LANES scratch sets and streams
-    const int64_t n_chunks = (desc->n + cn_max - 1) / cn_max;
     const int lanes = (int)(n_chunks < RK_LANES ? n_chunks : RK_LANES);
     for (int k = 0; k < lanes; ++k) {
         st = ensure_scratch(h, k, cn_max * desc->dof);
