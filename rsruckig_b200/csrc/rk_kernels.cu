@@ -1,23 +1,17 @@
-// rk_kernels.cu — the four kernels of the batched calculator and the C ABI
-// (include/ruckig_b200.h). sm_100a only; compiled with --fmad=false.
+// rk_kernels.cu — the C ABI (include/ruckig_b200.h) and the kernels that are not part of the calculation pipeline.
+// sm_100a only; compiled with --fmad=false.
 //
-//   k_step1   one thread per (DoF, trajectory): validation of that DoF, brake
-//             pre-trajectory, Step 1 (extremal profiles -> block of feasible
-//             durations)                          calculator_target.rs:300-474
-//   k_sync    one thread per trajectory: status from validation / Step-1
-//             failures, synchronisation (common duration, limiting DoF),
-//             phase synchronisation, per-DoF decision "reuse an extremal
-//             profile or run Step 2"               calculator_target.rs:150-275, :475-747
-//   k_step2   one thread per (DoF, trajectory): Step 2 where needed, expansion
-//             of the winning compact profile into the full Profile arrays
-//                                                   calculator_target.rs:749-830
-//   k_at_time one thread per (DoF, trajectory), loop over K sample times
-//                                                   trajectory.rs:52-189
+//   rk_calculate_batch           launches the pipeline of rk_pipeline.cuh (see the map there) per chunk of ~4 Mi (DoF,
+//                                trajectory) items; chunks rotate over two scratch sets / streams; host inputs are staged
+//   k_validate                   InputParameter::validate with arbitrary flags          input_parameter.rs:251-420
+//   k_at_time                    Trajectory::at_time for K sample times                  trajectory.rs:52-189
+//   k_position_extrema,
+//   k_first_time_at_position     the trajectory query helpers                            profile.rs:754-895
+//   k_upd_dirty/gather/scatter/step   the closed-loop cycle (rk_update_batch)            ruckig.rs:266-321
+//   k_fp64_peak, k_selftest_division  measurement / self-test helpers
 //
-// Items are laid out DoF-major / trajectory-fastest, so a warp always works on
-// 32 consecutive trajectories of the same DoF: all global accesses are
-// coalesced 256-byte rows, and every lane of a warp runs the same solver
-// family with the same per-DoF options.
+// Dense arrays are laid out DoF-major / trajectory-fastest, so a warp works on 32 consecutive trajectories of one DoF and
+// its global accesses are coalesced 256-byte rows; data read through compacted lists is packed per item (rk_params.cuh).
 #include <cuda_runtime.h>
 
 #include <cstdio>

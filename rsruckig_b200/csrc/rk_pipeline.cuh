@@ -4,15 +4,20 @@
 // 300-390 KB of SASS per kernel thrashed the instruction cache (ncu: `no_instruction` was the top stall) and warps
 // averaged 5-7 active lanes. The pipeline below keeps every kernel's code small and every warp on one solver family:
 //
-//   k1_setup            validation, brake pre-trajectory, zero-limit and non-third-order Step 1 (cheap closed forms)
-//   k1_family<0..4>     the Step-1 candidate families of the third-order position interface (three quartics, ACC0_ACC1, VEL),
-//                       one thread per (direction, DoF, trajectory), validated candidates go to per-family sub-lists in HBM
-//   k1_block            candidate list -> block of feasible durations (block.rs), numerical rescues
-//   k_sync              one thread per trajectory: status, common duration, limiting DoF, phase sync, per-DoF decision
-//   k2_first            everything that needs no Step-2 chain is finalised; Step-2 items run stage 0 of the chain
-//   k2_stage<F> x15     stage s of the chain (position_third_step2.rs:2449-2482) over the compacted list of items that
-//                       are still unsolved; solved items are expanded and stored at once, the rest move to the next list
-//   k2_fail             items that survive all 16 stages -> ErrorExecutionTimeCalculation
+//   k1_setup            validation, brake pre-trajectory, the packed per-item record, zero-limit and non-third-order Step 1
+//   k1_quartic_roots<T> the three quartic families of Step 1 (NONE, ACC0, ACC1), one thread per (direction, DoF, trajectory):
+//     + _check<T>       coefficients + closed-form roots -> root queue -> Newton polish + profile check with full warps
+//   k1_closed_cands     the closed-form families (ACC0_ACC1, four VEL variants): screened t[7] candidates -> queue ->
+//     + k1_cand_check   profile check with full warps; valid candidates set a byte of their sub-list's mask word
+//   k1_block            masks + stored durations -> block of feasible durations (block.rs) on slot references; k1_rescue for the
+//                       rare items without any candidate
+//   k_sync              one thread per trajectory: status, common duration, limiting DoF, phase sync, per-DoF decision,
+//                       list of the items that need the Step-2 chain
+//   k2_stage<F>         stage s of the chain (position_third_step2.rs:2449-2482) over the compacted list of items that are
+//                       still unsolved; a solved item leaves t[7] + jerk + codes, the rest move to the next list.
+//                       VEL/UDDU = k2_vel_scan_uddu -> k2_polish -> k2_vel_check_uddu, VEL/UDUD = k2_vel<8> (lockstep)
+//   k2_fail             items that survive all 18 stages -> ErrorExecutionTimeCalculation
+//   k_expand            every item: compact result -> the full profile arrays, coalesced rows
 //
 // Lists are compacted with warp-aggregated atomics; ordering inside a list does not matter (items are independent).
 #pragma once
@@ -36,16 +41,6 @@ namespace rk {
 // Direction slot 0 is UP for general items and sign(pd) for rest-target items (vf ~ 0 && af ~ 0). A slot holds t[7] and the duration.
 __device__ __forceinline__ int sub_slot_base(int sub) { return sub < 6 ? sub * 4 : (sub < 8 ? 24 + (sub - 6) * 2 : 28 + (sub - 8) * 4); }
 __device__ __forceinline__ int sub_limits(int sub) { return sub < 2 ? (int)L_NONE : (sub < 4 ? (int)L_ACC0 : (sub < 6 ? (int)L_ACC1 : (sub < 8 ? (int)L_ACC0_ACC1 : (int)L_VEL))); }
-
-__device__ __forceinline__ void sublist_get(const Params& P, int64_t wi, int64_t wstride, int sub, int k, const Lim& L, Cand& c) {
-    const double* base = vl_slot(P, wi, sub_slot_base(sub) + k);
-#pragma unroll
-    for (int q = 0; q < 7; ++q) c.t[q] = base[q];
-    c.ctrl = L.j_max;
-    c.ctrl2 = 0.0;
-    c.dur = t_sum6(c.t);
-    c.lim = sub_limits(sub); c.dir = (L.v_max > 0.0) ? DIR_UP : DIR_DOWN; c.cs = UDDU;
-}
 
 __device__ __forceinline__ void write_block(const Params& P, int64_t wi, int64_t wstride, const BlockRec& blk, bool found, uint32_t& meta) {
     double* w = P.ws + wi;
