@@ -60,8 +60,14 @@ struct SampleParams {
 // segment (three compares) and only falls back to the general search of trajectory.rs:60-140 when one of them fails. The
 // first version ran the general search for every sample: 186 instructions per sample, 84 % of the issue slots busy at
 // 3.2 TB/s; this form is bound by the output stream.
+#ifndef RK_AT_BLOCK
+#define RK_AT_BLOCK 128
+#endif
+#ifndef RK_AT_STORE
+#define RK_AT_STORE __stcs
+#endif
 template <bool PVA_ONLY>  // true: position, velocity and acceleration are all requested, jerk and section are not
-__global__ void __launch_bounds__(256) k_at_time(const SampleParams S) {
+__global__ void __launch_bounds__(RK_AT_BLOCK) k_at_time(const SampleParams S) {
     const int64_t total = (int64_t)S.dof * S.n;
     const int64_t gi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gi >= total) return;
@@ -169,14 +175,14 @@ __global__ void __launch_bounds__(256) k_at_time(const SampleParams S) {
         const double v = sv + t0 * (sa + tj / 2.0);
         const double a = sa + tj;
         if (PVA_ONLY) {
-            __stcs((double*)out_p, p); out_p += stride;
-            __stcs((double*)out_v, v); out_v += stride;
-            __stcs((double*)out_a, a); out_a += stride;
+            RK_AT_STORE((double*)out_p, p); out_p += stride;
+            RK_AT_STORE((double*)out_v, v); out_v += stride;
+            RK_AT_STORE((double*)out_a, a); out_a += stride;
         } else {
-            if (out_p) { __stcs((double*)out_p, p); out_p += stride; }
-            if (out_v) { __stcs((double*)out_v, v); out_v += stride; }
-            if (out_a) { __stcs((double*)out_a, a); out_a += stride; }
-            if (out_j) { __stcs((double*)out_j, sj); out_j += stride; }
+            if (out_p) { RK_AT_STORE((double*)out_p, p); out_p += stride; }
+            if (out_v) { RK_AT_STORE((double*)out_v, v); out_v += stride; }
+            if (out_a) { RK_AT_STORE((double*)out_a, a); out_a += stride; }
+            if (out_j) { RK_AT_STORE((double*)out_j, sj); out_j += stride; }
             if (out_s) { *out_s = section; out_s += S.n; }
         }
     }
@@ -1056,9 +1062,9 @@ rk_status rk_at_time_batch(rk_handle* h, const rk_trajectories* traj, const rk_s
     if (slices > (desc->steps + 31) / 32) slices = (desc->steps + 31) / 32;
     if (slices < 1) slices = 1;
     S.k_chunk = (int32_t)((desc->steps + slices - 1) / slices);
-    const dim3 grid((unsigned)((total + 255) / 256), (unsigned)((desc->steps + S.k_chunk - 1) / S.k_chunk), 1);
-    if (S.pos && S.vel && S.acc && !S.jerk && !S.section) rk::k_at_time<true><<<grid, 256, 0, h->stream>>>(S);
-    else rk::k_at_time<false><<<grid, 256, 0, h->stream>>>(S);
+    const dim3 grid((unsigned)((total + RK_AT_BLOCK - 1) / RK_AT_BLOCK), (unsigned)((desc->steps + S.k_chunk - 1) / S.k_chunk), 1);
+    if (S.pos && S.vel && S.acc && !S.jerk && !S.section) rk::k_at_time<true><<<grid, RK_AT_BLOCK, 0, h->stream>>>(S);
+    else rk::k_at_time<false><<<grid, RK_AT_BLOCK, 0, h->stream>>>(S);
     h->launches += 1;
     RK_CUDA(cudaGetLastError());
     if (host) {
