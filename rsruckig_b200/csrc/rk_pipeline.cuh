@@ -1011,7 +1011,8 @@ __global__ void __launch_bounds__(RK_LS_BLOCK, RK_LS_MINB) k2_vel(const Params P
         const bool up_first = s.pd > it.tf * it.b.v0;
         const Lim L = lim_dir(up_first != second_direction, it.x.v_max, it.x.v_min, it.x.a_max, it.x.a_min, it.x.j_max);
         Hit h;
-        const bool found = (F == 1) ? s2_vel_uddu_lockstep(s, L, h, active) : s2_vel_udud_lockstep(s, L, h, active);
+        static_assert(F == 8, "the UDDU half runs as k2_vel_scan_uddu -> k2_polish -> k2_vel_check_uddu");
+        const bool found = s2_vel_udud_lockstep(s, L, h, active);
         RK_PHASE_BARRIER();
         if (found) put_solution(P, it, wstride, h);
         append_unsolved(list_out, P.counters + step + 1, active && !found, wi);

@@ -283,26 +283,6 @@ __device__ __forceinline__ bool vel_uddu_candidates(const S2& s, const Lim& L, H
     return found;
 }
 
-__device__ __forceinline__ bool s2_vel_uddu_lockstep(const S2& s, const Lim& L, Hit& h, bool active) {
-    double pol[6], c_lo[6], c_hi[6];
-    int n_cand;
-    bool found = vel_uddu_candidates(s, L, h, active, pol, c_lo, c_hi, n_cand);
-    // phase D: polish and validate the candidates in order, one candidate index per round of the whole block
-#pragma unroll 1
-    for (int c = 0; c < 6; ++c) {
-        const bool mine = active && !found && c < n_cand;
-        if (!__syncthreads_or(mine)) break;
-        double root = 0.0;
-        if (mine) {
-            const double lo = c_lo[c], hi = c_hi[c];
-            root = (lo != hi) ? shrink_interval<6>(pol, lo, hi) : hi;
-        }
-        RK_PHASE_BARRIER();
-        if (mine) found = vel_uddu_root(s, L, h, root);
-    }
-    return found;
-}
-
 // UDUD half of time_vel (:825-973)
 __device__ RK_S2_FN bool s2_vel_udud(const S2& s, const Lim& L, Hit& h) {
     RK_S2_LOCALS
@@ -392,7 +372,7 @@ __device__ RK_S2_FN bool s2_vel_udud(const S2& s, const Lim& L, Hit& h) {
     return false;
 }
 
-// Lockstep form of the UDUD half (see s2_vel_uddu_lockstep).
+// Lockstep form of the UDUD half: phases A-C as above, then the two bracketing levels inside the kernel.
 __device__ __forceinline__ bool s2_vel_udud_lockstep(const S2& s, const Lim& L, Hit& h, bool active) {
     RK_S2_LOCALS
     const real a0_p5 = s.a0_p5, a0_p6 = s.a0_p6, af_p6 = s.af_p6;
