@@ -12,10 +12,12 @@ is fixed as N grows ("weak" scaling); trajectories are independent, ranks never 
 value  = trajectories/s, inputs and outputs resident in HBM, CUDA events on the library's stream, max over ranks.
 e2e    = the same through the C ABI with HOST buffers (pinned): H2D of the nine input arrays, the three kernels, D2H of
          status + duration — all inside the timed region.
-roofline: the path is FP64-pipe bound, so `bound` is "fp64": achieved = FP64 flop per trajectory
-         (profiles/algorithmic_ops.json: adds + muls + 2 x FMAs the algorithm executes for the bench distribution, counted
-         with ncu) x trajectories/s; peak = a DFMA probe run on the same GPU right before the timed region
-         (MEASURED_PEAKS.json has no FP64 entry). The HBM side is reported next to it against MEASURED_PEAKS.json's copy
+roofline: the path is FP64-pipe bound, so `bound` is "fp64": achieved = ALGORITHMIC FP64 operations per
+         trajectory (profiles/algorithmic_ops_oracle.json: the oracle compiled with a counting scalar, add/sub/mul/div/sqrt/libm
+         call = 1 each, tools/count_algorithmic_ops.py) x trajectories/s; `executed` beside it = the FP64 flop the kernels
+         really execute (profiles/algorithmic_ops.json, ncu: adds + muls + 2 x FMAs, divisions and square roots expanded into
+         their Newton iterations, candidates evaluated that the reference skips); peak = a DFMA probe run on the same GPU
+         right before the timed region (MEASURED_PEAKS.json has no FP64 entry). The HBM side is reported next to it against MEASURED_PEAKS.json's copy
          bandwidth. `latency_64k` (p50 of one 64Ki batch) and `at_time` (configs[3] rollout, HBM-write bound) ride along.
 cpu_baseline: the C++ restatement of the reference (oracle/, glibc libm) on this box's host cores, on a bounded sample.
 """
@@ -43,11 +45,21 @@ BYTES_OUT = (16 * DOF + 3) * 8         # compact result record of SURVEY.md §8d
 
 
 def algorithmic_flop_per_trajectory() -> tuple[float, str]:
+    """operations of the reference algorithm itself, counted by the op-counting build of the oracle."""
+    p = os.path.join(ROOT, "profiles", "algorithmic_ops_oracle.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["flop_per_trajectory_7dof"]), d["definition"] + f" ({d['n']} trajectories of the bench distribution, tools/count_algorithmic_ops.py)"
+    return 60e3, "a-priori static estimate of SURVEY.md §8d (lower end); the op-counting oracle has not been run"
+
+
+def executed_flop_per_trajectory() -> tuple[float, str]:
+    """What the kernels execute (ncu), as opposed to what the algorithm needs."""
     p = os.path.join(ROOT, "profiles", "algorithmic_ops.json")
     if os.path.exists(p):
         d = json.load(open(p))
-        return float(d["flop_per_trajectory_7dof"]), d.get("how", "op-counting oracle")
-    return 60e3, "a-priori static estimate of SURVEY.md §8d (lower end); the op-counting oracle has not been run"
+        return float(d["flop_per_trajectory_7dof"]), d.get("how", "ncu")
+    return 0.0, "not measured"
 
 
 def measured_peaks() -> dict:
@@ -398,6 +410,7 @@ def run_b200(args):
 
     if rank == 0:
         flop, flop_how = algorithmic_flop_per_trajectory()
+        xflop, xflop_how = executed_flop_per_trajectory()
         peaks = measured_peaks()
         per_gpu = value / world
         achieved_tflops = flop * per_gpu / 1e12
@@ -421,6 +434,8 @@ def run_b200(args):
                                         "k2_vel_scan_uddu + k2_polish + k2_vel_check_uddu, VEL/UDUD as k2_vel<8>), k2_fail, k_expand; no single kernel "
                                         "holds more than 11 % of the step (profiles/r1_ncu_summary.md), so the roofline is quoted for the whole step",
                              "flop_per_trajectory": flop, "flop_how": flop_how,
+                             "executed": {"flop_per_trajectory": xflop, "achieved": xflop * per_gpu / 1e12, "unit": "TFLOP/s",
+                                          "frac": xflop * per_gpu / 1e12 / fp64_peak_tflops if fp64_peak_tflops else None, "how": xflop_how},
                              "fp64_issue_frac": (ops.get("fp64_instructions") or 0) * per_gpu / (fp64_peak_tflops * 1e12 / 2) if fp64_peak_tflops else None,
                              "peak_how": "DFMA probe (rk_measure_fp64_peak) on this GPU before the timed region, FMA = 2 flop; the kernels run "
                                          "with --fmad=false, so an add or a mul fills a DFMA issue slot with 1 flop (fp64_issue_frac = FP64 "

@@ -27,7 +27,7 @@ out = {"flop_per_trajectory_7dof": (dadd + dmul + 2 * dfma) / n, "dadd": dadd / 
        "fp64_instructions": (dadd + dmul + dfma) / n, "thread_instructions": s("smsp__thread_inst_executed.sum") / n,
        "dram_bytes_per_trajectory": (s("dram__bytes_read.sum") + s("dram__bytes_write.sum")) / n, "kernel_launches_per_step": per_step,
        "sum_of_kernel_durations_us": s("gpu__time_duration.sum") / 1e3,
-       "how": f"FP64 operations executed per 7-DoF trajectory by one calculate step (all {per_step} kernel launches), counted by ncu (smsp__sass_thread_inst_executed_op_{{dadd,dmul,dfma}}_pred_on.sum, flop = dadd + dmul + 2*dfma) on {n} trajectories of the bench distribution. The kernels run the reference's operation sequence without FMA contraction, so dadd + dmul are the algorithm's additions and multiplications (plus what the kernel pipeline recomputes when an item is picked up again by a later kernel); the dfma are the Newton iterations inside divisions and square roots. An op-counting build of the oracle was attempted and dropped (see DESIGN.md)."}
+       "how": f"FP64 operations executed per 7-DoF trajectory by one calculate step (all {per_step} kernel launches), counted by ncu (smsp__sass_thread_inst_executed_op_{{dadd,dmul,dfma}}_pred_on.sum, flop = dadd + dmul + 2*dfma) on {n} trajectories of the bench distribution. The kernels run the reference's operation sequence without FMA contraction, so dadd + dmul are the algorithm's additions and multiplications (plus what the kernel pipeline recomputes when an item is picked up again by a later kernel); the dfma are the Newton iterations inside divisions and square roots. The algorithm's own count (op-counting build of the oracle) is profiles/algorithmic_ops_oracle.json."}
 json.dump(out, open("gpurun_out/algorithmic_ops.json", "w"), indent=1)
 print(json.dumps({k: v for k, v in out.items() if k != "how"}))
 PY
