@@ -587,6 +587,15 @@ rk_status fail(rk_status s, const std::string& m) {
 #ifndef RK_LANES
 #define RK_LANES 2
 #endif
+#ifndef RK_BIG_LANES
+#define RK_BIG_LANES 2  // scratch sets / streams used by batches of more than one full chunk (a third set: no gain, +12 GB)
+#endif
+#ifndef RK_SMALL_SPLIT
+#define RK_SMALL_SPLIT 2  // 64 Ki x 7-DoF: 1.27 -> 1.19 ms; 4 parts on 2 or 4 streams measured slower
+#endif
+#ifndef RK_SMALL_SPLIT_MIN_ITEMS
+#define RK_SMALL_SPLIT_MIN_ITEMS (192 * 1024)
+#endif
 #ifndef RK_STAGE_BUFS
 #define RK_STAGE_BUFS 4  // host-buffer calls: input chunks are copied this many chunks ahead of the kernels
 #endif
@@ -688,6 +697,27 @@ static rk_status ensure_stage(rk_handle* h, size_t dev_bytes, size_t pinned_byte
         h->stage_pinned_bytes = pinned_bytes;
     }
     return RK_OK;
+}
+
+// One launch of a pipeline kernel. With RK_PDL the launch carries the programmatic-stream-serialization attribute and the
+// kernel itself waits for its predecessor (RK_PDL_ENTER).
+template <typename... KA, typename... A>
+static inline void rk_launch(void (*kern)(KA...), unsigned grid, unsigned block, cudaStream_t s, A... args) {
+#if RK_PDL
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kern, KA(args)...);
+#else
+    kern<<<grid, block, 0, s>>>(KA(args)...);
+#endif
 }
 
 static rk_status fill_params(rk::Params& P, const rk_batch_desc* desc, const rk_batch_in* in) {
@@ -838,10 +868,15 @@ rk_status rk_calculate_batch(rk_handle* h, const rk_batch_desc* desc, const rk_b
 
     // chunks of about CHUNK_ITEMS (DoF, trajectory) items, equally sized (8 Mi x 7 DoF = exactly 14 x 4 Mi items must not
     // become 14 chunks and a 15th of four trajectories)
-    const int64_t n_chunks = ((int64_t)desc->n * desc->dof + CHUNK_ITEMS - 1) / CHUNK_ITEMS;
+    int64_t n_chunks = ((int64_t)desc->n * desc->dof + CHUNK_ITEMS - 1) / CHUNK_ITEMS;
+    // a batch that fits one chunk but is large enough to fill the GPU several times over is still split, so that the
+    // short list-driven kernels of one part run beside the long kernels of the other (latency of a 64 Ki batch)
+    const bool small_split = n_chunks < RK_SMALL_SPLIT && (int64_t)desc->n * desc->dof >= (int64_t)RK_SMALL_SPLIT_MIN_ITEMS;
+    if (small_split) n_chunks = RK_SMALL_SPLIT;
     const int64_t cn_max = (desc->n + n_chunks - 1) / n_chunks;
     // more than one chunk: consecutive chunks rotate over RK_LANES scratch sets and streams
-    const int lanes = (int)(n_chunks < RK_LANES ? n_chunks : RK_LANES);
+    const int max_lanes = small_split ? RK_LANES : RK_BIG_LANES;
+    const int lanes = (int)(n_chunks < max_lanes ? n_chunks : max_lanes);
     for (int k = 0; k < lanes; ++k) {
         st = ensure_scratch(h, k, cn_max * desc->dof);
         if (st != RK_OK) return st;
@@ -930,42 +965,47 @@ rk_status rk_calculate_batch(rk_handle* h, const rk_batch_desc* desc, const rk_b
             RK_CUDA(cudaMemsetAsync(c.pend, 0xFF, sizeof(uint32_t) * it, cs));
         }
         RK_CUDA(cudaMemsetAsync(c.counters, 0, sizeof(uint32_t) * RK_N_COUNTERS, cs));
-        rk::k1_setup<<<grid_items, 128, 0, cs>>>(P);
+        rk_launch(rk::k1_setup, grid_items, 128, cs, P);
         const unsigned grid_fam = (unsigned)((2 * items + 127) / 128);
-        rk::k1_quartic_roots<0><<<grid_fam, 128, 0, cs>>>(P);
-        rk::k1_quartic_check<0><<<grid_list, 128, 0, cs>>>(P);
-        rk::k1_quartic_roots<1><<<grid_fam, 128, 0, cs>>>(P);
-        rk::k1_quartic_check<1><<<grid_list, 128, 0, cs>>>(P);
-        rk::k1_quartic_roots<2><<<grid_fam, 128, 0, cs>>>(P);
-        rk::k1_quartic_check<2><<<grid_list, 128, 0, cs>>>(P);
-        rk::k1_closed_cands<<<grid_fam, 128, 0, cs>>>(P);
-        rk::k1_cand_check<<<grid_list, 128, 0, cs>>>(P);
-        rk::k1_block<<<grid_items, 128, 0, cs>>>(P);
-        rk::k1_rescue<<<(unsigned)h->sm_count, 128, 0, cs>>>(P);
-        rk::k_sync<<<(unsigned)((P.cn + 127) / 128), 128, 0, cs>>>(P);
+        rk_launch(rk::k1_quartic_roots<0>, grid_fam, 128, cs, P);
+        rk_launch(rk::k1_quartic_check<0>, grid_list, 128, cs, P);
+        rk_launch(rk::k1_quartic_roots<1>, grid_fam, 128, cs, P);
+        rk_launch(rk::k1_quartic_check<1>, grid_list, 128, cs, P);
+        rk_launch(rk::k1_quartic_roots<2>, grid_fam, 128, cs, P);
+        rk_launch(rk::k1_quartic_check<2>, grid_list, 128, cs, P);
+#if RK_CC_SPLIT
+        rk_launch(rk::k1_closed_cands<0>, grid_fam, 128, cs, P);
+        rk_launch(rk::k1_closed_cands<1>, grid_fam, 128, cs, P);
+#else
+        rk_launch(rk::k1_closed_cands<2>, grid_fam, 128, cs, P);
+#endif
+        rk_launch(rk::k1_cand_check, grid_list, 128, cs, P);
+        rk_launch(rk::k1_block, grid_items, 128, cs, P);
+        rk_launch(rk::k1_rescue, (unsigned)h->sm_count, 128, cs, P);
+        rk_launch(rk::k_sync, (unsigned)((P.cn + 127) / 128), 128, cs, P);
         static const int fam[RK_S2_STEPS] = {0, 1, 8, 2, 3, 0, 1, 8, 2, 3, 4, 5, 6, 7, 4, 5, 6, 7};
         static const int dir2[RK_S2_STEPS] = {0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 0, 0, 0, 0, 1, 1, 1, 1};
         for (int step = 0; step < RK_S2_STEPS; ++step) {
             switch (fam[step]) {
-                case 0: rk::k2_stage<0><<<grid_list, 128, 0, cs>>>(P, step, dir2[step]); break;
+                case 0: rk_launch(rk::k2_stage<0>, grid_list, 128, cs, P, step, dir2[step]); break;
                 case 1:
-                    rk::k2_vel_scan_uddu<<<grid_vel, RK_LS_BLOCK, 0, cs>>>(P, step, dir2[step]);
-                    rk::k2_polish<6, false><<<(unsigned)h->sm_count * 8u, 128, 0, cs>>>(P, 33 + 4 * step, 34 + 4 * step);
-                    rk::k2_vel_check_uddu<<<grid_list, 128, 0, cs>>>(P, step, dir2[step]);
+                    rk_launch(rk::k2_vel_scan_uddu, grid_vel, RK_LS_BLOCK, cs, P, step, dir2[step]);
+                    rk_launch(rk::k2_polish<6, false>, (unsigned)h->sm_count * 8u, 128, cs, P, 33 + 4 * step, 34 + 4 * step);
+                    rk_launch(rk::k2_vel_check_uddu, grid_list, 128, cs, P, step, dir2[step]);
                     h->launches += 2;
                     break;
-                case 2: rk::k2_stage<2><<<grid_list, 128, 0, cs>>>(P, step, dir2[step]); break;
-                case 3: rk::k2_stage<3><<<grid_list, 128, 0, cs>>>(P, step, dir2[step]); break;
-                case 4: rk::k2_stage<4><<<grid_list, 128, 0, cs>>>(P, step, dir2[step]); break;
-                case 5: rk::k2_stage<5><<<grid_list, 128, 0, cs>>>(P, step, dir2[step]); break;
-                case 6: rk::k2_stage<6><<<grid_list, 128, 0, cs>>>(P, step, dir2[step]); break;
-                case 7: rk::k2_stage<7><<<grid_list, 128, 0, cs>>>(P, step, dir2[step]); break;
-                default: rk::k2_vel<8><<<grid_vel, RK_LS_BLOCK, 0, cs>>>(P, step, dir2[step]); break;
+                case 2: rk_launch(rk::k2_stage<2>, grid_list, 128, cs, P, step, dir2[step]); break;
+                case 3: rk_launch(rk::k2_stage<3>, grid_list, 128, cs, P, step, dir2[step]); break;
+                case 4: rk_launch(rk::k2_stage<4>, grid_list, 128, cs, P, step, dir2[step]); break;
+                case 5: rk_launch(rk::k2_stage<5>, grid_list, 128, cs, P, step, dir2[step]); break;
+                case 6: rk_launch(rk::k2_stage<6>, grid_list, 128, cs, P, step, dir2[step]); break;
+                case 7: rk_launch(rk::k2_stage<7>, grid_list, 128, cs, P, step, dir2[step]); break;
+                default: rk_launch(rk::k2_vel<8>, grid_vel, RK_LS_BLOCK, cs, P, step, dir2[step]); break;
             }
         }
-        rk::k2_fail<<<(unsigned)h->sm_count, 128, 0, cs>>>(P);
-        rk::k_expand<<<grid_items, 128, 0, cs>>>(P);
-        h->launches += 14 + RK_S2_STEPS;
+        rk_launch(rk::k2_fail, (unsigned)h->sm_count, 128, cs, P);
+        rk_launch(rk::k_expand, grid_items, 128, cs, P);
+        h->launches += 14 + RK_CC_SPLIT + RK_S2_STEPS;
         if (host) RK_CUDA(cudaEventRecord(h->ev_computed[chunk_index % RK_STAGE_BUFS], cs));
     }
     for (int k = 1; k < lanes; ++k) {

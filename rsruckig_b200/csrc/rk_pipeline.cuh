@@ -28,6 +28,24 @@
 #include "rk_step2_acc.cuh"
 #include "rk_step2_none.cuh"
 
+// Programmatic dependent launch: the pipeline is 36 short dependent kernels per chunk, so the launch latency between them
+// shows in the latency of a small batch. With RK_PDL = 1 every launch carries the programmatic-stream-serialization
+// attribute and every kernel starts with griddepcontrol.wait (= cudaGridDependencySynchronize: returns when the preceding
+// kernel of the stream has completed and flushed), so the next kernel is set up while its predecessor drains. Every kernel
+// waits unconditionally before its first memory access, hence completion of kernel k still implies completion of all
+// kernels before it. 64 Ki x 7-DoF batch: 1.19 -> 1.12 ms, 16 Ki: 0.68 -> 0.60 ms; large batches unchanged (two chunks in
+// flight already hide the gaps). RK_PDL = 2 (griddepcontrol.launch_dependents at kernel entry as well) was measured
+// slower: 1.30 ms — the early successor blocks take the slots the other stream's kernel would have used.
+#ifndef RK_PDL
+#define RK_PDL 1
+#endif
+#if RK_PDL == 2
+#define RK_PDL_ENTER() do { asm volatile("griddepcontrol.launch_dependents;"); asm volatile("griddepcontrol.wait;" ::: "memory"); } while (0)
+#elif RK_PDL == 1
+#define RK_PDL_ENTER() asm volatile("griddepcontrol.wait;" ::: "memory")
+#else
+#define RK_PDL_ENTER() ((void)0)
+#endif
 #ifndef RK_MIN_BLOCKS
 #define RK_MIN_BLOCKS 4
 #endif
@@ -72,6 +90,7 @@ __device__ __forceinline__ void append_unsolved(uint32_t* list, uint32_t* counte
 #define RK_SU_MINB 4
 #endif
 __global__ void __launch_bounds__(128, RK_SU_MINB) k1_setup(const Params P) {
+    RK_PDL_ENTER();
     const int64_t wstride = (int64_t)P.dof * P.cn;
     const int64_t wi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (wi >= wstride) return;
@@ -191,7 +210,15 @@ __device__ __forceinline__ Lim family_limits(const DofIn& x, const Bound& b, int
 // tests of the profile check that need no integration, parked in their sub-list slots and queued. Phase B, one thread per
 // queued candidate: the full profile check, a valid candidate sets its byte of the sub-list's mask word. The order in which
 // the reference would have met the candidates is restored by k1_block (for VEL only the first valid variant counts).
-__global__ void __launch_bounds__(128, 8) k1_closed_cands(const Params P) {
+#ifndef RK_CC_MINB
+#define RK_CC_MINB 8
+#endif
+#ifndef RK_CC_SPLIT
+#define RK_CC_SPLIT 0  // 1: ACC0_ACC1 and VEL in two launches (PART 0 / 1) instead of one (PART 2)
+#endif
+template <int PART>
+__global__ void __launch_bounds__(128, RK_CC_MINB) k1_closed_cands(const Params P) {
+    RK_PDL_ENTER();
     const int64_t wstride = (int64_t)P.dof * P.cn;
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t parked3 = 0, parked4 = 0;
@@ -207,20 +234,24 @@ __global__ void __launch_bounds__(128, 8) k1_closed_cands(const Params P) {
             const DofIn x = load_rec(P, wi, b, bdur_);
             bool rest_target, trivial;
             const Lim L = family_limits(x, b, ds, rest_target, trivial);
-            P.wqmask[(int64_t)(6 + ds) * wstride + wi] = 0u;
-            P.wqmask[(int64_t)(8 + ds) * wstride + wi] = 0u;
+            if (PART != 1) P.wqmask[(int64_t)(6 + ds) * wstride + wi] = 0u;
+            if (PART != 0) P.wqmask[(int64_t)(8 + ds) * wstride + wi] = 0u;
             if (!trivial) {  // :1015-1025 — nothing moves: only the quartics of the first direction are tried
                 Step1Pos3<CandSink> s;
                 s.init(b, x.j_max);
                 s.first_only = false;
-                s.sink.parked = 0;
-                s.sink.base = vl_slot(P, wi, sub_slot_base(6 + ds));
-                s.family_acc0_acc1(L);
-                parked3 = s.sink.parked;
-                s.sink.parked = 0;
-                s.sink.base = vl_slot(P, wi, sub_slot_base(8 + ds));
-                s.family_vel(L);
-                parked4 = s.sink.parked;
+                if (PART != 1) {
+                    s.sink.parked = 0;
+                    s.sink.base = vl_slot(P, wi, sub_slot_base(6 + ds));
+                    s.family_acc0_acc1(L);
+                    parked3 = s.sink.parked;
+                }
+                if (PART != 0) {
+                    s.sink.parked = 0;
+                    s.sink.base = vl_slot(P, wi, sub_slot_base(8 + ds));
+                    s.family_vel(L);
+                    parked4 = s.sink.parked;
+                }
             }
         }
     }
@@ -235,6 +266,7 @@ __global__ void __launch_bounds__(128, 8) k1_closed_cands(const Params P) {
 }
 
 __global__ void __launch_bounds__(128, 8) k1_cand_check(const Params P) {
+    RK_PDL_ENTER();
     const int64_t wstride = (int64_t)P.dof * P.cn;
     const uint32_t count = P.counters[23];
     for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < count; e += gridDim.x * blockDim.x) {
@@ -261,6 +293,7 @@ __global__ void __launch_bounds__(128, 8) k1_cand_check(const Params P) {
 // to have a root in the same loop iteration. Root k of a sub-list writes slot k, which keeps the ascending order.
 template <int TYPE>
 __global__ void __launch_bounds__(128, RK_MIN_BLOCKS) k1_quartic_roots(const Params P) {
+    RK_PDL_ENTER();
     const int64_t wstride = (int64_t)P.dof * P.cn;
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     double roots[4];
@@ -316,6 +349,7 @@ __global__ void __launch_bounds__(128, RK_MIN_BLOCKS) k1_quartic_roots(const Par
 
 template <int TYPE>
 __global__ void __launch_bounds__(128, TYPE == 0 ? 6 : 8) k1_quartic_check(const Params P) {
+    RK_PDL_ENTER();
     const int64_t wstride = (int64_t)P.dof * P.cn;
     const uint32_t count = P.counters[20 + TYPE];
     for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < count; e += gridDim.x * blockDim.x) {
@@ -441,6 +475,7 @@ __device__ __forceinline__ uint32_t ref_codes(int ref) {
 }
 
 __global__ void __launch_bounds__(128, 4) k1_block(const Params P) {
+    RK_PDL_ENTER();
     const int64_t wstride = (int64_t)P.dof * P.cn;
     const int64_t wi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool rescue = false;
@@ -543,6 +578,7 @@ __global__ void __launch_bounds__(128, 4) k1_block(const Params P) {
 // Numerical rescues (:1142-1255) for the rare items none of the regular families produced a candidate for; the first rescue
 // that yields one wins.
 __global__ void __launch_bounds__(128) k1_rescue(const Params P) {
+    RK_PDL_ENTER();
     const int64_t wstride = (int64_t)P.dof * P.cn;
     const uint32_t n_items = P.counters[24];
     for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < n_items; e += gridDim.x * blockDim.x) {
@@ -869,6 +905,7 @@ __device__ __forceinline__ void sync_trajectory(const Params& P, int64_t il, uin
 #define RK_SY_MINB 8
 #endif
 __global__ void __launch_bounds__(128, RK_SY_MINB) k_sync(const Params P) {
+    RK_PDL_ENTER();
     const int64_t il = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = il < P.cn;
     uint32_t pm[RK_MAX_DOF];
@@ -962,6 +999,7 @@ __device__ __forceinline__ void report_step2_failure(const Params& P, int d, int
 // `step` numbers the launches of the chain (list 0 of step 0 is filled by k_sync); list `step & 1` is read, the other written.
 template <int F>
 __global__ void __launch_bounds__(128, F == 0 ? 6 : RK_MIN_BLOCKS) k2_stage(const Params P, int step, int second_dir) {
+    RK_PDL_ENTER();
     const int64_t wstride = (int64_t)P.dof * P.cn;
     const uint32_t* list_in = P.list[step & 1];
     uint32_t* list_out = P.list[(step + 1) & 1];
@@ -994,6 +1032,7 @@ __global__ void __launch_bounds__(128, F == 0 ? 6 : RK_MIN_BLOCKS) k2_stage(cons
 #endif
 template <int F>
 __global__ void __launch_bounds__(RK_LS_BLOCK, RK_LS_MINB) k2_vel(const Params P, int step, int second_dir) {
+    RK_PDL_ENTER();
     const int64_t wstride = (int64_t)P.dof * P.cn;
     const uint32_t* list_in = P.list[step & 1];
     uint32_t* list_out = P.list[(step + 1) & 1];
@@ -1036,6 +1075,7 @@ __device__ __forceinline__ double* vslot(const Params& P, int64_t wi, int64_t ws
 }
 
 __global__ void __launch_bounds__(RK_LS_BLOCK, RK_LS_MINB) k2_vel_scan_uddu(const Params P, int step, int second_dir) {
+    RK_PDL_ENTER();
     const int64_t wstride = (int64_t)P.dof * P.cn;
     const uint32_t* list_in = P.list[step & 1];
     uint32_t* list_out = P.list[(step + 1) & 1];
@@ -1091,6 +1131,7 @@ __global__ void __launch_bounds__(RK_LS_BLOCK, RK_LS_MINB) k2_vel_scan_uddu(cons
 #endif
 template <int N, bool DERIV>
 __global__ void __launch_bounds__(128, 8) k2_polish(const Params P, int counter_index, int cursor_index) {
+    RK_PDL_ENTER();
     const int64_t wstride = (int64_t)P.dof * P.cn;
     const uint32_t count = P.counters[counter_index];
     uint32_t* cursor = P.counters + cursor_index;  // tasks are claimed dynamically: the lanes of the whole grid stay balanced
@@ -1141,6 +1182,7 @@ __global__ void __launch_bounds__(128, 8) k2_polish(const Params P, int counter_
 }
 
 __global__ void __launch_bounds__(128, 6) k2_vel_check_uddu(const Params P, int step, int second_dir) {
+    RK_PDL_ENTER();
     const int64_t wstride = (int64_t)P.dof * P.cn;
     uint32_t* list_out = P.list[(step + 1) & 1];
     const uint32_t count = P.counters[32 + 4 * step];
@@ -1172,6 +1214,7 @@ __global__ void __launch_bounds__(128, 6) k2_vel_check_uddu(const Params P, int 
 
 // ------------------------------------------------------------------------------------------------ k2_fail
 __global__ void __launch_bounds__(128) k2_fail(const Params P) {
+    RK_PDL_ENTER();
     const int64_t wstride = (int64_t)P.dof * P.cn;
     const uint32_t count = P.counters[RK_S2_STEPS];
     for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < count; k += gridDim.x * blockDim.x) {
@@ -1195,6 +1238,7 @@ __global__ void __launch_bounds__(128) k2_fail(const Params P) {
 #define RK_EX_MINB 1
 #endif
 __global__ void __launch_bounds__(128, RK_EX_MINB) k_expand(const Params P) {
+    RK_PDL_ENTER();
     const int64_t wstride = (int64_t)P.dof * P.cn;
     {
         const int64_t wi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
