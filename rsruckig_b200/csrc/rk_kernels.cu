@@ -985,7 +985,9 @@ rk_status rk_calculate_batch(rk_handle* h, const rk_batch_desc* desc, const rk_b
         rk_launch(rk::k_sync, (unsigned)((P.cn + 127) / 128), 128, cs, P);
         static const int fam[RK_S2_STEPS] = {0, 1, 8, 2, 3, 0, 1, 8, 2, 3, 4, 5, 6, 7, 4, 5, 6, 7};
         static const int dir2[RK_S2_STEPS] = {0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 0, 0, 0, 0, 1, 1, 1, 1};
-        for (int step = 0; step < RK_S2_STEPS; ++step) {
+        // with RK_FUSE_TAIL the last eight stages (families 4-7 in both directions) and k2_fail are one launch (k2_tail)
+        const int n_steps = RK_FUSE_TAIL ? 10 : RK_S2_STEPS;
+        for (int step = 0; step < n_steps; ++step) {
             switch (fam[step]) {
                 case 0: rk_launch(rk::k2_stage<0>, grid_list, 128, cs, P, step, dir2[step]); break;
                 case 1:
@@ -1003,9 +1005,13 @@ rk_status rk_calculate_batch(rk_handle* h, const rk_batch_desc* desc, const rk_b
                 default: rk_launch(rk::k2_vel<8>, grid_vel, RK_LS_BLOCK, cs, P, step, dir2[step]); break;
             }
         }
+#if RK_FUSE_TAIL
+        rk_launch(rk::k2_tail, grid_list, 128, cs, P, n_steps);
+#else
         rk_launch(rk::k2_fail, (unsigned)h->sm_count, 128, cs, P);
+#endif
         rk_launch(rk::k_expand, grid_items, 128, cs, P);
-        h->launches += 14 + RK_CC_SPLIT + RK_S2_STEPS;
+        h->launches += 14 + RK_CC_SPLIT + n_steps;  // fused tail: k2_tail stands in for k2_fail
         if (host) RK_CUDA(cudaEventRecord(h->ev_computed[chunk_index % RK_STAGE_BUFS], cs));
     }
     for (int k = 1; k < lanes; ++k) {

@@ -1212,6 +1212,39 @@ __global__ void __launch_bounds__(128, 6) k2_vel_check_uddu(const Params P, int 
     }
 }
 
+// ------------------------------------------------------------------------------------------------ k2_tail
+// The last eight launches of the chain (ACC0_ACC1, ACC0, ACC1, NONE in the first and then in the second direction) see
+// less than 1 % of the items: as separate kernels they are nothing but launch latency. k2_tail walks one item through these
+// eight stages in the reference's order (position_third_step2.rs:2466-2481) and does k2_fail's bookkeeping for an item that
+// no family solves. `step` is the launch index the first of the fused stages would have had (its input list and counter).
+#ifndef RK_FUSE_TAIL
+#define RK_FUSE_TAIL 1
+#endif
+__global__ void __launch_bounds__(128, RK_MIN_BLOCKS) k2_tail(const Params P, int step) {
+    RK_PDL_ENTER();
+    const int64_t wstride = (int64_t)P.dof * P.cn;
+    const uint32_t* list_in = P.list[step & 1];
+    const uint32_t count = P.counters[step];
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < count; k += gridDim.x * blockDim.x) {
+        const uint32_t wi = list_in[k];
+        const ItemS2 it = load_item_s2(P, wi, wstride);
+        bool solved = false;
+#pragma unroll 1
+        for (int dir = 0; dir < 2 && !solved; ++dir) {
+            const bool second_direction = dir != 0;
+            solved = run_stage<4>(P, it, second_direction);
+            if (!solved) solved = run_stage<5>(P, it, second_direction);
+            if (!solved) solved = run_stage<6>(P, it, second_direction);
+            if (!solved) solved = run_stage<7>(P, it, second_direction);
+        }
+        if (!solved) {
+            report_step2_failure(P, it.d, it.ig);
+            P.wsrc[wi] = 0xFF;  // RK_SRC_FAILED: k_expand stores an idle profile
+            P.codes[it.gi] = pack_codes(L_NONE, UDDU, DIR_UP, RK_SRC_STEP2);
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ k2_fail
 __global__ void __launch_bounds__(128) k2_fail(const Params P) {
     RK_PDL_ENTER();
