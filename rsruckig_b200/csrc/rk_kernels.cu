@@ -596,6 +596,9 @@ rk_status fail(rk_status s, const std::string& m) {
 #ifndef RK_SMALL_SPLIT_MIN_ITEMS
 #define RK_SMALL_SPLIT_MIN_ITEMS (192 * 1024)
 #endif
+#ifndef RK_HOST_RAMP
+#define RK_HOST_RAMP 4  // host-buffer calls: the first chunk is computed in this many pieces (pipeline fill)
+#endif
 #ifndef RK_STAGE_BUFS
 #define RK_STAGE_BUFS 4  // host-buffer calls: input chunks are copied this many chunks ahead of the kernels
 #endif
@@ -632,7 +635,8 @@ struct rk_handle {
     void* stage_pinned = nullptr;
     size_t stage_pinned_bytes = 0;
     // host-buffer calculate: input chunks are copied on a second stream while the previous chunk is computed
-    cudaStream_t copy_stream = nullptr;
+    cudaStream_t copy_stream = nullptr, d2h_stream = nullptr;
+    cudaEvent_t ev_d2h = nullptr;
     cudaEvent_t ev_copied[RK_STAGE_BUFS] = {}, ev_computed[RK_STAGE_BUFS] = {};
     void* chunk_in[RK_STAGE_BUFS] = {};
     size_t chunk_in_bytes = 0;
@@ -790,6 +794,8 @@ rk_status rk_create(int32_t device, rk_handle** out) {
     RK_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     RK_CUDA(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device));
     RK_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    RK_CUDA(cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking));
+    RK_CUDA(cudaEventCreateWithFlags(&h->ev_d2h, cudaEventDisableTiming));
     h->lane_stream[0] = h->stream;
     for (int k = 1; k < RK_LANES; ++k) RK_CUDA(cudaStreamCreateWithFlags(&h->lane_stream[k], cudaStreamNonBlocking));
     RK_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
@@ -820,6 +826,8 @@ rk_status rk_destroy(rk_handle* h) {
         if (h->ev_computed[k]) cudaEventDestroy(h->ev_computed[k]);
     }
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    if (h->d2h_stream) cudaStreamDestroy(h->d2h_stream);
+    if (h->ev_d2h) cudaEventDestroy(h->ev_d2h);
     cudaStreamDestroy(h->stream);
     delete h;
     return RK_OK;
@@ -907,10 +915,25 @@ rk_status rk_calculate_batch(rk_handle* h, const rk_batch_desc* desc, const rk_b
         }
     }
 
+    // Host buffers: the kernels of the first chunk cannot start before its inputs have arrived, so the first chunk is cut
+    // into RK_HOST_RAMP pieces — the pipeline fills after a fraction of a chunk's copy time instead of a whole one. Results
+    // (status, duration, independent minimum durations) go back chunk by chunk on their own stream while later chunks
+    // are still computed.
+    const bool ramp = host && n_chunks >= 2 && cn_max >= (int64_t)RK_HOST_RAMP * 16384;
+    const bool d2h_per_chunk = host && out && n_chunks >= 2;
+    if (d2h_per_chunk) {  // earlier work on the caller-visible stream may still write the result arrays' device copies
+        RK_CUDA(cudaEventRecord(h->ev_fork, h->stream));
+        RK_CUDA(cudaStreamWaitEvent(h->d2h_stream, h->ev_fork, 0));
+    }
     int chunk_index = 0;
-    for (int64_t off = 0; off < desc->n; off += cn_max, ++chunk_index) {
+    for (int64_t off = 0, step_n = 0; off < desc->n; off += step_n, ++chunk_index) {
+        step_n = cn_max;
+        if (ramp && off < cn_max) {
+            const int64_t piece = (cn_max + RK_HOST_RAMP - 1) / RK_HOST_RAMP;
+            step_n = (cn_max - off < piece) ? (cn_max - off) : piece;
+        }
         P.off = off;
-        P.cn = (desc->n - off < cn_max) ? (desc->n - off) : cn_max;
+        P.cn = (desc->n - off < step_n) ? (desc->n - off) : step_n;
         const int lane_set = chunk_index % lanes;
         cudaStream_t cs = h->lane_stream[lane_set];
         const rk_handle::Scratch& c = h->sc[lane_set];
@@ -1013,6 +1036,20 @@ rk_status rk_calculate_batch(rk_handle* h, const rk_batch_desc* desc, const rk_b
         rk_launch(rk::k_expand, grid_items, 128, cs, P);
         h->launches += 14 + RK_CC_SPLIT + n_steps;  // fused tail: k2_tail stands in for k2_fail
         if (host) RK_CUDA(cudaEventRecord(h->ev_computed[chunk_index % RK_STAGE_BUFS], cs));
+        if (d2h_per_chunk) {
+            RK_CUDA(cudaStreamWaitEvent(h->d2h_stream, h->ev_computed[chunk_index % RK_STAGE_BUFS], 0));
+            if (out->status)
+                RK_CUDA(cudaMemcpyAsync(out->status + off, traj->status + off, sizeof(int32_t) * P.cn, cudaMemcpyDeviceToHost, h->d2h_stream));
+            if (out->duration)
+                RK_CUDA(cudaMemcpyAsync(out->duration + off, traj->duration + off, sizeof(double) * P.cn, cudaMemcpyDeviceToHost, h->d2h_stream));
+            if (out->independent_min_durations)
+                RK_CUDA(cudaMemcpy2DAsync(out->independent_min_durations + off, sizeof(double) * desc->n, traj->imd + off, sizeof(double) * desc->n,
+                                          sizeof(double) * P.cn, (size_t)desc->dof, cudaMemcpyDeviceToHost, h->d2h_stream));
+        }
+    }
+    if (d2h_per_chunk) {
+        RK_CUDA(cudaEventRecord(h->ev_d2h, h->d2h_stream));
+        RK_CUDA(cudaStreamWaitEvent(h->stream, h->ev_d2h, 0));
     }
     for (int k = 1; k < lanes; ++k) {
         RK_CUDA(cudaEventRecord(h->ev_join[k], h->lane_stream[k]));
@@ -1020,7 +1057,7 @@ rk_status rk_calculate_batch(rk_handle* h, const rk_batch_desc* desc, const rk_b
     }
     RK_CUDA(cudaGetLastError());
 
-    if (out) {
+    if (out && !d2h_per_chunk) {
         const cudaMemcpyKind kind = host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
         if (out->status) RK_CUDA(cudaMemcpyAsync(out->status, traj->status, sizeof(int32_t) * desc->n, kind, h->stream));
         if (out->duration) RK_CUDA(cudaMemcpyAsync(out->duration, traj->duration, sizeof(double) * desc->n, kind, h->stream));

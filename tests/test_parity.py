@@ -256,3 +256,35 @@ def test_device_buffers_and_full_size_properties(gpu):
     assert float((A[7] - d["target_acceleration"]).abs()[:, ok].max()) <= 1e-10
     ts6 = torch.from_numpy(otg.read(cabi.RK_FIELD_T_SUM)).cuda()[6] + torch.from_numpy(otg.read(cabi.RK_FIELD_BRAKE_DURATION)).cuda()[0]
     assert float((ts6 - duration[None, :]).abs()[:, ok].max()) <= 1e-9 * float(duration[ok].max())
+
+
+@pytest.mark.gpu
+def test_host_buffers_over_several_chunks_return_results_chunk_by_chunk(gpu):
+    """A host-buffer batch of more than one chunk: the first chunk is computed in pieces while later inputs are still being
+    copied, and status / duration / independent_min_durations come back chunk by chunk on their own stream. 20 DoFs make a
+    chunk 209 715 trajectories, so 450 000 trajectories are three chunks (the first in four pieces). Everything the call
+    returns equals what the trajectories object holds, and both equal the oracle bit for bit."""
+    n, dof = 450_000, 20
+    f = workloads.bench_inputs(n, dof, seed=21)
+    from oracle.oracle import OracleBatch
+    from rsruckig_b200 import ThrowErrorHandler
+    otg = gpu(dof, 0.005, ThrowErrorHandler)
+    status = np.full(n, 12345, dtype=np.int32)
+    duration = np.full(n, -1.0)
+    imd = np.full((dof, n), -1.0)
+    for _ in range(2):  # the second call re-uses the staging buffers and events of the first
+        status[:] = 12345
+        otg.calculate(f, n=n, memory_space=cabi.RK_MEM_HOST, status=status, duration=duration, independent_min_durations=imd)
+        assert np.array_equal(status, otg.read(cabi.RK_FIELD_STATUS))
+        assert np.array_equal(duration, otg.read(cabi.RK_FIELD_DURATION))
+        assert np.array_equal(imd, otg.read(cabi.RK_FIELD_INDEPENDENT_MIN_DURATIONS))
+    ob = OracleBatch(n, dof, "portable")
+    ob.calculate(f, threads=16)
+    st_o = ob.read(cabi.RK_FIELD_STATUS)
+    assert np.array_equal(status, st_o)
+    ok = st_o == 0
+    assert ok.mean() > 0.8
+    assert np.array_equal(duration[ok], ob.read(cabi.RK_FIELD_DURATION)[ok])
+    assert np.array_equal(imd[:, ok], ob.read(cabi.RK_FIELD_INDEPENDENT_MIN_DURATIONS)[:, ok])
+    for fld in (cabi.RK_FIELD_T, cabi.RK_FIELD_P):
+        assert np.array_equal(otg.read(fld)[:, :, ok], ob.read(fld)[:, :, ok])
