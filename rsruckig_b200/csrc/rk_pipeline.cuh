@@ -1213,35 +1213,63 @@ __global__ void __launch_bounds__(128, 6) k2_vel_check_uddu(const Params P, int 
 }
 
 // ------------------------------------------------------------------------------------------------ k2_tail
-// The last eight launches of the chain (ACC0_ACC1, ACC0, ACC1, NONE in the first and then in the second direction) see
-// less than 1 % of the items: as separate kernels they are nothing but launch latency. k2_tail walks one item through these
-// eight stages in the reference's order (position_third_step2.rs:2466-2481) and does k2_fail's bookkeeping for an item that
-// no family solves. `step` is the launch index the first of the fused stages would have had (its input list and counter).
+// The last eight launches of the chain (ACC0_ACC1, ACC0, ACC1, NONE in the first and then in the second direction,
+// position_third_step2.rs:2466-2481) see less than 1 % of the items: as separate kernels they are nothing but launch and
+// single-thread latency. k2_tail evaluates the eight (direction, family) variants of an item SIDE BY SIDE — warp w of a
+// block runs family 4 + w for 16 items x 2 directions, so every warp stays in one family's code — and the first variant in
+// the reference's order that produced a profile stores it (the families only read the item, so evaluating one that the
+// reference would not have reached changes nothing). An item no variant solves gets k2_fail's bookkeeping. `step` is the
+// launch index the first of the fused stages would have had (its input list and counter).
 #ifndef RK_FUSE_TAIL
 #define RK_FUSE_TAIL 1
 #endif
+template <int F>
+__device__ __noinline__ bool tail_family(const ItemS2& it, bool second_direction, Hit& h) {
+    S2 s;
+    s.init(it.b, it.tf, it.x.j_max);
+    const bool up_first = s.pd > it.tf * it.b.v0;
+    const Lim L = lim_dir(up_first != second_direction, it.x.v_max, it.x.v_min, it.x.a_max, it.x.a_min, it.x.j_max);
+    return run_family<F>(s, L, h);
+}
+
 __global__ void __launch_bounds__(128, RK_MIN_BLOCKS) k2_tail(const Params P, int step) {
     RK_PDL_ENTER();
+    __shared__ uint32_t solved_by[16];  // per item of the block: bit (4 * direction + family slot) set = that variant has a profile
     const int64_t wstride = (int64_t)P.dof * P.cn;
     const uint32_t* list_in = P.list[step & 1];
     const uint32_t count = P.counters[step];
-    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < count; k += gridDim.x * blockDim.x) {
-        const uint32_t wi = list_in[k];
-        const ItemS2 it = load_item_s2(P, wi, wstride);
-        bool solved = false;
-#pragma unroll 1
-        for (int dir = 0; dir < 2 && !solved; ++dir) {
-            const bool second_direction = dir != 0;
-            solved = run_stage<4>(P, it, second_direction);
-            if (!solved) solved = run_stage<5>(P, it, second_direction);
-            if (!solved) solved = run_stage<6>(P, it, second_direction);
-            if (!solved) solved = run_stage<7>(P, it, second_direction);
+    const int fam = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int slot = lane & 15, dir = lane >> 4;
+    const int variant = 4 * dir + fam;
+    for (uint32_t base = blockIdx.x * 16u; base < count; base += gridDim.x * 16u) {  // uniform per block
+        if (threadIdx.x < 16) solved_by[threadIdx.x] = 0u;
+        __syncthreads();
+        const uint32_t k = base + slot;
+        const bool live = k < count;
+        bool ok = false;
+        Hit h;
+        ItemS2 it;
+        uint32_t wi = 0;
+        if (live) {
+            wi = list_in[k];
+            it = load_item_s2(P, wi, wstride);
+            if (fam == 0) ok = tail_family<4>(it, dir != 0, h);
+            else if (fam == 1) ok = tail_family<5>(it, dir != 0, h);
+            else if (fam == 2) ok = tail_family<6>(it, dir != 0, h);
+            else ok = tail_family<7>(it, dir != 0, h);
+            if (ok) atomicOr(&solved_by[slot], 1u << variant);
         }
-        if (!solved) {
-            report_step2_failure(P, it.d, it.ig);
-            P.wsrc[wi] = 0xFF;  // RK_SRC_FAILED: k_expand stores an idle profile
-            P.codes[it.gi] = pack_codes(L_NONE, UDDU, DIR_UP, RK_SRC_STEP2);
+        __syncthreads();
+        if (live) {
+            const uint32_t m = solved_by[slot];
+            if (ok && (m & ((1u << variant) - 1u)) == 0u) put_solution(P, it, wstride, h);  // first in the reference's order
+            if (m == 0u && variant == 0) {
+                report_step2_failure(P, it.d, it.ig);
+                P.wsrc[wi] = 0xFF;  // RK_SRC_FAILED: k_expand stores an idle profile
+                P.codes[it.gi] = pack_codes(L_NONE, UDDU, DIR_UP, RK_SRC_STEP2);
+            }
         }
+        __syncthreads();
     }
 }
 
