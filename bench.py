@@ -430,9 +430,9 @@ def run_b200(args):
                                              "(ncu, profiles/r1_ops_per_kernel.csv), per GPU; = "
                                              f"{(ops.get('dram_bytes_per_trajectory') or 0) * per_gpu / 1e9:.0f} GB/s at the measured rate",
                              "kernels": "one step per chunk of 4Mi (DoF, trajectory) items = k1_setup, 3 x (k1_quartic_roots, k1_quartic_check), "
-                                        "k1_closed_cands, k1_cand_check, k1_block, k1_rescue, k_sync, 18 chain stages (k2_stage<F>; VEL/UDDU as "
-                                        "k2_vel_scan_uddu + k2_polish + k2_vel_check_uddu, VEL/UDUD as k2_vel<8>), k2_fail, k_expand; no single kernel "
-                                        "holds more than 11 % of the step (profiles/r1_ncu_summary.md), so the roofline is quoted for the whole step",
+                                        "k1_closed_cands, k1_cand_check, k1_block, k1_rescue, k_sync, 10 chain stages (k2_stage<F>; VEL/UDDU as "
+                                        "k2_vel_scan_uddu + k2_polish + k2_vel_check_uddu, VEL/UDUD as k2_vel<8>), k2_tail (the last 8 stages), k_expand; no single kernel "
+                                        "holds more than 13 % of the step (profiles/r1_ncu_summary.md), so the roofline is quoted for the whole step",
                              "flop_per_trajectory": flop, "flop_how": flop_how,
                              "executed": {"flop_per_trajectory": xflop, "achieved": xflop * per_gpu / 1e12, "unit": "TFLOP/s",
                                           "frac": xflop * per_gpu / 1e12 / fp64_peak_tflops if fp64_peak_tflops else None, "how": xflop_how},

@@ -288,3 +288,25 @@ def test_host_buffers_over_several_chunks_return_results_chunk_by_chunk(gpu):
     assert np.array_equal(imd[:, ok], ob.read(cabi.RK_FIELD_INDEPENDENT_MIN_DURATIONS)[:, ok])
     for fld in (cabi.RK_FIELD_T, cabi.RK_FIELD_P):
         assert np.array_equal(otg.read(fld)[:, :, ok], ob.read(fld)[:, :, ok])
+
+
+@pytest.mark.parametrize("n,dof", [(1, 7), (2, 7), (31, 7), (33, 3), (127, 7), (129, 1), (4097, 7),
+                                   (28087, 7),      # 196 609 items: the smallest 7-DoF batch that is split in two (ragged) halves
+                                   (524289, 8)])    # one trajectory more than a full chunk of 4 Mi items: two ragged chunks
+def test_ragged_and_boundary_sizes_exact(gpu, n, dof):
+    """Batch sizes that are not multiples of the warp / block / chunk size, and the two sizes at which the chunking changes."""
+    f = workloads.edge_case_inputs(n, dof, seed=n % 97) if n < 5000 else workloads.bench_inputs(n, dof, seed=n % 97)
+    otg, ob = run_both(gpu, f, n, dof, threads=16)
+    assert_exact(otg, ob, label=f"n={n} dof={dof}")
+
+
+def test_empty_batch_is_a_no_op(gpu):
+    from rsruckig_b200 import ThrowErrorHandler
+    otg = gpu(7, 0.005, ThrowErrorHandler)
+    f = {k: v[:, :0].copy() for k, v in workloads.bench_inputs(4, 7, seed=1).items()}
+    status = np.zeros(0, dtype=np.int32)
+    duration = np.zeros(0)
+    before = otg.kernel_launches()  # the handle of a device is shared by the calculators of a process
+    otg.calculate(f, n=0, memory_space=cabi.RK_MEM_HOST, status=status, duration=duration)
+    otg.sync()
+    assert otg.kernel_launches() == before
