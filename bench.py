@@ -208,6 +208,8 @@ def run_b200(args):
         entry.build()
     torch.cuda.set_device(local)
     if world > 1:
+        # stdout carries exactly one JSON line: NCCL's own messages (its version banner under NCCL_DEBUG=VERSION) go to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         dist.barrier()
     from rsruckig_b200 import BatchRuckig, ThrowErrorHandler, _cabi as cabi
