@@ -208,10 +208,19 @@ def run_b200(args):
         entry.build()
     torch.cuda.set_device(local)
     if world > 1:
-        # stdout carries exactly one JSON line: NCCL's own messages (its version banner under NCCL_DEBUG=VERSION) go to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-        dist.barrier()
+        # stdout carries exactly one JSON line: what NCCL prints while the communicator comes up (its version banner under
+        # NCCL_DEBUG=VERSION ignores NCCL_DEBUG_FILE) is sent to stderr by pointing fd 1 at fd 2 for the duration
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
     from rsruckig_b200 import BatchRuckig, ThrowErrorHandler, _cabi as cabi
     import ctypes as C
 
