@@ -173,8 +173,9 @@ rk_status rk_trajectories_destroy(rk_trajectories* t);
 /* ---- the hot path ------------------------------------------------------ */
 /* Ruckig::calculate for every trajectory of the batch (ruckig.rs:210-218 ->
  * calculator_target.rs:278-833). Asynchronous on the handle's stream when
- * memory_space is RK_MEM_DEVICE (large batches are internally spread over a
- * second stream that joins the handle's stream again before the call returns);
+ * memory_space is RK_MEM_DEVICE (batches of 192 Ki (DoF, trajectory) items or
+ * more are internally spread over a second stream that joins the handle's
+ * stream again before the call returns);
  * with RK_MEM_HOST the inputs are staged chunk by chunk through device buffers
  * (pin the host arrays for full PCIe speed) and the call returns after the
  * results reached `out`. */
