@@ -182,6 +182,7 @@ struct Profile {
 
     // profile.rs:323-482 (set_limits is always false in the reference, :498)
     bool check(ControlSigns control_signs_, ReachedLimits limits_, double jf, double v_max, double v_min, double a_max, double a_min) {
+        RKO_PHASE(RKO_PH_CHECK);
         if (t[0] < 0.0) return false;
 
         t_sum[0] = t[0];
@@ -468,6 +469,7 @@ struct PositiveSet {
 
 // roots.rs:132-231
 static inline PositiveSet<3> solve_cub(double a, double b, double c, double d) {
+    RKO_PHASE(RKO_PH_ROOTS);
     PositiveSet<3> roots;
 
     if (std::fabs(d) < EPS) {
@@ -593,6 +595,7 @@ static inline int solve_resolvent(double x[3], double a, double b, double c) {
 
 // roots.rs:278-370
 static inline PositiveSet<4> solve_quart_monic(double a, double b, double c, double d) {
+    RKO_PHASE(RKO_PH_ROOTS);
     PositiveSet<4> roots;
 
     const double a_squared = a * a;
@@ -723,6 +726,7 @@ static inline double poly_eval(const Poly& p, double x) {
 
 // roots.rs:424-481 (MAX_ITS = 128, :420)
 static inline double shrink_interval(const Poly& p, double l, double h) {
+    RKO_PHASE(RKO_PH_NEWTON);
     const Poly deriv = poly_deri(p);
     const double fl = poly_eval(p, l);
     const double fh = poly_eval(p, h);

@@ -27,15 +27,24 @@
 #include <utility>
 #include <vector>
 
+#define RKO_PHASE(id) rkc::Scope rkc_scope_(id)
 #include "../include/ruckig_b200.h"
 #include "rko_math.hpp"  // glibc flavour: the libm calls stay opaque (1 op each)
 
 namespace rkc {
 enum { ADD = 0, MUL, DIV, SQRT, LIBM, NOPS };
-static uint64_t g_ops[NOPS];  // single-threaded by construction (rko_count_calculate)
+static uint64_t g_ops[RKO_PH_COUNT][NOPS];  // single-threaded by construction (rko_count_calculate)
+static int g_phase = RKO_PH_OTHER;
 static constexpr void bump(int k) {
-    if (!__builtin_is_constant_evaluated()) ++g_ops[k];
+    if (!__builtin_is_constant_evaluated()) ++g_ops[g_phase][k];
 }
+// RKO_PHASE(id) at the top of a function of the oracle: operations until the end of that scope belong to phase `id`
+// (the innermost marker wins: a profile check called from a Step-1 family counts as check, not as that family).
+struct Scope {
+    int saved;
+    explicit Scope(int id) : saved(g_phase) { g_phase = id; }
+    ~Scope() { g_phase = saved; }
+};
 }  // namespace rkc
 
 struct cnt {
@@ -122,20 +131,21 @@ static inline cnt fmax_(cnt a, cnt b) { return (a != a) ? b : ((b != b) ? a : (b
 
 extern "C" {
 
+int32_t rko_count_phases() { return RKO_PH_COUNT; }
+
 // Ruckig::calculate for every problem of the batch on the calling thread (fresh
-// Ruckig + Trajectory each, as rko_batch_calculate does). ops[5] receives the
-// totals {add+sub, mul, div, sqrt, libm}; status / duration (nullable) let the
-// caller check that the counting build takes the same branches as the plain one.
+// Ruckig + Trajectory each, as rko_batch_calculate does). ops[RKO_PH_COUNT][5]
+// receives the totals {add+sub, mul, div, sqrt, libm} per phase (rko_math.hpp);
+// status / duration (nullable) let the caller check that the counting build
+// takes the same branches as the plain one.
 void rko_count_calculate(const rk_batch_desc* d, const rk_batch_in* in, uint64_t* ops, int32_t* status, double* duration) {
     using namespace rko;
     const int64_t n = d->n;
     const int D = d->dof;
     const bool throw_mode = d->error_mode == RK_ERRORS_THROW;
-    for (int k = 0; k < rkc::NOPS; ++k) rkc::g_ops[k] = 0;
-    uint64_t acc[rkc::NOPS] = {0};
+    uint64_t acc[RKO_PH_COUNT][rkc::NOPS] = {{0}};
     InputParameter ip(D);
     for (int64_t i = 0; i < n; ++i) {
-        // filling the input is data movement, not algorithm: counters are reset around it
         ip.control_interface = d->control_interface;
         ip.synchronization = d->synchronization;
         ip.duration_discretization = d->duration_discretization;
@@ -165,15 +175,18 @@ void rko_count_calculate(const rk_batch_desc* d, const rk_batch_in* in, uint64_t
             const double md = in->minimum_duration[i];
             if (md == md) { ip.has_minimum_duration = true; ip.minimum_duration = md; }
         }
-        for (int k = 0; k < rkc::NOPS; ++k) rkc::g_ops[k] = 0;
+        std::memset(rkc::g_ops, 0, sizeof(rkc::g_ops));  // filling the input above is data movement, not algorithm
+        rkc::g_phase = RKO_PH_OTHER;
         Ruckig otg(D, d->delta_time, throw_mode);
         Trajectory tr(D);
         Outcome o = otg.calculate(ip, tr);
-        for (int k = 0; k < rkc::NOPS; ++k) acc[k] += rkc::g_ops[k];
+        for (int p = 0; p < RKO_PH_COUNT; ++p)
+            for (int k = 0; k < rkc::NOPS; ++k) acc[p][k] += rkc::g_ops[p][k];
         if (status) status[i] = o.code;
         if (duration) duration[i] = (double)tr.duration;
     }
-    for (int k = 0; k < rkc::NOPS; ++k) ops[k] = acc[k];
+    for (int p = 0; p < RKO_PH_COUNT; ++p)
+        for (int k = 0; k < rkc::NOPS; ++k) ops[p * rkc::NOPS + k] = acc[p][k];
 }
 
 }  // extern "C"

@@ -20,6 +20,27 @@
 // Microsystems 1993, FreeBSD msun revisions) — third-party published
 // algorithms, not part of /root/reference.
 #pragma once
+// Phase markers for the op-counting build (rko_count.cpp defines RKO_PHASE before it includes the oracle): a scope that
+// attributes the operations counted inside it to one part of the algorithm. They expand to nothing everywhere else.
+#ifndef RKO_PHASE
+#define RKO_PHASE(id) ((void)0)
+#endif
+enum {
+    RKO_PH_OTHER = 0,      // validation, brake, block, synchronisation, dispatch
+    RKO_PH_S1_QUARTIC,     // position_third_step1.rs:329-601 (NONE / ACC0 / ACC1)
+    RKO_PH_S1_ACC0_ACC1,   // :241-327
+    RKO_PH_S1_VEL,         // :97-240
+    RKO_PH_S1_RESCUE,      // :603-895
+    RKO_PH_S2_ACC0_ACC1_VEL,
+    RKO_PH_S2_VEL,
+    RKO_PH_S2_ACC0_VEL,
+    RKO_PH_S2_ACC1_VEL,
+    RKO_PH_S2_TAIL,        // ACC0_ACC1, ACC1, ACC0, NONE of Step 2
+    RKO_PH_CHECK,          // Profile::check (profile.rs:323-482), whoever calls it
+    RKO_PH_ROOTS,          // solve_quart_monic / solve_cub (roots.rs:132-370), whoever calls it
+    RKO_PH_NEWTON,         // shrink_interval (roots.rs:425-481)
+    RKO_PH_COUNT
+};
 #include <cmath>
 #include <cstdint>
 #include <cstring>

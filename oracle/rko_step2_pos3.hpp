@@ -52,6 +52,7 @@ struct PositionThirdOrderStep2 {
 
     // :130-245
     bool time_acc0_acc1_vel(Profile& profile, double v_max, double v_min, double a_max, double a_min, double j_max) {
+        RKO_PHASE(RKO_PH_S2_ACC0_ACC1_VEL);
         // Profile UDDU, Solution 1
         if ((2.0 * (a_max - a_min) + ad) / j_max < tf) {
             const double h1 = std::sqrt(
@@ -142,6 +143,7 @@ struct PositionThirdOrderStep2 {
 
     // :247-414
     bool time_acc1_vel(Profile& profile, double v_max, double v_min, double a_max, double a_min, double j_max) {
+        RKO_PHASE(RKO_PH_S2_ACC1_VEL);
         // Profile UDDU
         {
             const double ph1 = a0_a0 + af_af
@@ -284,6 +286,7 @@ struct PositionThirdOrderStep2 {
 
     // :416-605
     bool time_acc0_vel(Profile& profile, double v_max, double v_min, double a_max, double a_min, double j_max) {
+        RKO_PHASE(RKO_PH_S2_ACC0_VEL);
         if (tf < fmax_((-a0 + a_max) / j_max, 0.0) + fmax_(a_max / j_max, 0.0)) return false;
 
         const double ph1 = 12.0
@@ -547,6 +550,7 @@ struct PositionThirdOrderStep2 {
 
     // :607-974
     bool time_vel(Profile& profile, double v_max, double v_min, double a_max, double a_min, double j_max) {
+        RKO_PHASE(RKO_PH_S2_VEL);
         using roots::Poly; using roots::poly_eval; using roots::poly_deri; using roots::poly_monic_deri;
         using roots::shrink_interval; using roots::TOLERANCE;
         const double tz_min = fmax_(0.0, -a0 / j_max);
@@ -773,6 +777,7 @@ struct PositionThirdOrderStep2 {
 
     // :976-1079
     bool time_acc0_acc1(Profile& profile, double v_max, double v_min, double a_max, double a_min, double) {
+        RKO_PHASE(RKO_PH_S2_TAIL);
         if (std::fabs(a0) < EPS && std::fabs(af) < EPS) {
             const double h1 = 2.0 * a_min * g1
                 + vd_vd
@@ -853,6 +858,7 @@ struct PositionThirdOrderStep2 {
 
     // :1081-1310
     bool time_acc1(Profile& profile, double v_max, double v_min, double a_max, double a_min, double j_max) {
+        RKO_PHASE(RKO_PH_S2_TAIL);
         // a3 != 0.0
         // Case UDDU
         {
@@ -1035,6 +1041,7 @@ struct PositionThirdOrderStep2 {
 
     // :1312-1437
     bool time_acc0(Profile& profile, double v_max, double v_min, double a_max, double a_min, double j_max) {
+        RKO_PHASE(RKO_PH_S2_TAIL);
         // UDUD
         {
             const double h1 = std::sqrt(
@@ -1124,6 +1131,7 @@ struct PositionThirdOrderStep2 {
 
     // :1439-2202
     bool time_none(Profile& profile, double v_max, double v_min, double a_max, double a_min, double j_max) {
+        RKO_PHASE(RKO_PH_S2_TAIL);
         if (std::fabs(v0) < EPS && std::fabs(a0) < EPS && std::fabs(af) < EPS) {
             const double h1 = std::sqrt(tf_tf * vf_vf + pow2(4.0 * pd - tf * vf));
             const double jf = 4.0 * (4.0 * pd - 2.0 * tf * vf + h1) / tf_p3;

@@ -42,6 +42,7 @@ struct PositionThirdOrderStep1 {
 
     // :97-240 (all four variants are checked as ReachedLimits::Vel, quirk Q6)
     void time_all_vel(double v_max, double v_min, double a_max, double a_min, double j_max, bool) {
+        RKO_PHASE(RKO_PH_S1_VEL);
         Profile* profile = &valid_profiles[current_index];
         // ACC0_ACC1_VEL
         profile->t[0] = (-a0 + a_max) / j_max;
@@ -128,6 +129,7 @@ struct PositionThirdOrderStep1 {
 
     // :241-327
     void time_acc0_acc1(double v_max, double v_min, double a_max, double a_min, double j_max, bool return_after_found) {
+        RKO_PHASE(RKO_PH_S1_ACC0_ACC1);
         double h1 = (3. * (af_p4 * a_max - a0_p4 * a_min)
             + a_max * a_min * (8. * (a0_p3 - af_p3)
                 + 3. * a_max * a_min * (a_max - a_min)
@@ -181,6 +183,7 @@ struct PositionThirdOrderStep1 {
 
     // :329-601
     void time_all_none_acc0_acc1(double v_max, double v_min, double a_max, double a_min, double j_max, bool return_after_found) {
+        RKO_PHASE(RKO_PH_S1_QUARTIC);
         const double j_max_j_max_l = j_max * j_max;  // the local that shadows self.j_max_j_max in part of the reference
         // NONE UDDU / UDUD Strategy: t7 == 0 (equals UDDU)
         const double h2_none = (a0_a0 - af_af) / (2.0 * j_max) + (vf - v0);
@@ -382,6 +385,7 @@ struct PositionThirdOrderStep1 {
 
     // :603-642
     void time_acc1_vel_two_step(double v_max, double v_min, double a_max, double a_min, double j_max) {
+        RKO_PHASE(RKO_PH_S1_RESCUE);
         Profile* profile = &valid_profiles[current_index];
         profile->t[0] = 0.0;
         profile->t[1] = 0.0;
@@ -406,6 +410,7 @@ struct PositionThirdOrderStep1 {
 
     // :644-778
     void time_acc0_two_step(double v_max, double v_min, double a_max, double a_min, double j_max) {
+        RKO_PHASE(RKO_PH_S1_RESCUE);
         // Two step
         {
             Profile* profile = &valid_profiles[current_index];
@@ -498,6 +503,7 @@ struct PositionThirdOrderStep1 {
 
     // :780-841
     void time_vel_two_step(double v_max, double v_min, double a_max, double a_min, double j_max) {
+        RKO_PHASE(RKO_PH_S1_RESCUE);
         const double h1 = std::sqrt(af_af / (2.0 * j_max_j_max) + (v_max - vf) / j_max);
         // Four step
         {
@@ -543,6 +549,7 @@ struct PositionThirdOrderStep1 {
 
     // :843-895
     void time_none_two_step(double v_max, double v_min, double a_max, double a_min, double j_max) {
+        RKO_PHASE(RKO_PH_S1_RESCUE);
         // Two step
         {
             Profile* profile = &valid_profiles[current_index];

@@ -29,14 +29,23 @@ def load_count():
     lib = C.CDLL(os.path.join(ROOT, "oracle", "_build", "liboracle_count.so"))
     lib.rko_count_calculate.argtypes = [C.POINTER(cabi.RkBatchDesc), C.POINTER(cabi.RkBatchIn), C.c_void_p, C.c_void_p, C.c_void_p]
     lib.rko_count_calculate.restype = None
+    lib.rko_count_phases.restype = C.c_int32
     return lib
+
+
+# oracle/rko_math.hpp, enum RKO_PH_*
+PHASES = ["other (validation, brake, block, synchronisation, dispatch)", "step1 quartic families NONE/ACC0/ACC1 (without check and root solver)",
+          "step1 ACC0_ACC1", "step1 VEL", "step1 rescues", "step2 ACC0_ACC1_VEL", "step2 VEL (without Newton and check)", "step2 ACC0_VEL", "step2 ACC1_VEL",
+          "step2 ACC0_ACC1 / ACC1 / ACC0 / NONE", "Profile::check (all callers)", "solve_quart_monic / solve_cub (all callers)", "shrink_interval (all callers)"]
 
 
 def count(fields, n, dof, **kw):
     lib = load_count()
     desc, keep = cabi.make_desc(n, dof, delta_time=0.005, memory_space=cabi.RK_MEM_HOST, **kw)
     bin_ = cabi.make_in(fields)
-    ops = np.zeros(5, dtype=np.uint64)
+    n_ph = lib.rko_count_phases()
+    assert n_ph == len(PHASES)
+    ops = np.zeros((n_ph, 5), dtype=np.uint64)
     status = np.zeros(n, dtype=np.int32)
     duration = np.zeros(n)
     lib.rko_count_calculate(C.byref(desc), C.byref(bin_), ops.ctypes.data, status.ctypes.data, duration.ctypes.data)
@@ -48,8 +57,9 @@ def count(fields, n, dof, **kw):
     assert np.array_equal(status, s2), "counting build took a different branch (status)"
     assert np.array_equal(duration[ok].view(np.uint64), d2[ok].view(np.uint64)), "counting build took a different branch (duration)"
     names = ["add_sub", "mul", "div", "sqrt", "libm"]
-    per = {k: float(v) / n for k, v in zip(names, ops)}
+    per = {k: float(v) / n for k, v in zip(names, ops.sum(axis=0))}
     per["total"] = float(ops.sum()) / n
+    per["by_phase"] = {ph: round(float(ops[i].sum()) / n, 2) for i, ph in enumerate(PHASES)}
     return per, status
 
 
