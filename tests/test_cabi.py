@@ -71,3 +71,17 @@ def test_product_does_not_reference_the_oracle():
                 assert "oracle" not in text.replace("the oracle's", "").replace("(the oracle", "") or f in ("workloads.py", "rk_math.cuh", "rk_core.cuh"), f
                 assert not re.search(r"^\s*(from|import)\s+oracle", text, flags=re.M), f
                 assert '#include "../../oracle' not in text and "rko_" not in text, f
+
+
+def test_rust_sys_crate_declares_every_function_of_the_header():
+    """bindings/rust/ruckig-b200-sys is source only (no Rust toolchain here): at least its list of functions and the field
+    constants must follow the header."""
+    src = open(os.path.join(ROOT, "bindings", "rust", "ruckig-b200-sys", "src", "lib.rs")).read()
+    declared = sorted(set(re.findall(r"pub fn (rk_[a-z0-9_]+)\s*\(", src)))
+    assert declared == declared_symbols()
+    header = open(os.path.join(ROOT, "include", "ruckig_b200.h")).read()
+    fields = re.search(r"enum \{\s*RK_FIELD_STATUS = 0,(.*?)RK_FIELD_COUNT", header, flags=re.S).group(0)
+    fields = re.sub(r"/\*.*?\*/", "", fields, flags=re.S)
+    names = re.findall(r"\b(RK_FIELD_[A-Z0-9_]+)\b", fields)[:-1]
+    for value, name in enumerate(names):
+        assert re.search(rf"pub const {name}: i32 = {value};", src), name
