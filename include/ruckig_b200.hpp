@@ -11,6 +11,7 @@
 //                     get_profiles, get_position_extrema, get_first_time_at_position}   trajectory.rs:158-246
 //   RuckigResult, RuckigError, ThrowErrorHandler / IgnoreErrorHandler          result.rs:34-61, error.rs:15-122
 //   BatchRuckig<DOF, E>: the batched entry point (n problems in SoA arrays [dof][n], host or device memory)
+//   BatchRollout<DOF, E>: n closed control loops on the device (the batched Ruckig::update)
 //
 // As in the reference DOF = 0 means "number of DoFs given at run time" (Ruckig::new(Some(n), ..)), any other DOF fixes it.
 // Every calculation runs on the GPU — a single problem is a batch of one; there is no CPU path behind these classes:
@@ -581,6 +582,66 @@ private:
     rk_handle* handle_;
     rk_trajectories* traj_ = nullptr;
     int64_t n_ = 0;
+};
+
+// ------------------------------------------------------------------------------------------------------------ BatchRollout
+// n independent closed control loops on the device: the batched Ruckig::update (ruckig.rs:266-321). update() is one control
+// cycle for every environment: those whose input changed (or that were never calculated) are re-solved, all advance their time
+// by delta_time, sample their trajectory and — with pass_to_input — get the new state written into in.current_*, ready for the
+// next cycle (OutputParameter::pass_to_input). All buffers are DEVICE arrays [dof][n] / [n] (rk_update_batch takes no host
+// buffers). Same calls as rsruckig_b200.api.BatchRollout, which tests/test_rollout.py holds to one stateful oracle calculator
+// per environment.
+template <size_t DOF, class E = ThrowErrorHandler>
+class BatchRollout {
+public:
+    int64_t n;
+    size_t degrees_of_freedom;
+    double delta_time;
+
+    BatchRollout(int64_t n_, double delta_time_, std::optional<size_t> dofs = std::nullopt, int32_t device = 0)
+        : n(n_), degrees_of_freedom(detail::resolve_dofs(DOF, dofs)), delta_time(delta_time_), handle_(detail::Engine::get(device).h) {
+        detail::check(rk_rollout_create(handle_, n, (int32_t)degrees_of_freedom, &rollout_));
+    }
+    ~BatchRollout() { if (rollout_) rk_rollout_destroy(rollout_); }
+    BatchRollout(const BatchRollout&) = delete;
+    BatchRollout& operator=(const BatchRollout&) = delete;
+
+    void reset() { detail::check(rk_rollout_reset(handle_, rollout_)); }  // Ruckig::reset + a fresh OutputParameter per environment
+
+    // One control cycle. `out` names the device arrays that receive OutputParameter's fields (each nullable) and carries the
+    // pass_to_input / reset_time_on_new_calculation switches. Returns the number of environments that were re-solved.
+    int64_t update(const rk_batch_in& in, const rk_update_out& out, BatchSettings settings = {}) {
+        settings.device_memory = true;
+        rk_batch_desc d{};
+        d.n = n;
+        d.dof = (int32_t)degrees_of_freedom;
+        d.control_interface = (int32_t)settings.control_interface;
+        d.synchronization = (int32_t)settings.synchronization;
+        d.duration_discretization = (int32_t)settings.duration_discretization;
+        d.error_mode = E::throws ? RK_ERRORS_THROW : RK_ERRORS_IGNORE;
+        d.memory_space = RK_MEM_DEVICE;
+        d.delta_time = delta_time;
+        std::vector<int32_t> ci, sy;
+        if (settings.per_dof_control_interface) {
+            for (ControlInterface c : *settings.per_dof_control_interface) ci.push_back((int32_t)c);
+            d.per_dof_control_interface = ci.data();
+        }
+        if (settings.per_dof_synchronization) {
+            for (Synchronization c : *settings.per_dof_synchronization) sy.push_back((int32_t)c);
+            d.per_dof_synchronization = sy.data();
+        }
+        int64_t recalculated = 0;
+        detail::check(rk_update_batch(handle_, &d, &in, rollout_, &out, &recalculated));
+        return recalculated;
+    }
+
+    rk_trajectories* trajectories() const { return rk_rollout_trajectories(rollout_); }  // owned by the rollout
+    void sync() const { detail::check(rk_sync(handle_)); }
+    void* stream() const { return rk_stream(handle_); }
+
+private:
+    rk_handle* handle_;
+    rk_rollout* rollout_ = nullptr;
 };
 
 }  // namespace ruckig_b200

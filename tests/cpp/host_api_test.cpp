@@ -171,6 +171,16 @@ static void test_batch_matches_single() {
     CHECK(batch.error_message(0).empty());
 }
 
+// Never called: instantiates the device-buffer classes so that the whole header is compiled under -Wall -Wextra -Werror (their
+// behaviour is covered through the same C calls by tests/test_rollout.py).
+[[maybe_unused]] static int64_t instantiate_device_buffer_classes(const rk_batch_in& in, const rk_update_out& out) {
+    BatchRollout<7, IgnoreErrorHandler> rollout(4, 0.005);
+    rollout.reset();
+    const int64_t recalculated = rollout.update(in, out);
+    rollout.sync();
+    return recalculated + (rollout.trajectories() != nullptr) + (rollout.stream() != nullptr);
+}
+
 int main(int argc, char** argv) {
     if (argc > 1 && std::strcmp(argv[1], "--no-gpu") == 0) {
         try {
