@@ -372,8 +372,8 @@ __device__ RK_S2_FN bool s2_vel_udud(const S2& s, const Lim& L, Hit& h) {
     return false;
 }
 
-// Warp-level pool for the bracketing levels of the UDUD half (RK_UDUD_WARP_POOL = 1; written at the end of round 1: bit-identical
-// to the oracle on 58 652 7-DoF bench trajectories (tools/quick_parity.py), speed NOT yet measured — off by default). The two levels run shrink_interval at 7-9 of 32 lanes
+// Warp-level pool for the bracketing levels of the UDUD half (RK_UDUD_WARP_POOL = 1; written at the end of round 1: parity-green on
+// 58 652 7-DoF bench trajectories (tools/quick_parity.py), speed NOT yet measured — off by default). The two levels run shrink_interval at 7-9 of 32 lanes
 // (profiles/r1_ncu_summary.md): few lanes hold an active item, and those hold 0-6 brackets each. Here the lanes of a warp
 // deposit polynomial and brackets in shared memory and the warp's brackets are dealt out evenly, one per lane per pass; the
 // owner reads its roots back. shrink_interval is a pure function of (polynomial, l, h), so who evaluates it changes nothing.
