@@ -335,7 +335,7 @@ impl<const DOF: usize, E: RuckigErrorHandler> BatchRuckig<DOF, E> {
                    acceleration: Option<&mut [f64]>, jerk: Option<&mut [f64]>) -> Result<(), RuckigError> {
         let traj = self.traj.as_ref().ok_or_else(|| RuckigError::CalculatorError("calculate() has not been called".to_string()))?;
         let want = steps * traj.dof * traj.n;
-        let mut out_ptr = |s: Option<&mut [f64]>| -> Result<*mut f64, RuckigError> {
+        let out_ptr = |s: Option<&mut [f64]>| -> Result<*mut f64, RuckigError> {
             match s {
                 None => Ok(ptr::null_mut()),
                 Some(s) if s.len() == want => Ok(s.as_mut_ptr()),
@@ -487,7 +487,7 @@ impl<const DOF: usize, E: RuckigErrorHandler> GpuRuckig<DOF, E> {
         }
         output.time += self.delta_time;
         let time = output.time;
-        let GpuOutput { trajectory, new_position, new_velocity, new_acceleration, new_jerk, .. } = output;
+        let GpuOutput { trajectory, new_position, new_velocity, new_acceleration, new_jerk, .. } = &mut *output;
         trajectory.at_time(time, &mut Some(&mut new_position[..]), &mut Some(&mut new_velocity[..]), &mut Some(&mut new_acceleration[..]),
                            &mut Some(&mut new_jerk[..]), &mut None)?;
         output.did_section_change = false;  // ruckig.rs:300-302: new_section is passed by value
