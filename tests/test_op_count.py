@@ -27,12 +27,15 @@ def test_counting_build_follows_the_plain_oracle_and_counts_are_stable():
     per, status = m.count(workloads.bench_inputs(n, 7, seed=3), n, 7)  # asserts status + duration bit-equal inside
     assert (status >= 0).mean() > 0.9
     assert abs(per["total"] - (per["add_sub"] + per["mul"] + per["div"] + per["sqrt"] + per["libm"])) < 1e-6
+    assert abs(per["total"] - sum(per["by_phase"].values())) < 0.1  # every operation is attributed to exactly one phase
+    assert per["by_phase"]["shrink_interval (all callers)"] > 0.15 * per["total"]  # the Newton bracketing of Step-2 VEL is the largest part
     # the committed figure bench.py uses was produced by the same tool on 262144 trajectories: a 4096 sample lands within 5 %
     ref = json.load(open(os.path.join(ROOT, "profiles", "algorithmic_ops_oracle.json")))
     assert abs(per["total"] / ref["flop_per_trajectory_7dof"] - 1.0) < 0.05
     # a single-DoF problem has no Step 2: far fewer operations than one seventh of a 7-DoF trajectory's Step 1 + Step 2
     per1, _ = m.count(workloads.bench_inputs(n, 1, seed=3), n, 1)
     assert per1["total"] < per["total"] / 7
+    assert per1["by_phase"]["shrink_interval (all callers)"] == 0 and per1["by_phase"]["step2 VEL (without Newton and check)"] == 0
 
 
 def test_velocity_interface_is_cheap():
