@@ -213,6 +213,9 @@ __device__ __forceinline__ Lim family_limits(const DofIn& x, const Bound& b, int
 #ifndef RK_CC_MINB
 #define RK_CC_MINB 8
 #endif
+#ifndef RK_CC_BARRIER
+#define RK_CC_BARRIER 0
+#endif
 #ifndef RK_CC_SPLIT
 #define RK_CC_SPLIT 0  // 1: ACC0_ACC1 and VEL in two launches (PART 0 / 1) instead of one (PART 2)
 #endif
@@ -224,6 +227,46 @@ __global__ void __launch_bounds__(128, RK_CC_MINB) k1_closed_cands(const Params 
     uint32_t parked3 = 0, parked4 = 0;
     int ds = 0;
     int64_t wi = 0;
+#if RK_CC_BARRIER
+    // Lockstep form (prepared at the end of round 1, not yet measured): a block barrier between the two families keeps the warps
+    // of a block in the same few KB of code (no_instruction is 2.3 warp-cycles per issued instruction in this kernel).
+    bool active = false;
+    Bound b;
+    DofIn x;
+    Lim L;
+    if (tid < 2 * wstride) {
+        ds = (int)(tid / wstride);
+        wi = tid - (int64_t)ds * wstride;
+        const uint32_t meta = P.wmeta[(int64_t)WM_META * wstride + wi];
+        if (meta & M_S1_PENDING) {
+            double bdur_;
+            x = load_rec(P, wi, b, bdur_);
+            bool rest_target, trivial;
+            L = family_limits(x, b, ds, rest_target, trivial);
+            if (PART != 1) P.wqmask[(int64_t)(6 + ds) * wstride + wi] = 0u;
+            if (PART != 0) P.wqmask[(int64_t)(8 + ds) * wstride + wi] = 0u;
+            active = !trivial;  // :1015-1025 — nothing moves: only the quartics of the first direction are tried
+        }
+    }
+    Step1Pos3<CandSink> s;
+    if (active) {
+        s.init(b, x.j_max);
+        s.first_only = false;
+        if (PART != 1) {
+            s.sink.parked = 0;
+            s.sink.base = vl_slot(P, wi, sub_slot_base(6 + ds));
+            s.family_acc0_acc1(L);
+            parked3 = s.sink.parked;
+        }
+    }
+    __syncthreads();
+    if (active && PART != 0) {
+        s.sink.parked = 0;
+        s.sink.base = vl_slot(P, wi, sub_slot_base(8 + ds));
+        s.family_vel(L);
+        parked4 = s.sink.parked;
+    }
+#else
     if (tid < 2 * wstride) {
         ds = (int)(tid / wstride);
         wi = tid - (int64_t)ds * wstride;
@@ -255,6 +298,7 @@ __global__ void __launch_bounds__(128, RK_CC_MINB) k1_closed_cands(const Params 
             }
         }
     }
+#endif
     const int mine = __popc(parked3) + __popc(parked4);
     uint32_t e = warp_reserve(P.counters + 23, mine);
 #pragma unroll
