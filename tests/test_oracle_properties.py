@@ -54,3 +54,39 @@ def test_working_trajectories_reach_the_target_inside_the_limits(flavour, gen, d
     assert after_brake.sum() > 500_000
     assert np.all((vel <= v_max[None] + 1e-7)[after_brake]) and np.all((vel >= v_min[None] - 1e-7)[after_brake])
     assert np.all((acc <= a_max[None] + 1e-7)[after_brake]) and np.all((acc >= a_min[None] - 1e-7)[after_brake])
+
+
+@pytest.mark.parametrize("flavour", ["glibc", "portable"])
+def test_replanning_from_a_state_on_the_trajectory_never_finds_a_shorter_one(flavour):
+    """SURVEY.md 8c safeguard (2), the random-input form of `check_full_duration` (tests_known.rs:15-27): take the state a
+    trajectory of duration T passes through at time t and plan again from there. The rest of the old trajectory is a valid
+    answer, and the old one was time-optimal, so the new duration can never be shorter than T - t; it is exactly T - t
+    unless T - t now sits on the edge of a blocked interval (then the next feasible duration is taken: longer). A restatement
+    that returned non-optimal profiles, or profiles that do not pass through the states it reports, would break this."""
+    from oracle.oracle import OracleBatch
+    n, dof, K = 6000, 3, 128
+    f = workloads.bench_inputs(n, dof, seed=5)
+    ob = OracleBatch(n, dof, flavour)
+    ob.calculate(f, threads=4)
+    ok = ob.read(cabi.RK_FIELD_STATUS) == 0
+    T = ob.read(cabi.RK_FIELD_DURATION)
+    dt = float(np.median(T[ok])) / 48
+    pos, vel, acc, _, _ = ob.at_time(time_start=0.0, delta_time=dt, steps=K, threads=4)
+    tk = np.cumsum(np.full(K, dt))  # repeated addition, as at_time accumulates its sample times
+    k = np.searchsorted(tk, 0.6 * T, side="right") - 1  # the last sample not later than 0.6 T
+    use = ok & (k >= 0)
+    idx = np.nonzero(use)[0]
+    assert idx.size > 0.9 * n
+    g = {key: v.copy() for key, v in f.items()}
+    g["current_position"][:, idx] = pos[k[idx], :, idx].T
+    g["current_velocity"][:, idx] = vel[k[idx], :, idx].T
+    g["current_acceleration"][:, idx] = acc[k[idx], :, idx].T
+    ob2 = OracleBatch(n, dof, flavour)
+    ob2.calculate(g, threads=4)
+    st2, T2 = ob2.read(cabi.RK_FIELD_STATUS), ob2.read(cabi.RK_FIELD_DURATION)
+    # a sampled state can sit one ulp beyond a limit it was riding on; Step 1 then finds no profile for a handful of them
+    assert (st2[use] != 0).mean() < 0.005
+    both = use & (st2 == 0)
+    d = (T2 - (T - tk[np.clip(k, 0, K - 1)]))[both]
+    assert d.min() > -1e-9, d.min()
+    assert (np.abs(d) < 1e-9).mean() > 0.8
