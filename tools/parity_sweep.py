@@ -18,6 +18,24 @@ for seed in range(10, 10 + int(sys.argv[1]) if len(sys.argv) > 1 else 18):
     otg, ob = run_both(BatchRuckig, f, n, 7, threads=16)
     total += assert_exact(otg, ob, label=f"7dof seed {seed}")
     del otg, ob
+    # states ON trajectories (closed-loop distribution: velocities / accelerations riding their limits, sometimes one ulp beyond):
+    # re-plan from the state each trajectory of a smaller batch passes through at about 0.6 of its duration
+    n = 100_000
+    f = workloads.bench_inputs(n, 7, seed=300 + seed)
+    otg, ob = run_both(BatchRuckig, f, n, 7, threads=16)
+    from rsruckig_b200 import _cabi as cabi
+    T, ok = ob.read(cabi.RK_FIELD_DURATION), ob.read(cabi.RK_FIELD_STATUS) == 0
+    K = 32
+    dt = float(np.median(T[ok])) / 12
+    pos, vel, acc, _, _ = ob.at_time(time_start=0.0, delta_time=dt, steps=K, threads=16, want_jerk=False)
+    k = np.searchsorted(np.cumsum(np.full(K, dt)), 0.6 * T, side="right") - 1
+    idx = np.nonzero(ok & (k >= 0))[0]
+    for name, arr in (("current_position", pos), ("current_velocity", vel), ("current_acceleration", acc)):
+        f[name][:, idx] = arr[k[idx], :, idx].T
+    del otg, ob, pos, vel, acc
+    otg, ob = run_both(BatchRuckig, f, n, 7, threads=16)
+    total += assert_exact(otg, ob, label=f"re-planned states seed {seed}")
+    del otg, ob
     n = 200_000
     f = workloads.config2_inputs(n, seed=seed)
     otg, ob = run_both(BatchRuckig, f, n, 6, threads=16)
