@@ -990,25 +990,11 @@ rk_status rk_calculate_batch(rk_handle* h, const rk_batch_desc* desc, const rk_b
         RK_CUDA(cudaMemsetAsync(c.counters, 0, sizeof(uint32_t) * RK_N_COUNTERS, cs));
         rk_launch(rk::k1_setup, grid_items, 128, cs, P);
         const unsigned grid_fam = (unsigned)((2 * items + 127) / 128);
-        const unsigned grid_fam_pool = (unsigned)((2 * items + 128 * RK_QP_ITEMS - 1) / (128 * RK_QP_ITEMS));  // RK_QP_ITEMS work items per thread
-        (void)grid_fam_pool;
-#if RK_QUARTIC_POOL & 1
-        rk_launch(rk::k1_quartic_roots_pool<0>, grid_fam_pool, 128, cs, P);
-#else
         rk_launch(rk::k1_quartic_roots<0>, grid_fam, 128, cs, P);
-#endif
         rk_launch(rk::k1_quartic_check<0>, grid_list, 128, cs, P);
-#if RK_QUARTIC_POOL & 2
-        rk_launch(rk::k1_quartic_roots_pool<1>, grid_fam_pool, 128, cs, P);
-#else
         rk_launch(rk::k1_quartic_roots<1>, grid_fam, 128, cs, P);
-#endif
         rk_launch(rk::k1_quartic_check<1>, grid_list, 128, cs, P);
-#if RK_QUARTIC_POOL & 4
-        rk_launch(rk::k1_quartic_roots_pool<2>, grid_fam_pool, 128, cs, P);
-#else
         rk_launch(rk::k1_quartic_roots<2>, grid_fam, 128, cs, P);
-#endif
         rk_launch(rk::k1_quartic_check<2>, grid_list, 128, cs, P);
 #if RK_CC_SPLIT
         rk_launch(rk::k1_closed_cands<0>, grid_fam, 128, cs, P);

@@ -213,9 +213,6 @@ __device__ __forceinline__ Lim family_limits(const DofIn& x, const Bound& b, int
 #ifndef RK_CC_MINB
 #define RK_CC_MINB 8
 #endif
-#ifndef RK_CC_BARRIER
-#define RK_CC_BARRIER 0
-#endif
 #ifndef RK_CC_SPLIT
 #define RK_CC_SPLIT 0  // 1: ACC0_ACC1 and VEL in two launches (PART 0 / 1) instead of one (PART 2)
 #endif
@@ -227,46 +224,6 @@ __global__ void __launch_bounds__(128, RK_CC_MINB) k1_closed_cands(const Params 
     uint32_t parked3 = 0, parked4 = 0;
     int ds = 0;
     int64_t wi = 0;
-#if RK_CC_BARRIER
-    // Lockstep form (prepared at the end of round 1, not yet measured): a block barrier between the two families keeps the warps
-    // of a block in the same few KB of code (no_instruction is 2.3 warp-cycles per issued instruction in this kernel).
-    bool active = false;
-    Bound b;
-    DofIn x;
-    Lim L;
-    if (tid < 2 * wstride) {
-        ds = (int)(tid / wstride);
-        wi = tid - (int64_t)ds * wstride;
-        const uint32_t meta = P.wmeta[(int64_t)WM_META * wstride + wi];
-        if (meta & M_S1_PENDING) {
-            double bdur_;
-            x = load_rec(P, wi, b, bdur_);
-            bool rest_target, trivial;
-            L = family_limits(x, b, ds, rest_target, trivial);
-            if (PART != 1) P.wqmask[(int64_t)(6 + ds) * wstride + wi] = 0u;
-            if (PART != 0) P.wqmask[(int64_t)(8 + ds) * wstride + wi] = 0u;
-            active = !trivial;  // :1015-1025 — nothing moves: only the quartics of the first direction are tried
-        }
-    }
-    Step1Pos3<CandSink> s;
-    if (active) {
-        s.init(b, x.j_max);
-        s.first_only = false;
-        if (PART != 1) {
-            s.sink.parked = 0;
-            s.sink.base = vl_slot(P, wi, sub_slot_base(6 + ds));
-            s.family_acc0_acc1(L);
-            parked3 = s.sink.parked;
-        }
-    }
-    __syncthreads();
-    if (active && PART != 0) {
-        s.sink.parked = 0;
-        s.sink.base = vl_slot(P, wi, sub_slot_base(8 + ds));
-        s.family_vel(L);
-        parked4 = s.sink.parked;
-    }
-#else
     if (tid < 2 * wstride) {
         ds = (int)(tid / wstride);
         wi = tid - (int64_t)ds * wstride;
@@ -298,7 +255,6 @@ __global__ void __launch_bounds__(128, RK_CC_MINB) k1_closed_cands(const Params 
             }
         }
     }
-#endif
     const int mine = __popc(parked3) + __popc(parked4);
     uint32_t e = warp_reserve(P.counters + 23, mine);
 #pragma unroll
@@ -387,113 +343,6 @@ __global__ void __launch_bounds__(128, RK_MIN_BLOCKS) k1_quartic_roots(const Par
         if (k < n_roots) {
             P.rq_item[base + k] = make_uint2((uint32_t)wi, (uint32_t)ds | ((uint32_t)k << 1));
             P.rq_root[base + k] = roots[k];
-        }
-    }
-}
-
-// Pooled form of k1_quartic_roots (RK_QUARTIC_POOL = bit mask of the families that use it; written at the end of round 1, NOT
-// yet run on a GPU — 0 by default). The ACC0 / ACC1 kernels run at 17-19 of 32 lanes because the sign pre-screen
-// (position_third_step1.rs:404-422) drops about half of the quartics before the closed-form solver. Here every thread prepares
-// RK_QP_ITEMS work items (coefficients, range, pre-screen — uniform code), the survivors of the warp go into a queue in shared
-// memory, and the solver runs over that queue 32 entries at a time. solve_quart_monic is a pure function of the four
-// coefficients, so who evaluates it changes nothing; the queue entry carries the work item the roots belong to.
-#ifndef RK_QUARTIC_POOL
-#define RK_QUARTIC_POOL 0
-#endif
-#ifndef RK_QP_ITEMS
-#define RK_QP_ITEMS 2
-#endif
-struct QuarticTask {
-    double q[4], t_min, t_max;
-    uint32_t wi, ds;
-};
-template <int TYPE>
-__global__ void __launch_bounds__(128, RK_MIN_BLOCKS) k1_quartic_roots_pool(const Params P) {
-    RK_PDL_ENTER();
-    __shared__ QuarticTask queue[4][32 * RK_QP_ITEMS];
-    const int64_t wstride = (int64_t)P.dof * P.cn;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const unsigned lt_mask = (1u << lane) - 1u;
-    int queued = 0;  // uniform per warp
-#pragma unroll 1
-    for (int j = 0; j < RK_QP_ITEMS; ++j) {
-        const int64_t tid = ((int64_t)blockIdx.x * RK_QP_ITEMS + j) * blockDim.x + threadIdx.x;
-        bool has = false;
-        QuarticTask task;
-        if (tid < 2 * wstride) {
-            const int ds = (int)(tid / wstride);
-            const int64_t wi = tid - (int64_t)ds * wstride;
-            const uint32_t meta = P.wmeta[(int64_t)WM_META * wstride + wi];
-            if (meta & M_S1_PENDING) {
-                Bound b;
-                double bdur_;
-                const DofIn x = load_rec(P, wi, b, bdur_);
-                bool rest_target, trivial;
-                const Lim L = family_limits(x, b, ds, rest_target, trivial);
-                P.wqmask[(int64_t)(TYPE * 2 + ds) * wstride + wi] = 0u;
-                if (!(trivial && ds == 1)) {  // :1015-1025 — nothing moves: only the first direction is tried
-                    Step1Pos3<QuarticSink> s;
-                    s.init(b, x.j_max);
-                    s.sink.n_roots = 0;
-                    s.sink.has_prep = false;
-                    s.first_only = false;
-                    if (TYPE == 0) s.template quartic_none<QUARTIC_PREP>(L, 0.0);
-                    else if (TYPE == 1) s.template quartic_acc0<QUARTIC_PREP>(L, 0.0);
-                    else s.template quartic_acc1<QUARTIC_PREP>(L, 0.0);
-                    has = s.sink.has_prep;
-                    if (has) {
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) task.q[k] = s.sink.prep[k];
-                        task.t_min = s.sink.prep[4];
-                        task.t_max = s.sink.prep[5];
-                        task.wi = (uint32_t)wi;
-                        task.ds = (uint32_t)ds;
-                    }
-                }
-            }
-        }
-        const unsigned ballot = __ballot_sync(0xffffffffu, has);
-        if (has) queue[warp][queued + __popc(ballot & lt_mask)] = task;
-        queued += __popc(ballot);
-    }
-    __syncwarp();
-#pragma unroll 1
-    for (int first = 0; first < queued; first += 32) {  // uniform per warp
-        double roots[4];
-        int n_roots = 0;
-        uint32_t wi = 0, ds = 0;
-        if (first + lane < queued) {
-            const QuarticTask task = queue[warp][first + lane];
-            wi = task.wi;
-            ds = task.ds;
-            const Roots r4 = solve_quart_monic(task.q[0], task.q[1], task.q[2], task.q[3]);
-#pragma unroll
-            for (int ri = 0; ri < 4; ++ri) {
-                const double r = r4.get(ri);
-                if (ri < r4.n && !(r < task.t_min || r > task.t_max)) {  // ascending order: rank = position among the kept roots
-                    if (n_roots == 0) roots[0] = r; else if (n_roots == 1) roots[1] = r; else if (n_roots == 2) roots[2] = r; else roots[3] = r;
-                    ++n_roots;
-                }
-            }
-        }
-        // warp-aggregated append of a variable number of entries per lane (as in k1_quartic_roots)
-        int incl = n_roots;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int up = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += up;
-        }
-        const int total = __shfl_sync(0xffffffffu, incl, 31);
-        if (total == 0) continue;
-        uint32_t base = 0;
-        if (lane == 31) base = atomicAdd(P.counters + 20 + TYPE, (uint32_t)total);
-        base = __shfl_sync(0xffffffffu, base, 31) + (uint32_t)(incl - n_roots);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            if (k < n_roots) {
-                P.rq_item[base + k] = make_uint2(wi, ds | ((uint32_t)k << 1));
-                P.rq_root[base + k] = roots[k];
-            }
         }
     }
 }

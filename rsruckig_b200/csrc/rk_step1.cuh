@@ -107,7 +107,7 @@ __device__ __noinline__ bool calculate_block(BlockRec& blk, Cand* vp, int n, dou
 }
 
 // ===================================================== third-order position interface
-enum : int { QUARTIC_ROOTS = 0, QUARTIC_CANDIDATE = 1, QUARTIC_PREP = 2 };  // PREP: coefficients + range only (k1_quartic_roots_pool)
+enum : int { QUARTIC_ROOTS = 0, QUARTIC_CANDIDATE = 1 };
 
 // Where validated candidates go: a local list (numerical rescues, zero-limit case) ...
 struct LocalSink {
@@ -115,7 +115,6 @@ struct LocalSink {
     static constexpr bool screen_only = false;
     int variant;
     __device__ __forceinline__ void push_root(double) {}
-    __device__ __forceinline__ void set_prep(double, double, double, double, double, double) {}
     Cand vp[6];
     int count;
     __device__ __forceinline__ void put(const double (&t)[7], int lim, const Lim& L) {
@@ -135,14 +134,8 @@ struct QuarticSink {
     int variant;
     double roots[4];
     int n_roots;
-    double prep[6];  // QUARTIC_PREP: the monic quartic's coefficients, t_min, t_max of a quartic that passed its pre-screen
-    bool has_prep;
     double* slot;  // the 64-byte candidate slot this root owns: t[7] + duration
     int count;
-    __device__ __forceinline__ void set_prep(double q0, double q1, double q2, double q3, double t_min, double t_max) {
-        prep[0] = q0; prep[1] = q1; prep[2] = q2; prep[3] = q3; prep[4] = t_min; prep[5] = t_max;
-        has_prep = true;
-    }
     __device__ __forceinline__ void push_root(double r) {
         if (n_roots == 0) roots[0] = r; else if (n_roots == 1) roots[1] = r; else if (n_roots == 2) roots[2] = r; else roots[3] = r;
         ++n_roots;
@@ -161,7 +154,6 @@ struct CandSink {
     static constexpr bool inline_check = true;
     static constexpr bool screen_only = true;
     __device__ __forceinline__ void push_root(double) {}
-    __device__ __forceinline__ void set_prep(double, double, double, double, double, double) {}
     double* base;     // slot 0 of this sub-list for this item (64-byte slots: t[7] + duration)
     int variant;      // slot inside the sub-list the next candidate goes to
     uint32_t parked;  // bit v set: slot v holds a candidate to be checked
@@ -358,7 +350,6 @@ struct Step1Pos3 {
         const real pn1 = -2.0 * (a0_a0 + af_af - 2.0 * j_max * (v0 + vf)) / (jl);
         const real pn2 = 4.0 * (a0_p3 - af_p3 + 3.0 * j_max * (af * vf - a0 * v0)) / (3.0 * jl * j_max) - 4.0 * pd / j_max;
         const real pn3 = -h2_h2 / (jl);
-        if (MODE == QUARTIC_PREP) { sink.set_prep(0.0, pn1, pn2, pn3, t_min_none, t_max_none); return; }
         double t[7];
         if (MODE == QUARTIC_ROOTS) {  // phase A: closed-form roots, keep the ones inside [t_min, t_max] in ascending order
             const Roots roots = solve_quart_monic(0.0, pn1, pn2, pn3);
@@ -419,7 +410,6 @@ struct Step1Pos3 {
         const real m3 = pa3 + (pa2 + (pa1 + (pa0 + t_min_acc0) * t_min_acc0) * t_min_acc0) * t_min_acc0;
         const bool acc0_has_solution = (m0 < 0.0) || (m1 < 0.0) || (m2 < 0.0) || (m3 <= 0.0);
         if (MODE == QUARTIC_ROOTS && !acc0_has_solution) return;
-        if (MODE == QUARTIC_PREP) { if (acc0_has_solution) sink.set_prep(pa0, pa1, pa2, pa3, t_min_acc0, t_max_acc0); return; }
         double t[7];
         if (MODE == QUARTIC_ROOTS) {  // phase A: closed-form roots, keep the ones inside [t_min, t_max] in ascending order
             const Roots roots = solve_quart_monic(pa0, pa1, pa2, pa3);
@@ -470,7 +460,6 @@ struct Step1Pos3 {
         const real pb3 = h0_acc1 / (jj * jj);
         const bool acc1_has_solution = (pb0 < 0.0) || (pb1 < 0.0) || (pb2 < 0.0) || (pb3 <= 0.0);
         if (MODE == QUARTIC_ROOTS && !acc1_has_solution) return;
-        if (MODE == QUARTIC_PREP) { if (acc1_has_solution) sink.set_prep(pb0, pb1, pb2, pb3, t_min_acc1, t_max_acc1); return; }
         double t[7];
         if (MODE == QUARTIC_ROOTS) {  // phase A: closed-form roots, keep the ones inside [t_min, t_max] in ascending order
             const Roots roots = solve_quart_monic(pb0, pb1, pb2, pb3);

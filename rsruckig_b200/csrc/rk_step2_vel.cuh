@@ -372,63 +372,9 @@ __device__ RK_S2_FN bool s2_vel_udud(const S2& s, const Lim& L, Hit& h) {
     return false;
 }
 
-// Warp-level pool for the bracketing levels of the UDUD half (RK_UDUD_WARP_POOL = 1; written at the end of round 1: parity-green on
-// 58 652 7-DoF bench trajectories (tools/quick_parity.py), speed NOT yet measured — off by default). The two levels run shrink_interval at 7-9 of 32 lanes
-// (profiles/r1_ncu_summary.md): few lanes hold an active item, and those hold 0-6 brackets each. Here the lanes of a warp
-// deposit polynomial and brackets in shared memory and the warp's brackets are dealt out evenly, one per lane per pass; the
-// owner reads its roots back. shrink_interval is a pure function of (polynomial, l, h), so who evaluates it changes nothing.
-// All 32 lanes of the warp must call this (inactive lanes with n_tasks = 0). A bracket with lo == hi is a root already.
-#ifndef RK_UDUD_WARP_POOL
-#define RK_UDUD_WARP_POOL 0
-#endif
 #ifndef RK_LS_BLOCK
 #define RK_LS_BLOCK 128  // threads per block of the lockstep kernels (rk_pipeline.cuh)
 #endif
-struct WarpPool {
-    double poly[RK_LS_BLOCK / 32][32][7];
-    double lo[RK_LS_BLOCK / 32][32][7];  // receives the roots
-    double hi[RK_LS_BLOCK / 32][32][7];
-    int count[RK_LS_BLOCK / 32][32];
-};
-
-template <int N>
-__device__ __forceinline__ void warp_pool_shrink(WarpPool& pool, const double (&poly)[N], const double* lo, const double* hi, int n_tasks,
-                                                 double* roots) {
-    static_assert(N <= 7, "WarpPool::poly holds 7 coefficients");
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    pool.count[warp][lane] = n_tasks;
-    if (n_tasks > 0) {
-#pragma unroll
-        for (int i = 0; i < N; ++i) pool.poly[warp][lane][i] = poly[i];
-    }
-#pragma unroll 1
-    for (int k = 0; k < n_tasks; ++k) {
-        pool.lo[warp][lane][k] = lo[k];
-        pool.hi[warp][lane][k] = hi[k];
-    }
-    __syncwarp();
-    int total = 0;
-#pragma unroll 1
-    for (int o = 0; o < 32; ++o) total += pool.count[warp][o];
-    int owner = 0, base = 0;
-#pragma unroll 1
-    for (int t = lane; t < total; t += 32) {
-        while (t >= base + pool.count[warp][owner]) {
-            base += pool.count[warp][owner];
-            ++owner;
-        }
-        const int k = t - base;
-        double pc[N];
-#pragma unroll
-        for (int i = 0; i < N; ++i) pc[i] = pool.poly[warp][owner][i];
-        const double l = pool.lo[warp][owner][k], hh = pool.hi[warp][owner][k];
-        pool.lo[warp][owner][k] = (l != hh) ? shrink_interval<N>(pc, l, hh) : hh;  // task (owner, k) belongs to this lane alone
-    }
-    __syncwarp();
-#pragma unroll 1
-    for (int k = 0; k < n_tasks; ++k) roots[k] = pool.lo[warp][lane][k];
-    __syncwarp();  // the buffers are re-used by the next level
-}
 
 // Lockstep form of the UDUD half: phases A-C as above, then the two bracketing levels inside the kernel.
 __device__ __forceinline__ bool s2_vel_udud_lockstep(const S2& s, const Lim& L, Hit& h, bool active) {
@@ -493,51 +439,6 @@ __device__ __forceinline__ bool s2_vel_udud_lockstep(const S2& s, const Lim& L, 
         }
     }
 
-#if RK_UDUD_WARP_POOL
-    __shared__ WarpPool pool;
-    // phase D: extrema of the sextic — every bracket of the warp polished by whichever lane is free, then the candidates are
-    // recorded per item in the reference's order; pass k == n_iv is the interval ending at tz_max
-    double c_lo[7], c_hi[7];
-    int n_cand = 0;
-    {
-        double tzs[6];
-        warp_pool_shrink<6>(pool, deriv, iv_l, iv_r, active ? n_iv : 0, tzs);
-        if (active) {
-            real tz_current = tz_min;
-            real val_current = poly_eval<7>(pol, tz_current);
-#pragma unroll 1
-            for (int k = 0; k <= n_iv; ++k) {
-                const bool last = k == n_iv;
-                const real tz = last ? tz_max : real(tzs[last ? 0 : k]);
-                if (!last && tz >= tz_max) continue;
-                const real p_val = poly_eval<7>(pol, tz);
-                bool direct = false, bracket = false;
-                if (!last && fabs(p_val) < 64.0 * fabs(poly_eval<5>(dderiv, tz)) * ROOT_TOLERANCE) direct = true;
-                else if (val_current * p_val < 0.0) bracket = true;
-                if (direct || bracket) {
-                    c_lo[n_cand] = bracket ? (double)tz_current : (double)tz;
-                    c_hi[n_cand] = tz;
-                    ++n_cand;
-                }
-                tz_current = tz;
-                val_current = p_val;
-            }
-        }
-    }
-    RK_PHASE_BARRIER();
-
-    // phase E: all candidates polished through the pool (the reference polishes candidate c only after c - 1 failed: the extra
-    // roots are never looked at), then validated in order
-    double c_root[7];
-    warp_pool_shrink<7>(pool, pol, c_lo, c_hi, active ? n_cand : 0, c_root);
-    RK_PHASE_BARRIER();
-#pragma unroll 1
-    for (int c = 0; c < 7; ++c) {
-        const bool mine = active && !found && c < n_cand;
-        if (!__syncthreads_or(mine)) break;
-        if (mine) found = vel_udud_root(s, L, h, c_root[c]);
-    }
-#else
     // phase D: extrema of the sextic by bracketing, candidates recorded; pass k == n_iv is the interval ending at tz_max
     double c_lo[7], c_hi[7];
     int n_cand = 0;
@@ -580,7 +481,6 @@ __device__ __forceinline__ bool s2_vel_udud_lockstep(const S2& s, const Lim& L, 
         RK_PHASE_BARRIER();
         if (mine) found = vel_udud_root(s, L, h, root);
     }
-#endif
     return found;
 }
 
