@@ -42,6 +42,7 @@ def load(flavour: str = "portable"):
     lib.rko_bench_calculate.argtypes = [C.POINTER(cabi.RkBatchDesc), C.POINTER(cabi.RkBatchIn), C.c_int32, vp, vp]
     lib.rko_bench_calculate.restype = C.c_double
     lib.rko_batch_validate.argtypes = [C.POINTER(cabi.RkBatchDesc), C.POINTER(cabi.RkBatchIn), C.c_int32, C.c_int32, vp]
+    lib.rko_batch_validate_messages.argtypes = [C.POINTER(cabi.RkBatchDesc), C.POINTER(cabi.RkBatchIn), C.c_int32, C.c_int32, vp, vp, C.c_int32]
     lib.rko_batch_read.argtypes = [vp, C.c_int32, vp]
     lib.rko_batch_read.restype = C.c_int32
     lib.rko_batch_position_extrema.argtypes = [vp, vp]
@@ -220,6 +221,17 @@ class OracleBatch:
         valid = np.zeros(self.n, dtype=np.uint8)
         self.lib.rko_batch_validate(C.byref(desc), C.byref(bin_), int(check_current), int(check_target), valid.ctypes.data)
         return valid
+
+    def validate_messages(self, fields: dict, *, check_current: bool, check_target: bool, delta_time=0.005, **kw):
+        """(valid[n], messages[n]): the oracle's text of the first failing check ("<check> (DoF d)"), "" when none."""
+        desc, keep = cabi.make_desc(self.n, self.dof, delta_time=delta_time, memory_space=cabi.RK_MEM_HOST, **kw)
+        bin_ = cabi.make_in(fields)
+        valid = np.zeros(self.n, dtype=np.uint8)
+        stride = 192
+        msgs = np.zeros((self.n, stride), dtype=np.uint8)
+        self.lib.rko_batch_validate_messages(C.byref(desc), C.byref(bin_), int(check_current), int(check_target), valid.ctypes.data,
+                                             msgs.ctypes.data, stride)
+        return valid, msgs.view(f"S{stride}")[:, 0]
 
     def read(self, field: int) -> np.ndarray:
         n, dof = self.n, self.dof

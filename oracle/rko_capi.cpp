@@ -164,6 +164,24 @@ void rko_batch_validate(const rk_batch_desc* d, const rk_batch_in* in, int32_t c
     }
 }
 
+// As rko_batch_validate, and the text of the first failing check per trajectory ("" when valid or when only the delta_time
+// rule fails) into msgs[i * msg_stride ...] (NUL-terminated, truncated to the stride).
+void rko_batch_validate_messages(const rk_batch_desc* d, const rk_batch_in* in, int32_t check_current, int32_t check_target, uint8_t* valid,
+                                 char* msgs, int32_t msg_stride) {
+    InputParameter ip(d->dof);
+    for (int64_t i = 0; i < d->n; ++i) {
+        fill_input(ip, d, in, i);
+        const std::string m = ip.validate(check_current != 0, check_target != 0);
+        bool ok = m.empty();
+        if (d->delta_time <= 0.0 && d->duration_discretization != DD_CONTINUOUS) ok = false;
+        valid[i] = ok ? 1 : 0;
+        char* o = msgs + i * (int64_t)msg_stride;
+        const size_t k = m.size() < (size_t)msg_stride - 1 ? m.size() : (size_t)msg_stride - 1;
+        std::memcpy(o, m.data(), k);
+        o[k] = 0;
+    }
+}
+
 int32_t rko_batch_read(void* pb, int32_t field, void* dst) {
     Batch* b = (Batch*)pb;
     const int64_t n = b->n;
