@@ -226,7 +226,8 @@ def run_b200(args):
 
     n = args.n
     dev = torch.device("cuda", local)
-    otg = BatchRuckig(DOF, DELTA_TIME, ThrowErrorHandler, device=local)
+    layout = cabi.RK_RESULT_COMPACT if args.layout == "compact" else cabi.RK_RESULT_FULL
+    otg = BatchRuckig(DOF, DELTA_TIME, ThrowErrorHandler, device=local, result_layout=layout)
     lib = otg._engine.lib
     stream = torch.cuda.ExternalStream(lib.rk_stream(otg.handle), device=dev)
 
@@ -320,7 +321,7 @@ def run_b200(args):
     if not args.no_extras and rank == 0:
         n64 = 65536
         f64k = {k: v[:, :n64].contiguous() for k, v in f.items()}
-        otg64 = BatchRuckig(DOF, DELTA_TIME, ThrowErrorHandler, device=local)
+        otg64 = BatchRuckig(DOF, DELTA_TIME, ThrowErrorHandler, device=local, result_layout=layout)
         st64 = torch.zeros(n64, dtype=torch.int32, device=dev)
         du64 = torch.zeros(n64, dtype=torch.float64, device=dev)
         run64 = lambda: otg64.calculate(f64k, n=n64, memory_space=cabi.RK_MEM_DEVICE, status=st64, duration=du64)
@@ -468,6 +469,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--n", type=int, default=8 << 20, help="trajectories per GPU")
     ap.add_argument("--cpu-sample", type=int, default=0, help="trajectories per step of the reference arm (0 = 131072 per thread)")
+    ap.add_argument("--layout", default="compact", choices=["compact", "full"],
+                    help="device-resident result: compact record (20 doubles per DoF, SURVEY.md 8b/8d) or the reference's full Profile (59)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the 64Ki-batch latency and the at_time rollout")

@@ -19,6 +19,8 @@ pub const RK_ERRORS_THROW: i32 = 0;
 pub const RK_ERRORS_IGNORE: i32 = 1;
 pub const RK_MEM_HOST: i32 = 0;
 pub const RK_MEM_DEVICE: i32 = 1;
+pub const RK_RESULT_FULL: i32 = 0;     // profile.rs:76-118 verbatim, 59 doubles per (DoF, trajectory)
+pub const RK_RESULT_COMPACT: i32 = 1;  // 20 doubles per (DoF, trajectory), expanded on the fly by every reader
 pub const RK_MAX_DOF: usize = 64;
 // fields of rk_trajectories_read (enum in the header, same order)
 pub const RK_FIELD_STATUS: i32 = 0;
@@ -87,6 +89,7 @@ extern "C" {
     pub fn rk_create(device: i32, out: *mut *mut rk_handle) -> rk_status;                      // Ruckig::new        ruckig.rs:110
     pub fn rk_destroy(h: *mut rk_handle) -> rk_status;
     pub fn rk_trajectories_create(h: *mut rk_handle, n: i64, dof: i32, out: *mut *mut rk_trajectories) -> rk_status; // Trajectory::new trajectory.rs:37
+    pub fn rk_trajectories_create_ex(h: *mut rk_handle, n: i64, dof: i32, result_layout: i32, out: *mut *mut rk_trajectories) -> rk_status; // RK_RESULT_FULL | RK_RESULT_COMPACT
     pub fn rk_trajectories_destroy(t: *mut rk_trajectories) -> rk_status;
     pub fn rk_calculate_batch(h: *mut rk_handle, desc: *const rk_batch_desc, input: *const rk_batch_in,
                               traj: *mut rk_trajectories, out: *const rk_batch_out) -> rk_status;                 // Ruckig::calculate  ruckig.rs:210

@@ -167,7 +167,15 @@ typedef struct rk_sample_out {
 /* ---- lifetime --------------------------------------------------------- */
 rk_status rk_create(int32_t device, rk_handle** out);                 /* Ruckig::new, ruckig.rs:110 */
 rk_status rk_destroy(rk_handle* h);
-rk_status rk_trajectories_create(rk_handle* h, int64_t n, int32_t dof, rk_trajectories** out); /* Trajectory::new, trajectory.rs:37-50 */
+rk_status rk_trajectories_create(rk_handle* h, int64_t n, int32_t dof, rk_trajectories** out); /* Trajectory::new, trajectory.rs:37-50; RK_RESULT_FULL */
+/* Layout of the device-resident result (SURVEY.md §8b "compact and/or full, selectable"):
+ *   RK_RESULT_FULL     the reference's Profile verbatim (profile.rs:76-118): 59 doubles per (DoF, trajectory), 3.3 KB per 7-DoF trajectory;
+ *   RK_RESULT_COMPACT  what the calculation decided — t[7], the control values, the brake pre-trajectory, the boundary states:
+ *                      20 doubles per (DoF, trajectory), 1.1 KB per 7-DoF trajectory. Every consumer (rk_at_time_batch, the
+ *                      query helpers, rk_trajectories_read of any field) integrates the remaining Profile fields on the fly
+ *                      with the operations the full layout was filled with: results are bit-identical in both layouts. */
+enum { RK_RESULT_FULL = 0, RK_RESULT_COMPACT = 1 };
+rk_status rk_trajectories_create_ex(rk_handle* h, int64_t n, int32_t dof, int32_t result_layout, rk_trajectories** out);
 rk_status rk_trajectories_destroy(rk_trajectories* t);
 
 /* ---- the hot path ------------------------------------------------------ */

@@ -17,6 +17,7 @@ RK_SYNC_TIME, RK_SYNC_TIME_IF_NECESSARY, RK_SYNC_PHASE, RK_SYNC_NONE = 0, 1, 2, 
 RK_CONTINUOUS, RK_DISCRETE = 0, 1
 RK_ERRORS_THROW, RK_ERRORS_IGNORE = 0, 1
 RK_MEM_HOST, RK_MEM_DEVICE = 0, 1
+RK_RESULT_FULL, RK_RESULT_COMPACT = 0, 1
 RK_MAX_DOF = 64
 
 (RK_FIELD_STATUS, RK_FIELD_DURATION, RK_FIELD_INDEPENDENT_MIN_DURATIONS, RK_FIELD_LIMITING_DOF, RK_FIELD_CODES,
@@ -124,7 +125,7 @@ _LIB = None
 LIB_PATH = os.environ.get("RK_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libruckig_b200.so")
 
 EXPORTS = (
-    "rk_create", "rk_destroy", "rk_trajectories_create", "rk_trajectories_destroy", "rk_calculate_batch",
+    "rk_create", "rk_destroy", "rk_trajectories_create", "rk_trajectories_create_ex", "rk_trajectories_destroy", "rk_calculate_batch",
     "rk_validate_batch", "rk_at_time_batch", "rk_trajectories_read", "rk_sync", "rk_stream", "rk_kernel_launches",
     "rk_status_string", "rk_last_error", "rk_version", "rk_measure_fp64_peak", "rk_selftest_division",
     "rk_position_extrema_batch", "rk_first_time_at_position_batch",
@@ -145,6 +146,7 @@ def load():
     lib.rk_create.argtypes = [C.c_int32, C.POINTER(vp)]
     lib.rk_destroy.argtypes = [vp]
     lib.rk_trajectories_create.argtypes = [vp, C.c_int64, C.c_int32, C.POINTER(vp)]
+    lib.rk_trajectories_create_ex.argtypes = [vp, C.c_int64, C.c_int32, C.c_int32, C.POINTER(vp)]
     lib.rk_trajectories_destroy.argtypes = [vp]
     lib.rk_calculate_batch.argtypes = [vp, C.POINTER(RkBatchDesc), C.POINTER(RkBatchIn), vp, C.POINTER(RkBatchOut)]
     lib.rk_validate_batch.argtypes = [vp, C.POINTER(RkBatchDesc), C.POINTER(RkBatchIn), C.c_int32, C.c_int32, vp, vp]
@@ -171,7 +173,7 @@ def load():
     lib.rk_rollout_trajectories.argtypes = [vp]
     lib.rk_rollout_trajectories.restype = vp
     lib.rk_update_batch.argtypes = [vp, C.POINTER(RkBatchDesc), C.POINTER(RkBatchIn), vp, C.POINTER(RkUpdateOut), C.POINTER(C.c_int64)]
-    for f in ("rk_create", "rk_destroy", "rk_trajectories_create", "rk_trajectories_destroy", "rk_calculate_batch",
+    for f in ("rk_create", "rk_destroy", "rk_trajectories_create", "rk_trajectories_create_ex", "rk_trajectories_destroy", "rk_calculate_batch",
               "rk_validate_batch", "rk_at_time_batch", "rk_trajectories_read", "rk_sync", "rk_rollout_create", "rk_rollout_destroy",
               "rk_rollout_reset", "rk_update_batch", "rk_position_extrema_batch", "rk_first_time_at_position_batch"):
         getattr(lib, f).restype = C.c_int32

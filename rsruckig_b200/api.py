@@ -240,6 +240,19 @@ class Trajectory:
         self._engine = None  # set by Ruckig.calculate
         self._dev = None
 
+    def close(self):
+        """Release the device-side trajectory (also done when the object is collected)."""
+        dev, eng = self._dev, self._engine
+        self._dev = None
+        if dev is not None and eng is not None:
+            try:
+                eng.free_trajectories(dev)
+            except Exception:  # interpreter shutdown: the library may be gone already
+                pass
+
+    def __del__(self):
+        self.close()
+
     def get_duration(self) -> float:  # trajectory.rs:197-199
         return self.duration
 
@@ -310,9 +323,9 @@ class _Engine:
         cabi.check(self.lib.rk_create(device, C.byref(self.h)))
         self.device = device
 
-    def new_trajectories(self, n: int, dof: int) -> C.c_void_p:
+    def new_trajectories(self, n: int, dof: int, layout: int = cabi.RK_RESULT_FULL) -> C.c_void_p:
         t = C.c_void_p()
-        cabi.check(self.lib.rk_trajectories_create(self.h, n, dof, C.byref(t)))
+        cabi.check(self.lib.rk_trajectories_create_ex(self.h, n, dof, int(layout), C.byref(t)))
         return t
 
     def free_trajectories(self, t):
@@ -420,13 +433,35 @@ class BatchRuckig:
     Arrays are SoA `[dof][n]` float64 (numpy = host buffers, torch CUDA tensors = device buffers).
     """
 
-    def __init__(self, dofs: int, delta_time: float, error_handler=ThrowErrorHandler, device: int = 0):
+    def __init__(self, dofs: int, delta_time: float, error_handler=ThrowErrorHandler, device: int = 0,
+                 result_layout: int | None = None):
+        """result_layout: cabi.RK_RESULT_FULL (the reference's Profile verbatim, 59 doubles per DoF) or
+        cabi.RK_RESULT_COMPACT (20 doubles per DoF, expanded on the fly by every reader; same results bit for bit).
+        Default: RK_B200_RESULT_LAYOUT from the environment ("compact" / "full"), else full."""
         self.degrees_of_freedom = int(dofs)
         self.delta_time = float(delta_time)
         self.error_handler = error_handler
         self._engine = _Engine.get(device)
         self._traj = None
         self._n = 0
+        if result_layout is None:
+            import os
+            result_layout = cabi.RK_RESULT_COMPACT if os.environ.get("RK_B200_RESULT_LAYOUT", "full") == "compact" else cabi.RK_RESULT_FULL
+        self.result_layout = int(result_layout)
+
+    def close(self):
+        """Release the device-side trajectories (also done when the object is collected)."""
+        traj = self._traj
+        self._traj = None
+        self._n = 0
+        if traj is not None:
+            try:
+                self._engine.free_trajectories(traj)
+            except Exception:  # interpreter shutdown: the library may be gone already
+                pass
+
+    def __del__(self):
+        self.close()
 
     @property
     def handle(self):
@@ -436,7 +471,7 @@ class BatchRuckig:
         if self._traj is None or self._n != n:
             if self._traj is not None:
                 self._engine.free_trajectories(self._traj)
-            self._traj = self._engine.new_trajectories(n, self.degrees_of_freedom)
+            self._traj = self._engine.new_trajectories(n, self.degrees_of_freedom, self.result_layout)
             self._n = n
 
     def calculate(self, fields: dict, *, n: int, memory_space: int, control_interface=ControlInterface.Position,

@@ -45,6 +45,9 @@ __global__ void __launch_bounds__(128) k_validate(const Params P, uint8_t* valid
 struct SampleParams {
     int64_t n;
     int32_t dof, steps, k_chunk;
+    int32_t rewind;  // sample times do not grow (delta_time < 0 or NaN): every sample runs the general search
+    int32_t n_starts;                  // > 0: start[y] = the accumulated time before the first sample of slice y
+    double start[16];
     double time_start, delta_time;
     const double* prof;
     const double* duration;
@@ -66,92 +69,135 @@ struct SampleParams {
 #ifndef RK_AT_STORE
 #define RK_AT_STORE __stcs
 #endif
-template <bool PVA_ONLY>  // true: position, velocity and acceleration are all requested, jerk and section are not
-__global__ void __launch_bounds__(RK_AT_BLOCK) k_at_time(const SampleParams S) {
+// Reader side of the two trajectory layouts: the full Profile is read in place (row stride dof * n); a compact record
+// (RK_RESULT_COMPACT, rk_store.cuh) is expanded once per thread into a 59-double local array (stride 1) by the same
+// operations that fill the full layout, so every reader below sees bit-identical values either way.
+__device__ __forceinline__ void load_compact_profile(const double* prof, int64_t gi, int64_t total, double* local) {
+    double r[COMPACT_SLOTS];
+#pragma unroll
+    for (int s = 0; s < COMPACT_SLOTS; ++s) r[s] = prof[(int64_t)s * total + gi];
+    expand_compact(r, ProfileSink{local, 1, 0});
+}
+
+// PVA_ONLY: position, velocity and acceleration are all requested, jerk and section are not. COMPACT: trajectory layout.
+// t * j / 6 of util.rs:27-33 as the correctly rounded IEEE quotient: y = RN(1/6), q0 = a * y, r = fma(-6, q0, a),
+// q = fma(y, r, q0) is a / 6 correctly rounded whenever no intermediate leaves the normal range (Markstein; the same tail nvcc
+// emits after refining its own reciprocal, with the reciprocal a compile-time constant instead of MUFU.RCP64H + 5 FMAs per
+// sample); +-0, +-inf and NaN come out of a * y already; tiny / huge numerators take the compiler's division.
+__device__ __noinline__ double div6_rare(double a) { return a / 6.0; }
+__device__ __forceinline__ double div6(double a) {
+    const double y = __longlong_as_double(0x3FC5555555555555LL);
+    const uint32_t ea = hi_word(a) & 0x7ff00000u;
+    const double q0 = a * y;
+    const double r = __fma_rn(-6.0, q0, a);
+    const double q = __fma_rn(y, r, q0);
+    const bool moderate = (ea - 0x20b00000u) <= 0x3e800000u;  // 2^-500 <= |a| <= 2^500
+    const bool trivial = (ea == 0x7ff00000u) | (a == 0.0);
+    double res = moderate ? q : q0;
+    if (__builtin_expect(!(moderate | trivial), 0)) res = div6_rare(a);  // kept out of line: if-converted, the compiler's division runs per sample
+    return res;
+}
+
+#define RK_AT_MAX_STARTS 16
+// PVA_ONLY: position, velocity and acceleration are all requested, jerk and section are not (the RL rollout). COMPACT:
+// trajectory layout (the one-off expansion of a compact record would otherwise set the register count: 117 instead of 68,
+// half the occupancy — hence the second launch bound).
+//
+// Per sample the fast path is: time += dt; td = time - A; t0 = td - B; three compares that restate the reference's own
+// conditions for staying in the current segment; integrate; three streaming stores. (A, B) and the three limits are
+// per-segment registers: trajectory end (A = brake + t_sum[6], B = 0, no limit), own end (A = brake duration, B = t_sum[6],
+// limit `time < duration`), phase `index` (A = brake duration, B = t_sum[index - 1], limits duration, t_sum[6], t_sum[index]).
+// x - 0.0 == x for every x, so an absent offset is a zero. ncu on the previous form of this loop: 128 warp instructions
+// per sample, 75 % of the issue slots — it was issue-bound at 5.1 TB/s; this form needs about a third of that.
+template <bool PVA_ONLY, bool COMPACT>
+__global__ void __launch_bounds__(RK_AT_BLOCK, COMPACT ? 7 : 0) k_at_time(const SampleParams S) {
     const int64_t total = (int64_t)S.dof * S.n;
     const int64_t gi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gi >= total) return;
     const int d = (int)(gi / S.n);
     const int64_t i = gi - (int64_t)d * S.n;
-    const double* q = S.prof + gi;
-    const int64_t st = total;
+    double local[COMPACT ? PROFILE_SLOTS : 1];
+    if (COMPACT) load_compact_profile(S.prof, gi, total, local);
+    const double* q = COMPACT ? local : S.prof + gi;
+    const int64_t st = COMPACT ? 1 : total;
 
     const double duration = S.duration[i];
     const double ts6 = q[(int64_t)(S_TSUM + 6) * st];
     const double p7 = q[(int64_t)(S_P + 7) * st], v7 = q[(int64_t)(S_V + 7) * st], a7 = q[(int64_t)(S_A + 7) * st];
     const double bdur = q[(int64_t)S_BRAKE_DUR * st];
     const double bt0 = q[(int64_t)S_BRAKE_T * st];
-    double bsub = (bdur > 0.0) ? bdur : 0.0;  // x - 0.0 == x: the reference subtracts bdur only if it is positive
+    const double bsub = (bdur > 0.0) ? bdur : 0.0;  // the reference subtracts bdur only if it is positive
     const double end_off = bdur + ts6;
-    const Den six(6.0);                       // integrate() divides t * j by 6: one refined reciprocal for all samples
+    const double ts0 = q[(int64_t)(S_TSUM + 0) * st];
+    const double INF = RK_INF;
 
-    // profile phase `index` ("first i with t_sum[i] > t", default 6, trajectory.rs:134-140; only grows)
+    // profile phase `index` ("first i with t_sum[i] > t", default 6, trajectory.rs:134-140; only grows while time grows)
     int index = 0;
-    double t_hi = q[(int64_t)(S_TSUM + 0) * st];  // t_sum[index]
-    double lsub = 0.0;                            // t_sum[index - 1] if index > 0 (else nothing is subtracted: 0.0)
+    double t_hi = ts0;   // t_sum[index]
+    double lsub = 0.0;   // t_sum[index - 1] if index > 0 (else nothing is subtracted: 0.0)
 
-    enum { SEG_SEARCH = 0, SEG_PHASE = 1, SEG_OWN_END = 2, SEG_END = 3 };
-    int seg = SEG_SEARCH;
-    double sp = 0.0, sv = 0.0, sa = 0.0, sj = 0.0;  // state the current segment integrates from
+    // current segment: offsets, limits (h_lim = -inf: no segment, the next sample runs the general search), start state
+    double A = 0.0, B = 0.0, d_lim = INF, t_lim = INF, h_lim = -INF;
+    double sp = 0.0, sv = 0.0, sa = 0.0, sj = 0.0;
     int section = 0;
 
     // blockIdx.y picks a slice of the K sample times; the time of sample k is k + 1 repeated additions of delta_time
-    // (ruckig.rs:293), so a slice first replays the additions of the samples before it (no memory traffic).
+    // (ruckig.rs:293). The host has done the additions up to each slice's first sample (same IEEE additions, same result);
+    // only with more than RK_AT_MAX_STARTS slices (tiny batches) a slice replays them itself.
     const int k_begin = blockIdx.y * S.k_chunk;
     const int k_end = (k_begin + S.k_chunk < S.steps) ? (k_begin + S.k_chunk) : S.steps;
     double time = S.time_start;
+    if (S.n_starts > 0) {
+        time = S.start[blockIdx.y];
+    } else {
 #pragma unroll 1
-    for (int k = 0; k < k_begin; ++k) time += S.delta_time;
-    int64_t stride = total * (int64_t)sizeof(double);
-    asm volatile("" : "+l"(stride), "+d"(bsub));  // keep both in registers: the compiler otherwise rebuilds them per sample
-    const int64_t o0 = (int64_t)k_begin * total + gi;
+        for (int k = 0; k < k_begin; ++k) time += S.delta_time;
+    }
+    const int64_t stride = total * (int64_t)sizeof(double);
+    const int64_t o0 = (int64_t)(k_begin - 1) * total + gi;  // pointers are advanced before each store
     char* out_p = S.pos ? (char*)(S.pos + o0) : nullptr;
     char* out_v = S.vel ? (char*)(S.vel + o0) : nullptr;
     char* out_a = S.acc ? (char*)(S.acc + o0) : nullptr;
     char* out_j = S.jerk ? (char*)(S.jerk + o0) : nullptr;
-    int32_t* out_s = (S.section && d == 0) ? S.section + (int64_t)k_begin * S.n + i : nullptr;
+    int32_t* out_s = (S.section && d == 0) ? S.section + (int64_t)(k_begin - 1) * S.n + i : nullptr;
+    const double dt = S.delta_time;
 #pragma unroll 1
     for (int k = k_begin; k < k_end; ++k) {
-        time += S.delta_time;
-        double t0 = 0.0;
-        bool stay = false;
-        if (seg == SEG_END) {  // time >= duration holds from here on (:60-83)
-            t0 = time - end_off;
-            stay = true;
-        } else if (seg != SEG_SEARCH && !(time >= duration)) {
-            const double td = time - bsub;  // the brake pre-trajectory is behind us (td >= bdur held and time grows)
-            if (seg == SEG_OWN_END) { t0 = td - ts6; stay = true; }               // td >= ts6 held and td grows (:122-132)
-            else if (!(td >= ts6) && t_hi > td) { t0 = td - lsub; stay = true; }   // still inside phase `index`
-        }
+        time += dt;
+        if (!PVA_ONLY && S.rewind) { h_lim = -INF; index = 0; t_hi = ts0; lsub = 0.0; }  // Trajectory::at_time is order-independent
+        double td = time - A;
+        double t0 = td - B;
+        const bool stay = !(time >= d_lim) & !(td >= t_lim) & (h_lim > td);
         if (!stay) {
-            if (time >= duration) {  // :60-83
+            if (time >= duration) {  // :60-83; stays true while time grows
                 section = 1;
-                seg = SEG_END;
+                A = end_off; B = 0.0; d_lim = INF; t_lim = INF; h_lim = INF;
                 t0 = time - end_off;
                 sp = p7; sv = v7; sa = a7; sj = 0.0;
             } else {
                 // cumulative_times[0] == duration > time, so the section index is 0 and t_diff == time (:85-99, Q13)
                 section = 0;
-                double td = time;
+                td = time;
                 bool set = false;
                 if (bdur > 0.0) {
-                    if (td < bdur) {  // brake pre-trajectory (:103-121); stays in SEG_SEARCH, it lasts a few samples at most
+                    if (td < bdur) {  // brake pre-trajectory (:103-121): no segment, it lasts a few samples at most
                         const int bi = (td < bt0) ? 0 : 1;
                         if (bi > 0) td -= bt0;
                         t0 = td;
                         sp = q[(int64_t)(S_BRAKE_P + bi) * st]; sv = q[(int64_t)(S_BRAKE_V + bi) * st];
                         sa = q[(int64_t)(S_BRAKE_A + bi) * st]; sj = q[(int64_t)(S_BRAKE_J + bi) * st];
-                        seg = SEG_SEARCH;
+                        h_lim = -INF;
                         set = true;
                     } else {
                         td -= bdur;
                     }
                 }
                 if (!set) {
-                    if (td >= ts6) {  // past this DoF's own end (:122-132)
+                    A = bsub; d_lim = duration;
+                    if (td >= ts6) {  // past this DoF's own end (:122-132); td >= ts6 keeps holding while time grows
                         t0 = td - ts6;
                         sp = p7; sv = v7; sa = a7; sj = 0.0;
-                        seg = SEG_OWN_END;
+                        B = ts6; t_lim = INF; h_lim = INF;
                     } else {
                         while (index < 6 && !(t_hi > td)) {
                             ++index;
@@ -161,29 +207,28 @@ __global__ void __launch_bounds__(RK_AT_BLOCK) k_at_time(const SampleParams S) {
                         t0 = td - lsub;
                         sp = q[(int64_t)(S_P + index) * st]; sv = q[(int64_t)(S_V + index) * st];
                         sa = q[(int64_t)(S_A + index) * st]; sj = q[(int64_t)(S_J + index) * st];
+                        B = lsub; t_lim = ts6;
                         // index == 6 is the default of the search, not a test of t_sum[6] > td: stay only on the reference's terms
-                        seg = (t_hi > td) ? SEG_PHASE : SEG_SEARCH;
+                        h_lim = (t_hi > td) ? t_hi : -INF;
                     }
                 }
             }
         }
-        // util.rs:27-33; t * j / 6 through the shared reciprocal (IEEE-exact, rk_math.cuh), +-0 numerators pass through
+        // util.rs:27-33
         const double tj = t0 * sj;
-        const bool tj_zero = tj == 0.0;
-        const double sixth = ddiv(tj_zero ? 1.0 : tj, six);
-        const double p = sp + t0 * (sv + t0 * (sa / 2.0 + (tj_zero ? tj : sixth)));
+        const double p = sp + t0 * (sv + t0 * (sa / 2.0 + div6(tj)));
         const double v = sv + t0 * (sa + tj / 2.0);
         const double a = sa + tj;
         if (PVA_ONLY) {
-            RK_AT_STORE((double*)out_p, p); out_p += stride;
-            RK_AT_STORE((double*)out_v, v); out_v += stride;
-            RK_AT_STORE((double*)out_a, a); out_a += stride;
+            out_p += stride; RK_AT_STORE((double*)out_p, p);
+            out_v += stride; RK_AT_STORE((double*)out_v, v);
+            out_a += stride; RK_AT_STORE((double*)out_a, a);
         } else {
-            if (out_p) { RK_AT_STORE((double*)out_p, p); out_p += stride; }
-            if (out_v) { RK_AT_STORE((double*)out_v, v); out_v += stride; }
-            if (out_a) { RK_AT_STORE((double*)out_a, a); out_a += stride; }
-            if (out_j) { RK_AT_STORE((double*)out_j, sj); out_j += stride; }
-            if (out_s) { *out_s = section; out_s += S.n; }
+            if (out_p) { out_p += stride; RK_AT_STORE((double*)out_p, p); }
+            if (out_v) { out_v += stride; RK_AT_STORE((double*)out_v, v); }
+            if (out_a) { out_a += stride; RK_AT_STORE((double*)out_a, a); }
+            if (out_j) { out_j += stride; RK_AT_STORE((double*)out_j, sj); }
+            if (out_s) { out_s += S.n; *out_s = section; }
         }
     }
 }
@@ -254,7 +299,7 @@ __global__ void __launch_bounds__(256) k_upd_gather(const UpdateParams U, int64_
 
 struct ScatterParams {
     int64_t n, m;
-    int32_t dof, throw_mode;
+    int32_t dof, throw_mode, slots;
     const uint32_t* idx;
     const double* s_prof; const uint32_t* s_codes; const int32_t* s_status; const double* s_duration; const double* s_imd;
     const int32_t* s_limiting; const int32_t* s_detail;
@@ -271,7 +316,7 @@ __global__ void __launch_bounds__(256) k_upd_scatter(const ScatterParams C, cons
     const int64_t g = (int64_t)d * C.n + i;
     const int64_t s_stride = (int64_t)C.dof * C.m, stride = (int64_t)C.dof * C.n;
 #pragma unroll 1
-    for (int r = 0; r < PROFILE_SLOTS; ++r) C.prof[(int64_t)r * stride + g] = C.s_prof[(int64_t)r * s_stride + t];
+    for (int r = 0; r < C.slots; ++r) C.prof[(int64_t)r * stride + g] = C.s_prof[(int64_t)r * s_stride + t];
     C.codes[g] = C.s_codes[t];
     C.imd[g] = C.s_imd[t];
     const int st = C.s_status[j];
@@ -299,7 +344,7 @@ __global__ void __launch_bounds__(256) k_upd_scatter(const ScatterParams C, cons
 
 struct StepParams {
     int64_t n;
-    int32_t dof, throw_mode, reset_time;
+    int32_t dof, throw_mode, reset_time, compact;
     double delta_time;
     const double* prof; const double* duration; const int32_t* status;
     const uint8_t* dirty;
@@ -377,7 +422,13 @@ __global__ void __launch_bounds__(256) k_upd_step(const StepParams T) {
     time += T.delta_time;
     const double duration = T.duration[i];
     double p, v, a, j;
-    sample_once(T.prof + gi, total, duration, time, p, v, a, j);
+    if (T.compact) {
+        double local[PROFILE_SLOTS];
+        load_compact_profile(T.prof, gi, total, local);
+        sample_once(local, 1, duration, time, p, v, a, j);
+    } else {
+        sample_once(T.prof + gi, total, duration, time, p, v, a, j);
+    }
     if (T.new_p) T.new_p[gi] = p;
     if (T.new_v) T.new_v[gi] = v;
     if (T.new_a) T.new_a[gi] = a;
@@ -423,7 +474,7 @@ __device__ __forceinline__ void check_step_for_position_extremum(double t_sum, d
 
 struct QueryParams {
     int64_t n;
-    int32_t dof;
+    int32_t dof, compact;
     const double* prof;
     double *e_min, *e_max, *e_tmin, *e_tmax;   // position extrema, [dof][n], nullable
     const double* position; double* time;      // first time at position, [dof][n]
@@ -434,8 +485,10 @@ __global__ void __launch_bounds__(256) k_position_extrema(const QueryParams Q) {
     const int64_t total = (int64_t)Q.dof * Q.n;
     const int64_t gi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gi >= total) return;
-    const double* q = Q.prof + gi;
-    const int64_t st = total;
+    double local[PROFILE_SLOTS];
+    if (Q.compact) load_compact_profile(Q.prof, gi, total, local);
+    const double* q = Q.compact ? local : Q.prof + gi;
+    const int64_t st = Q.compact ? 1 : total;
     double e_min = RK_INF, e_max = -RK_INF, e_tmin = 0.0, e_tmax = 0.0;
     const double bdur = q[(int64_t)S_BRAKE_DUR * st];
     const double bt0 = q[(int64_t)S_BRAKE_T * st], bt1 = q[(int64_t)(S_BRAKE_T + 1) * st];
@@ -468,8 +521,10 @@ __global__ void __launch_bounds__(256) k_first_time_at_position(const QueryParam
     const int64_t total = (int64_t)Q.dof * Q.n;
     const int64_t gi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gi >= total) return;
-    const double* q = Q.prof + gi;
-    const int64_t st = total;
+    double local[PROFILE_SLOTS];
+    if (Q.compact) load_compact_profile(Q.prof, gi, total, local);
+    const double* q = Q.compact ? local : Q.prof + gi;
+    const int64_t st = Q.compact ? 1 : total;
     const double pt = Q.position[gi];
     double result = __longlong_as_double(0x7ff8000000000000LL);
     bool found = false;
@@ -495,6 +550,16 @@ __global__ void __launch_bounds__(256) k_first_time_at_position(const QueryParam
     }
     if (!found && fabs(q[(int64_t)S_PF * st] - pt) < 1e-9) result = 0.0 + q[(int64_t)(S_TSUM + 6) * st];
     Q.time[gi] = result;
+}
+
+// rk_trajectories_read on a compact trajectory set: slots [first, first + count) of the full layout, expanded on the fly.
+__global__ void __launch_bounds__(256) k_read_expanded(const double* prof, int64_t total, int first, int count, double* dst) {
+    const int64_t gi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gi >= total) return;
+    double local[PROFILE_SLOTS];
+    load_compact_profile(prof, gi, total, local);
+#pragma unroll 1
+    for (int s = 0; s < count; ++s) dst[(int64_t)s * total + gi] = local[first + s];
 }
 
 // ------------------------------------------------------------------------------------------------ FP64 peak probe
@@ -646,6 +711,8 @@ struct rk_trajectories {
     rk_handle* h = nullptr;
     int64_t n = 0;
     int32_t dof = 0;
+    int32_t layout = RK_RESULT_FULL;  // RK_RESULT_FULL: 59 profile slots per (DoF, trajectory); RK_RESULT_COMPACT: 20 (rk_store.cuh)
+    int slots() const { return layout == RK_RESULT_COMPACT ? (int)rk::COMPACT_SLOTS : (int)rk::PROFILE_SLOTS; }
     double* prof = nullptr;
     uint32_t* codes = nullptr;
     int32_t* status = nullptr;
@@ -833,24 +900,35 @@ rk_status rk_destroy(rk_handle* h) {
     return RK_OK;
 }
 
-rk_status rk_trajectories_create(rk_handle* h, int64_t n, int32_t dof, rk_trajectories** out) {
+rk_status rk_trajectories_create_ex(rk_handle* h, int64_t n, int32_t dof, int32_t result_layout, rk_trajectories** out) {
     if (!h || !out || n < 0 || dof < 1 || dof > RK_MAX_DOF) return fail(RK_ERR_INVALID_ARGUMENT, "bad arguments to rk_trajectories_create");
+    if (result_layout != RK_RESULT_FULL && result_layout != RK_RESULT_COMPACT) return fail(RK_ERR_INVALID_ARGUMENT, "unknown result layout");
     RK_CUDA(cudaSetDevice(h->device));
     rk_trajectories* t = new rk_trajectories();
-    t->h = h; t->n = n; t->dof = dof;
+    t->h = h; t->n = n; t->dof = dof; t->layout = result_layout;
     const size_t items = (size_t)(n > 0 ? n : 1) * dof, nn = (size_t)(n > 0 ? n : 1);
-    RK_CUDA(cudaMalloc(&t->prof, sizeof(double) * rk::PROFILE_SLOTS * items));
-    RK_CUDA(cudaMalloc(&t->codes, sizeof(uint32_t) * items));
-    RK_CUDA(cudaMalloc(&t->imd, sizeof(double) * items));
-    RK_CUDA(cudaMalloc(&t->status, sizeof(int32_t) * nn));
-    RK_CUDA(cudaMalloc(&t->duration, sizeof(double) * nn));
-    RK_CUDA(cudaMalloc(&t->limiting, sizeof(int32_t) * nn));
-    RK_CUDA(cudaMalloc(&t->detail, sizeof(int32_t) * nn));
-    RK_CUDA(cudaMemsetAsync(t->prof, 0, sizeof(double) * rk::PROFILE_SLOTS * items, h->stream));
-    RK_CUDA(cudaMemsetAsync(t->duration, 0, sizeof(double) * nn, h->stream));
-    RK_CUDA(cudaMemsetAsync(t->status, 0, sizeof(int32_t) * nn, h->stream));
+    const size_t prof_bytes = sizeof(double) * (size_t)t->slots() * items;
+    cudaError_t e = cudaMalloc(&t->prof, prof_bytes);
+    if (e == cudaSuccess) e = cudaMalloc(&t->codes, sizeof(uint32_t) * items);
+    if (e == cudaSuccess) e = cudaMalloc(&t->imd, sizeof(double) * items);
+    if (e == cudaSuccess) e = cudaMalloc(&t->status, sizeof(int32_t) * nn);
+    if (e == cudaSuccess) e = cudaMalloc(&t->duration, sizeof(double) * nn);
+    if (e == cudaSuccess) e = cudaMalloc(&t->limiting, sizeof(int32_t) * nn);
+    if (e == cudaSuccess) e = cudaMalloc(&t->detail, sizeof(int32_t) * nn);
+    if (e == cudaSuccess) e = cudaMemsetAsync(t->prof, 0, prof_bytes, h->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(t->duration, 0, sizeof(double) * nn, h->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(t->status, 0, sizeof(int32_t) * nn, h->stream);
+    if (e != cudaSuccess) {  // nothing of a partially built object is leaked (the likely cause is a failed allocation)
+        rk_trajectories_destroy(t);
+        cudaGetLastError();
+        return fail(e == cudaErrorMemoryAllocation ? RK_ERR_OUT_OF_MEMORY : RK_ERR_CUDA, std::string("rk_trajectories_create: ") + cudaGetErrorString(e));
+    }
     *out = t;
     return RK_OK;
+}
+
+rk_status rk_trajectories_create(rk_handle* h, int64_t n, int32_t dof, rk_trajectories** out) {
+    return rk_trajectories_create_ex(h, n, dof, RK_RESULT_FULL, out);
 }
 
 rk_status rk_trajectories_destroy(rk_trajectories* t) {
@@ -873,6 +951,7 @@ rk_status rk_calculate_batch(rk_handle* h, const rk_batch_desc* desc, const rk_b
     const bool host = desc->memory_space == RK_MEM_HOST;
     P.prof = traj->prof; P.codes = traj->codes; P.status = traj->status; P.duration = traj->duration; P.imd = traj->imd;
     P.limiting = traj->limiting; P.detail = traj->detail;
+    P.compact = traj->layout == RK_RESULT_COMPACT;
 
     // chunks of about CHUNK_ITEMS (DoF, trajectory) items, equally sized (8 Mi x 7 DoF = exactly 14 x 4 Mi items must not
     // become 14 chunks and a 15th of four trajectories)
@@ -1106,6 +1185,7 @@ rk_status rk_at_time_batch(rk_handle* h, const rk_trajectories* traj, const rk_s
     rk::SampleParams S;
     S.n = traj->n; S.dof = traj->dof; S.steps = desc->steps;
     S.time_start = desc->time_start; S.delta_time = desc->delta_time;
+    S.rewind = !(desc->delta_time >= 0.0);
     S.prof = traj->prof; S.duration = traj->duration;
     const bool host = desc->memory_space == RK_MEM_HOST;
     const size_t per = sizeof(double) * (size_t)desc->steps * traj->dof * traj->n;
@@ -1142,12 +1222,32 @@ rk_status rk_at_time_batch(rk_handle* h, const rk_trajectories* traj, const rk_s
         }
         slices = best_s;
     }
+    {   // tuning aid: RK_B200_AT_SLICES overrides the heuristic
+        static const int forced = [] { const char* e = std::getenv("RK_B200_AT_SLICES"); return e ? std::atoi(e) : 0; }();
+        if (forced > 0) slices = forced;
+    }
     if (slices > (desc->steps + 31) / 32) slices = (desc->steps + 31) / 32;
+    if (slices > 65535) slices = 65535;  // gridDim.y
     if (slices < 1) slices = 1;
     S.k_chunk = (int32_t)((desc->steps + slices - 1) / slices);
     const dim3 grid((unsigned)((total + RK_AT_BLOCK - 1) / RK_AT_BLOCK), (unsigned)((desc->steps + S.k_chunk - 1) / S.k_chunk), 1);
-    if (S.pos && S.vel && S.acc && !S.jerk && !S.section) rk::k_at_time<true><<<grid, RK_AT_BLOCK, 0, h->stream>>>(S);
-    else rk::k_at_time<false><<<grid, RK_AT_BLOCK, 0, h->stream>>>(S);
+    S.n_starts = 0;
+    if (grid.y <= RK_AT_MAX_STARTS) {  // the repeated additions of ruckig.rs:293 up to each slice's first sample, done once here
+        S.n_starts = (int32_t)grid.y;
+        volatile double t = desc->time_start;  // volatile: plain IEEE double additions, one at a time
+        for (int k = 0, y = 0; y < (int)grid.y; ++k) {
+            if (k == y * S.k_chunk) S.start[y++] = t;
+            t = t + desc->delta_time;
+        }
+    }
+    const bool pva_only = S.pos && S.vel && S.acc && !S.jerk && !S.section && !S.rewind;
+    if (traj->layout == RK_RESULT_COMPACT) {
+        if (pva_only) rk::k_at_time<true, true><<<grid, RK_AT_BLOCK, 0, h->stream>>>(S);
+        else rk::k_at_time<false, true><<<grid, RK_AT_BLOCK, 0, h->stream>>>(S);
+    } else {
+        if (pva_only) rk::k_at_time<true, false><<<grid, RK_AT_BLOCK, 0, h->stream>>>(S);
+        else rk::k_at_time<false, false><<<grid, RK_AT_BLOCK, 0, h->stream>>>(S);
+    }
     h->launches += 1;
     RK_CUDA(cudaGetLastError());
     if (host) {
@@ -1181,15 +1281,12 @@ struct rk_rollout {
     bool last_present[13] = {};
 };
 
-rk_status rk_rollout_create(rk_handle* h, int64_t n, int32_t dof, rk_rollout** out) {
-    if (!h || !out || n < 1 || dof < 1 || dof > RK_MAX_DOF) return fail(RK_ERR_INVALID_ARGUMENT, "bad arguments to rk_rollout_create");
-    RK_CUDA(cudaSetDevice(h->device));
-    rk_rollout* r = new rk_rollout();
-    r->h = h; r->n = n; r->dof = dof;
-    rk_status st = rk_trajectories_create(h, n, dof, &r->traj);
-    if (st == RK_OK) st = rk_trajectories_create(h, n, dof, &r->tmp);
+static rk_status rollout_alloc(rk_handle* h, rk_rollout* r) {
+    const int64_t n = r->n;
+    const size_t items = (size_t)n * r->dof;
+    rk_status st = rk_trajectories_create(h, n, r->dof, &r->traj);
+    if (st == RK_OK) st = rk_trajectories_create(h, n, r->dof, &r->tmp);
     if (st != RK_OK) return st;
-    const size_t items = (size_t)n * dof;
     for (int f = 0; f < 11; ++f) {
         RK_CUDA(cudaMalloc(&r->last[f], sizeof(double) * items));
         RK_CUDA(cudaMalloc(&r->gin[f], sizeof(double) * items));
@@ -1201,8 +1298,24 @@ rk_status rk_rollout_create(rk_handle* h, int64_t n, int32_t dof, rk_rollout** o
     RK_CUDA(cudaMalloc(&r->initialized, n)); RK_CUDA(cudaMalloc(&r->dirty, n));
     RK_CUDA(cudaMalloc(&r->idx, sizeof(uint32_t) * n)); RK_CUDA(cudaMalloc(&r->count, sizeof(uint32_t)));
     RK_CUDA(cudaMallocHost(&r->count_host, sizeof(uint32_t)));
-    *out = r;
     return rk_rollout_reset(h, r);
+}
+
+rk_status rk_rollout_create(rk_handle* h, int64_t n, int32_t dof, rk_rollout** out) {
+    if (!h || !out || n < 1 || dof < 1 || dof > RK_MAX_DOF) return fail(RK_ERR_INVALID_ARGUMENT, "bad arguments to rk_rollout_create");
+    if (n > (int64_t)0xFFFFFFFFll) return fail(RK_ERR_INVALID_ARGUMENT, "rk_rollout_create: n exceeds 2^32 - 1 (environment indices are 32-bit)");
+    RK_CUDA(cudaSetDevice(h->device));
+    rk_rollout* r = new rk_rollout();
+    r->h = h; r->n = n; r->dof = dof;
+    const rk_status st = rollout_alloc(h, r);
+    if (st != RK_OK) {  // nothing of a partially built rollout is leaked
+        const std::string why = g_last_error;
+        rk_rollout_destroy(r);
+        cudaGetLastError();
+        return fail(st, why);
+    }
+    *out = r;
+    return RK_OK;
 }
 
 rk_status rk_rollout_reset(rk_handle* h, rk_rollout* r) {
@@ -1287,6 +1400,7 @@ rk_status rk_update_batch(rk_handle* h, const rk_batch_desc* desc, const rk_batc
         if (st != RK_OK) return st;
         rk::ScatterParams C{};
         C.n = n; C.m = m; C.dof = dof; C.throw_mode = desc->error_mode == RK_ERRORS_THROW; C.idx = r->idx;
+        C.slots = r->traj->slots();
         C.s_prof = view.prof; C.s_codes = view.codes; C.s_status = view.status; C.s_duration = view.duration; C.s_imd = view.imd;
         C.s_limiting = view.limiting; C.s_detail = view.detail;
         C.prof = r->traj->prof; C.codes = r->traj->codes; C.status = r->traj->status; C.duration = r->traj->duration; C.imd = r->traj->imd;
@@ -1302,6 +1416,7 @@ rk_status rk_update_batch(rk_handle* h, const rk_batch_desc* desc, const rk_batc
     rk::StepParams T{};
     T.n = n; T.dof = dof; T.throw_mode = desc->error_mode == RK_ERRORS_THROW; T.reset_time = out->reset_time_on_new_calculation;
     T.delta_time = desc->delta_time;
+    T.compact = r->traj->layout == RK_RESULT_COMPACT;
     T.prof = r->traj->prof; T.duration = r->traj->duration; T.status = r->traj->status; T.dirty = r->dirty;
     T.time_in = r->time[r->time_cur]; T.time_out = r->time[r->time_cur ^ 1];
     T.last_p = r->last[0]; T.last_v = r->last[1]; T.last_a = r->last[2];
@@ -1334,7 +1449,7 @@ rk_status rk_position_extrema_batch(rk_handle* h, const rk_trajectories* traj, d
         for (int k = 0; k < 4; ++k) dev[k] = dst[k] ? (double*)((char*)h->stage_dev + k * per) : nullptr;
     }
     rk::QueryParams Q{};
-    Q.n = traj->n; Q.dof = traj->dof; Q.prof = traj->prof;
+    Q.n = traj->n; Q.dof = traj->dof; Q.prof = traj->prof; Q.compact = traj->layout == RK_RESULT_COMPACT;
     Q.e_min = dev[0]; Q.e_max = dev[1]; Q.e_tmin = dev[2]; Q.e_tmax = dev[3];
     rk::k_position_extrema<<<(unsigned)(((int64_t)traj->n * traj->dof + 255) / 256), 256, 0, h->stream>>>(Q);
     h->launches += 1;
@@ -1363,6 +1478,7 @@ rk_status rk_first_time_at_position_batch(rk_handle* h, const rk_trajectories* t
     }
     rk::QueryParams Q{};
     Q.n = traj->n; Q.dof = traj->dof; Q.prof = traj->prof; Q.position = d_pos; Q.time = d_time;
+    Q.compact = traj->layout == RK_RESULT_COMPACT;
     rk::k_first_time_at_position<<<(unsigned)(((int64_t)traj->n * traj->dof + 255) / 256), 256, 0, h->stream>>>(Q);
     h->launches += 1;
     RK_CUDA(cudaGetLastError());
@@ -1379,7 +1495,11 @@ rk_status rk_trajectories_read(rk_handle* h, const rk_trajectories* t, int32_t f
     const size_t items = (size_t)t->n * t->dof;
     const void* src = nullptr;
     size_t bytes = 0;
-    auto slots = [&](int first, int count) { src = t->prof + (size_t)first * items; bytes = sizeof(double) * count * items; };
+    int ex_first = -1, ex_count = 0;  // compact layout: the field is expanded by a kernel instead of copied
+    auto slots = [&](int first, int count) {
+        src = t->prof + (size_t)first * items; bytes = sizeof(double) * count * items;
+        if (t->layout == RK_RESULT_COMPACT) { ex_first = first; ex_count = count; }
+    };
     switch (field) {
         case RK_FIELD_STATUS: src = t->status; bytes = sizeof(int32_t) * t->n; break;
         case RK_FIELD_DURATION: src = t->duration; bytes = sizeof(double) * t->n; break;
@@ -1402,7 +1522,20 @@ rk_status rk_trajectories_read(rk_handle* h, const rk_trajectories* t, int32_t f
         case RK_FIELD_PF_VF_AF: slots(rk::S_PF, 3); break;
         default: return fail(RK_ERR_INVALID_ARGUMENT, "unknown field");
     }
-    if (bytes == 0) return RK_OK;
+    if (bytes == 0 || t->n == 0) return RK_OK;
+    if (ex_first >= 0) {
+        double* dev = (double*)dst;
+        if (dst_memory_space == RK_MEM_HOST) {
+            rk_status st = ensure_stage(h, bytes, 0);
+            if (st != RK_OK) return st;
+            dev = (double*)h->stage_dev;
+        }
+        rk::k_read_expanded<<<(unsigned)((items + 255) / 256), 256, 0, h->stream>>>(t->prof, (int64_t)items, ex_first, ex_count, dev);
+        h->launches += 1;
+        RK_CUDA(cudaGetLastError());
+        if (dst_memory_space != RK_MEM_HOST) return RK_OK;
+        src = dev;
+    }
     RK_CUDA(cudaMemcpyAsync(dst, src, bytes, dst_memory_space == RK_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, h->stream));
     if (dst_memory_space == RK_MEM_HOST) RK_CUDA(cudaStreamSynchronize(h->stream));
     return RK_OK;

@@ -21,6 +21,7 @@ struct Params {
     int32_t discrete;
     int32_t throw_mode;
     int32_t check_current, check_target;
+    int32_t compact;  // trajectory storage layout: 0 = full Profile (59 slots), 1 = compact record (COMPACT_SLOTS, rk_store.cuh)
     double delta_time;
     int8_t ci[RK_MAX_DOF];
     int8_t sync[RK_MAX_DOF];
@@ -40,7 +41,7 @@ struct Params {
     uint32_t* pend;      // VEL stage: items whose root candidates are being polished, [dof * cn]
     uint32_t* counters;  // [0..18] list lengths per Step-2 stage, [20..22] quartic root queues, [24] rescue list, [32 + 2 * step], [33 + 2 * step] pending items / polish tasks of VEL stage `step`
     // trajectory storage
-    double* prof;     // [PROFILE_SLOTS][dof][n]
+    double* prof;     // [PROFILE_SLOTS or COMPACT_SLOTS][dof][n]
     uint32_t* codes;  // [dof][n]
     int32_t* status;  // [n]
     double* duration; // [n]

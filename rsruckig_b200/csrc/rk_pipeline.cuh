@@ -172,6 +172,13 @@ __global__ void __launch_bounds__(128, RK_SU_MINB) k1_setup(const Params P) {
     P.wmeta[(int64_t)WM_META * wstride + wi] = meta;
 
     // the parts of the final Profile that do not depend on the later stages
+    if (P.compact) {  // compact record: the state before the brake pre-trajectory, the brake itself, the target
+        out.put(C_P0, x.p0); out.put(C_V0, x.v0); out.put(C_A0, x.a0);
+        out.put(C_BRAKE_T, bt0); out.put(C_BRAKE_T + 1, bt1);
+        out.put(C_BRAKE_J, kind == K_POS2 ? ba0 : bj0); out.put(C_BRAKE_J + 1, bj1);
+        out.put(C_PF, pf_store); out.put(C_VF, vf_store); out.put(C_AF, af_store);
+        return;
+    }
     out.put(S_BRAKE_DUR, bdur);
     out.put(S_BRAKE_T, bt0); out.put(S_BRAKE_T + 1, bt1);
     out.put(S_BRAKE_J, bj0); out.put(S_BRAKE_J + 1, bj1);
@@ -1311,8 +1318,12 @@ __global__ void __launch_bounds__(128, RK_EX_MINB) k_expand(const Params P) {
         ProfileSink out{P.prof, (int64_t)P.dof * P.n, it.gi};
         if (src == RK_SRC_NONE || kind == K_NONE) {
             // disabled DoF (calculator_target.rs:313-323) or a trajectory that ended with an error status
-            const int64_t g = (int64_t)it.d * P.in_n + (it.ig + P.in_shift);
-            store_idle_profile(out, P.p0[g], P.v0[g], P.a0[g]);
+            if (P.compact) {
+                out.put(C_META, compact_meta(kind, kind, CM_IDLE_STATE, false, false, UDDU));
+            } else {
+                const int64_t g = (int64_t)it.d * P.in_n + (it.ig + P.in_shift);
+                store_idle_profile(out, P.p0[g], P.v0[g], P.a0[g]);
+            }
             P.codes[it.gi] = pack_codes(L_NONE, UDDU, DIR_UP, RK_SRC_NONE);
             return;
         }
@@ -1320,12 +1331,14 @@ __global__ void __launch_bounds__(128, RK_EX_MINB) k_expand(const Params P) {
             // A disabled DoF whose profile the reference overwrites with its block's p_min (zero duration :535-541, the
             // single-DoF shortcut :475-481, a disabled limiting DoF): the block of a disabled DoF on a fresh calculator holds
             // Profile::default().
-            store_idle_profile(out, 0.0, 0.0, 0.0);
+            if (P.compact) out.put(C_META, compact_meta(kind, kind, CM_IDLE_ZERO, false, false, UDDU));
+            else store_idle_profile(out, 0.0, 0.0, 0.0);
             P.codes[it.gi] = pack_codes(L_NONE, UDDU, DIR_UP, src);
             return;
         }
         if (src == RK_SRC_FAILED) {  // k2_fail has set the status and the code word
-            store_idle_profile(out, 0.0, 0.0, 0.0);
+            if (P.compact) out.put(C_META, compact_meta(kind, kind, CM_IDLE_ZERO, false, false, UDDU));
+            else store_idle_profile(out, 0.0, 0.0, 0.0);
             return;
         }
         double t[7], ctrl, ctrl2;
@@ -1361,12 +1374,20 @@ __global__ void __launch_bounds__(128, RK_EX_MINB) k_expand(const Params P) {
             }
         }
         if (ok) {
-            const double p7 = store_profile(out, store_kind, t, ctrl, ctrl2, cs, lim_check, it.b.p0, it.b.v0, it.b.a0, it.x.vf, it.x.af);
-            if (pf_from_p7) out.put(S_PF, p7);
+            if (P.compact) {
+#pragma unroll
+                for (int i = 0; i < 7; ++i) out.put(C_T + i, t[i]);
+                out.put(C_CTRL, ctrl); out.put(C_CTRL2, ctrl2);
+                out.put(C_META, compact_meta(kind, store_kind, CM_PROFILE, forces_a3_zero(lim_check), pf_from_p7, cs));
+            } else {
+                const double p7 = store_profile(out, store_kind, t, ctrl, ctrl2, cs, lim_check, it.b.p0, it.b.v0, it.b.a0, it.x.vf, it.x.af);
+                if (pf_from_p7) out.put(S_PF, p7);
+            }
             P.codes[it.gi] = pack_codes(lim, cs, dir, src);
         } else {
             report_step2_failure(P, it.d, it.ig);
-            store_idle_profile(out, 0.0, 0.0, 0.0);
+            if (P.compact) out.put(C_META, compact_meta(kind, kind, CM_IDLE_ZERO, false, false, UDDU));
+            else store_idle_profile(out, 0.0, 0.0, 0.0);
             P.codes[it.gi] = pack_codes(L_NONE, UDDU, DIR_UP, RK_SRC_STEP2);
         }
     }

@@ -130,4 +130,69 @@ __device__ __forceinline__ void store_idle_profile(const ProfileSink& o, double 
     o.put(S_A + 7, a7); o.put(S_V + 7, v7); o.put(S_P + 7, p7);
 }
 
+// ------------------------------------------------------------------------------------------------ compact result record
+// RK_RESULT_COMPACT: 20 doubles per (DoF, trajectory) instead of the 59 of the full Profile — what the
+// calculation actually decided (t[7], the control values, the brake pre-trajectory) plus the boundary states it started from.
+// Every other Profile field is a deterministic function of these: expand_compact() below runs the very operations the
+// full-layout path runs (store_profile, the brake integration of k1_setup), so the expanded arrays are bit-identical to
+// what RK_RESULT_FULL stores. Same structure-of-arrays rows: slot s of DoF d, trajectory i : prof[(s * dof + d) * n + i].
+//   T 0..6 | CTRL 7 (jerk / acceleration / velocity of the control pattern) | CTRL2 8 | P0 V0 A0 9..11 (the input's current
+//   state = state before the brake pre-trajectory) | BRAKE_T 12,13 | BRAKE_J 14,15 (second-order brake: slot 14 holds
+//   BrakeProfile::a[0], its jerks are zero) | PF VF AF 16..18 | META 19
+enum : int { C_T = 0, C_CTRL = 7, C_CTRL2 = 8, C_P0 = 9, C_V0 = 10, C_A0 = 11, C_BRAKE_T = 12, C_BRAKE_J = 14, C_PF = 16, C_VF = 17, C_AF = 18,
+             C_META = 19, COMPACT_SLOTS = 20 };
+// META (an exactly representable small integer): bits 0..2 solver kind of the DoF (K_*: decides the brake variant), 3..5 kind
+// the profile is expanded with (differs after phase synchronisation), 6..7 CM_IDLE_*, 8 a[3] forced to zero, 9 pf = p[7],
+// 10 control signs
+enum : int { CM_PROFILE = 0, CM_IDLE_STATE = 1, CM_IDLE_ZERO = 2 };
+__device__ __forceinline__ double compact_meta(int kind, int store_kind, int idle, bool zero_a3, bool pf_from_p7, int cs) {
+    return (double)(kind | (store_kind << 3) | (idle << 6) | ((zero_a3 ? 1 : 0) << 8) | ((pf_from_p7 ? 1 : 0) << 9) | ((cs & 1) << 10));
+}
+
+// Compact record -> the 59 fields of the full layout, written through `o` (a stride-1 local array for the readers).
+__device__ __forceinline__ void expand_compact(const double (&r)[COMPACT_SLOTS], const ProfileSink& o) {
+    const int m = (int)r[C_META];
+    const int kind = m & 7, store_kind = (m >> 3) & 7, idle = (m >> 6) & 3, cs = (m >> 10) & 1;
+    const bool zero_a3 = (m >> 8) & 1, pf_from_p7 = (m >> 9) & 1;
+    // brake pre-trajectory: the integration of k1_setup (brake.rs:195-235)
+    const double bt0 = r[C_BRAKE_T], bt1 = r[C_BRAKE_T + 1];
+    const double bj0 = (kind == K_POS2) ? 0.0 : r[C_BRAKE_J], bj1 = r[C_BRAKE_J + 1];
+    double bdur = 0.0, ba0 = 0.0, ba1 = 0.0, bv0 = 0.0, bv1 = 0.0, bp0 = 0.0, bp1 = 0.0;
+    double ps = r[C_P0], vs = r[C_V0], as = r[C_A0];
+    if (kind == K_POS3 || kind == K_VEL3) {
+        if (!(bt0 <= 0.0 && bt1 <= 0.0)) {
+            bdur = bt0;
+            bp0 = ps; bv0 = vs; ba0 = as;
+            integrate(bt0, ps, vs, as, bj0, ps, vs, as);
+            if (bt1 > 0.0) {
+                bdur += bt1;
+                bp1 = ps; bv1 = vs; ba1 = as;
+                integrate(bt1, ps, vs, as, bj1, ps, vs, as);
+            }
+        }
+    } else if (kind == K_POS2) {
+        ba0 = r[C_BRAKE_J];
+        if (!(bt0 <= 0.0)) {
+            bdur = bt0;
+            bp0 = ps; bv0 = vs;
+            integrate(bt0, ps, vs, ba0, 0.0, ps, vs, as);
+        }
+    }
+    o.put(S_BRAKE_DUR, bdur);
+    o.put(S_BRAKE_T, bt0); o.put(S_BRAKE_T + 1, bt1);
+    o.put(S_BRAKE_J, bj0); o.put(S_BRAKE_J + 1, bj1);
+    o.put(S_BRAKE_A, ba0); o.put(S_BRAKE_A + 1, ba1);
+    o.put(S_BRAKE_V, bv0); o.put(S_BRAKE_V + 1, bv1);
+    o.put(S_BRAKE_P, bp0); o.put(S_BRAKE_P + 1, bp1);
+    o.put(S_PF, r[C_PF]); o.put(S_VF, r[C_VF]); o.put(S_AF, r[C_AF]);
+    if (idle == CM_IDLE_STATE) { store_idle_profile(o, r[C_P0], r[C_V0], r[C_A0]); return; }
+    if (idle == CM_IDLE_ZERO) { store_idle_profile(o, 0.0, 0.0, 0.0); return; }
+    double t[7];
+#pragma unroll
+    for (int i = 0; i < 7; ++i) t[i] = r[C_T + i];
+    // store_profile only asks forces_a3_zero(lim_check): L_VEL forces it, L_NONE does not
+    const double p7 = store_profile(o, store_kind, t, r[C_CTRL], r[C_CTRL2], cs, zero_a3 ? (int)L_VEL : (int)L_NONE, ps, vs, as, r[C_VF], r[C_AF]);
+    if (pf_from_p7) o.put(S_PF, p7);
+}
+
 }  // namespace rk

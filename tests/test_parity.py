@@ -31,7 +31,8 @@ def run_both(BatchRuckig, fields, n, dof, *, delta_time=0.005, flavour="portable
     from oracle.oracle import OracleBatch
     from rsruckig_b200 import IgnoreErrorHandler, ThrowErrorHandler
     error_mode = kw.pop("error_mode", cabi.RK_ERRORS_THROW)
-    otg = BatchRuckig(dof, delta_time, ThrowErrorHandler if error_mode == cabi.RK_ERRORS_THROW else IgnoreErrorHandler)
+    otg = BatchRuckig(dof, delta_time, ThrowErrorHandler if error_mode == cabi.RK_ERRORS_THROW else IgnoreErrorHandler,
+                      result_layout=kw.pop("result_layout", None))
     otg.calculate(fields, n=n, memory_space=cabi.RK_MEM_HOST, **kw)
     ob = OracleBatch(n, dof, flavour)
     ob.calculate(fields, delta_time=delta_time, threads=threads, error_mode=error_mode, **kw)
