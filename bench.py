@@ -41,7 +41,7 @@ METRIC = "7-DoF trajectory calculations/s (position interface, Time sync)"
 UNIT = "trajectories/s"
 DELTA_TIME = 0.005
 BYTES_IN = 9 * DOF * 8                 # nine mandatory f64 arrays
-BYTES_OUT = (16 * DOF + 3) * 8         # compact result record of SURVEY.md §8d; the kernels store the full 472 B Profile per DoF
+BYTES_OUT = (16 * DOF + 3) * 8         # compact result record of SURVEY.md §8d (the algorithmic figure); RK_RESULT_COMPACT stores 20 doubles + codes per DoF
 
 
 def algorithmic_flop_per_trajectory() -> tuple[float, str]:
@@ -71,11 +71,18 @@ def measured_peaks() -> dict:
     return {"hbm_gbs": 6650.0, "_source": "fallback"}
 
 
-def config(n_per_gpu: int, n_gpus: int) -> dict:
-    return {"workload": f"{n_per_gpu} x 7-DoF position interface per GPU, Time sync, reference bench input distribution "
-                        f"(BASELINE.json configs[4]: 64Mi sharded over 8 GPUs -> 8Mi per GPU)",
-            "n_per_gpu": n_per_gpu, "n_total": n_per_gpu * n_gpus, "dof": DOF, "delta_time": DELTA_TIME,
-            "l2": "inputs (4.0 GB per GPU at the default size) exceed the 126 MB L2, no flush needed",
+def config(n_per_gpu: int, n_gpus: int, scaling: str = "weak", layout: str = "compact") -> dict:
+    if scaling == "strong":
+        what = (f"BASELINE.json configs[4] as written: {n_per_gpu * n_gpus} x 7-DoF position interface in total, sharded over {n_gpus} GPU(s) "
+                f"({n_per_gpu} per GPU), Time sync, reference bench input distribution")
+    else:
+        what = (f"{n_per_gpu} x 7-DoF position interface per GPU, Time sync, reference bench input distribution "
+                f"(BASELINE.json configs[4]: 64Mi sharded over 8 GPUs -> 8Mi per GPU)")
+    return {"workload": what, "n_per_gpu": n_per_gpu, "n_total": n_per_gpu * n_gpus, "dof": DOF, "delta_time": DELTA_TIME,
+            "result_layout": f"{layout}: " + ("20 doubles per (DoF, trajectory) stay on the device (t[7], control values, brake pre-trajectory, boundary "
+                                              "states; every reader expands them bit-identically), SURVEY.md 8b" if layout == "compact" else
+                                              "the reference's Profile verbatim, 59 doubles per (DoF, trajectory)"),
+            "l2": f"inputs ({n_per_gpu * BYTES_IN / 1e9:.1f} GB per GPU) exceed the 126 MB L2, no flush needed",
             "sharding": "contiguous index ranges, no collective"}
 
 
@@ -127,6 +134,36 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def bind_to_gpu_cores(index: int) -> dict:
+    """Pin this rank to the CPU cores (and thereby the NUMA node) `nvidia-smi topo -m` lists for its GPU, BEFORE any pinned host
+    buffer is allocated: the staging buffers of the host-buffer path are then first-touched on the GPU's own node, and eight ranks
+    do not pull their 4.2 GB per step through the other socket (round 1: end-to-end efficiency 0.52 at N = 8 with unbound ranks)."""
+    import re
+    info = {"bound": False}
+    try:
+        out = subprocess.run(["nvidia-smi", "topo", "-m"], capture_output=True, text=True, timeout=30).stdout
+        row = next((ln for ln in out.splitlines() if re.match(rf"^GPU{index}\s", ln)), None)
+        if row is None:
+            return info
+        lists = [t for t in re.split(r"\s+", row.strip())[1:] if re.fullmatch(r"\d+(-\d+)?(,\d+(-\d+)?)*", t)]
+        if not lists:
+            return info
+        cpus = set()
+        for part in lists[0].split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0)
+        use = cpus & allowed
+        if use and use != allowed:
+            os.sched_setaffinity(0, use)
+            info.update({"bound": True, "cpus": lists[0], "numa": lists[1] if len(lists) > 1 else None, "n_cpus": len(use)})
+        else:
+            info.update({"cpus": lists[0], "note": "GPU's cores = all allowed cores (single node) or none allowed; nothing to bind"})
+    except Exception as e:  # no nvidia-smi, exotic topology output: run unbound
+        info["error"] = str(e)[:80]
+    return info
+
+
 def run_reference(args):
     """The reference's CPU algorithm (C++ restatement, glibc libm) on all host cores; rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
@@ -147,8 +184,8 @@ def run_reference(args):
     total = sum(secs)
     value = n * args.steps / total
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": config(args.n, args.gpus),
+            "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": config(args.n, args.gpus, args.scaling, args.layout),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                              "sample": f"{n} trajectories of the same distribution per step; C++17 restatement of rsruckig v2.1.2 (oracle/, "
                                        f"g++ -O2 -ffp-contract=off, glibc libm), one reused calculator per thread, static partition over {threads} threads; "
@@ -206,6 +243,7 @@ def run_b200(args):
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU path; use --impl reference for the CPU baseline)"
     if rank == 0:
         entry.build()
+    binding = bind_to_gpu_cores(local) if not args.no_bind else {"bound": False, "note": "--no-bind"}
     torch.cuda.set_device(local)
     if world > 1:
         # stdout carries exactly one JSON line: what NCCL prints while the communicator comes up (its version banner under
@@ -279,15 +317,18 @@ def run_b200(args):
     # ---- e2e: host (pinned) buffers through the C ABI, H2D + kernels + D2H inside the timed region
     e2e = None
     if not args.no_e2e:
-        hf = {k: torch.empty(v.shape, dtype=v.dtype, pin_memory=True) for k, v in f.items()}
+        # host buffers are bounded to 8Mi trajectories (4.2 GB pinned): a strong-scaling shard of 64Mi would pin 34 GB of host memory
+        n_e = min(n, 8 << 20)
+        otg_e = otg if n_e == n else BatchRuckig(DOF, DELTA_TIME, ThrowErrorHandler, device=local, result_layout=layout)
+        hf = {k: torch.empty((v.shape[0], n_e), dtype=v.dtype, pin_memory=True) for k, v in f.items()}
         for k in hf:
-            hf[k].copy_(f[k])
-        h_status = torch.empty(n, dtype=torch.int32, pin_memory=True)
-        h_duration = torch.empty(n, dtype=torch.float64, pin_memory=True)
+            hf[k].copy_(f[k][:, :n_e])
+        h_status = torch.empty(n_e, dtype=torch.int32, pin_memory=True)
+        h_duration = torch.empty(n_e, dtype=torch.float64, pin_memory=True)
         torch.cuda.synchronize()
 
         def step_host():
-            otg.calculate(hf, n=n, memory_space=cabi.RK_MEM_HOST, status=h_status, duration=h_duration)
+            otg_e.calculate(hf, n=n_e, memory_space=cabi.RK_MEM_HOST, status=h_status, duration=h_duration)
 
         for _ in range(max(1, min(args.warmup, 2))):
             step_host()
@@ -308,11 +349,13 @@ def run_b200(args):
         if world > 1:
             dist.barrier()
             dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
-        assert bool((h_status == status.cpu()).all()), "host-buffer and device-buffer runs disagree"
-        e2e = {"value": n * world * k_e2e / float(t_e.item()), "unit": UNIT, "steps": k_e2e,
-               "h2d_bytes_per_step": int(sum(v.numel() * v.element_size() for v in hf.values())),
+        assert bool((h_status == status[:n_e].cpu()).all()), "host-buffer and device-buffer runs disagree"
+        e2e = {"value": n_e * world * k_e2e / float(t_e.item()), "unit": UNIT, "steps": k_e2e, "n_per_gpu": n_e,
+               "h2d_bytes_per_step": int(sum(v.numel() * v.element_size() for v in hf.values())), "host_binding": binding,
                "d2h_bytes_per_step": int(h_status.numel() * 4 + h_duration.numel() * 8),
-               "note": "rk_calculate_batch with RK_MEM_HOST on pinned buffers; trajectories stay device-resident for rk_at_time_batch"}
+               "note": "rk_calculate_batch with RK_MEM_HOST on pinned buffers; status + duration (12 B per trajectory) come back, the trajectories "
+                       "themselves stay device-resident for rk_at_time_batch / the query helpers — a host consumer that wants every Profile pays "
+                       "another 20 (compact) or 59 (full) doubles per DoF through rk_trajectories_read, which this number does not include"}
 
     # ---- p50 latency of one 64Ki batch (the second half of BASELINE.json's metric) and the at_time rollout of configs[3]
     latency = None
@@ -322,6 +365,9 @@ def run_b200(args):
         n64 = 65536
         f64k = {k: v[:, :n64].contiguous() for k, v in f.items()}
         otg64 = BatchRuckig(DOF, DELTA_TIME, ThrowErrorHandler, device=local, result_layout=layout)
+        # the RL rollout keeps the reference's full Profile (216 MB for 64Ki x 7): at_time then reads phase starts instead of integrating them
+        otg_roll = BatchRuckig(DOF, DELTA_TIME, ThrowErrorHandler, device=local, result_layout=cabi.RK_RESULT_FULL)
+        otg_roll.calculate(f64k, n=n64, memory_space=cabi.RK_MEM_DEVICE)
         st64 = torch.zeros(n64, dtype=torch.int32, device=dev)
         du64 = torch.zeros(n64, dtype=torch.float64, device=dev)
         run64 = lambda: otg64.calculate(f64k, n=n64, memory_space=cabi.RK_MEM_DEVICE, status=st64, duration=du64)
@@ -346,8 +392,8 @@ def run_b200(args):
         pos = torch.empty((K, DOF, n64), dtype=torch.float64, device=dev)
         vel = torch.empty_like(pos)
         acc = torch.empty_like(pos)
-        sample = lambda: otg64.at_time(time_start=0.0, delta_time=DELTA_TIME, steps=K, memory_space=cabi.RK_MEM_DEVICE,
-                                       position=pos, velocity=vel, acceleration=acc)
+        sample = lambda: otg_roll.at_time(time_start=0.0, delta_time=DELTA_TIME, steps=K, memory_space=cabi.RK_MEM_DEVICE,
+                                          position=pos, velocity=vel, acceleration=acc)
         for _ in range(3):
             sample()
         otg64.sync()
@@ -372,13 +418,14 @@ def run_b200(args):
         b2.synchronize()
         fill_gbs = 3 * out_bytes / (a2.elapsed_time(b2) * 1e-3) / 1e9
         peaks_ = measured_peaks()
-        sampling = {"workload": f"{n64} x {DOF}-DoF trajectories, {K} control cycles of Trajectory::at_time (position, velocity, acceleration)",
+        sampling = {"workload": f"{n64} x {DOF}-DoF trajectories (full Profile layout), {K} control cycles of Trajectory::at_time (position, velocity, acceleration)",
                     "ms_per_rollout": ms_s, "samples_per_s": n64 * K / (ms_s * 1e-3),
                     "roofline": {"bound": "hbm", "achieved": out_bytes / (ms_s * 1e-3) / 1e9, "peak": peaks_["hbm_gbs"], "unit": "GB/s",
                                  "frac": out_bytes / (ms_s * 1e-3) / 1e9 / peaks_["hbm_gbs"], "of": peaks_["_source"],
                                  "bytes_per_launch": out_bytes, "write_only_fill_gbs": fill_gbs,
                                  "frac_of_write_only_fill": out_bytes / (ms_s * 1e-3) / 1e9 / fill_gbs, "note": "algorithmic bytes = 3 x 8 B x DoF per sample written; the 472 B profile per (DoF, trajectory) read once is amortised over K"}}
         del pos, vel, acc
+        otg_roll.close()
         # closed control loops: rk_update_batch, 64Ki environments, every 10th cycle a tenth of them is
         # re-targeted mid-motion and re-solved from its current state; all advance one cycle and pass the state on
         from rsruckig_b200 import BatchRollout
@@ -432,8 +479,8 @@ def run_b200(args):
         if os.path.exists(ops_path):
             ops = json.load(open(ops_path))
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-                "data": "synthetic", "config": config(n, world), "gpu_launches": int(gpu_launches), "launches_per_step": int(launches_per_step),
+                "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic", "config": config(n, world, args.scaling, args.layout), "gpu_launches": int(gpu_launches), "launches_per_step": int(launches_per_step),
                 "working_fraction": n_working / n, "clocks": clocks, "e2e": e2e, "latency_64k": latency, "at_time": sampling, "closed_loop": closed_loop,
                 "roofline": {"bound": "fp64", "achieved": achieved_tflops, "peak": fp64_peak_tflops, "unit": "TFLOP/s",
                              "frac": achieved_tflops / fp64_peak_tflops if fp64_peak_tflops else None,
@@ -453,7 +500,10 @@ def run_b200(args):
                                          "with --fmad=false, so an add or a mul fills a DFMA issue slot with 1 flop (fp64_issue_frac = FP64 "
                                          "instructions issued / DFMA issue peak)",
                              "hbm": {"achieved": hbm_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": hbm_gbs / peaks["hbm_gbs"],
-                                     "of": peaks["_source"], "bytes_per_trajectory": BYTES_IN + BYTES_OUT}}}
+                                     "of": peaks["_source"], "bytes_per_trajectory": BYTES_IN + BYTES_OUT},
+                             # the other half of BASELINE.json's metric and the HBM-bound sampling kernel, inside the key the driver keeps
+                             "latency_64k": latency,
+                             "at_time": (sampling or {}).get("roofline")}}
         if not args.no_cpu and world == 1:  # the CPU baseline is reported at N = 1 only
             line["cpu_baseline"] = cpu_baseline_sample(os.cpu_count() or 1)
         print(json.dumps(line), flush=True)
@@ -467,17 +517,23 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--n", type=int, default=8 << 20, help="trajectories per GPU")
+    ap.add_argument("--n", type=int, default=8 << 20, help="trajectories per GPU (weak scaling)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --n trajectories per GPU (the default, 8Mi = configs[4]'s shard on 8 GPUs); strong: --total trajectories split over the GPUs")
+    ap.add_argument("--total", type=int, default=64 << 20, help="total trajectories of a strong-scaling run (configs[4]: 64Mi)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="trajectories per step of the reference arm (0 = 131072 per thread)")
     ap.add_argument("--layout", default="compact", choices=["compact", "full"],
                     help="device-resident result: compact record (20 doubles per DoF, SURVEY.md 8b/8d) or the reference's full Profile (59)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-bind", action="store_true", help="do not pin the rank to the CPU cores / NUMA node of its GPU")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the 64Ki-batch latency and the at_time rollout")
     ap.add_argument("--sample-steps", type=int, default=1000, help="control cycles of the at_time rollout (configs[3])")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
+    if args.scaling == "strong":
+        args.n = args.total // max(1, int(os.environ.get("WORLD_SIZE", str(args.gpus))))
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -91,6 +91,7 @@ extern "C" {
     pub fn rk_trajectories_create(h: *mut rk_handle, n: i64, dof: i32, out: *mut *mut rk_trajectories) -> rk_status; // Trajectory::new trajectory.rs:37
     pub fn rk_trajectories_create_ex(h: *mut rk_handle, n: i64, dof: i32, result_layout: i32, out: *mut *mut rk_trajectories) -> rk_status; // RK_RESULT_FULL | RK_RESULT_COMPACT
     pub fn rk_trajectories_destroy(t: *mut rk_trajectories) -> rk_status;
+    pub fn rk_debug_counters(h: *mut rk_handle, out: *mut u32) -> rk_status; // diagnostics: 112 work-list counters of the last chunk
     pub fn rk_calculate_batch(h: *mut rk_handle, desc: *const rk_batch_desc, input: *const rk_batch_in,
                               traj: *mut rk_trajectories, out: *const rk_batch_out) -> rk_status;                 // Ruckig::calculate  ruckig.rs:210
     pub fn rk_validate_batch(h: *mut rk_handle, desc: *const rk_batch_desc, input: *const rk_batch_in,

@@ -259,6 +259,9 @@ rk_status rk_trajectories_read(rk_handle* h, const rk_trajectories* traj, int32_
 rk_status rk_sync(rk_handle* h);                      /* wait for the handle's stream */
 void* rk_stream(rk_handle* h);                        /* the cudaStream_t, for event timing by the caller */
 int64_t rk_kernel_launches(const rk_handle* h);       /* kernels launched through this handle so far */
+/* Diagnostics: the 112 work-list counters the last chunk computed on scratch set 0 left behind (how many (DoF, trajectory)
+ * items entered each stage of the Step-2 chain, queue lengths of the Step-1 kernels; layout in rk_params.cuh). */
+rk_status rk_debug_counters(rk_handle* h, uint32_t* out /* [112] host */);
 /* Roofline denominator for this path (it is FP64-pipe bound): runs a register-resident chain of
  * dependent-free DFMAs on every SM for about `milliseconds` and reports the sustained rate, an FMA counted as 2 flop. */
 rk_status rk_measure_fp64_peak(rk_handle* h, double milliseconds, double* tflops);

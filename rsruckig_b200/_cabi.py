@@ -129,7 +129,7 @@ EXPORTS = (
     "rk_validate_batch", "rk_at_time_batch", "rk_trajectories_read", "rk_sync", "rk_stream", "rk_kernel_launches",
     "rk_status_string", "rk_last_error", "rk_version", "rk_measure_fp64_peak", "rk_selftest_division",
     "rk_position_extrema_batch", "rk_first_time_at_position_batch",
-    "rk_rollout_create", "rk_rollout_destroy", "rk_rollout_reset", "rk_rollout_trajectories", "rk_update_batch",
+    "rk_debug_counters", "rk_rollout_create", "rk_rollout_destroy", "rk_rollout_reset", "rk_rollout_trajectories", "rk_update_batch",
 )
 
 
@@ -174,7 +174,7 @@ def load():
     lib.rk_rollout_trajectories.restype = vp
     lib.rk_update_batch.argtypes = [vp, C.POINTER(RkBatchDesc), C.POINTER(RkBatchIn), vp, C.POINTER(RkUpdateOut), C.POINTER(C.c_int64)]
     for f in ("rk_create", "rk_destroy", "rk_trajectories_create", "rk_trajectories_create_ex", "rk_trajectories_destroy", "rk_calculate_batch",
-              "rk_validate_batch", "rk_at_time_batch", "rk_trajectories_read", "rk_sync", "rk_rollout_create", "rk_rollout_destroy",
+              "rk_validate_batch", "rk_at_time_batch", "rk_trajectories_read", "rk_sync", "rk_debug_counters", "rk_rollout_create", "rk_rollout_destroy",
               "rk_rollout_reset", "rk_update_batch", "rk_position_extrema_batch", "rk_first_time_at_position_batch"):
         getattr(lib, f).restype = C.c_int32
     _LIB = lib

@@ -1596,6 +1596,15 @@ rk_status rk_selftest_division(rk_handle* h, int64_t n, uint64_t seed, int64_t* 
     return RK_OK;
 }
 
+rk_status rk_debug_counters(rk_handle* h, uint32_t* out) {
+    if (!h || !out) return fail(RK_ERR_INVALID_ARGUMENT, "NULL argument to rk_debug_counters");
+    if (!h->sc[0].counters) return fail(RK_ERR_INVALID_ARGUMENT, "no calculation has run on this handle yet");
+    RK_CUDA(cudaSetDevice(h->device));
+    RK_CUDA(cudaStreamSynchronize(h->stream));
+    RK_CUDA(cudaMemcpy(out, h->sc[0].counters, sizeof(uint32_t) * RK_N_COUNTERS, cudaMemcpyDeviceToHost));
+    return RK_OK;
+}
+
 void* rk_stream(rk_handle* h) { return h ? (void*)h->stream : nullptr; }
 int64_t rk_kernel_launches(const rk_handle* h) { return h ? h->launches : 0; }
 
