@@ -94,6 +94,9 @@ extern "C" {
     pub fn rk_debug_counters(h: *mut rk_handle, out: *mut u32) -> rk_status; // diagnostics: 112 work-list counters of the last chunk
     pub fn rk_calculate_batch(h: *mut rk_handle, desc: *const rk_batch_desc, input: *const rk_batch_in,
                               traj: *mut rk_trajectories, out: *const rk_batch_out) -> rk_status;                 // Ruckig::calculate  ruckig.rs:210
+    pub fn rk_shard_range(n: i64, parts: i32, part: i32, first: *mut i64, count: *mut i64);
+    pub fn rk_calculate_batch_multi(handles: *const *mut rk_handle, trajs: *const *mut rk_trajectories, parts: i32, desc: *const rk_batch_desc,
+                                    input: *const rk_batch_in, out: *const rk_batch_out) -> rk_status;                // one host batch over all GPUs
     pub fn rk_validate_batch(h: *mut rk_handle, desc: *const rk_batch_desc, input: *const rk_batch_in,
                              check_current: i32, check_target: i32, valid: *mut u8, reason: *mut i32) -> rk_status; // validate_input ruckig.rs:150
     pub fn rk_at_time_batch(h: *mut rk_handle, traj: *const rk_trajectories, desc: *const rk_sample_desc,

@@ -190,6 +190,15 @@ rk_status rk_trajectories_destroy(rk_trajectories* t);
 rk_status rk_calculate_batch(rk_handle* h, const rk_batch_desc* desc, const rk_batch_in* in,
                              rk_trajectories* traj, const rk_batch_out* out);
 
+/* The same for ONE host batch spread over several handles — normally one per GPU of the box (north_star: "sharded trivially
+ * across the 8 GPUs of one box with no collectives beyond a final host gather"), so a Rust / C++ host uses every device
+ * without one process per GPU. Part g computes the contiguous index range rk_shard_range(n, parts, g) on handles[g] into
+ * trajs[g] (created for exactly that many trajectories); the parts run concurrently on one host thread each and write their
+ * slices of `out` (the gather). Host arrays only. Every part needs its own handle; two handles may share a device. */
+void rk_shard_range(int64_t n, int32_t parts, int32_t part, int64_t* first, int64_t* count);
+rk_status rk_calculate_batch_multi(rk_handle* const* handles, rk_trajectories* const* trajs, int32_t parts,
+                                   const rk_batch_desc* desc, const rk_batch_in* in, const rk_batch_out* out);
+
 /* Ruckig::validate_input(input, check_current, check_target) (ruckig.rs:150-171,
  * input_parameter.rs:251-420): valid[i] = 1 if trajectory i passes. reason[i] (may be NULL) = 0 if valid, else
  * (check_id << 8) | dof of the FIRST failing check in the reference's order; check ids are RK_INVALID_* below. */

@@ -129,7 +129,7 @@ EXPORTS = (
     "rk_validate_batch", "rk_at_time_batch", "rk_trajectories_read", "rk_sync", "rk_stream", "rk_kernel_launches",
     "rk_status_string", "rk_last_error", "rk_version", "rk_measure_fp64_peak", "rk_selftest_division",
     "rk_position_extrema_batch", "rk_first_time_at_position_batch",
-    "rk_debug_counters", "rk_rollout_create", "rk_rollout_destroy", "rk_rollout_reset", "rk_rollout_trajectories", "rk_update_batch",
+    "rk_debug_counters", "rk_shard_range", "rk_calculate_batch_multi", "rk_rollout_create", "rk_rollout_destroy", "rk_rollout_reset", "rk_rollout_trajectories", "rk_update_batch",
 )
 
 
@@ -149,6 +149,10 @@ def load():
     lib.rk_trajectories_create_ex.argtypes = [vp, C.c_int64, C.c_int32, C.c_int32, C.POINTER(vp)]
     lib.rk_trajectories_destroy.argtypes = [vp]
     lib.rk_calculate_batch.argtypes = [vp, C.POINTER(RkBatchDesc), C.POINTER(RkBatchIn), vp, C.POINTER(RkBatchOut)]
+    lib.rk_calculate_batch_multi.argtypes = [C.POINTER(vp), C.POINTER(vp), C.c_int32, C.POINTER(RkBatchDesc), C.POINTER(RkBatchIn), C.POINTER(RkBatchOut)]
+    lib.rk_shard_range.argtypes = [C.c_int64, C.c_int32, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    lib.rk_shard_range.restype = None
+    lib.rk_debug_counters.argtypes = [vp, vp]
     lib.rk_validate_batch.argtypes = [vp, C.POINTER(RkBatchDesc), C.POINTER(RkBatchIn), C.c_int32, C.c_int32, vp, vp]
     lib.rk_at_time_batch.argtypes = [vp, vp, C.POINTER(RkSampleDesc), C.POINTER(RkSampleOut)]
     lib.rk_trajectories_read.argtypes = [vp, vp, C.c_int32, vp, C.c_int32]
@@ -174,8 +178,8 @@ def load():
     lib.rk_rollout_trajectories.restype = vp
     lib.rk_update_batch.argtypes = [vp, C.POINTER(RkBatchDesc), C.POINTER(RkBatchIn), vp, C.POINTER(RkUpdateOut), C.POINTER(C.c_int64)]
     for f in ("rk_create", "rk_destroy", "rk_trajectories_create", "rk_trajectories_create_ex", "rk_trajectories_destroy", "rk_calculate_batch",
-              "rk_validate_batch", "rk_at_time_batch", "rk_trajectories_read", "rk_sync", "rk_debug_counters", "rk_rollout_create", "rk_rollout_destroy",
-              "rk_rollout_reset", "rk_update_batch", "rk_position_extrema_batch", "rk_first_time_at_position_batch"):
+              "rk_validate_batch", "rk_at_time_batch", "rk_trajectories_read", "rk_sync", "rk_debug_counters", "rk_calculate_batch_multi",
+              "rk_rollout_create", "rk_rollout_destroy", "rk_rollout_reset", "rk_update_batch", "rk_position_extrema_batch", "rk_first_time_at_position_batch"):
         getattr(lib, f).restype = C.c_int32
     _LIB = lib
     return lib

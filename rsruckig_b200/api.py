@@ -536,6 +536,90 @@ class BatchRuckig:
         return int(self._engine.lib.rk_kernel_launches(self._engine.h))
 
 
+class MultiBatchRuckig:
+    """One host batch over several handles — one per GPU of the box by default (rk_calculate_batch_multi): contiguous index
+    ranges (sharding.shard_range == rk_shard_range), one host thread per part, status / duration / independent minimum
+    durations gathered into the caller's host arrays. `devices` may name a device more than once (several handles on one GPU)."""
+
+    def __init__(self, dofs: int, delta_time: float, error_handler=ThrowErrorHandler, devices=None, result_layout: int = cabi.RK_RESULT_FULL):
+        self.degrees_of_freedom, self.delta_time, self.error_handler = int(dofs), float(delta_time), error_handler
+        self.lib = cabi.load()
+        if devices is None:
+            import torch
+            devices = list(range(torch.cuda.device_count()))
+        self.devices = [int(d) for d in devices]
+        self.result_layout = int(result_layout)
+        self._handles, self._trajs, self._n = [], [], -1
+        for d in self.devices:
+            h = C.c_void_p()
+            cabi.check(self.lib.rk_create(d, C.byref(h)))
+            self._handles.append(h)
+
+    def close(self):
+        try:
+            for t in self._trajs:
+                self.lib.rk_trajectories_destroy(t)
+            for h in self._handles:
+                self.lib.rk_destroy(h)
+        except Exception:
+            pass
+        self._trajs, self._handles = [], []
+
+    def __del__(self):
+        self.close()
+
+    def part_range(self, n: int, g: int):
+        from .sharding import shard_range
+        return shard_range(n, g, len(self.devices))
+
+    def _ensure(self, n: int):
+        if n == self._n:
+            return
+        for t in self._trajs:
+            self.lib.rk_trajectories_destroy(t)
+        self._trajs = []
+        for g, h in enumerate(self._handles):
+            lo, hi = self.part_range(n, g)
+            t = C.c_void_p()
+            cabi.check(self.lib.rk_trajectories_create_ex(h, hi - lo, self.degrees_of_freedom, self.result_layout, C.byref(t)))
+            self._trajs.append(t)
+        self._n = n
+
+    def calculate(self, fields: dict, *, n: int, status=None, duration=None, independent_min_durations=None, **kw):
+        """fields / outputs: host (numpy or pinned torch) arrays [dof][n] / [n]."""
+        self._ensure(n)
+        desc, keep = cabi.make_desc(n, self.degrees_of_freedom, memory_space=cabi.RK_MEM_HOST, delta_time=self.delta_time,
+                                    error_mode=cabi.RK_ERRORS_THROW if self.error_handler.throws else cabi.RK_ERRORS_IGNORE, **kw)
+        bin_ = cabi.make_in(fields)
+        out = cabi.RkBatchOut(cabi.ptr(status), cabi.ptr(duration), cabi.ptr(independent_min_durations))
+        G = len(self._handles)
+        hs = (C.c_void_p * G)(*[h.value for h in self._handles])
+        ts = (C.c_void_p * G)(*[t.value for t in self._trajs])
+        cabi.check(self.lib.rk_calculate_batch_multi(hs, ts, G, C.byref(desc), C.byref(bin_), C.byref(out)))
+
+    def read(self, field: int) -> np.ndarray:
+        """One field of all parts, concatenated in index order (host array)."""
+        parts = []
+        for g, (h, t) in enumerate(zip(self._handles, self._trajs)):
+            lo, hi = self.part_range(self._n, g)
+            m, dof = hi - lo, self.degrees_of_freedom
+            if m == 0:
+                continue
+            if field in (cabi.RK_FIELD_STATUS, cabi.RK_FIELD_LIMITING_DOF, cabi.RK_FIELD_ERROR_DETAIL):
+                o = np.empty(m, dtype=np.int32)
+            elif field == cabi.RK_FIELD_DURATION:
+                o = np.empty(m)
+            elif field == cabi.RK_FIELD_INDEPENDENT_MIN_DURATIONS:
+                o = np.empty((dof, m))
+            elif field == cabi.RK_FIELD_CODES:
+                o = np.empty((dof, m), dtype=np.uint32)
+            else:
+                o = np.empty((cabi.FIELD_SLOTS[field], dof, m))
+            cabi.check(self.lib.rk_trajectories_read(h, t, field, o.ctypes.data, cabi.RK_MEM_HOST))
+            parts.append(o)
+        return np.concatenate(parts, axis=-1)
+
+
 class BatchRollout:
     """n independent closed control loops on the device: the batched `Ruckig::update` (ruckig.rs:266-321).
 

@@ -19,6 +19,8 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <thread>
+#include <vector>
 
 #include "../../include/ruckig_b200.h"
 #include "rk_pipeline.cuh"
@@ -940,11 +942,37 @@ rk_status rk_trajectories_destroy(rk_trajectories* t) {
     return RK_OK;
 }
 
-rk_status rk_calculate_batch(rk_handle* h, const rk_batch_desc* desc, const rk_batch_in* in, rk_trajectories* traj, const rk_batch_out* out) {
+}  // extern "C"
+
+// Ruckig::calculate for trajectories [first, first + desc->n) of caller arrays whose DoF rows are `stride` elements apart
+// (rk_calculate_batch: first = 0, stride = n; rk_calculate_batch_multi: one index range per device of one host batch).
+static rk_status calculate_impl(rk_handle* h, const rk_batch_desc* desc, const rk_batch_in* in_full, rk_trajectories* traj, const rk_batch_out* out_full,
+                                int64_t stride, int64_t first) {
     if (!h || !traj) return fail(RK_ERR_INVALID_ARGUMENT, "handle / trajectories is NULL");
+    if (!desc || !in_full) return fail(RK_ERR_INVALID_ARGUMENT, "desc / in is NULL");
+    rk_batch_in in_shifted = *in_full;
+    {
+        const double** d11[11] = {&in_shifted.current_position, &in_shifted.current_velocity, &in_shifted.current_acceleration, &in_shifted.target_position,
+                                  &in_shifted.target_velocity, &in_shifted.target_acceleration, &in_shifted.max_velocity, &in_shifted.max_acceleration,
+                                  &in_shifted.max_jerk, &in_shifted.min_velocity, &in_shifted.min_acceleration};
+        for (auto p : d11) if (*p) *p += first;
+        if (in_shifted.enabled) in_shifted.enabled += first;
+        if (in_shifted.minimum_duration) in_shifted.minimum_duration += first;
+    }
+    const rk_batch_in* in = &in_shifted;
+    rk_batch_out out_shifted{};
+    const rk_batch_out* out = nullptr;
+    if (out_full) {
+        out_shifted = *out_full;
+        if (out_shifted.status) out_shifted.status += first;
+        if (out_shifted.duration) out_shifted.duration += first;
+        if (out_shifted.independent_min_durations) out_shifted.independent_min_durations += first;
+        out = &out_shifted;
+    }
     rk::Params P;
     rk_status st = fill_params(P, desc, in);
     if (st != RK_OK) return st;
+    P.in_n = stride;
     if (traj->n != desc->n || traj->dof != desc->dof) return fail(RK_ERR_INVALID_ARGUMENT, "trajectories were created for another (n, dof)");
     if (desc->n == 0) return RK_OK;
     RK_CUDA(cudaSetDevice(h->device));
@@ -973,6 +1001,13 @@ rk_status rk_calculate_batch(rk_handle* h, const rk_batch_desc* desc, const rk_b
         for (int k = 1; k < lanes; ++k) RK_CUDA(cudaStreamWaitEvent(h->lane_stream[k], h->ev_fork, 0));
     }
 
+    // the synchronisation stage as warp-level reductions (k_sync_lanes) where its preconditions hold, else the generic kernel
+    bool sync_lanes = desc->dof <= 8 && !P.discrete;
+    for (int d = 0; d < desc->dof; ++d) sync_lanes = sync_lanes && P.sync[d] != RK_SYNC_PHASE;
+    {
+        static const int forced = [] { const char* e = std::getenv("RK_B200_SYNC_KERNEL"); return e ? (e[0] == 'g' ? 1 : 0) : 0; }();
+        if (forced) sync_lanes = false;  // RK_B200_SYNC_KERNEL=generic: A/B and parity of the two kernels against each other
+    }
     // host buffers: per-chunk staging, double buffered
     const rk::Params host_ptrs = P;
     const double* rk::Params::*dslots[11] = {&rk::Params::p0, &rk::Params::v0, &rk::Params::a0, &rk::Params::pf, &rk::Params::vf, &rk::Params::af,
@@ -1026,7 +1061,7 @@ rk_status rk_calculate_batch(rk_handle* h, const rk_batch_desc* desc, const rk_b
             const size_t per = sizeof(double) * (size_t)desc->dof * (size_t)P.cn;
             for (auto m : dslots) {
                 if (!(host_ptrs.*m)) continue;
-                RK_CUDA(cudaMemcpy2DAsync(dev, sizeof(double) * P.cn, host_ptrs.*m + off, sizeof(double) * desc->n, sizeof(double) * P.cn,
+                RK_CUDA(cudaMemcpy2DAsync(dev, sizeof(double) * P.cn, host_ptrs.*m + off, sizeof(double) * stride, sizeof(double) * P.cn,
                                           (size_t)desc->dof, cudaMemcpyHostToDevice, h->copy_stream));
                 P.*m = (const double*)dev;
                 dev += per;
@@ -1037,7 +1072,7 @@ rk_status rk_calculate_batch(rk_handle* h, const rk_batch_desc* desc, const rk_b
                 dev += sizeof(double) * (size_t)P.cn;
             }
             if (host_ptrs.enabled) {
-                RK_CUDA(cudaMemcpy2DAsync(dev, (size_t)P.cn, host_ptrs.enabled + off, (size_t)desc->n, (size_t)P.cn, (size_t)desc->dof,
+                RK_CUDA(cudaMemcpy2DAsync(dev, (size_t)P.cn, host_ptrs.enabled + off, (size_t)stride, (size_t)P.cn, (size_t)desc->dof,
                                           cudaMemcpyHostToDevice, h->copy_stream));
                 P.enabled = (const uint8_t*)dev;
             }
@@ -1084,7 +1119,8 @@ rk_status rk_calculate_batch(rk_handle* h, const rk_batch_desc* desc, const rk_b
         rk_launch(rk::k1_cand_check, grid_list, 128, cs, P);
         rk_launch(rk::k1_block, grid_items, 128, cs, P);
         rk_launch(rk::k1_rescue, (unsigned)h->sm_count, 128, cs, P);
-        rk_launch(rk::k_sync, (unsigned)((P.cn + 127) / 128), 128, cs, P);
+        if (sync_lanes) rk_launch(rk::k_sync_lanes, (unsigned)((P.cn + 31) / 32), 256, cs, P);
+        else rk_launch(rk::k_sync, (unsigned)((P.cn + 127) / 128), 128, cs, P);
         static const int fam[RK_S2_STEPS] = {0, 1, 8, 2, 3, 0, 1, 8, 2, 3, 4, 5, 6, 7, 4, 5, 6, 7};
         static const int dir2[RK_S2_STEPS] = {0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 0, 0, 0, 0, 1, 1, 1, 1};
         // with RK_FUSE_TAIL the last eight stages (families 4-7 in both directions) and k2_fail are one launch (k2_tail)
@@ -1122,7 +1158,7 @@ rk_status rk_calculate_batch(rk_handle* h, const rk_batch_desc* desc, const rk_b
             if (out->duration)
                 RK_CUDA(cudaMemcpyAsync(out->duration + off, traj->duration + off, sizeof(double) * P.cn, cudaMemcpyDeviceToHost, h->d2h_stream));
             if (out->independent_min_durations)
-                RK_CUDA(cudaMemcpy2DAsync(out->independent_min_durations + off, sizeof(double) * desc->n, traj->imd + off, sizeof(double) * desc->n,
+                RK_CUDA(cudaMemcpy2DAsync(out->independent_min_durations + off, sizeof(double) * stride, traj->imd + off, sizeof(double) * desc->n,
                                           sizeof(double) * P.cn, (size_t)desc->dof, cudaMemcpyDeviceToHost, h->d2h_stream));
         }
     }
@@ -1141,9 +1177,57 @@ rk_status rk_calculate_batch(rk_handle* h, const rk_batch_desc* desc, const rk_b
         if (out->status) RK_CUDA(cudaMemcpyAsync(out->status, traj->status, sizeof(int32_t) * desc->n, kind, h->stream));
         if (out->duration) RK_CUDA(cudaMemcpyAsync(out->duration, traj->duration, sizeof(double) * desc->n, kind, h->stream));
         if (out->independent_min_durations)
-            RK_CUDA(cudaMemcpyAsync(out->independent_min_durations, traj->imd, sizeof(double) * desc->n * desc->dof, kind, h->stream));
+            RK_CUDA(cudaMemcpy2DAsync(out->independent_min_durations, sizeof(double) * stride, traj->imd, sizeof(double) * desc->n,
+                                      sizeof(double) * desc->n, (size_t)desc->dof, kind, h->stream));
     }
     if (host) RK_CUDA(cudaStreamSynchronize(h->stream));
+    return RK_OK;
+}
+
+extern "C" {
+
+rk_status rk_calculate_batch(rk_handle* h, const rk_batch_desc* desc, const rk_batch_in* in, rk_trajectories* traj, const rk_batch_out* out) {
+    if (!desc) return fail(RK_ERR_INVALID_ARGUMENT, "desc / in is NULL");
+    return calculate_impl(h, desc, in, traj, out, desc->n, 0);
+}
+
+void rk_shard_range(int64_t n, int32_t parts, int32_t part, int64_t* first, int64_t* count) {
+    const int64_t base = n / parts, rem = n % parts;
+    const int64_t lo = (int64_t)part * base + (part < rem ? part : rem);
+    if (first) *first = lo;
+    if (count) *count = base + (part < rem ? 1 : 0);
+}
+
+rk_status rk_calculate_batch_multi(rk_handle* const* handles, rk_trajectories* const* trajs, int32_t parts, const rk_batch_desc* desc,
+                                   const rk_batch_in* in, const rk_batch_out* out) {
+    if (!handles || !trajs || parts < 1 || !desc || !in) return fail(RK_ERR_INVALID_ARGUMENT, "NULL / empty argument to rk_calculate_batch_multi");
+    if (desc->memory_space != RK_MEM_HOST) return fail(RK_ERR_INVALID_ARGUMENT, "rk_calculate_batch_multi takes host arrays (device memory belongs to one device)");
+    for (int g = 0; g < parts; ++g) {
+        if (!handles[g] || !trajs[g]) return fail(RK_ERR_INVALID_ARGUMENT, "a handle / trajectories entry is NULL");
+        int64_t lo, cnt;
+        rk_shard_range(desc->n, parts, g, &lo, &cnt);
+        if (trajs[g]->n != cnt || trajs[g]->dof != desc->dof) return fail(RK_ERR_INVALID_ARGUMENT, "trajectories[g] must hold rk_shard_range(n, parts, g) trajectories");
+        for (int k = 0; k < g; ++k)
+            if (handles[k] == handles[g]) return fail(RK_ERR_INVALID_ARGUMENT, "every part needs its own handle (a handle is one stream + scratch)");
+    }
+    // one host thread per part: each part stages, computes and returns its own index range; parts on different devices (or on
+    // different handles of one device) overlap completely, there is no exchange between them
+    std::vector<rk_status> result((size_t)parts, RK_OK);
+    std::vector<std::string> message((size_t)parts);
+    std::vector<std::thread> workers;
+    for (int g = 0; g < parts; ++g) {
+        workers.emplace_back([&, g] {
+            int64_t lo, cnt;
+            rk_shard_range(desc->n, parts, g, &lo, &cnt);
+            rk_batch_desc sub = *desc;
+            sub.n = cnt;
+            result[(size_t)g] = cnt > 0 ? calculate_impl(handles[g], &sub, in, trajs[g], out, desc->n, lo) : RK_OK;
+            if (result[(size_t)g] != RK_OK) message[(size_t)g] = g_last_error;
+        });
+    }
+    for (auto& w : workers) w.join();
+    for (int g = 0; g < parts; ++g)
+        if (result[(size_t)g] != RK_OK) return fail(result[(size_t)g], "part " + std::to_string(g) + ": " + message[(size_t)g]);
     return RK_OK;
 }
 

@@ -940,6 +940,232 @@ __global__ void __launch_bounds__(128, RK_SY_MINB) k_sync(const Params P) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------ k_sync_lanes
+// The synchronisation stage as warp-level reductions over the DoFs (the common configuration: at most 8 DoFs, continuous
+// durations, no DoF with Phase synchronisation; everything else runs k_sync above). One lane per (trajectory, DoF), 8 lanes
+// per trajectory, 4 trajectories per warp: every lane holds the block of ITS DoF in registers — t_min, the two blocked
+// intervals, the brake duration — and the trajectory-level decisions of calculator_target.rs:150-275 / :454-550 / :714-747 are
+// ballots and xor-shuffle min / max reductions inside the 8-lane group; nothing is sorted and nothing lives in local memory.
+//
+// Why no sort is needed (continuous durations). The reference sorts the 3 * DOF + 1 candidates (DOF minimum durations, the right
+// ends of the blocked intervals, the minimum duration) stably by value and tests them in order FROM SORTED POSITION DOF - 1.
+// Let T be the largest per-DoF minimum duration. A candidate below T is blocked by the DoF that owns T, so whether the scan
+// starts before or after it changes nothing. Candidates equal to T all share one verdict; of those, the scan skips the first
+// max(0, DOF - 1 - L) in index order (L = candidates below T) — that decides WHICH of several tied candidates is reported as the
+// limiting one. Everything above T is visited in (value, index) order, and equal values again share a verdict. So: one max
+// reduction for T, one count for L, one n-th-set-bit for the tie, then a min reduction per distinct value above T until one
+// is not blocked. With Discrete durations the rounded candidates no longer dominate the raw minimum durations ulp for ulp, so
+// that mode keeps the literal sort of k_sync.
+__device__ __forceinline__ double group_max8(double v) {
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) { const double u = __shfl_xor_sync(0xffffffffu, v, o); v = (u > v) ? u : v; }
+    return v;
+}
+__device__ __forceinline__ double group_min8(double v) {
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) { const double u = __shfl_xor_sync(0xffffffffu, v, o); v = (u < v) ? u : v; }
+    return v;
+}
+__device__ __forceinline__ int group_sum8(int v) {
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__global__ void __launch_bounds__(256, 4) k_sync_lanes(const Params P) {
+    RK_PDL_ENTER();
+    __shared__ uint8_t src_of[8][32];  // the block's 32 trajectories x 8 DoFs, transposed for the DoF-major stores at the end
+    const int lane = threadIdx.x & 31, d = lane & 7, gshift = lane & 24;  // gshift: first lane of this trajectory's group
+    const int64_t il = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    const int D = P.dof;
+    const bool tvalid = il < P.cn, mine = tvalid && d < D;
+    const int64_t wstride = (int64_t)D * P.cn, wi = (int64_t)d * P.cn + il, ig = P.off + il;
+    auto gbyte = [&](bool pred) { return (__ballot_sync(0xffffffffu, pred) >> gshift) & 0xFFu; };
+
+    uint32_t m = 0;
+    double t_min = 0.0, a_left = 0.0, a_right = 0.0, b_left = 0.0, b_right = 0.0, bdur = 0.0;
+    if (mine) {
+        const double* w = P.ws + wi;
+        m = P.wmeta[wi];
+        t_min = w[(int64_t)W_TMIN * wstride]; a_left = w[(int64_t)W_ALEFT * wstride]; a_right = w[(int64_t)W_ARIGHT * wstride];
+        b_left = w[(int64_t)W_BLEFT * wstride]; b_right = w[(int64_t)W_BRIGHT * wstride]; bdur = w[(int64_t)W_BRAKE_DUR * wstride];
+    }
+    const int sync_d = (d < D) ? (int)P.sync[d] : (int)RK_SYNC_NONE;
+    const bool none = sync_d == RK_SYNC_NONE;
+    const bool enabled = mine && (m & M_ENABLED), has_a = (m & M_HAS_A) != 0, has_b = (m & M_HAS_B) != 0;
+    const bool sync_on = mine && !none;  // takes part in candidates and blocking
+
+    int status = RK_RESULT_WORKING, detail = 0, limiting = -1;
+    double duration = 0.0;
+    int src = RK_SRC_NONE;
+
+    // NB: the four trajectories of a warp take different paths, so every ballot / shuffle below is executed unconditionally by
+    // all 32 lanes and only the USE of its result is conditional.
+
+    // Err(ValidationError): first failing DoF (input_parameter.rs:251-420)
+    const uint32_t vc = (m >> M_VCODE_SHIFT) & 0xFFu;
+    const uint32_t vbits = gbyte(mine && vc != 0);
+    const int dfv = vbits ? __ffs(vbits) - 1 : 0;
+    const uint32_t vc_first = __shfl_sync(0xffffffffu, vc, gshift + dfv);
+    if (P.throw_mode && vbits) {
+        status = RK_RESULT_ERROR_INVALID_INPUT;
+        detail = (int)(vc_first << 8) | dfv;
+    }
+    // Step-1 failure: lowest DoF index decides (calculator_target.rs:454-471)
+    const uint32_t fbits = gbyte(enabled && !(m & M_FOUND));
+    const int dff = fbits ? __ffs(fbits) - 1 : 0;
+    const int zl_first = __shfl_sync(0xffffffffu, (int)((m & M_ZERO_LIMITS) != 0), gshift + dff);
+    if (status == 0 && fbits) {
+        status = zl_first ? RK_RESULT_ERROR_ZERO_LIMITS : RK_RESULT_ERROR_EXECUTION_TIME_CALCULATION;
+        detail = (1 << 8) | dff;
+    }
+    const double md_raw = (P.min_dur && tvalid) ? P.min_dur[ig + P.in_shift] : __longlong_as_double(0x7ff8000000000000LL);
+    const bool has_md = md_raw == md_raw;
+    const double md = has_md ? md_raw : 0.0;
+
+    bool done = status != 0;
+    const double t_min_first = __shfl_sync(0xffffffffu, t_min, gshift);
+    if (!done && D == 1 && !has_md) {  // :475-481 (also for a disabled DoF: blocks[0].p_min is copied unconditionally)
+        duration = t_min_first;
+        if (d == 0) src = RK_SRC_STEP1_MIN;
+        done = true;
+    }
+
+    // ---- synchronize (:150-275); every lane of the warp runs the reductions, `done` groups ignore the outcome
+    const double c0 = sync_on ? t_min : (mine ? 0.0 : -RK_INF);  // lanes without a DoF never win a max and are never counted
+    const double c1 = (sync_on && has_a) ? a_right : RK_INF;
+    const double c2 = (sync_on && has_b) ? b_right : RK_INF;
+    const double c3 = has_md ? md : RK_INF;  // candidate 3 * DOF, held by every lane, counted once (lane 0 of the group)
+    const bool any_interval = gbyte(sync_on && (has_a || has_b)) != 0 || has_md;  // idx_end = any_interval ? NC : DOF (:203-215)
+    auto blocked_by_me = [&](double ts) {  // block.rs:157-172
+        return sync_on && (ts < t_min || (has_a && ts > a_left && ts < a_right) || (has_b && ts > b_left && ts < b_right));
+    };
+    auto value_ok = [&](double ts) {  // one verdict per candidate VALUE (:227-240)
+        const bool blocked = gbyte(blocked_by_me(ts)) != 0;
+        return !(blocked || ts < md || isinf(ts));
+    };
+    // bit s * 8 + d = candidate s of DoF d, bit 24 = the minimum duration: bit order == the reference's index order s * DOF + d
+    // (the interval ends and the minimum duration are only in the sorted set when any_interval)
+    auto equal_mask = [&](double v) {
+        const uint32_t e0 = gbyte(mine && c0 == v), e1 = gbyte(mine && c1 == v), e2 = gbyte(mine && c2 == v);
+        return any_interval ? (e0 | (e1 << 8) | (e2 << 16) | ((c3 == v) ? (1u << 24) : 0u)) : e0;
+    };
+    const double T = group_max8(c0);
+    int below = mine && c0 < T;
+    if (any_interval) below += (mine && c1 < T) + (mine && c2 < T) + (d == 0 && c3 < T);
+    const int L = group_sum8(below);
+    int which_bit = -1;
+    double ts = T;
+    {
+        const uint32_t ties = equal_mask(T);
+        const int skip = (D - 1 - L > 0) ? (D - 1 - L) : 0;
+        const bool ok = value_ok(T);
+        if (ok) which_bit = (int)__fns(ties, 0, skip + 1);  // the tie the scan meets first at or after sorted position DOF - 1
+    }
+    {
+        // any_interval: the distinct values above T, ascending. The loop is warp-uniform: a group that is finished (or has no
+        // interval at all) keeps voting with stale values and ignores the results.
+        double cur = T;
+        bool open = any_interval && which_bit < 0;
+        while (__any_sync(0xffffffffu, open)) {
+            double mn = RK_INF;
+            if (mine) {
+                if (c1 > cur && c1 < mn) mn = c1;
+                if (c2 > cur && c2 < mn) mn = c2;
+                if (c0 > cur && c0 < mn) mn = c0;
+            }
+            if (c3 > cur && c3 < mn) mn = c3;
+            mn = group_min8(mn);
+            const bool ok = value_ok(mn);
+            const uint32_t eq = equal_mask(mn);
+            if (open) {
+                if (isinf(mn)) { open = false; }  // only infinite candidates are left: none is ever accepted
+                else if (ok) { which_bit = __ffs(eq) - 1; ts = mn; open = false; }
+                else cur = mn;
+            }
+        }
+    }
+    {
+        // no interval: the tail of the (fresh) index array is zero, so after the DOF sorted minimum durations the scan meets
+        // candidate 0 again and again (Q4)
+        const double first = __shfl_sync(0xffffffffu, c0, gshift);
+        const bool ok = value_ok(first);
+        if (!any_interval && which_bit < 0 && ok) { which_bit = 0; ts = first; }
+    }
+    const bool zero_limits_any = gbyte(mine && (m & M_ZERO_LIMITS)) != 0;
+    const bool all_none = gbyte(mine && !none) == 0;
+
+    if (!done) {
+        if (which_bit < 0) {  // :492-518
+            status = zero_limits_any ? RK_RESULT_ERROR_ZERO_LIMITS : RK_RESULT_ERROR_SYNCHRONIZATION_CALCULATION;
+            detail = 2 << 8;
+            done = true;
+        } else {
+            duration = ts;
+            if (which_bit < 24) {
+                limiting = which_bit & 7;
+                if (d == limiting) src = which_bit >> 3;  // 0 p_min, 1 a.profile, 2 b.profile
+            }
+        }
+    }
+    // None synchronisation (:520-528): in DoF order, a larger minimum duration takes over
+    {
+        const bool none_on = enabled && none;
+        const double tm = none_on ? t_min : -RK_INF;
+        const double tmax = group_max8(tm);
+        const uint32_t at_max = gbyte(none_on && t_min == tmax);
+        if (!done) {
+            if (none_on) src = RK_SRC_STEP1_MIN;
+            if (tmax > duration) { duration = tmax; limiting = __ffs(at_max) - 1; }
+        }
+    }
+    if (!done) {
+        if (duration > 7.6e3) {  // :531-533
+            status = RK_RESULT_ERROR_TRAJECTORY_DURATION;
+            done = true;
+        } else if (fabs(duration - 0.0) < EPS) {  // :535-541: every DoF, disabled ones included
+            src = RK_SRC_STEP1_MIN;
+            done = true;
+        } else if (all_none) {  // :543-550: all DoFs unsynchronised
+            done = true;
+        }
+    }
+    // ---- time synchronisation dispatch (:714-747), one DoF per lane
+    if (!done && enabled && !(d == limiting || none)) {
+        const double t_profile = duration - bdur - 0.0;
+        bool rest = false;
+        if (sync_d == RK_SYNC_TIME_IF_NECESSARY) {
+            const int64_t g = (int64_t)d * P.in_n + (ig + P.in_shift);
+            rest = fabs(P.vf[g]) < EPS && fabs(P.af[g]) < EPS;
+        }
+        // extremal profile re-use; b is only looked at when a is absent (Q3)
+        if (rest || fabs(t_profile - t_min) < 2.0 * EPS) src = RK_SRC_STEP1_MIN;
+        else if (has_a && fabs(t_profile - a_right) < 2.0 * EPS) src = RK_SRC_STEP1_A;
+        else if (!has_a && has_b && fabs(t_profile - b_right) < 2.0 * EPS) src = RK_SRC_STEP1_B;
+        else src = RK_SRC_STEP2;
+    }
+    if (tvalid && d == 0) {
+        P.status[ig] = status;
+        P.duration[ig] = duration;
+        P.limiting[ig] = limiting;
+        P.detail[ig] = detail;
+    }
+    // Per-DoF results leave the block DoF-major — warp w writes DoF w of the block's 32 consecutive trajectories — so that the
+    // chain list keeps runs of consecutive trajectories per DoF like k_sync's (in (trajectory, DoF) order the Step-2 kernels
+    // that walk the list lose the locality of their structure-of-arrays reads: measured -6 % on the whole step).
+    src_of[d][threadIdx.x >> 3] = (uint8_t)((mine ? src : RK_SRC_NONE) | ((mine && (m & M_KIND_MASK) == K_POS3) ? 0x80 : 0));
+    __syncthreads();
+    {
+        const int d2 = threadIdx.x >> 5, t2 = threadIdx.x & 31;
+        const int64_t il2 = (int64_t)blockIdx.x * 32 + t2;
+        const bool mine2 = il2 < P.cn && d2 < D;
+        const uint8_t v = src_of[d2][t2];
+        const uint32_t wi2 = (uint32_t)((int64_t)d2 * P.cn + il2);
+        if (mine2) P.wsrc[wi2] = v & 0x7F;
+        append_unsolved(P.list[0], P.counters + 0, mine2 && v == (0x80 | RK_SRC_STEP2), wi2);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ Step-2 chain
 // The 16 stages of position_third_step2.rs:2449-2482, with the VEL family split into its UDDU and UDUD halves (each half
 // is a pure function of the inputs; UDUD only runs for items the UDDU half did not solve): 18 launches, families

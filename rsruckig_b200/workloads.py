@@ -4,8 +4,10 @@ generalised to any DoF count and to the BASELINE.json configurations.
 Three independent seeded streams, as in the reference (seeds 42 / 43 / 44): positions ~ N(0, 4); velocities /
 accelerations ~ N(0, 0.8) or exactly 0 (current v: p=0.9, current a: 0.8, target v: 0.7, target a: 0.6);
 max_velocity = U(0.1, 12) + |target_velocity|; max_acceleration = U(0.1, 12) + |target_acceleration|;
-max_jerk = U(0.1, 12). The streams are numpy PCG64 (not rand_pcg's Pcg64Mcg + ziggurat: bit-reproducing the Rust
-generators is not required, the same arrays feed the GPU and the oracle). Layout: SoA [dof][n] float64.
+max_jerk = U(0.1, 12). `bench_inputs` draws from numpy PCG64 streams (any seed, vectorised: what the tests and the
+benchmark use); `reference_bench_inputs` is the reference's OWN stream — Pcg64Mcg seeds 42 / 43 / 44 through rand_distr's
+ziggurat Normal and rand's Uniform in the draw order of benchmark_target.rs:137-153 (csrc/refstream.c) — so that a Rust
+build of rsruckig can be run on bit-identical problems (tools/rsruckig_dump). Layout: SoA [dof][n] float64.
 """
 from __future__ import annotations
 
@@ -96,3 +98,42 @@ def edge_case_inputs(n: int, dof: int, *, seed: int = 0) -> dict:
     f["target_acceleration"] = np.clip(f["target_acceleration"], f["min_acceleration"] * 0.98, None)
     f["enabled"] = np.ascontiguousarray((rng.random(shape) > 0.05).astype(np.uint8))
     return {k: np.ascontiguousarray(v) for k, v in f.items()}
+
+
+_REFSTREAM = None
+
+
+def _refstream():
+    """librefstream.so (csrc/refstream.c, host-only C, built by __graft_entry__.build())."""
+    global _REFSTREAM
+    if _REFSTREAM is None:
+        import ctypes as C
+        import os
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "librefstream.so")
+        if not os.path.exists(path):
+            raise RuntimeError(f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`")
+        lib = C.CDLL(path)
+        vp = C.c_void_p
+        lib.refstream_pcg_new_next.argtypes = [C.c_uint64, C.c_uint64, vp, C.c_int32]
+        lib.refstream_pcg_new_next.restype = C.c_uint64
+        lib.refstream_pcg_from_seed_next.argtypes = [vp, vp, C.c_int32]
+        lib.refstream_pcg_seed_from_u64_next.argtypes = [C.c_uint64, vp, C.c_int32]
+        lib.refstream_ziggurat_tables.argtypes = [vp, vp]
+        lib.refstream_normal.argtypes = [C.c_uint64, C.c_double, C.c_double, vp, C.c_int64]
+        lib.refstream_uniform.argtypes = [C.c_uint64, C.c_double, C.c_double, vp, C.c_int64]
+        lib.refstream_bench_inputs.argtypes = [C.c_int64, C.c_int32, vp]
+        _REFSTREAM = lib
+    return _REFSTREAM
+
+
+def reference_bench_inputs(n: int, dof: int = 7) -> dict:
+    """The first n problems of the reference benchmark's own input stream (bench/src/benchmark_target.rs:115-153): three
+    `Pcg64Mcg::seed_from_u64` streams (42 positions, 43 velocities / accelerations, 44 limits), `Normal` by the 256-layer
+    ziggurat, `Uniform` by the 52-bit mantissa method, drawn per problem in the reference's order. Problems the reference skips
+    (validate_input(false, false) fails) are kept: they consumed their draws there too and fail validation on every side."""
+    import ctypes as C
+    lib = _refstream()
+    arrays = [np.zeros((dof, n), dtype=np.float64) for _ in FIELDS]
+    ptrs = (C.c_void_p * len(FIELDS))(*[a.ctypes.data for a in arrays])
+    lib.refstream_bench_inputs(n, dof, ptrs)
+    return dict(zip(FIELDS, arrays))

@@ -98,6 +98,26 @@ def test_ten_million_bench_inputs_match_the_reference_oracle(gpu):
           f"max rel. sampled p/v/a error {worst_pva:.2e} vs glibc oracle; bitwise vs portable oracle")
 
 
+def test_reference_benchmark_stream_first_million(gpu):
+    """The reference benchmark's own inputs (Pcg64Mcg seeds 42 / 43 / 44 + rand_distr, benchmark_target.rs:115-153; restated in
+    csrc/refstream.c and pinned on rand_pcg's known answers): the first 2^20 problems, same bar as the 10 M run."""
+    from test_parity import assert_exact, run_both
+    n, dof = 1 << 20, 7
+    f = workloads.reference_bench_inputs(n, dof)
+    otg, ob = run_both(gpu, f, n, dof, threads=THREADS, result_layout=cabi.RK_RESULT_COMPACT)
+    working = assert_exact(otg, ob, label="reference stream (portable)")
+    assert working > 0.9 * n
+    from oracle.oracle import OracleBatch
+    og = OracleBatch(n, dof, "glibc")
+    og.calculate(f, threads=THREADS)
+    st = og.read(cabi.RK_FIELD_STATUS)
+    assert np.array_equal(otg.read(cabi.RK_FIELD_STATUS), st)
+    ok = st == 0
+    assert not (((otg.read(cabi.RK_FIELD_CODES) ^ og.read(cabi.RK_FIELD_CODES)) & 0xFFFFFF)[:, ok]).any()
+    du, du_g = otg.read(cabi.RK_FIELD_DURATION)[ok], og.read(cabi.RK_FIELD_DURATION)[ok]
+    assert float(np.max(np.abs(du - du_g) / du_g.clip(1e-300))) <= REL
+
+
 def replanned_states(f, ob, n, frac):
     """Inputs whose current state is the state each (Working) trajectory of `ob` passes through at about frac * duration,
     on a grid of 32 sample times accumulated by repeated addition like a control loop would."""

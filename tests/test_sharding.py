@@ -60,3 +60,43 @@ def test_gloo_world_size_2_gather_and_max():
     ref = np.arange(n, dtype=np.float64)
     assert full.shape == (2, n)
     assert np.array_equal(full[0], ref * 2.0) and np.array_equal(full[1], ref + 0.5)
+
+
+def test_shard_range_matches_the_c_abi():
+    """rk_shard_range (the split rk_calculate_batch_multi uses) is the same function as sharding.shard_range."""
+    import ctypes as C
+    from rsruckig_b200 import _cabi as cabi
+    lib = cabi.load()
+    for n, parts in ((0, 1), (1, 2), (7, 2), (64, 8), (1_000_003, 8), (8 << 20, 3)):
+        for g in range(parts):
+            lo, cnt = C.c_int64(-1), C.c_int64(-1)
+            lib.rk_shard_range(n, parts, g, C.byref(lo), C.byref(cnt))
+            assert (lo.value, lo.value + cnt.value) == shard_range(n, g, parts)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("parts", [1, 2, 3])
+def test_multi_handle_batch_equals_single_handle_bitwise(parts):
+    """rk_calculate_batch_multi over every visible device (and, to exercise several parts on a one-GPU box, several handles per
+    device): everything it returns and everything the parts hold equals one rk_calculate_batch bit for bit."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from rsruckig_b200 import BatchRuckig, MultiBatchRuckig, ThrowErrorHandler, workloads, _cabi as cabi
+    n, dof = 300_001, 7
+    f = workloads.bench_inputs(n, dof, seed=51)
+    f["minimum_duration"] = np.where(np.arange(n) % 5 == 0, 6.0, np.nan)
+    f["enabled"] = np.ascontiguousarray((np.random.default_rng(52).random((dof, n)) > 0.03).astype(np.uint8))
+    one = BatchRuckig(dof, 0.005, ThrowErrorHandler)
+    st1, du1, im1 = np.zeros(n, dtype=np.int32), np.zeros(n), np.zeros((dof, n))
+    one.calculate(f, n=n, memory_space=cabi.RK_MEM_HOST, status=st1, duration=du1, independent_min_durations=im1)
+    devices = [g % torch.cuda.device_count() for g in range(max(parts, torch.cuda.device_count()))]
+    multi = MultiBatchRuckig(dof, 0.005, ThrowErrorHandler, devices=devices)
+    st, du, im = np.full(n, 77, dtype=np.int32), np.full(n, -1.0), np.full((dof, n), -1.0)
+    multi.calculate(f, n=n, status=st, duration=du, independent_min_durations=im)
+    assert np.array_equal(st, st1) and np.array_equal(du, du1) and np.array_equal(im, im1)
+    ok = st1 == 0
+    for fld in (cabi.RK_FIELD_T, cabi.RK_FIELD_P, cabi.RK_FIELD_CODES, cabi.RK_FIELD_LIMITING_DOF, cabi.RK_FIELD_BRAKE_T):
+        a, b = multi.read(fld), one.read(fld)
+        assert np.array_equal(a[..., ok], b[..., ok]), fld
+    multi.close()
