@@ -1208,15 +1208,18 @@ __device__ __forceinline__ bool run_family(const S2& s, const Lim& L, Hit& h) {
     return s2_none(s, L, h);
 }
 
-// A solved Step-2 item leaves only its compact solution behind — t[7] and the jerk in block-profile slot 0 of the scratch
-// (unused by third-order position items, whose block profiles are references) and the code word; k_expand integrates it into
-// the full profile arrays later, with full warps and coalesced stores.
+// A solved Step-2 item leaves only its compact solution behind — t[7] and the jerk as ONE 64-byte record in the item's own
+// (no longer needed) candidate area, and the code word; k_expand turns it into the stored result later, with full warps and
+// coalesced stores. (Round 1 kept the eight doubles in structure-of-arrays rows: eight partially filled sectors per item
+// whenever the work list does not run over consecutive items.)
 __device__ __forceinline__ void put_solution(const Params& P, const ItemS2& it, int64_t wstride, const Hit& h) {
-    double* base = P.ws + (int64_t)W_CAND * wstride + it.wi;
-#pragma unroll
-    for (int k = 0; k < 7; ++k) base[(int64_t)k * wstride] = h.t[k];
-    base[7 * wstride] = h.jf;
+    double2* rec = reinterpret_cast<double2*>(P.vl + it.wi * VL_ITEM_DOUBLES + V_SOL);
+    rec[0] = make_double2(h.t[0], h.t[1]);
+    rec[1] = make_double2(h.t[2], h.t[3]);
+    rec[2] = make_double2(h.t[4], h.t[5]);
+    rec[3] = make_double2(h.t[6], h.jf);
     P.codes[it.gi] = pack_codes(h.lim, h.cs, h.dir, RK_SRC_STEP2);
+    (void)wstride;
 }
 
 template <int F>
@@ -1607,10 +1610,10 @@ __global__ void __launch_bounds__(128, RK_EX_MINB) k_expand(const Params P) {
         int lim, cs, dir, lim_check, store_kind = kind;
         bool pf_from_p7 = false, ok = true;
         if (src == RK_SRC_STEP2 && kind == K_POS3) {  // solved by a stage of the chain (put_solution)
-            const double* base = P.ws + (int64_t)W_CAND * wstride + wi;
-#pragma unroll
-            for (int k = 0; k < 7; ++k) t[k] = base[(int64_t)k * wstride];
-            ctrl = base[7 * wstride];
+            const double2* rec = reinterpret_cast<const double2*>(P.vl + wi * VL_ITEM_DOUBLES + V_SOL);
+            const double2 r0 = rec[0], r1 = rec[1], r2 = rec[2], r3 = rec[3];
+            t[0] = r0.x; t[1] = r0.y; t[2] = r1.x; t[3] = r1.y; t[4] = r2.x; t[5] = r2.y; t[6] = r3.x;
+            ctrl = r3.y;
             ctrl2 = 0.0;
             const uint32_t c = P.codes[it.gi];
             lim = c & 0xFF; cs = (c >> 8) & 0xFF; dir = (c >> 16) & 0xFF;

@@ -29,7 +29,8 @@ enum : int { W_P0 = 0, W_V0 = 1, W_A0 = 2, W_TMIN = 3, W_ALEFT = 4, W_ARIGHT = 5
              VL_SLOTS = 36, VL_SLOT_DOUBLES = 8, VL_ITEM_DOUBLES = 36 * 8 };
 // Step 2, VEL family: a chain item re-uses its own (no longer needed) sub-list area for the polynomial, the root brackets and
 // the polished roots that travel between the scan, polish and check kernels (double offsets into the item's vl area).
-enum : int { V_POL = 0, V_LO = 8, V_HI = 16, V_ROOT = 24, V_TZ = 32, V1_LO = 40, V1_HI = 48, V1_ROOT = 56 };
+enum : int { V_POL = 0, V_LO = 8, V_HI = 16, V_ROOT = 24, V_TZ = 32, V1_LO = 40, V1_HI = 48, V1_ROOT = 56,
+             V_SOL = 64 };  // the compact Step-2 solution of the item, t[7] + jerk: one 64-byte record (put_solution)
 // meta words per item: [0] flags below, [1..3] codes of the three block profiles
 enum : int { WM_META = 0, WM_CAND = 1, WM_WORDS = 4 };
 enum : uint32_t { M_KIND_MASK = 0xFu, M_FOUND = 1u << 4, M_HAS_A = 1u << 5, M_HAS_B = 1u << 6, M_S1_PENDING = 1u << 7, M_ZERO_LIMITS = 1u << 8,
