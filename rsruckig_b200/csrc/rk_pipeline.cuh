@@ -232,13 +232,13 @@ __global__ void __launch_bounds__(128, RK_CC_MINB) k1_closed_cands(const Params 
     int ds = 0;
     int64_t wi = 0;
     if (tid < 2 * wstride) {
-        ds = (int)(tid / wstride);
-        wi = tid - (int64_t)ds * wstride;
+        ds = (int)(tid & 1);  // the two directions of an item sit in adjacent lanes: its 96-byte record is fetched once
+        wi = tid >> 1;
         const uint32_t meta = P.wmeta[(int64_t)WM_META * wstride + wi];
+        Bound b;
+        double bdur_;
+        const DofIn x = load_rec(P, wi, b, bdur_);  // before the test of meta: two independent loads instead of a dependent pair
         if (meta & M_S1_PENDING) {
-            Bound b;
-            double bdur_;
-            const DofIn x = load_rec(P, wi, b, bdur_);
             bool rest_target, trivial;
             const Lim L = family_limits(x, b, ds, rest_target, trivial);
             if (PART != 1) P.wqmask[(int64_t)(6 + ds) * wstride + wi] = 0u;
@@ -308,13 +308,13 @@ __global__ void __launch_bounds__(128, RK_MIN_BLOCKS) k1_quartic_roots(const Par
     int ds = 0;
     int64_t wi = 0;
     if (tid < 2 * wstride) {
-        ds = (int)(tid / wstride);
-        wi = tid - (int64_t)ds * wstride;
+        ds = (int)(tid & 1);  // the two directions of an item sit in adjacent lanes: its 96-byte record is fetched once
+        wi = tid >> 1;
         const uint32_t meta = P.wmeta[(int64_t)WM_META * wstride + wi];
+        Bound b;
+        double bdur_;
+        const DofIn x = load_rec(P, wi, b, bdur_);  // before the test of meta: two independent loads instead of a dependent pair
         if (meta & M_S1_PENDING) {
-            Bound b;
-            double bdur_;
-            const DofIn x = load_rec(P, wi, b, bdur_);
             bool rest_target, trivial;
             const Lim L = family_limits(x, b, ds, rest_target, trivial);
             P.wqmask[(int64_t)(TYPE * 2 + ds) * wstride + wi] = 0u;
@@ -488,12 +488,12 @@ __global__ void __launch_bounds__(128, 4) k1_block(const Params P) {
     bool rescue = false;
     if (wi < wstride) {
         uint32_t meta = P.wmeta[(int64_t)WM_META * wstride + wi];
+        Bound b;
+        double bdur;
+        const DofIn x = load_rec(P, wi, b, bdur);  // before the test of meta: independent loads
         if (meta & M_S1_PENDING) {
             const int d = (int)(wi / P.cn);
             const int64_t ig = P.off + (wi - (int64_t)d * P.cn);
-            Bound b;
-            double bdur;
-            const DofIn x = load_rec(P, wi, b, bdur);
             const double pf = b.pf, vf = b.vf, af = b.af, p0 = b.p0, v0 = b.v0, a0 = b.a0;
             const double pd = pf - p0;
             const bool rest_target = fabs(vf) < EPS && fabs(af) < EPS;
