@@ -350,8 +350,34 @@ def run_b200(args):
             dist.barrier()
             dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
         assert bool((h_status == status[:n_e].cpu()).all()), "host-buffer and device-buffer runs disagree"
+        # what the box's host path can feed: every rank copies pinned host memory to its GPU at the same time (1 GiB x 4); the
+        # end-to-end rate cannot exceed what the SLOWEST rank's copy rate allows (the timing is a max over ranks)
+        probe_h = torch.empty(1 << 30, dtype=torch.uint8, pin_memory=True)
+        probe_d = torch.empty(1 << 30, dtype=torch.uint8, device=dev)
+        probe_d.copy_(probe_h, non_blocking=True)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record()
+        for _ in range(4):
+            probe_d.copy_(probe_h, non_blocking=True)
+        p1.record()
+        torch.cuda.synchronize()
+        h2d_gbs = 4 * (1 << 30) / (p0.elapsed_time(p1) * 1e-3) / 1e9
+        t_sum = torch.tensor([h2d_gbs], dtype=torch.float64, device=dev)
+        t_min = t_sum.clone()
+        if world > 1:
+            dist.all_reduce(t_sum, op=dist.ReduceOp.SUM)
+            dist.all_reduce(t_min, op=dist.ReduceOp.MIN)
+        del probe_h, probe_d
+        in_bytes = sum(v.numel() * v.element_size() for v in hf.values())
+        host_path = {"h2d_pinned_gbs_aggregate": float(t_sum.item()), "h2d_pinned_gbs_slowest_rank": float(t_min.item()),
+                     "ceiling": world * n_e / (in_bytes / (float(t_min.item()) * 1e9)), "unit": UNIT,
+                     "note": "all ranks copying pinned host memory to their GPUs concurrently; ceiling = trajectories/s if the step were nothing "
+                             "but the slowest rank's input copy (504 B per trajectory)"}
         e2e = {"value": n_e * world * k_e2e / float(t_e.item()), "unit": UNIT, "steps": k_e2e, "n_per_gpu": n_e,
-               "h2d_bytes_per_step": int(sum(v.numel() * v.element_size() for v in hf.values())), "host_binding": binding,
+               "h2d_bytes_per_step": int(sum(v.numel() * v.element_size() for v in hf.values())), "host_binding": binding, "host_path": host_path,
                "d2h_bytes_per_step": int(h_status.numel() * 4 + h_duration.numel() * 8),
                "note": "rk_calculate_batch with RK_MEM_HOST on pinned buffers; status + duration (12 B per trajectory) come back, the trajectories "
                        "themselves stay device-resident for rk_at_time_batch / the query helpers — a host consumer that wants every Profile pays "
