@@ -1008,6 +1008,9 @@ static rk_status calculate_impl(rk_handle* h, const rk_batch_desc* desc, const r
         static const int forced = [] { const char* e = std::getenv("RK_B200_SYNC_KERNEL"); return e ? (e[0] == 'g' ? 1 : 0) : 0; }();
         if (forced) sync_lanes = false;  // RK_B200_SYNC_KERNEL=generic: A/B and parity of the two kernels against each other
     }
+    // position interface on every DoF: the lean set-up kernel (third-order items inline, the rest queued for k1_rescue)
+    bool setup_lean = true;
+    for (int d = 0; d < desc->dof; ++d) setup_lean = setup_lean && P.ci[d] == RK_POSITION;
     // host buffers: per-chunk staging, double buffered
     const rk::Params host_ptrs = P;
     const double* rk::Params::*dslots[11] = {&rk::Params::p0, &rk::Params::v0, &rk::Params::a0, &rk::Params::pf, &rk::Params::vf, &rk::Params::af,
@@ -1102,7 +1105,8 @@ static rk_status calculate_impl(rk_handle* h, const rk_batch_desc* desc, const r
             RK_CUDA(cudaMemsetAsync(c.pend, 0xFF, sizeof(uint32_t) * it, cs));
         }
         RK_CUDA(cudaMemsetAsync(c.counters, 0, sizeof(uint32_t) * RK_N_COUNTERS, cs));
-        rk_launch(rk::k1_setup, grid_items, 128, cs, P);
+        if (setup_lean) rk_launch(rk::k1_setup_lean, grid_items, 128, cs, P);
+        else rk_launch(rk::k1_setup, grid_items, 128, cs, P);
         const unsigned grid_fam = (unsigned)((2 * items + 127) / 128);
         rk_launch(rk::k1_quartic_roots<0>, grid_fam, 128, cs, P);
         rk_launch(rk::k1_quartic_check<0>, grid_list, 128, cs, P);
@@ -1118,7 +1122,7 @@ static rk_status calculate_impl(rk_handle* h, const rk_batch_desc* desc, const r
 #endif
         rk_launch(rk::k1_cand_check, grid_list, 128, cs, P);
         rk_launch(rk::k1_block, grid_items, 128, cs, P);
-        rk_launch(rk::k1_rescue, (unsigned)h->sm_count, 128, cs, P);
+        rk_launch(rk::k1_rescue, (unsigned)h->sm_count * 4u, 128, cs, P);
         if (sync_lanes) rk_launch(rk::k_sync_lanes, (unsigned)((P.cn + 31) / 32), 256, cs, P);
         else rk_launch(rk::k_sync, (unsigned)((P.cn + 127) / 128), 128, cs, P);
         static const int fam[RK_S2_STEPS] = {0, 1, 8, 2, 3, 0, 1, 8, 2, 3, 4, 5, 6, 7, 4, 5, 6, 7};
@@ -1148,7 +1152,8 @@ static rk_status calculate_impl(rk_handle* h, const rk_batch_desc* desc, const r
 #else
         rk_launch(rk::k2_fail, (unsigned)h->sm_count, 128, cs, P);
 #endif
-        rk_launch(rk::k_expand, grid_items, 128, cs, P);
+        if (P.compact) rk_launch(rk::k_expand_compact, grid_items, 128, cs, P);
+        else rk_launch(rk::k_expand, grid_items, 128, cs, P);
         h->launches += 14 + RK_CC_SPLIT + n_steps;  // fused tail: k2_tail stands in for k2_fail
         if (host) RK_CUDA(cudaEventRecord(h->ev_computed[chunk_index % RK_STAGE_BUFS], cs));
         if (d2h_per_chunk) {

@@ -89,11 +89,7 @@ __device__ __forceinline__ void append_unsolved(uint32_t* list, uint32_t* counte
 #ifndef RK_SU_MINB
 #define RK_SU_MINB 4
 #endif
-__global__ void __launch_bounds__(128, RK_SU_MINB) k1_setup(const Params P) {
-    RK_PDL_ENTER();
-    const int64_t wstride = (int64_t)P.dof * P.cn;
-    const int64_t wi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (wi >= wstride) return;
+__device__ __forceinline__ void setup_item(const Params& P, int64_t wi, int64_t wstride) {
     const int d = (int)(wi / P.cn);
     const int64_t il = wi - (int64_t)d * P.cn;
     const int64_t ig = P.off + il;
@@ -186,6 +182,79 @@ __global__ void __launch_bounds__(128, RK_SU_MINB) k1_setup(const Params P) {
     out.put(S_BRAKE_V, bv0); out.put(S_BRAKE_V + 1, bv1);
     out.put(S_BRAKE_P, bp0); out.put(S_BRAKE_P + 1, bp1);
     out.put(S_PF, pf_store); out.put(S_VF, vf_store); out.put(S_AF, af_store);
+}
+
+__global__ void __launch_bounds__(128, RK_SU_MINB) k1_setup(const Params P) {
+    RK_PDL_ENTER();
+    const int64_t wstride = (int64_t)P.dof * P.cn;
+    const int64_t wi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (wi >= wstride) return;
+    setup_item(P, wi, wstride);
+}
+
+// k1_setup for the case almost every item of a position-interface batch is: an enabled third-order DoF with non-zero limits
+// that passes validation (or is not validated: ignoring handler). Only that path is compiled in — validation, the third-order
+// brake pre-trajectory, the packed record — so the kernel runs at 8 blocks per SM instead of k1_setup's 4 (128 registers for
+// the solver variants it carries). Every other item (disabled, invalid under the throwing handler, zero or infinite limits)
+// is marked "not pending", so that the family kernels pass over it, and queued; k1_rescue runs the general setup_item on
+// the queue before k_sync needs its block.
+__global__ void __launch_bounds__(128, 8) k1_setup_lean(const Params P) {
+    RK_PDL_ENTER();
+    const int64_t wstride = (int64_t)P.dof * P.cn;
+    const int64_t wi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool other = false;
+    if (wi < wstride) {
+        const int d = (int)(wi / P.cn);
+        const int64_t il = wi - (int64_t)d * P.cn;
+        const int64_t ig = P.off + il;
+        const DofIn x = load_dof(P, d, ig);
+        const int ci = P.ci[d];
+        const int vcode = validate_dof(x, ci, false, true);  // Ruckig::calculate validates with (false, true), ruckig.rs:215
+        const int kind = kind_of(ci, x.a_max, x.j_max);
+        other = !(kind == K_POS3 && x.enabled && (vcode == 0 || !P.throw_mode) && !(x.j_max == 0.0 || x.a_max == 0.0 || x.a_min == 0.0));
+        if (other) {
+            P.wmeta[(int64_t)WM_META * wstride + wi] = 0u;  // not pending: quartic / closed-form / block kernels skip the item
+        } else {
+            // brake pre-trajectory (calculator_target.rs:330-387, brake.rs:195-220)
+            Brake br;
+            br.t[0] = 0.0; br.t[1] = 0.0; br.j[0] = 0.0; br.j[1] = 0.0; br.a0 = 0.0;
+            position_brake(br, x.v0, x.a0, x.v_max, x.v_min, x.a_max, x.a_min, x.j_max);
+            const double bt0 = br.t[0], bt1 = br.t[1], bj0 = br.j[0], bj1 = br.j[1];
+            double bdur = 0.0, ba0 = 0.0, ba1 = 0.0, bv0 = 0.0, bv1 = 0.0, bp0 = 0.0, bp1 = 0.0;
+            double ps = x.p0, vs = x.v0, as = x.a0;
+            if (!(bt0 <= 0.0 && bt1 <= 0.0)) {
+                bdur = bt0;
+                bp0 = ps; bv0 = vs; ba0 = as;
+                integrate(bt0, ps, vs, as, bj0, ps, vs, as);
+                if (bt1 > 0.0) {
+                    bdur += bt1;
+                    bp1 = ps; bv1 = vs; ba1 = as;
+                    integrate(bt1, ps, vs, as, bj1, ps, vs, as);
+                }
+            }
+            double* w = P.ws + wi;
+            w[(int64_t)W_P0 * wstride] = ps; w[(int64_t)W_V0 * wstride] = vs; w[(int64_t)W_A0 * wstride] = as;
+            w[(int64_t)W_BRAKE_DUR * wstride] = bdur;
+            store_rec(P, wi, ps, vs, as, x, bdur);
+            P.wmeta[(int64_t)WM_META * wstride + wi] = (uint32_t)K_POS3 | ((uint32_t)vcode << M_VCODE_SHIFT) | M_ENABLED | M_S1_PENDING;
+            ProfileSink out{P.prof, (int64_t)P.dof * P.n, (int64_t)d * P.n + ig};
+            if (P.compact) {
+                out.put(C_P0, x.p0); out.put(C_V0, x.v0); out.put(C_A0, x.a0);
+                out.put(C_BRAKE_T, bt0); out.put(C_BRAKE_T + 1, bt1);
+                out.put(C_BRAKE_J, bj0); out.put(C_BRAKE_J + 1, bj1);
+                out.put(C_PF, x.pf); out.put(C_VF, x.vf); out.put(C_AF, x.af);
+            } else {
+                out.put(S_BRAKE_DUR, bdur);
+                out.put(S_BRAKE_T, bt0); out.put(S_BRAKE_T + 1, bt1);
+                out.put(S_BRAKE_J, bj0); out.put(S_BRAKE_J + 1, bj1);
+                out.put(S_BRAKE_A, ba0); out.put(S_BRAKE_A + 1, ba1);
+                out.put(S_BRAKE_V, bv0); out.put(S_BRAKE_V + 1, bv1);
+                out.put(S_BRAKE_P, bp0); out.put(S_BRAKE_P + 1, bp1);
+                out.put(S_PF, x.pf); out.put(S_VF, x.vf); out.put(S_AF, x.af);
+            }
+        }
+    }
+    append_unsolved(P.list[1], P.counters + 25, other, (uint32_t)wi);
 }
 
 // warp-aggregated append of a variable number of entries per lane; returns the lane's first index
@@ -596,11 +665,17 @@ __global__ void __launch_bounds__(128, 4) k1_block(const Params P) {
     append_unsolved(P.list[0], P.counters + 24, rescue, (uint32_t)wi);
 }
 
+__device__ __noinline__ void setup_item_rare(const Params& P, int64_t wi, int64_t wstride) { setup_item(P, wi, wstride); }
+
 // Numerical rescues (:1142-1255) for the rare items none of the regular families produced a candidate for; the first rescue
 // that yields one wins.
 __global__ void __launch_bounds__(128) k1_rescue(const Params P) {
     RK_PDL_ENTER();
     const int64_t wstride = (int64_t)P.dof * P.cn;
+    // the items k1_setup_lean passed over (the counter stays zero when the general k1_setup ran): complete set-up, including
+    // the Step 1 of the cheap variants
+    const uint32_t n_other = P.counters[25];
+    for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < n_other; e += gridDim.x * blockDim.x) setup_item_rare(P, P.list[1][e], wstride);
     const uint32_t n_items = P.counters[24];
     for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < n_items; e += gridDim.x * blockDim.x) {
         const int64_t wi = P.list[0][e];
@@ -1568,7 +1643,7 @@ __global__ void __launch_bounds__(128) k2_fail(const Params P) {
 // full 256-byte rows. The cheap non-third-order Step 2 variants are solved right here.
 #define RK_SRC_FAILED 0xFF
 #ifndef RK_EX_MINB
-#define RK_EX_MINB 1
+#define RK_EX_MINB 4  // 128 registers, no spills: 162 -> 144 us per 300 k-trajectory chunk against the unconstrained 168
 #endif
 __global__ void __launch_bounds__(128, RK_EX_MINB) k_expand(const Params P) {
     RK_PDL_ENTER();
@@ -1658,5 +1733,80 @@ __global__ void __launch_bounds__(128, RK_EX_MINB) k_expand(const Params P) {
     }
 }
 
+
+// k_expand for the compact result layout (RK_RESULT_COMPACT): nothing is integrated, the decided t[7] and control values are
+// copied into the record next to what k1_setup already stored (boundary states, brake, target). The common sources need
+// neither the item's 96-byte record nor its inputs: a Step-2 solution is one 64-byte read (put_solution), a re-used Step-1
+// profile is its candidate slot plus the jerk limit. Same decisions and code words as k_expand.
+__global__ void __launch_bounds__(128, 8) k_expand_compact(const Params P) {
+    RK_PDL_ENTER();
+    const int64_t wstride = (int64_t)P.dof * P.cn;
+    const int64_t wi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (wi >= wstride) return;
+    const uint32_t meta = P.wmeta[(int64_t)WM_META * wstride + wi];
+    const int src = P.wsrc[wi];
+    const int kind = meta & M_KIND_MASK;
+    const int d = (int)(wi / P.cn);
+    const int64_t ig = P.off + (wi - (int64_t)d * P.cn);
+    const int64_t gi = (int64_t)d * P.n + ig;
+    ProfileSink out{P.prof, (int64_t)P.dof * P.n, gi};
+    if (src == RK_SRC_NONE || kind == K_NONE) {  // disabled DoF (calculator_target.rs:313-323) or an error status
+        out.put(C_META, compact_meta(kind, kind, CM_IDLE_STATE, false, false, UDDU));
+        P.codes[gi] = pack_codes(L_NONE, UDDU, DIR_UP, RK_SRC_NONE);
+        return;
+    }
+    if (!(meta & M_ENABLED)) {  // a disabled DoF the reference overwrites with its block's (default) p_min
+        out.put(C_META, compact_meta(kind, kind, CM_IDLE_ZERO, false, false, UDDU));
+        P.codes[gi] = pack_codes(L_NONE, UDDU, DIR_UP, src);
+        return;
+    }
+    if (src == RK_SRC_FAILED) {  // the chain has set the status and the code word
+        out.put(C_META, compact_meta(kind, kind, CM_IDLE_ZERO, false, false, UDDU));
+        return;
+    }
+    double t[7], ctrl, ctrl2 = 0.0;
+    int lim, cs, dir, lim_check, store_kind = kind;
+    bool pf_from_p7 = false, ok = true;
+    if (src == RK_SRC_STEP2 && kind == K_POS3) {  // solved by a stage of the chain (put_solution)
+        const double2* rec = reinterpret_cast<const double2*>(P.vl + wi * VL_ITEM_DOUBLES + V_SOL);
+        const double2 r0 = rec[0], r1 = rec[1], r2 = rec[2], r3 = rec[3];
+        t[0] = r0.x; t[1] = r0.y; t[2] = r1.x; t[3] = r1.y; t[4] = r2.x; t[5] = r2.y; t[6] = r3.x;
+        ctrl = r3.y;
+        const uint32_t c = P.codes[gi];
+        lim = c & 0xFF; cs = (c >> 8) & 0xFF; dir = (c >> 16) & 0xFF;
+        lim_check = lim;
+    } else if (src == RK_SRC_STEP2) {  // the cheap non-third-order Step 2 variants are solved right here
+        const ItemS2 it = load_item_s2(P, wi, wstride);
+        Cand c;
+        if (kind == K_POS2) { ok = step2_pos2(it.b, it.tf, it.x.v_max, it.x.v_min, it.x.a_max, it.x.a_min, c); pf_from_p7 = true; }
+        else if (kind == K_POS1) ok = step2_pos1(it.b, it.tf, c);
+        else if (kind == K_VEL3) { ok = step2_vel3(it.b, it.tf, it.x.a_max, it.x.a_min, it.x.j_max, c); pf_from_p7 = true; }
+        else { ok = step2_vel2(it.b, it.tf, it.x.a_max, it.x.a_min, c); pf_from_p7 = true; }
+        copy_t(t, c.t);
+        ctrl = c.ctrl; ctrl2 = c.ctrl2; lim = c.lim; cs = c.cs; dir = c.dir;
+        lim_check = lim;
+    } else {
+        const int slot = (src == RK_SRC_PHASE) ? 2 : src;
+        uint32_t c;
+        ws_get_cand(P, wi, wstride, slot, P.rec[wi * 6 + 5].x, t, ctrl, ctrl2, c);  // [5].x = j_max
+        lim = c & 0xFF; cs = (c >> 8) & 0xF; dir = (c >> 16) & 0x7F;
+        lim_check = lim;
+        if (src == RK_SRC_PHASE) {  // validated with ReachedLimits::None, labelled with the limiting DoF's limits (Q25)
+            lim_check = L_NONE;
+            store_kind = (int)((c >> 12) & 0xFu) - 1;
+        }
+    }
+    if (ok) {
+#pragma unroll
+        for (int i = 0; i < 7; ++i) out.put(C_T + i, t[i]);
+        out.put(C_CTRL, ctrl); out.put(C_CTRL2, ctrl2);
+        out.put(C_META, compact_meta(kind, store_kind, CM_PROFILE, forces_a3_zero(lim_check), pf_from_p7, cs));
+        P.codes[gi] = pack_codes(lim, cs, dir, src);
+    } else {
+        report_step2_failure(P, d, ig);
+        out.put(C_META, compact_meta(kind, kind, CM_IDLE_ZERO, false, false, UDDU));
+        P.codes[gi] = pack_codes(L_NONE, UDDU, DIR_UP, RK_SRC_STEP2);
+    }
+}
 
 }  // namespace rk
