@@ -512,7 +512,7 @@ def run_b200(args):
                              "frac": achieved_tflops / fp64_peak_tflops if fp64_peak_tflops else None,
                              "traffic": (ops.get("dram_bytes_per_trajectory") or 0) * n or None,
                              "traffic_note": f"dram__bytes_read.sum + dram__bytes_write.sum over the {ops.get('kernel_launches_per_step', '?')} kernel launches of one step "
-                                             "(ncu, profiles/r1_ops_per_kernel.csv), per GPU; = "
+                                             "(ncu, profiles/r2_ops_per_kernel.csv), per GPU; = "
                                              f"{(ops.get('dram_bytes_per_trajectory') or 0) * per_gpu / 1e9:.0f} GB/s at the measured rate",
                              "kernels": "one step per chunk of 4Mi (DoF, trajectory) items = k1_setup, 3 x (k1_quartic_roots, k1_quartic_check), "
                                         "k1_closed_cands, k1_cand_check, k1_block, k1_rescue, k_sync, 10 chain stages (k2_stage<F>; VEL/UDDU as "

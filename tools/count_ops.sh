@@ -1,7 +1,7 @@
 #!/bin/bash
 # FP64 operations, thread instructions and DRAM bytes per 7-DoF trajectory of one calculate step (run under gpurun).
 # Writes gpurun_out/ops_<tag>.csv (ncu launch list) and gpurun_out/algorithmic_ops.json.
-TAG=${1:-r1}
+TAG=${1:-r2}
 N=262144
 python bench.py --n $N --steps 1 --warmup 1 --no-e2e --no-cpu --no-extras > /dev/null 2>&1 || exit 1
 ncu --metrics smsp__sass_thread_inst_executed_op_dadd_pred_on.sum,smsp__sass_thread_inst_executed_op_dmul_pred_on.sum,smsp__sass_thread_inst_executed_op_dfma_pred_on.sum,smsp__thread_inst_executed.sum,dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum \
@@ -18,8 +18,8 @@ for r in rows:
     if len(r) == len(hdr) and r[0].isdigit() and any(t in r[ki] for t in ("k1_", "k2_", "k_sync", "k_expand")):
         launches.setdefault(int(r[ii]), {"name": r[ki]})[r[mi]] = float(r[vi].replace(",", "")) * mult.get(r[ui], 1)
 ids = sorted(launches)
-n_steps = sum(1 for i in ids if "k1_setup" in launches[i]["name"])   # one chunk per step at this size
-per_step = len(ids) // n_steps    # warm-up steps + timed step, identical launch sequences
+n_steps = 4                       # bench.py runs at least 3 warm-up steps + the timed step, identical launch sequences
+per_step = len(ids) // n_steps    # (a batch of this size is computed as two halves on two streams: both are in the step)
 step = [launches[i] for i in ids[-per_step:]]
 s = lambda m: sum(l.get(m, 0.0) for l in step)
 dadd, dmul, dfma = (s(f"smsp__sass_thread_inst_executed_op_{o}_pred_on.sum") for o in ("dadd", "dmul", "dfma"))
