@@ -252,11 +252,18 @@ fn engine(device: i32) -> Result<*mut sys::rk_handle, RuckigError> {
 
 /// Device-resident trajectories of one batch (`Vec<Trajectory<DOF>>`, trajectory.rs:14-21).
 struct Trajectories { t: *mut sys::rk_trajectories, h: *mut sys::rk_handle, n: usize, dof: usize }
+
+/// What stays on the device per (DoF, trajectory): the reference's `Profile` verbatim (59 doubles) or the 20 doubles the
+/// calculation decided; every reader returns identical values either way (ruckig_b200.h, RK_RESULT_*).
+#[derive(Clone, Copy, Debug, PartialEq, Eq)]
+pub enum ResultLayout { Full = sys::RK_RESULT_FULL as isize, Compact = sys::RK_RESULT_COMPACT as isize }
+
 impl Trajectories {
-    fn new(h: *mut sys::rk_handle, n: usize, dof: usize) -> Result<Self, RuckigError> {
+    fn new(h: *mut sys::rk_handle, n: usize, dof: usize) -> Result<Self, RuckigError> { Self::with_layout(h, n, dof, ResultLayout::Full) }
+    fn with_layout(h: *mut sys::rk_handle, n: usize, dof: usize, layout: ResultLayout) -> Result<Self, RuckigError> {
         let mut t = ptr::null_mut();
         // SAFETY: valid handle and out-pointer.
-        check(unsafe { sys::rk_trajectories_create(h, n as i64, dof as i32, &mut t) })?;
+        check(unsafe { sys::rk_trajectories_create_ex(h, n as i64, dof as i32, layout as i32, &mut t) })?;
         Ok(Self { t, h, n, dof })
     }
     fn read_i32(&self, field: i32, len: usize) -> Result<Vec<i32>, RuckigError> {
@@ -270,6 +277,64 @@ impl Drop for Trajectories {
     fn drop(&mut self) {
         // SAFETY: created by rk_trajectories_create and destroyed exactly once; its handle lives as long as the thread.
         unsafe { sys::rk_trajectories_destroy(self.t) };
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------ MultiBatchRuckig
+/// One host batch over several CUDA devices (`rk_calculate_batch_multi`): contiguous index ranges (`rk_shard_range`), one
+/// handle per entry of `devices`, the parts run concurrently inside the library and gather status / duration into the
+/// caller's vectors. north_star: "sharded trivially across the 8 GPUs of one box with no collectives beyond a final host gather".
+pub struct MultiBatchRuckig<const DOF: usize> {
+    pub degrees_of_freedom: usize,
+    pub delta_time: f64,
+    layout: ResultLayout,
+    handles: Vec<*mut sys::rk_handle>,
+    parts: Vec<Trajectories>,
+    n: usize,
+}
+
+impl<const DOF: usize> MultiBatchRuckig<DOF> {
+    pub fn new(dofs: Option<usize>, delta_time: f64, devices: &[i32], layout: ResultLayout) -> Result<Self, RuckigError> {
+        let mut handles = Vec::new();
+        for &d in devices {
+            let mut h = ptr::null_mut();
+            // SAFETY: `h` is a valid out-pointer; every part owns its own handle (a handle is one stream + scratch).
+            check(unsafe { sys::rk_create(d, &mut h) })?;
+            handles.push(h);
+        }
+        Ok(Self { degrees_of_freedom: dofs.unwrap_or(DOF), delta_time, layout, handles, parts: Vec::new(), n: usize::MAX })
+    }
+
+    /// `Ruckig::calculate` for every problem; `status[i]` is the `RuckigResult` value (-100 = `Err(ValidationError)` under the
+    /// throwing semantics the library is asked for here).
+    pub fn calculate(&mut self, input: &BatchInput<DOF>, status: &mut Vec<i32>, durations: &mut Vec<f64>) -> Result<(), RuckigError> {
+        let (n, d, g) = (input.n, input.degrees_of_freedom, self.handles.len());
+        if n != self.n {
+            self.parts.clear();
+            for (k, &h) in self.handles.iter().enumerate() {
+                let (mut first, mut count) = (0i64, 0i64);
+                // SAFETY: plain arithmetic on the two out-pointers.
+                unsafe { sys::rk_shard_range(n as i64, g as i32, k as i32, &mut first, &mut count) };
+                self.parts.push(Trajectories::with_layout(h, count as usize, d, self.layout)?);
+            }
+            self.n = n;
+        }
+        status.resize(n, 0);
+        durations.resize(n, 0.0);
+        let (mut ci, mut sy) = (Vec::new(), Vec::new());
+        let (desc, inp) = input.as_ffi(self.delta_time, sys::RK_ERRORS_THROW, &mut ci, &mut sy);
+        let out = sys::rk_batch_out { status: status.as_mut_ptr(), duration: durations.as_mut_ptr(), independent_min_durations: ptr::null_mut() };
+        let trajs: Vec<*mut sys::rk_trajectories> = self.parts.iter().map(|p| p.t).collect();
+        // SAFETY: `handles` and `trajs` have `g` live entries each; desc / inp / out point to live host buffers of the documented sizes.
+        check(unsafe { sys::rk_calculate_batch_multi(self.handles.as_ptr(), trajs.as_ptr(), g as i32, &desc, &inp, &out) })
+    }
+}
+
+impl<const DOF: usize> Drop for MultiBatchRuckig<DOF> {
+    fn drop(&mut self) {
+        self.parts.clear();
+        // SAFETY: created by rk_create above, destroyed exactly once, after the trajectories that refer to them.
+        for &h in &self.handles { unsafe { sys::rk_destroy(h) }; }
     }
 }
 

@@ -495,8 +495,10 @@ public:
     size_t degrees_of_freedom;
     double delta_time;
 
-    explicit BatchRuckig(double delta_time_, std::optional<size_t> dofs = std::nullopt, int32_t device = 0)
-        : degrees_of_freedom(detail::resolve_dofs(DOF, dofs)), delta_time(delta_time_), handle_(detail::Engine::get(device).h) {}
+    // result_layout: RK_RESULT_FULL keeps the reference's Profile per DoF on the device (59 doubles), RK_RESULT_COMPACT the 20
+    // doubles the calculation decided; every reader (at_time, read, the query helpers) returns identical values either way
+    explicit BatchRuckig(double delta_time_, std::optional<size_t> dofs = std::nullopt, int32_t device = 0, int32_t result_layout = RK_RESULT_FULL)
+        : degrees_of_freedom(detail::resolve_dofs(DOF, dofs)), delta_time(delta_time_), handle_(detail::Engine::get(device).h), layout_(result_layout) {}
     ~BatchRuckig() { if (traj_) rk_trajectories_destroy(traj_); }
     BatchRuckig(const BatchRuckig&) = delete;
     BatchRuckig& operator=(const BatchRuckig&) = delete;
@@ -556,7 +558,7 @@ private:
         if (traj_ && n_ == n) return;
         if (traj_) rk_trajectories_destroy(traj_);
         traj_ = nullptr;
-        detail::check(rk_trajectories_create(handle_, n, (int32_t)degrees_of_freedom, &traj_));
+        detail::check(rk_trajectories_create_ex(handle_, n, (int32_t)degrees_of_freedom, layout_, &traj_));
         n_ = n;
     }
     rk_batch_desc make_desc(int64_t n, const BatchSettings& s, std::vector<int32_t>& ci, std::vector<int32_t>& sy) const {
@@ -580,8 +582,82 @@ private:
         return d;
     }
     rk_handle* handle_;
+    int32_t layout_ = RK_RESULT_FULL;
     rk_trajectories* traj_ = nullptr;
     int64_t n_ = 0;
+};
+
+// ------------------------------------------------------------------------------------------------------------ MultiBatchRuckig
+// One HOST batch over several devices (rk_calculate_batch_multi): part g = the contiguous index range rk_shard_range(n, G, g) on
+// its own handle, all parts concurrently (one host thread each inside the library), status / duration / independent minimum
+// durations gathered into the caller's arrays. `devices` may name a device more than once. north_star: "sharded trivially
+// across the 8 GPUs of one box with no collectives beyond a final host gather".
+template <size_t DOF, class E = ThrowErrorHandler>
+class MultiBatchRuckig {
+public:
+    size_t degrees_of_freedom;
+    double delta_time;
+
+    MultiBatchRuckig(double delta_time_, const std::vector<int32_t>& devices, std::optional<size_t> dofs = std::nullopt, int32_t result_layout = RK_RESULT_COMPACT)
+        : degrees_of_freedom(detail::resolve_dofs(DOF, dofs)), delta_time(delta_time_), layout_(result_layout) {
+        for (int32_t d : devices) {
+            rk_handle* h = nullptr;
+            detail::check(rk_create(d, &h));
+            handles_.push_back(h);
+        }
+    }
+    ~MultiBatchRuckig() {
+        for (rk_trajectories* t : trajs_) rk_trajectories_destroy(t);
+        for (rk_handle* h : handles_) rk_destroy(h);
+    }
+    MultiBatchRuckig(const MultiBatchRuckig&) = delete;
+    MultiBatchRuckig& operator=(const MultiBatchRuckig&) = delete;
+
+    size_t parts() const { return handles_.size(); }
+    rk_handle* handle(size_t g) const { return handles_[g]; }
+    rk_trajectories* trajectories(size_t g) const { return trajs_[g]; }  // part g holds trajectories rk_shard_range(n, parts(), g)
+
+    void calculate(int64_t n, const rk_batch_in& in, BatchSettings settings = {}, int32_t* status = nullptr, double* duration = nullptr,
+                   double* independent_min_durations = nullptr) {
+        if (n != n_) {
+            for (rk_trajectories* t : trajs_) rk_trajectories_destroy(t);
+            trajs_.clear();
+            for (size_t g = 0; g < handles_.size(); ++g) {
+                int64_t first = 0, count = 0;
+                rk_shard_range(n, (int32_t)handles_.size(), (int32_t)g, &first, &count);
+                rk_trajectories* t = nullptr;
+                detail::check(rk_trajectories_create_ex(handles_[g], count, (int32_t)degrees_of_freedom, layout_, &t));
+                trajs_.push_back(t);
+            }
+            n_ = n;
+        }
+        rk_batch_desc d{};
+        d.n = n;
+        d.dof = (int32_t)degrees_of_freedom;
+        d.control_interface = (int32_t)settings.control_interface;
+        d.synchronization = (int32_t)settings.synchronization;
+        d.duration_discretization = (int32_t)settings.duration_discretization;
+        d.error_mode = E::throws ? RK_ERRORS_THROW : RK_ERRORS_IGNORE;
+        d.memory_space = RK_MEM_HOST;
+        d.delta_time = delta_time;
+        std::vector<int32_t> ci, sy;
+        if (settings.per_dof_control_interface) {
+            for (ControlInterface c : *settings.per_dof_control_interface) ci.push_back((int32_t)c);
+            d.per_dof_control_interface = ci.data();
+        }
+        if (settings.per_dof_synchronization) {
+            for (Synchronization c : *settings.per_dof_synchronization) sy.push_back((int32_t)c);
+            d.per_dof_synchronization = sy.data();
+        }
+        rk_batch_out out{status, duration, independent_min_durations};
+        detail::check(rk_calculate_batch_multi(handles_.data(), trajs_.data(), (int32_t)handles_.size(), &d, &in, &out));
+    }
+
+private:
+    int32_t layout_;
+    std::vector<rk_handle*> handles_;
+    std::vector<rk_trajectories*> trajs_;
+    int64_t n_ = -1;
 };
 
 // ------------------------------------------------------------------------------------------------------------ BatchRollout

@@ -169,6 +169,21 @@ static void test_batch_matches_single() {
         }
     }
     CHECK(batch.error_message(0).empty());
+
+    // the compact result layout and the multi-handle entry (two handles on device 0) return the same bits
+    BatchRuckig<2, ThrowErrorHandler> compact(0.005, std::nullopt, 0, RK_RESULT_COMPACT);
+    std::vector<int32_t> status_c(n, -1);
+    std::vector<double> duration_c(n, 0.0), pos_c(3 * D * n), t_full(7 * D * n), t_compact(7 * D * n);
+    compact.calculate(n, in, {}, status_c.data(), duration_c.data());
+    compact.at_time(0.0, 0.1, 3, false, pos_c.data());
+    batch.read(RK_FIELD_T, t_full.data());
+    compact.read(RK_FIELD_T, t_compact.data());
+    CHECK(status_c == status && duration_c == duration && pos_c == pos && t_compact == t_full);
+    MultiBatchRuckig<2, ThrowErrorHandler> multi(0.005, {0, 0});
+    std::vector<int32_t> status_m(n, -1);
+    std::vector<double> duration_m(n, 0.0);
+    multi.calculate(n, in, {}, status_m.data(), duration_m.data());
+    CHECK(multi.parts() == 2 && status_m == status && duration_m == duration);
 }
 
 // Never called: instantiates the device-buffer classes so that the whole header is compiled under -Wall -Wextra -Werror (their
