@@ -10,8 +10,9 @@ default batch is BASELINE.json configs[4] sharded over 8 GPUs (64 Mi / 8 = 8 Mi 
 is fixed as N grows ("weak" scaling); trajectories are independent, ranks never exchange data.
 
 value  = trajectories/s, inputs and outputs resident in HBM, CUDA events on the library's stream, max over ranks.
-e2e    = the same through the C ABI with HOST buffers (pinned): H2D of the nine input arrays, the three kernels, D2H of
-         status + duration — all inside the timed region.
+e2e    = the same through the C ABI with HOST buffers (pinned): H2D of the nine input arrays, the kernel pipeline, D2H of
+         status + duration — all inside the timed region; `e2e.host_path` = what the box's host path can feed (all ranks copying
+         pinned memory at once).
 roofline: the path is FP64-pipe bound, so `bound` is "fp64": achieved = ALGORITHMIC FP64 operations per
          trajectory (profiles/algorithmic_ops_oracle.json: the oracle compiled with a counting scalar, add/sub/mul/div/sqrt/libm
          call = 1 each, tools/count_algorithmic_ops.py) x trajectories/s; `executed` beside it = the FP64 flop the kernels
@@ -514,10 +515,10 @@ def run_b200(args):
                              "traffic_note": f"dram__bytes_read.sum + dram__bytes_write.sum over the {ops.get('kernel_launches_per_step', '?')} kernel launches of one step "
                                              "(ncu, profiles/r2_ops_per_kernel.csv), per GPU; = "
                                              f"{(ops.get('dram_bytes_per_trajectory') or 0) * per_gpu / 1e9:.0f} GB/s at the measured rate",
-                             "kernels": "one step per chunk of 4Mi (DoF, trajectory) items = k1_setup, 3 x (k1_quartic_roots, k1_quartic_check), "
-                                        "k1_closed_cands, k1_cand_check, k1_block, k1_rescue, k_sync, 10 chain stages (k2_stage<F>; VEL/UDDU as "
-                                        "k2_vel_scan_uddu + k2_polish + k2_vel_check_uddu, VEL/UDUD as k2_vel<8>), k2_tail (the last 8 stages), k_expand; no single kernel "
-                                        "holds more than 13 % of the step (profiles/r1_ncu_summary.md), so the roofline is quoted for the whole step",
+                             "kernels": "one step per chunk of 4Mi (DoF, trajectory) items = k1_setup_lean, 3 x (k1_quartic_roots, k1_quartic_check), "
+                                        "k1_closed_cands, k1_cand_check, k1_block, k1_rescue, k_sync_lanes, 10 chain stages (k2_stage<F>; VEL/UDDU as "
+                                        "k2_vel_scan_uddu + k2_polish + k2_vel_check_uddu, VEL/UDUD as k2_vel<8>), k2_tail (the last 8 stages), k_expand_compact; no single "
+                                        "kernel holds more than 14 % of the step (profiles/r2_ncu_summary.md), so the roofline is quoted for the whole step",
                              "flop_per_trajectory": flop, "flop_how": flop_how,
                              "executed": {"flop_per_trajectory": xflop, "achieved": xflop * per_gpu / 1e12, "unit": "TFLOP/s",
                                           "frac": xflop * per_gpu / 1e12 / fp64_peak_tflops if fp64_peak_tflops else None, "how": xflop_how},

@@ -1087,7 +1087,10 @@ static rk_status calculate_impl(rk_handle* h, const rk_batch_desc* desc, const r
         const int64_t items = P.cn * P.dof;
         const unsigned grid_items = (unsigned)((items + 127) / 128);
         // list-driven stages: a few resident waves per SM, grid-stride over the (device-side) list length
-        unsigned grid_list = (unsigned)h->sm_count * 16u;
+#ifndef RK_LIST_WAVES
+#define RK_LIST_WAVES 16
+#endif
+        unsigned grid_list = (unsigned)h->sm_count * (unsigned)RK_LIST_WAVES;
         if (grid_list > grid_items) grid_list = grid_items;
         const unsigned grid_vel = (grid_list * 128u + RK_LS_BLOCK - 1u) / RK_LS_BLOCK;
         if (poison_scratch()) {  // debugging aid (RK_B200_POISON=1): no kernel may depend on what an earlier call left behind
