@@ -399,6 +399,7 @@ __device__ __forceinline__ void sample_once(const double* q, int64_t st, double 
 }
 
 // One control cycle of every environment: time += delta_time, at_time, pass_to_input, Working / Finished (ruckig.rs:292-321).
+template <bool COMPACT>  // trajectory layout (rollouts keep the full layout; the compact instantiation carries the expansion)
 __global__ void __launch_bounds__(256) k_upd_step(const StepParams T) {
     const int64_t total = (int64_t)T.dof * T.n;
     const int64_t gi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -424,8 +425,8 @@ __global__ void __launch_bounds__(256) k_upd_step(const StepParams T) {
     time += T.delta_time;
     const double duration = T.duration[i];
     double p, v, a, j;
-    if (T.compact) {
-        double local[PROFILE_SLOTS];
+    if (COMPACT) {
+        double local[COMPACT ? PROFILE_SLOTS : 1];
         load_compact_profile(T.prof, gi, total, local);
         sample_once(local, 1, duration, time, p, v, a, j);
     } else {
@@ -1518,7 +1519,8 @@ rk_status rk_update_batch(rk_handle* h, const rk_batch_desc* desc, const rk_batc
     }
     T.new_p = out->new_position; T.new_v = out->new_velocity; T.new_a = out->new_acceleration; T.new_j = out->new_jerk;
     T.result = out->result; T.new_calc = out->new_calculation; T.time_user = out->time;
-    rk::k_upd_step<<<(unsigned)((n * dof + 255) / 256), 256, 0, h->stream>>>(T);
+    if (T.compact) rk::k_upd_step<true><<<(unsigned)((n * dof + 255) / 256), 256, 0, h->stream>>>(T);
+    else rk::k_upd_step<false><<<(unsigned)((n * dof + 255) / 256), 256, 0, h->stream>>>(T);
     h->launches += 1;
     r->time_cur ^= 1;
     RK_CUDA(cudaGetLastError());

@@ -85,6 +85,15 @@ __device__ __forceinline__ void append_unsolved(uint32_t* list, uint32_t* counte
     if (unsolved) list[base + __popc(mask & ((1u << lane) - 1u))] = item;
 }
 
+// The five bits of a pending third-order item that k1_block decides on (instead of re-reading the item's record there)
+__device__ __forceinline__ uint32_t block_bits(double ps, double vs, double as, const DofIn& x) {
+    const double pd = x.pf - ps;
+    const bool rest_target = fabs(x.vf) < EPS && fabs(x.af) < EPS;
+    const bool trivial = rest_target && fabs(vs) < EPS && fabs(as) < EPS && fabs(pd) < EPS;
+    return (rest_target ? M_REST_TARGET : 0u) | (trivial ? M_TRIVIAL : 0u) | ((pd >= 0.0) ? M_PD_NONNEG : 0u)
+           | ((x.v_max > 0.0) ? M_VMAX_POS : 0u) | ((x.v_min > 0.0) ? M_VMIN_POS : 0u);
+}
+
 // ------------------------------------------------------------------------------------------------ k1_setup
 #ifndef RK_SU_MINB
 #define RK_SU_MINB 4
@@ -144,7 +153,7 @@ __device__ __forceinline__ void setup_item(const Params& P, int64_t wi, int64_t 
 
         const Bound b{ps, vs, as, x.pf, x.vf, x.af};
         if (kind == K_POS3 && !(x.j_max == 0.0 || x.a_max == 0.0 || x.a_min == 0.0)) {
-            meta |= M_S1_PENDING;  // the three family kernels and k1_block take over
+            meta |= M_S1_PENDING | block_bits(ps, vs, as, x);  // the three family kernels and k1_block take over
         } else {
             switch (kind) {
                 case K_POS3: found = step1_pos3_zero_limits(b, x.v_max, x.v_min, x.a_max, x.a_min, x.j_max, bdur, blk); break;
@@ -236,7 +245,8 @@ __global__ void __launch_bounds__(128, 8) k1_setup_lean(const Params P) {
             w[(int64_t)W_P0 * wstride] = ps; w[(int64_t)W_V0 * wstride] = vs; w[(int64_t)W_A0 * wstride] = as;
             w[(int64_t)W_BRAKE_DUR * wstride] = bdur;
             store_rec(P, wi, ps, vs, as, x, bdur);
-            P.wmeta[(int64_t)WM_META * wstride + wi] = (uint32_t)K_POS3 | ((uint32_t)vcode << M_VCODE_SHIFT) | M_ENABLED | M_S1_PENDING;
+            P.wmeta[(int64_t)WM_META * wstride + wi] =
+                (uint32_t)K_POS3 | ((uint32_t)vcode << M_VCODE_SHIFT) | M_ENABLED | M_S1_PENDING | block_bits(ps, vs, as, x);
             ProfileSink out{P.prof, (int64_t)P.dof * P.n, (int64_t)d * P.n + ig};
             if (P.compact) {
                 out.put(C_P0, x.p0); out.put(C_V0, x.v0); out.put(C_A0, x.a0);
@@ -557,22 +567,17 @@ __global__ void __launch_bounds__(128, 4) k1_block(const Params P) {
     bool rescue = false;
     if (wi < wstride) {
         uint32_t meta = P.wmeta[(int64_t)WM_META * wstride + wi];
-        Bound b;
-        double bdur;
-        const DofIn x = load_rec(P, wi, b, bdur);  // before the test of meta: independent loads
+        const double bdur = P.ws[(int64_t)W_BRAKE_DUR * wstride + wi];  // with the five bits of meta: all this kernel needs of the record
         if (meta & M_S1_PENDING) {
             const int d = (int)(wi / P.cn);
             const int64_t ig = P.off + (wi - (int64_t)d * P.cn);
-            const double pf = b.pf, vf = b.vf, af = b.af, p0 = b.p0, v0 = b.v0, a0 = b.a0;
-            const double pd = pf - p0;
-            const bool rest_target = fabs(vf) < EPS && fabs(af) < EPS;
-            const bool trivial = rest_target && fabs(v0) < EPS && fabs(a0) < EPS && fabs(pd) < EPS;
+            const bool rest_target = (meta & M_REST_TARGET) != 0, trivial = (meta & M_TRIVIAL) != 0;
             // direction slot 0 is UP for general items and sign(pd) for rest-target items; the Direction label of a profile
             // follows the sign of the direction-resolved v_max (profile.rs), the control value follows `up`
-            const double v_max = x.v_max, v_min = x.v_min;
-            const bool up0 = rest_target ? (pd >= 0.0) : true;
-            const int tag_slot0 = ((((up0 ? v_max : v_min) > 0.0) ? DIR_UP : DIR_DOWN) << 16) | ((up0 ? 1 : 0) << 24);
-            const int tag_slot1 = ((((up0 ? v_min : v_max) > 0.0) ? DIR_UP : DIR_DOWN) << 16) | ((up0 ? 0 : 1) << 24);
+            const bool vmax_pos = (meta & M_VMAX_POS) != 0, vmin_pos = (meta & M_VMIN_POS) != 0;
+            const bool up0 = rest_target ? ((meta & M_PD_NONNEG) != 0) : true;
+            const int tag_slot0 = (((up0 ? vmax_pos : vmin_pos) ? DIR_UP : DIR_DOWN) << 16) | ((up0 ? 1 : 0) << 24);
+            const int tag_slot1 = (((up0 ? vmin_pos : vmax_pos) ? DIR_UP : DIR_DOWN) << 16) | ((up0 ? 0 : 1) << 24);
 
             // byte k of a sub-list's mask word says whether slot k holds a validated candidate
             uint32_t qmask[10];
@@ -1749,6 +1754,10 @@ __global__ void __launch_bounds__(128, 8) k_expand_compact(const Params P) {
     const int d = (int)(wi / P.cn);
     const int64_t ig = P.off + (wi - (int64_t)d * P.cn);
     const int64_t gi = (int64_t)d * P.n + ig;
+    // the common source (a Step-2 solution) is read before `src` is known: independent loads instead of a dependent chain
+    const double2* sol = reinterpret_cast<const double2*>(P.vl + wi * VL_ITEM_DOUBLES + V_SOL);
+    const double2 r0 = sol[0], r1 = sol[1], r2 = sol[2], r3 = sol[3];
+    const uint32_t code_in = P.codes[gi];
     ProfileSink out{P.prof, (int64_t)P.dof * P.n, gi};
     if (src == RK_SRC_NONE || kind == K_NONE) {  // disabled DoF (calculator_target.rs:313-323) or an error status
         out.put(C_META, compact_meta(kind, kind, CM_IDLE_STATE, false, false, UDDU));
@@ -1768,11 +1777,9 @@ __global__ void __launch_bounds__(128, 8) k_expand_compact(const Params P) {
     int lim, cs, dir, lim_check, store_kind = kind;
     bool pf_from_p7 = false, ok = true;
     if (src == RK_SRC_STEP2 && kind == K_POS3) {  // solved by a stage of the chain (put_solution)
-        const double2* rec = reinterpret_cast<const double2*>(P.vl + wi * VL_ITEM_DOUBLES + V_SOL);
-        const double2 r0 = rec[0], r1 = rec[1], r2 = rec[2], r3 = rec[3];
         t[0] = r0.x; t[1] = r0.y; t[2] = r1.x; t[3] = r1.y; t[4] = r2.x; t[5] = r2.y; t[6] = r3.x;
         ctrl = r3.y;
-        const uint32_t c = P.codes[gi];
+        const uint32_t c = code_in;
         lim = c & 0xFF; cs = (c >> 8) & 0xFF; dir = (c >> 16) & 0xFF;
         lim_check = lim;
     } else if (src == RK_SRC_STEP2) {  // the cheap non-third-order Step 2 variants are solved right here

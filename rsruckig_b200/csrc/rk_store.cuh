@@ -34,7 +34,11 @@ enum : int { V_POL = 0, V_LO = 8, V_HI = 16, V_ROOT = 24, V_TZ = 32, V1_LO = 40,
 // meta words per item: [0] flags below, [1..3] codes of the three block profiles
 enum : int { WM_META = 0, WM_CAND = 1, WM_WORDS = 4 };
 enum : uint32_t { M_KIND_MASK = 0xFu, M_FOUND = 1u << 4, M_HAS_A = 1u << 5, M_HAS_B = 1u << 6, M_S1_PENDING = 1u << 7, M_ZERO_LIMITS = 1u << 8,
-                  M_ENABLED = 1u << 9, M_VCODE_SHIFT = 16 };
+                  M_ENABLED = 1u << 9,
+                  // what k1_block needs of a pending item's 96-byte record, as five bits (set by the set-up kernels): target at
+                  // rest, nothing moves at all, pf >= p0 (post-brake), the signs of the velocity limits
+                  M_REST_TARGET = 1u << 10, M_TRIVIAL = 1u << 11, M_PD_NONNEG = 1u << 12, M_VMAX_POS = 1u << 13, M_VMIN_POS = 1u << 14,
+                  M_VCODE_SHIFT = 16 };
 
 struct ProfileSink {
     double* prof;  // base of the trajectory storage
