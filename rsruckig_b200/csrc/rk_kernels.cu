@@ -71,6 +71,9 @@ struct SampleParams {
 #ifndef RK_AT_STORE
 #define RK_AT_STORE __stcs
 #endif
+#ifndef RK_AT_MINB
+#define RK_AT_MINB 0
+#endif
 // Reader side of the two trajectory layouts: the full Profile is read in place (row stride dof * n); a compact record
 // (RK_RESULT_COMPACT, rk_store.cuh) is expanded once per thread into a 59-double local array (stride 1) by the same
 // operations that fill the full layout, so every reader below sees bit-identical values either way.
@@ -112,7 +115,7 @@ __device__ __forceinline__ double div6(double a) {
 // x - 0.0 == x for every x, so an absent offset is a zero. ncu on the previous form of this loop: 128 warp instructions
 // per sample, 75 % of the issue slots — it was issue-bound at 5.1 TB/s; this form needs about a third of that.
 template <bool PVA_ONLY, bool COMPACT>
-__global__ void __launch_bounds__(RK_AT_BLOCK, COMPACT ? 7 : 0) k_at_time(const SampleParams S) {
+__global__ void __launch_bounds__(RK_AT_BLOCK, COMPACT ? 7 : RK_AT_MINB) k_at_time(const SampleParams S) {
     const int64_t total = (int64_t)S.dof * S.n;
     const int64_t gi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gi >= total) return;
@@ -130,13 +133,14 @@ __global__ void __launch_bounds__(RK_AT_BLOCK, COMPACT ? 7 : 0) k_at_time(const 
     const double bt0 = q[(int64_t)S_BRAKE_T * st];
     const double bsub = (bdur > 0.0) ? bdur : 0.0;  // the reference subtracts bdur only if it is positive
     const double end_off = bdur + ts6;
-    const double ts0 = q[(int64_t)(S_TSUM + 0) * st];
+    // all seven t_sum in registers: the phase search used to walk t_sum[index] with one dependent global load per step,
+    // zero-length phases included (ncu: 6.8 warp-cycles of long_scoreboard per issued instruction). Prefetching the start state
+    // of the next phase as well was measured and changes nothing: the kernel is bound by the DRAM write stream by now.
+    double ts[7];
+#pragma unroll
+    for (int r = 0; r < 6; ++r) ts[r] = q[(int64_t)(S_TSUM + r) * st];
+    ts[6] = ts6;
     const double INF = RK_INF;
-
-    // profile phase `index` ("first i with t_sum[i] > t", default 6, trajectory.rs:134-140; only grows while time grows)
-    int index = 0;
-    double t_hi = ts0;   // t_sum[index]
-    double lsub = 0.0;   // t_sum[index - 1] if index > 0 (else nothing is subtracted: 0.0)
 
     // current segment: offsets, limits (h_lim = -inf: no segment, the next sample runs the general search), start state
     double A = 0.0, B = 0.0, d_lim = INF, t_lim = INF, h_lim = -INF;
@@ -166,7 +170,7 @@ __global__ void __launch_bounds__(RK_AT_BLOCK, COMPACT ? 7 : 0) k_at_time(const 
 #pragma unroll 1
     for (int k = k_begin; k < k_end; ++k) {
         time += dt;
-        if (!PVA_ONLY && S.rewind) { h_lim = -INF; index = 0; t_hi = ts0; lsub = 0.0; }  // Trajectory::at_time is order-independent
+        if (!PVA_ONLY && S.rewind) h_lim = -INF;  // Trajectory::at_time is order-independent: every sample runs the general search
         double td = time - A;
         double t0 = td - B;
         const bool stay = !(time >= d_lim) & !(td >= t_lim) & (h_lim > td);
@@ -201,11 +205,16 @@ __global__ void __launch_bounds__(RK_AT_BLOCK, COMPACT ? 7 : 0) k_at_time(const 
                         sp = p7; sv = v7; sa = a7; sj = 0.0;
                         B = ts6; t_lim = INF; h_lim = INF;
                     } else {
-                        while (index < 6 && !(t_hi > td)) {
-                            ++index;
-                            lsub = t_hi;
-                            t_hi = q[(int64_t)(S_TSUM + index) * st];
-                        }
+                        // "first i with t_sum[i] > t", default 6 (trajectory.rs:134-140)
+                        int index = 6;
+#pragma unroll
+                        for (int r = 5; r >= 0; --r) if (ts[r] > td) index = r;
+                        double t_hi = ts[6];  // t_sum[index]
+                        double lsub = 0.0;    // t_sum[index - 1] if index > 0 (else nothing is subtracted: 0.0)
+#pragma unroll
+                        for (int r = 0; r < 6; ++r) if (index == r) t_hi = ts[r];
+#pragma unroll
+                        for (int r = 1; r < 7; ++r) if (index == r) lsub = ts[r - 1];
                         t0 = td - lsub;
                         sp = q[(int64_t)(S_P + index) * st]; sv = q[(int64_t)(S_V + index) * st];
                         sa = q[(int64_t)(S_A + index) * st]; sj = q[(int64_t)(S_J + index) * st];
@@ -1303,14 +1312,24 @@ rk_status rk_at_time_batch(rk_handle* h, const rk_trajectories* traj, const rk_s
     // 1000 cycles runs at 3.1 TB/s unsliced, 2.4 TB/s in slices of 50).
     int64_t slices = (300000 + total - 1) / total;
     if (slices < 1) slices = 1;
-    {   // ... and a few slices more when that evens out the last wave of blocks (64 Ki x 7 DoF alone is 1.5 waves of 2048
-        // threads per SM): pick the slice count whose last wave is fullest, charging 1.5 % per extra slice for the re-read
-        const double wave = (double)h->sm_count * 2048.0;
+    const bool pva_only = dev[0] && dev[1] && dev[2] && !dev[3] && !dsec && !S.rewind;
+    const bool compact = traj->layout == RK_RESULT_COMPACT;
+    void (*kern)(const rk::SampleParams) = compact ? (pva_only ? rk::k_at_time<true, true> : rk::k_at_time<false, true>)
+                                                   : (pva_only ? rk::k_at_time<true, false> : rk::k_at_time<false, false>);
+    {   // ... and a few slices more when that evens out the last wave of blocks (64 Ki x 7 DoF alone is four waves and a
+        // sliver): pick the slice count whose last wave is fullest, charging 2 % per extra slice for the re-read (measured on
+        // 64 Ki x 7 x 1000: 5.45 / 5.61 / 5.64 / 5.61 / 5.55 / 5.47 TB/s with 1 / 2 / 3 / 4 / 6 / 8 slices)
+        static int resident[4] = {0, 0, 0, 0};  // blocks per SM of the four instantiations
+        int& blocks_per_sm = resident[(compact ? 2 : 0) + (pva_only ? 1 : 0)];
+        if (blocks_per_sm == 0) {
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, RK_AT_BLOCK, 0) != cudaSuccess || blocks_per_sm < 1) blocks_per_sm = 6;
+        }
+        const double wave = (double)h->sm_count * (double)blocks_per_sm * (double)RK_AT_BLOCK;
         double best = -1.0;
         int64_t best_s = slices;
         for (int64_t sl = slices; sl <= slices + 7; ++sl) {
             const double waves = (double)total * (double)sl / wave;
-            const double eff = waves / (double)(int64_t)(waves + 0.999999) - 0.015 * (double)(sl - slices);
+            const double eff = waves / (double)(int64_t)(waves + 0.999999) - 0.02 * (double)(sl - slices);
             if (eff > best + 1e-9) { best = eff; best_s = sl; }
         }
         slices = best_s;
@@ -1333,14 +1352,7 @@ rk_status rk_at_time_batch(rk_handle* h, const rk_trajectories* traj, const rk_s
             t = t + desc->delta_time;
         }
     }
-    const bool pva_only = S.pos && S.vel && S.acc && !S.jerk && !S.section && !S.rewind;
-    if (traj->layout == RK_RESULT_COMPACT) {
-        if (pva_only) rk::k_at_time<true, true><<<grid, RK_AT_BLOCK, 0, h->stream>>>(S);
-        else rk::k_at_time<false, true><<<grid, RK_AT_BLOCK, 0, h->stream>>>(S);
-    } else {
-        if (pva_only) rk::k_at_time<true, false><<<grid, RK_AT_BLOCK, 0, h->stream>>>(S);
-        else rk::k_at_time<false, false><<<grid, RK_AT_BLOCK, 0, h->stream>>>(S);
-    }
+    kern<<<grid, RK_AT_BLOCK, 0, h->stream>>>(S);
     h->launches += 1;
     RK_CUDA(cudaGetLastError());
     if (host) {
