@@ -37,7 +37,7 @@ struct Bound {
 
 // util.rs:27-33
 __device__ __forceinline__ void integrate(double t, double p0, double v0, double a0, double j, double& p, double& v, double& a) {
-    p = p0 + t * (v0 + t * (a0 / 2.0 + sdiv(t * j, 6.0)));
+    p = p0 + t * (v0 + t * (a0 / 2.0 + div6(t * j)));
     v = v0 + t * (a0 + t * j / 2.0);
     a = a0 + t * j;
 }
@@ -100,7 +100,7 @@ __device__ __forceinline__ bool check_pos3_body(double t0, double t1, double t2,
         const double tj = t[i] * j[i];
         a[i + 1] = a[i] + tj;
         v[i + 1] = v[i] + t[i] * (a[i] + tj / 2.0);
-        p = p + t[i] * (v[i] + t[i] * (a[i] / 2.0 + ((i & 1) ? tj : sdiv(tj, 6.0))));
+        p = p + t[i] * (v[i] + t[i] * (a[i] / 2.0 + ((i & 1) ? tj : div6(tj))));
 
         if (i == 2 && zero_a3) a[3] = 0.0;
 
@@ -549,6 +549,58 @@ __device__ __forceinline__ double poly_eval(const double (&c)[N], double x) {
     return result;
 }
 
+// Several polynomials at ONE point: poly_eval walks the powers 1, x, x * x, ... by repeated multiplication whatever the
+// polynomial, so polynomials evaluated at the same x (f and f' of a Newton step; the quintic, its derivative and second
+// derivative at an extremum) share them — the same products in the same order, hence the same bits as separate poly_eval
+// calls, at N - 2 multiplications and one pair of range tests less per extra polynomial. (The compiler does not find this
+// itself: the products sit behind each call's own x ~ 0 / x ~ 1 branches.)
+template <int M>
+struct PolyPoint {
+    double xn[M];
+    bool zero, one;
+    __device__ __forceinline__ explicit PolyPoint(double x) {
+        zero = fabs(x) < EPS;
+        one = fabs(x - 1.0) < EPS;
+        double p = 1.0;
+#pragma unroll
+        for (int k = 0; k < M; ++k) { xn[k] = p; p *= x; }
+    }
+    template <int N>
+    __device__ __forceinline__ double eval(const double (&c)[N]) const {
+        static_assert(N <= M, "PolyPoint holds too few powers");
+        double result = 0.0;
+        if (zero) {
+            result = c[N - 1];
+        } else if (one) {
+#pragma unroll
+            for (int i = 0; i < N; ++i) result += c[i];
+        } else {
+#pragma unroll
+            for (int i = N - 1; i >= 0; --i) result += c[i] * xn[N - 1 - i];
+        }
+        return result;
+    }
+    template <int N1, int N2>
+    __device__ __forceinline__ void eval2(const double (&c1)[N1], const double (&c2)[N2], double& r1, double& r2) const {
+        static_assert(N1 <= M && N2 <= M, "PolyPoint holds too few powers");
+        double a = 0.0, b = 0.0;
+        if (zero) {
+            a = c1[N1 - 1]; b = c2[N2 - 1];
+        } else if (one) {
+#pragma unroll
+            for (int i = 0; i < N1; ++i) a += c1[i];
+#pragma unroll
+            for (int i = 0; i < N2; ++i) b += c2[i];
+        } else {
+#pragma unroll
+            for (int i = N1 - 1; i >= 0; --i) a += c1[i] * xn[N1 - 1 - i];
+#pragma unroll
+            for (int i = N2 - 1; i >= 0; --i) b += c2[i] * xn[N2 - 1 - i];
+        }
+        r1 = a; r2 = b;
+    }
+};
+
 // roots.rs:379-386
 template <int N>
 __device__ __forceinline__ void poly_deri(const double (&c)[N], double (&d)[N - 1]) {
@@ -578,8 +630,8 @@ __device__ __forceinline__ double shrink_interval(const double (&p)[N], double l
     double rts = (l + h) / 2.0;
     double dxold = fabs(h - l);
     double dx = dxold;
-    double f = poly_eval<N>(p, rts);
-    double df = poly_eval<N - 1>(deriv, rts);
+    double f, df;
+    PolyPoint<N>(rts).template eval2<N, N - 1>(p, deriv, f, df);
     for (int it = 0; it < 128; ++it) {
         if ((((rts - h) * df - f) * ((rts - l) * df - f) > 0.0) || fabs(2.0 * f) > fabs(dxold) * fabs(df)) {
             dxold = dx;
@@ -594,8 +646,7 @@ __device__ __forceinline__ double shrink_interval(const double (&p)[N], double l
             if (fabs(temp - rts) < EPS) break;
         }
         if (fabs(dx) < 1e-14) break;
-        f = poly_eval<N>(p, rts);
-        df = poly_eval<N - 1>(deriv, rts);
+        PolyPoint<N>(rts).template eval2<N, N - 1>(p, deriv, f, df);
         if (f < 0.0) l = rts; else h = rts;
     }
     return rts;
@@ -620,8 +671,7 @@ struct ShrinkState {
         rts = (l + h) / 2.0;
         dxold = fabs(h - l);
         dx = dxold;
-        f = poly_eval<N>(p, rts);
-        df = poly_eval<N - 1>(deriv, rts);
+        PolyPoint<N>(rts).template eval2<N, N - 1>(p, deriv, f, df);
         it = 0;
         return false;
     }
@@ -642,8 +692,7 @@ struct ShrinkState {
             if (fabs(temp - rts) < EPS) return true;
         }
         if (fabs(dx) < 1e-14) return true;
-        f = poly_eval<N>(p, rts);
-        df = poly_eval<N - 1>(deriv, rts);
+        PolyPoint<N>(rts).template eval2<N, N - 1>(p, deriv, f, df);
         if (f < 0.0) l = rts; else h = rts;
         return false;
     }

@@ -84,25 +84,6 @@ __device__ __forceinline__ void load_compact_profile(const double* prof, int64_t
     expand_compact(r, ProfileSink{local, 1, 0});
 }
 
-// PVA_ONLY: position, velocity and acceleration are all requested, jerk and section are not. COMPACT: trajectory layout.
-// t * j / 6 of util.rs:27-33 as the correctly rounded IEEE quotient: y = RN(1/6), q0 = a * y, r = fma(-6, q0, a),
-// q = fma(y, r, q0) is a / 6 correctly rounded whenever no intermediate leaves the normal range (Markstein; the same tail nvcc
-// emits after refining its own reciprocal, with the reciprocal a compile-time constant instead of MUFU.RCP64H + 5 FMAs per
-// sample); +-0, +-inf and NaN come out of a * y already; tiny / huge numerators take the compiler's division.
-__device__ __noinline__ double div6_rare(double a) { return a / 6.0; }
-__device__ __forceinline__ double div6(double a) {
-    const double y = __longlong_as_double(0x3FC5555555555555LL);
-    const uint32_t ea = hi_word(a) & 0x7ff00000u;
-    const double q0 = a * y;
-    const double r = __fma_rn(-6.0, q0, a);
-    const double q = __fma_rn(y, r, q0);
-    const bool moderate = (ea - 0x20b00000u) <= 0x3e800000u;  // 2^-500 <= |a| <= 2^500
-    const bool trivial = (ea == 0x7ff00000u) | (a == 0.0);
-    double res = moderate ? q : q0;
-    if (__builtin_expect(!(moderate | trivial), 0)) res = div6_rare(a);  // kept out of line: if-converted, the compiler's division runs per sample
-    return res;
-}
-
 #define RK_AT_MAX_STARTS 16
 // PVA_ONLY: position, velocity and acceleration are all requested, jerk and section are not (the RL rollout). COMPACT:
 // trajectory layout (the one-off expansion of a compact record would otherwise set the register count: 117 instead of 68,
@@ -632,7 +613,9 @@ __global__ void __launch_bounds__(256) k_selftest_division(int64_t n, uint64_t s
         const bool ok1 = nan_ref ? (q1 != q1) : (__double_as_longlong(q1) == __double_as_longlong(ref));
         const bool ok2 = nan_ref ? (q2 != q2) : (__double_as_longlong(q2) == __double_as_longlong(ref));
         const bool ok3 = (ref3 != ref3) ? (q3 != q3) : (__double_as_longlong(q3) == __double_as_longlong(ref3));
-        bad += (ok1 ? 0 : 1) + (ok2 ? 0 : 1) + (ok3 ? 0 : 1);
+        const double q6 = div6(a), ref6 = a / 6.0;  // the constant-reciprocal form used for t * j / 6 (util.rs:27-33)
+        const bool ok6 = (ref6 != ref6) ? (q6 != q6) : (__double_as_longlong(q6) == __double_as_longlong(ref6));
+        bad += (ok1 ? 0 : 1) + (ok2 ? 0 : 1) + (ok3 ? 0 : 1) + (ok6 ? 0 : 1);
     }
     if (bad) atomicAdd(mismatches, bad);
 }

@@ -221,10 +221,10 @@ struct Step1Pos3 {
         auto rest_ok = [&]() { return t[0] >= 0.0 && t[1] >= 0.0 && t[2] >= 0.0 && t[4] >= 0.0 && t[5] >= 0.0 && t[6] >= 0.0; };
         // ACC0_ACC1_VEL
         t[0] = (-a0 + a_max) / j_max;
-        t[1] = (a0_a0 / 2.0 - a_max * a_max - j_max * (v0 - v_max)) / (a_max * j_max);
+        t[1] = (a0_a0 * 0.5 - a_max * a_max - j_max * (v0 - v_max)) / (a_max * j_max);
         t[2] = a_max / j_max;
         t[4] = -a_min / j_max;
-        t[5] = -(af_af / 2.0 - a_min * a_min - j_max * (vf - v_max)) / (a_min * j_max);
+        t[5] = -(af_af * 0.5 - a_min * a_min - j_max * (vf - v_max)) / (a_min * j_max);
         t[6] = t[4] + af / j_max;
         if (rest_ok()) {
             t[3] = (3.0 * (a0_p4 * a_min - af_p4 * a_max)
@@ -261,7 +261,7 @@ struct Step1Pos3 {
         // ACC0_VEL
         const real t_acc1 = sqrt(af_af / (2.0 * jj) + (v_max - vf) / j_max);
         t[0] = (-a0 + a_max) / j_max;
-        t[1] = (a0_a0 / 2.0 - a_max * a_max - j_max * (v0 - v_max)) / (a_max * j_max);
+        t[1] = (a0_a0 * 0.5 - a_max * a_max - j_max * (v0 - v_max)) / (a_max * j_max);
         t[2] = a_max / j_max;
         t[4] = t_acc1;
         t[5] = 0.0;
@@ -286,7 +286,7 @@ struct Step1Pos3 {
         t[2] = t_acc0;
         if (rest_ok()) {
             t[3] = (af_p3 - a0_p3) / (3.0 * jj * v_max)
-                   + (a0 * v0 - af * vf + (af_af * t_acc1 + a0_a0 * t_acc0) / 2.0) / (j_max * v_max)
+                   + (a0 * v0 - af * vf + (af_af * t_acc1 + a0_a0 * t_acc0) * 0.5) / (j_max * v_max)
                    - (v0 / v_max + 1.0) * t_acc0
                    - (vf / v_max + 1.0) * t_acc1
                    + pd / v_max;
@@ -305,7 +305,7 @@ struct Step1Pos3 {
                     / (3. * (a_max - a_min) * jj)
                     + 4. * (a_max * vf_vf - a_min * v0_v0 - 2. * a_min * a_max * pd) / (a_max - a_min);
         if (!(h1 >= 0.)) return;
-        h1 = sqrt(h1) / 2.;
+        h1 = sqrt(h1) * 0.5;
         const real h2 = a0_a0 / (2. * a_max * j_max) + (a_min - 2. * a_max) / (2. * j_max) - v0 / a_max;
         const real h3 = -af_af / (2. * a_min * j_max) - (a_max - 2. * a_min) / (2. * j_max) + vf / a_min;
         double t[7];
@@ -369,15 +369,15 @@ struct Step1Pos3 {
                                         + (4.0 * a0_p3 + 2.0 * af_p3 - 6.0 * a0_a0 * (af + 2.0 * j_max * tt) + 12.0 * (af - a0) * j_max * v0
                                            + 3.0 * jj * (-4.0 * pd + (h1 + 8.0 * v0) * tt))
                                           / (12.0 * jj);
-                    const real deriv = h2_none + 2.0 * v0 - a0_a0 / j_max + h2_h2 / (4.0 * h1) + (3.0 * h1) / 4.0;
+                    const real deriv = h2_none + 2.0 * v0 - a0_a0 / j_max + h2_h2 / (4.0 * h1) + (3.0 * h1) * 0.25;
                     tt -= orig / deriv;
                 }
                 const real h0 = h2_none / (2.0 * j_max * tt);
-                t[0] = h0 + tt / 2.0 - a0 / j_max;
+                t[0] = h0 + tt * 0.5 - a0 / j_max;
                 t[1] = 0.0;
                 t[2] = tt;
                 t[3] = 0.0; t[4] = 0.0; t[5] = 0.0;
-                t[6] = -h0 + tt / 2.0 + af / j_max;
+                t[6] = -h0 + tt * 0.5 + af / j_max;
                 emit(t, L_NONE, L);
             }
         }
@@ -448,9 +448,9 @@ struct Step1Pos3 {
         const real h3_acc1 = -(a0_a0 + af_af) / (2.0 * j_max * a_min) + a_min / j_max + (vf - v0) / a_min;
         const real t_min_acc1 = (a_min - a0) / j_max;
         const real t_max_acc1 = (a_max - a0) / j_max;
-        const real h0_acc1 = (a0_p4 - af_p4) / 4.0
+        const real h0_acc1 = (a0_p4 - af_p4) * 0.25
                                + 2.0 * (af_p3 - a0_p3) * a_min / 3.0
-                               + (a0_a0 - af_af) * a_min * a_min / 2.0
+                               + (a0_a0 - af_af) * a_min * a_min * 0.5
                                + j_max * (af_af * vf + a0_a0 * v0 + 2.0 * a_min * (j_max * pd - a0 * v0 - af * vf)
                                           + a_min * a_min * (v0 + vf) + j_max * (v0_v0 - vf_vf));
         const real h2_acc1 = a0_a0 - a0 * a_min + 2.0 * j_max * v0;
@@ -476,26 +476,26 @@ struct Step1Pos3 {
                 if (tt > EPS) {  // up to three Newton steps (regarding pd)
                     const real h5 = a0_p3 + 2.0 * j_max * a0 * v0;
                     real h1 = j_max * tt;
-                    real orig = -(h0_acc1 / 2.0
-                                    + h1 * (h5 + a0 * (a_min - 2.0 * h1) * (a_min - h1) + a0_a0 * (5.0 * h1 / 2.0 - 2.0 * a_min)
-                                            + a_min * a_min * h1 / 2.0 + j_max * (h1 / 2.0 - a_min) * (h1 * tt + 2.0 * v0)))
+                    real orig = -(h0_acc1 * 0.5
+                                    + h1 * (h5 + a0 * (a_min - 2.0 * h1) * (a_min - h1) + a0_a0 * (5.0 * h1 * 0.5 - 2.0 * a_min)
+                                            + a_min * a_min * h1 * 0.5 + j_max * (h1 * 0.5 - a_min) * (h1 * tt + 2.0 * v0)))
                                   / j_max;
                     real deriv = (a_min - a0 - h1) * (h2_acc1 + h1 * (4.0 * a0 - a_min + 2.0 * h1));
                     tt -= rmin(orig / deriv, tt);
 
                     h1 = j_max * tt;
-                    orig = -(h0_acc1 / 2.0
-                             + h1 * (h5 + a0 * (a_min - 2.0 * h1) * (a_min - h1) + a0_a0 * (5.0 * h1 / 2.0 - 2.0 * a_min)
-                                     + a_min * a_min * h1 / 2.0 + j_max * (h1 / 2.0 - a_min) * (h1 * tt + 2.0 * v0)))
+                    orig = -(h0_acc1 * 0.5
+                             + h1 * (h5 + a0 * (a_min - 2.0 * h1) * (a_min - h1) + a0_a0 * (5.0 * h1 * 0.5 - 2.0 * a_min)
+                                     + a_min * a_min * h1 * 0.5 + j_max * (h1 * 0.5 - a_min) * (h1 * tt + 2.0 * v0)))
                            / j_max;
                     if (fabs(orig) > 1e-9) {
                         deriv = (a_min - a0 - h1) * (h2_acc1 + h1 * (4.0 * a0 - a_min + 2.0 * h1));
                         tt -= orig / deriv;
 
                         h1 = j_max * tt;
-                        orig = -(h0_acc1 / 2.0
-                                 + h1 * (h5 + a0 * (a_min - 2.0 * h1) * (a_min - h1) + a0_a0 * (5.0 * h1 / 2.0 - 2.0 * a_min)
-                                         + a_min * a_min * h1 / 2.0 + j_max * (h1 / 2.0 - a_min) * (h1 * tt + 2.0 * v0)))
+                        orig = -(h0_acc1 * 0.5
+                                 + h1 * (h5 + a0 * (a_min - 2.0 * h1) * (a_min - h1) + a0_a0 * (5.0 * h1 * 0.5 - 2.0 * a_min)
+                                         + a_min * a_min * h1 * 0.5 + j_max * (h1 * 0.5 - a_min) * (h1 * tt + 2.0 * v0)))
                                / j_max;
                         if (fabs(orig) > 1e-9) {
                             deriv = (a_min - a0 - h1) * (h2_acc1 + h1 * (4.0 * a0 - a_min + 2.0 * h1));
@@ -519,7 +519,7 @@ struct Step1Pos3 {
     __device__ __forceinline__ void rescue_none(const Lim& L) {  // :843-895
         const Den j_max = L.j_max;
         double t[7] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-        const real h0 = sqrt((a0_a0 + af_af) / 2.0 + j_max * (b.vf - b.v0)) * fabs(j_max) / j_max;
+        const real h0 = sqrt((a0_a0 + af_af) * 0.5 + j_max * (b.vf - b.v0)) * fabs(j_max) / j_max;
         t[0] = (h0 - b.a0) / j_max;
         t[2] = (h0 - b.af) / j_max;
         if (emit(t, L_NONE, L)) return;
@@ -574,7 +574,7 @@ struct Step1Pos3 {
         t[0] = -a0 / j_max;
         t[1] = 0.0;
         t[2] = 0.0;
-        t[3] = (af_p3 - a0_p3) / (3.0 * jj * v_max) + (a0 * v0 - af * vf + (af_af * h1) / 2.0) / (j_max * v_max) - (vf / v_max + 1.0) * h1 + pd / v_max;
+        t[3] = (af_p3 - a0_p3) / (3.0 * jj * v_max) + (a0 * v0 - af * vf + (af_af * h1) * 0.5) / (j_max * v_max) - (vf / v_max + 1.0) * h1 + pd / v_max;
         t[4] = h1;
         t[5] = 0.0;
         t[6] = h1 + af / j_max;
@@ -582,7 +582,7 @@ struct Step1Pos3 {
         t[0] = 0.0;
         t[1] = 0.0;
         t[2] = a0 / j_max;
-        t[3] = (af_p3 - a0_p3) / (3.0 * jj * v_max) + (a0 * v0 - af * vf + (af_af * h1 + a0_p3 / j_max) / 2.0) / (j_max * v_max)
+        t[3] = (af_p3 - a0_p3) / (3.0 * jj * v_max) + (a0 * v0 - af * vf + (af_af * h1 + a0_p3 / j_max) * 0.5) / (j_max * v_max)
                - (v0 / v_max + 1.0) * a0 / j_max - (vf / v_max + 1.0) * h1 + pd / v_max;
         t[4] = h1;
         t[5] = 0.0;
@@ -603,7 +603,7 @@ struct Step1Pos3 {
                                    + a_min * a0 * (a0_a0 - 2.0 * j_max * (v0 + v_max)) / j_max))
                / (24.0 * a_min * jj * v_max);
         t[4] = -a_min / j_max;
-        t[5] = -(af_af / 2.0 - a_min * a_min + j_max * (v_max - vf)) / (a_min * j_max);
+        t[5] = -(af_af * 0.5 - a_min * a_min + j_max * (v_max - vf)) / (a_min * j_max);
         t[6] = t[4] + af / j_max;
         emit(t, L_ACC1_VEL, L);
     }

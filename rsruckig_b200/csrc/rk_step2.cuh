@@ -126,7 +126,7 @@ __device__ RK_S2_FN bool s2_acc1_vel(const S2& s, const Lim& L, Hit& h) {
                            + 12.0 * j_max * ph2 + 6.0 * a0_a0 * ph3)
                           / (12.0 * j_max_j_max * j_max_j_max);
         const real t_min = -a0 / j_max;
-        const real t_max = rmin((tf + 2.0 * a_min / j_max - (a0 + af) / j_max) / 2.0, (a_max - a0) / j_max);
+        const real t_max = rmin((tf + 2.0 * a_min / j_max - (a0 + af) / j_max) * 0.5, (a_max - a0) / j_max);
         const Roots roots = solve_quart_monic(c0, c1, c2, c3);
 #pragma unroll 1
         for (int ri = 0; ri < roots.n; ++ri) {
@@ -148,7 +148,7 @@ __device__ RK_S2_FN bool s2_acc1_vel(const S2& s, const Lim& L, Hit& h) {
                                      * ((a0_a0 + af_af) / (a_min * j_max) + (a_min - a0 - 2.0 * af) / j_max + (4.0 * a0 * tt + 2.0 * h0 - 2.0 * vd) / a_min + 2.0 * tf - 3.0 * tt);
                 tt -= orig / deriv;
             }
-            const real h1 = -((a0_a0 + af_af) / 2.0 + j_max * (-vd + 2.0 * a0 * tt + j_max * tt * tt)) / a_min;
+            const real h1 = -((a0_a0 + af_af) * 0.5 + j_max * (-vd + 2.0 * a0 * tt + j_max * tt * tt)) / a_min;
             t[0] = tt;
             t[1] = 0.0;
             t[2] = a0 / j_max + tt;
@@ -172,13 +172,13 @@ __device__ RK_S2_FN bool s2_acc1_vel(const S2& s, const Lim& L, Hit& h) {
                            - 6.0 * a0_a0 * ph3 + 6.0 * af_af * ph2)
                           / (12.0 * j_max_j_max * j_max_j_max);
         const real t_min = -a0 / j_max;
-        const real t_max = rmin((tf + ad / j_max - 2.0 * a_max / j_max) / 2.0, (a_max - a0) / j_max);
+        const real t_max = rmin((tf + ad / j_max - 2.0 * a_max / j_max) * 0.5, (a_max - a0) / j_max);
         const Roots roots = solve_quart_monic(c0, c1, c2, c3);
 #pragma unroll 1
         for (int ri = 0; ri < roots.n; ++ri) {
             const real tt = roots.get(ri);
             if (tt > t_max || tt < t_min) continue;
-            const real h1 = ((a0_a0 - af_af) / 2.0 + j_max_j_max * tt * tt - j_max * (vd - 2.0 * a0 * tt)) / a_max;
+            const real h1 = ((a0_a0 - af_af) * 0.5 + j_max_j_max * tt * tt - j_max * (vd - 2.0 * a0 * tt)) / a_max;
             t[0] = tt;
             t[1] = 0.0;
             t[2] = tt + a0 / j_max;
@@ -226,7 +226,7 @@ __device__ RK_S2_FN bool s2_acc0_vel(const S2& s, const Lim& L, Hit& h) {
                 const real deriv = -tt * (a0_a0 - af_af + 2.0 * a_max * (ad - j_max * tf) + a_max * a_max + 3.0 * a_max * j_max * tt + 2.0 * j_max * h1) / a_max;
                 tt -= orig / deriv;
             }
-            const real h1 = ((a0_a0 - af_af) / 2.0 + j_max * (j_max * tt * tt + vd)) / a_max;
+            const real h1 = ((a0_a0 - af_af) * 0.5 + j_max * (j_max * tt * tt + vd)) / a_max;
             t[0] = (-a0 + a_max) / j_max;
             t[1] = (h1 - a_max) / j_max;
             t[2] = a_max / j_max;
@@ -265,7 +265,7 @@ __device__ RK_S2_FN bool s2_acc0_vel(const S2& s, const Lim& L, Hit& h) {
                 const real deriv = tt * (a0_a0 + af_af - 2.0 * j_max * h1 - 2.0 * (a0 + af + j_max * tf) * a_max + a_max * a_max + 3.0 * a_max * j_max * tt) / a_max;
                 tt -= orig / deriv;
             }
-            const real h1 = ((a0_a0 + af_af) / 2.0 + j_max * (vd - j_max * tt * tt)) / a_max;
+            const real h1 = ((a0_a0 + af_af) * 0.5 + j_max * (vd - j_max * tt * tt)) / a_max;
             t[0] = (-a0 + a_max) / j_max;
             t[1] = (h1 - a_max) / j_max;
             t[2] = a_max / j_max;

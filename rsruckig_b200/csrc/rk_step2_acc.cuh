@@ -36,7 +36,7 @@ __device__ RK_S2_FN bool s2_acc0_acc1(const S2& s, const Lim& L, Hit& h) {
                                         + a0_a0 * (3.0 * af - 4.0 * (2.0 * a_max + a_min)))
                                      * (2.0 * a_min * g1 + vd * vd + a_max * (2.0 * pd + a_min * tf * tf - 2.0 * tf * vf)));
         const real jf = -(3.0 * af_af * a_max * tf - 3.0 * a0_a0 * a_min * tf - 6.0 * ad * a_max * a_min * tf + 3.0 * a_max * a_min * (a_min - a_max) * tf
-                            + 3.0 * (a0_a0 - af_af) * vd + 6.0 * vd * (af * a_min - a0 * a_max) + 3.0 * (a_max * a_max - a_min * a_min) * vd + h1 / 4.0)
+                            + 3.0 * (a0_a0 - af_af) * vd + 6.0 * vd * (af * a_min - a0 * a_max) + 3.0 * (a_max * a_max - a_min * a_min) * vd + h1 * 0.25)
                           / (6.0 * (2.0 * a_min * g1 + vd * vd + a_max * (2.0 * pd + a_min * tf_tf - 2.0 * tf * vf)));
         t[0] = (a_max - a0) / jf;
         t[1] = (a0_a0 - af_af + 2.0 * ad * a_min - 2.0 * (a_max * a_max - 2.0 * a_max * a_min + a_min * a_min + a_min * jf * tf - jf * vd))
@@ -66,7 +66,7 @@ __device__ RK_S2_FN bool s2_acc1(const S2& s, const Lim& L, Hit& h) {
         const real h1 = sqrt((a0_a0 + af_af - 2.0 * a0 * af - 2.0 * ad * j_max * tf + 2.0 * h0) / j_max_j_max + tf_tf);
         t[0] = -(a0_a0 + af_af + 2.0 * a0 * (j_max * tf - af) - 2.0 * j_max * vd + h0) / (2.0 * j_max * (-ad + j_max * tf));
         t[1] = 0.0;
-        t[2] = (tf - h1) / 2.0 - ad / (2.0 * j_max);
+        t[2] = (tf - h1) * 0.5 - ad / (2.0 * j_max);
         t[3] = 0.0;
         t[4] = 0.0;
         t[5] = h1;
@@ -87,7 +87,7 @@ __device__ RK_S2_FN bool s2_acc1(const S2& s, const Lim& L, Hit& h) {
         t[1] = 0.0;
         t[2] = -(a0_a0 + af_af - 2.0 * a0 * af + 2.0 * j_max * (vd - a0 * tf) + h0) / (2.0 * j_max * (ad + j_max * tf));
         t[3] = 0.0;
-        t[4] = ad / (2.0 * j_max) + (tf - h1) / 2.0;
+        t[4] = ad / (2.0 * j_max) + (tf - h1) * 0.5;
         t[5] = h1;
         t[6] = tf - (t[5] + t[4] + t[2]);
         RK_TRY(UDUD, L_ACC1, j_max)
@@ -166,7 +166,7 @@ __device__ RK_S2_FN bool s2_acc0(const S2& s, const Lim& L, Hit& h) {
                 + 6.0 * af * (a_max * a_max - j_max * vd) + 3.0 * a0 * (af_af - 2.0 * (a_max * a_max + j_max * vd))
                 - 6.0 * j_max * (a_max * (a_max * tf - 2.0 * vd) + j_max * g2))
                / h1;
-        t[2] = -(ad + h0 / h1) / (2.0 * j_max) + tf / 2.0 - t[1] / 2.0;
+        t[2] = -(ad + h0 / h1) / (2.0 * j_max) + tf * 0.5 - t[1] * 0.5;
         t[3] = h0 / (j_max * h1);
         t[4] = 0.0;
         t[5] = 0.0;

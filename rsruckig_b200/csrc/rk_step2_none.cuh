@@ -14,7 +14,7 @@ __device__ RK_S2_FN bool s2_none(const S2& s, const Lim& L, Hit& h) {
     if (fabs(v0) < EPS && fabs(a0) < EPS && fabs(af) < EPS) {
         const real h1 = sqrt(tf_tf * vf_vf + sq(4.0 * pd - tf * vf));
         const real jf = 4.0 * (4.0 * pd - 2.0 * tf * vf + h1) / tf_p3;
-        t[0] = tf / 4.0;
+        t[0] = tf * 0.25;
         t[1] = 0.0;
         t[2] = 2.0 * t[0];
         t[3] = 0.0;
@@ -34,13 +34,13 @@ __device__ RK_S2_FN bool s2_none(const S2& s, const Lim& L, Hit& h) {
 #pragma unroll 1
         for (int ri = 0; ri < roots.n; ++ri) {
             real tt = roots.get(ri);
-            if (tt > tf / 2.0 || tt > (a_max - a0) / j_max) continue;
+            if (tt > tf * 0.5 || tt > (a_max - a0) / j_max) continue;
             // Single Newton step (regarding pd)
             {
                 const real h1 = (j_max * tt * (tt - tf) + vd) / (j_max * (2.0 * tt - tf));
                 const real h2 = (2.0 * j_max * tt * (tt - tf) + j_max * tf_tf - 2.0 * vd) / (j_max * (2.0 * tt - tf) * (2.0 * tt - tf));
-                const real orig = (-2.0 * pd + 2.0 * tf * v0 + h1 * h1 * j_max * (tf - 2.0 * tt) + j_max * tf * (2.0 * h1 * tt - tt * tt - (h1 - tt) * tf)) / 2.0;
-                const real deriv = (j_max * tf * (2.0 * tt - tf) * (h2 - 1.0)) / 2.0 + h1 * j_max * (tf - (2.0 * tt - tf) * h2 - h1);
+                const real orig = (-2.0 * pd + 2.0 * tf * v0 + h1 * h1 * j_max * (tf - 2.0 * tt) + j_max * tf * (2.0 * h1 * tt - tt * tt - (h1 - tt) * tf)) * 0.5;
+                const real deriv = (j_max * tf * (2.0 * tt - tf) * (h2 - 1.0)) * 0.5 + h1 * j_max * (tf - (2.0 * tt - tf) * h2 - h1);
                 tt -= orig / deriv;
             }
             t[0] = tt;
@@ -96,7 +96,7 @@ __device__ RK_S2_FN bool s2_none(const S2& s, const Lim& L, Hit& h) {
                            + 12.0 * j_max_j_max * (vd_vd + j_max * tf * g2))
                           / (12.0 * j_max_j_max * j_max_j_max);
         const real t_min = ad / j_max;
-        const real t_max = rmin((a_max - a0) / j_max, (ad / j_max + tf) / 2.0);
+        const real t_max = rmin((a_max - a0) / j_max, (ad / j_max + tf) * 0.5);
         const Roots roots = solve_quart_monic(c0, c1, c2, c3);
 #pragma unroll 1
         for (int ri = 0; ri < roots.n; ++ri) {
@@ -138,9 +138,9 @@ __device__ RK_S2_FN bool s2_none(const S2& s, const Lim& L, Hit& h) {
         t[1] = 0.0;
         t[2] = 0.0;
         t[3] = (af_p3 - a0_p3 + 3.0 * (af_af - a0_a0) * j_max * tf - 3.0 * ad * (a0 * af + 2.0 * j_max * vd) - 6.0 * j_max_j_max * g2) / h1;
-        t[4] = (tf - t[3] - h0) / 2.0 - ad / (2.0 * j_max);
+        t[4] = (tf - t[3] - h0) * 0.5 - ad / (2.0 * j_max);
         t[5] = h0;
-        t[6] = (tf - t[3] + ad / j_max - h0) / 2.0;
+        t[6] = (tf - t[3] + ad / j_max - h0) * 0.5;
         RK_TRY(UDDU, L_NONE, j_max)
     }
 
@@ -184,7 +184,7 @@ __device__ RK_S2_FN bool s2_none(const S2& s, const Lim& L, Hit& h) {
             if (tt > t_max) continue;
             // Single Newton step (regarding pd)
             {
-                const real h1 = ad_ad / 2.0 + j_max * (af * tt + (j_max * tt - a0) * (tt - tf) - vd);
+                const real h1 = ad_ad * 0.5 + j_max * (af * tt + (j_max * tt - a0) * (tt - tf) - vd);
                 const real h2 = -ad + j_max * (tf - 2.0 * tt);
                 const real h3 = sqrt(h1);
                 const real orig = (af_p3 - a0_p3 + 3.0 * af * j_max * tt * (af + j_max * tt) + 3.0 * a0_a0 * (af + j_max * tt)
@@ -204,7 +204,7 @@ __device__ RK_S2_FN bool s2_none(const S2& s, const Lim& L, Hit& h) {
             t[1] = 0.0;
             t[2] = tt;
             t[3] = tf - 2.0 * tt - ad / j_max - h1;
-            t[4] = h1 / 2.0;
+            t[4] = h1 * 0.5;
             t[5] = 0.0;
             t[6] = tf - (tt + t[3] + t[4]);
             RK_TRY(UDDU, L_NONE, j_max)
@@ -265,9 +265,9 @@ __device__ RK_S2_FN bool s2_none(const S2& s, const Lim& L, Hit& h) {
     // 3 step profile (UZD), T 012
     {
         const real h1 = sqrt(-ad_ad + j_max * (2.0 * (a0 + af) * tf - 4.0 * vd + j_max * tf_tf)) / fabs(j_max);
-        t[0] = (tf - h1 + ad / j_max) / 2.0;
+        t[0] = (tf - h1 + ad / j_max) * 0.5;
         t[1] = h1;
-        t[2] = (tf - h1 - ad / j_max) / 2.0;
+        t[2] = (tf - h1 - ad / j_max) * 0.5;
         t[3] = 0.0;
         t[4] = 0.0;
         t[5] = 0.0;
@@ -302,7 +302,7 @@ __device__ RK_S2_FN bool s2_none(const S2& s, const Lim& L, Hit& h) {
     {
         t[0] = (ad_ad / j_max + 2.0 * (a0 + af) * tf - j_max * tf_tf - 4.0 * vd) / (4.0 * (ad - j_max * tf));
         t[1] = 0.0;
-        t[2] = -ad / (2.0 * j_max) + tf / 2.0;
+        t[2] = -ad / (2.0 * j_max) + tf * 0.5;
         t[3] = 0.0;
         t[4] = 0.0;
         t[5] = 0.0;

@@ -80,14 +80,14 @@ __device__ RK_S2_FN bool s2_vel_uddu(const S2& s, const Lim& L, Hit& h) {
     RK_S2_LOCALS
     const real a0_p6 = s.a0_p6, af_p6 = s.af_p6;
     const real tz_min = rmax(0.0, -a0 / j_max);
-    const real tz_max = rmin((tf - a0 / j_max) / 2.0, (a_max - a0) / j_max);
+    const real tz_max = rmin((tf - a0 / j_max) * 0.5, (a_max - a0) / j_max);
 
     if (fabs(v0) < EPS && fabs(a0) < EPS && fabs(vf) < EPS && fabs(af) < EPS) {
-        const Roots roots = solve_cub(1.0, -tf / 2.0, 0.0, pd / (2.0 * j_max));
+        const Roots roots = solve_cub(1.0, -tf * 0.5, 0.0, pd / (2.0 * j_max));
 #pragma unroll 1
         for (int ri = 0; ri < roots.n; ++ri) {
             real tt = roots.get(ri);
-            if (tt > tf / 4.0) continue;
+            if (tt > tf * 0.25) continue;
             // Single Newton step (regarding pd)
             if (tt > EPS) {
                 const real orig = -pd + j_max * tt * tt * (tf - 2.0 * tt);
@@ -200,11 +200,11 @@ __device__ __forceinline__ bool vel_uddu_candidates(const S2& s, const Lim& L, H
 
     if (active && fabs(v0) < EPS && fabs(a0) < EPS && fabs(vf) < EPS && fabs(af) < EPS) {  // rare, handled out of step
         active = false;
-        const Roots roots = solve_cub(1.0, -tf / 2.0, 0.0, pd / (2.0 * j_max));
+        const Roots roots = solve_cub(1.0, -tf * 0.5, 0.0, pd / (2.0 * j_max));
 #pragma unroll 1
         for (int ri = 0; ri < roots.n && !found; ++ri) {
             real tt = roots.get(ri);
-            if (tt > tf / 4.0) continue;
+            if (tt > tf * 0.25) continue;
             if (tt > EPS) {
                 const real orig = -pd + j_max * tt * tt * (tf - 2.0 * tt);
                 const real deriv_ = 2.0 * j_max * tt * (tf - 3.0 * tt);
@@ -222,7 +222,7 @@ __device__ __forceinline__ bool vel_uddu_candidates(const S2& s, const Lim& L, H
     // phase A: the monic quintic and its derivatives
     if (active) {
         tz_min = rmax(0.0, -a0 / j_max);
-        tz_max = rmin((tf - a0 / j_max) / 2.0, (a_max - a0) / j_max);
+        tz_max = rmin((tf - a0 / j_max) * 0.5, (a_max - a0) / j_max);
         const real p1 = af_af - 2.0 * j_max * (-2.0 * af * tf + j_max * tf_tf + 3.0 * vd);
         const real ph1 = af_p3 - 3.0 * j_max_j_max * g1 - 3.0 * af * j_max * vd;
         const real ph2 = af_p4 + 8.0 * af_p3 * j_max * tf
@@ -260,10 +260,16 @@ __device__ __forceinline__ bool vel_uddu_candidates(const S2& s, const Lim& L, H
             bool direct = false, bracket = false;
             real val_new;
             if (!last) {
-                const real orig = poly_eval<5>(deriv, tz);
-                if (fabs(orig) > ROOT_TOLERANCE) tz -= orig / poly_eval<4>(dderiv, tz);
-                val_new = poly_eval<6>(pol, tz);
-                if (fabs(val_new) < 64.0 * fabs(poly_eval<4>(dderiv, tz)) * ROOT_TOLERANCE) direct = true;
+                {   // polynomials evaluated at the same point share its powers (PolyPoint, rk_core.cuh)
+                    const PolyPoint<5> at(tz);
+                    const real orig = at.eval<5>(deriv);
+                    if (fabs(orig) > ROOT_TOLERANCE) tz -= orig / at.eval<4>(dderiv);
+                }
+                const PolyPoint<6> at(tz);
+                double v_new, dd_new;
+                at.eval2<6, 4>(pol, dderiv, v_new, dd_new);
+                val_new = v_new;
+                if (fabs(val_new) < 64.0 * fabs(dd_new) * ROOT_TOLERANCE) direct = true;
                 else if (val_current * val_new < 0.0) bracket = true;
             } else {
                 val_new = poly_eval<6>(pol, tz_max);
@@ -288,7 +294,7 @@ __device__ RK_S2_FN bool s2_vel_udud(const S2& s, const Lim& L, Hit& h) {
     RK_S2_LOCALS
     const real a0_p5 = s.a0_p5, a0_p6 = s.a0_p6, af_p6 = s.af_p6;
     const real tz_min = rmax(0.0, -a0 / j_max);
-    const real tz_max = rmin((tf - a0 / j_max) / 2.0, (a_max - a0) / j_max);
+    const real tz_max = rmin((tf - a0 / j_max) * 0.5, (a_max - a0) / j_max);
 
     const real ph1 = af_af - 2.0 * j_max * (2.0 * af * tf + j_max * tf_tf - 3.0 * vd);
     const real ph2 = af_p3 - 3.0 * j_max_j_max * g1 + 3.0 * af * j_max * vd;
@@ -387,7 +393,7 @@ __device__ __forceinline__ bool s2_vel_udud_lockstep(const S2& s, const Lim& L, 
     // phase A: the monic sextic and its derivatives
     if (active) {
         tz_min = rmax(0.0, -a0 / j_max);
-        tz_max = rmin((tf - a0 / j_max) / 2.0, (a_max - a0) / j_max);
+        tz_max = rmin((tf - a0 / j_max) * 0.5, (a_max - a0) / j_max);
         const real ph1 = af_af - 2.0 * j_max * (2.0 * af * tf + j_max * tf_tf - 3.0 * vd);
         const real ph2 = af_p3 - 3.0 * j_max_j_max * g1 + 3.0 * af * j_max * vd;
         const real ph3 = 2.0 * j_max * tf * g1 + 3.0 * vd_vd;
@@ -419,20 +425,26 @@ __device__ __forceinline__ bool s2_vel_udud_lockstep(const S2& s, const Lim& L, 
     int n_iv = 0;
     if (active) {
         real dd_tz_current = tz_min;
+        real d_current = poly_eval<6>(deriv, dd_tz_current);  // the value at the left end is the previous pass's value at its right end
 #pragma unroll 1
         for (int ri = 0; ri < dd_extremas.n; ++ri) {
             real tz = dd_extremas.get(ri);
             if (tz >= tz_max) continue;
-            const real orig = poly_eval<5>(dderiv, tz);
-            if (fabs(orig) > ROOT_TOLERANCE) tz -= orig / poly_eval<4>(ddderiv, tz);
-            if (poly_eval<6>(deriv, dd_tz_current) * poly_eval<6>(deriv, tz) < 0.0) {
+            {   // polynomials evaluated at the same point share its powers (PolyPoint, rk_core.cuh)
+                const PolyPoint<5> at(tz);
+                const real orig = at.eval<5>(dderiv);
+                if (fabs(orig) > ROOT_TOLERANCE) tz -= orig / at.eval<4>(ddderiv);
+            }
+            const real d_new = poly_eval<6>(deriv, tz);
+            if (d_current * d_new < 0.0) {
                 bool dup = false;
                 for (int k = 0; k < n_iv; ++k) dup |= (iv_l[k] == dd_tz_current && iv_r[k] == tz);
                 if (!dup && n_iv < 6) { iv_l[n_iv] = dd_tz_current; iv_r[n_iv] = tz; ++n_iv; }
             }
             dd_tz_current = tz;
+            d_current = d_new;
         }
-        if (poly_eval<6>(deriv, dd_tz_current) * poly_eval<6>(deriv, tz_max) < 0.0) {
+        if (d_current * poly_eval<6>(deriv, tz_max) < 0.0) {
             bool dup = false;
             for (int k = 0; k < n_iv; ++k) dup |= (iv_l[k] == dd_tz_current && iv_r[k] == tz_max);
             if (!dup && n_iv < 6) { iv_l[n_iv] = dd_tz_current; iv_r[n_iv] = tz_max; ++n_iv; }
@@ -453,9 +465,10 @@ __device__ __forceinline__ bool s2_vel_udud_lockstep(const S2& s, const Lim& L, 
             const bool last = k == n_iv;
             const real tz = last ? tz_max : real(shrink_interval<6>(deriv, iv_l[last ? 0 : k], iv_r[last ? 0 : k]));
             if (last || !(tz >= tz_max)) {
-                const real p_val = poly_eval<7>(pol, tz);
+                const PolyPoint<7> at(tz);
+                const real p_val = at.eval<7>(pol);
                 bool direct = false, bracket = false;
-                if (!last && fabs(p_val) < 64.0 * fabs(poly_eval<5>(dderiv, tz)) * ROOT_TOLERANCE) direct = true;
+                if (!last && fabs(p_val) < 64.0 * fabs(at.eval<5>(dderiv)) * ROOT_TOLERANCE) direct = true;
                 else if (val_current * p_val < 0.0) bracket = true;
                 if (direct || bracket) {
                     c_lo[n_cand] = bracket ? (double)tz_current : (double)tz;

@@ -44,7 +44,7 @@ struct Step1Vel3 {
     }
     // velocity_third_step1.rs:64-117
     __device__ __forceinline__ void time_none(real a_max, real a_min, real j_max, bool first_only) {
-        real h1 = (b.a0 * b.a0 + b.af * b.af) / 2.0 + j_max * vd;
+        real h1 = (b.a0 * b.a0 + b.af * b.af) * 0.5 + j_max * vd;
         if (!(h1 >= 0.0)) return;
         h1 = sqrt(h1);
         double t[7];
@@ -111,7 +111,7 @@ __device__ __forceinline__ bool step2_vel3_dir(const Bound& b, real tf, real vd,
     {
         const real h1 = sqrt((-ad * ad + 2.0 * j_max * ((b.a0 + b.af) * tf - 2.0 * vd)) / (j_max * j_max) + tf * tf);
         zero_t(t);
-        t[0] = ad / (2.0 * j_max) + (tf - h1) / 2.0;
+        t[0] = ad / (2.0 * j_max) + (tf - h1) * 0.5;
         t[1] = h1;
         t[2] = tf - (t[0] + h1);
         if (check_vel3(t, UDDU, L_ACC0, j_max, a_max, a_min, b)) { set_cand(c, t, j_max, 0.0, L_ACC0, dir, UDDU); return true; }

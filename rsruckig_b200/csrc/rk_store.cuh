@@ -75,7 +75,7 @@ __device__ __forceinline__ double store_profile(const ProfileSink& o, int kind, 
             const double tj = t[i] * j[i];  // as in check_pos3: +-0 / 6 == +-0 for the always-zero jerks
             a[i + 1] = a[i] + tj;
             v[i + 1] = v[i] + t[i] * (a[i] + tj / 2.0);
-            p[i + 1] = p[i] + t[i] * (v[i] + t[i] * (a[i] / 2.0 + ((i & 1) ? tj : sdiv(tj, 6.0))));
+            p[i + 1] = p[i] + t[i] * (v[i] + t[i] * (a[i] / 2.0 + ((i & 1) ? tj : div6(tj))));
             if (i == 2 && zero_a3) a[3] = 0.0;
         }
     } else if (kind == K_POS2) {  // profile.rs:549-637
