@@ -408,9 +408,9 @@ __device__ __noinline__ Roots solve_cub(double a, double b, double c, double d) 
 
 // roots.rs:237-274
 __device__ __forceinline__ int solve_resolvent(double (&x)[3], double a, double b, double c) {
-    a = sdiv(a, 3.0);
+    a = div3(a);
     const double a2 = a * a;
-    double q = a2 - sdiv(b, 3.0);
+    double q = a2 - div3(b);
     const double r = (a * (2.0 * a2 - b) + c) / 2.0;
     const double r2 = r * r;
     const double q3 = q * q * q;
@@ -418,7 +418,7 @@ __device__ __forceinline__ int solve_resolvent(double (&x)[3], double a, double 
         const double q_sqrt = sqrt(q);
         const double t = rmax(rmin(sdiv(r, q * q_sqrt), 1.0), -1.0);
         q = -2.0 * q_sqrt;
-        const double theta = sdiv(m_acos(t), 3.0);  // acos(1) = 0 is common after the clamp
+        const double theta = div3(m_acos(t));  // acos(1) = 0 is common after the clamp
         double sn, cs;
         m_sincos(theta, sn, cs);
         const double ux = cs * q;
@@ -503,8 +503,9 @@ __device__ RK_QUART_FN Roots solve_quart_monic(double a, double b, double c, dou
         const double sqrt_d = sqrt(d_);
         q1 = (y + sqrt_d) / 2.0;
         q2 = (y - sqrt_d) / 2.0;
-        p1 = sdiv(a * q1 - c, q1 - q2);
-        p2 = sdiv(c - a * q2, q1 - q2);
+        const Den q12(q1 - q2);  // one reciprocal for the two quotients
+        p1 = ddiv(a * q1 - c, q12);
+        p2 = ddiv(c - a * q2, q12);
     }
 
     const double EPS16 = 16.0 * EPS;

@@ -615,7 +615,9 @@ __global__ void __launch_bounds__(256) k_selftest_division(int64_t n, uint64_t s
         const bool ok3 = (ref3 != ref3) ? (q3 != q3) : (__double_as_longlong(q3) == __double_as_longlong(ref3));
         const double q6 = div6(a), ref6 = a / 6.0;  // the constant-reciprocal form used for t * j / 6 (util.rs:27-33)
         const bool ok6 = (ref6 != ref6) ? (q6 != q6) : (__double_as_longlong(q6) == __double_as_longlong(ref6));
-        bad += (ok1 ? 0 : 1) + (ok2 ? 0 : 1) + (ok3 ? 0 : 1) + (ok6 ? 0 : 1);
+        const double q3c = div3(a), ref3c = a / 3.0;  // the three divisions by 3 of the resolvent (roots.rs:237-252)
+        const bool ok3c = (ref3c != ref3c) ? (q3c != q3c) : (__double_as_longlong(q3c) == __double_as_longlong(ref3c));
+        bad += (ok1 ? 0 : 1) + (ok2 ? 0 : 1) + (ok3 ? 0 : 1) + (ok6 ? 0 : 1) + (ok3c ? 0 : 1);
     }
     if (bad) atomicAdd(mismatches, bad);
 }

@@ -240,7 +240,7 @@ struct Step1Pos3 {
         }
 
         // ACC1_VEL (t[4..6] carry over)
-        const real t_acc0 = sqrt(a0_a0 / (2.0 * jj) + (v_max - v0) / j_max);
+        const real t_acc0 = sqrt(a0_a0 / twice(jj) + (v_max - v0) / j_max);
         t[0] = t_acc0 - a0 / j_max;
         t[1] = 0.0;
         t[2] = t_acc0;
@@ -259,7 +259,7 @@ struct Step1Pos3 {
         }
 
         // ACC0_VEL
-        const real t_acc1 = sqrt(af_af / (2.0 * jj) + (v_max - vf) / j_max);
+        const real t_acc1 = sqrt(af_af / twice(jj) + (v_max - vf) / j_max);
         t[0] = (-a0 + a_max) / j_max;
         t[1] = (a0_a0 * 0.5 - a_max * a_max - j_max * (v0 - v_max)) / (a_max * j_max);
         t[2] = a_max / j_max;
@@ -306,8 +306,8 @@ struct Step1Pos3 {
                     + 4. * (a_max * vf_vf - a_min * v0_v0 - 2. * a_min * a_max * pd) / (a_max - a_min);
         if (!(h1 >= 0.)) return;
         h1 = sqrt(h1) * 0.5;
-        const real h2 = a0_a0 / (2. * a_max * j_max) + (a_min - 2. * a_max) / (2. * j_max) - v0 / a_max;
-        const real h3 = -af_af / (2. * a_min * j_max) - (a_max - 2. * a_min) / (2. * j_max) + vf / a_min;
+        const real h2 = a0_a0 / (2. * a_max * j_max) + (a_min - 2. * a_max) / twice(j_max) - v0 / a_max;
+        const real h3 = -af_af / (2. * a_min * j_max) - (a_max - 2. * a_min) / twice(j_max) + vf / a_min;
         double t[7];
         // UDDU: Solution 2
         if (h2 > h1 / a_max && h3 > -h1 / a_min) {
@@ -343,7 +343,7 @@ struct Step1Pos3 {
         const real v0 = b.v0, a0 = b.a0, vf = b.vf, af = b.af;
         const Den a_max = L.a_max, a_min = L.a_min, j_max = L.j_max;
         const real jl = j_max * j_max;  // the reference mixes this local with the member computed from the UP jerk; equal values
-        const real h2_none = (a0_a0 - af_af) / (2.0 * j_max) + (vf - v0);
+        const real h2_none = (a0_a0 - af_af) / twice(j_max) + (vf - v0);
         const real h2_h2 = h2_none * h2_none;
         const real t_min_none = (a0 - af) / j_max;
         const real t_max_none = (a_max - a_min) / j_max;
@@ -449,7 +449,7 @@ struct Step1Pos3 {
         const real t_min_acc1 = (a_min - a0) / j_max;
         const real t_max_acc1 = (a_max - a0) / j_max;
         const real h0_acc1 = (a0_p4 - af_p4) * 0.25
-                               + 2.0 * (af_p3 - a0_p3) * a_min / 3.0
+                               + 2.0 * (af_p3 - a0_p3) * a_min / THREE
                                + (a0_a0 - af_af) * a_min * a_min * 0.5
                                + j_max * (af_af * vf + a0_a0 * v0 + 2.0 * a_min * (j_max * pd - a0 * v0 - af * vf)
                                           + a_min * a_min * (v0 + vf) + j_max * (v0_v0 - vf_vf));
@@ -569,7 +569,7 @@ struct Step1Pos3 {
     __device__ __forceinline__ void rescue_vel(const Lim& L) {  // :780-841
         const real v0 = b.v0, a0 = b.a0, vf = b.vf, af = b.af;
         const Den v_max = L.v_max, j_max = L.j_max;
-        const real h1 = sqrt(af_af / (2.0 * jj) + (v_max - vf) / j_max);
+        const real h1 = sqrt(af_af / twice(jj) + (v_max - vf) / j_max);
         double t[7];
         t[0] = -a0 / j_max;
         t[1] = 0.0;

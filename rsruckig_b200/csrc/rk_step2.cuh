@@ -72,7 +72,7 @@ __device__ RK_S2_FN bool s2_acc0_acc1_vel(const S2& s, const Lim& L, Hit& h) {
     RK_S2_LOCALS
     // Profile UDDU, Solution 1
     if ((2.0 * (a_max - a_min) + ad) / j_max < tf) {
-        const real h1 = sqrt((a0_p4 + af_p4 - 4.0 * a0_p3 * (2.0 * a_max + a_min) / 3.0 - 4.0 * af_p3 * (a_max + 2.0 * a_min) / 3.0
+        const real h1 = sqrt((a0_p4 + af_p4 - 4.0 * a0_p3 * (2.0 * a_max + a_min) / THREE - 4.0 * af_p3 * (a_max + 2.0 * a_min) / THREE
                                 + 2.0 * (a0_a0 - af_af) * a_max * a_max
                                 + (4.0 * a0 * a_max - 2.0 * a0_a0) * (af_af - 2.0 * af * a_min + (a_min - a_max) * a_min + 2.0 * j_max * (a_min * tf - vd))
                                 + 2.0 * af_af * (a_min * a_min + 2.0 * j_max * (a_max * tf - vd))
@@ -86,7 +86,7 @@ __device__ RK_S2_FN bool s2_acc0_acc1_vel(const S2& s, const Lim& L, Hit& h) {
         t[1] = (-(af_af - a0_a0 + 2.0 * a_max * a_max + a_min * (a_min - 2.0 * ad - 3.0 * a_max) + 2.0 * j_max * (a_min * tf - vd)) + a_min * h1)
                / (2.0 * (a_max - a_min) * j_max);
         t[2] = a_max / j_max;
-        t[3] = (a_min - a_max + h1) / (2.0 * j_max);
+        t[3] = (a_min - a_max + h1) / twice(j_max);
         t[4] = -a_min / j_max;
         t[5] = tf - (t[0] + t[1] + t[2] + t[3] + 2.0 * t[4] + af / j_max);
         t[6] = t[4] + af / j_max;

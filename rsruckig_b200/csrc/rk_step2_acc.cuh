@@ -61,12 +61,12 @@ __device__ RK_S2_FN bool s2_acc1(const S2& s, const Lim& L, Hit& h) {
                                   + 6.0 * a0_a0 * (af - j_max * tf) * (af - j_max * tf) + 24.0 * af * j_max_j_max * g1
                                   - 4.0 * a0 * (af_p3 - 3.0 * af_af * j_max * tf + 6.0 * j_max_j_max * (-pd + tf * vf))
                                   - 12.0 * j_max_j_max * (-vd_vd + j_max * tf * g2))
-                               / 3.0)
+                               / THREE)
                           / j_max;
         const real h1 = sqrt((a0_a0 + af_af - 2.0 * a0 * af - 2.0 * ad * j_max * tf + 2.0 * h0) / j_max_j_max + tf_tf);
         t[0] = -(a0_a0 + af_af + 2.0 * a0 * (j_max * tf - af) - 2.0 * j_max * vd + h0) / (2.0 * j_max * (-ad + j_max * tf));
         t[1] = 0.0;
-        t[2] = (tf - h1) * 0.5 - ad / (2.0 * j_max);
+        t[2] = (tf - h1) * 0.5 - ad / twice(j_max);
         t[3] = 0.0;
         t[4] = 0.0;
         t[5] = h1;
@@ -80,14 +80,14 @@ __device__ RK_S2_FN bool s2_acc1(const S2& s, const Lim& L, Hit& h) {
                                   + 6.0 * a0_a0 * (af + j_max * tf) * (af + j_max * tf) + 24.0 * af * j_max_j_max * g1
                                   - 4.0 * a0 * (a0_a0 * af + af_p3 + 3.0 * af_af * j_max * tf + 6.0 * j_max_j_max * (-pd + tf * vf))
                                   + 12.0 * j_max_j_max * (vd_vd + j_max * tf * g2))
-                               / 3.0)
+                               / THREE)
                           / j_max;
         const real h1 = sqrt((a0_a0 + af_af - 2.0 * a0 * af + 2.0 * ad * j_max * tf + 2.0 * h0) / j_max_j_max + tf_tf);
         t[0] = 0.0;
         t[1] = 0.0;
         t[2] = -(a0_a0 + af_af - 2.0 * a0 * af + 2.0 * j_max * (vd - a0 * tf) + h0) / (2.0 * j_max * (ad + j_max * tf));
         t[3] = 0.0;
-        t[4] = ad / (2.0 * j_max) + (tf - h1) * 0.5;
+        t[4] = ad / twice(j_max) + (tf - h1) * 0.5;
         t[5] = h1;
         t[6] = tf - (t[5] + t[4] + t[2]);
         RK_TRY(UDUD, L_ACC1, j_max)
@@ -143,7 +143,7 @@ __device__ RK_S2_FN bool s2_acc0(const S2& s, const Lim& L, Hit& h) {
     RK_S2_LOCALS
     // UDUD
     {
-        const real h1 = sqrt(ad_ad / (2.0 * j_max_j_max) - ad * (a_max - a0) / (j_max_j_max) + (a_max * tf - vd) / j_max);
+        const real h1 = sqrt(ad_ad / twice(j_max_j_max) - ad * (a_max - a0) / (j_max_j_max) + (a_max * tf - vd) / j_max);
         t[0] = (a_max - a0) / j_max;
         t[1] = tf - ad / j_max - 2.0 * h1;
         t[2] = h1;
@@ -166,7 +166,7 @@ __device__ RK_S2_FN bool s2_acc0(const S2& s, const Lim& L, Hit& h) {
                 + 6.0 * af * (a_max * a_max - j_max * vd) + 3.0 * a0 * (af_af - 2.0 * (a_max * a_max + j_max * vd))
                 - 6.0 * j_max * (a_max * (a_max * tf - 2.0 * vd) + j_max * g2))
                / h1;
-        t[2] = -(ad + h0 / h1) / (2.0 * j_max) + tf * 0.5 - t[1] * 0.5;
+        t[2] = -(ad + h0 / h1) / twice(j_max) + tf * 0.5 - t[1] * 0.5;
         t[3] = h0 / (j_max * h1);
         t[4] = 0.0;
         t[5] = 0.0;

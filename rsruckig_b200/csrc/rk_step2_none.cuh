@@ -112,7 +112,7 @@ __device__ RK_S2_FN bool s2_none(const S2& s, const Lim& L, Hit& h) {
                                            * (a0 * tf_tf - 2.0 * pd + 2.0 * tf * v0 + h1 * h1 * j_max * (tf - 2.0 * tt)
                                               + j_max * tf * (2.0 * h1 * tt - tt * tt - (h1 - tt) * tf)))
                                     / (6.0 * j_max_j_max);
-                const real deriv = (h0 * (-ad + j_max * tf) * (h2 - 1.0)) / (2.0 * j_max) + h1 * (-ad + j_max * (tf - h1) - h0 * h2);
+                const real deriv = (h0 * (-ad + j_max * tf) * (h2 - 1.0)) / twice(j_max) + h1 * (-ad + j_max * (tf - h1) - h0 * h2);
                 tt -= orig / deriv;
             }
             t[0] = tt;
@@ -138,7 +138,7 @@ __device__ RK_S2_FN bool s2_none(const S2& s, const Lim& L, Hit& h) {
         t[1] = 0.0;
         t[2] = 0.0;
         t[3] = (af_p3 - a0_p3 + 3.0 * (af_af - a0_a0) * j_max * tf - 3.0 * ad * (a0 * af + 2.0 * j_max * vd) - 6.0 * j_max_j_max * g2) / h1;
-        t[4] = (tf - t[3] - h0) * 0.5 - ad / (2.0 * j_max);
+        t[4] = (tf - t[3] - h0) * 0.5 - ad / twice(j_max);
         t[5] = h0;
         t[6] = (tf - t[3] + ad / j_max - h0) * 0.5;
         RK_TRY(UDDU, L_NONE, j_max)
@@ -195,7 +195,7 @@ __device__ RK_S2_FN bool s2_none(const S2& s, const Lim& L, Hit& h) {
                 const real deriv = (6.0 * j_max * h2 * h3 / fabs(j_max) + 2.0 * (-ad - j_max * tf) * h2
                                       - 2.0 * (3.0 * ad_ad + af * j_max * (8.0 * tt - 2.0 * tf) + 4.0 * a0 * j_max * (-2.0 * tt + tf)
                                                + 2.0 * j_max * (j_max * tt * (3.0 * tt - 2.0 * tf) - vd)))
-                                     / (4.0 * j_max);
+                                     / four_times(j_max);
                 tt -= orig / deriv;
             }
             const real h1 = sqrt(2.0 * ad_ad + 4.0 * j_max * (ad * tt + a0 * tf + j_max * tt * (tt - tf) - vd)) / fabs(j_max);
@@ -250,7 +250,7 @@ __device__ RK_S2_FN bool s2_none(const S2& s, const Lim& L, Hit& h) {
         for (int ri = 0; ri < roots.n; ++ri) {
             const real tt = roots.get(ri);
             if (tt > tf || tt > (a_max - a0) / j_max) continue;
-            const real h1 = sqrt(ad_ad / (2.0 * j_max_j_max) + (a0 * (tt + tf) - af * tt + j_max * tt * tf - vd) / j_max);
+            const real h1 = sqrt(ad_ad / twice(j_max_j_max) + (a0 * (tt + tf) - af * tt + j_max * tt * tf - vd) / j_max);
             t[0] = tt;
             t[1] = tf - ad / j_max - 2.0 * h1;
             t[2] = h1;
@@ -302,7 +302,7 @@ __device__ RK_S2_FN bool s2_none(const S2& s, const Lim& L, Hit& h) {
     {
         t[0] = (ad_ad / j_max + 2.0 * (a0 + af) * tf - j_max * tf_tf - 4.0 * vd) / (4.0 * (ad - j_max * tf));
         t[1] = 0.0;
-        t[2] = -ad / (2.0 * j_max) + tf * 0.5;
+        t[2] = -ad / twice(j_max) + tf * 0.5;
         t[3] = 0.0;
         t[4] = 0.0;
         t[5] = 0.0;

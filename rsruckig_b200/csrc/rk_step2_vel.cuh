@@ -17,7 +17,7 @@ __device__ __forceinline__ bool vel_uddu_root(const S2& s, const Lim& L, Hit& h,
     RK_S2_LOCALS
     // Single Newton step (regarding pd)
     {
-        const real h1 = sqrt((a0_a0 + af_af) / (2.0 * j_max_j_max) + (2.0 * a0 * tt + j_max * tt * tt - vd) / j_max);
+        const real h1 = sqrt((a0_a0 + af_af) / twice(j_max_j_max) + (2.0 * a0 * tt + j_max * tt * tt - vd) / j_max);
         if (h1 == h1) {  // a NaN h1 makes orig NaN and the reference's guard below skips the step: skip the arithmetic as well
             const real orig = -pd
                                 - (2.0 * a0_p3 + 4.0 * af_p3 + 24.0 * a0 * j_max * tt * (af + j_max * (h1 + tt - tf)) + 6.0 * a0_a0 * (af + j_max * (2.0 * tt - tf))
@@ -30,7 +30,7 @@ __device__ __forceinline__ bool vel_uddu_root(const S2& s, const Lim& L, Hit& h,
     }
     if (tt > tf || tt != tt) return false;
 
-    const real h1 = sqrt((a0_a0 + af_af) / (2.0 * j_max_j_max) + (tt * (2.0 * a0 + j_max * tt) - vd) / j_max);
+    const real h1 = sqrt((a0_a0 + af_af) / twice(j_max_j_max) + (tt * (2.0 * a0 + j_max * tt) - vd) / j_max);
     if (h1 != h1) return false;  // t[4] = NaN fails the profile check
     t[0] = tt;
     t[1] = 0.0;
@@ -48,14 +48,14 @@ __device__ __forceinline__ bool vel_udud_root(const S2& s, const Lim& L, Hit& h,
     RK_S2_LOCALS
     // Double Newton step (regarding pd)
     {
-        real h1 = sqrt((af_af - a0_a0) / (2.0 * j_max_j_max) - ((2.0 * a0 + j_max * tt) * tt - vd) / j_max);
+        real h1 = sqrt((af_af - a0_a0) / twice(j_max_j_max) - ((2.0 * a0 + j_max * tt) * tt - vd) / j_max);
         if (h1 != h1) return false;  // NaN poisons tt and with it every duration: the check fails
         real orig = -pd + (af_p3 - a0_p3 + 3.0 * a0_a0 * j_max * (tf - 2.0 * tt)) / (6.0 * j_max_j_max) + (2.0 * a0 + j_max * tt) * tt * (tf - tt)
                       + (j_max * h1 - af) * h1 * h1 + tf * v0;
         real deriv_newton = (a0 + j_max * tt) * (2.0 * (af + j_max * tf) - 3.0 * j_max * (h1 + tt) - a0) / j_max;
         tt -= orig / deriv_newton;
 
-        h1 = sqrt((af_af - a0_a0) / (2.0 * j_max_j_max) - ((2.0 * a0 + j_max * tt) * tt - vd) / j_max);
+        h1 = sqrt((af_af - a0_a0) / twice(j_max_j_max) - ((2.0 * a0 + j_max * tt) * tt - vd) / j_max);
         orig = -pd + (af_p3 - a0_p3 + 3.0 * a0_a0 * j_max * (tf - 2.0 * tt)) / (6.0 * j_max_j_max) + (2.0 * a0 + j_max * tt) * tt * (tf - tt)
                + (j_max * h1 - af) * h1 * h1 + tf * v0;
         if (fabs(orig) > 1e-9) {
@@ -63,7 +63,7 @@ __device__ __forceinline__ bool vel_udud_root(const S2& s, const Lim& L, Hit& h,
             tt -= orig / deriv_newton;
         }
     }
-    const real h1 = sqrt((af_af - a0_a0) / (2.0 * j_max_j_max) - ((2.0 * a0 + j_max * tt) * tt - vd) / j_max);
+    const real h1 = sqrt((af_af - a0_a0) / twice(j_max_j_max) - ((2.0 * a0 + j_max * tt) * tt - vd) / j_max);
     t[0] = tt;
     t[1] = 0.0;
     t[2] = tt + a0 / j_max;
@@ -83,7 +83,7 @@ __device__ RK_S2_FN bool s2_vel_uddu(const S2& s, const Lim& L, Hit& h) {
     const real tz_max = rmin((tf - a0 / j_max) * 0.5, (a_max - a0) / j_max);
 
     if (fabs(v0) < EPS && fabs(a0) < EPS && fabs(vf) < EPS && fabs(af) < EPS) {
-        const Roots roots = solve_cub(1.0, -tf * 0.5, 0.0, pd / (2.0 * j_max));
+        const Roots roots = solve_cub(1.0, -tf * 0.5, 0.0, pd / twice(j_max));
 #pragma unroll 1
         for (int ri = 0; ri < roots.n; ++ri) {
             real tt = roots.get(ri);
@@ -200,7 +200,7 @@ __device__ __forceinline__ bool vel_uddu_candidates(const S2& s, const Lim& L, H
 
     if (active && fabs(v0) < EPS && fabs(a0) < EPS && fabs(vf) < EPS && fabs(af) < EPS) {  // rare, handled out of step
         active = false;
-        const Roots roots = solve_cub(1.0, -tf * 0.5, 0.0, pd / (2.0 * j_max));
+        const Roots roots = solve_cub(1.0, -tf * 0.5, 0.0, pd / twice(j_max));
 #pragma unroll 1
         for (int ri = 0; ri < roots.n && !found; ++ri) {
             real tt = roots.get(ri);
@@ -306,7 +306,7 @@ __device__ RK_S2_FN bool s2_vel_udud(const S2& s, const Lim& L, Hit& h) {
     double pol[7];
     pol[0] = 1.0;
     pol[1] = (5.0 * a0 - ph5) / j_max;
-    pol[2] = (39.0 * a0_a0 - ph1 - 16.0 * a0 * ph5) / (4.0 * j_max_j_max);
+    pol[2] = (39.0 * a0_a0 - ph1 - 16.0 * a0 * ph5) / four_times(j_max_j_max);
     pol[3] = (55.0 * a0_p3 - 33.0 * a0_a0 * ph5 - 6.0 * a0 * ph1 + 2.0 * ph2) / (6.0 * j_max_j_max * j_max);
     pol[4] = (101.0 * a0_p4 + ph4 - 76.0 * a0_p3 * ph5 - 30.0 * a0_a0 * ph1 + 16.0 * a0 * ph2) / (24.0 * j_max_j_max * j_max_j_max);
     pol[5] = (a0 * (11.0 * a0_p4 + ph4 - 10.0 * a0_p3 * ph5 - 6.0 * a0_a0 * ph1 + 4.0 * a0 * ph2)) / (12.0 * j_max_j_max * j_max_j_max * j_max);
@@ -401,7 +401,7 @@ __device__ __forceinline__ bool s2_vel_udud_lockstep(const S2& s, const Lim& L, 
         const real ph5 = af + j_max * tf;
         pol[0] = 1.0;
         pol[1] = (5.0 * a0 - ph5) / j_max;
-        pol[2] = (39.0 * a0_a0 - ph1 - 16.0 * a0 * ph5) / (4.0 * j_max_j_max);
+        pol[2] = (39.0 * a0_a0 - ph1 - 16.0 * a0 * ph5) / four_times(j_max_j_max);
         pol[3] = (55.0 * a0_p3 - 33.0 * a0_a0 * ph5 - 6.0 * a0 * ph1 + 2.0 * ph2) / (6.0 * j_max_j_max * j_max);
         pol[4] = (101.0 * a0_p4 + ph4 - 76.0 * a0_p3 * ph5 - 30.0 * a0_a0 * ph1 + 16.0 * a0 * ph2) / (24.0 * j_max_j_max * j_max_j_max);
         pol[5] = (a0 * (11.0 * a0_p4 + ph4 - 10.0 * a0_p3 * ph5 - 6.0 * a0_a0 * ph1 + 4.0 * a0 * ph2)) / (12.0 * j_max_j_max * j_max_j_max * j_max);

@@ -111,7 +111,7 @@ __device__ __forceinline__ bool step2_vel3_dir(const Bound& b, real tf, real vd,
     {
         const real h1 = sqrt((-ad * ad + 2.0 * j_max * ((b.a0 + b.af) * tf - 2.0 * vd)) / (j_max * j_max) + tf * tf);
         zero_t(t);
-        t[0] = ad / (2.0 * j_max) + (tf - h1) * 0.5;
+        t[0] = ad / twice(j_max) + (tf - h1) * 0.5;
         t[1] = h1;
         t[2] = tf - (t[0] + h1);
         if (check_vel3(t, UDDU, L_ACC0, j_max, a_max, a_min, b)) { set_cand(c, t, j_max, 0.0, L_ACC0, dir, UDDU); return true; }
