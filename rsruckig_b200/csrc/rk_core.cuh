@@ -614,7 +614,11 @@ template <int N>
 __device__ __forceinline__ void poly_monic_deri(const double (&c)[N], double (&d)[N - 1]) {
     d[0] = 1.0;
 #pragma unroll
-    for (int i = 1; i < N - 1; ++i) d[i] = sdiv((double)(N - 1 - i) * c[i], (double)(N - 1));
+    for (int i = 1; i < N - 1; ++i) {
+        const double num = (double)(N - 1 - i) * c[i];
+        // the callers' degrees are 5 and 6: a literal divisor, through its constant reciprocal (rk_math.cuh)
+        d[i] = (N - 1 == 5) ? div_lit<5>(num) : ((N - 1 == 6) ? div_lit<6>(num) : sdiv(num, (double)(N - 1)));
+    }
 }
 
 // roots.rs:424-481: safeguarded Newton / bisection, at most 128 iterations, tolerance 1e-14.

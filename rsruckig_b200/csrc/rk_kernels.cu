@@ -617,7 +617,9 @@ __global__ void __launch_bounds__(256) k_selftest_division(int64_t n, uint64_t s
         const bool ok6 = (ref6 != ref6) ? (q6 != q6) : (__double_as_longlong(q6) == __double_as_longlong(ref6));
         const double q3c = div3(a), ref3c = a / 3.0;  // the three divisions by 3 of the resolvent (roots.rs:237-252)
         const bool ok3c = (ref3c != ref3c) ? (q3c != q3c) : (__double_as_longlong(q3c) == __double_as_longlong(ref3c));
-        bad += (ok1 ? 0 : 1) + (ok2 ? 0 : 1) + (ok3 ? 0 : 1) + (ok6 ? 0 : 1) + (ok3c ? 0 : 1);
+        const double q5 = div_lit<5>(a), ref5 = a / 5.0;  // poly_monic_deri of the quintic (roots.rs:389-397)
+        const bool ok5 = (ref5 != ref5) ? (q5 != q5) : (__double_as_longlong(q5) == __double_as_longlong(ref5));
+        bad += (ok1 ? 0 : 1) + (ok2 ? 0 : 1) + (ok3 ? 0 : 1) + (ok6 ? 0 : 1) + (ok3c ? 0 : 1) + (ok5 ? 0 : 1);
     }
     if (bad) atomicAdd(mismatches, bad);
 }
