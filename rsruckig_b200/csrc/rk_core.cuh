@@ -96,15 +96,25 @@ __device__ __forceinline__ bool check_pos3_body(double t0, double t1, double t2,
     v[0] = v0;
 #pragma unroll
     for (int i = 0; i < 7; ++i) {
-        // j[1], j[3], j[5] are exactly 0: t * 0 is +-0 (or NaN), and +-0 / 6 is that same +-0, so the division is skipped there
-        const double tj = t[i] * j[i];
-        a[i + 1] = a[i] + tj;
-        v[i + 1] = v[i] + t[i] * (a[i] + tj / 2.0);
-        p = p + t[i] * (v[i] + t[i] * (a[i] / 2.0 + ((i & 1) ? tj : div6(tj))));
+        if (i & 1) {
+            // j[1], j[3], j[5] are exactly +0 and every t[i] is finite and >= 0 here (NaN and the infinite sum were rejected
+            // above), so t * j is +0 and the reference's `+ tj`, `+ tj / 2`, `+ tj / 6` add +0: they can only turn a -0 into +0,
+            // which no comparison of this function sees (the integrated values themselves never leave it). Five operations
+            // less per constant-acceleration phase.
+            a[i + 1] = a[i];
+            v[i + 1] = v[i] + t[i] * a[i];
+            p = p + t[i] * (v[i] + t[i] * (a[i] / 2.0));
+        } else {
+            const double tj = t[i] * j[i];
+            a[i + 1] = a[i] + tj;
+            v[i + 1] = v[i] + t[i] * (a[i] + tj / 2.0);
+            p = p + t[i] * (v[i] + t[i] * (a[i] / 2.0 + div6(tj)));
+        }
 
         if (i == 2 && zero_a3) a[3] = 0.0;
 
-        if (i > 1 && a[i + 1] * a[i] < -EPS) {
+        // (after a constant-acceleration phase a[i + 1] * a[i] is a square: the test can only fire for i = 2, 4, 6)
+        if (i > 1 && !(i & 1) && a[i + 1] * a[i] < -EPS) {
             const double v_a_zero = v[i] - sdiv(a[i] * a[i], 2.0 * j[i]);
             if (v_a_zero > v_upp_lim || v_a_zero < v_low_lim) return false;
         }
