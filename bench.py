@@ -377,7 +377,41 @@ def run_b200(args):
                      "ceiling": world * n_e / (in_bytes / (float(t_min.item()) * 1e9)), "unit": UNIT,
                      "note": "all ranks copying pinned host memory to their GPUs concurrently; ceiling = trajectories/s if the step were nothing "
                              "but the slowest rank's input copy (504 B per trajectory)"}
-        e2e = {"value": n_e * world * k_e2e / float(t_e.item()), "unit": UNIT, "steps": k_e2e, "n_per_gpu": n_e,
+        # a fleet of identical robots: the same current / target states, the five limit arrays shared per DoF (RK_LIMITS_PER_DOF,
+        # [dof] instead of [dof][n]): 336 instead of 504 bytes staged per trajectory. Another workload (other limits), reported apart.
+        fleet = None
+        if not args.no_extras:
+            hs = {k: v for k, v in hf.items() if not k.startswith("max_")}
+            for k in ("max_velocity", "max_acceleration", "max_jerk"):
+                hs[k] = hf[k].max(dim=1).values.contiguous().pin_memory()  # the largest limit of the batch: the inputs stay valid
+
+            def step_fleet():
+                otg_e.calculate(hs, n=n_e, memory_space=cabi.RK_MEM_HOST, status=h_status, duration=h_duration, limits_layout=cabi.RK_LIMITS_PER_DOF)
+
+            step_fleet()
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            with torch.cuda.stream(stream):
+                f0.record(stream)
+                for _ in range(k_e2e):
+                    step_fleet()
+                f1.record(stream)
+            otg.sync()
+            torch.cuda.synchronize()
+            t_f = torch.tensor([f0.elapsed_time(f1) * 1e-3], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.barrier()
+                dist.all_reduce(t_f, op=dist.ReduceOp.MAX)
+            fleet = {"value": n_e * world * k_e2e / float(t_f.item()), "unit": UNIT,
+                     "h2d_bytes_per_step": int(sum(v.numel() * v.element_size() for v in hs.values())),
+                     "working_fraction": float((h_status == 0).float().mean().item()),
+                     "note": "same current / target states, max_velocity / max_acceleration / max_jerk shared per DoF (limits_layout = "
+                             "RK_LIMITS_PER_DOF: [dof] arrays, the batch's largest values): a fleet of identical robots stages 336 instead of "
+                             "504 bytes per trajectory; not the headline workload"}
+            step_host()  # the headline workload's results back in place (the status comparison below and the readers after it)
+        e2e = {"value": n_e * world * k_e2e / float(t_e.item()), "unit": UNIT, "steps": k_e2e, "n_per_gpu": n_e, "shared_limits": fleet,
                "h2d_bytes_per_step": int(sum(v.numel() * v.element_size() for v in hf.values())), "host_binding": binding, "host_path": host_path,
                "d2h_bytes_per_step": int(h_status.numel() * 4 + h_duration.numel() * 8),
                "note": "rk_calculate_batch with RK_MEM_HOST on pinned buffers; status + duration (12 B per trajectory) come back, the trajectories "

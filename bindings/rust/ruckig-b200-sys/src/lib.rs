@@ -19,6 +19,8 @@ pub const RK_ERRORS_THROW: i32 = 0;
 pub const RK_ERRORS_IGNORE: i32 = 1;
 pub const RK_MEM_HOST: i32 = 0;
 pub const RK_MEM_DEVICE: i32 = 1;
+pub const RK_LIMITS_PER_TRAJECTORY: i32 = 0;
+pub const RK_LIMITS_PER_DOF: i32 = 1;  // max_* / min_* arrays are [dof], one value per DoF for the whole batch
 pub const RK_RESULT_FULL: i32 = 0;     // profile.rs:76-118 verbatim, 59 doubles per (DoF, trajectory)
 pub const RK_RESULT_COMPACT: i32 = 1;  // 20 doubles per (DoF, trajectory), expanded on the fly by every reader
 pub const RK_MAX_DOF: usize = 64;
@@ -62,6 +64,7 @@ pub struct rk_batch_desc {
     pub duration_discretization: i32,  // DurationDiscretization    (input_parameter.rs:110-117)
     pub error_mode: i32,               // 0 = ThrowErrorHandler, 1 = IgnoreErrorHandler (error.rs:98-122)
     pub memory_space: i32,             // 0 = host pointers, 1 = device pointers
+    pub limits_layout: i32,            // 0 = limit arrays [dof][n], 1 = [dof] shared by the whole batch (RK_LIMITS_PER_DOF)
     pub delta_time: f64,               // Ruckig::delta_time
     pub per_dof_control_interface: *const i32, // [dof] or null
     pub per_dof_synchronization: *const i32,   // [dof] or null

@@ -206,6 +206,7 @@ impl<const DOF: usize> BatchInput<DOF> {
             duration_discretization: discretization_code(&self.duration_discretization),
             error_mode,
             memory_space: sys::RK_MEM_HOST,
+            limits_layout: sys::RK_LIMITS_PER_TRAJECTORY,
             delta_time,
             per_dof_control_interface: if self.per_dof_control_interface.is_some() { ci.as_ptr() } else { ptr::null() },
             per_dof_synchronization: if self.per_dof_synchronization.is_some() { sy.as_ptr() } else { ptr::null() },

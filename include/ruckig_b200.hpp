@@ -487,6 +487,7 @@ struct BatchSettings {
     std::optional<std::vector<ControlInterface>> per_dof_control_interface;
     std::optional<std::vector<Synchronization>> per_dof_synchronization;
     bool device_memory = false;  // rk_batch_in / outputs are device pointers (asynchronous on stream()) instead of host pointers
+    bool limits_per_dof = false; // the five limit arrays are [dof], shared by the whole batch (RK_LIMITS_PER_DOF), instead of [dof][n]
 };
 
 template <size_t DOF, class E = ThrowErrorHandler>
@@ -570,6 +571,7 @@ private:
         d.duration_discretization = (int32_t)s.duration_discretization;
         d.error_mode = E::throws ? RK_ERRORS_THROW : RK_ERRORS_IGNORE;
         d.memory_space = s.device_memory ? RK_MEM_DEVICE : RK_MEM_HOST;
+        d.limits_layout = s.limits_per_dof ? RK_LIMITS_PER_DOF : RK_LIMITS_PER_TRAJECTORY;
         d.delta_time = delta_time;
         if (s.per_dof_control_interface) {
             for (ControlInterface c : *s.per_dof_control_interface) ci.push_back((int32_t)c);

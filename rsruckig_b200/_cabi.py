@@ -17,6 +17,7 @@ RK_SYNC_TIME, RK_SYNC_TIME_IF_NECESSARY, RK_SYNC_PHASE, RK_SYNC_NONE = 0, 1, 2, 
 RK_CONTINUOUS, RK_DISCRETE = 0, 1
 RK_ERRORS_THROW, RK_ERRORS_IGNORE = 0, 1
 RK_MEM_HOST, RK_MEM_DEVICE = 0, 1
+RK_LIMITS_PER_TRAJECTORY, RK_LIMITS_PER_DOF = 0, 1
 RK_RESULT_FULL, RK_RESULT_COMPACT = 0, 1
 RK_MAX_DOF = 64
 
@@ -46,6 +47,7 @@ class RkBatchDesc(C.Structure):
         ("duration_discretization", C.c_int32),
         ("error_mode", C.c_int32),
         ("memory_space", C.c_int32),
+        ("limits_layout", C.c_int32),
         ("delta_time", C.c_double),
         ("per_dof_control_interface", c_int32_p),
         ("per_dof_synchronization", c_int32_p),
@@ -96,7 +98,7 @@ def ptr(a) -> int | None:
 
 def make_desc(n, dof, *, control_interface=RK_POSITION, synchronization=RK_SYNC_TIME,
               duration_discretization=RK_CONTINUOUS, error_mode=RK_ERRORS_THROW, memory_space=RK_MEM_HOST,
-              delta_time=0.005, per_dof_control_interface=None, per_dof_synchronization=None):
+              delta_time=0.005, per_dof_control_interface=None, per_dof_synchronization=None, limits_layout=0):
     """Build an rk_batch_desc; returns (desc, keepalive) — keep `keepalive` referenced while desc is in use."""
     keep = []
     d = RkBatchDesc()
@@ -104,6 +106,7 @@ def make_desc(n, dof, *, control_interface=RK_POSITION, synchronization=RK_SYNC_
     d.control_interface, d.synchronization = int(control_interface), int(synchronization)
     d.duration_discretization, d.error_mode, d.memory_space = int(duration_discretization), int(error_mode), int(memory_space)
     d.delta_time = float(delta_time)
+    d.limits_layout = int(limits_layout)
     for name, val in (("per_dof_control_interface", per_dof_control_interface), ("per_dof_synchronization", per_dof_synchronization)):
         if val is not None:
             arr = np.ascontiguousarray(np.asarray([int(x) for x in val], dtype=np.int32))

@@ -477,15 +477,16 @@ class BatchRuckig:
     def calculate(self, fields: dict, *, n: int, memory_space: int, control_interface=ControlInterface.Position,
                   synchronization=Synchronization.Time, duration_discretization=DurationDiscretization.Continuous,
                   per_dof_control_interface=None, per_dof_synchronization=None, status=None, duration=None,
-                  independent_min_durations=None):
-        """fields: name -> buffer for the rk_batch_in members. Outputs (optional) are caller-owned buffers."""
+                  independent_min_durations=None, limits_layout=cabi.RK_LIMITS_PER_TRAJECTORY):
+        """fields: name -> buffer for the rk_batch_in members. Outputs (optional) are caller-owned buffers.
+        limits_layout=cabi.RK_LIMITS_PER_DOF: the five limit arrays are `[dof]`, shared by the whole batch."""
         self._ensure(n)
         desc, keep = cabi.make_desc(n, self.degrees_of_freedom, control_interface=control_interface,
                                     synchronization=synchronization, duration_discretization=duration_discretization,
                                     error_mode=cabi.RK_ERRORS_THROW if self.error_handler.throws else cabi.RK_ERRORS_IGNORE,
                                     memory_space=memory_space, delta_time=self.delta_time,
                                     per_dof_control_interface=per_dof_control_interface,
-                                    per_dof_synchronization=per_dof_synchronization)
+                                    per_dof_synchronization=per_dof_synchronization, limits_layout=limits_layout)
         bin_ = cabi.make_in(fields)
         out = cabi.RkBatchOut(cabi.ptr(status), cabi.ptr(duration), cabi.ptr(independent_min_durations))
         eng = self._engine
@@ -651,14 +652,15 @@ class BatchRollout:
     def update(self, fields: dict, *, control_interface=ControlInterface.Position, synchronization=Synchronization.Time,
                duration_discretization=DurationDiscretization.Continuous, per_dof_control_interface=None, per_dof_synchronization=None,
                new_position=None, new_velocity=None, new_acceleration=None, new_jerk=None, result=None, new_calculation=None,
-               time=None, pass_to_input=True, reset_time_on_new_calculation=False) -> int:
+               time=None, pass_to_input=True, reset_time_on_new_calculation=False,
+               limits_layout=cabi.RK_LIMITS_PER_TRAJECTORY) -> int:
         """One control cycle; returns the number of environments that were re-solved."""
         desc, keep = cabi.make_desc(self.n, self.degrees_of_freedom, control_interface=control_interface,
                                     synchronization=synchronization, duration_discretization=duration_discretization,
                                     error_mode=cabi.RK_ERRORS_THROW if self.error_handler.throws else cabi.RK_ERRORS_IGNORE,
                                     memory_space=cabi.RK_MEM_DEVICE, delta_time=self.delta_time,
                                     per_dof_control_interface=per_dof_control_interface,
-                                    per_dof_synchronization=per_dof_synchronization)
+                                    per_dof_synchronization=per_dof_synchronization, limits_layout=limits_layout)
         bin_ = cabi.make_in(fields)
         out = cabi.RkUpdateOut(cabi.ptr(new_position), cabi.ptr(new_velocity), cabi.ptr(new_acceleration), cabi.ptr(new_jerk),
                                cabi.ptr(result), cabi.ptr(new_calculation), cabi.ptr(time), int(bool(pass_to_input)),

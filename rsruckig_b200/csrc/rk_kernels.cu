@@ -229,6 +229,7 @@ __global__ void __launch_bounds__(RK_AT_BLOCK, COMPACT ? 7 : RK_AT_MINB) k_at_ti
 struct UpdateParams {
     int64_t n;
     int32_t dof;
+    int32_t lim_per_dof;            // the caller's five limit arrays (in[6..10]) are [dof]; the stored copies are always [dof][n]
     // the caller's inputs ([dof][n]; v_min / a_min / enabled / min_dur may be null) and the copies of the last calculation
     const double* in[11];
     double* last[11];
@@ -255,7 +256,7 @@ __global__ void __launch_bounds__(256) k_upd_dirty(const UpdateParams U) {
             const int64_t g = (int64_t)d * U.n + i;
 #pragma unroll
             for (int f = 0; f < 11; ++f)
-                if (U.in[f] && !(U.in[f][g] == U.last[f][g])) dirty = true;
+                if (U.in[f] && !(U.in[f][(f >= 6 && U.lim_per_dof) ? (int64_t)d : g] == U.last[f][g])) dirty = true;
             if (U.enabled && U.enabled[g] != U.last_enabled[g]) dirty = true;
         }
         if (!dirty && U.min_dur) {
@@ -284,7 +285,7 @@ __global__ void __launch_bounds__(256) k_upd_gather(const UpdateParams U, int64_
     const int64_t g = (int64_t)d * U.n + U.idx[j];
 #pragma unroll
     for (int f = 0; f < 11; ++f)
-        if (U.in[f]) U.gin[f][t] = U.in[f][g];
+        if (U.in[f]) U.gin[f][t] = U.in[f][(f >= 6 && U.lim_per_dof) ? (int64_t)d : g];
     if (U.enabled) U.g_enabled[t] = U.enabled[g];
     if (d == 0 && U.min_dur) U.g_min_dur[j] = U.min_dur[U.idx[j]];
 }
@@ -704,6 +705,7 @@ struct rk_handle {
     cudaEvent_t ev_copied[RK_STAGE_BUFS] = {}, ev_computed[RK_STAGE_BUFS] = {};
     void* chunk_in[RK_STAGE_BUFS] = {};
     size_t chunk_in_bytes = 0;
+    double* lim_dev = nullptr;  // [5][RK_MAX_DOF]: the limit arrays of a host-buffer call with RK_LIMITS_PER_DOF
 };
 
 struct rk_trajectories {
@@ -812,6 +814,9 @@ static rk_status fill_params(rk::Params& P, const rk_batch_desc* desc, const rk_
     P.v_min = in->min_velocity; P.a_min = in->min_acceleration;
     P.enabled = in->enabled; P.min_dur = in->minimum_duration;
     P.in_n = desc->n; P.in_shift = 0;
+    if (desc->limits_layout != RK_LIMITS_PER_TRAJECTORY && desc->limits_layout != RK_LIMITS_PER_DOF)
+        return fail(RK_ERR_INVALID_ARGUMENT, "limits_layout is neither RK_LIMITS_PER_TRAJECTORY nor RK_LIMITS_PER_DOF");
+    P.lim_per_dof = desc->limits_layout == RK_LIMITS_PER_DOF;
     return RK_OK;
 }
 
@@ -819,19 +824,22 @@ static rk_status fill_params(rk::Params& P, const rk_batch_desc* desc, const rk_
 static rk_status stage_inputs(rk_handle* h, rk::Params& P, size_t extra_dev_bytes, char** extra_dev) {
     const size_t per = sizeof(double) * (size_t)P.dof * (size_t)P.n;
     const double** slots[11] = {&P.p0, &P.v0, &P.a0, &P.pf, &P.vf, &P.af, &P.v_max, &P.a_max, &P.j_max, &P.v_min, &P.a_min};
+    const size_t per_lim = P.lim_per_dof ? sizeof(double) * (size_t)P.dof : per;  // slots 6..10 are the limit arrays
     size_t bytes = 0;
-    for (auto s : slots) if (*s) bytes += per;
+    for (int k = 0; k < 11; ++k) if (*slots[k]) bytes += ((k >= 6 ? per_lim : per) + 255) / 256 * 256;
     const size_t en_bytes = P.enabled ? (size_t)P.dof * (size_t)P.n : 0;
     const size_t md_bytes = P.min_dur ? sizeof(double) * (size_t)P.n : 0;
     const size_t in_bytes = bytes + md_bytes + ((en_bytes + 255) / 256) * 256;
     rk_status st = ensure_stage(h, in_bytes + extra_dev_bytes, 0);
     if (st != RK_OK) return st;
     char* dev = (char*)h->stage_dev;
-    for (auto s : slots) {
+    for (int k = 0; k < 11; ++k) {
+        const double** s = slots[k];
         if (!*s) continue;
-        RK_CUDA(cudaMemcpyAsync(dev, *s, per, cudaMemcpyHostToDevice, h->stream));
+        const size_t sz = k >= 6 ? per_lim : per;
+        RK_CUDA(cudaMemcpyAsync(dev, *s, sz, cudaMemcpyHostToDevice, h->stream));
         *s = (const double*)dev;
-        dev += per;
+        dev += (sz + 255) / 256 * 256;
     }
     if (P.min_dur) {
         RK_CUDA(cudaMemcpyAsync(dev, P.min_dur, md_bytes, cudaMemcpyHostToDevice, h->stream));
@@ -891,6 +899,7 @@ rk_status rk_destroy(rk_handle* h) {
         if (h->ev_copied[k]) cudaEventDestroy(h->ev_copied[k]);
         if (h->ev_computed[k]) cudaEventDestroy(h->ev_computed[k]);
     }
+    if (h->lim_dev) cudaFree(h->lim_dev);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->d2h_stream) cudaStreamDestroy(h->d2h_stream);
     if (h->ev_d2h) cudaEventDestroy(h->ev_d2h);
@@ -952,7 +961,8 @@ static rk_status calculate_impl(rk_handle* h, const rk_batch_desc* desc, const r
         const double** d11[11] = {&in_shifted.current_position, &in_shifted.current_velocity, &in_shifted.current_acceleration, &in_shifted.target_position,
                                   &in_shifted.target_velocity, &in_shifted.target_acceleration, &in_shifted.max_velocity, &in_shifted.max_acceleration,
                                   &in_shifted.max_jerk, &in_shifted.min_velocity, &in_shifted.min_acceleration};
-        for (auto p : d11) if (*p) *p += first;
+        const int n_shift = desc->limits_layout == RK_LIMITS_PER_DOF ? 6 : 11;  // [dof] limit arrays belong to every part
+        for (int k = 0; k < n_shift; ++k) if (*d11[k]) *d11[k] += first;
         if (in_shifted.enabled) in_shifted.enabled += first;
         if (in_shifted.minimum_duration) in_shifted.minimum_duration += first;
     }
@@ -1015,7 +1025,7 @@ static rk_status calculate_impl(rk_handle* h, const rk_batch_desc* desc, const r
     if (host) {
         const size_t per = sizeof(double) * (size_t)desc->dof * (size_t)cn_max;
         size_t bytes = 0;
-        for (auto m : dslots) if (host_ptrs.*m) bytes += per;
+        for (int k = 0; k < (P.lim_per_dof ? 6 : 11); ++k) if (host_ptrs.*dslots[k]) bytes += per;
         if (host_ptrs.min_dur) bytes += sizeof(double) * (size_t)cn_max;
         if (host_ptrs.enabled) bytes += (((size_t)desc->dof * (size_t)cn_max + 255) / 256) * 256;
         if (bytes > h->chunk_in_bytes) {
@@ -1026,6 +1036,15 @@ static rk_status calculate_impl(rk_handle* h, const rk_batch_desc* desc, const r
             h->chunk_in_bytes = 0;
             for (int k = 0; k < RK_STAGE_BUFS; ++k) RK_CUDA(cudaMalloc(&h->chunk_in[k], bytes));
             h->chunk_in_bytes = bytes;
+        }
+        if (P.lim_per_dof) {  // one value per DoF: copied once, ahead of the first chunk on the same stream
+            if (!h->lim_dev) RK_CUDA(cudaMalloc(&h->lim_dev, sizeof(double) * 5 * RK_MAX_DOF));
+            for (int k = 6; k < 11; ++k) {
+                if (!(host_ptrs.*dslots[k])) continue;
+                double* dst = h->lim_dev + (size_t)(k - 6) * RK_MAX_DOF;
+                RK_CUDA(cudaMemcpyAsync(dst, host_ptrs.*dslots[k], sizeof(double) * (size_t)desc->dof, cudaMemcpyHostToDevice, h->copy_stream));
+                P.*dslots[k] = dst;
+            }
         }
     }
 
@@ -1059,7 +1078,8 @@ static rk_status calculate_impl(rk_handle* h, const rk_batch_desc* desc, const r
             if (chunk_index >= RK_STAGE_BUFS) RK_CUDA(cudaStreamWaitEvent(h->copy_stream, h->ev_computed[buf], 0));
             char* dev = (char*)h->chunk_in[buf];
             const size_t per = sizeof(double) * (size_t)desc->dof * (size_t)P.cn;
-            for (auto m : dslots) {
+            for (int k = 0; k < (P.lim_per_dof ? 6 : 11); ++k) {
+                const auto m = dslots[k];
                 if (!(host_ptrs.*m)) continue;
                 RK_CUDA(cudaMemcpy2DAsync(dev, sizeof(double) * P.cn, host_ptrs.*m + off, sizeof(double) * stride, sizeof(double) * P.cn,
                                           (size_t)desc->dof, cudaMemcpyHostToDevice, h->copy_stream));
@@ -1463,6 +1483,7 @@ rk_status rk_update_batch(rk_handle* h, const rk_batch_desc* desc, const rk_batc
     U.enabled = in->enabled; U.last_enabled = r->last_enabled; U.g_enabled = r->g_enabled;
     U.min_dur = in->minimum_duration; U.last_min_dur = r->last_min_dur; U.g_min_dur = r->g_min_dur;
     U.force_all = force_all ? 1 : 0;
+    U.lim_per_dof = P.lim_per_dof;
     U.initialized = r->initialized; U.dirty = r->dirty; U.idx = r->idx; U.count = r->count;
 
     RK_CUDA(cudaMemsetAsync(r->count, 0, sizeof(uint32_t), h->stream));
@@ -1478,6 +1499,7 @@ rk_status rk_update_batch(rk_handle* h, const rk_batch_desc* desc, const rk_batc
         h->launches += 1;
         rk_batch_desc sub = *desc;
         sub.n = m;
+        sub.limits_layout = RK_LIMITS_PER_TRAJECTORY;  // the gathered inputs are per trajectory
         rk_batch_in gi{};
         gi.current_position = r->gin[0]; gi.current_velocity = r->gin[1]; gi.current_acceleration = r->gin[2];
         gi.target_position = r->gin[3]; gi.target_velocity = r->gin[4]; gi.target_acceleration = r->gin[5];

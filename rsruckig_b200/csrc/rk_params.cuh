@@ -22,6 +22,7 @@ struct Params {
     int32_t throw_mode;
     int32_t check_current, check_target;
     int32_t compact;  // trajectory storage layout: 0 = full Profile (59 slots), 1 = compact record (COMPACT_SLOTS, rk_store.cuh)
+    int32_t lim_per_dof;  // the five limit arrays are [dof] (RK_LIMITS_PER_DOF) instead of [dof][n]
     double delta_time;
     int8_t ci[RK_MAX_DOF];
     int8_t sync[RK_MAX_DOF];
@@ -60,9 +61,10 @@ __device__ __forceinline__ DofIn load_dof(const Params& P, int d, int64_t ig) {
     DofIn x;
     x.p0 = P.p0[g]; x.v0 = P.v0[g]; x.a0 = P.a0[g];
     x.pf = P.pf[g]; x.vf = P.vf[g]; x.af = P.af[g];
-    x.v_max = P.v_max[g]; x.a_max = P.a_max[g]; x.j_max = P.j_max[g];
-    x.v_min = P.v_min ? P.v_min[g] : -x.v_max;
-    x.a_min = P.a_min ? P.a_min[g] : -x.a_max;
+    const int64_t gl = P.lim_per_dof ? (int64_t)d : g;
+    x.v_max = P.v_max[gl]; x.a_max = P.a_max[gl]; x.j_max = P.j_max[gl];
+    x.v_min = P.v_min ? P.v_min[gl] : -x.v_max;
+    x.a_min = P.a_min ? P.a_min[gl] : -x.a_max;
     x.enabled = P.enabled ? (P.enabled[g] != 0) : true;
     return x;
 }

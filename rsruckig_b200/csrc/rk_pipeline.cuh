@@ -377,8 +377,11 @@ __global__ void __launch_bounds__(128, 8) k1_cand_check(const Params P) {
 // root) does the Newton polish, builds t[7] and validates the profile. A (DoF, direction) has 0-4 in-range roots and most
 // candidates die in the check, so phase B runs the expensive part with full warps instead of the few lanes that happened
 // to have a root in the same loop iteration. Root k of a sub-list writes slot k, which keeps the ascending order.
+#ifndef RK_QR_MINB
+#define RK_QR_MINB RK_MIN_BLOCKS
+#endif
 template <int TYPE>
-__global__ void __launch_bounds__(128, RK_MIN_BLOCKS) k1_quartic_roots(const Params P) {
+__global__ void __launch_bounds__(128, RK_QR_MINB) k1_quartic_roots(const Params P) {
     RK_PDL_ENTER();
     const int64_t wstride = (int64_t)P.dof * P.cn;
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1481,8 +1484,11 @@ __global__ void __launch_bounds__(RK_LS_BLOCK, RK_LS_MINB) k2_vel_scan_uddu(cons
 #ifndef RK_REFILL
 #define RK_REFILL 16
 #endif
+#ifndef RK_PO_MINB
+#define RK_PO_MINB 8
+#endif
 template <int N, bool DERIV>
-__global__ void __launch_bounds__(128, 8) k2_polish(const Params P, int counter_index, int cursor_index) {
+__global__ void __launch_bounds__(128, RK_PO_MINB) k2_polish(const Params P, int counter_index, int cursor_index) {
     RK_PDL_ENTER();
     const int64_t wstride = (int64_t)P.dof * P.cn;
     const uint32_t count = P.counters[counter_index];

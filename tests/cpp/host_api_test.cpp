@@ -184,6 +184,18 @@ static void test_batch_matches_single() {
     std::vector<double> duration_m(n, 0.0);
     multi.calculate(n, in, {}, status_m.data(), duration_m.data());
     CHECK(multi.parts() == 2 && status_m == status && duration_m == duration);
+
+    // RK_LIMITS_PER_DOF: one limit per DoF for the whole batch (the limits above are the same for every trajectory)
+    const std::vector<double> vm_d(D, 1.0), am_d(D, 2.0), jm_d(D, 3.0);
+    rk_batch_in shared = in;
+    shared.max_velocity = vm_d.data(); shared.max_acceleration = am_d.data(); shared.max_jerk = jm_d.data();
+    BatchSettings fleet;
+    fleet.limits_per_dof = true;
+    std::vector<int32_t> status_s(n, -1);
+    std::vector<double> duration_s(n, 0.0), t_shared(7 * D * n);
+    compact.calculate(n, shared, fleet, status_s.data(), duration_s.data());
+    compact.read(RK_FIELD_T, t_shared.data());
+    CHECK(status_s == status && duration_s == duration && t_shared == t_full);
 }
 
 // Never called: instantiates the device-buffer classes so that the whole header is compiled under -Wall -Wextra -Werror (their

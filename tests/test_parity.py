@@ -311,3 +311,71 @@ def test_empty_batch_is_a_no_op(gpu):
     otg.calculate(f, n=0, memory_space=cabi.RK_MEM_HOST, status=status, duration=duration)
     otg.sync()
     assert otg.kernel_launches() == before
+
+
+def _same_results(a, b, *, label):
+    """Two BatchRuckig objects hold the same results bit for bit (status, duration, codes, every profile field)."""
+    for f in (cabi.RK_FIELD_STATUS, cabi.RK_FIELD_DURATION, cabi.RK_FIELD_LIMITING_DOF, cabi.RK_FIELD_INDEPENDENT_MIN_DURATIONS,
+              cabi.RK_FIELD_CODES, cabi.RK_FIELD_ERROR_DETAIL) + PROFILE_FIELDS:
+        x, y = a.read(f), b.read(f)
+        same = (x == y) | ((x != x) & (y != y))
+        assert same.all(), f"{label}: field {f} differs in {int((~same).sum())} places"
+
+
+def test_limits_per_dof_layout(gpu):
+    """RK_LIMITS_PER_DOF: the five limit arrays as [dof] (a fleet of identical robots) give the same bits as the same values
+    spelled out per trajectory — host buffers staged in several chunks, device buffers, asymmetric minimum limits, validation,
+    and the closed loop (rk_update_batch)."""
+    import torch
+    from rsruckig_b200 import BatchRollout, ThrowErrorHandler
+    dof = 7
+    rng = np.random.default_rng(5)
+    lim = {"max_velocity": rng.uniform(2.0, 12.0, dof), "max_acceleration": rng.uniform(2.0, 12.0, dof), "max_jerk": rng.uniform(1.0, 12.0, dof),
+           "min_velocity": -rng.uniform(2.0, 12.0, dof), "min_acceleration": -rng.uniform(2.0, 12.0, dof)}
+    for n, space in ((700_001, cabi.RK_MEM_HOST), (50_000, cabi.RK_MEM_DEVICE)):  # 700 001 x 7 items = two chunks of scratch
+        f = workloads.bench_inputs(n, dof, seed=21)
+        # targets inside the shared limits now and then outside them: both statuses must come out the same in both layouts
+        full = dict(f)
+        for k, v in lim.items():
+            full[k] = np.ascontiguousarray(np.repeat(v[:, None], n, axis=1))
+        shared = dict(f)
+        shared.update({k: np.ascontiguousarray(v) for k, v in lim.items()})
+        if space == cabi.RK_MEM_DEVICE:
+            full = {k: torch.from_numpy(v).cuda() for k, v in full.items()}
+            shared = {k: torch.from_numpy(v).cuda() for k, v in shared.items()}
+        a, b = gpu(dof, 0.005, ThrowErrorHandler), gpu(dof, 0.005, ThrowErrorHandler)
+        a.calculate(full, n=n, memory_space=space)
+        b.calculate(shared, n=n, memory_space=space, limits_layout=cabi.RK_LIMITS_PER_DOF)
+        st = a.read(cabi.RK_FIELD_STATUS)
+        assert (st == 0).sum() > 0.3 * n and (st == -100).sum() > 0, "the batch should hold valid and invalid problems"
+        _same_results(a, b, label=f"limits per DoF, n = {n}, memory space {space}")
+    # validate_input
+    n = 20_000
+    f = workloads.bench_inputs(n, dof, seed=22)
+    full, shared = dict(f), dict(f)
+    for k, v in lim.items():
+        full[k] = np.ascontiguousarray(np.repeat(v[:, None], n, axis=1))
+        shared[k] = np.ascontiguousarray(v)
+    otg = gpu(dof, 0.005, ThrowErrorHandler)
+    for cc, ct in ((True, True), (False, True)):
+        va, ra = otg.validate(full, n=n, check_current=cc, check_target=ct)
+        vb, rb = otg.validate(shared, n=n, check_current=cc, check_target=ct, limits_layout=cabi.RK_LIMITS_PER_DOF)
+        assert np.array_equal(va, vb) and np.array_equal(ra, rb)
+    # closed loop: ten cycles, every cycle's state equal
+    n = 4096
+    f = workloads.bench_inputs(n, dof, seed=23)
+    states = []
+    for layout in (cabi.RK_LIMITS_PER_TRAJECTORY, cabi.RK_LIMITS_PER_DOF):
+        g = {k: torch.from_numpy(v.copy()).cuda() for k, v in f.items()}
+        for k, v in lim.items():
+            g[k] = torch.from_numpy(np.repeat(v[:, None], n, axis=1).copy() if layout == cabi.RK_LIMITS_PER_TRAJECTORY else v.copy()).cuda()
+        roll = BatchRollout(n, dof, 0.01, ThrowErrorHandler)
+        pos = torch.zeros((dof, n), dtype=torch.float64, device="cuda")
+        res = torch.zeros(n, dtype=torch.int32, device="cuda")
+        seq = []
+        for _ in range(10):
+            roll.update(g, new_position=pos, result=res, pass_to_input=True, limits_layout=layout)
+            seq.append((pos.cpu().numpy().copy(), res.cpu().numpy().copy()))
+        states.append(seq)
+    for (pa, ra), (pb, rb) in zip(*states):
+        assert np.array_equal(ra, rb) and np.array_equal(pa, pb)
