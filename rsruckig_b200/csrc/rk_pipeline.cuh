@@ -49,6 +49,19 @@
 #ifndef RK_MIN_BLOCKS
 #define RK_MIN_BLOCKS 4
 #endif
+// resident blocks per SM of the list-driven check kernels (A/B knobs; 128 threads per block)
+#ifndef RK_QC_MINB
+#define RK_QC_MINB(TYPE) ((TYPE) == 0 ? 6 : 8)
+#endif
+#ifndef RK_CK_MINB
+#define RK_CK_MINB 8
+#endif
+#ifndef RK_VC_MINB
+#define RK_VC_MINB 6
+#endif
+#ifndef RK_S0_MINB
+#define RK_S0_MINB 6
+#endif
 
 namespace rk {
 
@@ -351,7 +364,7 @@ __global__ void __launch_bounds__(128, RK_CC_MINB) k1_closed_cands(const Params 
         if ((parked4 >> v) & 1u) P.rq_item[e++] = make_uint2((uint32_t)wi, (uint32_t)ds | (uint32_t)((8 + ds) << 1) | ((uint32_t)v << 8));
 }
 
-__global__ void __launch_bounds__(128, 8) k1_cand_check(const Params P) {
+__global__ void __launch_bounds__(128, RK_CK_MINB) k1_cand_check(const Params P) {
     RK_PDL_ENTER();
     const int64_t wstride = (int64_t)P.dof * P.cn;
     const uint32_t count = P.counters[23];
@@ -378,7 +391,7 @@ __global__ void __launch_bounds__(128, 8) k1_cand_check(const Params P) {
 // candidates die in the check, so phase B runs the expensive part with full warps instead of the few lanes that happened
 // to have a root in the same loop iteration. Root k of a sub-list writes slot k, which keeps the ascending order.
 #ifndef RK_QR_MINB
-#define RK_QR_MINB RK_MIN_BLOCKS
+#define RK_QR_MINB 12  // 40 registers, 72 bytes of spills: the kernels are bound by issue slots under fp64 dependency stalls, and 48 warps per SM beat 32 (+0.8 % on the step)
 #endif
 template <int TYPE>
 __global__ void __launch_bounds__(128, RK_QR_MINB) k1_quartic_roots(const Params P) {
@@ -437,7 +450,7 @@ __global__ void __launch_bounds__(128, RK_QR_MINB) k1_quartic_roots(const Params
 }
 
 template <int TYPE>
-__global__ void __launch_bounds__(128, TYPE == 0 ? 6 : 8) k1_quartic_check(const Params P) {
+__global__ void __launch_bounds__(128, RK_QC_MINB(TYPE)) k1_quartic_check(const Params P) {
     RK_PDL_ENTER();
     const int64_t wstride = (int64_t)P.dof * P.cn;
     const uint32_t count = P.counters[20 + TYPE];
@@ -1331,7 +1344,7 @@ __device__ __forceinline__ void report_step2_failure(const Params& P, int d, int
 // ------------------------------------------------------------------------------------------------ k2_stage
 // `step` numbers the launches of the chain (list 0 of step 0 is filled by k_sync); list `step & 1` is read, the other written.
 template <int F>
-__global__ void __launch_bounds__(128, F == 0 ? 6 : RK_MIN_BLOCKS) k2_stage(const Params P, int step, int second_dir) {
+__global__ void __launch_bounds__(128, F == 0 ? RK_S0_MINB : RK_MIN_BLOCKS) k2_stage(const Params P, int step, int second_dir) {
     RK_PDL_ENTER();
     const int64_t wstride = (int64_t)P.dof * P.cn;
     const uint32_t* list_in = P.list[step & 1];
@@ -1539,7 +1552,7 @@ __global__ void __launch_bounds__(128, RK_PO_MINB) k2_polish(const Params P, int
     }
 }
 
-__global__ void __launch_bounds__(128, 6) k2_vel_check_uddu(const Params P, int step, int second_dir) {
+__global__ void __launch_bounds__(128, RK_VC_MINB) k2_vel_check_uddu(const Params P, int step, int second_dir) {
     RK_PDL_ENTER();
     const int64_t wstride = (int64_t)P.dof * P.cn;
     uint32_t* list_out = P.list[(step + 1) & 1];
