@@ -1549,6 +1549,10 @@ __global__ void __launch_bounds__(128, RK_PO_MINB) k2_polish(const Params P, int
             *out = st.rts;
             have = false;
         }
+        if (have && st.step()) {  // a second iteration per trip: the refill test (two ballots, a count) is a tenth of a trip
+            *out = st.rts;
+            have = false;
+        }
     }
 }
 
