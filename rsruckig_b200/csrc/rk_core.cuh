@@ -10,7 +10,21 @@
 //
 // Arithmetic follows the reference's association order and is compiled with
 // --fmad=false: decisions such as `< f64::EPSILON` depend on the last bits.
-#pragma once
+// Included once per pass: rk_kernels.cu compiles these headers twice — into namespace rk (exact divisions with their fall-back
+// branch) and, with RK_PASS2 defined and `rk` renamed, into namespace rk_lazy (rk_math.cuh, RK_LAZY_DDIV).
+#ifndef RK_PASS2
+#ifndef RK_H_CORE_1
+#define RK_H_CORE_1
+#define RK_H_CORE_GO
+#endif
+#else
+#ifndef RK_H_CORE_2
+#define RK_H_CORE_2
+#define RK_H_CORE_GO
+#endif
+#endif
+#ifdef RK_H_CORE_GO
+#undef RK_H_CORE_GO
 #include <cfloat>
 #include <cstdint>
 
@@ -714,3 +728,4 @@ struct ShrinkState {
 };
 
 }  // namespace rk
+#endif  // RK_H_CORE_GO

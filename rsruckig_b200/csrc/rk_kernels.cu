@@ -23,7 +23,20 @@
 #include <vector>
 
 #include "../../include/ruckig_b200.h"
+#include "rk_pipeline.cuh"  // pass 1: namespace rk — every division exact on the spot (fast path + fall-back branch)
+
+// Pass 2: the same headers into namespace rk_lazy, where a division by a `Den` raises a per-thread flag instead of branching
+// to its fall-back (rk_math.cuh). The hot kernels are launched from rk_lazy and redo a flagged work item through the
+// `*_exact` entry points of pass 1; everything else runs from namespace rk.
+namespace rk_exact = rk;
+#define RK_PASS2
+#undef RK_LAZY_DDIV
+#define RK_LAZY_DDIV 1
+#define rk rk_lazy
 #include "rk_pipeline.cuh"
+#undef rk
+#undef RK_LAZY_DDIV
+#define RK_LAZY_DDIV 0
 
 
 namespace rk {
@@ -750,7 +763,8 @@ static rk_status ensure_scratch(rk_handle* h, int set, int64_t items) {
     RK_CUDA(cudaMalloc(&c.list[0], sizeof(uint32_t) * items));
     RK_CUDA(cudaMalloc(&c.list[1], sizeof(uint32_t) * items));
     RK_CUDA(cudaMalloc(&c.pend, sizeof(uint32_t) * items));
-    RK_CUDA(cudaMalloc(&c.counters, sizeof(uint32_t) * RK_N_COUNTERS));
+    RK_CUDA(cudaMalloc(&c.counters, 512 + sizeof(rk::Params)));  // [0, 448): the work-list counters; [512, ...): the chunk's parameter block (Params::self)
+    static_assert(sizeof(uint32_t) * RK_N_COUNTERS <= 512, "counters overlap the parameter block");
     c.ws_items = items;
     return RK_OK;
 }
@@ -817,6 +831,10 @@ static rk_status fill_params(rk::Params& P, const rk_batch_desc* desc, const rk_
     if (desc->limits_layout != RK_LIMITS_PER_TRAJECTORY && desc->limits_layout != RK_LIMITS_PER_DOF)
         return fail(RK_ERR_INVALID_ARGUMENT, "limits_layout is neither RK_LIMITS_PER_TRAJECTORY nor RK_LIMITS_PER_DOF");
     P.lim_per_dof = desc->limits_layout == RK_LIMITS_PER_DOF;
+    {   // test hook: the lazy kernels send every fourth work item through their exact redo path (tests/test_parity.py)
+        static const int forced = [] { const char* e = std::getenv("RK_B200_FORCE_REDO"); return (e && e[0] == '1') ? 1 : 0; }();
+        P.force_redo = forced;
+    }
     return RK_OK;
 }
 
@@ -1125,6 +1143,9 @@ static rk_status calculate_impl(rk_handle* h, const rk_batch_desc* desc, const r
             RK_CUDA(cudaMemsetAsync(c.pend, 0xFF, sizeof(uint32_t) * it, cs));
         }
         RK_CUDA(cudaMemsetAsync(c.counters, 0, sizeof(uint32_t) * RK_N_COUNTERS, cs));
+        static_assert(sizeof(rk_lazy::Params) == sizeof(rk::Params), "the two passes share one parameter block");
+        P.self = reinterpret_cast<const char*>(c.counters) + 512;  // the set-up kernel deposits the parameter block there (exact redo paths)
+        const rk_lazy::Params& LP = reinterpret_cast<const rk_lazy::Params&>(P);  // kernels of pass 2 (see the top of this file)
         if (setup_lean) rk_launch(rk::k1_setup_lean, grid_items, 128, cs, P);
         else rk_launch(rk::k1_setup, grid_items, 128, cs, P);
         const unsigned grid_fam = (unsigned)((2 * items + 127) / 128);
@@ -1138,7 +1159,7 @@ static rk_status calculate_impl(rk_handle* h, const rk_batch_desc* desc, const r
         rk_launch(rk::k1_closed_cands<0>, grid_fam, 128, cs, P);
         rk_launch(rk::k1_closed_cands<1>, grid_fam, 128, cs, P);
 #else
-        rk_launch(rk::k1_closed_cands<2>, grid_fam, 128, cs, P);
+        rk_launch(rk_lazy::k1_closed_cands<2>, grid_fam, 128, cs, LP);
 #endif
         rk_launch(rk::k1_cand_check, grid_list, 128, cs, P);
         rk_launch(rk::k1_block, grid_items, 128, cs, P);
@@ -1151,7 +1172,7 @@ static rk_status calculate_impl(rk_handle* h, const rk_batch_desc* desc, const r
         const int n_steps = RK_FUSE_TAIL ? 10 : RK_S2_STEPS;
         for (int step = 0; step < n_steps; ++step) {
             switch (fam[step]) {
-                case 0: rk_launch(rk::k2_stage<0>, grid_list, 128, cs, P, step, dir2[step]); break;
+                case 0: rk_launch(rk_lazy::k2_stage<0>, grid_list, 128, cs, LP, step, dir2[step]); break;
                 case 1:
                     rk_launch(rk::k2_vel_scan_uddu, grid_vel, RK_LS_BLOCK, cs, P, step, dir2[step]);
                     rk_launch(rk::k2_polish<6, false>, (unsigned)h->sm_count * 8u, 128, cs, P, 33 + 4 * step, 34 + 4 * step);
@@ -1159,7 +1180,7 @@ static rk_status calculate_impl(rk_handle* h, const rk_batch_desc* desc, const r
                     h->launches += 2;
                     break;
                 case 2: rk_launch(rk::k2_stage<2>, grid_list, 128, cs, P, step, dir2[step]); break;
-                case 3: rk_launch(rk::k2_stage<3>, grid_list, 128, cs, P, step, dir2[step]); break;
+                case 3: rk_launch(rk_lazy::k2_stage<3>, grid_list, 128, cs, LP, step, dir2[step]); break;
                 case 4: rk_launch(rk::k2_stage<4>, grid_list, 128, cs, P, step, dir2[step]); break;
                 case 5: rk_launch(rk::k2_stage<5>, grid_list, 128, cs, P, step, dir2[step]); break;
                 case 6: rk_launch(rk::k2_stage<6>, grid_list, 128, cs, P, step, dir2[step]); break;

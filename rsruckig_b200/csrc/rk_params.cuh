@@ -1,6 +1,20 @@
 // rk_params.cuh — kernel parameter block, per-DoF input loading, input validation and the scratch (workspace) accessors
 // shared by all kernels of the pipeline.
-#pragma once
+// Included once per pass: rk_kernels.cu compiles these headers twice — into namespace rk (exact divisions with their fall-back
+// branch) and, with RK_PASS2 defined and `rk` renamed, into namespace rk_lazy (rk_math.cuh, RK_LAZY_DDIV).
+#ifndef RK_PASS2
+#ifndef RK_H_PARAMS_1
+#define RK_H_PARAMS_1
+#define RK_H_PARAMS_GO
+#endif
+#else
+#ifndef RK_H_PARAMS_2
+#define RK_H_PARAMS_2
+#define RK_H_PARAMS_GO
+#endif
+#endif
+#ifdef RK_H_PARAMS_GO
+#undef RK_H_PARAMS_GO
 #include <cuda_runtime.h>
 
 #include "../../include/ruckig_b200.h"
@@ -23,6 +37,8 @@ struct Params {
     int32_t check_current, check_target;
     int32_t compact;  // trajectory storage layout: 0 = full Profile (59 slots), 1 = compact record (COMPACT_SLOTS, rk_store.cuh)
     int32_t lim_per_dof;  // the five limit arrays are [dof] (RK_LIMITS_PER_DOF) instead of [dof][n]
+    const void* self;     // this parameter block in global memory (written by the set-up kernel): what the out-of-line exact redo paths of the lazy kernels work from — a kernel parameter passed on by reference would be copied to local memory by every thread
+    int32_t force_redo;   // test hook (RK_B200_FORCE_REDO=1): the lazy kernels redo a quarter of their work items through the exact path
     double delta_time;
     int8_t ci[RK_MAX_DOF];
     int8_t sync[RK_MAX_DOF];
@@ -185,3 +201,4 @@ __device__ __forceinline__ void ws_get_cand(const Params& P, int64_t wi, int64_t
 
 
 }  // namespace rk
+#endif  // RK_H_PARAMS_GO

@@ -20,7 +20,21 @@
 //   k_expand            every item: compact result -> the full profile arrays, coalesced rows
 //
 // Lists are compacted with warp-aggregated atomics; ordering inside a list does not matter (items are independent).
-#pragma once
+// Included once per pass: rk_kernels.cu compiles these headers twice — into namespace rk (exact divisions with their fall-back
+// branch) and, with RK_PASS2 defined and `rk` renamed, into namespace rk_lazy (rk_math.cuh, RK_LAZY_DDIV).
+#ifndef RK_PASS2
+#ifndef RK_H_PIPELINE_1
+#define RK_H_PIPELINE_1
+#define RK_H_PIPELINE_GO
+#endif
+#else
+#ifndef RK_H_PIPELINE_2
+#define RK_H_PIPELINE_2
+#define RK_H_PIPELINE_GO
+#endif
+#endif
+#ifdef RK_H_PIPELINE_GO
+#undef RK_H_PIPELINE_GO
 #include "rk_params.cuh"
 #include "rk_step_misc.cuh"
 #include "rk_step2.cuh"
@@ -97,6 +111,26 @@ __device__ __forceinline__ void append_unsolved(uint32_t* list, uint32_t* counte
     base = __shfl_sync(0xffffffffu, base, leader);
     if (unsolved) list[base + __popc(mask & ((1u << lane) - 1u))] = item;
 }
+
+// Lazy kernels (pass 2 of rk_kernels.cu, namespace rk_lazy): a division whose operands leave the fast path's domain raises the
+// thread's flag instead of branching to the exact division (rk_math.cuh); the kernel clears the flag before a work item,
+// looks at it afterwards and, if it is up, recomputes the item through the `*_exact` entry point of namespace rk — the same
+// unit function compiled in pass 1, out of line. The flag is never up on ordinary data (tiny / huge intermediate values), so
+// the test hook P.force_redo sends every fourth item through the exact path to keep that path under the parity tests.
+// Launched from rk_lazy: k1_closed_cands (-10.6 % kernel time), k2_stage<0> (-4 %), k2_stage<3> (-12 %): +1.2 % on the whole step.
+// The quartic kernels, the check kernels and the VEL check were built the same way and measured slower (+3 .. +10 %): they hold
+// few `Den` divisions, and the out-of-line exact copy in the kernel costs their tight register budgets more than the branches did.
+// With no redo behind it at all (a timing experiment) the lazy form of EVERY kernel is worth +5.1 %.
+#undef RK_LAZY_BEGIN
+#if RK_LAZY_DDIV
+#define RK_LAZY_BEGIN() (rk_flag() = 0)
+__device__ __forceinline__ bool redo_wanted(const Params& P, uint32_t key) {
+    return (rk_flag() != 0) | ((P.force_redo != 0) & (((key * 2654435761u) >> 30) == 0u));
+}
+#define RK_EXACT_PARAMS(P) (*static_cast<const rk_exact::Params*>((P).self))
+#else
+#define RK_LAZY_BEGIN() ((void)0)
+#endif
 
 // The five bits of a pending third-order item that k1_block decides on (instead of re-reading the item's record there)
 __device__ __forceinline__ uint32_t block_bits(double ps, double vs, double as, const DofIn& x) {
@@ -206,8 +240,13 @@ __device__ __forceinline__ void setup_item(const Params& P, int64_t wi, int64_t 
     out.put(S_PF, pf_store); out.put(S_VF, vf_store); out.put(S_AF, af_store);
 }
 
+__device__ __forceinline__ void deposit_params(const Params& P) {
+    if (P.self && blockIdx.x == 0 && threadIdx.x == 0) *static_cast<Params*>(const_cast<void*>(P.self)) = P;
+}
+
 __global__ void __launch_bounds__(128, RK_SU_MINB) k1_setup(const Params P) {
     RK_PDL_ENTER();
+    deposit_params(P);
     const int64_t wstride = (int64_t)P.dof * P.cn;
     const int64_t wi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (wi >= wstride) return;
@@ -222,6 +261,7 @@ __global__ void __launch_bounds__(128, RK_SU_MINB) k1_setup(const Params P) {
 // the queue before k_sync needs its block.
 __global__ void __launch_bounds__(128, 8) k1_setup_lean(const Params P) {
     RK_PDL_ENTER();
+    deposit_params(P);
     const int64_t wstride = (int64_t)P.dof * P.cn;
     const int64_t wi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool other = false;
@@ -315,6 +355,43 @@ __device__ __forceinline__ Lim family_limits(const DofIn& x, const Bound& b, int
 #ifndef RK_CC_SPLIT
 #define RK_CC_SPLIT 0  // 1: ACC0_ACC1 and VEL in two launches (PART 0 / 1) instead of one (PART 2)
 #endif
+// the work of one (direction slot, item): candidates parked in their slots, bit v of parked3 / parked4 = variant v is to be checked
+template <int PART>
+__device__ __forceinline__ void closed_cands_unit(const Params& P, int64_t wstride, int64_t wi, int ds, uint32_t& parked3, uint32_t& parked4) {
+    parked3 = 0; parked4 = 0;
+    const uint32_t meta = P.wmeta[(int64_t)WM_META * wstride + wi];
+    Bound b;
+    double bdur_;
+    const DofIn x = load_rec(P, wi, b, bdur_);  // before the test of meta: two independent loads instead of a dependent pair
+    if (meta & M_S1_PENDING) {
+        bool rest_target, trivial;
+        const Lim L = family_limits(x, b, ds, rest_target, trivial);
+        if (PART != 1) P.wqmask[(int64_t)(6 + ds) * wstride + wi] = 0u;
+        if (PART != 0) P.wqmask[(int64_t)(8 + ds) * wstride + wi] = 0u;
+        if (!trivial) {  // :1015-1025 — nothing moves: only the quartics of the first direction are tried
+            Step1Pos3<CandSink> s;
+            s.init(b, x.j_max);
+            s.first_only = false;
+            if (PART != 1) {
+                s.sink.parked = 0;
+                s.sink.base = vl_slot(P, wi, sub_slot_base(6 + ds));
+                s.family_acc0_acc1(L);
+                parked3 = s.sink.parked;
+            }
+            if (PART != 0) {
+                s.sink.parked = 0;
+                s.sink.base = vl_slot(P, wi, sub_slot_base(8 + ds));
+                s.family_vel(L);
+                parked4 = s.sink.parked;
+            }
+        }
+    }
+}
+template <int PART>
+__device__ __noinline__ void closed_cands_exact(const Params& P, int64_t wstride, int64_t wi, int ds, uint32_t& parked3, uint32_t& parked4) {
+    closed_cands_unit<PART>(P, wstride, wi, ds, parked3, parked4);
+}
+
 template <int PART>
 __global__ void __launch_bounds__(128, RK_CC_MINB) k1_closed_cands(const Params P) {
     RK_PDL_ENTER();
@@ -326,33 +403,11 @@ __global__ void __launch_bounds__(128, RK_CC_MINB) k1_closed_cands(const Params 
     if (tid < 2 * wstride) {
         ds = (int)(tid & 1);  // the two directions of an item sit in adjacent lanes: its 96-byte record is fetched once
         wi = tid >> 1;
-        const uint32_t meta = P.wmeta[(int64_t)WM_META * wstride + wi];
-        Bound b;
-        double bdur_;
-        const DofIn x = load_rec(P, wi, b, bdur_);  // before the test of meta: two independent loads instead of a dependent pair
-        if (meta & M_S1_PENDING) {
-            bool rest_target, trivial;
-            const Lim L = family_limits(x, b, ds, rest_target, trivial);
-            if (PART != 1) P.wqmask[(int64_t)(6 + ds) * wstride + wi] = 0u;
-            if (PART != 0) P.wqmask[(int64_t)(8 + ds) * wstride + wi] = 0u;
-            if (!trivial) {  // :1015-1025 — nothing moves: only the quartics of the first direction are tried
-                Step1Pos3<CandSink> s;
-                s.init(b, x.j_max);
-                s.first_only = false;
-                if (PART != 1) {
-                    s.sink.parked = 0;
-                    s.sink.base = vl_slot(P, wi, sub_slot_base(6 + ds));
-                    s.family_acc0_acc1(L);
-                    parked3 = s.sink.parked;
-                }
-                if (PART != 0) {
-                    s.sink.parked = 0;
-                    s.sink.base = vl_slot(P, wi, sub_slot_base(8 + ds));
-                    s.family_vel(L);
-                    parked4 = s.sink.parked;
-                }
-            }
-        }
+        RK_LAZY_BEGIN();
+        closed_cands_unit<PART>(P, wstride, wi, ds, parked3, parked4);
+#if RK_LAZY_DDIV
+        if (redo_wanted(P, (uint32_t)tid)) rk_exact::closed_cands_exact<PART>(RK_EXACT_PARAMS(P), wstride, wi, ds, parked3, parked4);
+#endif
     }
     const int mine = __popc(parked3) + __popc(parked4);
     uint32_t e = warp_reserve(P.counters + 23, mine);
@@ -364,23 +419,28 @@ __global__ void __launch_bounds__(128, RK_CC_MINB) k1_closed_cands(const Params 
         if ((parked4 >> v) & 1u) P.rq_item[e++] = make_uint2((uint32_t)wi, (uint32_t)ds | (uint32_t)((8 + ds) << 1) | ((uint32_t)v << 8));
 }
 
+// one queued candidate: the full profile check; byte v of the sub-list's mask word = valid
+__device__ __forceinline__ void cand_check_unit(const Params& P, int64_t wstride, const uint2 it) {
+    const int64_t wi = it.x;
+    const int ds = it.y & 1, sub = (it.y >> 1) & 0x7F, v = it.y >> 8;
+    Bound b;
+    double bdur_;
+    const DofIn x = load_rec(P, wi, b, bdur_);
+    bool rest_target, trivial;
+    const Lim L = family_limits(x, b, ds, rest_target, trivial);
+    const double2* slot = reinterpret_cast<const double2*>(vl_slot(P, wi, sub_slot_base(sub) + v));
+    const double2 s0 = slot[0], s1 = slot[1], s2 = slot[2], s3 = slot[3];
+    const double t[7] = {s0.x, s0.y, s1.x, s1.y, s2.x, s2.y, s3.x};
+    if (check_pos3_inline(t, UDDU, sub_limits(sub), L.j_max, L, b)) reinterpret_cast<uint8_t*>(P.wqmask + (int64_t)sub * wstride + wi)[v] = 1;
+}
+
 __global__ void __launch_bounds__(128, RK_CK_MINB) k1_cand_check(const Params P) {
     RK_PDL_ENTER();
     const int64_t wstride = (int64_t)P.dof * P.cn;
     const uint32_t count = P.counters[23];
     for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < count; e += gridDim.x * blockDim.x) {
         const uint2 it = P.rq_item[e];
-        const int64_t wi = it.x;
-        const int ds = it.y & 1, sub = (it.y >> 1) & 0x7F, v = it.y >> 8;
-        Bound b;
-        double bdur_;
-        const DofIn x = load_rec(P, wi, b, bdur_);
-        bool rest_target, trivial;
-        const Lim L = family_limits(x, b, ds, rest_target, trivial);
-        const double2* slot = reinterpret_cast<const double2*>(vl_slot(P, wi, sub_slot_base(sub) + v));
-        const double2 s0 = slot[0], s1 = slot[1], s2 = slot[2], s3 = slot[3];
-        const double t[7] = {s0.x, s0.y, s1.x, s1.y, s2.x, s2.y, s3.x};
-        if (check_pos3_inline(t, UDDU, sub_limits(sub), L.j_max, L, b)) reinterpret_cast<uint8_t*>(P.wqmask + (int64_t)sub * wstride + wi)[v] = 1;
+        cand_check_unit(P, wstride, it);
     }
 }
 
@@ -390,6 +450,33 @@ __global__ void __launch_bounds__(128, RK_CK_MINB) k1_cand_check(const Params P)
 // root) does the Newton polish, builds t[7] and validates the profile. A (DoF, direction) has 0-4 in-range roots and most
 // candidates die in the check, so phase B runs the expensive part with full warps instead of the few lanes that happened
 // to have a root in the same loop iteration. Root k of a sub-list writes slot k, which keeps the ascending order.
+// one (direction slot, item): the quartic of family TYPE, its in-range roots in ascending order
+template <int TYPE>
+__device__ __forceinline__ void quartic_roots_unit(const Params& P, int64_t wstride, int64_t wi, int ds, double (&roots)[4], int& n_roots) {
+    n_roots = 0;
+    const uint32_t meta = P.wmeta[(int64_t)WM_META * wstride + wi];
+    Bound b;
+    double bdur_;
+    const DofIn x = load_rec(P, wi, b, bdur_);  // before the test of meta: two independent loads instead of a dependent pair
+    if (meta & M_S1_PENDING) {
+        bool rest_target, trivial;
+        const Lim L = family_limits(x, b, ds, rest_target, trivial);
+        P.wqmask[(int64_t)(TYPE * 2 + ds) * wstride + wi] = 0u;
+        if (!(trivial && ds == 1)) {  // :1015-1025 — nothing moves: only the first direction is tried
+            Step1Pos3<QuarticSink> s;
+            s.init(b, x.j_max);
+            s.sink.n_roots = 0;
+            s.first_only = false;
+            if (TYPE == 0) s.template quartic_none<QUARTIC_ROOTS>(L, 0.0);
+            else if (TYPE == 1) s.template quartic_acc0<QUARTIC_ROOTS>(L, 0.0);
+            else s.template quartic_acc1<QUARTIC_ROOTS>(L, 0.0);
+            n_roots = s.sink.n_roots;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) roots[k] = s.sink.roots[k];
+        }
+    }
+}
+
 #ifndef RK_QR_MINB
 #define RK_QR_MINB 12  // 40 registers, 72 bytes of spills: the kernels are bound by issue slots under fp64 dependency stalls, and 48 warps per SM beat 32 (+0.8 % on the step)
 #endif
@@ -405,27 +492,7 @@ __global__ void __launch_bounds__(128, RK_QR_MINB) k1_quartic_roots(const Params
     if (tid < 2 * wstride) {
         ds = (int)(tid & 1);  // the two directions of an item sit in adjacent lanes: its 96-byte record is fetched once
         wi = tid >> 1;
-        const uint32_t meta = P.wmeta[(int64_t)WM_META * wstride + wi];
-        Bound b;
-        double bdur_;
-        const DofIn x = load_rec(P, wi, b, bdur_);  // before the test of meta: two independent loads instead of a dependent pair
-        if (meta & M_S1_PENDING) {
-            bool rest_target, trivial;
-            const Lim L = family_limits(x, b, ds, rest_target, trivial);
-            P.wqmask[(int64_t)(TYPE * 2 + ds) * wstride + wi] = 0u;
-            if (!(trivial && ds == 1)) {  // :1015-1025 — nothing moves: only the first direction is tried
-                Step1Pos3<QuarticSink> s;
-                s.init(b, x.j_max);
-                s.sink.n_roots = 0;
-                s.first_only = false;
-                if (TYPE == 0) s.template quartic_none<QUARTIC_ROOTS>(L, 0.0);
-                else if (TYPE == 1) s.template quartic_acc0<QUARTIC_ROOTS>(L, 0.0);
-                else s.template quartic_acc1<QUARTIC_ROOTS>(L, 0.0);
-                n_roots = s.sink.n_roots;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) roots[k] = s.sink.roots[k];
-            }
-        }
+        quartic_roots_unit<TYPE>(P, wstride, wi, ds, roots, n_roots);
     }
     // warp-aggregated append of a variable number of entries per lane
     const int lane = threadIdx.x & 31;
@@ -449,6 +516,27 @@ __global__ void __launch_bounds__(128, RK_QR_MINB) k1_quartic_roots(const Params
     }
 }
 
+// one queued root: Newton polish, t[7], profile check; a valid candidate goes into the slot the root owns
+template <int TYPE>
+__device__ __forceinline__ void quartic_check_unit(const Params& P, int64_t wstride, const uint2 it, double root) {
+    const int64_t wi = it.x;
+    const int ds = it.y & 1, rank = it.y >> 1;
+    Bound b;
+    double bdur_;
+    const DofIn x = load_rec(P, wi, b, bdur_);
+    bool rest_target, trivial;
+    const Lim L = family_limits(x, b, ds, rest_target, trivial);
+    const int sub = TYPE * 2 + ds;
+    Step1Pos3<QuarticSink> s;
+    s.init(b, x.j_max);
+    s.first_only = false;
+    s.sink.slot = vl_slot(P, wi, sub_slot_base(sub) + rank);
+    if (TYPE == 0) s.template quartic_none<QUARTIC_CANDIDATE>(L, root);
+    else if (TYPE == 1) s.template quartic_acc0<QUARTIC_CANDIDATE>(L, root);
+    else s.template quartic_acc1<QUARTIC_CANDIDATE>(L, root);
+    if (s.sink.count > 0) reinterpret_cast<uint8_t*>(P.wqmask + (int64_t)sub * wstride + wi)[rank] = 1;
+}
+
 template <int TYPE>
 __global__ void __launch_bounds__(128, RK_QC_MINB(TYPE)) k1_quartic_check(const Params P) {
     RK_PDL_ENTER();
@@ -457,22 +545,7 @@ __global__ void __launch_bounds__(128, RK_QC_MINB(TYPE)) k1_quartic_check(const 
     for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < count; e += gridDim.x * blockDim.x) {
         const uint2 it = P.rq_item[e];
         const double root = P.rq_root[e];
-        const int64_t wi = it.x;
-        const int ds = it.y & 1, rank = it.y >> 1;
-        Bound b;
-        double bdur_;
-        const DofIn x = load_rec(P, wi, b, bdur_);
-        bool rest_target, trivial;
-        const Lim L = family_limits(x, b, ds, rest_target, trivial);
-        const int sub = TYPE * 2 + ds;
-        Step1Pos3<QuarticSink> s;
-        s.init(b, x.j_max);
-        s.first_only = false;
-        s.sink.slot = vl_slot(P, wi, sub_slot_base(sub) + rank);
-        if (TYPE == 0) s.template quartic_none<QUARTIC_CANDIDATE>(L, root);
-        else if (TYPE == 1) s.template quartic_acc0<QUARTIC_CANDIDATE>(L, root);
-        else s.template quartic_acc1<QUARTIC_CANDIDATE>(L, root);
-        if (s.sink.count > 0) reinterpret_cast<uint8_t*>(P.wqmask + (int64_t)sub * wstride + wi)[rank] = 1;
+        quartic_check_unit<TYPE>(P, wstride, it, root);
     }
 }
 
@@ -1341,6 +1414,17 @@ __device__ __forceinline__ void report_step2_failure(const Params& P, int d, int
     }
 }
 
+// one item of a chain stage: true = solved (its compact solution and code word are stored)
+template <int F>
+__device__ __forceinline__ bool stage_unit(const Params& P, uint32_t wi, int64_t wstride, bool second_direction) {
+    const ItemS2 it = load_item_s2(P, wi, wstride);
+    return run_stage<F>(P, it, second_direction);
+}
+template <int F>
+__device__ __noinline__ bool stage_exact(const Params& P, uint32_t wi, int64_t wstride, bool second_direction) {
+    return stage_unit<F>(P, wi, wstride, second_direction);
+}
+
 // ------------------------------------------------------------------------------------------------ k2_stage
 // `step` numbers the launches of the chain (list 0 of step 0 is filled by k_sync); list `step & 1` is read, the other written.
 template <int F>
@@ -1360,8 +1444,11 @@ __global__ void __launch_bounds__(128, F == 0 ? RK_S0_MINB : RK_MIN_BLOCKS) k2_s
         uint32_t wi = 0;
         if (k < count) {
             wi = list_in[k];
-            const ItemS2 it = load_item_s2(P, wi, wstride);
-            unsolved = !run_stage<F>(P, it, second_direction);
+            RK_LAZY_BEGIN();
+            unsolved = !stage_unit<F>(P, wi, wstride, second_direction);
+#if RK_LAZY_DDIV
+            if (redo_wanted(P, k)) unsolved = !rk_exact::stage_exact<F>(RK_EXACT_PARAMS(P), wi, wstride, second_direction);
+#endif
         }
         append_unsolved(list_out, P.counters + step + 1, unsolved, wi);
     }
@@ -1556,6 +1643,22 @@ __global__ void __launch_bounds__(128, RK_PO_MINB) k2_polish(const Params P, int
     }
 }
 
+// one pending item of the UDDU half: its polished candidates in order, the first valid one is stored; true = solved
+__device__ __forceinline__ bool vel_check_unit(const Params& P, uint32_t wi, int64_t wstride, bool second_direction) {
+    const ItemS2 it = load_item_s2(P, wi, wstride);
+    S2 s;
+    s.init(it.b, it.tf, it.x.j_max);
+    const bool up_first = s.pd > it.tf * it.b.v0;
+    const Lim L = lim_dir(up_first != second_direction, it.x.v_max, it.x.v_min, it.x.a_max, it.x.a_min, it.x.j_max);
+    const int n_cand = (int)P.wqmask[wi];
+    Hit h;
+    bool found = false;
+#pragma unroll 1
+    for (int c = 0; c < n_cand && !found; ++c) found = vel_uddu_root(s, L, h, *vslot(P, wi, wstride, V_ROOT + c));
+    if (found) put_solution(P, it, wstride, h);
+    return found;
+}
+
 __global__ void __launch_bounds__(128, RK_VC_MINB) k2_vel_check_uddu(const Params P, int step, int second_dir) {
     RK_PDL_ENTER();
     const int64_t wstride = (int64_t)P.dof * P.cn;
@@ -1570,18 +1673,7 @@ __global__ void __launch_bounds__(128, RK_VC_MINB) k2_vel_check_uddu(const Param
         uint32_t wi = 0;
         if (k < count) {
             wi = P.pend[k];
-            const ItemS2 it = load_item_s2(P, wi, wstride);
-            S2 s;
-            s.init(it.b, it.tf, it.x.j_max);
-            const bool up_first = s.pd > it.tf * it.b.v0;
-            const Lim L = lim_dir(up_first != second_direction, it.x.v_max, it.x.v_min, it.x.a_max, it.x.a_min, it.x.j_max);
-            const int n_cand = (int)P.wqmask[wi];
-            Hit h;
-            bool found = false;
-#pragma unroll 1
-            for (int c = 0; c < n_cand && !found; ++c) found = vel_uddu_root(s, L, h, *vslot(P, wi, wstride, V_ROOT + c));
-            if (found) put_solution(P, it, wstride, h);
-            unsolved = !found;
+            unsolved = !vel_check_unit(P, wi, wstride, second_direction);
         }
         append_unsolved(list_out, P.counters + step + 1, unsolved, wi);
     }
@@ -1840,3 +1932,4 @@ __global__ void __launch_bounds__(128, 8) k_expand_compact(const Params P) {
 }
 
 }  // namespace rk
+#endif  // RK_H_PIPELINE_GO

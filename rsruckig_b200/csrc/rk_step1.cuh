@@ -12,7 +12,21 @@
 // order and stops at the first hit; each family is a pure function of the
 // inputs, so here those threads run the common schedule and pick the winner by
 // the reference's priority afterwards. Candidates are kept as t[7] + codes.
-#pragma once
+// Included once per pass: rk_kernels.cu compiles these headers twice — into namespace rk (exact divisions with their fall-back
+// branch) and, with RK_PASS2 defined and `rk` renamed, into namespace rk_lazy (rk_math.cuh, RK_LAZY_DDIV).
+#ifndef RK_PASS2
+#ifndef RK_H_STEP1_1
+#define RK_H_STEP1_1
+#define RK_H_STEP1_GO
+#endif
+#else
+#ifndef RK_H_STEP1_2
+#define RK_H_STEP1_2
+#define RK_H_STEP1_GO
+#endif
+#endif
+#ifdef RK_H_STEP1_GO
+#undef RK_H_STEP1_GO
 #include "rk_core.cuh"
 
 namespace rk {
@@ -657,3 +671,4 @@ __device__ __noinline__ bool step1_pos3_zero_limits(const Bound& b, real v_max, 
 }
 
 }  // namespace rk
+#endif  // RK_H_STEP1_GO

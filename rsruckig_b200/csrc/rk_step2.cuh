@@ -7,7 +7,21 @@
 // order as the reference inside a family. The chain over the 16 (family,
 // direction) stages (position_third_step2.rs:2449-2482) lives in the kernel
 // file, where stages are executed warp-uniformly over compacted work lists.
-#pragma once
+// Included once per pass: rk_kernels.cu compiles these headers twice — into namespace rk (exact divisions with their fall-back
+// branch) and, with RK_PASS2 defined and `rk` renamed, into namespace rk_lazy (rk_math.cuh, RK_LAZY_DDIV).
+#ifndef RK_PASS2
+#ifndef RK_H_STEP2_1
+#define RK_H_STEP2_1
+#define RK_H_STEP2_GO
+#endif
+#else
+#ifndef RK_H_STEP2_2
+#define RK_H_STEP2_2
+#define RK_H_STEP2_GO
+#endif
+#endif
+#ifdef RK_H_STEP2_GO
+#undef RK_H_STEP2_GO
 #include "rk_core.cuh"
 
 namespace rk {
@@ -280,3 +294,4 @@ __device__ RK_S2_FN bool s2_acc0_vel(const S2& s, const Lim& L, Hit& h) {
 }
 
 }  // namespace rk
+#endif  // RK_H_STEP2_GO

@@ -1,7 +1,21 @@
 // rk_step2_acc.cuh — Step 2 families that do not reach the velocity limit and
 // are closed form (no polynomial solve): ACC0_ACC1, ACC1, ACC0
 // (position_third_step2.rs:976-1437). Some of them use a reduced jerk jf.
-#pragma once
+// Included once per pass: rk_kernels.cu compiles these headers twice — into namespace rk (exact divisions with their fall-back
+// branch) and, with RK_PASS2 defined and `rk` renamed, into namespace rk_lazy (rk_math.cuh, RK_LAZY_DDIV).
+#ifndef RK_PASS2
+#ifndef RK_H_STEP2_ACC_1
+#define RK_H_STEP2_ACC_1
+#define RK_H_STEP2_ACC_GO
+#endif
+#else
+#ifndef RK_H_STEP2_ACC_2
+#define RK_H_STEP2_ACC_2
+#define RK_H_STEP2_ACC_GO
+#endif
+#endif
+#ifdef RK_H_STEP2_ACC_GO
+#undef RK_H_STEP2_ACC_GO
 #include "rk_step2.cuh"
 
 namespace rk {
@@ -194,3 +208,4 @@ __device__ RK_S2_FN bool s2_acc0(const S2& s, const Lim& L, Hit& h) {
 }
 
 }  // namespace rk
+#endif  // RK_H_STEP2_ACC_GO

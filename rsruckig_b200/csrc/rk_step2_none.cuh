@@ -2,7 +2,21 @@
 // no limit is reached. The tail of the Step-2 chain: four quartics, two cubics
 // and several closed-form three-step profiles, tried in the reference's order.
 // Rare on random inputs (< 0.1 % of Step-2 results) but the heaviest family.
-#pragma once
+// Included once per pass: rk_kernels.cu compiles these headers twice — into namespace rk (exact divisions with their fall-back
+// branch) and, with RK_PASS2 defined and `rk` renamed, into namespace rk_lazy (rk_math.cuh, RK_LAZY_DDIV).
+#ifndef RK_PASS2
+#ifndef RK_H_STEP2_NONE_1
+#define RK_H_STEP2_NONE_1
+#define RK_H_STEP2_NONE_GO
+#endif
+#else
+#ifndef RK_H_STEP2_NONE_2
+#define RK_H_STEP2_NONE_2
+#define RK_H_STEP2_NONE_GO
+#endif
+#endif
+#ifdef RK_H_STEP2_NONE_GO
+#undef RK_H_STEP2_NONE_GO
 #include "rk_step2_acc.cuh"
 
 namespace rk {
@@ -313,3 +327,4 @@ __device__ RK_S2_FN bool s2_none(const S2& s, const Lim& L, Hit& h) {
 }
 
 }  // namespace rk
+#endif  // RK_H_STEP2_NONE_GO

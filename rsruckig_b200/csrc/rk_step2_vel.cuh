@@ -5,7 +5,21 @@
 // are found in closed form from its quartic (second) derivative, each sign
 // change between consecutive extrema is then bracketed and polished by the
 // safeguarded Newton iteration (shrink_interval).
-#pragma once
+// Included once per pass: rk_kernels.cu compiles these headers twice — into namespace rk (exact divisions with their fall-back
+// branch) and, with RK_PASS2 defined and `rk` renamed, into namespace rk_lazy (rk_math.cuh, RK_LAZY_DDIV).
+#ifndef RK_PASS2
+#ifndef RK_H_STEP2_VEL_1
+#define RK_H_STEP2_VEL_1
+#define RK_H_STEP2_VEL_GO
+#endif
+#else
+#ifndef RK_H_STEP2_VEL_2
+#define RK_H_STEP2_VEL_2
+#define RK_H_STEP2_VEL_GO
+#endif
+#endif
+#ifdef RK_H_STEP2_VEL_GO
+#undef RK_H_STEP2_VEL_GO
 #include "rk_step2.cuh"
 
 namespace rk {
@@ -503,3 +517,4 @@ __device__ __forceinline__ bool s2_vel(const S2& s, const Lim& L, Hit& h) {
 }
 
 }  // namespace rk
+#endif  // RK_H_STEP2_VEL_GO

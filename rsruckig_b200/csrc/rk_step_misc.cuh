@@ -4,7 +4,21 @@
 // {1,2}.rs) interfaces (max_jerk = inf), first-order position interface
 // (position_first_step{1,2}.rs; max_acceleration = inf as well).
 // All closed form, one sqrt at most; candidate order is the reference's.
-#pragma once
+// Included once per pass: rk_kernels.cu compiles these headers twice — into namespace rk (exact divisions with their fall-back
+// branch) and, with RK_PASS2 defined and `rk` renamed, into namespace rk_lazy (rk_math.cuh, RK_LAZY_DDIV).
+#ifndef RK_PASS2
+#ifndef RK_H_STEP_MISC_1
+#define RK_H_STEP_MISC_1
+#define RK_H_STEP_MISC_GO
+#endif
+#else
+#ifndef RK_H_STEP_MISC_2
+#define RK_H_STEP_MISC_2
+#define RK_H_STEP_MISC_GO
+#endif
+#endif
+#ifdef RK_H_STEP_MISC_GO
+#undef RK_H_STEP_MISC_GO
 #include "rk_step1.cuh"
 
 namespace rk {
@@ -353,3 +367,4 @@ __device__ __forceinline__ bool step2_pos1(const Bound& b, real tf, Cand& c) {
 }
 
 }  // namespace rk
+#endif  // RK_H_STEP_MISC_GO

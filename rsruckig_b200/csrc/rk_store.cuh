@@ -10,7 +10,21 @@
 //          BRAKE_V 52,53 | BRAKE_P 54,55 | PF,VF,AF 56..58           (59 slots)
 // A warp handles 32 consecutive trajectories of one DoF, so every load and
 // store below is a fully coalesced 256-byte row.
-#pragma once
+// Included once per pass: rk_kernels.cu compiles these headers twice — into namespace rk (exact divisions with their fall-back
+// branch) and, with RK_PASS2 defined and `rk` renamed, into namespace rk_lazy (rk_math.cuh, RK_LAZY_DDIV).
+#ifndef RK_PASS2
+#ifndef RK_H_STORE_1
+#define RK_H_STORE_1
+#define RK_H_STORE_GO
+#endif
+#else
+#ifndef RK_H_STORE_2
+#define RK_H_STORE_2
+#define RK_H_STORE_GO
+#endif
+#endif
+#ifdef RK_H_STORE_GO
+#undef RK_H_STORE_GO
 #include "rk_step1.cuh"
 
 namespace rk {
@@ -201,3 +215,4 @@ __device__ __forceinline__ void expand_compact(const double (&r)[COMPACT_SLOTS],
 }
 
 }  // namespace rk
+#endif  // RK_H_STORE_GO

@@ -386,3 +386,17 @@ def test_limits_per_dof_layout(gpu):
         assert bad.size == 0, f"cycle {cycle}: {bad.size} results differ, first at {bad[:5]}: {ra[bad[:5]]} vs {rb[bad[:5]]}"
         bad = np.argwhere(~((pa == pb) | ((pa != pa) & (pb != pb))))
         assert bad.shape[0] == 0, f"cycle {cycle}: {bad.shape[0]} positions differ, first at {bad[:5].tolist()}"
+
+
+def test_lazy_kernels_exact_redo_path(gpu):
+    """k1_closed_cands and two chain stages run from the lazy instantiation (rk_math.cuh: a `Den` division outside its fast path's
+    domain raises a per-thread flag, the kernel then recomputes the work item through the exact instantiation). Ordinary data
+    never raises the flag, so RK_B200_FORCE_REDO=1 (read when the library first builds a parameter block, hence a process of its
+    own) sends every fourth work item through the redo path: the results must not change by a bit."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, RK_B200_FORCE_REDO="1")
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "quick_parity.py")], cwd=root, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "compared" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]

@@ -25,7 +25,7 @@ with profile(activities=[ProfilerActivity.CUDA]) as prof:
     otg.calculate(f, n=n, memory_space=cabi.RK_MEM_DEVICE)
     otg.sync()
     torch.cuda.synchronize()
-ev = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA and "rk::" in e.name]
+ev = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA and ("rk::" in e.name or "rk_lazy::" in e.name)]
 ev.sort(key=lambda e: e.time_range.start)
 t0 = ev[0].time_range.start
 t1 = max(e.time_range.end for e in ev)
