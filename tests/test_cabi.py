@@ -85,3 +85,13 @@ def test_rust_sys_crate_declares_every_function_of_the_header():
     names = re.findall(r"\b(RK_FIELD_[A-Z0-9_]+)\b", fields)[:-1]
     for value, name in enumerate(names):
         assert re.search(rf"pub const {name}: i32 = {value};", src), name
+
+
+def test_library_carries_both_instantiations_of_the_pipeline():
+    """rk_kernels.cu compiles the device headers twice (namespace rk: exact divisions on the spot; rk_lazy: flag and redo,
+    DESIGN.md 4); the three kernels launched from rk_lazy and their exact counterparts must both be in the library."""
+    from rsruckig_b200 import _cabi
+    data = open(_cabi.LIB_PATH, "rb").read()
+    for sym in (b"_ZN7rk_lazy15k1_closed_candsILi2EEEvNS_6ParamsE", b"_ZN7rk_lazy8k2_stageILi0EEEvNS_6ParamsEii",
+                b"_ZN7rk_lazy8k2_stageILi3EEEvNS_6ParamsEii", b"_ZN2rk8k2_stageILi2EEEvNS_6ParamsEii", b"_ZN2rk16k1_quartic_rootsILi0EEEvNS_6ParamsE"):
+        assert sym in data, sym.decode()
